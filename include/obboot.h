@@ -1,0 +1,166 @@
+/* include/obboot.h -- C ABI of libobboot: the B200-native bootstrap-inference path of
+ * oaxaca_blinder (reference: dot-comma-hyphen/oaxaca-blinder-rs, crate oaxaca_blinder).
+ *
+ * This is the drop-in boundary: what a `build.rs`-linked `extern "C"` block in the reference
+ * crate would bind to replace the body of OaxacaBuilder::run() from the group split to the
+ * assembled results (builder.rs:808-950), and decompose_quantile()'s RIF pre-step
+ * (builder.rs:721-737).  Plain pointers and sizes only; #[repr(C)]-compatible structs; no C++
+ * or torch types.  INTEGRATION.md shows the Rust-side binding.
+ *
+ * Citations are file:line under oaxaca_blinder/src/ of the reference.
+ *
+ * There is NO CPU fallback: every compute entry point needs a CUDA device (sm_100a) and returns
+ * OB_ERR_CUDA / OB_ERR_NO_DEVICE otherwise.
+ */
+#ifndef OBBOOT_H
+#define OBBOOT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OBBOOT_ABI_VERSION 1
+
+/* ---- errors: OaxacaError variants (error.rs:6-19) + device errors ------------------------- */
+typedef enum ob_status {
+    OB_OK = 0,
+    OB_ERR_POLARS = 1,            /* PolarsError: malformed frame / dtype */
+    OB_ERR_COLUMN_NOT_FOUND = 2,  /* ColumnNotFound (builder.rs:776) */
+    OB_ERR_INVALID_GROUP = 3,     /* InvalidGroupVariable: <2 groups (builder.rs:67-71), empty group
+                                     (:431-435), negative weight (ols.rs:60-66), zero total weight (builder.rs:603-607) */
+    OB_ERR_NALGEBRA = 4,          /* NalgebraError: Cholesky failed on the point estimate (ols.rs:107-111) */
+    OB_ERR_DIAGNOSTIC = 5,        /* DiagnosticError (unused on this path) */
+    OB_ERR_INSUFFICIENT_DATA = 6, /* InsufficientData: n_obs <= k (ols.rs:98-105) */
+    OB_ERR_INVALID_ARG = 7,       /* null pointer / out-of-range option (no reference counterpart) */
+    OB_ERR_CUDA = 8,
+    OB_ERR_NCCL = 9,
+    OB_ERR_NO_DEVICE = 10,
+    OB_ERR_UNSUPPORTED = 11       /* shape outside what the kernels are built for (e.g. K+1 > 96) */
+} ob_status;
+
+/* ReferenceCoefficients (decomposition.rs:5-20).  Neumark == Pooled, Cotton == Weighted. */
+typedef enum ob_ref_kind { OB_REF_GROUP_A = 0, OB_REF_GROUP_B = 1, OB_REF_POOLED = 2, OB_REF_WEIGHTED = 3 } ob_ref_kind;
+
+typedef struct ob_ctx ob_ctx;        /* device, streams, workspace; one per calling thread (run(&self) is re-entrant) */
+typedef struct ob_design ob_design;  /* packed design of both groups, resident in HBM */
+
+ob_status ob_device_count(int32_t* n_out);
+ob_status ob_ctx_create(int32_t device, ob_ctx** out);
+void ob_ctx_destroy(ob_ctx* ctx);
+/* message of the last failing call on this context (owned by the context) */
+const char* ob_last_error(const ob_ctx* ctx);
+uint32_t ob_abi_version(void);
+
+/* ---- (1) design-matrix pack --------------------------------------------------------------
+ * The cleaned frame as the reference holds it at builder.rs:808: nulls dropped (:760-784),
+ * categorical levels sorted and coded (:380-418).  Column pointers are HOST memory (pinned or
+ * pageable); the call copies them to the device and packs
+ *   X_g = [__ob_intercept__ | continuous.. | dummies.. | outcome]   row-major, per group
+ * (prepare_data, builder.rs:294-378; column order :325-327; dummy for code c>=1 of categorical
+ * q sits at design column 1 + n_cont + sum_{q'<q}(levels[q']-1) + (c-1), code 0 is the base :402). */
+typedef struct ob_frame_view {
+    int64_t n;                         /* rows */
+    int32_t n_cont;                    /* continuous predictors, user order */
+    const double* const* cont;         /* [n_cont] columns of n doubles */
+    int32_t n_cat;                     /* categorical predictors, user order */
+    const int32_t* const* cat_codes;   /* [n_cat] columns of n codes in [0, cat_levels[q]) */
+    const int32_t* cat_levels;         /* [n_cat] level count m incl. base */
+    const double* outcome;             /* [n] */
+    const double* weights;             /* [n] or NULL (builder.rs:355-370) */
+    const uint8_t* group;              /* [n] 0 = group A, 1 = group B (reference_group), else ignored (builder.rs:73-94) */
+} ob_frame_view;
+
+ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* frame, ob_design** out);
+
+/* Same, from the dense matrices get_data_matrices() returns (builder.rs:252-291): row-major
+ * X_g [n_g x K] incl. the intercept column, y_g, optional w_g.  n_cont fixes the pooled
+ * indicator position (builder.rs:560-564). */
+ob_status ob_design_from_dense(ob_ctx* ctx, int32_t K, int32_t n_cont,
+                               const double* Xa, const double* ya, const double* wa, int64_t na,
+                               const double* Xb, const double* yb, const double* wb, int64_t nb,
+                               ob_design** out);
+void ob_design_destroy(ob_design* d);
+ob_status ob_design_shape(const ob_design* d, int64_t* na, int64_t* nb, int32_t* K, int32_t* n_cont);
+/* get_data_matrices() equivalent: copies the packed design back (row-major [n_g x K]); any pointer may be NULL */
+ob_status ob_design_download(ob_ctx* ctx, const ob_design* d, double* Xa, double* ya, double* wa,
+                             double* Xb, double* yb, double* wb);
+/* decompose_quantile pre-step (builder.rs:721-737 -> math/rif.rs:14-88): replaces each group's
+ * outcome by its RIF at quantile tau, computed on the device, unweighted, per group. */
+ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau);
+
+/* ---- (2)-(5) bootstrap ---------------------------------------------------------------------*/
+typedef struct ob_boot_opts {
+    int32_t ref_kind;                /* ob_ref_kind; builder default is GROUP_A (builder.rs:123) */
+    /* .normalize([...]) entries (normalization.rs:5-51), in user order */
+    int32_t n_norm;
+    const int32_t* norm_m;           /* [n_norm] level count incl. base (category_counts, builder.rs:799) */
+    const int32_t* norm_off;         /* [n_norm+1] offsets into norm_idx */
+    const int32_t* norm_idx;         /* design-column indices matched by the "{var}_" name prefix (normalization.rs:14-20) */
+    const int32_t* norm_has_base;    /* [n_norm] 1 if a base-category row is emitted (builder.rs:636-640) */
+    int64_t reps;                    /* bootstrap_reps; 0 is legal (all SE fields NaN, builder.rs:851-855) */
+    uint64_t seed;                   /* Philox key of the native resampling stream */
+    /* test-only explicit resample index stream (host memory): idx_a [reps x n_a], idx_b [reps x n_b],
+     * row positions within the group in frame order; NULL = native Philox stream */
+    const uint32_t* idx_a;
+    const uint32_t* idx_b;
+    /* replicate shard [rep_begin, rep_end) of the global replicate ids 0..reps-1 computed by this
+     * call; rep_end = 0 means reps.  Streams are keyed by global id, so results do not depend on the sharding. */
+    int64_t rep_begin;
+    int64_t rep_end;
+    int32_t skip_reduce;             /* 1: stop after per-replicate statistics (multi-GPU: gather first, then ob_reduce_stats) */
+    int32_t count_bits;              /* 0 auto, 8 or 16: width of the multiplicity matrix */
+    int64_t max_workspace_bytes;     /* 0 = default (60% of free HBM); bounds the multiplicity-matrix batch */
+} ob_boot_opts;
+
+/* Caller-allocated outputs (host memory).  D = K + n_base rows in each detailed list, where n_base =
+ * number of normalize entries with has_base; S = 5 + 2*D statistics per replicate, ordered
+ *   [explained, unexplained, endowments, coefficients, interaction, detailed_explained[D], detailed_unexplained[D]]
+ * (builder.rs:867-930).  Optional pointers may be NULL. */
+typedef struct ob_result {
+    /* point estimates (builder.rs:810-811, :932-950) */
+    double total_gap;
+    double* point_stats;     /* [S] */
+    double* xa_mean;         /* [K] */
+    double* xb_mean;         /* [K] */
+    double* beta_star;       /* [K] */
+    double* beta_a;          /* [K] optional: group coefficients after Yun */
+    double* beta_b;          /* [K] optional */
+    double* residuals_b;     /* [n_b] optional: OaxacaResults.residuals (builder.rs:946) */
+    /* reduction over successful replicates (inference.rs:4-34, builder.rs:849-865) */
+    int64_t n_ok;
+    double* std_err;         /* [S] */
+    double* p_value;         /* [S] */
+    double* ci_lower;        /* [S] */
+    double* ci_upper;        /* [S] */
+    double* t_stat;          /* [S] */
+    /* per-replicate detail for this call's shard, rows = rep_end - rep_begin (optional) */
+    double* rep_stats;       /* [rows x S], NaN rows for failed replicates */
+    int32_t* rep_status;     /* [rows] ob_status of each replicate (OB_OK / OB_ERR_NALGEBRA / ...) */
+    double* rep_beta_a;      /* [rows x K] */
+    double* rep_beta_b;      /* [rows x K] */
+    /* device timings of the last call, milliseconds (CUDA events) */
+    double ms_counts, ms_gram, ms_solve, ms_reduce, ms_total;
+    int32_t gpu_launches;    /* kernels launched by this call */
+} ob_result;
+
+int32_t ob_num_stats(int32_t K, int32_t n_norm, const int32_t* norm_has_base);
+
+ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* design, const ob_boot_opts* opts, ob_result* res);
+
+/* Reduction alone, on host arrays gathered from several shards, in replicate order
+ * (process_component, builder.rs:849-865): out arrays [S] each. */
+ob_status ob_reduce_stats(ob_ctx* ctx, const double* rep_stats, const int32_t* rep_status, int64_t reps, int32_t S,
+                          const double* point_stats, int64_t* n_ok, double* std_err, double* p_value,
+                          double* ci_lower, double* ci_upper, double* t_stat);
+
+/* Multiplicity counts of one replicate of the native stream (for the statistical validation
+ * tests): counts_out [n] for group g (0 = A, 1 = B) of design d. */
+ob_status ob_debug_counts(ob_ctx* ctx, const ob_design* d, uint64_t seed, int64_t rep, int32_t group,
+                          uint16_t* counts_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBBOOT_H */

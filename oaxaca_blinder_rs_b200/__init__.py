@@ -1,0 +1,11 @@
+"""obboot: B200-native bootstrap inference for the Oaxaca-Blinder decomposition.
+
+Drop-in for the bootstrap hot path of dot-comma-hyphen/oaxaca-blinder-rs (OaxacaBuilder::run /
+decompose_quantile).  The compute path is hand-written sm_100a CUDA behind the C ABI in
+include/obboot.h; this package is the host-side mirror of the reference's interface.
+"""
+from .core import (REF_GROUP_A, REF_GROUP_B, REF_POOLED, REF_WEIGHTED, Context, Design, NormVar,
+                   OaxacaError, bootstrap, num_stats, reduce_stats)
+
+__all__ = ["REF_GROUP_A", "REF_GROUP_B", "REF_POOLED", "REF_WEIGHTED", "Context", "Design", "NormVar",
+           "OaxacaError", "bootstrap", "num_stats", "reduce_stats"]

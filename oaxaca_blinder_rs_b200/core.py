@@ -1,0 +1,216 @@
+"""Numeric layer over the C ABI: Context, Design (packed in HBM), bootstrap().
+
+Mirrors what OaxacaBuilder::run() does after the group split (builder.rs:808-950); the name-level
+builder (strings, dummies, formula) lives in builder.py.  Every number comes from libobboot's CUDA
+kernels -- nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+REF_GROUP_A, REF_GROUP_B, REF_POOLED, REF_WEIGHTED = 0, 1, 2, 3
+
+
+class OaxacaError(RuntimeError):
+    """OaxacaError (error.rs:6-40) + device errors; .kind is the variant name."""
+
+    def __init__(self, code: int, msg: str):
+        self.code = code
+        self.kind = N.STATUS_NAMES.get(code, str(code))
+        super().__init__(msg or self.kind)
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(N._DP)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(N._IP)
+
+
+class Context:
+    """ob_ctx: one per calling thread / GPU."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        st = N.lib().ob_ctx_create(device, C.byref(self._h))
+        if st != 0:
+            raise OaxacaError(st, f"ob_ctx_create(device={device}) failed: {N.STATUS_NAMES.get(st)} "
+                                  f"(a B200 / sm_100a device is required; there is no CPU fallback)")
+        self.device = device
+
+    def check(self, st: int):
+        if st != 0:
+            raise OaxacaError(st, N.lib().ob_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            N.lib().ob_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class NormVar:
+    m: int
+    idx: Sequence[int]
+    has_base: bool = True
+
+
+class Design:
+    """ob_design: both groups' packed design matrices resident in HBM."""
+
+    def __init__(self, ctx: Context, handle: C.c_void_p):
+        self.ctx, self._h = ctx, handle
+        na, nb, K, nc = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+        N.lib().ob_design_shape(self._h, C.byref(na), C.byref(nb), C.byref(K), C.byref(nc))
+        self.n_a, self.n_b, self.K, self.n_cont = na.value, nb.value, K.value, nc.value
+
+    @classmethod
+    def from_dense(cls, ctx: Context, Xa, ya, wa, Xb, yb, wb, n_cont: int) -> "Design":
+        Xa = np.ascontiguousarray(Xa, dtype=np.float64)
+        Xb = np.ascontiguousarray(Xb, dtype=np.float64)
+        K = Xa.shape[1]
+        ya = np.ascontiguousarray(ya, dtype=np.float64)
+        yb = np.ascontiguousarray(yb, dtype=np.float64)
+        wa = None if wa is None else np.ascontiguousarray(wa, dtype=np.float64)
+        wb = None if wb is None else np.ascontiguousarray(wb, dtype=np.float64)
+        h = C.c_void_p()
+        ctx.check(N.lib().ob_design_from_dense(ctx._h, K, n_cont, _dp(Xa), _dp(ya), _dp(wa), Xa.shape[0],
+                                               _dp(Xb), _dp(yb), _dp(wb), Xb.shape[0], C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def pack(cls, ctx: Context, cont: Sequence[np.ndarray], cat_codes: Sequence[np.ndarray],
+             cat_levels: Sequence[int], outcome, weights, group) -> "Design":
+        """ob_design_pack from host columns (the cleaned, coded frame at builder.rs:808)."""
+        outcome = np.ascontiguousarray(outcome, dtype=np.float64)
+        n = outcome.shape[0]
+        cont = [np.ascontiguousarray(c, dtype=np.float64) for c in cont]
+        cats = [np.ascontiguousarray(c, dtype=np.int32) for c in cat_codes]
+        group = np.ascontiguousarray(group, dtype=np.uint8)
+        weights = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        assert all(c.shape == (n,) for c in cont + cats) and group.shape == (n,)
+        fv = N.FrameView()
+        fv.n, fv.n_cont, fv.n_cat = n, len(cont), len(cats)
+        cont_arr = (N._DP * max(len(cont), 1))(*[_dp(c) for c in cont])
+        cat_arr = (N._IP * max(len(cats), 1))(*[_ip(c) for c in cats])
+        lv = np.array(list(cat_levels) + [0], dtype=np.int32)
+        fv.cont, fv.cat_codes, fv.cat_levels = cont_arr, cat_arr, _ip(lv)
+        fv.outcome, fv.weights = _dp(outcome), _dp(weights)
+        fv.group = group.ctypes.data_as(C.POINTER(C.c_uint8))
+        h = C.c_void_p()
+        ctx.check(N.lib().ob_design_pack(ctx._h, C.byref(fv), C.byref(h)))
+        return cls(ctx, h)
+
+    def download(self):
+        """get_data_matrices() equivalent (builder.rs:252-291): (Xa, ya, wa, Xb, yb, wb) row-major."""
+        Xa, Xb = np.empty((self.n_a, self.K)), np.empty((self.n_b, self.K))
+        ya, yb, wa, wb = np.empty(self.n_a), np.empty(self.n_b), np.full(self.n_a, np.nan), np.full(self.n_b, np.nan)
+        self.ctx.check(N.lib().ob_design_download(self.ctx._h, self._h, _dp(Xa), _dp(ya), _dp(wa), _dp(Xb), _dp(yb), _dp(wb)))
+        return Xa, ya, wa, Xb, yb, wb
+
+    def apply_rif(self, tau: float):
+        self.ctx.check(N.lib().ob_design_apply_rif(self.ctx._h, self._h, float(tau)))
+
+    def debug_counts(self, seed: int, rep: int, group: int) -> np.ndarray:
+        n = self.n_a if group == 0 else self.n_b
+        out = np.empty(n, dtype=np.uint16)
+        self.ctx.check(N.lib().ob_debug_counts(self.ctx._h, self._h, seed, rep, group,
+                                               out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return out
+
+    def close(self):
+        if self._h:
+            N.lib().ob_design_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def num_stats(K: int, norm: Sequence[NormVar]) -> int:
+    return 5 + 2 * (K + sum(1 for v in norm if v.has_base))
+
+
+def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequence[NormVar] = (),
+              seed: int = 0, idx_a=None, idx_b=None, rep_begin: int = 0, rep_end: int = 0,
+              skip_reduce: bool = False, count_bits: int = 0, max_workspace_bytes: int = 0,
+              want_rep: bool = False, want_residuals: bool = True) -> dict:
+    """ob_bootstrap_run.  Returns point estimates, per-statistic SE/p/CI/t and (optionally) replicate detail."""
+    ctx, K = design.ctx, design.K
+    norm = list(norm)
+    S = num_stats(K, norm)
+    o = N.BootOpts()
+    o.ref_kind, o.n_norm = ref_kind, len(norm)
+    m = np.array([v.m for v in norm] + [0], dtype=np.int32)
+    off = np.zeros(len(norm) + 1, dtype=np.int32)
+    for i, v in enumerate(norm):
+        off[i + 1] = off[i] + len(v.idx)
+    idx = np.array([j for v in norm for j in v.idx] + [0], dtype=np.int32)
+    hb = np.array([int(v.has_base) for v in norm] + [0], dtype=np.int32)
+    o.norm_m, o.norm_off, o.norm_idx, o.norm_has_base = _ip(m), _ip(off), _ip(idx), _ip(hb)
+    o.reps, o.seed = reps, seed
+    if idx_a is not None:
+        idx_a = np.ascontiguousarray(idx_a, dtype=np.uint32)
+        idx_b = np.ascontiguousarray(idx_b, dtype=np.uint32)
+        assert idx_a.shape == (reps, design.n_a) and idx_b.shape == (reps, design.n_b)
+        o.idx_a, o.idx_b = idx_a.ctypes.data_as(N._U32P), idx_b.ctypes.data_as(N._U32P)
+    o.rep_begin, o.rep_end = rep_begin, rep_end
+    o.skip_reduce, o.count_bits, o.max_workspace_bytes = int(skip_reduce), count_bits, max_workspace_bytes
+    nrep = (rep_end if rep_end > 0 else reps) - rep_begin
+
+    r = N.Result()
+    a = dict(point_stats=np.empty(S), xa_mean=np.empty(K), xb_mean=np.empty(K), beta_star=np.empty(K),
+             beta_a=np.empty(K), beta_b=np.empty(K), std_err=np.full(S, np.nan), p_value=np.full(S, np.nan),
+             ci_lower=np.full(S, np.nan), ci_upper=np.full(S, np.nan), t_stat=np.zeros(S))
+    if want_residuals:
+        a["residuals_b"] = np.empty(design.n_b)
+    if want_rep or skip_reduce:
+        a["rep_stats"] = np.empty((max(nrep, 1), S))
+        a["rep_status"] = np.zeros(max(nrep, 1), dtype=np.int32)
+        a["rep_beta_a"] = np.empty((max(nrep, 1), K))
+        a["rep_beta_b"] = np.empty((max(nrep, 1), K))
+    for k, v in a.items():
+        setattr(r, k, _ip(v) if v.dtype == np.int32 else _dp(v))
+    ctx.check(N.lib().ob_bootstrap_run(ctx._h, design._h, C.byref(o), C.byref(r)))
+    out = dict(a)
+    for k in ("rep_stats", "rep_status", "rep_beta_a", "rep_beta_b"):
+        if k in out:
+            out[k] = out[k][:nrep]
+    out.update(total_gap=r.total_gap, n_ok=int(r.n_ok), S=S,
+               two_fold=a["point_stats"][:2].copy(), three_fold=a["point_stats"][2:5].copy(),
+               timings_ms=dict(counts=r.ms_counts, gram=r.ms_gram, solve=r.ms_solve, reduce=r.ms_reduce, total=r.ms_total),
+               gpu_launches=int(r.gpu_launches))
+    D = (S - 5) // 2
+    out["det_expl"], out["det_unexpl"] = a["point_stats"][5:5 + D].copy(), a["point_stats"][5 + D:].copy()
+    return out
+
+
+def reduce_stats(ctx: Context, rep_stats, rep_status, point_stats) -> dict:
+    """ob_reduce_stats on host arrays gathered from several shards (replicate order)."""
+    rep_stats = np.ascontiguousarray(rep_stats, dtype=np.float64)
+    reps, S = rep_stats.shape
+    rep_status = np.ascontiguousarray(rep_status, dtype=np.int32)
+    point_stats = np.ascontiguousarray(point_stats, dtype=np.float64)
+    out = {k: np.empty(S) for k in ("std_err", "p_value", "ci_lower", "ci_upper", "t_stat")}
+    nok = C.c_int64()
+    ctx.check(N.lib().ob_reduce_stats(ctx._h, _dp(rep_stats), _ip(rep_status), reps, S, _dp(point_stats),
+                                      C.byref(nok), *[_dp(out[k]) for k in
+                                                      ("std_err", "p_value", "ci_lower", "ci_upper", "t_stat")]))
+    out["n_ok"] = int(nok.value)
+    return out

@@ -1,0 +1,572 @@
+// csrc/api.cu -- libobboot C ABI (include/obboot.h): context, packed design, bootstrap driver.
+//
+// Takes over OaxacaBuilder::run() from the group split to the assembled results
+// (builder.rs:808-950).  Host code only orchestrates: every number is produced by the CUDA kernels
+// in this directory; there is no CPU compute path.
+#include "internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+using namespace ob;
+
+struct ob_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+};
+
+struct ob_design {
+    int device = 0;
+    int K = 0, n_cont = 0, V = 0, ldx = 0;
+    bool weighted = false;
+    GroupData g[2];
+};
+
+namespace {
+
+struct DevBuf {  // RAII device allocation
+    void* p = nullptr; size_t bytes = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t b) { alloc(b); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    void alloc(size_t b) {
+        if (p) { cudaFree(p); p = nullptr; }
+        bytes = b;
+        if (b) OB_CUDA(cudaMalloc(&p, b));
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct Timer {
+    cudaEvent_t a, b; cudaStream_t st; double* acc;
+    Timer(cudaStream_t s, double* accum) : st(s), acc(accum) {
+        cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st);
+    }
+    void stop() { cudaEventRecord(b, st); }
+    void collect() { float ms = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b); *acc += ms; }
+    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+
+template <typename F>
+ob_status guarded(ob_ctx* ctx, F&& f) {
+    try {
+        if (ctx) OB_CUDA(cudaSetDevice(ctx->device));
+        f();
+        return OB_OK;
+    } catch (const CudaError& e) {
+        if (ctx) {
+            char buf[512];
+            snprintf(buf, sizeof buf, "CUDA error: %s (%s) at %s:%d", cudaGetErrorString(e.code), e.what, e.file, e.line);
+            ctx->err = buf;
+        }
+        cudaGetLastError();
+        return (e.code == cudaErrorNoDevice || e.code == cudaErrorInsufficientDriver) ? OB_ERR_NO_DEVICE : OB_ERR_CUDA;
+    } catch (const StatusError& e) {
+        if (ctx) ctx->err = e.msg;
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        if (ctx) ctx->err = "host allocation failed";
+        return OB_ERR_INVALID_ARG;
+    }
+}
+
+[[noreturn]] void fail(ob_status c, const std::string& m) { throw StatusError{c, m}; }
+
+int64_t pad_rows(int64_t n) { return std::max<int64_t>(KT, (n + KT - 1) / KT * KT); }
+
+void alloc_group(GroupData& g, int64_t n, int ldx, bool weighted) {
+    g.n = n; g.n_pad = pad_rows(n);
+    OB_CUDA(cudaMalloc(&g.X, sizeof(double) * (size_t)g.n_pad * ldx));
+    OB_CUDA(cudaMemset(g.X, 0, sizeof(double) * (size_t)g.n_pad * ldx));
+    if (weighted) {
+        OB_CUDA(cudaMalloc(&g.w, sizeof(double) * (size_t)g.n_pad));
+        OB_CUDA(cudaMemset(g.w, 0, sizeof(double) * (size_t)g.n_pad));
+    }
+}
+
+const char* status_text(int s) {
+    switch (s) {
+    case OB_ERR_INVALID_GROUP: return "Invalid group variable: No data in groups for weighted coefficients.";
+    case OB_ERR_NALGEBRA: return "Nalgebra error: Failed to perform Cholesky decomposition. Matrix may be singular or not positive definite due to multicollinearity.";
+    case OB_ERR_INSUFFICIENT_DATA: return "Insufficient data: Insufficient data for OLS calculation: n_obs must be strictly greater than k";
+    default: return "error";
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t ob_abi_version(void) { return OBBOOT_ABI_VERSION; }
+
+ob_status ob_device_count(int32_t* n_out) {
+    if (!n_out) return OB_ERR_INVALID_ARG;
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); *n_out = 0; return OB_ERR_NO_DEVICE; }
+    *n_out = n;
+    return OB_OK;
+}
+
+ob_status ob_ctx_create(int32_t device, ob_ctx** out) {
+    if (!out) return OB_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return OB_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) return OB_ERR_INVALID_ARG;
+    auto ctx = std::make_unique<ob_ctx>();
+    ctx->device = device;
+    const ob_status st = guarded(ctx.get(), [&] {
+        cudaDeviceProp prop;
+        OB_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) fail(OB_ERR_NO_DEVICE, "libobboot is built for sm_100a (B200) only");
+        ctx->num_sms = prop.multiProcessorCount;
+        OB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    });
+    if (st != OB_OK) return st;
+    *out = ctx.release();
+    return OB_OK;
+}
+
+void ob_ctx_destroy(ob_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* ob_last_error(const ob_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int32_t ob_num_stats(int32_t K, int32_t n_norm, const int32_t* norm_has_base) {
+    int nb = 0;
+    for (int v = 0; v < n_norm; ++v) nb += (norm_has_base && norm_has_base[v]) ? 1 : 0;
+    return 5 + 2 * (K + nb);
+}
+
+void ob_design_destroy(ob_design* d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    for (auto& g : d->g) { if (g.X) cudaFree(g.X); if (g.w) cudaFree(g.w); }
+    delete d;
+}
+
+ob_status ob_design_shape(const ob_design* d, int64_t* na, int64_t* nb, int32_t* K, int32_t* n_cont) {
+    if (!d) return OB_ERR_INVALID_ARG;
+    if (na) *na = d->g[0].n;
+    if (nb) *nb = d->g[1].n;
+    if (K) *K = d->K;
+    if (n_cont) *n_cont = d->n_cont;
+    return OB_OK;
+}
+
+ob_status ob_design_from_dense(ob_ctx* ctx, int32_t K, int32_t n_cont,
+                               const double* Xa, const double* ya, const double* wa, int64_t na,
+                               const double* Xb, const double* yb, const double* wb, int64_t nb,
+                               ob_design** out) {
+    if (!ctx || !out) return OB_ERR_INVALID_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        if (K < 1 || n_cont < 0 || n_cont > K - 1 || na < 0 || nb < 0) fail(OB_ERR_INVALID_ARG, "bad design shape");
+        if ((na && (!Xa || !ya)) || (nb && (!Xb || !yb))) fail(OB_ERR_INVALID_ARG, "null design pointer");
+        if ((wa == nullptr) != (wb == nullptr) && na && nb) fail(OB_ERR_INVALID_ARG, "weights must be given for both groups or neither");
+        if (K + 1 > 91) fail(OB_ERR_UNSUPPORTED, "design wider than 90 columns is not supported by the solve kernel");
+        const double* ws[2] = {wa, wb};
+        const int64_t ns[2] = {na, nb};
+        for (int g = 0; g < 2; ++g)
+            if (ws[g])
+                for (int64_t i = 0; i < ns[g]; ++i)
+                    if (ws[g][i] < 0.0) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: Weights cannot be negative");  // ols.rs:60-66
+        std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
+        d->device = ctx->device; d->K = K; d->n_cont = n_cont; d->V = K + 1; d->ldx = design_ldx(K + 1);
+        d->weighted = (wa != nullptr) || (wb != nullptr);
+        const double* Xs[2] = {Xa, Xb};
+        const double* ys[2] = {ya, yb};
+        for (int g = 0; g < 2; ++g) {
+            alloc_group(d->g[g], ns[g], d->ldx, d->weighted);
+            if (ns[g] == 0) continue;
+            OB_CUDA(cudaMemcpy2DAsync(d->g[g].X, sizeof(double) * d->ldx, Xs[g], sizeof(double) * K, sizeof(double) * K,
+                                      (size_t)ns[g], cudaMemcpyHostToDevice, ctx->stream));
+            OB_CUDA(cudaMemcpy2DAsync(d->g[g].X + K, sizeof(double) * d->ldx, ys[g], sizeof(double), sizeof(double),
+                                      (size_t)ns[g], cudaMemcpyHostToDevice, ctx->stream));
+            if (d->weighted && ws[g])
+                OB_CUDA(cudaMemcpyAsync(d->g[g].w, ws[g], sizeof(double) * (size_t)ns[g], cudaMemcpyHostToDevice, ctx->stream));
+        }
+        OB_CUDA(cudaStreamSynchronize(ctx->stream));
+        *out = d.release();
+    });
+}
+
+ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
+    if (!ctx || !f || !out) return OB_ERR_INVALID_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        if (f->n < 0 || f->n_cont < 0 || f->n_cat < 0) fail(OB_ERR_INVALID_ARG, "bad frame shape");
+        if (f->n && (!f->outcome || !f->group)) fail(OB_ERR_INVALID_ARG, "null frame column");
+        int K = 1 + f->n_cont;
+        std::vector<int32_t> dummy_start(std::max(f->n_cat, 1), 0);
+        for (int q = 0; q < f->n_cat; ++q) {
+            if (f->cat_levels[q] < 1) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: Could not get reference category");  // builder.rs:392-399
+            dummy_start[q] = K;
+            K += f->cat_levels[q] - 1;
+        }
+        if (K + 1 > 91) fail(OB_ERR_UNSUPPORTED, "design wider than 90 columns is not supported by the solve kernel");
+        cudaStream_t st = ctx->stream;
+        const int64_t n = f->n;
+        // ---- stage the frame columns in HBM ----
+        std::vector<DevBuf> cols(f->n_cont), cats(f->n_cat);
+        std::vector<const double*> h_cont(std::max(f->n_cont, 1), nullptr);
+        std::vector<const int32_t*> h_cat(std::max(f->n_cat, 1), nullptr);
+        for (int c = 0; c < f->n_cont; ++c) {
+            if (!f->cont[c]) fail(OB_ERR_INVALID_ARG, "null predictor column");
+            cols[c].alloc(sizeof(double) * (size_t)std::max<int64_t>(n, 1));
+            OB_CUDA(cudaMemcpyAsync(cols[c].p, f->cont[c], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+            h_cont[c] = cols[c].as<double>();
+        }
+        for (int q = 0; q < f->n_cat; ++q) {
+            if (!f->cat_codes[q]) fail(OB_ERR_INVALID_ARG, "null categorical column");
+            cats[q].alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(n, 1));
+            OB_CUDA(cudaMemcpyAsync(cats[q].p, f->cat_codes[q], sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
+            h_cat[q] = cats[q].as<int32_t>();
+        }
+        DevBuf d_y(sizeof(double) * (size_t)std::max<int64_t>(n, 1)), d_grp((size_t)std::max<int64_t>(n, 1)), d_w;
+        OB_CUDA(cudaMemcpyAsync(d_y.p, f->outcome, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+        OB_CUDA(cudaMemcpyAsync(d_grp.p, f->group, (size_t)n, cudaMemcpyHostToDevice, st));
+        if (f->weights) {
+            d_w.alloc(sizeof(double) * (size_t)std::max<int64_t>(n, 1));
+            OB_CUDA(cudaMemcpyAsync(d_w.p, f->weights, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+        }
+        DevBuf d_cont_ptrs(sizeof(void*) * h_cont.size()), d_cat_ptrs(sizeof(void*) * h_cat.size());
+        DevBuf d_levels(sizeof(int32_t) * std::max(f->n_cat, 1)), d_dstart(sizeof(int32_t) * dummy_start.size());
+        OB_CUDA(cudaMemcpyAsync(d_cont_ptrs.p, h_cont.data(), sizeof(void*) * h_cont.size(), cudaMemcpyHostToDevice, st));
+        OB_CUDA(cudaMemcpyAsync(d_cat_ptrs.p, h_cat.data(), sizeof(void*) * h_cat.size(), cudaMemcpyHostToDevice, st));
+        if (f->n_cat) OB_CUDA(cudaMemcpyAsync(d_levels.p, f->cat_levels, sizeof(int32_t) * f->n_cat, cudaMemcpyHostToDevice, st));
+        OB_CUDA(cudaMemcpyAsync(d_dstart.p, dummy_start.data(), sizeof(int32_t) * dummy_start.size(), cudaMemcpyHostToDevice, st));
+
+        PackArgs pa;
+        pa.n = n; pa.n_cont = f->n_cont; pa.n_cat = f->n_cat;
+        pa.d_cont = d_cont_ptrs.as<const double*>(); pa.d_cat = d_cat_ptrs.as<const int32_t*>();
+        pa.d_cat_levels = d_levels.as<int32_t>(); pa.d_dummy_start = d_dstart.as<int32_t>();
+        pa.d_y = d_y.as<double>(); pa.d_w = d_w.as<double>(); pa.d_group = d_grp.as<uint8_t>();
+        pa.K = K; pa.ldx = design_ldx(K + 1);
+
+        const int nblk = pack_num_blocks(n);
+        DevBuf d_bc(sizeof(long long) * 2 * (size_t)std::max(nblk, 1)), d_tot(sizeof(long long) * 2), d_flags(sizeof(int) * 4);
+        OB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * 4, st));
+        pack_count_scan(pa, d_bc.as<long long>(), d_tot.as<long long>(), d_flags.as<int>(), st);
+        long long tot[2]; int flags[4];
+        OB_CUDA(cudaMemcpyAsync(tot, d_tot.p, sizeof tot, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        if (flags[0]) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: Weights cannot be negative");
+
+        std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
+        d->device = ctx->device; d->K = K; d->n_cont = f->n_cont; d->V = K + 1; d->ldx = pa.ldx;
+        d->weighted = f->weights != nullptr;
+        alloc_group(d->g[0], tot[0], d->ldx, d->weighted);
+        alloc_group(d->g[1], tot[1], d->ldx, d->weighted);
+        pack_scatter(pa, d_bc.as<long long>(), d->g[0], d->g[1], d_flags.as<int>(), st);
+        OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        if (flags[1]) fail(OB_ERR_INVALID_ARG, "categorical code outside [0, levels)");
+        *out = d.release();
+    });
+}
+
+ob_status ob_design_download(ob_ctx* ctx, const ob_design* d, double* Xa, double* ya, double* wa,
+                             double* Xb, double* yb, double* wb) {
+    if (!ctx || !d) return OB_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        double* Xs[2] = {Xa, Xb}; double* ys[2] = {ya, yb}; double* ws[2] = {wa, wb};
+        for (int g = 0; g < 2; ++g) {
+            const GroupData& G = d->g[g];
+            if (G.n == 0) continue;
+            if (Xs[g]) OB_CUDA(cudaMemcpy2DAsync(Xs[g], sizeof(double) * d->K, G.X, sizeof(double) * d->ldx,
+                                                 sizeof(double) * d->K, (size_t)G.n, cudaMemcpyDeviceToHost, ctx->stream));
+            if (ys[g]) OB_CUDA(cudaMemcpy2DAsync(ys[g], sizeof(double), G.X + d->K, sizeof(double) * d->ldx, sizeof(double),
+                                                 (size_t)G.n, cudaMemcpyDeviceToHost, ctx->stream));
+            if (ws[g] && G.w) OB_CUDA(cudaMemcpyAsync(ws[g], G.w, sizeof(double) * (size_t)G.n, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        OB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau) {
+    if (!ctx || !d) return OB_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        for (int g = 0; g < 2; ++g) {
+            const size_t sb = rif_scratch_bytes(d->g[g].n);
+            DevBuf scratch(sb);
+            rif_transform(d->g[g], d->K, d->ldx, tau, scratch.p, sb, ctx->stream);
+            OB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    });
+}
+
+ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_result* res) {
+    if (!ctx || !d || !o || !res) return OB_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        cudaStream_t st = ctx->stream;
+        const int K = d->K, V = d->V;
+        if (o->ref_kind < 0 || o->ref_kind > 3) fail(OB_ERR_INVALID_ARG, "ref_kind out of range");
+        if (o->reps < 0 || o->n_norm < 0) fail(OB_ERR_INVALID_ARG, "negative reps / n_norm");
+        const int64_t rb = o->rep_begin, re = o->rep_end > 0 ? o->rep_end : o->reps;
+        if (rb < 0 || re < rb || re > o->reps) fail(OB_ERR_INVALID_ARG, "bad replicate shard");
+        const int64_t nrep = re - rb;
+        // builder.rs:431-435 (either group empty)
+        if (d->g[0].n == 0 || d->g[1].n == 0) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: One group has no data");
+        int n_base = 0, n_idx = 0;
+        for (int v = 0; v < o->n_norm; ++v) {
+            n_base += o->norm_has_base[v] ? 1 : 0;
+            if (o->norm_off[v + 1] < o->norm_off[v]) fail(OB_ERR_INVALID_ARG, "norm_off not monotone");
+        }
+        if (o->n_norm) n_idx = o->norm_off[o->n_norm];
+        for (int t = 0; t < n_idx; ++t)
+            if (o->norm_idx[t] < 0 || o->norm_idx[t] >= K) fail(OB_ERR_INVALID_ARG, "norm_idx outside the design");
+        const int D = K + n_base, S = 5 + 2 * D;
+        const bool index_mode = o->idx_a != nullptr || o->idx_b != nullptr;
+        if (index_mode && nrep > 0 && (!o->idx_a || !o->idx_b)) fail(OB_ERR_INVALID_ARG, "index stream needs both idx_a and idx_b");
+        if (o->count_bits != 0 && o->count_bits != 8 && o->count_bits != 16) fail(OB_ERR_INVALID_ARG, "count_bits must be 0, 8 or 16");
+        int count_bytes = o->count_bits == 16 ? 2 : 1;
+
+        res->ms_counts = res->ms_gram = res->ms_solve = res->ms_reduce = res->ms_total = 0.0;
+        res->gpu_launches = 0;
+        res->n_ok = 0;
+        Timer t_total(st, &res->ms_total);
+
+        // ---- normalisation spec on the device ----
+        const int nn = std::max(o->n_norm, 1);
+        DevBuf d_nm(sizeof(int) * nn), d_noff(sizeof(int) * (nn + 1)), d_nidx(sizeof(int) * std::max(n_idx, 1)), d_nhb(sizeof(int) * nn);
+        if (o->n_norm) {
+            OB_CUDA(cudaMemcpyAsync(d_nm.p, o->norm_m, sizeof(int) * o->n_norm, cudaMemcpyHostToDevice, st));
+            OB_CUDA(cudaMemcpyAsync(d_noff.p, o->norm_off, sizeof(int) * (o->n_norm + 1), cudaMemcpyHostToDevice, st));
+            if (n_idx) OB_CUDA(cudaMemcpyAsync(d_nidx.p, o->norm_idx, sizeof(int) * n_idx, cudaMemcpyHostToDevice, st));
+            OB_CUDA(cudaMemcpyAsync(d_nhb.p, o->norm_has_base, sizeof(int) * o->n_norm, cudaMemcpyHostToDevice, st));
+        }
+
+        // ---- outputs over all slots of this shard (slot 0 = point estimate) ----
+        const int64_t slots = 1 + nrep;
+        const bool want_beta = res->rep_beta_a || res->rep_beta_b || res->beta_a || res->beta_b;
+        DevBuf d_stats(sizeof(double) * (size_t)slots * S), d_status(sizeof(int) * (size_t)slots);
+        DevBuf d_ba(want_beta ? sizeof(double) * (size_t)slots * K : 0), d_bb(want_beta ? sizeof(double) * (size_t)slots * K : 0);
+        DevBuf d_point(sizeof(double) * (5 * (size_t)K + 1));
+        DevBuf d_flags(sizeof(int) * 4);
+
+        // ---- batch the multiplicity matrix by panels under the workspace budget ----
+        const int ntiles = (int)((num_pairs(V) + BN - 1) / BN);
+        const int Pld = ntiles * BN;
+        const int64_t panels_total = (slots + BM - 1) / BM;
+        const int64_t n_pad[2] = {d->g[0].n_pad, d->g[1].n_pad};
+        size_t free_b = 0, total_b = 0;
+        OB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const double budget = o->max_workspace_bytes > 0 ? (double)o->max_workspace_bytes : 0.6 * (double)free_b;
+
+        for (int attempt = 0; attempt < 2; ++attempt) {  // second attempt only widens uint8 -> uint16 after saturation
+            const double per_panel = (double)(n_pad[0] + n_pad[1]) * BM * count_bytes +
+                                     (index_mode ? (double)(d->g[0].n + d->g[1].n) * BM * 4.0 : 0.0) +
+                                     2.0 * BM * Pld * 8.0 + 2.0 * 64.0 * ntiles * (BM * BN * 8.0);
+            const double fixed = 0.0;
+            int64_t ppb = (int64_t)std::floor((budget - fixed) / per_panel);
+            ppb = std::max<int64_t>(1, std::min<int64_t>(ppb, panels_total));
+            // reduction kernel caps a batch? no: batches only bound workspace
+            DevBuf d_C[2], d_idx[2], d_colsum(sizeof(long long) * (size_t)ppb * BM);
+            for (int g = 0; g < 2; ++g) d_C[g].alloc((size_t)ppb * n_pad[g] * BM * count_bytes);
+            DevBuf d_gram(sizeof(double) * 2 * (size_t)ppb * BM * Pld);
+            bool saturated = false;
+
+            GramPlan plan; int64_t plan_panels = -1;
+            DevBuf d_partials, d_pairs;
+            {
+                const std::vector<uint16_t> pairs = gram_pair_table(V, ntiles);
+                d_pairs.alloc(sizeof(uint16_t) * pairs.size());
+                OB_CUDA(cudaMemcpyAsync(d_pairs.p, pairs.data(), sizeof(uint16_t) * pairs.size(), cudaMemcpyHostToDevice, st));
+                OB_CUDA(cudaStreamSynchronize(st));
+            }
+
+            for (int64_t p0 = 0; p0 < panels_total && !saturated; p0 += ppb) {
+                const int64_t pn = std::min(ppb, panels_total - p0);
+                const int64_t slot_lo = p0 * BM, slot_hi = std::min(slots, (p0 + pn) * BM);
+                const int64_t bslots = slot_hi - slot_lo;
+                const int first_slot = (p0 == 0) ? 1 : 0;
+                const int64_t brep = bslots - first_slot;                 // replicates in this batch
+                const int64_t rep0 = rb + slot_lo - 1;                    // global replicate id of local slot 0
+                OB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * 4, st));
+
+                // (2) replicate generation
+                Timer t_counts(st, &res->ms_counts);
+                for (int g = 0; g < 2; ++g) {
+                    CountsArgs ca;
+                    ca.C = d_C[g].p; ca.count_bytes = count_bytes; ca.n = d->g[g].n; ca.n_pad = n_pad[g];
+                    ca.panels = (int)pn; ca.slots = bslots; ca.first_slot = first_slot; ca.rep0 = rep0;
+                    ca.group = g; ca.seed = o->seed;
+                    if (index_mode) {
+                        const uint32_t* h = (g == 0 ? o->idx_a : o->idx_b);
+                        const size_t nb = sizeof(uint32_t) * (size_t)std::max<int64_t>(brep, 1) * d->g[g].n;
+                        if (d_idx[g].bytes < nb) d_idx[g].alloc(nb);
+                        if (brep > 0)
+                            OB_CUDA(cudaMemcpyAsync(d_idx[g].p, h + (size_t)(rep0 + first_slot) * d->g[g].n,
+                                                    sizeof(uint32_t) * (size_t)brep * d->g[g].n, cudaMemcpyHostToDevice, st));
+                        counts_from_indices(ca, d_idx[g].as<uint32_t>(), d_flags.as<int>(), st);
+                        res->gpu_launches += 1 + (brep > 0 ? (int)((brep + 32767) / 32768) : 0);
+                    } else {
+                        counts_philox(ca, d_colsum.as<long long>(), d_flags.as<int>(), st);
+                        res->gpu_launches += 1 + (brep > 0 ? 1 : 0);
+                    }
+                }
+                t_counts.stop();
+
+                // (3) Gram / cross-product contraction
+                if (plan_panels != pn) {
+                    plan = gram_make_plan(V, (int)pn, n_pad, count_bytes, d->weighted, ctx->num_sms);
+                    plan_panels = pn;
+                    d_partials.alloc(sizeof(double) * (size_t)plan.num_partials * BM * BN);
+                }
+                Timer t_gram(st, &res->ms_gram);
+                GramArgs ga;
+                for (int g = 0; g < 2; ++g) { ga.X[g] = d->g[g].X; ga.w[g] = d->weighted ? d->g[g].w : nullptr; ga.C[g] = d_C[g].p; }
+                ga.count_bytes = count_bytes; ga.partials = d_partials.as<double>();
+                ga.d_pairs = d_pairs.as<uint16_t>(); ga.gram = d_gram.as<double>();
+                gram_launch(plan, ga, st);
+                res->gpu_launches += 2;
+                t_gram.stop();
+
+                // (4) solves + decomposition epilogue
+                Timer t_solve(st, &res->ms_solve);
+                SolveArgs sa;
+                sa.gram = d_gram.as<double>(); sa.slots_pad = pn * BM; sa.Pld = Pld; sa.slots = bslots;
+                sa.K = K; sa.n_cont = d->n_cont; sa.ref_kind = o->ref_kind;
+                sa.n_norm = o->n_norm; sa.d_norm_m = d_nm.as<int>(); sa.d_norm_off = d_noff.as<int>();
+                sa.d_norm_idx = d_nidx.as<int>(); sa.d_norm_has_base = d_nhb.as<int>();
+                sa.n_base = n_base; sa.S = S; sa.weighted = d->weighted ? 1 : 0;
+                sa.na = (double)d->g[0].n; sa.nb = (double)d->g[1].n;
+                sa.stats = d_stats.as<double>() + (size_t)slot_lo * S;
+                sa.status = d_status.as<int>() + slot_lo;
+                sa.beta_a = want_beta ? d_ba.as<double>() + (size_t)slot_lo * K : nullptr;
+                sa.beta_b = want_beta ? d_bb.as<double>() + (size_t)slot_lo * K : nullptr;
+                sa.point_extra = (p0 == 0) ? d_point.as<double>() : nullptr;
+                solve_launch(sa, st);
+                res->gpu_launches += 1;
+                t_solve.stop();
+
+                int flags[4];
+                OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+                OB_CUDA(cudaStreamSynchronize(st));
+                t_counts.collect(); t_gram.collect(); t_solve.collect();
+                if (flags[2]) fail(OB_ERR_INVALID_ARG, "resample index out of range");
+                if (flags[0]) fail(OB_ERR_CUDA, "Poisson body overshot n (probability < 1e-15 per replicate); rerun with another seed");
+                if (flags[1]) {
+                    if (count_bytes == 2 || o->count_bits == 8) fail(OB_ERR_UNSUPPORTED, "row multiplicity overflows the count width");
+                    saturated = true;
+                }
+            }
+            if (!saturated) break;
+            count_bytes = 2;  // widen and redo
+            res->ms_counts = res->ms_gram = res->ms_solve = 0.0;
+        }
+
+        // ---- point estimate (builder.rs:810-811): a failure here is a hard error ----
+        int point_status = 0;
+        std::vector<double> point(5 * (size_t)K + 1);
+        OB_CUDA(cudaMemcpyAsync(&point_status, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(point.data(), d_point.p, sizeof(double) * point.size(), cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        if (point_status != OB_OK) fail((ob_status)point_status, status_text(point_status));
+        res->total_gap = point[5 * K];
+        if (res->xa_mean) memcpy(res->xa_mean, point.data(), sizeof(double) * K);
+        if (res->xb_mean) memcpy(res->xb_mean, point.data() + K, sizeof(double) * K);
+        if (res->beta_star) memcpy(res->beta_star, point.data() + 2 * K, sizeof(double) * K);
+        if (res->point_stats) OB_CUDA(cudaMemcpyAsync(res->point_stats, d_stats.p, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
+        if (res->beta_a) OB_CUDA(cudaMemcpyAsync(res->beta_a, d_ba.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
+        if (res->beta_b) OB_CUDA(cudaMemcpyAsync(res->beta_b, d_bb.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
+        if (res->residuals_b) {  // builder.rs:946: raw residuals of group B under its un-normalised fit
+            DevBuf d_res(sizeof(double) * (size_t)d->g[1].n);
+            residuals_launch(d->g[1], K, d->ldx, d_point.as<double>() + 4 * K, d_res.as<double>(), st);
+            res->gpu_launches += 1;
+            OB_CUDA(cudaMemcpyAsync(res->residuals_b, d_res.p, d_res.bytes, cudaMemcpyDeviceToHost, st));
+            OB_CUDA(cudaStreamSynchronize(st));
+        }
+
+        // ---- (5) reduction to standard errors / p-values / percentile CIs ----
+        if (!o->skip_reduce) {
+            DevBuf d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long));
+            Timer t_red(st, &res->ms_reduce);
+            reduce_stats_launch(d_stats.as<double>() + S, d_status.as<int>() + 1, nrep, S, d_stats.as<double>(),
+                                d_out.as<double>(), d_nok.as<long long>(), st);
+            res->gpu_launches += 1;
+            t_red.stop();
+            std::vector<double> out5(5 * (size_t)S);
+            long long nok = 0;
+            OB_CUDA(cudaMemcpyAsync(out5.data(), d_out.p, d_out.bytes, cudaMemcpyDeviceToHost, st));
+            OB_CUDA(cudaMemcpyAsync(&nok, d_nok.p, sizeof nok, cudaMemcpyDeviceToHost, st));
+            OB_CUDA(cudaStreamSynchronize(st));
+            t_red.collect();
+            res->n_ok = nok;
+            double* dst[5] = {res->std_err, res->p_value, res->ci_lower, res->ci_upper, res->t_stat};
+            for (int k = 0; k < 5; ++k)
+                if (dst[k]) memcpy(dst[k], out5.data() + (size_t)k * S, sizeof(double) * S);
+        }
+        if (nrep > 0) {
+            if (res->rep_stats) OB_CUDA(cudaMemcpyAsync(res->rep_stats, d_stats.as<double>() + S, sizeof(double) * (size_t)nrep * S, cudaMemcpyDeviceToHost, st));
+            if (res->rep_status) OB_CUDA(cudaMemcpyAsync(res->rep_status, d_status.as<int>() + 1, sizeof(int) * (size_t)nrep, cudaMemcpyDeviceToHost, st));
+            if (res->rep_beta_a) OB_CUDA(cudaMemcpyAsync(res->rep_beta_a, d_ba.as<double>() + K, sizeof(double) * (size_t)nrep * K, cudaMemcpyDeviceToHost, st));
+            if (res->rep_beta_b) OB_CUDA(cudaMemcpyAsync(res->rep_beta_b, d_bb.as<double>() + K, sizeof(double) * (size_t)nrep * K, cudaMemcpyDeviceToHost, st));
+        }
+        t_total.stop();
+        OB_CUDA(cudaStreamSynchronize(st));
+        t_total.collect();
+    });
+}
+
+ob_status ob_reduce_stats(ob_ctx* ctx, const double* rep_stats, const int32_t* rep_status, int64_t reps, int32_t S,
+                          const double* point_stats, int64_t* n_ok, double* std_err, double* p_value,
+                          double* ci_lower, double* ci_upper, double* t_stat) {
+    if (!ctx || S < 1 || reps < 0 || !point_stats || (reps && (!rep_stats || !rep_status))) return OB_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        cudaStream_t st = ctx->stream;
+        DevBuf d_stats(sizeof(double) * (size_t)std::max<int64_t>(reps, 1) * S), d_status(sizeof(int) * (size_t)std::max<int64_t>(reps, 1));
+        DevBuf d_point(sizeof(double) * S), d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long));
+        if (reps) {
+            OB_CUDA(cudaMemcpyAsync(d_stats.p, rep_stats, sizeof(double) * (size_t)reps * S, cudaMemcpyHostToDevice, st));
+            OB_CUDA(cudaMemcpyAsync(d_status.p, rep_status, sizeof(int) * (size_t)reps, cudaMemcpyHostToDevice, st));
+        }
+        OB_CUDA(cudaMemcpyAsync(d_point.p, point_stats, sizeof(double) * S, cudaMemcpyHostToDevice, st));
+        reduce_stats_launch(d_stats.as<double>(), d_status.as<int>(), reps, S, d_point.as<double>(), d_out.as<double>(),
+                            d_nok.as<long long>(), st);
+        std::vector<double> out5(5 * (size_t)S);
+        long long nok = 0;
+        OB_CUDA(cudaMemcpyAsync(out5.data(), d_out.p, d_out.bytes, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(&nok, d_nok.p, sizeof nok, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        if (n_ok) *n_ok = nok;
+        double* dst[5] = {std_err, p_value, ci_lower, ci_upper, t_stat};
+        for (int k = 0; k < 5; ++k)
+            if (dst[k]) memcpy(dst[k], out5.data() + (size_t)k * S, sizeof(double) * S);
+    });
+}
+
+ob_status ob_debug_counts(ob_ctx* ctx, const ob_design* d, uint64_t seed, int64_t rep, int32_t group,
+                          uint16_t* counts_out) {
+    if (!ctx || !d || !counts_out || group < 0 || group > 1 || rep < 0) return OB_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        cudaStream_t st = ctx->stream;
+        const GroupData& G = d->g[group];
+        DevBuf d_C((size_t)G.n_pad * BM * 2), d_colsum(sizeof(long long) * BM), d_flags(sizeof(int) * 4);
+        OB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * 4, st));
+        CountsArgs ca;
+        ca.C = d_C.p; ca.count_bytes = 2; ca.n = G.n; ca.n_pad = G.n_pad; ca.panels = 1; ca.slots = 2;
+        ca.first_slot = 1; ca.rep0 = rep - 1; ca.group = group; ca.seed = seed;
+        counts_philox(ca, d_colsum.as<long long>(), d_flags.as<int>(), st);
+        // slot 1 column of the single panel
+        OB_CUDA(cudaMemcpy2DAsync(counts_out, sizeof(uint16_t), d_C.as<uint16_t>() + 1, sizeof(uint16_t) * BM,
+                                  sizeof(uint16_t), (size_t)G.n, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+}  // extern "C"

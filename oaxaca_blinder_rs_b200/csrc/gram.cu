@@ -1,0 +1,274 @@
+// csrc/gram.cu -- replicate Gram / cross-product accumulation  G_b = sum_i c[i,b] w_i z_i  on the
+// FP64 tensor cores (DMMA.8x8x4), replacing per replicate the gather + X'WX + X'Wy + column means
+// of the reference (builder.rs:822-829 sample_n_literal, prepare_data :294-378, ols.rs:68-89,
+// estimation.rs:56-71).
+//
+// Contraction:  [slots x n] (multiplicities, A operand)  x  [n x P'] (Z, B operand), per group.
+//   * A[i][b] = c[i,b] * w_i : counts arrive as uint8/uint16 tiles by TMA bulk copy and are widened
+//     once per CTA tile into an fp64 shared-memory tile (exact: magic-number int->double, one FMA).
+//   * Z is never materialised (110 GB at n=1e7,K=51): z_i[(j,l)] = x_ij * x_il is formed in
+//     registers from the staged design rows while loading B fragments (one DMUL per fragment
+//     element, 1/64 of the DMMA work).  Column (j,l) order = row-major upper triangle of
+//     [x|y][x|y]^T, so G, X'Wy, the column sums (means) and sum(w) all come out of one pass.
+//   * CTA tile 128 slots x 128 columns, 8 warps (2 x 4), warp tile 64 x 32 = 8 x 4 DMMA sub-tiles,
+//     KT = 32 rows per stage, 3-4 stage TMA/mbarrier pipeline.
+//   * Split-n: the rows of a group are cut into `segs` fixed segments whose size depends only on the
+//     group's row count.  Work unit = (group, panel, column tile, segment): accumulated from zero,
+//     flushed as one partial tile.  A persistent grid of one CTA per SM walks equal contiguous unit
+//     ranges; gram_reduce sums a tile's partials in ascending segment order.  The summation tree of
+//     every Gram entry is therefore fixed by (n_g, K) alone: results are bit-identical run to run and
+//     do not depend on how replicates are batched or sharded over GPUs.
+#include "common.cuh"
+#include "internal.h"
+
+#include <algorithm>
+
+namespace ob {
+
+constexpr int LDA = BM + 4;  // fp64 A tile row stride: 132 = 4 mod 16 -> conflict-free fragment loads
+
+struct GramKernelParams {
+    const double* X[2];
+    const double* w[2];
+    const void* C[2];
+    long long n_pad[2];
+    int segs[2];            // row segments per tile
+    int seg_rows[2];        // rows per segment (multiple of KT)
+    long long units0;       // units of group 0 = panels * ntiles * segs[0]
+    long long units_total;
+    int ldx, panels, ntiles, stages;
+    double* partials;       // [units_total][BM*BN], unit-major
+    const uint16_t* pairs;
+};
+
+template <typename CountT>
+__device__ __forceinline__ void widen_counts(const CountT* __restrict__ craw, double* __restrict__ as,
+                                             const double* __restrict__ ws, bool weighted, int tid) {
+    // thread (r = tid/8, q = tid%8) widens columns {16e + 2q, 16e + 2q + 1 : e = 0..7} of row r
+    const int r = tid >> 3, q = tid & 7;
+    const CountT* src = craw + r * BM + q * 2;
+    double* dst = as + r * LDA + q * 2;
+    const double two52 = 4503599627370496.0;
+    double wr = 1.0, off = -two52;
+    if (weighted) { wr = ws[r]; off = -two52 * wr; }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        unsigned c0, c1;
+        if (sizeof(CountT) == 1) {
+            const unsigned v = *reinterpret_cast<const uint16_t*>(src + e * 16);
+            c0 = v & 0xFFu; c1 = v >> 8;
+        } else {
+            const unsigned v = *reinterpret_cast<const uint32_t*>(src + e * 16);
+            c0 = v & 0xFFFFu; c1 = v >> 16;
+        }
+        // (2^52 + c) is exact in fp64; fma(2^52 + c, w, -2^52 w) = round(c * w) in one operation
+        double2 o;
+        o.x = fma(__hiloint2double(0x43300000, (int)c0), wr, off);
+        o.y = fma(__hiloint2double(0x43300000, (int)c1), wr, off);
+        *reinterpret_cast<double2*>(dst + e * 16) = o;
+    }
+}
+
+template <typename CountT>
+__global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int lk = lane & 3, lg = lane >> 2;
+    const int ldx = p.ldx, NST = p.stages;
+    const bool weighted = p.w[0] != nullptr;
+
+    // ---- shared memory carve-up (all regions 16-B aligned) ----
+    double* As = reinterpret_cast<double*>(smem_raw);                   // [2][KT*LDA]
+    double* Xs = As + 2 * KT * LDA;                                     // [NST][KT*ldx]
+    double* Ws = Xs + (size_t)NST * KT * ldx;                           // [NST][KT]
+    CountT* Cr = reinterpret_cast<CountT*>(Ws + (size_t)NST * KT);      // [NST][KT*BM]
+    uint64_t* full = reinterpret_cast<uint64_t*>(Cr + (size_t)NST * KT * BM);  // [NST]
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const long long u0 = p.units_total * (long long)blockIdx.x / gridDim.x;
+    const long long u1 = p.units_total * (long long)(blockIdx.x + 1) / gridDim.x;
+    const uint32_t stage_bytes = (uint32_t)(KT * ldx * sizeof(double) + KT * BM * sizeof(CountT) +
+                                            (weighted ? KT * sizeof(double) : 0));
+    uint32_t it_base = 0;  // pipeline stage counter across units (slot = it % NST, parity = (it / NST) & 1)
+
+    for (long long u = u0; u < u1; ++u) {
+        const int g = (u >= p.units0) ? 1 : 0;
+        const long long ug = u - (g ? p.units0 : 0);
+        const int segs = g ? p.segs[1] : p.segs[0], seg_rows = g ? p.seg_rows[1] : p.seg_rows[0];
+        const long long n_pad = g ? p.n_pad[1] : p.n_pad[0];
+        const long long tile = ug / segs;
+        const int seg = (int)(ug - tile * segs);
+        const long long row0 = (long long)seg * seg_rows;
+        const long long row1 = min(row0 + seg_rows, n_pad);
+        const int nstages = (int)((row1 - row0) / KT);
+        const int panel = (int)(tile / p.ntiles), nt = (int)(tile - (long long)panel * p.ntiles);
+
+        const double* Xg = (g ? p.X[1] : p.X[0]) + row0 * ldx;
+        const CountT* Cg = reinterpret_cast<const CountT*>(g ? p.C[1] : p.C[0]) + ((long long)panel * n_pad + row0) * BM;
+        const double* wg = weighted ? (g ? p.w[1] : p.w[0]) + row0 : nullptr;
+
+        auto issue = [&](int s) {  // thread 0 only
+            const uint32_t it = it_base + (uint32_t)s;
+            const int slot = (int)(it % (uint32_t)NST);
+            fence_proxy_async();
+            mbar_expect_tx(&full[slot], stage_bytes);
+            tma_load_1d(Xs + (size_t)slot * KT * ldx, Xg + (long long)s * KT * ldx, KT * ldx * sizeof(double), &full[slot]);
+            tma_load_1d(Cr + (size_t)slot * KT * BM, Cg + (long long)s * KT * BM, KT * BM * sizeof(CountT), &full[slot]);
+            if (weighted) tma_load_1d(Ws + (size_t)slot * KT, wg + (long long)s * KT, KT * sizeof(double), &full[slot]);
+        };
+
+        // column pair (j,l) offsets of this thread's four B sub-tiles
+        int oj[4], ol[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int col = nt * BN + wn * 32 + s * 8 + lg;
+            const uint32_t pr = *reinterpret_cast<const uint32_t*>(p.pairs + 2 * col);
+            oj[s] = pr & 0xFFFFu; ol[s] = pr >> 16;
+        }
+
+        double acc[8][4][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { acc[i][s][0] = 0.0; acc[i][s][1] = 0.0; }
+
+        if (tid == 0)
+            for (int s = 0; s < NST - 1 && s < nstages; ++s) issue(s);
+
+        for (int s = 0; s < nstages; ++s) {
+            const uint32_t it = it_base + (uint32_t)s;
+            const int slot = (int)(it % (uint32_t)NST);
+            mbar_wait(&full[slot], (it / (uint32_t)NST) & 1u);
+            double* Acur = As + (s & 1) * KT * LDA;
+            widen_counts<CountT>(Cr + (size_t)slot * KT * BM, Acur, Ws + (size_t)slot * KT, weighted, tid);
+            __syncthreads();  // A tile visible; every warp is done with stage s-1 -> its slot is free
+            if (tid == 0 && s + NST - 1 < nstages) issue(s + NST - 1);
+
+            const double* abase = Acur + lk * LDA + wm * 64 + lg;
+            const double* xbase = Xs + (size_t)slot * KT * ldx + lk * ldx;
+#pragma unroll
+            for (int kk = 0; kk < KT / 4; ++kk) {
+                double a[8], b[4];
+                const double* arow = abase + kk * 4 * LDA;
+                const double* xrow = xbase + kk * 4 * ldx;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = arow[i * 8];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) b[t] = xrow[oj[t]] * xrow[ol[t]];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) dmma884(acc[i][t][0], acc[i][t][1], a[i], b[t]);
+            }
+        }
+        it_base += (uint32_t)nstages;
+        __syncthreads();  // all warps done with the last stage before the next unit refills A / slots
+
+        // flush the partial tile [BM][BN] row-major
+        double* out = p.partials + (size_t)u * (BM * BN);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int m = wm * 64 + i * 8 + lg, n = wn * 32 + t * 8 + 2 * lk;
+                *reinterpret_cast<double2*>(out + m * BN + n) = make_double2(acc[i][t][0], acc[i][t][1]);
+            }
+    }
+}
+
+// out[g][panel*BM + m][nt*BN + n] = sum over the tile's segment partials in ascending segment order
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ partials, int segs0, int segs1,
+                                                          double* __restrict__ gram, int panels, int ntiles) {
+    const int tile_id = blockIdx.x;
+    const int tiles_g = panels * ntiles;
+    const int g = tile_id / tiles_g, t = tile_id - g * tiles_g;
+    const int panel = t / ntiles, nt = t - panel * ntiles;
+    const int cnt = g ? segs1 : segs0;
+    const size_t first = g ? (size_t)tiles_g * segs0 + (size_t)t * segs1 : (size_t)t * segs0;
+    const size_t slots_pad = (size_t)panels * BM, Pld = (size_t)ntiles * BN;
+    for (int e = threadIdx.x + blockIdx.y * blockDim.x; e < BM * BN / 2; e += blockDim.x * gridDim.y) {
+        double2 s = make_double2(0.0, 0.0);
+        for (int q = 0; q < cnt; ++q) {
+            const double2 v = reinterpret_cast<const double2*>(partials + (first + q) * (BM * BN))[e];
+            s.x += v.x; s.y += v.y;
+        }
+        const int m = (2 * e) / BN, n = (2 * e) % BN;
+        double* dst = gram + ((size_t)g * slots_pad + (size_t)panel * BM + m) * Pld + (size_t)nt * BN + n;
+        *reinterpret_cast<double2*>(dst) = s;
+    }
+}
+
+std::vector<uint16_t> gram_pair_table(int V, int ntiles) {
+    std::vector<uint16_t> t((size_t)ntiles * BN * 2);
+    size_t c = 0;
+    for (int j = 0; j < V; ++j)
+        for (int l = j; l < V; ++l) { t[2 * c] = (uint16_t)j; t[2 * c + 1] = (uint16_t)l; ++c; }
+    for (; c < (size_t)ntiles * BN; ++c) { t[2 * c] = (uint16_t)(V - 1); t[2 * c + 1] = (uint16_t)(V - 1); }  // padding: harmless duplicates of (y,y)
+    return t;
+}
+
+static size_t gram_smem(int ldx, int stages, int count_bytes) {
+    return sizeof(double) * (2 * KT * LDA + (size_t)stages * KT * ldx + (size_t)stages * KT) +
+           (size_t)stages * KT * BM * count_bytes + sizeof(uint64_t) * stages;
+}
+
+// Segment count depends on the group's (padded) row count only -- never on panels, batch or grid --
+// so the per-entry summation order is a function of the data shape alone.
+static void segment_rows(int64_t n_pad, int& segs, int& seg_rows) {
+    const int64_t stages = n_pad / KT;
+    int64_t s = std::min<int64_t>(64, std::max<int64_t>(1, stages / 4));
+    int64_t per = (stages + s - 1) / s;           // stages per segment
+    s = (stages + per - 1) / per;
+    segs = (int)s; seg_rows = (int)(per * KT);
+}
+
+GramPlan gram_make_plan(int V, int panels, const int64_t n_pad[2], int count_bytes, bool weighted, int num_sms) {
+    (void)weighted;
+    GramPlan pl;
+    pl.V = V; pl.ldx = design_ldx(V); pl.panels = panels;
+    pl.ntiles = (int)((num_pairs(V) + BN - 1) / BN);
+    int64_t total = 0;
+    for (int g = 0; g < 2; ++g) {
+        pl.n_pad[g] = n_pad[g];
+        segment_rows(n_pad[g], pl.segs[g], pl.seg_rows[g]);
+        pl.units[g] = (int64_t)pl.segs[g] * panels * pl.ntiles;
+        total += pl.units[g];
+    }
+    pl.grid = (int)std::min<int64_t>(num_sms, std::max<int64_t>(total, 1));
+    pl.stages = 4;
+    while (pl.stages > 2 && gram_smem(pl.ldx, pl.stages, count_bytes) > 220 * 1024) --pl.stages;
+    pl.smem_bytes = gram_smem(pl.ldx, pl.stages, count_bytes);
+    pl.num_partials = (int64_t)total;
+    return pl;
+}
+
+void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st) {
+    GramKernelParams p;
+    for (int g = 0; g < 2; ++g) {
+        p.X[g] = a.X[g]; p.w[g] = a.w[g]; p.C[g] = a.C[g];
+        p.n_pad[g] = pl.n_pad[g]; p.segs[g] = pl.segs[g]; p.seg_rows[g] = pl.seg_rows[g];
+    }
+    p.units0 = pl.units[0];
+    p.units_total = pl.units[0] + pl.units[1];
+    p.ldx = pl.ldx; p.panels = pl.panels; p.ntiles = pl.ntiles; p.stages = pl.stages;
+    p.partials = a.partials; p.pairs = a.d_pairs;
+    if (a.count_bytes == 1) {
+        OB_CUDA(cudaFuncSetAttribute(gram_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+        gram_kernel<uint8_t><<<pl.grid, GRAM_THREADS, pl.smem_bytes, st>>>(p);
+    } else {
+        OB_CUDA(cudaFuncSetAttribute(gram_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+        gram_kernel<uint16_t><<<pl.grid, GRAM_THREADS, pl.smem_bytes, st>>>(p);
+    }
+    OB_CUDA(cudaGetLastError());
+    dim3 rg(2 * pl.panels * pl.ntiles, 4);
+    gram_reduce_kernel<<<rg, 256, 0, st>>>(a.partials, pl.segs[0], pl.segs[1], a.gram, pl.panels, pl.ntiles);
+    OB_CUDA(cudaGetLastError());
+}
+
+}  // namespace ob

@@ -1,0 +1,196 @@
+// csrc/pack.cu -- design-matrix pack: frame columns -> per-group row-major designs in HBM.
+//
+// Done ONCE per dataset, replacing what the reference redoes for every replicate: split_groups
+// (builder.rs:61-102: string unique/sort/equal/filter), prepare_data (builder.rs:294-378: intercept,
+// predictor select, dummy columns, three n x K copies) and the sqrt(w) scaling copy (ols.rs:68-78).
+//
+//   X_g[r][:] = [1 | continuous.. | dummies.. | outcome | 0-pad]      r = rank of the row inside group g
+// Row order inside a group is frame order (stable), as df.filter() gives (builder.rs:85-94), so
+// row positions agree with the oracle's and with an external resample index stream.
+// Dummy for code c >= 1 of categorical q: design column dummy_start[q] + c - 1 (builder.rs:402-409).
+//
+// HBM-bound: reads 8 B x (n_cont + 2) + 4 B x n_cat + 1 B per row, writes 8 B x ldx per row.
+// Three launches: per-block group counts -> single-block exclusive scan -> staged transpose/scatter.
+#include "common.cuh"
+#include "internal.h"
+
+namespace ob {
+
+constexpr int PK_ROWS = 128;   // rows per block
+constexpr int PK_THREADS = 256;
+
+__global__ void __launch_bounds__(PK_THREADS) pack_count_kernel(const uint8_t* __restrict__ group,
+                                                                const double* __restrict__ w, long long n,
+                                                                long long* __restrict__ block_counts,
+                                                                int* __restrict__ flags) {
+    __shared__ int ca, cb;
+    if (threadIdx.x == 0) { ca = 0; cb = 0; }
+    __syncthreads();
+    const long long row0 = (long long)blockIdx.x * PK_ROWS;
+    int a = 0, b = 0;
+    for (int t = threadIdx.x; t < PK_ROWS; t += PK_THREADS) {
+        const long long i = row0 + t;
+        if (i < n) {
+            const uint8_t g = group[i];
+            a += g == 0; b += g == 1;
+            if (w && g <= 1 && w[i] < 0.0) atomicOr(&flags[0], 1);   // ols.rs:60-66
+        }
+    }
+    if (a) atomicAdd(&ca, a);
+    if (b) atomicAdd(&cb, b);
+    __syncthreads();
+    if (threadIdx.x == 0) { block_counts[2 * blockIdx.x] = ca; block_counts[2 * blockIdx.x + 1] = cb; }
+}
+
+// exclusive scan of block_counts [nblocks][2] in place; totals[2] receives the group sizes
+__global__ void __launch_bounds__(1024) pack_scan_kernel(long long* __restrict__ bc, int nblocks, long long* totals) {
+    __shared__ long long part[2][1024];
+    const int t = threadIdx.x;
+    const int per = (nblocks + 1023) / 1024;
+    const int lo = t * per, hi = min(lo + per, nblocks);
+    long long sa = 0, sb = 0;
+    for (int i = lo; i < hi; ++i) { sa += bc[2 * i]; sb += bc[2 * i + 1]; }
+    part[0][t] = sa; part[1][t] = sb;
+    __syncthreads();
+    if (t < 2) {  // 1024-element serial scan per group: negligible
+        long long run = 0;
+        for (int i = 0; i < 1024; ++i) { const long long v = part[t][i]; part[t][i] = run; run += v; }
+        totals[t] = run;
+    }
+    __syncthreads();
+    long long ra = part[0][t], rb = part[1][t];
+    for (int i = lo; i < hi; ++i) {
+        const long long va = bc[2 * i], vb = bc[2 * i + 1];
+        bc[2 * i] = ra; bc[2 * i + 1] = rb;
+        ra += va; rb += vb;
+    }
+}
+
+struct PackKernelParams {
+    long long n; int n_cont, n_cat, K, ldx;
+    const double* const* cont; const int32_t* const* cat; const int32_t* cat_levels; const int32_t* dummy_start;
+    const double* y; const double* w; const uint8_t* group;
+    const long long* block_base;   // [nblocks][2] exclusive scan
+    double* XA; double* XB; double* wA; double* wB;
+    int* flags;
+};
+
+__global__ void __launch_bounds__(PK_THREADS) pack_scatter_kernel(const PackKernelParams p) {
+    extern __shared__ __align__(16) double tile[];      // [PK_ROWS][V + 1] (stride odd-ish padded)
+    __shared__ int lrank[PK_ROWS];                      // local rank within the row's group, -1 = ignored row
+    __shared__ uint8_t lgrp[PK_ROWS];
+    __shared__ int srcA[PK_ROWS], srcB[PK_ROWS];
+    __shared__ int cnt[2];
+    const int V = p.K + 1, ts = V | 1;
+    const long long row0 = (long long)blockIdx.x * PK_ROWS;
+    const int rows = (int)min((long long)PK_ROWS, p.n - row0);
+    const int tid = threadIdx.x;
+
+    // stable local ranks: warp 0..3 each own 32 rows; ballot + prefix over warps
+    __shared__ int wcount[4][2];
+    if (tid < PK_ROWS) {
+        const int g = (tid < rows) ? p.group[row0 + tid] : 255;
+        lgrp[tid] = (uint8_t)g;
+        const unsigned ma = __ballot_sync(0xffffffffu, g == 0), mb = __ballot_sync(0xffffffffu, g == 1);
+        const unsigned below = (1u << (tid & 31)) - 1u;
+        lrank[tid] = g == 0 ? __popc(ma & below) : (g == 1 ? __popc(mb & below) : -1);
+        if ((tid & 31) == 0) { wcount[tid >> 5][0] = __popc(ma); wcount[tid >> 5][1] = __popc(mb); }
+    }
+    __syncthreads();
+    if (tid < PK_ROWS && lrank[tid] >= 0) {
+        const int g = lgrp[tid];
+        int off = 0;
+        for (int wv = 0; wv < (tid >> 5); ++wv) off += wcount[wv][g];
+        const int r = lrank[tid] + off;
+        lrank[tid] = r;
+        (g == 0 ? srcA : srcB)[r] = tid;
+    }
+    if (tid == 0) {
+        cnt[0] = wcount[0][0] + wcount[1][0] + wcount[2][0] + wcount[3][0];
+        cnt[1] = wcount[0][1] + wcount[1][1] + wcount[2][1] + wcount[3][1];
+    }
+    // stage the block's rows: column-wise coalesced reads -> tile[row][col]
+    for (int e = tid; e < V * PK_ROWS; e += PK_THREADS) {
+        const int c = e / PK_ROWS, t = e - c * PK_ROWS;
+        double val = 0.0;
+        if (t < rows) {
+            const long long i = row0 + t;
+            if (c == 0) val = 1.0;                                       // __ob_intercept__ (builder.rs:330)
+            else if (c <= p.n_cont) val = p.cont[c - 1][i];
+            else if (c == p.K) val = p.y[i];
+            else {
+                int q = 0;
+                while (q + 1 < p.n_cat && c >= p.dummy_start[q + 1]) ++q;
+                const int code = p.cat[q][i];
+                if (code < 0 || code >= p.cat_levels[q]) atomicOr(&p.flags[1], 1);
+                val = (code == c - p.dummy_start[q] + 1) ? 1.0 : 0.0;    // builder.rs:402-409
+            }
+        }
+        tile[t * ts + c] = val;
+    }
+    __syncthreads();
+    const long long baseA = p.block_base[2 * blockIdx.x], baseB = p.block_base[2 * blockIdx.x + 1];
+    // write out: consecutive threads -> consecutive columns of consecutive packed rows
+    for (int e = tid; e < cnt[0] * V; e += PK_THREADS) {
+        const int r = e / V, c = e - r * V;
+        p.XA[(baseA + r) * p.ldx + c] = tile[srcA[r] * ts + c];
+    }
+    for (int e = tid; e < cnt[1] * V; e += PK_THREADS) {
+        const int r = e / V, c = e - r * V;
+        p.XB[(baseB + r) * p.ldx + c] = tile[srcB[r] * ts + c];
+    }
+    if (p.w) {
+        for (int r = tid; r < cnt[0]; r += PK_THREADS) p.wA[baseA + r] = p.w[row0 + srcA[r]];
+        for (int r = tid; r < cnt[1]; r += PK_THREADS) p.wB[baseB + r] = p.w[row0 + srcB[r]];
+    }
+}
+
+int pack_num_blocks(int64_t n) { return (int)((n + PK_ROWS - 1) / PK_ROWS); }
+
+void pack_count_scan(const PackArgs& a, long long* d_block_counts, long long* d_totals, int* d_flags, cudaStream_t st) {
+    const int nb = pack_num_blocks(a.n);
+    if (nb == 0) { OB_CUDA(cudaMemsetAsync(d_totals, 0, 2 * sizeof(long long), st)); return; }
+    pack_count_kernel<<<nb, PK_THREADS, 0, st>>>(a.d_group, a.d_w, a.n, d_block_counts, d_flags);
+    OB_CUDA(cudaGetLastError());
+    pack_scan_kernel<<<1, 1024, 0, st>>>(d_block_counts, nb, d_totals);
+    OB_CUDA(cudaGetLastError());
+}
+
+void pack_scatter(const PackArgs& a, const long long* d_block_base, GroupData ga, GroupData gb, int* d_flags,
+                  cudaStream_t st) {
+    const int nb = pack_num_blocks(a.n);
+    if (nb == 0) return;
+    PackKernelParams p;
+    p.n = a.n; p.n_cont = a.n_cont; p.n_cat = a.n_cat; p.K = a.K; p.ldx = a.ldx;
+    p.cont = a.d_cont; p.cat = a.d_cat; p.cat_levels = a.d_cat_levels; p.dummy_start = a.d_dummy_start;
+    p.y = a.d_y; p.w = a.d_w; p.group = a.d_group; p.block_base = d_block_base;
+    p.XA = ga.X; p.XB = gb.X; p.wA = ga.w; p.wB = gb.w; p.flags = d_flags;
+    const int V = a.K + 1;
+    const size_t smem = sizeof(double) * (size_t)PK_ROWS * (V | 1);
+    OB_CUDA(cudaFuncSetAttribute(pack_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pack_scatter_kernel<<<nb, PK_THREADS, smem, st>>>(p);
+    OB_CUDA(cudaGetLastError());
+}
+
+// ---- point-estimate residuals r = y - X beta (ols.rs:118-119), one warp per row ----
+__global__ void __launch_bounds__(256) residuals_kernel(const double* __restrict__ X, long long n, int K, int ldx,
+                                                        const double* __restrict__ beta, double* __restrict__ out) {
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const double* row = X + warp * ldx;
+    double s = 0.0;
+    for (int j = lane; j < K; j += 32) s += row[j] * beta[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[warp] = row[K] - s;
+}
+
+void residuals_launch(const GroupData& g, int K, int ldx, const double* d_beta, double* d_out, cudaStream_t st) {
+    if (g.n == 0) return;
+    const long long threads = g.n * 32;
+    residuals_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(g.X, g.n, K, ldx, d_beta, d_out);
+    OB_CUDA(cudaGetLastError());
+}
+
+}  // namespace ob

@@ -1,0 +1,249 @@
+// csrc/resample.cu -- replicate generation: the multiplicity matrix C (rows x replicate slots).
+//
+// Replaces DataFrame::sample_n_literal(n_g, with_replacement=true) + the gather of every column
+// (builder.rs:822-829): a replicate is fully described by how often each row was drawn, so the
+// resample is a count vector c[:,b] ~ Multinomial(n_g; 1/n_g, ..) and no row is ever moved.
+//
+// Layout per group: C[panel][row][BM] (count_t = uint8/uint16), panel = 128 replicate slots, so a
+// (32 rows x 128 slots) tile is one contiguous TMA bulk copy for gram.cu.  Slot 0 of panel 0 is the
+// point estimate (count 1 on every valid row); slot s >= 1 is global replicate rep_first + s - 1.
+//
+// Two sources:
+//  (a) counts_from_indices: explicit index stream (parity tests) -> exact histogram, bit-exact
+//      against the oracle's gather for any stream.
+//  (b) counts_philox: native counter-based stream.  Exact multinomial without n*B global atomics:
+//        body   c_i ~ iid Poisson(lambda), lambda = 1 - delta/n, delta = ceil(8 sqrt(n)), by 64-bit
+//               inverse-CDF of a Philox4x32-10 word keyed by (seed; row, group, replicate)
+//               -> conditional on the column sum S the body is Multinomial(S; uniform);
+//        fix-up n - S (about 8 sqrt(n), >= 0 except with probability < 1e-15) further uniform draws
+//               added with atomics -> Multinomial(n; uniform) exactly, sum of counts = n_g as the
+//               reference's unweighted means require (estimation.rs:66, ols.rs:83).
+//      Every draw is keyed by global ids, so counts do not depend on grid shape, batch split or on
+//      how replicates/rows are sharded over GPUs.
+#include "common.cuh"
+#include "internal.h"
+
+#include <cmath>
+
+namespace ob {
+
+constexpr int KMAX = 24;  // P(Poisson(<=1) > 23) < 2^-64
+
+struct PoissonTable {
+    unsigned long long T[KMAX];  // T[k] = floor(P(X <= k) * 2^64); count = #{k : U >= T[k]}
+    unsigned int Th[KMAX];       // high words
+    int lambda_zero;
+};
+
+// counter layout: (c0, c1, c2, c3) = (row_lo | draw_lo, row_hi | group<<8 | attempt<<16, replicate key, stream tag)
+enum : uint32_t { STREAM_BODY = 0x0B0D1u, STREAM_REFINE = 0x0F19Eu, STREAM_FIXUP = 0x0F1Cu };
+
+__device__ __forceinline__ int poisson_exact(uint32_t u_hi, const PoissonTable& t, uint64_t row, uint32_t c1,
+                                             uint64_t rep, uint32_t k0, uint32_t k1) {
+    // low word comes from the refinement stream, keyed by the single replicate id
+    const Philox4 r = philox4x32_10((uint32_t)row, c1, (uint32_t)rep, STREAM_REFINE ^ (uint32_t)(rep >> 32), k0, k1);
+    const unsigned long long U = ((unsigned long long)u_hi << 32) | r.x;
+    int c = 0;
+#pragma unroll 1
+    for (int k = 0; k < KMAX; ++k) c += (U >= t.T[k]) ? 1 : 0;
+    return c;
+}
+
+__device__ __forceinline__ int poisson_draw(uint32_t u, const PoissonTable& t, uint64_t row, uint32_t c1,
+                                            uint64_t rep, uint32_t k0, uint32_t k1) {
+    int c = (u > t.Th[0]) + (u > t.Th[1]) + (u > t.Th[2]) + (u > t.Th[3]);
+    if (u >= t.Th[3] || u == t.Th[0] || u == t.Th[1] || u == t.Th[2]) c = poisson_exact(u, t, row, c1, rep, k0, k1);
+    return c;
+}
+
+template <typename CountT>
+__global__ void __launch_bounds__(256) counts_philox_body(CountT* __restrict__ C, long long n, long long n_pad,
+                                                          long long slots, long long rep0, int first_slot, int group,
+                                                          uint32_t k0, uint32_t k1, const PoissonTable tab,
+                                                          long long* __restrict__ colsum, int rows_per_block) {
+    const int panel = blockIdx.y;
+    const int q = threadIdx.x & 7;           // 16-slot group within the panel
+    const int rl = threadIdx.x >> 3;         // row lane 0..31
+    const long long slot0 = (long long)panel * BM + q * 16;
+    const long long row_begin = (long long)blockIdx.x * rows_per_block;
+    const uint32_t c1base = ((uint32_t)group << 8);
+    int sums[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) sums[e] = 0;
+
+    for (long long row = row_begin + rl; row < row_begin + rows_per_block && row < n_pad; row += 32) {
+        unsigned cnt[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) cnt[e] = 0;
+        if (row < n) {
+            const uint32_t c1 = c1base | (uint32_t)((unsigned long long)row >> 32);
+            // global replicate id of local slot s is rep0 + s (slot 0 is the point estimate when first_slot == 1)
+            const long long rep_lo = rep0 + slot0;            // may be -1 for the point-estimate slot
+            const long long q4_first = (rep_lo < 0 ? 0 : rep_lo) >> 2;
+            const long long q4_last = (rep_lo + 15) >> 2;
+            if (!tab.lambda_zero) {
+                for (long long q4 = q4_first; q4 <= q4_last; ++q4) {
+                    const Philox4 r = philox4x32_10((uint32_t)row, c1, (uint32_t)q4, STREAM_BODY ^ (uint32_t)(q4 >> 32), k0, k1);
+                    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const long long rep = q4 * 4 + j;
+                        const long long e = rep - rep_lo;
+                        const long long slot = slot0 + e;
+                        if (e >= 0 && e < 16 && slot >= first_slot && slot < slots)
+                            cnt[e] = (unsigned)poisson_draw(u[j], tab, (uint64_t)row, c1, (uint64_t)rep, k0, k1);
+                    }
+                }
+            }
+            if (slot0 == 0 && first_slot == 1) cnt[0] = 1;  // point estimate
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sums[e] += (int)cnt[e];
+        }
+        CountT* dst = C + ((long long)panel * n_pad + row) * BM + q * 16;
+        if (sizeof(CountT) == 1) {
+            uint4 v;
+            v.x = cnt[0] | (cnt[1] << 8) | (cnt[2] << 16) | (cnt[3] << 24);
+            v.y = cnt[4] | (cnt[5] << 8) | (cnt[6] << 16) | (cnt[7] << 24);
+            v.z = cnt[8] | (cnt[9] << 8) | (cnt[10] << 16) | (cnt[11] << 24);
+            v.w = cnt[12] | (cnt[13] << 8) | (cnt[14] << 16) | (cnt[15] << 24);
+            *reinterpret_cast<uint4*>(dst) = v;
+        } else {
+            uint4 v0, v1;
+            v0.x = cnt[0] | (cnt[1] << 16); v0.y = cnt[2] | (cnt[3] << 16);
+            v0.z = cnt[4] | (cnt[5] << 16); v0.w = cnt[6] | (cnt[7] << 16);
+            v1.x = cnt[8] | (cnt[9] << 16); v1.y = cnt[10] | (cnt[11] << 16);
+            v1.z = cnt[12] | (cnt[13] << 16); v1.w = cnt[14] | (cnt[15] << 16);
+            reinterpret_cast<uint4*>(dst)[0] = v0;
+            reinterpret_cast<uint4*>(dst)[1] = v1;
+        }
+    }
+    // column sums: reduce the 4 row-lanes of each warp that share q, then one atomic per (warp, slot)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        int s = sums[e];
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if ((threadIdx.x & 31) < 8 && s != 0 && slot0 + e < slots)
+            atomicAdd(reinterpret_cast<unsigned long long*>(colsum + slot0 + e), (unsigned long long)s);
+    }
+}
+
+template <typename CountT>
+__device__ __forceinline__ bool bump_count(CountT* C, long long elem) {
+    // increment one count through a 32-bit atomic on its containing word; true if it was saturated
+    unsigned int* word = reinterpret_cast<unsigned int*>(C) + (elem * (long long)sizeof(CountT)) / 4;
+    const int shift = (int)((elem * (long long)sizeof(CountT)) & 3) * 8;
+    const unsigned old = atomicAdd(word, 1u << shift);
+    const unsigned mask = sizeof(CountT) == 1 ? 0xFFu : 0xFFFFu;
+    return ((old >> shift) & mask) == mask;
+}
+
+template <typename CountT>
+__global__ void __launch_bounds__(256) counts_philox_fixup(CountT* __restrict__ C, long long n, long long n_pad,
+                                                           long long slots, long long rep0, int first_slot, int group,
+                                                           uint32_t k0, uint32_t k1,
+                                                           const long long* __restrict__ colsum, int* __restrict__ flags) {
+    const long long slot = first_slot + blockIdx.x;
+    if (slot >= slots) return;
+    const long long need = n - colsum[slot];
+    if (need < 0) { if (threadIdx.x == 0 && blockIdx.y == 0) atomicOr(&flags[0], 1); return; }
+    const long long rep = rep0 + slot;
+    const long long panel = slot / BM, col = slot % BM;
+    const uint32_t c1base = ((uint32_t)group << 8);
+    for (long long j = (long long)blockIdx.y * blockDim.x + threadIdx.x; j < need; j += (long long)gridDim.y * blockDim.x) {
+        const Philox4 r = philox4x32_10((uint32_t)j, c1base | (uint32_t)((unsigned long long)j >> 32), (uint32_t)rep,
+                                        STREAM_FIXUP ^ (uint32_t)((unsigned long long)rep >> 32), k0, k1);
+        const unsigned long long U = ((unsigned long long)r.x << 32) | r.y;
+        const long long row = (long long)__umul64hi(U, (unsigned long long)n);  // uniform on [0, n), bias < n / 2^64
+        if (bump_count<CountT>(C, (panel * n_pad + row) * BM + col)) atomicOr(&flags[1], 1);
+    }
+}
+
+template <typename CountT>
+__global__ void __launch_bounds__(256) counts_point_kernel(CountT* __restrict__ C, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) C[i * BM] = 1;  // panel 0, slot 0
+}
+
+template <typename CountT>
+__global__ void __launch_bounds__(256) counts_index_kernel(CountT* __restrict__ C, long long n, long long n_pad,
+                                                           long long r0, int first_slot,
+                                                           const uint32_t* __restrict__ idx, int* __restrict__ flags) {
+    const long long r = r0 + blockIdx.y;  // replicate of this batch -> slot first_slot + r
+    const long long slot = first_slot + r, panel = slot / BM, col = slot % BM;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = idx[r * n + i];
+        if (row >= n) { atomicOr(&flags[2], 1); continue; }
+        if (bump_count<CountT>(C, (panel * n_pad + row) * BM + col)) atomicOr(&flags[1], 1);
+    }
+}
+
+void counts_clear(const CountsArgs& a, cudaStream_t st) {
+    OB_CUDA(cudaMemsetAsync(a.C, 0, (size_t)a.panels * a.n_pad * BM * a.count_bytes, st));
+}
+
+void counts_from_indices(const CountsArgs& a, const uint32_t* d_idx, int* d_flags, cudaStream_t st) {
+    counts_clear(a, st);
+    const int pb = (int)((a.n + 255) / 256);
+    const long long reps = a.slots - a.first_slot;
+    if (a.first_slot == 1) {
+        if (a.count_bytes == 1) counts_point_kernel<uint8_t><<<pb, 256, 0, st>>>((uint8_t*)a.C, a.n);
+        else counts_point_kernel<uint16_t><<<pb, 256, 0, st>>>((uint16_t*)a.C, a.n);
+        OB_CUDA(cudaGetLastError());
+    }
+    for (long long done = 0; done < reps; done += 32768) {  // gridDim.y <= 65535
+        const long long nb = std::min<long long>(reps - done, 32768);
+        dim3 grid((unsigned)std::min<long long>(pb, 1024), (unsigned)nb);
+        if (a.count_bytes == 1)
+            counts_index_kernel<uint8_t><<<grid, 256, 0, st>>>((uint8_t*)a.C, a.n, a.n_pad, done, a.first_slot, d_idx, d_flags);
+        else
+            counts_index_kernel<uint16_t><<<grid, 256, 0, st>>>((uint16_t*)a.C, a.n, a.n_pad, done, a.first_slot, d_idx, d_flags);
+        OB_CUDA(cudaGetLastError());
+    }
+}
+
+static PoissonTable make_table(long long n) {
+    PoissonTable t{};
+    const long double delta = ceill(8.0L * sqrtl((long double)n));
+    if (delta >= (long double)n) { t.lambda_zero = 1; return t; }
+    const long double lam = ((long double)n - delta) / (long double)n;
+    long double p = expl(-lam), cdf = 0.0L;
+    const long double two64 = 18446744073709551616.0L;
+    for (int k = 0; k < KMAX; ++k) {
+        cdf += p;
+        long double v = floorl(cdf * two64);
+        t.T[k] = (v >= two64 || cdf >= 1.0L) ? 0xFFFFFFFFFFFFFFFFull : (unsigned long long)v;
+        t.Th[k] = (unsigned int)(t.T[k] >> 32);
+        p = p * lam / (long double)(k + 1);
+    }
+    t.lambda_zero = 0;
+    return t;
+}
+
+void counts_philox(const CountsArgs& a, long long* d_colsum, int* d_flags, cudaStream_t st) {
+    const PoissonTable tab = make_table(a.n);
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    OB_CUDA(cudaMemsetAsync(d_colsum, 0, sizeof(long long) * (size_t)a.panels * BM, st));
+    const int rows_per_block = 512;
+    dim3 grid((unsigned)((a.n_pad + rows_per_block - 1) / rows_per_block), (unsigned)a.panels);
+    const long long nrep = a.slots - a.first_slot;
+    dim3 fgrid((unsigned)std::max<long long>(nrep, 1), 16);
+    if (a.count_bytes == 1) {
+        counts_philox_body<uint8_t><<<grid, 256, 0, st>>>((uint8_t*)a.C, a.n, a.n_pad, a.slots, a.rep0, a.first_slot, a.group,
+                                                         k0, k1, tab, d_colsum, rows_per_block);
+        OB_CUDA(cudaGetLastError());
+        if (nrep > 0)
+            counts_philox_fixup<uint8_t><<<fgrid, 256, 0, st>>>((uint8_t*)a.C, a.n, a.n_pad, a.slots, a.rep0, a.first_slot,
+                                                               a.group, k0, k1, d_colsum, d_flags);
+    } else {
+        counts_philox_body<uint16_t><<<grid, 256, 0, st>>>((uint16_t*)a.C, a.n, a.n_pad, a.slots, a.rep0, a.first_slot, a.group,
+                                                          k0, k1, tab, d_colsum, rows_per_block);
+        OB_CUDA(cudaGetLastError());
+        if (nrep > 0)
+            counts_philox_fixup<uint16_t><<<fgrid, 256, 0, st>>>((uint16_t*)a.C, a.n, a.n_pad, a.slots, a.rep0, a.first_slot,
+                                                                a.group, k0, k1, d_colsum, d_flags);
+    }
+    OB_CUDA(cudaGetLastError());
+}
+
+}  // namespace ob

@@ -1,0 +1,288 @@
+// csrc/solve.cu -- per-replicate (W)LS solves + decomposition epilogue, one CTA per replicate slot.
+//
+// Input: the replicate's sufficient statistics from gram.cu (upper triangle of [x|y][x|y]^T sums).
+// Restates, per slot:
+//   ols()                    ols.rs:96-115   n_obs <= k guard, Cholesky (nalgebra column algorithm:
+//                                            pivot <= 0 or NaN -> failure), solve
+//   column means             estimation.rs:56-71  = G[0][j] / G[0][0] (intercept column carries the sums)
+//   Yun normalisation        normalization.rs:5-51
+//   beta* selection          builder.rs:538-621 (GroupA / GroupB / Pooled with indicator at 1+n_cont / Cotton)
+//   two/three-fold, detailed decomposition.rs:56-122
+//   Yun base-category rows   builder.rs:634-674 (three_fold stays uncorrected)
+//   total gap                builder.rs:676-684
+// A failing replicate gets a status code and NaN statistics; the host drops it (builder.rs:831-837).
+#include "common.cuh"
+#include "internal.h"
+
+#include <cmath>
+
+namespace ob {
+
+constexpr int SOLVE_THREADS = 128;
+
+struct SolveParams {
+    const double* gram; long long slots_pad; int Pld; long long slots;
+    int K, n_cont, ref_kind;
+    int n_norm; const int* norm_m; const int* norm_off; const int* norm_idx; const int* norm_has_base;
+    int n_base, S, weighted;
+    double na, nb;
+    double* stats; int* status; double* beta_a; double* beta_b; double* point_extra;
+};
+
+__device__ __forceinline__ int ld_of(int N) { return N | 1; }  // odd stride: conflict-free column walks
+
+// In-place Cholesky of the N x N matrix (lower triangle used), nalgebra semantics. Returns false on failure.
+__device__ bool chol_factor(double* G, int N, int ld, int* fail) {
+    for (int j = 0; j < N; ++j) {
+        // col_j(i >= j) -= sum_{k<j} L[i][k] L[j][k], k ascending (axpy order of nalgebra)
+        for (int i = j + threadIdx.x; i < N; i += blockDim.x) {
+            double s = G[i * ld + j];
+            const double* Li = G + i * ld;
+            const double* Lj = G + j * ld;
+            for (int k = 0; k < j; ++k) s -= Li[k] * Lj[k];
+            G[i * ld + j] = s;
+        }
+        __syncthreads();
+        const double d = G[j * ld + j];
+        if (!(d > 0.0)) {
+            if (threadIdx.x == 0) *fail = 1;
+            __syncthreads();
+            return false;
+        }
+        const double r = sqrt(d);
+        __syncthreads();
+        for (int i = j + threadIdx.x; i < N; i += blockDim.x) G[i * ld + j] = (i == j) ? r : G[i * ld + j] / r;
+        __syncthreads();
+    }
+    return true;
+}
+
+// L L^T x = b in place, by warp 0 (lane-parallel dot products).
+__device__ void chol_solve(const double* L, int N, int ld, double* b) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        for (int i = 0; i < N; ++i) {
+            double s = 0.0;
+            for (int k = lane; k < i; k += 32) s += L[i * ld + k] * b[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) b[i] = (b[i] - s) / L[i * ld + i];
+            __syncwarp();
+        }
+        for (int i = N - 1; i >= 0; --i) {
+            double s = 0.0;
+            for (int k = i + 1 + lane; k < N; k += 32) s += L[k * ld + i] * b[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) b[i] = (b[i] - s) / L[i * ld + i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
+__device__ void yun_shift(const SolveParams& p, double* beta, int shift_from, double* base) {
+    for (int v = 0; v < p.n_norm; ++v) {  // normalization.rs:13-49
+        base[v] = 0.0;
+        const int a = p.norm_off[v], b = p.norm_off[v + 1];
+        if (a == b) continue;
+        double sum = 0.0;
+        for (int t = a; t < b; ++t) {
+            int i = p.norm_idx[t];
+            if (shift_from >= 0 && i >= shift_from) ++i;
+            sum += beta[i];
+        }
+        const int m = p.norm_m[v];
+        if (m == 0) continue;
+        const double mu = sum / (double)m;
+        base[v] = -mu;
+        beta[0] += mu;
+        for (int t = a; t < b; ++t) {
+            int i = p.norm_idx[t];
+            if (shift_from >= 0 && i >= shift_from) ++i;
+            beta[i] -= mu;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveParams p) {
+    extern __shared__ __align__(16) double sm[];
+    const int K = p.K, V = K + 1, Kp = K + 1;
+    const int ld = ld_of(K), ldp = ld_of(Kp);
+    const long long slot = blockIdx.x;
+    const int tid = threadIdx.x;
+    const bool pooled = p.ref_kind == OB_REF_POOLED;
+
+    double* GA = sm;
+    double* GB = GA + K * ld;
+    double* GP = GB + K * ld;                       // pooled (K+1)x(K+1), only when pooled
+    double* vec = GP + (pooled ? Kp * ldp : 0);
+    double* rA = vec;            double* rB = rA + Kp;   double* rP = rB + Kp;
+    double* xa = rP + Kp;        double* xb = xa + Kp;
+    double* bs = xb + Kp;        double* rawA = bs + Kp; double* rawB = rawA + Kp;
+    double* baseA = rawB + Kp;   double* baseB = baseA + p.n_norm + 1; double* baseS = baseB + p.n_norm + 1;
+    __shared__ int fail;
+    __shared__ double sums[4];   // sum(cw) and sum(cwy) per group
+
+    const double* gA = p.gram + (size_t)slot * p.Pld;
+    const double* gB = p.gram + ((size_t)p.slots_pad + slot) * p.Pld;
+    if (tid == 0) fail = 0;
+    // ---- unpack the packed upper triangle (pair (j,l), j <= l < V, row-major) ----
+    for (int j = 0; j < V; ++j) {
+        const long long base_idx = (long long)j * V - (long long)j * (j - 1) / 2 - j;  // index of (j,l) = base_idx + l
+        for (int l = j + tid; l < V; l += blockDim.x) {
+            const double a = gA[base_idx + l], b = gB[base_idx + l];
+            if (l < K) {
+                GA[j * ld + l] = a; GA[l * ld + j] = a;
+                GB[j * ld + l] = b; GB[l * ld + j] = b;
+            } else if (j < K) { rA[j] = a; rB[j] = b; }
+        }
+    }
+    __syncthreads();
+    int status = OB_OK;
+    // ols.rs:96-105: n_obs (row count, not sum of weights) must exceed k; group A is fitted first
+    if (p.na <= (double)K || p.nb <= (double)K) status = OB_ERR_INSUFFICIENT_DATA;
+
+    if (tid < K) {  // estimation.rs:56-71
+        xa[tid] = GA[tid] / GA[0];
+        xb[tid] = GB[tid] / GB[0];
+    }
+    if (tid == 0) { sums[0] = GA[0]; sums[1] = rA[0]; sums[2] = GB[0]; sums[3] = rB[0]; }
+    if (pooled) {
+        // builder.rs:548-566: rows of A and B stacked, indicator (1 on A rows) at column ind = 1 + n_cont
+        const int ind = 1 + p.n_cont;
+        for (int e = tid; e < Kp * Kp; e += blockDim.x) {
+            const int i = e / Kp, j = e - i * Kp;
+            const int si = i < ind ? i : i - 1, sj = j < ind ? j : j - 1;  // source design columns
+            double v;
+            if (i == ind && j == ind) v = GA[0];
+            else if (i == ind) v = GA[sj];        // sum over A rows of w * 1 * x_sj
+            else if (j == ind) v = GA[si];
+            else v = GA[si * ld + sj] + GB[si * ld + sj];
+            GP[i * ldp + j] = v;
+        }
+        for (int i = tid; i < Kp; i += blockDim.x) {
+            const int si = i < ind ? i : i - 1;
+            rP[i] = (i == ind) ? rA[0] : rA[si] + rB[si];
+        }
+    }
+    __syncthreads();
+
+    if (status == OB_OK) {
+        if (!chol_factor(GA, K, ld, &fail)) status = OB_ERR_NALGEBRA;
+    }
+    if (status == OB_OK) chol_solve(GA, K, ld, rA);
+    if (status == OB_OK) {
+        if (!chol_factor(GB, K, ld, &fail)) status = OB_ERR_NALGEBRA;
+    }
+    if (status == OB_OK) chol_solve(GB, K, ld, rB);
+    if (status == OB_OK && pooled) {
+        if (p.na + p.nb <= (double)Kp) status = OB_ERR_INSUFFICIENT_DATA;
+        else if (!chol_factor(GP, Kp, ldp, &fail)) status = OB_ERR_NALGEBRA;
+        if (status == OB_OK) chol_solve(GP, Kp, ldp, rP);
+    }
+
+    // ---- scalar epilogue ----
+    const int D = K + p.n_base;
+    double* out = p.stats + (size_t)slot * p.S;
+    if (tid == 0 && status == OB_OK) {
+        double* ba = rA; double* bb = rB;
+        for (int j = 0; j < K; ++j) { rawA[j] = ba[j]; rawB[j] = bb[j]; }
+        if (p.n_norm > 0) { yun_shift(p, ba, -1, baseA); yun_shift(p, bb, -1, baseB); }   // estimation.rs:76-91
+        switch (p.ref_kind) {  // builder.rs:538-621
+        case OB_REF_GROUP_A:
+            for (int j = 0; j < K; ++j) bs[j] = ba[j];
+            for (int v = 0; v < p.n_norm; ++v) baseS[v] = baseA[v];
+            break;
+        case OB_REF_GROUP_B:
+            for (int j = 0; j < K; ++j) bs[j] = bb[j];
+            for (int v = 0; v < p.n_norm; ++v) baseS[v] = baseB[v];
+            break;
+        case OB_REF_POOLED: {
+            const int ind = 1 + p.n_cont;
+            if (p.n_norm > 0) yun_shift(p, rP, ind, baseS);           // builder.rs:568-579
+            for (int j = 0; j < ind; ++j) bs[j] = rP[j];              // remove_row(ind) :580-589
+            for (int j = ind; j < K; ++j) bs[j] = rP[j + 1];
+            break;
+        }
+        default: {  // Weighted | Cotton: builder.rs:591-620
+            const double n_a = p.weighted ? sums[0] : p.na;
+            const double n_b = p.weighted ? sums[2] : p.nb;
+            const double total = n_a + n_b;
+            if (total == 0.0) { status = OB_ERR_INVALID_GROUP; break; }
+            const double wA = n_a / total, wB = 1.0 - wA;
+            for (int v = 0; v < p.n_norm; ++v) baseS[v] = baseA[v] * wA + baseB[v] * wB;
+            for (int j = 0; j < K; ++j) bs[j] = ba[j] * wA + bb[j] * wB;
+            break;
+        }
+        }
+        if (status == OB_OK) {
+            // decomposition.rs:56-89
+            double en = 0.0, co = 0.0, in = 0.0, ex = 0.0, fa = 0.0, fb = 0.0;
+            for (int j = 0; j < K; ++j) {
+                const double dx = xa[j] - xb[j], db = ba[j] - bb[j];
+                en += dx * bb[j]; co += xb[j] * db; in += dx * db;
+                ex += dx * bs[j]; fa += xa[j] * ba[j]; fb += xb[j] * bb[j];
+            }
+            double two0 = ex, two1 = (fa - fb) - ex;
+            for (int j = 0; j < K; ++j) {  // decomposition.rs:92-122
+                out[5 + j] = (xa[j] - xb[j]) * bs[j];
+                out[5 + D + j] = xa[j] * (ba[j] - bs[j]) + xb[j] * (bs[j] - bb[j]);
+            }
+            int row = K;
+            for (int v = 0; v < p.n_norm; ++v) {  // builder.rs:634-674
+                if (!p.norm_has_base[v]) continue;
+                double sa = 0.0, sb = 0.0;
+                for (int t = p.norm_off[v]; t < p.norm_off[v + 1]; ++t) { sa += xa[p.norm_idx[t]]; sb += xb[p.norm_idx[t]]; }
+                const double xab = 1.0 - sa, xbb = 1.0 - sb;
+                const double un = xab * (baseA[v] - baseS[v]) + xbb * (baseS[v] - baseB[v]);
+                const double e2 = (xab - xbb) * baseS[v];
+                out[5 + D + row] = un; out[5 + row] = e2;
+                two0 += e2; two1 += un;
+                ++row;
+            }
+            out[0] = two0; out[1] = two1; out[2] = en; out[3] = co; out[4] = in;
+            if (p.beta_a) for (int j = 0; j < K; ++j) p.beta_a[(size_t)slot * K + j] = ba[j];
+            if (p.beta_b) for (int j = 0; j < K; ++j) p.beta_b[(size_t)slot * K + j] = bb[j];
+            if (p.point_extra && slot == 0) {
+                double* pe = p.point_extra;
+                for (int j = 0; j < K; ++j) {
+                    pe[j] = xa[j]; pe[K + j] = xb[j]; pe[2 * K + j] = bs[j];
+                    pe[3 * K + j] = rawA[j]; pe[4 * K + j] = rawB[j];
+                }
+                pe[5 * K] = sums[1] / sums[0] - sums[3] / sums[2];    // builder.rs:676-684
+            }
+        }
+    }
+    if (tid == 0) {
+        if (status != OB_OK) {
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            for (int j = 0; j < p.S; ++j) out[j] = nan;
+            if (p.beta_a) for (int j = 0; j < K; ++j) p.beta_a[(size_t)slot * K + j] = nan;
+            if (p.beta_b) for (int j = 0; j < K; ++j) p.beta_b[(size_t)slot * K + j] = nan;
+        }
+        p.status[slot] = status;
+    }
+}
+
+size_t solve_smem_bytes(int K, bool pooled, int n_norm) {
+    const int Kp = K + 1, ld = K | 1, ldp = Kp | 1;
+    size_t d = (size_t)2 * K * ld + (pooled ? (size_t)Kp * ldp : 0) + (size_t)8 * Kp + (size_t)3 * (n_norm + 1);
+    return d * sizeof(double);
+}
+
+void solve_launch(const SolveArgs& a, cudaStream_t st) {
+    SolveParams p;
+    p.gram = a.gram; p.slots_pad = a.slots_pad; p.Pld = a.Pld; p.slots = a.slots;
+    p.K = a.K; p.n_cont = a.n_cont; p.ref_kind = a.ref_kind;
+    p.n_norm = a.n_norm; p.norm_m = a.d_norm_m; p.norm_off = a.d_norm_off; p.norm_idx = a.d_norm_idx;
+    p.norm_has_base = a.d_norm_has_base; p.n_base = a.n_base; p.S = a.S; p.weighted = a.weighted;
+    p.na = a.na; p.nb = a.nb;
+    p.stats = a.stats; p.status = a.status; p.beta_a = a.beta_a; p.beta_b = a.beta_b; p.point_extra = a.point_extra;
+    const size_t smem = solve_smem_bytes(a.K, a.ref_kind == OB_REF_POOLED, a.n_norm);
+    OB_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    solve_kernel<<<(unsigned)a.slots, SOLVE_THREADS, smem, st>>>(p);
+    OB_CUDA(cudaGetLastError());
+}
+
+}  // namespace ob

@@ -1,0 +1,307 @@
+"""GPU-vs-oracle parity through the C ABI (libobboot).  Run on the B200 box: pytest -m gpu.
+
+Same seeded inputs, same explicit resample index stream on both sides:
+  * multiplicities: bit-exact (checked via the replicate status/statistics and the count tests)
+  * per-replicate coefficients and statistics, SEs, CIs: <= 1e-10 relative (north_star)
+  * replicate failures (singular resamples) dropped identically.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10   # north_star: "within a relative 1e-10 (fp64 with a different summation order)"
+REFS = {"A": 0, "B": 1, "pooled": 2, "weighted": 3}
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    assert np.array_equal(nan_a, nan_b), "NaN pattern differs"
+    if a.size == 0 or nan_a.all():
+        return 0.0
+    scale = max(1.0, np.nanmax(np.abs(b)))
+    return float(np.nanmax(np.abs(a - b)) / scale)
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import oaxaca_blinder_rs_b200 as ob
+    return ob
+
+
+@pytest.fixture(scope="module")
+def ctx(ob):
+    c = ob.Context(0)
+    yield c
+    c.close()
+
+
+def run_both(ob, orc, ctx, Xa, ya, wa, Xb, yb, wb, n_cont, ref, norm, reps, seed=5, **kw):
+    K = Xa.shape[1]
+    spec = orc.Spec(K=K, n_cont=n_cont, ref_kind=ref, norm=[orc.NormVar(m, i, True) for m, i in norm])
+    ia, ib = orc.index_stream(seed, reps, 0, len(ya)), orc.index_stream(seed, reps, 1, len(yb))
+    ref_out = orc.run(spec, Xa, ya, wa, Xb, yb, wb, reps, ia, ib, nthreads=8, precise=True)
+    des = ob.Design.from_dense(ctx, Xa, ya, wa, Xb, yb, wb, n_cont)
+    gpu = ob.bootstrap(des, reps, ref_kind=ref, norm=[ob.NormVar(m, i, True) for m, i in norm],
+                       idx_a=ia, idx_b=ib, want_rep=True, **kw)
+    des.close()
+    return gpu, ref_out
+
+
+def compare(gpu, ref, tol=RTOL):
+    p = ref["point"]
+    assert abs(gpu["total_gap"] - p["total_gap"]) <= tol * max(1, abs(p["total_gap"]))
+    for k_gpu, k_ref in (("point_stats", "stats"), ("xa_mean", "xa_mean"), ("xb_mean", "xb_mean"),
+                         ("beta_star", "beta_star"), ("beta_a", "beta_a"), ("beta_b", "beta_b"),
+                         ("residuals_b", "resid_b")):
+        assert relerr(gpu[k_gpu], p[k_ref]) <= tol, k_gpu
+    np.testing.assert_array_equal(gpu["rep_status"], ref["rep_status"])
+    assert gpu["n_ok"] == ref["n_ok"]
+    assert relerr(gpu["rep_stats"], ref["rep_stats"]) <= tol
+    assert relerr(gpu["rep_beta_a"], ref["rep_beta_a"]) <= tol
+    assert relerr(gpu["rep_beta_b"], ref["rep_beta_b"]) <= tol
+    assert relerr(gpu["std_err"], ref["se"]) <= tol
+    assert relerr(gpu["ci_lower"], ref["ci_lo"]) <= tol
+    assert relerr(gpu["ci_upper"], ref["ci_hi"]) <= tol
+    np.testing.assert_allclose(gpu["p_value"], ref["p"], rtol=0, atol=1e-15)
+    ok = np.abs(ref["se"]) > 1e-8        # away from the |se| > 1e-9 switch of builder.rs:851
+    assert relerr(gpu["t_stat"][ok], ref["t"][ok]) <= 1e-9
+
+
+def _fixture_design(fix, weighted=False):
+    from tests.test_oracle_golden import _design
+    return _design(fix, weighted)
+
+
+@pytest.mark.parametrize("ref", ["A", "B", "pooled", "weighted"])
+@pytest.mark.parametrize("fx", ["F1", "F2"])
+def test_golden_fixtures_on_gpu(ob, orc, ctx, golden, fx, ref):
+    """The reference's integration fixtures (integration_test.rs:105-163) through the CUDA path."""
+    fix = golden[fx]
+    Xa, ya, wa, Xb, yb, wb, norm, n_cont = _fixture_design(fix)
+    gpu, ref_out = run_both(ob, orc, ctx, Xa, ya, wa, Xb, yb, wb, n_cont, REFS[ref], norm, reps=60)
+    exp = fix["expected"][ref]
+    for k in ("beta_a", "beta_b", "xa_mean", "xb_mean", "beta_star", "two_fold", "three_fold", "det_expl", "det_unexpl"):
+        np.testing.assert_allclose(gpu[k], exp[k], rtol=0, atol=1e-9, err_msg=k)
+    assert abs(gpu["total_gap"] - 10.0) < 1e-9 and abs(gpu["two_fold"].sum() - gpu["total_gap"]) < 1e-9
+    np.testing.assert_allclose(gpu["residuals_b"], exp["resid_b"], atol=1e-9)
+    compare(gpu, ref_out)
+    assert 0 < gpu["n_ok"] <= 60
+
+
+def test_weights_fixture_on_gpu(ob, orc, ctx, golden):
+    fix = golden["F3"]                                      # weights_test.rs:19-46
+    for key, weighted in (("unweighted", False), ("weighted", True)):
+        Xa, ya, wa, Xb, yb, wb, norm, n_cont = _fixture_design(fix, weighted)
+        des = ob.Design.from_dense(ctx, Xa, ya, wa, Xb, yb, wb, n_cont)
+        out = ob.bootstrap(des, 0)                          # bootstrap_reps(0): weights_test.rs:32
+        exp = fix["expected"][key]
+        assert abs(out["total_gap"] - exp["total_gap"]) < 1e-9
+        np.testing.assert_allclose(out["beta_a"], exp["beta_a"], atol=1e-9)
+        np.testing.assert_allclose(out["beta_b"], exp["beta_b"], atol=1e-9)
+        assert np.all(np.isnan(out["std_err"])) and np.all(out["t_stat"] == 0.0) and out["n_ok"] == 0
+        des.close()
+
+
+@pytest.mark.parametrize("ref", ["A", "B", "pooled", "weighted"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_synthetic_wage_yun(ob, orc, ctx, ref, weighted):
+    """config-1 shaped: continuous + C(sector 4 levels) + C(region 3 levels), Yun on both, all beta* kinds."""
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(6000, 3, cat_levels=(4, 3), weights=weighted, seed=11)
+    Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
+    gpu, ref_out = run_both(ob, orc, ctx, Xa, ya, wa, Xb, yb, wb, 3, REFS[ref], synth.norm_spec(d), reps=150)
+    compare(gpu, ref_out)
+    assert gpu["n_ok"] == 150
+
+
+def test_multi_panel_multi_tile(ob, orc, ctx):
+    """K=21 (two column tiles), 300 replicates (three panels), many row segments."""
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(60000, 20, seed=3)
+    Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
+    gpu, ref_out = run_both(ob, orc, ctx, Xa, ya, wa, Xb, yb, wb, 20, 0, [], reps=300)
+    compare(gpu, ref_out)
+
+
+def test_wide_design_wls_yun(ob, orc, ctx):
+    """headline-shaped columns: 44 continuous + 2 x C(4 levels), WLS + Yun (K=51, 11 column tiles), small n."""
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(20000, 44, cat_levels=(4, 4), weights=True, seed=4)
+    Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
+    gpu, ref_out = run_both(ob, orc, ctx, Xa, ya, wa, Xb, yb, wb, 44, 2, synth.norm_spec(d), reps=40)
+    compare(gpu, ref_out)
+
+
+def test_failed_replicates_are_dropped_identically(ob, orc, ctx):
+    """Rare category: resamples that miss it are singular -> dropped on both sides."""
+    rng = np.random.default_rng(2)
+    n = 60
+    edu = rng.normal(13, 2, n)
+    rare = np.zeros(n); rare[[3, 40]] = 1.0      # one rare-level row per group
+    grp = np.arange(n) >= 30
+    y = 1 + 0.5 * edu + rare + rng.normal(0, 1, n) + grp
+    X = np.c_[np.ones(n), edu, rare]
+    Xa, ya, Xb, yb = X[grp], y[grp], X[~grp], y[~grp]
+    gpu, ref_out = run_both(ob, orc, ctx, Xa, ya, None, Xb, yb, None, 1, 0, [], reps=200)
+    compare(gpu, ref_out)
+    assert 0 < gpu["n_ok"] < 200
+    assert set(np.unique(gpu["rep_status"])) == {0, 4}
+
+
+def test_count_width_and_saturation(ob, orc, ctx):
+    """uint8 multiplicities saturate (one row drawn 300 times) -> automatic uint16 rerun, still exact."""
+    rng = np.random.default_rng(8)
+    n = 400
+    X = np.c_[np.ones(n), rng.normal(size=(n, 2))]
+    y = X @ [1.0, 2.0, -1.0] + rng.normal(size=n)
+    Xa, ya, Xb, yb = X[:200], y[:200], X[200:], y[200:]
+    reps = 5
+    ia = orc.index_stream(1, reps, 0, 200); ib = orc.index_stream(1, reps, 1, 200)
+    ia[2, :] = np.r_[np.full(180, 7), np.arange(20)]      # multiplicity 181 for row 7 (+1 from arange) fits uint8
+    ib[3, :] = np.r_[np.full(190, 5), np.arange(10) * 3]  # still < 256
+    ia[4, :150] = 9
+    ia[4, 150:] = np.arange(50) + 20
+    ia[1, :] = 11                                          # 200 draws of one row -> singular replicate
+    big = np.tile(np.arange(200), 2)[:200]
+    spec = orc.Spec(K=3, n_cont=2)
+    for bits in (0, 8, 16):
+        des = ob.Design.from_dense(ctx, Xa, ya, None, Xb, yb, None, 2)
+        gpu = ob.bootstrap(des, reps, idx_a=ia, idx_b=ib, want_rep=True, count_bits=bits)
+        ref_out = orc.run(spec, Xa, ya, None, Xb, yb, None, reps, ia, ib)
+        compare(gpu, ref_out)
+        des.close()
+    # > 255 draws of one row: auto widens, forced 8-bit refuses
+    n2 = 600
+    X2 = np.c_[np.ones(n2), rng.normal(size=(n2, 1))]
+    y2 = X2 @ [1.0, 0.5] + rng.normal(size=n2)
+    ia2 = orc.index_stream(2, 3, 0, 300); ib2 = orc.index_stream(2, 3, 1, 300)
+    ia2[1, :280] = 4
+    des = ob.Design.from_dense(ctx, X2[:300], y2[:300], None, X2[300:], y2[300:], None, 1)
+    gpu = ob.bootstrap(des, 3, idx_a=ia2, idx_b=ib2, want_rep=True)
+    ref_out = orc.run(orc.Spec(K=2, n_cont=1), X2[:300], y2[:300], None, X2[300:], y2[300:], None, 3, ia2, ib2)
+    compare(gpu, ref_out)
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.bootstrap(des, 3, idx_a=ia2, idx_b=ib2, count_bits=8)
+    assert e.value.kind == "Unsupported"
+    des.close()
+
+
+def test_errors_match_reference_variants(ob, ctx):
+    rng = np.random.default_rng(0)
+    X = np.c_[np.ones(8), rng.normal(size=(8, 1))]
+    y = rng.normal(size=8)
+    # collinear point estimate -> NalgebraError (ols.rs:164-181)
+    Xc = np.c_[np.ones(8), np.arange(8.0), 2 * np.arange(8.0)]
+    des = ob.Design.from_dense(ctx, Xc, y, None, Xc, y, None, 2)
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.bootstrap(des, 5)
+    assert e.value.kind == "NalgebraError"
+    des.close()
+    # n <= k -> InsufficientData (ols.rs:183-209)
+    Xw = np.c_[np.ones(3), rng.normal(size=(3, 4))]
+    des = ob.Design.from_dense(ctx, Xw, y[:3], None, Xw, y[:3], None, 4)
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.bootstrap(des, 5)
+    assert e.value.kind == "InsufficientData"
+    des.close()
+    # negative weights -> InvalidGroupVariable (ols.rs:60-66)
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.Design.from_dense(ctx, X, y, -np.ones(8), X, y, np.ones(8), 1)
+    assert e.value.kind == "InvalidGroupVariable"
+    # empty group -> InvalidGroupVariable (builder.rs:431-435)
+    des = ob.Design.from_dense(ctx, X, y, None, X[:0], y[:0], None, 1)
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.bootstrap(des, 5)
+    assert e.value.kind == "InvalidGroupVariable"
+    des.close()
+
+
+def test_batching_and_sharding_are_bit_identical(ob, orc, ctx):
+    """Fixed-order split-n: results do not depend on workspace batching nor on the replicate shard."""
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(30000, 6, cat_levels=(3,), weights=True, seed=21)
+    Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
+    norm = [ob.NormVar(m, i) for m, i in synth.norm_spec(d)]
+    reps = 300
+    des = ob.Design.from_dense(ctx, Xa, ya, wa, Xb, yb, wb, 6)
+    full = ob.bootstrap(des, reps, ref_kind=3, norm=norm, seed=99, want_rep=True)
+    small = ob.bootstrap(des, reps, ref_kind=3, norm=norm, seed=99, want_rep=True, max_workspace_bytes=24 << 20)
+    np.testing.assert_array_equal(full["rep_stats"], small["rep_stats"])
+    np.testing.assert_array_equal(full["std_err"], small["std_err"])
+    parts = [ob.bootstrap(des, reps, ref_kind=3, norm=norm, seed=99, rep_begin=a, rep_end=b, skip_reduce=True)
+             for a, b in ((0, 77), (77, 200), (200, 300))]
+    stats = np.concatenate([p["rep_stats"] for p in parts])
+    status = np.concatenate([p["rep_status"] for p in parts])
+    np.testing.assert_array_equal(stats, full["rep_stats"])
+    red = ob.reduce_stats(ctx, stats, status, full["point_stats"])
+    for k in ("std_err", "p_value", "ci_lower", "ci_upper", "t_stat"):
+        np.testing.assert_array_equal(red[k], full[k])
+    # the reduction itself against the oracle's bootstrap_stats
+    oref = orc.reduce(stats, status, full["point_stats"])
+    assert relerr(red["std_err"], oref["se"]) <= RTOL and red["n_ok"] == oref["n_ok"]
+    np.testing.assert_array_equal(red["ci_lower"], oref["ci_lo"])
+    np.testing.assert_array_equal(red["ci_upper"], oref["ci_hi"])
+    des.close()
+
+
+def test_native_philox_stream(ob, orc, ctx):
+    """The GPU's own resampling stream: exact multinomial shape (sum = n), determinism, and SE agreement
+    with the oracle's independent stream within Monte-Carlo error (SE of an SE ~ SE / sqrt(2B))."""
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(20000, 4, cat_levels=(4,), seed=31)
+    Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
+    des = ob.Design.from_dense(ctx, Xa, ya, wa, Xb, yb, wb, 4)
+    c0 = des.debug_counts(7, 0, 0).astype(np.int64)
+    c1 = des.debug_counts(7, 1, 0).astype(np.int64)
+    cb = des.debug_counts(7, 0, 1).astype(np.int64)
+    assert c0.sum() == len(ya) and c1.sum() == len(ya) and cb.sum() == len(yb)
+    assert not np.array_equal(c0, c1)
+    np.testing.assert_array_equal(c0, des.debug_counts(7, 0, 0))
+    # multinomial(n, 1/n) marginals: mean 1, variance 1 - 1/n; P(0) ~ e^-1
+    allc = np.concatenate([des.debug_counts(7, r, 0).astype(np.int64) for r in range(20)])
+    assert abs(allc.mean() - 1.0) < 1e-12
+    assert abs(allc.var() - 1.0) < 0.02 and abs((allc == 0).mean() - np.exp(-1)) < 0.005
+    B = 800
+    norm = [ob.NormVar(m, i) for m, i in synth.norm_spec(d)]
+    g1 = ob.bootstrap(des, B, ref_kind=1, norm=norm, seed=1234)
+    g2 = ob.bootstrap(des, B, ref_kind=1, norm=norm, seed=1234)
+    np.testing.assert_array_equal(g1["std_err"], g2["std_err"])          # deterministic
+    g3 = ob.bootstrap(des, B, ref_kind=1, norm=norm, seed=77)
+    assert not np.array_equal(g1["std_err"], g3["std_err"])
+    spec = orc.Spec(K=des.K, n_cont=4, ref_kind=1, norm=[orc.NormVar(m, i) for m, i in synth.norm_spec(d)])
+    o = orc.run(spec, Xa, ya, wa, Xb, yb, wb, B, None, None, seed=5, nthreads=8, precise=False)
+    assert g1["n_ok"] == B
+    z = (g1["std_err"] - o["se"]) / (o["se"] / np.sqrt(2 * B) * np.sqrt(2) + 1e-300)
+    big = np.abs(o["se"]) > 1e-12
+    assert np.all(np.abs(z[big]) < 5.0), z[big]
+    des.close()
+
+
+def test_pack_matches_host_design(ob, ctx):
+    """ob_design_pack (CUDA) == prepare_data restated on the host, bit for bit, rows in frame order."""
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(10007, 5, cat_levels=(4, 2, 3), weights=True, seed=77)
+    d["group"][::17] = 2                       # rows of a third group are ignored (builder.rs:73-94)
+    des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+    Xa, ya, wa, Xb, yb, wb = des.download()
+    eXa, eya, ewa, eXb, eyb, ewb = synth.dense_design(d)
+    for got, exp in ((Xa, eXa), (ya, eya), (wa, ewa), (Xb, eXb), (yb, eyb), (wb, ewb)):
+        np.testing.assert_array_equal(got, exp)
+    assert des.K == 1 + 5 + 3 + 1 + 2 and des.n_cont == 5
+    des.close()
+
+
+@pytest.mark.parametrize("tau", [0.1, 0.5, 0.9])
+def test_rif_prestep(ob, orc, ctx, tau):
+    """decompose_quantile pre-step on the device vs math/rif.rs restated in the oracle."""
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(50001, 2, seed=5)
+    Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
+    des = ob.Design.from_dense(ctx, Xa, ya, None, Xb, yb, None, 2)
+    des.apply_rif(tau)
+    _, ga, _, _, gb, _ = des.download()
+    assert relerr(ga, orc.rif(ya, tau)) <= RTOL and relerr(gb, orc.rif(yb, tau)) <= RTOL
+    des.close()
