@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py -- bootstrap replicates/sec of the B200-native oaxaca_blinder bootstrap path.
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): synthetic wage data,
+n = 10M rows, k = 50 predictors (44 continuous + C(sector) + C(region), 4 levels each -> K = 51 design
+columns), sample weights (WLS), Yun normalisation of both categoricals, B = 2000 bootstrap replicates.
+A "step" is one full bootstrap (point estimate + 2000 replicates + SE/CI reduction).
+
+  value  reps/s with the packed design already resident in HBM (ob_bootstrap_run only)
+  e2e    reps/s through the C ABI from pinned HOST columns: H2D + pack + bootstrap + results D2H per step
+  roofline     Gram contraction kernel: algorithmic 2*n*P*B flop / its CUDA-event time vs the FP64 DMMA peak
+  cpu_baseline the oracle port (reference-shaped CPU restatement) on the box's host cores, bounded sample
+
+--impl reference times that CPU restatement on all host threads (the Rust reference cannot be built here:
+no cargo/rustc in the image, dependencies not vendored).  N > 1: one rank per GPU (torchrun), replicates
+sharded, one NCCL all-gather of the statistics block, reduction on every rank; total work fixed -> strong.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n, n_cont, cat_levels, weights, normalize, reps, ref_kind)
+    "config3_n10M_k50_wls_yun_B2000": (10_000_000, 44, (4, 4), True, True, 2000, 0),
+    "config2_n1M_k20_B1000": (1_000_000, 20, (), False, False, 1000, 0),
+    "smoke_n200k_k50_B256": (200_000, 44, (4, 4), True, True, 256, 0),
+}
+FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool (profiles/r01_fp64_peaks.json): DMMA.8x8x4 issue peak
+FP64_CUBLAS_DGEMM_TFLOPS = 35.4  # measured on this pool (profiles/r01_dgemm_peak.json): cuBLAS DGEMM 8192^3
+
+
+def algorithmic_flops(n, K, reps):
+    P = K * (K + 1) // 2 + K      # F_rep = 2 n P, P = K(K+1)/2 + K
+    return 2.0 * n * P * reps, P
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.stop_flag = threading.Event()
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_data(name):
+    from oaxaca_blinder_rs_b200 import synth
+    n, n_cont, cats, weights, normalize, reps, ref = WORKLOADS[name]
+    d = synth.make_wage(n, n_cont, cat_levels=cats, weights=weights)
+    norm = synth.norm_spec(d) if normalize else []
+    return d, norm, reps, ref
+
+
+def cpu_baseline(d, norm, ref, threads, reps_cpu):
+    """Times the oracle port (reference-shaped arithmetic) on `threads` host threads over reps_cpu replicates."""
+    from oracle import pyoracle as orc
+    from oaxaca_blinder_rs_b200 import synth
+    Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
+    K = Xa.shape[1]
+    spec = orc.Spec(K=K, n_cont=len(d["cont"]), ref_kind=ref, norm=[orc.NormVar(m, i) for m, i in norm])
+    t0 = time.perf_counter()
+    out = orc.run(spec, Xa, ya, wa, Xb, yb, wb, reps_cpu, None, None, seed=1, nthreads=threads, precise=False, want_rep=False)
+    dt = time.perf_counter() - t0
+    # the point pass is part of run(); per-replicate cost is independent of B -> reps/s over (reps_cpu + 1) passes
+    return (reps_cpu + 1) / dt, dt, out["n_ok"]
+
+
+def host_threads_and_sample(d, K):
+    import psutil
+    cores = os.cpu_count() or 1
+    per_thread = d["n"] * K * 8 * (2.2 if d["weights"] is not None else 1.2)     # gathered copy (+ sqrt(w)-scaled copy)
+    avail = psutil.virtual_memory().available
+    dense = d["n"] * K * 8 * 1.3
+    threads = int(max(1, min(cores, (0.7 * avail - dense) // per_thread)))
+    return cores, threads
+
+
+def run_reference(args, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d, norm, reps, ref = make_data(name)
+    K = 1 + len(d["cont"]) + sum(m - 1 for m in d["cat_levels"])
+    cores, threads = host_threads_and_sample(d, K)
+    reps_cpu = max(threads - 1, 1)          # + the point pass = `threads` passes, one per thread
+    vals = []
+    for it in range(args.warmup + args.steps):
+        v, dt, _ = cpu_baseline(d, norm, ref, threads, reps_cpu)
+        if it >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals])) * 1e3
+    sample = f"{reps_cpu} replicates + point pass per step on {threads} OpenMP threads (of {cores} cores), full n"
+    line = {"impl": "reference", "metric": "bootstrap_reps_per_sec", "value": value, "unit": "reps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "n": d["n"], "k": K - 1, "reps": reps, "wls": d["weights"] is not None,
+                       "yun": bool(norm)},
+            "cpu_baseline": {"value": value, "unit": "reps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "reps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU restatement of the reference algorithm (oracle port), not the Rust binary"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config3_n10M_k50_wls_yun_B2000", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    name = args.workload
+    if args.impl == "reference":
+        return run_reference(args, name)
+
+    import torch
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import distributed as obd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU path. Use --impl reference for the CPU baseline.")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    d, norm, reps, ref = make_data(name)
+    n = d["n"]
+    K = 1 + len(d["cont"]) + sum(m - 1 for m in d["cat_levels"])
+    normv = [ob.NormVar(m, i) for m, i in norm]
+    ctx = ob.Context(local)
+
+    # pinned host columns for the end-to-end leg
+    def pin(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(a[:1]).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    pinned = dict(cont=[pin(c) for c in d["cont"]], cat=[pin(c) for c in d["cat_codes"]], y=pin(d["outcome"]),
+                  w=pin(d["weights"]) if d["weights"] is not None else None, g=pin(d["group"]))
+    h2d = sum(t.numel() * t.element_size() for t in pinned["cont"] + pinned["cat"] + [pinned["y"], pinned["g"]]
+              + ([pinned["w"]] if pinned["w"] is not None else []))
+
+    def pack():
+        return ob.Design.pack(ctx, [t.numpy() for t in pinned["cont"]], [t.numpy() for t in pinned["cat"]],
+                              d["cat_levels"], pinned["y"].numpy(), None if pinned["w"] is None else pinned["w"].numpy(),
+                              pinned["g"].numpy())
+
+    def step(design):
+        if world == 1:
+            return ob.bootstrap(design, reps, ref_kind=ref, norm=normv, seed=2026)
+        return obd.bootstrap_sharded(design, reps, device=torch.device("cuda", local), ref_kind=ref, norm=normv, seed=2026)
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    design = pack()
+    for _ in range(args.warmup):
+        out = step(design)
+
+    # ---- device-resident leg: K steps, CUDA events on the library's stream are summed inside (ms_total);
+    #      the wall bracket below (barrier + synchronize on both sides) is what is reported ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    sync()
+    t0 = time.perf_counter()
+    gram_ms, total_ms, launches = [], [], 0
+    for _ in range(args.steps):
+        out = step(design)
+        gram_ms.append(out["timings_ms"]["gram_main"] if "gram_main" in out["timings_ms"] else out["timings_ms"]["gram"])
+        total_ms.append(out["timings_ms"]["total"])
+        launches += out["gpu_launches"]
+    sync()
+    dt = time.perf_counter() - t0
+    sampler.stop_flag.set()
+    sampler.join()
+    design.close()
+
+    # ---- end-to-end leg: pinned host columns -> H2D + pack + bootstrap + D2H, every step ----
+    sync()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        dsg = pack()
+        out_e = step(dsg)
+        dsg.close()
+    sync()
+    dt_e = time.perf_counter() - t1
+    S = out["S"]
+    d2h = 8 * (S * 6 + 3 * K + 1) + 8 * out["residuals_b"].size
+
+    times = torch.tensor([dt, dt_e], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dt, dt_e = times.tolist()
+
+    if rank == 0:
+        flops, P = algorithmic_flops(n, K, reps)
+        flops_rank = flops / world                        # replicates are sharded: per-launch algorithmic work
+        g_ms = float(np.mean(gram_ms))
+        achieved = flops_rank / (g_ms * 1e-3) / 1e12
+        line = {"metric": "bootstrap_reps_per_sec", "value": reps * args.steps / dt, "unit": "reps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": name, "n": n, "k": K - 1, "K": K, "P": P, "reps": reps,
+                           "wls": d["weights"] is not None, "yun": bool(norm), "parallelism": f"replicate-shard x{world}",
+                           "l2": "inputs larger than L2 (design 4.2 GB, multiplicities 20 GB per step)"},
+                "e2e": {"value": reps * args.steps / dt_e, "unit": "reps/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "tensor", "kernel": "gram_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
+                             "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
+                             "frac_of_cublas_dgemm": achieved / FP64_CUBLAS_DGEMM_TFLOPS,
+                             "peak_source": "measured on this pool: FP64 DMMA issue peak, profiles/r01_fp64_peaks.json "
+                                            "(MEASURED_PEAKS.json has no fp64 entry); cuBLAS DGEMM 35.4",
+                             "launch_ms": g_ms, "flop_per_launch": flops_rank, "traffic": None},
+                "stage_ms": {k: float(v) for k, v in out["timings_ms"].items()},
+                "clocks": sampler.summary(),
+                "n_ok": int(out["n_ok"])}
+        if world == 1 and not args.no_cpu_baseline:
+            cores, threads = host_threads_and_sample(d, K)
+            reps_cpu = max(threads - 1, 1)
+            v, cdt, _ = cpu_baseline(d, norm, ref, threads, reps_cpu)
+            line["cpu_baseline"] = {"value": v, "unit": "reps/s", "cores": threads, "kind": "port",
+                                    "sample": f"{reps_cpu} replicates + point pass, full n, {cdt:.1f} s on {threads} of {cores} cores"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

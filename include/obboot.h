@@ -142,6 +142,7 @@ typedef struct ob_result {
     double* rep_beta_b;      /* [rows x K] */
     /* device timings of the last call, milliseconds (CUDA events) */
     double ms_counts, ms_gram, ms_solve, ms_reduce, ms_total;
+    double ms_gram_kernel;   /* the DMMA contraction kernel alone (ms_gram also covers the split-n partial reduction) */
     int32_t gpu_launches;    /* kernels launched by this call */
 } ob_result;
 

@@ -43,7 +43,8 @@ class Result(C.Structure):
                 ("n_ok", C.c_int64), ("std_err", _DP), ("p_value", _DP), ("ci_lower", _DP), ("ci_upper", _DP),
                 ("t_stat", _DP), ("rep_stats", _DP), ("rep_status", _IP), ("rep_beta_a", _DP), ("rep_beta_b", _DP),
                 ("ms_counts", C.c_double), ("ms_gram", C.c_double), ("ms_solve", C.c_double),
-                ("ms_reduce", C.c_double), ("ms_total", C.c_double), ("gpu_launches", C.c_int32)]
+                ("ms_reduce", C.c_double), ("ms_total", C.c_double), ("ms_gram_kernel", C.c_double),
+                ("gpu_launches", C.c_int32)]
 
 
 def build(force: bool = False) -> str:

@@ -194,7 +194,8 @@ def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequ
             out[k] = out[k][:nrep]
     out.update(total_gap=r.total_gap, n_ok=int(r.n_ok), S=S,
                two_fold=a["point_stats"][:2].copy(), three_fold=a["point_stats"][2:5].copy(),
-               timings_ms=dict(counts=r.ms_counts, gram=r.ms_gram, solve=r.ms_solve, reduce=r.ms_reduce, total=r.ms_total),
+               timings_ms=dict(counts=r.ms_counts, gram=r.ms_gram, gram_main=r.ms_gram_kernel, solve=r.ms_solve,
+                               reduce=r.ms_reduce, total=r.ms_total),
                gpu_launches=int(r.gpu_launches))
     D = (S - 5) // 2
     out["det_expl"], out["det_unexpl"] = a["point_stats"][5:5 + D].copy(), a["point_stats"][5 + D:].copy()

@@ -335,7 +335,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         if (o->count_bits != 0 && o->count_bits != 8 && o->count_bits != 16) fail(OB_ERR_INVALID_ARG, "count_bits must be 0, 8 or 16");
         int count_bytes = o->count_bits == 16 ? 2 : 1;
 
-        res->ms_counts = res->ms_gram = res->ms_solve = res->ms_reduce = res->ms_total = 0.0;
+        res->ms_counts = res->ms_gram = res->ms_solve = res->ms_reduce = res->ms_total = res->ms_gram_kernel = 0.0;
         res->gpu_launches = 0;
         res->n_ok = 0;
         Timer t_total(st, &res->ms_total);
@@ -432,7 +432,9 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 for (int g = 0; g < 2; ++g) { ga.X[g] = d->g[g].X; ga.w[g] = d->weighted ? d->g[g].w : nullptr; ga.C[g] = d_C[g].p; }
                 ga.count_bytes = count_bytes; ga.partials = d_partials.as<double>();
                 ga.d_pairs = d_pairs.as<uint16_t>(); ga.gram = d_gram.as<double>();
-                gram_launch(plan, ga, st);
+                cudaEvent_t ev0, ev1;
+                OB_CUDA(cudaEventCreate(&ev0)); OB_CUDA(cudaEventCreate(&ev1));
+                gram_launch(plan, ga, st, ev0, ev1);
                 res->gpu_launches += 2;
                 t_gram.stop();
 
@@ -458,6 +460,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
                 OB_CUDA(cudaStreamSynchronize(st));
                 t_counts.collect(); t_gram.collect(); t_solve.collect();
+                { float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1); res->ms_gram_kernel += ms; cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
                 if (flags[2]) fail(OB_ERR_INVALID_ARG, "resample index out of range");
                 if (flags[0]) fail(OB_ERR_CUDA, "Poisson body overshot n (probability < 1e-15 per replicate); rerun with another seed");
                 if (flags[1]) {
@@ -467,7 +470,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
             }
             if (!saturated) break;
             count_bytes = 2;  // widen and redo
-            res->ms_counts = res->ms_gram = res->ms_solve = 0.0;
+            res->ms_counts = res->ms_gram = res->ms_solve = res->ms_gram_kernel = 0.0;
         }
 
         // ---- point estimate (builder.rs:810-811): a failure here is a hard error ----

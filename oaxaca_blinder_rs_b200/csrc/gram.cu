@@ -248,7 +248,7 @@ GramPlan gram_make_plan(int V, int panels, const int64_t n_pad[2], int count_byt
     return pl;
 }
 
-void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st) {
+void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEvent_t ev_main_begin, cudaEvent_t ev_main_end) {
     GramKernelParams p;
     for (int g = 0; g < 2; ++g) {
         p.X[g] = a.X[g]; p.w[g] = a.w[g]; p.C[g] = a.C[g];
@@ -258,6 +258,7 @@ void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st) {
     p.units_total = pl.units[0] + pl.units[1];
     p.ldx = pl.ldx; p.panels = pl.panels; p.ntiles = pl.ntiles; p.stages = pl.stages;
     p.partials = a.partials; p.pairs = a.d_pairs;
+    if (ev_main_begin) OB_CUDA(cudaEventRecord(ev_main_begin, st));
     if (a.count_bytes == 1) {
         OB_CUDA(cudaFuncSetAttribute(gram_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
         gram_kernel<uint8_t><<<pl.grid, GRAM_THREADS, pl.smem_bytes, st>>>(p);
@@ -266,6 +267,7 @@ void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st) {
         gram_kernel<uint16_t><<<pl.grid, GRAM_THREADS, pl.smem_bytes, st>>>(p);
     }
     OB_CUDA(cudaGetLastError());
+    if (ev_main_end) OB_CUDA(cudaEventRecord(ev_main_end, st));
     dim3 rg(2 * pl.panels * pl.ntiles, 4);
     gram_reduce_kernel<<<rg, 256, 0, st>>>(a.partials, pl.segs[0], pl.segs[1], a.gram, pl.panels, pl.ntiles);
     OB_CUDA(cudaGetLastError());

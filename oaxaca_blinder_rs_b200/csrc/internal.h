@@ -76,7 +76,8 @@ struct GramArgs {
     const uint16_t* d_pairs;     // [ntiles*BN][2] column offsets (j,l) within a design row
     double* gram;                // out: [2][panels*BM][ntiles*BN]
 };
-void gram_launch(const GramPlan& plan, const GramArgs& args, cudaStream_t st);
+void gram_launch(const GramPlan& plan, const GramArgs& args, cudaStream_t st, cudaEvent_t ev_main_begin = nullptr,
+                 cudaEvent_t ev_main_end = nullptr);
 std::vector<uint16_t> gram_pair_table(int V, int ntiles);
 
 // ---- solve.cu ----

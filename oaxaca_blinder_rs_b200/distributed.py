@@ -1,0 +1,66 @@
+"""Replicate sharding across GPUs (mode R): one process per GPU, every rank holds the
+full packed design, rank r computes a contiguous range of global replicate ids with the counter-based
+stream keyed by global id, one all-gather of the [reps_r x S] statistics block, then every rank reduces
+the identical gathered array.  Plumbing only (torch.distributed: NCCL on GPUs, gloo in CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+
+
+def shard_range(rank: int, world: int, reps: int) -> Tuple[int, int]:
+    """Contiguous, balanced replicate range [begin, end) of `rank`; the first reps % world ranks get one more."""
+    base, extra = divmod(reps, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def gather_replicates(local_stats: np.ndarray, local_status: np.ndarray, reps: int, S: int, group=None, device=None):
+    """All-gather the per-rank replicate rows into global replicate order.  Returns (stats [reps,S], status [reps])
+    identical on every rank.  Uneven shards are padded to the largest shard for the collective."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    b, e = shard_range(rank, world, reps)
+    assert local_stats.shape == (e - b, S) and local_status.shape == (e - b,)
+    cap = -(-reps // world) if reps else 0
+    buf = torch.zeros((max(cap, 1), S + 1), dtype=torch.float64)
+    if e > b:
+        buf[: e - b, :S] = torch.from_numpy(np.ascontiguousarray(local_stats))
+        buf[: e - b, S] = torch.from_numpy(local_status.astype(np.float64))
+    if device is not None:
+        buf = buf.to(device)
+    out = torch.empty((world,) + tuple(buf.shape), dtype=torch.float64, device=buf.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    out = out.cpu().numpy()
+    stats = np.empty((reps, S))
+    status = np.empty(reps, dtype=np.int32)
+    for r in range(world):
+        rb, re = shard_range(r, world, reps)
+        stats[rb:re] = out[r, : re - rb, :S]
+        status[rb:re] = out[r, : re - rb, S].astype(np.int32)
+    return stats, status
+
+
+def bootstrap_sharded(design, reps: int, group=None, device=None, **kw) -> dict:
+    """ob_bootstrap_run on this rank's replicate shard + all-gather + ob_reduce_stats (same result on all ranks)."""
+    import torch.distributed as dist
+    from . import core
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    b, e = shard_range(rank, world, reps)
+    part = core.bootstrap(design, reps, rep_begin=b, rep_end=e, skip_reduce=True, **kw) if e > b else \
+        core.bootstrap(design, 0, skip_reduce=True, **{k: v for k, v in kw.items() if k not in ("idx_a", "idx_b")})
+    S = part["S"]
+    local_stats = part["rep_stats"] if e > b else np.empty((0, S))
+    local_status = part["rep_status"] if e > b else np.empty(0, dtype=np.int32)
+    stats, status = gather_replicates(local_stats, local_status, reps, S, group=group, device=device)
+    red = core.reduce_stats(design.ctx, stats, status, part["point_stats"]) if reps else \
+        dict(std_err=np.full(S, np.nan), p_value=np.full(S, np.nan), ci_lower=np.full(S, np.nan),
+             ci_upper=np.full(S, np.nan), t_stat=np.zeros(S), n_ok=0)
+    out = dict(part)
+    out.update(red)
+    out["rep_stats"], out["rep_status"] = stats, status
+    return out

@@ -33,20 +33,35 @@ int32_t orc_n_stats(const orc_spec* s) { return 5 + 2 * (s->K + orc_n_base(s)); 
 /* ---- nalgebra Cholesky semantics (nalgebra 0.32 linalg/cholesky.rs, restated from its
  * published algorithm: column-by-column; a pivot that is zero, negative or NaN -> None).
  * Call site ols.rs:107-111.  G is K x K row-major, lower triangle is overwritten by L. ---- */
+/* smallest pivot relative to its original diagonal seen since the last reset: 1 - R^2 of the most
+ * collinear column.  Tests use it to recognise numerically rank-deficient resamples, where the sign of
+ * a rounding-noise pivot -- and hence success/failure -- is not reproducible across summation orders. */
+static _Thread_local double tls_min_pivot = 1.0;
+
 static int chol_factor(ld* G, int K) {
+    ld* diag0 = (ld*)malloc(sizeof(ld) * (size_t)K);
+    for (int j = 0; j < K; ++j) diag0[j] = G[j * K + j];
     for (int j = 0; j < K; ++j) {
         for (int k = 0; k < j; ++k) {
             const ld f = G[j * K + k];
             for (int i = j; i < K; ++i) G[i * K + j] -= G[i * K + k] * f;
         }
         const ld d = G[j * K + j];
-        if (!(d > 0.0L)) return 0;
+        {
+            const double rel = (diag0[j] > 0.0L) ? (double)(d / diag0[j]) : 0.0;
+            if (!(rel >= tls_min_pivot)) tls_min_pivot = rel;
+        }
+        if (!(d > 0.0L)) { free(diag0); return 0; }
         const ld r = sqrtl(d);
         G[j * K + j] = r;
         for (int i = j + 1; i < K; ++i) G[i * K + j] /= r;
     }
+    free(diag0);
     return 1;
 }
+
+double orc_last_min_pivot(void) { return tls_min_pivot; }
+void orc_reset_min_pivot(void) { tls_min_pivot = 1.0; }
 
 static void chol_solve(const ld* L, int K, ld* b) { /* ols.rs:115 */
     for (int i = 0; i < K; ++i) {
@@ -517,8 +532,10 @@ int orc_run(const orc_spec* s,
                 ysb[i] = yb[jb[i]];
                 if (wsb) wsb[i] = wb[jb[i]];
             }
+            orc_reset_min_pivot();
             const int r = orc_single_pass(s, Xsa, ysa, wsa, na, Xsb, ysb, wsb, nb, precise, &po);
             if (out->rep_status) out->rep_status[b] = r;
+            if (out->rep_min_pivot) out->rep_min_pivot[b] = orc_last_min_pivot();
             if (r == ORC_OK) {
                 orc_pass_to_stats(s, &po, st);
                 if (out->rep_stats) memcpy(out->rep_stats + b * S, st, sizeof(double) * (size_t)S);

@@ -108,6 +108,7 @@ typedef struct {
     int32_t* rep_status;  /* [reps] ORC_* code */
     double* rep_beta_a;   /* [reps x K] */
     double* rep_beta_b;   /* [reps x K] */
+    double* rep_min_pivot;/* [reps] smallest Cholesky pivot relative to its diagonal (numerical-rank indicator) */
     /* reduction over the successful replicates, in replicate order (builder.rs:849-930) */
     int64_t n_ok;
     double* se;  double* p;  double* ci_lo;  double* ci_hi;  double* t;   /* [S] each */
@@ -131,6 +132,10 @@ void orc_fill_indices(uint64_t seed, int64_t rep, int32_t group, int64_t n, uint
 void orc_reduce(const double* rep_stats, const int32_t* rep_status, int64_t reps, int32_t S,
                 const double* point_stats, int64_t* n_ok,
                 double* se, double* p, double* ci_lo, double* ci_hi, double* t);
+
+/* numerical-rank indicator of the Cholesky factorisations since the last reset (thread-local) */
+double orc_last_min_pivot(void);
+void orc_reset_min_pivot(void);
 
 /* flatten a pass into the S-vector layout */
 void orc_pass_to_stats(const orc_spec* s, const orc_pass_out* p, double* stats);

@@ -46,7 +46,7 @@ class _PassOut(C.Structure):
 
 class _RunOut(C.Structure):
     _fields_ = [("point", _PassOut), ("rep_stats", _DP), ("rep_status", C.POINTER(C.c_int32)),
-                ("rep_beta_a", _DP), ("rep_beta_b", _DP), ("n_ok", C.c_int64),
+                ("rep_beta_a", _DP), ("rep_beta_b", _DP), ("rep_min_pivot", _DP), ("n_ok", C.c_int64),
                 ("se", _DP), ("p", _DP), ("ci_lo", _DP), ("ci_hi", _DP), ("t", _DP)]
 
 
@@ -237,6 +237,8 @@ def run(spec: Spec, Xa, ya, wa, Xb, yb, wb, reps: int, idx_a=None, idx_b=None, s
     red = {k: np.empty(S) for k in ("se", "p", "ci_lo", "ci_hi", "t")}
     ro.rep_stats, ro.rep_status = _dp(rep_stats), rep_status.ctypes.data_as(C.POINTER(C.c_int32))
     ro.rep_beta_a, ro.rep_beta_b = _dp(rep_beta_a), _dp(rep_beta_b)
+    rep_min_pivot = np.ones(R)
+    ro.rep_min_pivot = _dp(rep_min_pivot)
     for k, v in red.items():
         setattr(ro, k, _dp(v))
     u32p = C.POINTER(C.c_uint32)
@@ -254,7 +256,7 @@ def run(spec: Spec, Xa, ya, wa, Xb, yb, wb, reps: int, idx_a=None, idx_b=None, s
     if rc:
         raise OracleError(rc)
     out = {"point": _pass_dict(ro.point, arrs), "n_ok": int(ro.n_ok), "rep_stats": rep_stats[:reps],
-           "rep_status": rep_status[:reps]}
+           "rep_status": rep_status[:reps], "rep_min_pivot": rep_min_pivot[:reps]}
     if want_rep:
         out["rep_beta_a"], out["rep_beta_b"] = rep_beta_a[:reps], rep_beta_b[:reps]
     out.update(red)
