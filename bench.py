@@ -32,6 +32,7 @@ WORKLOADS = {
     "config3_n10M_k50_wls_yun_B2000": (10_000_000, 44, (4, 4), True, True, 2000, 0),
     "config2_n1M_k20_B1000": (1_000_000, 20, (), False, False, 1000, 0),
     "smoke_n200k_k50_B256": (200_000, 44, (4, 4), True, True, 256, 0),
+    "probe_n1M_k50_B255": (1_000_000, 44, (4, 4), True, True, 255, 0),   # ncu-sized: two full panels
 }
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool (profiles/r01_fp64_peaks.json): DMMA.8x8x4 issue peak
 FP64_CUBLAS_DGEMM_TFLOPS = 35.4  # measured on this pool (profiles/r01_dgemm_peak.json): cuBLAS DGEMM 8192^3

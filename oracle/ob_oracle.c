@@ -47,8 +47,8 @@ static int chol_factor(ld* G, int K) {
             for (int i = j; i < K; ++i) G[i * K + j] -= G[i * K + k] * f;
         }
         const ld d = G[j * K + j];
-        {
-            const double rel = (diag0[j] > 0.0L) ? (double)(d / diag0[j]) : 0.0;
+        if (diag0[j] > 0.0L) { /* an exactly zero column (absent category) is singular in any arithmetic: not ambiguous */
+            const double rel = (double)(d / diag0[j]);
             if (!(rel >= tls_min_pivot)) tls_min_pivot = rel;
         }
         if (!(d > 0.0L)) { free(diag0); return 0; }
