@@ -17,6 +17,7 @@ struct ob_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;   // stream-ordered workspace pool: freed blocks stay cached between calls
     std::string err;
 };
 
@@ -29,20 +30,39 @@ struct ob_design {
 
 namespace {
 
-struct DevBuf {  // RAII device allocation
+// RAII workspace allocation from the context's stream-ordered pool (cudaMallocFromPoolAsync): the
+// multi-GB multiplicity / partial buffers are reused across calls instead of paying cudaMalloc/cudaFree
+// (hundreds of ms at n = 1e7) every bootstrap.
+thread_local ob_ctx* g_alloc_ctx = nullptr;
+
+struct DevBuf {
     void* p = nullptr; size_t bytes = 0;
-    DevBuf() = default;
-    explicit DevBuf(size_t b) { alloc(b); }
+    ob_ctx* ctx = nullptr;
+    DevBuf() : ctx(g_alloc_ctx) {}
+    explicit DevBuf(size_t b) : ctx(g_alloc_ctx) { alloc(b); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), ctx(o.ctx) { o.p = nullptr; o.bytes = 0; }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) { cudaFreeAsync(p, ctx->stream); p = nullptr; }
+        bytes = 0;
+    }
     void alloc(size_t b) {
-        if (p) { cudaFree(p); p = nullptr; }
+        release();
         bytes = b;
-        if (b) OB_CUDA(cudaMalloc(&p, b));
+        if (b) OB_CUDA(cudaMallocFromPoolAsync(&p, b, ctx->pool, ctx->stream));
     }
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
+
+// bytes the pool holds but is not using: available to the next call in addition to cudaMemGetInfo's free
+size_t pool_idle_bytes(ob_ctx* ctx) {
+    unsigned long long reserved = 0, used = 0;
+    cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+    cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &used);
+    return reserved > used ? (size_t)(reserved - used) : 0;
+}
 
 struct Timer {
     cudaEvent_t a, b; cudaStream_t st; double* acc;
@@ -58,6 +78,7 @@ template <typename F>
 ob_status guarded(ob_ctx* ctx, F&& f) {
     try {
         if (ctx) OB_CUDA(cudaSetDevice(ctx->device));
+        g_alloc_ctx = ctx;
         f();
         return OB_OK;
     } catch (const CudaError& e) {
@@ -129,6 +150,14 @@ ob_status ob_ctx_create(int32_t device, ob_ctx** out) {
         if (prop.major != 10) fail(OB_ERR_NO_DEVICE, "libobboot is built for sm_100a (B200) only");
         ctx->num_sms = prop.multiProcessorCount;
         OB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        OB_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
+        unsigned long long keep = ~0ull;   // never trim on synchronisation: the workspace is reused by the next call
+        OB_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
     });
     if (st != OB_OK) return st;
     *out = ctx.release();
@@ -138,6 +167,8 @@ ob_status ob_ctx_create(int32_t device, ob_ctx** out) {
 void ob_ctx_destroy(ob_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -365,7 +396,8 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         const int64_t n_pad[2] = {d->g[0].n_pad, d->g[1].n_pad};
         size_t free_b = 0, total_b = 0;
         OB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        const double budget = o->max_workspace_bytes > 0 ? (double)o->max_workspace_bytes : 0.6 * (double)free_b;
+        const double budget = o->max_workspace_bytes > 0 ? (double)o->max_workspace_bytes
+                                                         : 0.6 * ((double)free_b + (double)pool_idle_bytes(ctx));
 
         for (int attempt = 0; attempt < 2; ++attempt) {  // second attempt only widens uint8 -> uint16 after saturation
             const double per_panel = (double)(n_pad[0] + n_pad[1]) * BM * count_bytes +

@@ -41,32 +41,25 @@ struct GramKernelParams {
     const uint16_t* pairs;
 };
 
+// Widening of the count tile: thread (r = tid/8, q = tid%8) converts columns {16e + 2q, 16e + 2q + 1}
+// of row r for e = 0..7.  One (LDS.U16/U32 -> 2 DFMA -> STS.128) step per e, so the eight steps of the
+// NEXT stage can be interleaved with the eight k-steps of the current stage's DMMA loop.
 template <typename CountT>
-__device__ __forceinline__ void widen_counts(const CountT* __restrict__ craw, double* __restrict__ as,
-                                             const double* __restrict__ ws, bool weighted, int tid) {
-    // thread (r = tid/8, q = tid%8) widens columns {16e + 2q, 16e + 2q + 1 : e = 0..7} of row r
-    const int r = tid >> 3, q = tid & 7;
-    const CountT* src = craw + r * BM + q * 2;
-    double* dst = as + r * LDA + q * 2;
-    const double two52 = 4503599627370496.0;
-    double wr = 1.0, off = -two52;
-    if (weighted) { wr = ws[r]; off = -two52 * wr; }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        unsigned c0, c1;
-        if (sizeof(CountT) == 1) {
-            const unsigned v = *reinterpret_cast<const uint16_t*>(src + e * 16);
-            c0 = v & 0xFFu; c1 = v >> 8;
-        } else {
-            const unsigned v = *reinterpret_cast<const uint32_t*>(src + e * 16);
-            c0 = v & 0xFFFFu; c1 = v >> 16;
-        }
-        // (2^52 + c) is exact in fp64; fma(2^52 + c, w, -2^52 w) = round(c * w) in one operation
-        double2 o;
-        o.x = fma(__hiloint2double(0x43300000, (int)c0), wr, off);
-        o.y = fma(__hiloint2double(0x43300000, (int)c1), wr, off);
-        *reinterpret_cast<double2*>(dst + e * 16) = o;
+__device__ __forceinline__ void widen_step(const CountT* __restrict__ src, double* __restrict__ dst, int e,
+                                           double wr, double off) {
+    unsigned c0, c1;
+    if (sizeof(CountT) == 1) {
+        const unsigned v = *reinterpret_cast<const uint16_t*>(src + e * 16);
+        c0 = v & 0xFFu; c1 = v >> 8;
+    } else {
+        const unsigned v = *reinterpret_cast<const uint32_t*>(src + e * 16);
+        c0 = v & 0xFFFFu; c1 = v >> 16;
     }
+    // (2^52 + c) is exact in fp64; fma(2^52 + c, w, -2^52 w) = round(c * w) in one operation
+    double2 o;
+    o.x = fma(__hiloint2double(0x43300000, (int)c0), wr, off);
+    o.y = fma(__hiloint2double(0x43300000, (int)c1), wr, off);
+    *reinterpret_cast<double2*>(dst + e * 16) = o;
 }
 
 template <typename CountT>
@@ -138,19 +131,39 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
 #pragma unroll
             for (int s = 0; s < 4; ++s) { acc[i][s][0] = 0.0; acc[i][s][1] = 0.0; }
 
+        const double two52 = 4503599627370496.0;
+        const int cr = tid >> 3, cq = tid & 7;   // widening role of this thread: row cr, column pairs 16e + 2cq
+        auto widen_setup = [&](int s, const CountT*& src, double*& dst, double& wr, double& off) {
+            const int slot = (int)((it_base + (uint32_t)s) % (uint32_t)NST);
+            src = Cr + (size_t)slot * KT * BM + cr * BM + cq * 2;
+            dst = As + (s & 1) * KT * LDA + cr * LDA + cq * 2;
+            wr = weighted ? Ws[(size_t)slot * KT + cr] : 1.0;
+            off = -two52 * wr;
+        };
+        auto wait_stage = [&](int s) {
+            const uint32_t it = it_base + (uint32_t)s;
+            mbar_wait(&full[it % (uint32_t)NST], (it / (uint32_t)NST) & 1u);
+        };
+
+        // prologue: fill the pipeline, widen stage 0 (the only exposed widening of the unit)
         if (tid == 0)
-            for (int s = 0; s < NST - 1 && s < nstages; ++s) issue(s);
+            for (int s = 0; s < NST && s < nstages; ++s) issue(s);
+        {
+            wait_stage(0);
+            const CountT* src; double* dst; double wr, off;
+            widen_setup(0, src, dst, wr, off);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) widen_step<CountT>(src, dst, e, wr, off);
+        }
+        __syncthreads();
 
         for (int s = 0; s < nstages; ++s) {
-            const uint32_t it = it_base + (uint32_t)s;
-            const int slot = (int)(it % (uint32_t)NST);
-            mbar_wait(&full[slot], (it / (uint32_t)NST) & 1u);
-            double* Acur = As + (s & 1) * KT * LDA;
-            widen_counts<CountT>(Cr + (size_t)slot * KT * BM, Acur, Ws + (size_t)slot * KT, weighted, tid);
-            __syncthreads();  // A tile visible; every warp is done with stage s-1 -> its slot is free
-            if (tid == 0 && s + NST - 1 < nstages) issue(s + NST - 1);
+            const int slot = (int)((it_base + (uint32_t)s) % (uint32_t)NST);
+            const bool has_next = s + 1 < nstages;
+            const CountT* nsrc = nullptr; double* ndst = nullptr; double nwr = 1.0, noff = 0.0;
+            if (has_next) { wait_stage(s + 1); widen_setup(s + 1, nsrc, ndst, nwr, noff); }
 
-            const double* abase = Acur + lk * LDA + wm * 64 + lg;
+            const double* abase = As + (s & 1) * KT * LDA + lk * LDA + wm * 64 + lg;
             const double* xbase = Xs + (size_t)slot * KT * ldx + lk * ldx;
 #pragma unroll
             for (int kk = 0; kk < KT / 4; ++kk) {
@@ -161,15 +174,16 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
                 for (int i = 0; i < 8; ++i) a[i] = arow[i * 8];
 #pragma unroll
                 for (int t = 0; t < 4; ++t) b[t] = xrow[oj[t]] * xrow[ol[t]];
+                if (has_next) widen_step<CountT>(nsrc, ndst, kk, nwr, noff);   // next stage's A tile, in the DMMA shadow
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
                     for (int t = 0; t < 4; ++t) dmma884(acc[i][t][0], acc[i][t][1], a[i], b[t]);
             }
+            __syncthreads();  // stage s fully consumed (X rows, its A tile) and stage s+1's A tile complete
+            if (tid == 0 && s + NST < nstages) issue(s + NST);   // refill the slot stage s just released
         }
         it_base += (uint32_t)nstages;
-        __syncthreads();  // all warps done with the last stage before the next unit refills A / slots
-
         // flush the partial tile [BM][BN] row-major
         double* out = p.partials + (size_t)u * (BM * BN);
 #pragma unroll
