@@ -22,6 +22,7 @@
 #include "internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace ob {
 
@@ -41,29 +42,39 @@ struct GramKernelParams {
     const uint16_t* pairs;
 };
 
-// Widening of the count tile: thread (r = tid/8, q = tid%8) converts columns {16e + 2q, 16e + 2q + 1}
-// of row r for e = 0..7.  One (LDS.U16/U32 -> 2 DFMA -> STS.128) step per e, so the eight steps of the
-// NEXT stage can be interleaved with the eight k-steps of the current stage's DMMA loop.
-template <typename CountT>
+// Widening of the count tile.  With T threads, thread (r = tid / (T/32), q = tid % (T/32)) converts columns
+// {2(T/32) e + 2q, +1} of row r for e = 0 .. 4096/(2T) - 1.  One (LDS.U16/U32 -> 2 DFMA -> STS.128) step per
+// e, so the steps of the NEXT stage are interleaved with the k-steps of the current stage's DMMA loop.
+template <typename CountT, int CSTRIDE>
 __device__ __forceinline__ void widen_step(const CountT* __restrict__ src, double* __restrict__ dst, int e,
                                            double wr, double off) {
     unsigned c0, c1;
     if (sizeof(CountT) == 1) {
-        const unsigned v = *reinterpret_cast<const uint16_t*>(src + e * 16);
+        const unsigned v = *reinterpret_cast<const uint16_t*>(src + e * CSTRIDE);
         c0 = v & 0xFFu; c1 = v >> 8;
     } else {
-        const unsigned v = *reinterpret_cast<const uint32_t*>(src + e * 16);
+        const unsigned v = *reinterpret_cast<const uint32_t*>(src + e * CSTRIDE);
         c0 = v & 0xFFFFu; c1 = v >> 16;
     }
     // (2^52 + c) is exact in fp64; fma(2^52 + c, w, -2^52 w) = round(c * w) in one operation
     double2 o;
     o.x = fma(__hiloint2double(0x43300000, (int)c0), wr, off);
     o.y = fma(__hiloint2double(0x43300000, (int)c1), wr, off);
-    *reinterpret_cast<double2*>(dst + e * 16) = o;
+    *reinterpret_cast<double2*>(dst + e * CSTRIDE) = o;
 }
 
-template <typename CountT>
-__global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelParams p) {
+// NWM warps along M (slots) x 4 warps along N (columns); warp tile (128/NWM) x 32 = MI x 4 DMMA sub-tiles.
+//   NWM = 2: 8 warps, 64 x 32 warp tiles (fewest shared-memory reads per DMMA)
+//   NWM = 4: 16 warps, 32 x 32 warp tiles (4 warps per scheduler: more latency cover)
+template <typename CountT, int NWM>
+__global__ void __launch_bounds__(NWM * 128, 1) gram_kernel(const GramKernelParams p) {
+    constexpr int T = NWM * 128;            // threads
+    constexpr int MI = BM / NWM / 8;        // m sub-tiles per warp
+    constexpr int TPR = T / 32;             // widening threads per row
+    constexpr int WSTEPS = BM / (2 * TPR);  // widening steps per thread per stage
+    constexpr int CSTRIDE = 2 * TPR;
+    constexpr int KSTEPS = KT / 4;
+    static_assert(WSTEPS <= KSTEPS, "widening must fit in the k-step loop");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
@@ -89,6 +100,8 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
     const uint32_t stage_bytes = (uint32_t)(KT * ldx * sizeof(double) + KT * BM * sizeof(CountT) +
                                             (weighted ? KT * sizeof(double) : 0));
     uint32_t it_base = 0;  // pipeline stage counter across units (slot = it % NST, parity = (it / NST) & 1)
+    const double two52 = 4503599627370496.0;
+    const int cr = tid / TPR, cq = tid % TPR;   // widening role of this thread
 
     for (long long u = u0; u < u1; ++u) {
         const int g = (u >= p.units0) ? 1 : 0;
@@ -115,24 +128,6 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
             tma_load_1d(Cr + (size_t)slot * KT * BM, Cg + (long long)s * KT * BM, KT * BM * sizeof(CountT), &full[slot]);
             if (weighted) tma_load_1d(Ws + (size_t)slot * KT, wg + (long long)s * KT, KT * sizeof(double), &full[slot]);
         };
-
-        // column pair (j,l) offsets of this thread's four B sub-tiles
-        int oj[4], ol[4];
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int col = nt * BN + wn * 32 + s * 8 + lg;
-            const uint32_t pr = *reinterpret_cast<const uint32_t*>(p.pairs + 2 * col);
-            oj[s] = pr & 0xFFFFu; ol[s] = pr >> 16;
-        }
-
-        double acc[8][4][2];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int s = 0; s < 4; ++s) { acc[i][s][0] = 0.0; acc[i][s][1] = 0.0; }
-
-        const double two52 = 4503599627370496.0;
-        const int cr = tid >> 3, cq = tid & 7;   // widening role of this thread: row cr, column pairs 16e + 2cq
         auto widen_setup = [&](int s, const CountT*& src, double*& dst, double& wr, double& off) {
             const int slot = (int)((it_base + (uint32_t)s) % (uint32_t)NST);
             src = Cr + (size_t)slot * KT * BM + cr * BM + cq * 2;
@@ -145,6 +140,21 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
             mbar_wait(&full[it % (uint32_t)NST], (it / (uint32_t)NST) & 1u);
         };
 
+        // column pair (j,l) offsets of this thread's four B sub-tiles
+        int oj[4], ol[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int col = nt * BN + wn * 32 + s * 8 + lg;
+            const uint32_t pr = *reinterpret_cast<const uint32_t*>(p.pairs + 2 * col);
+            oj[s] = pr & 0xFFFFu; ol[s] = pr >> 16;
+        }
+
+        double acc[MI][4][2];
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { acc[i][s][0] = 0.0; acc[i][s][1] = 0.0; }
+
         // prologue: fill the pipeline, widen stage 0 (the only exposed widening of the unit)
         if (tid == 0)
             for (int s = 0; s < NST && s < nstages; ++s) issue(s);
@@ -153,7 +163,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
             const CountT* src; double* dst; double wr, off;
             widen_setup(0, src, dst, wr, off);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) widen_step<CountT>(src, dst, e, wr, off);
+            for (int e = 0; e < WSTEPS; ++e) widen_step<CountT, CSTRIDE>(src, dst, e, wr, off);
         }
         __syncthreads();
 
@@ -163,20 +173,20 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
             const CountT* nsrc = nullptr; double* ndst = nullptr; double nwr = 1.0, noff = 0.0;
             if (has_next) { wait_stage(s + 1); widen_setup(s + 1, nsrc, ndst, nwr, noff); }
 
-            const double* abase = As + (s & 1) * KT * LDA + lk * LDA + wm * 64 + lg;
+            const double* abase = As + (s & 1) * KT * LDA + lk * LDA + wm * (MI * 8) + lg;
             const double* xbase = Xs + (size_t)slot * KT * ldx + lk * ldx;
 #pragma unroll
-            for (int kk = 0; kk < KT / 4; ++kk) {
-                double a[8], b[4];
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+                double a[MI], b[4];
                 const double* arow = abase + kk * 4 * LDA;
                 const double* xrow = xbase + kk * 4 * ldx;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = arow[i * 8];
+                for (int i = 0; i < MI; ++i) a[i] = arow[i * 8];
 #pragma unroll
                 for (int t = 0; t < 4; ++t) b[t] = xrow[oj[t]] * xrow[ol[t]];
-                if (has_next) widen_step<CountT>(nsrc, ndst, kk, nwr, noff);   // next stage's A tile, in the DMMA shadow
+                if (has_next && kk < WSTEPS) widen_step<CountT, CSTRIDE>(nsrc, ndst, kk, nwr, noff);  // next A tile, in the DMMA shadow
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < MI; ++i)
 #pragma unroll
                     for (int t = 0; t < 4; ++t) dmma884(acc[i][t][0], acc[i][t][1], a[i], b[t]);
             }
@@ -184,13 +194,14 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
             if (tid == 0 && s + NST < nstages) issue(s + NST);   // refill the slot stage s just released
         }
         it_base += (uint32_t)nstages;
+
         // flush the partial tile [BM][BN] row-major
         double* out = p.partials + (size_t)u * (BM * BN);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const int m = wm * 64 + i * 8 + lg, n = wn * 32 + t * 8 + 2 * lk;
+                const int m = wm * (MI * 8) + i * 8 + lg, n = wn * 32 + t * 8 + 2 * lk;
                 *reinterpret_cast<double2*>(out + m * BN + n) = make_double2(acc[i][t][0], acc[i][t][1]);
             }
     }
@@ -259,6 +270,8 @@ GramPlan gram_make_plan(int V, int panels, const int64_t n_pad[2], int count_byt
     while (pl.stages > 2 && gram_smem(pl.ldx, pl.stages, count_bytes) > 220 * 1024) --pl.stages;
     pl.smem_bytes = gram_smem(pl.ldx, pl.stages, count_bytes);
     pl.num_partials = (int64_t)total;
+    const char* v = getenv("OBBOOT_GRAM_WARPS_M");   // tuning knob (2 or 4); default chosen by measurement
+    pl.warps_m = (v && atoi(v) == 4) ? 4 : 2;
     return pl;
 }
 
@@ -273,12 +286,14 @@ void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEve
     p.ldx = pl.ldx; p.panels = pl.panels; p.ntiles = pl.ntiles; p.stages = pl.stages;
     p.partials = a.partials; p.pairs = a.d_pairs;
     if (ev_main_begin) OB_CUDA(cudaEventRecord(ev_main_begin, st));
-    if (a.count_bytes == 1) {
-        OB_CUDA(cudaFuncSetAttribute(gram_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-        gram_kernel<uint8_t><<<pl.grid, GRAM_THREADS, pl.smem_bytes, st>>>(p);
+    auto launch = [&](auto kernel, int threads) {
+        OB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
+        kernel<<<pl.grid, threads, pl.smem_bytes, st>>>(p);
+    };
+    if (pl.warps_m == 4) {
+        if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 4>, 512); else launch(gram_kernel<uint16_t, 4>, 512);
     } else {
-        OB_CUDA(cudaFuncSetAttribute(gram_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-        gram_kernel<uint16_t><<<pl.grid, GRAM_THREADS, pl.smem_bytes, st>>>(p);
+        if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 2>, 256); else launch(gram_kernel<uint16_t, 2>, 256);
     }
     OB_CUDA(cudaGetLastError());
     if (ev_main_end) OB_CUDA(cudaEventRecord(ev_main_end, st));

@@ -67,6 +67,7 @@ struct GramPlan {
     int grid;
     int64_t num_partials;         // = units[0] + units[1]
     size_t smem_bytes; int stages;
+    int warps_m;                  // 2: 8 warps (64x32 warp tiles), 4: 16 warps (32x32 warp tiles)
 };
 GramPlan gram_make_plan(int V, int panels, const int64_t n_pad[2], int count_bytes, bool weighted, int num_sms);
 struct GramArgs {

@@ -39,7 +39,7 @@ struct PoissonTable {
 enum : uint32_t { STREAM_BODY = 0x0B0D1u, STREAM_REFINE = 0x0F19Eu, STREAM_FIXUP = 0x0F1Cu };
 
 __device__ __forceinline__ int poisson_exact(uint32_t u_hi, const PoissonTable& t, uint64_t row, uint32_t c1,
-                                             uint64_t rep, uint32_t k0, uint32_t k1) {
+                                          uint64_t rep, uint32_t k0, uint32_t k1) {
     // low word comes from the refinement stream, keyed by the single replicate id
     const Philox4 r = philox4x32_10((uint32_t)row, c1, (uint32_t)rep, STREAM_REFINE ^ (uint32_t)(rep >> 32), k0, k1);
     const unsigned long long U = ((unsigned long long)u_hi << 32) | r.x;
@@ -49,14 +49,23 @@ __device__ __forceinline__ int poisson_exact(uint32_t u_hi, const PoissonTable& 
     return c;
 }
 
-__device__ __forceinline__ int poisson_draw(uint32_t u, const PoissonTable& t, uint64_t row, uint32_t c1,
-                                            uint64_t rep, uint32_t k0, uint32_t k1) {
-    int c = (u > t.Th[0]) + (u > t.Th[1]) + (u > t.Th[2]) + (u > t.Th[3]);
-    if (u >= t.Th[3] || u == t.Th[0] || u == t.Th[1] || u == t.Th[2]) c = poisson_exact(u, t, row, c1, rep, k0, k1);
+constexpr int KFAST = 8;   // thresholds resolved inline; P(Poisson(<=1) > 7) ~ 1e-6, so the exact path is ~never divergent
+
+// count = #{k : U >= T[k]} for the 64-bit uniform U = (u : refinement word).  The high word decides unless it
+// equals a threshold's high word or lies beyond the inline table; only then is the low word drawn.
+__device__ __forceinline__ int poisson_draw(uint32_t u, const uint32_t (&th)[KFAST], const PoissonTable& t,
+                                            uint64_t row, uint32_t c1, uint64_t rep, uint32_t k0, uint32_t k1) {
+    int c = 0;
+    bool amb = u >= th[KFAST - 1];
+#pragma unroll
+    for (int k = 0; k < KFAST; ++k) { c += (u > th[k]) ? 1 : 0; amb |= (u == th[k]); }
+    if (amb) c = poisson_exact(u, t, row, c1, rep, k0, k1);
     return c;
 }
 
-template <typename CountT>
+// SH = (global replicate id of local slot 0) mod 4: Philox words are keyed by floor(rep / 4), so a thread's
+// 16 consecutive replicates span 4 (SH == 0) or 5 key groups; SH is uniform over the launch -> compile-time.
+template <typename CountT, int SH>
 __global__ void __launch_bounds__(256) counts_philox_body(CountT* __restrict__ C, long long n, long long n_pad,
                                                           long long slots, long long rep0, int first_slot, int group,
                                                           uint32_t k0, uint32_t k1, const PoissonTable tab,
@@ -67,6 +76,17 @@ __global__ void __launch_bounds__(256) counts_philox_body(CountT* __restrict__ C
     const long long slot0 = (long long)panel * BM + q * 16;
     const long long row_begin = (long long)blockIdx.x * rows_per_block;
     const uint32_t c1base = ((uint32_t)group << 8);
+    uint32_t th[KFAST];
+#pragma unroll
+    for (int k = 0; k < KFAST; ++k) th[k] = tab.Th[k];
+    // replicate of local slot s is rep0 + s; first key group of this thread (rep0 + slot0 - SH is a multiple of 4)
+    const long long rep_lo = rep0 + slot0;
+    const long long q4_first = (rep_lo - SH) >> 2;
+    // validity of slot e (0..15) is row-independent: slot >= first_slot && slot < slots
+    unsigned valid = 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+        if (slot0 + e >= first_slot && slot0 + e < slots) valid |= 1u << e;
     int sums[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) sums[e] = 0;
@@ -77,23 +97,18 @@ __global__ void __launch_bounds__(256) counts_philox_body(CountT* __restrict__ C
         for (int e = 0; e < 16; ++e) cnt[e] = 0;
         if (row < n) {
             const uint32_t c1 = c1base | (uint32_t)((unsigned long long)row >> 32);
-            // global replicate id of local slot s is rep0 + s (slot 0 is the point estimate when first_slot == 1)
-            const long long rep_lo = rep0 + slot0;            // may be -1 for the point-estimate slot
-            const long long q4_first = (rep_lo < 0 ? 0 : rep_lo) >> 2;
-            const long long q4_last = (rep_lo + 15) >> 2;
-            if (!tab.lambda_zero) {
-                for (long long q4 = q4_first; q4 <= q4_last; ++q4) {
-                    const Philox4 r = philox4x32_10((uint32_t)row, c1, (uint32_t)q4, STREAM_BODY ^ (uint32_t)(q4 >> 32), k0, k1);
-                    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+            if (!tab.lambda_zero && valid) {
+                uint32_t u[20];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const long long rep = q4 * 4 + j;
-                        const long long e = rep - rep_lo;
-                        const long long slot = slot0 + e;
-                        if (e >= 0 && e < 16 && slot >= first_slot && slot < slots)
-                            cnt[e] = (unsigned)poisson_draw(u[j], tab, (uint64_t)row, c1, (uint64_t)rep, k0, k1);
-                    }
+                for (int gidx = 0; gidx < (SH ? 5 : 4); ++gidx) {
+                    const long long q4 = q4_first + gidx;
+                    const Philox4 r = philox4x32_10((uint32_t)row, c1, (uint32_t)q4, STREAM_BODY ^ (uint32_t)(q4 >> 32), k0, k1);
+                    u[4 * gidx] = r.x; u[4 * gidx + 1] = r.y; u[4 * gidx + 2] = r.z; u[4 * gidx + 3] = r.w;
                 }
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (valid & (1u << e))
+                        cnt[e] = (unsigned)poisson_draw(u[SH + e], th, tab, (uint64_t)row, c1, (uint64_t)(rep_lo + e), k0, k1);
             }
             if (slot0 == 0 && first_slot == 1) cnt[0] = 1;  // point estimate
 #pragma unroll
@@ -117,14 +132,23 @@ __global__ void __launch_bounds__(256) counts_philox_body(CountT* __restrict__ C
             reinterpret_cast<uint4*>(dst)[1] = v1;
         }
     }
-    // column sums: reduce the 4 row-lanes of each warp that share q, then one atomic per (warp, slot)
+    // column sums: reduce the 4 row-lanes of each warp that share q, then the 8 warps through shared memory,
+    // then ONE global atomic per (block, slot): same-address global atomics serialise in L2
+    __shared__ int ssum[BM];
+    if (threadIdx.x < BM) ssum[threadIdx.x] = 0;
+    __syncthreads();
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
         int s = sums[e];
         s += __shfl_xor_sync(0xffffffffu, s, 8);
         s += __shfl_xor_sync(0xffffffffu, s, 16);
-        if ((threadIdx.x & 31) < 8 && s != 0 && slot0 + e < slots)
-            atomicAdd(reinterpret_cast<unsigned long long*>(colsum + slot0 + e), (unsigned long long)s);
+        if ((threadIdx.x & 31) < 8 && s != 0) atomicAdd(&ssum[q * 16 + e], s);
+    }
+    __syncthreads();
+    if (threadIdx.x < BM) {
+        const long long slot = (long long)panel * BM + threadIdx.x;
+        const int s = ssum[threadIdx.x];
+        if (s != 0 && slot < slots) atomicAdd(reinterpret_cast<unsigned long long*>(colsum + slot), (unsigned long long)s);
     }
 }
 
@@ -224,25 +248,23 @@ void counts_philox(const CountsArgs& a, long long* d_colsum, int* d_flags, cudaS
     const PoissonTable tab = make_table(a.n);
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     OB_CUDA(cudaMemsetAsync(d_colsum, 0, sizeof(long long) * (size_t)a.panels * BM, st));
-    const int rows_per_block = 512;
+    const int rows_per_block = 2048;
     dim3 grid((unsigned)((a.n_pad + rows_per_block - 1) / rows_per_block), (unsigned)a.panels);
     const long long nrep = a.slots - a.first_slot;
     dim3 fgrid((unsigned)std::max<long long>(nrep, 1), 16);
-    if (a.count_bytes == 1) {
-        counts_philox_body<uint8_t><<<grid, 256, 0, st>>>((uint8_t*)a.C, a.n, a.n_pad, a.slots, a.rep0, a.first_slot, a.group,
-                                                         k0, k1, tab, d_colsum, rows_per_block);
+    const int sh = (int)(((a.rep0 % 4) + 4) % 4);
+    auto body = [&](auto ct) {
+        using CT = decltype(ct);
+#define OB_BODY(SHV) counts_philox_body<CT, SHV><<<grid, 256, 0, st>>>((CT*)a.C, a.n, a.n_pad, a.slots, a.rep0, \
+            a.first_slot, a.group, k0, k1, tab, d_colsum, rows_per_block)
+        switch (sh) { case 0: OB_BODY(0); break; case 1: OB_BODY(1); break; case 2: OB_BODY(2); break; default: OB_BODY(3); }
+#undef OB_BODY
         OB_CUDA(cudaGetLastError());
         if (nrep > 0)
-            counts_philox_fixup<uint8_t><<<fgrid, 256, 0, st>>>((uint8_t*)a.C, a.n, a.n_pad, a.slots, a.rep0, a.first_slot,
-                                                               a.group, k0, k1, d_colsum, d_flags);
-    } else {
-        counts_philox_body<uint16_t><<<grid, 256, 0, st>>>((uint16_t*)a.C, a.n, a.n_pad, a.slots, a.rep0, a.first_slot, a.group,
-                                                          k0, k1, tab, d_colsum, rows_per_block);
-        OB_CUDA(cudaGetLastError());
-        if (nrep > 0)
-            counts_philox_fixup<uint16_t><<<fgrid, 256, 0, st>>>((uint16_t*)a.C, a.n, a.n_pad, a.slots, a.rep0, a.first_slot,
-                                                                a.group, k0, k1, d_colsum, d_flags);
-    }
+            counts_philox_fixup<CT><<<fgrid, 256, 0, st>>>((CT*)a.C, a.n, a.n_pad, a.slots, a.rep0, a.first_slot,
+                                                           a.group, k0, k1, d_colsum, d_flags);
+    };
+    if (a.count_bytes == 1) body(uint8_t{}); else body(uint16_t{});
     OB_CUDA(cudaGetLastError());
 }
 
