@@ -33,9 +33,9 @@ def gather_replicates(local_stats: np.ndarray, local_status: np.ndarray, reps: i
         buf[: e - b, S] = torch.from_numpy(local_status.astype(np.float64))
     if device is not None:
         buf = buf.to(device)
-    out = torch.empty((world,) + tuple(buf.shape), dtype=torch.float64, device=buf.device)
+    out = torch.empty((world * buf.shape[0], S + 1), dtype=torch.float64, device=buf.device)   # concatenated form
     dist.all_gather_into_tensor(out, buf, group=group)
-    out = out.cpu().numpy()
+    out = out.cpu().numpy().reshape(world, buf.shape[0], S + 1)
     stats = np.empty((reps, S))
     status = np.empty(reps, dtype=np.int32)
     for r in range(world):
