@@ -1,0 +1,508 @@
+// csrc/host/builder.cc -- see builder.h.  Citations: file:line under oaxaca_blinder/src/ of the reference.
+#include "builder.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+
+namespace ob {
+
+// ------------------------------------------------------------------ frame
+void DataFrame::add_f64(const std::string& name, std::vector<double> data, std::vector<uint8_t> valid) {
+    if (!cols_.empty() && data.size() != height_) throw OaxacaError(OB_ERR_POLARS, "column length mismatch: " + name);
+    height_ = data.size();
+    Column c; c.name = name; c.is_str = false; c.f64 = std::move(data); c.valid = std::move(valid);
+    cols_.push_back(std::move(c));
+}
+void DataFrame::add_str(const std::string& name, std::vector<std::string> data, std::vector<uint8_t> valid) {
+    if (!cols_.empty() && data.size() != height_) throw OaxacaError(OB_ERR_POLARS, "column length mismatch: " + name);
+    height_ = data.size();
+    Column c; c.name = name; c.is_str = true; c.str = std::move(data); c.valid = std::move(valid);
+    cols_.push_back(std::move(c));
+}
+const Column* DataFrame::find(const std::string& name) const {
+    for (const auto& c : cols_) if (c.name == name) return &c;
+    return nullptr;
+}
+
+static std::vector<std::string> split_csv_line(const std::string& line) {
+    std::vector<std::string> out; std::string cur; bool q = false;
+    for (size_t i = 0; i < line.size(); ++i) {
+        const char ch = line[i];
+        if (q) { if (ch == '"') { if (i + 1 < line.size() && line[i + 1] == '"') { cur += '"'; ++i; } else q = false; } else cur += ch; }
+        else if (ch == '"') q = true;
+        else if (ch == ',') { out.push_back(cur); cur.clear(); }
+        else if (ch != '\r') cur += ch;
+    }
+    out.push_back(cur);
+    return out;
+}
+
+DataFrame DataFrame::read_csv(const std::string& path) {   // main.rs:161-165 (LazyCsvReader, has_header)
+    std::ifstream in(path);
+    if (!in) throw OaxacaError(OB_ERR_POLARS, "No such file or directory: " + path);
+    std::string line;
+    if (!std::getline(in, line)) throw OaxacaError(OB_ERR_POLARS, "empty CSV: " + path);
+    const std::vector<std::string> header = split_csv_line(line);
+    std::vector<std::vector<std::string>> cells(header.size());
+    while (std::getline(in, line)) {
+        if (line.empty() || line == "\r") continue;
+        std::vector<std::string> f = split_csv_line(line);
+        f.resize(header.size());
+        for (size_t c = 0; c < header.size(); ++c) cells[c].push_back(f[c]);
+    }
+    DataFrame df;
+    for (size_t c = 0; c < header.size(); ++c) {
+        bool numeric = true, any = false;
+        for (const auto& s : cells[c]) {
+            if (s.empty()) continue;
+            any = true;
+            char* end = nullptr;
+            std::strtod(s.c_str(), &end);
+            if (end == s.c_str() || *end != '\0') { numeric = false; break; }
+        }
+        std::vector<uint8_t> valid(cells[c].size(), 1);
+        bool has_null = false;
+        for (size_t i = 0; i < cells[c].size(); ++i) if (cells[c][i].empty()) { valid[i] = 0; has_null = true; }
+        if (!has_null) valid.clear();
+        if (numeric && any) {
+            std::vector<double> v(cells[c].size(), 0.0);
+            for (size_t i = 0; i < v.size(); ++i) if (!cells[c][i].empty()) v[i] = std::strtod(cells[c][i].c_str(), nullptr);
+            df.add_f64(header[c], std::move(v), std::move(valid));
+        } else {
+            df.add_str(header[c], std::move(cells[c]), std::move(valid));
+        }
+    }
+    return df;
+}
+
+// ------------------------------------------------------------------ errors, formula
+std::string OaxacaError::display(ob_status k, const std::string& d) {   // error.rs:27-38
+    switch (k) {
+    case OB_ERR_POLARS: return "Polars error: " + d;
+    case OB_ERR_COLUMN_NOT_FOUND: return "Column not found: " + d;
+    case OB_ERR_INVALID_GROUP: return "Invalid group variable: " + d;
+    case OB_ERR_NALGEBRA: return "Nalgebra error: " + d;
+    case OB_ERR_DIAGNOSTIC: return "Diagnostic error: " + d;
+    case OB_ERR_INSUFFICIENT_DATA: return "Insufficient data: " + d;
+    default: return d;
+    }
+}
+
+static std::string trim(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && std::isspace((unsigned char)s[a])) ++a;
+    while (b > a && std::isspace((unsigned char)s[b - 1])) --b;
+    return s.substr(a, b - a);
+}
+
+Formula Formula::parse(const std::string& s) {   // formula.rs:12-60
+    std::vector<std::string> parts;
+    { std::stringstream ss(s); std::string p; while (std::getline(ss, p, '~')) parts.push_back(p); if (!s.empty() && s.back() == '~') parts.push_back(""); }
+    if (parts.size() != 2)
+        throw OaxacaError(OB_ERR_INVALID_GROUP, OaxacaError::display(OB_ERR_INVALID_GROUP,
+                          "Invalid formula format. Expected 'outcome ~ predictors', got '" + s + "'"));
+    Formula f;
+    f.outcome = trim(parts[0]);
+    if (f.outcome.empty())
+        throw OaxacaError(OB_ERR_INVALID_GROUP, OaxacaError::display(OB_ERR_INVALID_GROUP, "Outcome variable is missing"));
+    std::stringstream ss(parts[1]);
+    std::string term;
+    while (std::getline(ss, term, '+')) {
+        term = trim(term);
+        if (term.empty()) continue;
+        if (term.rfind("C(", 0) == 0 && term.back() == ')') f.categorical_predictors.push_back(trim(term.substr(2, term.size() - 3)));
+        else if (term.rfind("factor(", 0) == 0 && term.back() == ')') f.categorical_predictors.push_back(trim(term.substr(7, term.size() - 8)));
+        else f.predictors.push_back(term);
+    }
+    if (f.predictors.empty() && f.categorical_predictors.empty())
+        throw OaxacaError(OB_ERR_INVALID_GROUP, OaxacaError::display(OB_ERR_INVALID_GROUP, "No predictors specified"));
+    return f;
+}
+
+// ------------------------------------------------------------------ builder
+OaxacaBuilder::OaxacaBuilder(DataFrame df, const std::string& outcome, const std::string& group,
+                             const std::string& reference_group)
+    : dataframe_(std::move(df)), outcome_(outcome), group_(group), reference_group_(reference_group) {}
+
+OaxacaBuilder OaxacaBuilder::from_formula(DataFrame df, const std::string& formula, const std::string& group,
+                                          const std::string& reference_group) {   // builder.rs:139-160
+    const Formula f = Formula::parse(formula);
+    OaxacaBuilder b(std::move(df), f.outcome, group, reference_group);
+    b.predictors_ = f.predictors;
+    b.categorical_ = f.categorical_predictors;
+    return b;
+}
+
+// the cleaned, coded frame at builder.rs:808
+struct OaxacaBuilder::Prepared {
+    size_t n = 0;                                   // rows after drop_nulls
+    std::vector<std::vector<double>> cont;          // predictors, compacted
+    std::vector<std::vector<int32_t>> cat_codes;
+    std::vector<int32_t> cat_levels;
+    std::vector<double> y, w;
+    std::vector<uint8_t> group;
+    std::vector<std::string> names;                 // design column names (builder.rs:325-327)
+    std::map<std::string, size_t> category_counts;  // builder.rs:799
+    std::map<std::string, std::string> base_categories;   // builder.rs:800
+    // .normalize spec (normalization.rs:14-38, builder.rs:636-647)
+    std::vector<int32_t> norm_m, norm_off, norm_idx, norm_has_base;
+    std::vector<std::string> base_names;
+};
+
+static void require_f64(const Column* c) {
+    if (c->is_str) throw OaxacaError(OB_ERR_POLARS, OaxacaError::display(OB_ERR_POLARS,
+                       "invalid series dtype: expected `Float64`, got `str` for series with name `" + c->name + "`"));
+}
+static void require_str(const Column* c) {
+    if (!c->is_str) throw OaxacaError(OB_ERR_POLARS, OaxacaError::display(OB_ERR_POLARS,
+                        "invalid series dtype: expected `String`, got `f64` for series with name `" + c->name + "`"));
+}
+
+OaxacaBuilder::Prepared OaxacaBuilder::prepare() const {
+    Prepared p;
+    // clean_dataframe (builder.rs:760-784): existence check in this order, then drop rows with a null in any used column
+    std::vector<std::string> cols = {outcome_, group_};
+    cols.insert(cols.end(), predictors_.begin(), predictors_.end());
+    cols.insert(cols.end(), categorical_.begin(), categorical_.end());
+    if (has_weights_) cols.push_back(weights_col_);
+    if (has_selection_) cols.push_back(selection_outcome_);
+    cols.insert(cols.end(), selection_predictors_.begin(), selection_predictors_.end());
+    std::vector<const Column*> used;
+    for (const auto& c : cols) {
+        const Column* col = dataframe_.find(c);
+        if (!col) throw OaxacaError(OB_ERR_COLUMN_NOT_FOUND, OaxacaError::display(OB_ERR_COLUMN_NOT_FOUND, c));
+        used.push_back(col);
+    }
+    const size_t N = dataframe_.height();
+    std::vector<size_t> keep;
+    keep.reserve(N);
+    for (size_t i = 0; i < N; ++i) {
+        bool ok = true;
+        for (const Column* c : used) if (!c->is_valid(i)) { ok = false; break; }
+        if (ok) keep.push_back(i);
+    }
+    p.n = keep.size();
+
+    // create_dummies_manual (builder.rs:380-418) on the FULL cleaned frame, before the split (:794-806)
+    p.names.push_back("__ob_intercept__");
+    for (const auto& pr : predictors_) p.names.push_back(pr);
+    for (const auto& cat : categorical_) {
+        const Column* c = dataframe_.find(cat);
+        require_str(c);
+        std::set<std::string> uniq;
+        for (size_t i : keep) uniq.insert(c->str[i]);
+        if (uniq.empty())
+            throw OaxacaError(OB_ERR_INVALID_GROUP, OaxacaError::display(OB_ERR_INVALID_GROUP, "Could not get reference category for " + cat));
+        const std::vector<std::string> levels(uniq.begin(), uniq.end());   // sorted ascending (:384-388)
+        std::map<std::string, int32_t> code;
+        for (size_t l = 0; l < levels.size(); ++l) code[levels[l]] = (int32_t)l;
+        std::vector<int32_t> codes(p.n);
+        for (size_t r = 0; r < p.n; ++r) codes[r] = code[c->str[keep[r]]];
+        p.cat_codes.push_back(std::move(codes));
+        p.cat_levels.push_back((int32_t)levels.size());
+        p.category_counts[cat] = levels.size();
+        p.base_categories[cat] = cat + "_" + levels[0];                    // :400
+        for (size_t l = 1; l < levels.size(); ++l) p.names.push_back(cat + "_" + levels[l]);   // :402-404
+    }
+
+    // numeric columns
+    const Column* yc = dataframe_.find(outcome_);
+    require_f64(yc);
+    p.y.resize(p.n);
+    for (size_t r = 0; r < p.n; ++r) p.y[r] = yc->f64[keep[r]];
+    for (const auto& pr : predictors_) {
+        const Column* c = dataframe_.find(pr);
+        require_f64(c);
+        std::vector<double> v(p.n);
+        for (size_t r = 0; r < p.n; ++r) v[r] = c->f64[keep[r]];
+        p.cont.push_back(std::move(v));
+    }
+    if (has_weights_) {
+        const Column* c = dataframe_.find(weights_col_);
+        require_f64(c);
+        p.w.resize(p.n);
+        for (size_t r = 0; r < p.n; ++r) p.w[r] = c->f64[keep[r]];
+    }
+
+    // split_groups (builder.rs:61-102)
+    const Column* gc = dataframe_.find(group_);
+    require_str(gc);
+    std::set<std::string> ug;
+    for (size_t i : keep) ug.insert(gc->str[i]);
+    if (ug.size() < 2)
+        throw OaxacaError(OB_ERR_INVALID_GROUP, OaxacaError::display(OB_ERR_INVALID_GROUP, "Not enough groups for comparison"));
+    auto it = ug.begin();
+    std::string a_name = *it;
+    if (a_name == reference_group_) a_name = *(++it);                      // :79-83
+    p.group.resize(p.n);
+    for (size_t r = 0; r < p.n; ++r) {
+        const std::string& g = gc->str[keep[r]];
+        p.group[r] = g == a_name ? 0 : (g == reference_group_ ? 1 : 2);   // rows of any third group are ignored (:85-94)
+    }
+
+    // .normalize(): membership by name prefix "{var}_" over ALL predictor names (normalization.rs:14-20)
+    p.norm_off.push_back(0);
+    for (const auto& var : normalization_vars_) {
+        const std::string prefix = var + "_";
+        int cnt = 0;
+        for (size_t i = 0; i < p.names.size(); ++i)
+            if (p.names[i].rfind(prefix, 0) == 0) { p.norm_idx.push_back((int32_t)i); ++cnt; }
+        p.norm_off.push_back((int32_t)p.norm_idx.size());
+        auto cc = p.category_counts.find(var);
+        p.norm_m.push_back(cc != p.category_counts.end() ? (int32_t)cc->second : cnt + 1);   // normalization.rs:31-34
+        auto bc = p.base_categories.find(var);
+        p.norm_has_base.push_back(bc != p.base_categories.end() ? 1 : 0);                     // builder.rs:636-640
+        if (bc != p.base_categories.end()) p.base_names.push_back(bc->second);
+    }
+    return p;
+}
+
+namespace {
+struct CtxGuard {
+    ob_ctx* ctx = nullptr; ob_design* des = nullptr;
+    ~CtxGuard() { if (des) ob_design_destroy(des); if (ctx) ob_ctx_destroy(ctx); }
+};
+void check(ob_ctx* ctx, ob_status st) {
+    if (st == OB_OK) return;
+    std::string msg = ctx ? ob_last_error(ctx) : "";
+    if (msg.empty()) msg = "libobboot error " + std::to_string((int)st);
+    throw OaxacaError(st, msg);
+}
+}  // namespace
+
+OaxacaResults OaxacaBuilder::run() const { return run_impl(false, 0.0); }
+
+OaxacaResults OaxacaBuilder::decompose_quantile(double quantile) const {
+    // builder.rs:711-757: RIF per group on the cleaned frame, then a fresh builder with the same predictors /
+    // categoricals / reps / reference / normalize / weights (Heckman settings are NOT forwarded) -> run()
+    OaxacaBuilder b = *this;
+    b.has_selection_ = false; b.selection_outcome_.clear(); b.selection_predictors_.clear();
+    return b.run_impl(true, quantile);
+}
+
+OaxacaResults OaxacaBuilder::run_impl(bool rif, double tau) const {
+    if (has_selection_)
+        throw OaxacaError(OB_ERR_UNSUPPORTED, "heckman_selection: the Heckman estimator is outside the B200 bootstrap path "
+                                              "(SURVEY.md 8f); no CPU fallback is provided");
+    Prepared p = prepare();
+    CtxGuard g;
+    ob_status st = ob_ctx_create(device_, &g.ctx);
+    if (st != OB_OK) throw OaxacaError(st, "no usable CUDA device (B200 / sm_100a required; there is no CPU fallback)");
+
+    std::vector<const double*> cont(std::max<size_t>(p.cont.size(), 1), nullptr);
+    for (size_t c = 0; c < p.cont.size(); ++c) cont[c] = p.cont[c].data();
+    std::vector<const int32_t*> cats(std::max<size_t>(p.cat_codes.size(), 1), nullptr);
+    for (size_t c = 0; c < p.cat_codes.size(); ++c) cats[c] = p.cat_codes[c].data();
+    ob_frame_view fv{};
+    fv.n = (int64_t)p.n; fv.n_cont = (int32_t)p.cont.size(); fv.cont = cont.data();
+    fv.n_cat = (int32_t)p.cat_codes.size(); fv.cat_codes = cats.data(); fv.cat_levels = p.cat_levels.data();
+    fv.outcome = p.y.data(); fv.weights = has_weights_ ? p.w.data() : nullptr; fv.group = p.group.data();
+    check(g.ctx, ob_design_pack(g.ctx, &fv, &g.des));
+    if (rif) check(g.ctx, ob_design_apply_rif(g.ctx, g.des, tau));
+
+    int64_t na = 0, nb = 0; int32_t K = 0, nc = 0;
+    ob_design_shape(g.des, &na, &nb, &K, &nc);
+    const int n_norm = (int)normalization_vars_.size();
+    const int S = ob_num_stats(K, n_norm, p.norm_has_base.data());
+    const int D = (S - 5) / 2;
+
+    ob_boot_opts o{};
+    switch (reference_coeffs_) {
+    case ReferenceCoefficients::GroupA: o.ref_kind = OB_REF_GROUP_A; break;
+    case ReferenceCoefficients::GroupB: o.ref_kind = OB_REF_GROUP_B; break;
+    case ReferenceCoefficients::Pooled: case ReferenceCoefficients::Neumark: o.ref_kind = OB_REF_POOLED; break;
+    default: o.ref_kind = OB_REF_WEIGHTED; break;
+    }
+    o.n_norm = n_norm; o.norm_m = p.norm_m.data(); o.norm_off = p.norm_off.data();
+    o.norm_idx = p.norm_idx.data(); o.norm_has_base = p.norm_has_base.data();
+    o.reps = (int64_t)bootstrap_reps_; o.seed = seed_;
+    o.idx_a = idx_a_; o.idx_b = idx_b_;
+
+    OaxacaResults R;
+    std::vector<double> point(S), se(S), pv(S), lo(S), hi(S), t(S);
+    R.xa_mean.resize(K); R.xb_mean.resize(K); R.beta_star.resize(K); R.residuals.resize((size_t)nb);
+    ob_result r{};
+    r.point_stats = point.data(); r.xa_mean = R.xa_mean.data(); r.xb_mean = R.xb_mean.data(); r.beta_star = R.beta_star.data();
+    r.residuals_b = R.residuals.data();
+    r.std_err = se.data(); r.p_value = pv.data(); r.ci_lower = lo.data(); r.ci_upper = hi.data(); r.t_stat = t.data();
+    check(g.ctx, ob_bootstrap_run(g.ctx, g.des, &o, &r));
+
+    R.bootstrap_reps = (int64_t)bootstrap_reps_;
+    R.successful_bootstraps = r.n_ok;
+    if (r.n_ok < (int64_t)bootstrap_reps_)   // builder.rs:841-847
+        std::cerr << "Warning: " << (bootstrap_reps_ - r.n_ok) << " out of " << bootstrap_reps_
+                  << " bootstrap replications failed and were discarded. The analysis is based on " << r.n_ok
+                  << " successful replications." << std::endl;
+    auto comp = [&](const std::string& name, int j) {
+        return ComponentResult{name, point[j], se[j], t[j], pv[j], lo[j], hi[j]};
+    };
+    R.total_gap = r.total_gap;
+    R.two_fold.aggregate = {comp("explained", 0), comp("unexplained", 1)};                            // :867-884
+    R.three_fold.aggregate = {comp("endowments", 2), comp("coefficients", 3), comp("interaction", 4)}; // :885-910
+    std::vector<std::string> rows = p.names;
+    rows.insert(rows.end(), p.base_names.begin(), p.base_names.end());                                // :661-669
+    for (int j = 0; j < D; ++j) {
+        R.two_fold.detailed_explained.push_back(comp(rows[j], 5 + j));
+        R.two_fold.detailed_unexplained.push_back(comp(rows[j], 5 + D + j));
+    }
+    R.n_a = (size_t)na; R.n_b = (size_t)nb;
+    R.predictor_names = p.names;
+    R.ms_total = r.ms_total; R.ms_gram = r.ms_gram;
+    return R;
+}
+
+DataMatrices OaxacaBuilder::get_data_matrices() const {   // builder.rs:252-291
+    Prepared p = prepare();
+    CtxGuard g;
+    ob_status st = ob_ctx_create(device_, &g.ctx);
+    if (st != OB_OK) throw OaxacaError(st, "no usable CUDA device (B200 / sm_100a required; there is no CPU fallback)");
+    std::vector<const double*> cont(std::max<size_t>(p.cont.size(), 1), nullptr);
+    for (size_t c = 0; c < p.cont.size(); ++c) cont[c] = p.cont[c].data();
+    std::vector<const int32_t*> cats(std::max<size_t>(p.cat_codes.size(), 1), nullptr);
+    for (size_t c = 0; c < p.cat_codes.size(); ++c) cats[c] = p.cat_codes[c].data();
+    ob_frame_view fv{};
+    fv.n = (int64_t)p.n; fv.n_cont = (int32_t)p.cont.size(); fv.cont = cont.data();
+    fv.n_cat = (int32_t)p.cat_codes.size(); fv.cat_codes = cats.data(); fv.cat_levels = p.cat_levels.data();
+    fv.outcome = p.y.data(); fv.weights = nullptr; fv.group = p.group.data();
+    check(g.ctx, ob_design_pack(g.ctx, &fv, &g.des));
+    int64_t na = 0, nb = 0; int32_t K = 0, nc = 0;
+    ob_design_shape(g.des, &na, &nb, &K, &nc);
+    DataMatrices m;
+    m.n_a = (size_t)na; m.n_b = (size_t)nb; m.k = (size_t)K; m.predictor_names = p.names;
+    m.x_a.resize(m.n_a * m.k); m.y_a.resize(m.n_a); m.x_b.resize(m.n_b * m.k); m.y_b.resize(m.n_b);
+    check(g.ctx, ob_design_download(g.ctx, g.des, m.x_a.data(), m.y_a.data(), nullptr, m.x_b.data(), m.y_b.data(), nullptr));
+    return m;
+}
+
+std::string OaxacaBuilder::describe() const {
+    const Prepared p = prepare();
+    std::ostringstream os;
+    size_t na = 0, nb = 0;
+    for (uint8_t g : p.group) { na += g == 0; nb += g == 1; }
+    auto ivec = [&](const std::vector<int32_t>& v) { os << '['; for (size_t i = 0; i < v.size(); ++i) { if (i) os << ','; os << v[i]; } os << ']'; };
+    auto svec = [&](const std::vector<std::string>& v) { os << '['; for (size_t i = 0; i < v.size(); ++i) { if (i) os << ','; os << '"' << v[i] << '"'; } os << ']'; };
+    os << "{\"rows\":" << p.n << ",\"n_a\":" << na << ",\"n_b\":" << nb << ",\"names\":"; svec(p.names);
+    os << ",\"base_names\":"; svec(p.base_names);
+    os << ",\"cat_levels\":"; ivec(p.cat_levels);
+    os << ",\"norm_m\":"; ivec(p.norm_m); os << ",\"norm_off\":"; ivec(p.norm_off);
+    os << ",\"norm_idx\":"; ivec(p.norm_idx); os << ",\"norm_has_base\":"; ivec(p.norm_has_base);
+    os << ",\"group\":["; for (size_t i = 0; i < p.group.size(); ++i) { if (i) os << ','; os << (int)p.group[i]; } os << "]}";
+    return os.str();
+}
+
+// ------------------------------------------------------------------ presentation
+static std::string fmt(double v, int prec) {
+    char b[64];
+    if (std::isnan(v)) return "NaN";
+    snprintf(b, sizeof b, "%.*f", prec, v);
+    return b;
+}
+
+static void table(std::ostream& os, const char* first, const char* second, const std::vector<ComponentResult>& rows) {
+    std::vector<std::vector<std::string>> cells;
+    cells.push_back({first, second, "Std. Err.", "p-value", "95% CI"});
+    for (const auto& c : rows)
+        cells.push_back({c.name, fmt(c.estimate, 4), fmt(c.std_err, 4), fmt(c.p_value, 4),
+                         "[" + fmt(c.ci_lower, 3) + ", " + fmt(c.ci_upper, 3) + "]"});
+    std::vector<size_t> wdt(5, 0);
+    for (const auto& r : cells) for (int i = 0; i < 5; ++i) wdt[i] = std::max(wdt[i], r[i].size());
+    auto rule = [&] { os << '+'; for (int i = 0; i < 5; ++i) os << std::string(wdt[i] + 2, '-') << '+'; os << '\n'; };
+    rule();
+    for (size_t r = 0; r < cells.size(); ++r) {
+        os << '|';
+        for (int i = 0; i < 5; ++i) os << ' ' << cells[r][i] << std::string(wdt[i] - cells[r][i].size() + 1, ' ') << '|';
+        os << '\n';
+        if (r == 0) rule();
+    }
+    rule();
+}
+
+void OaxacaResults::summary(std::ostream& os) const {   // display.rs:9-79
+    os << "Oaxaca-Blinder Decomposition Results\n";
+    os << "========================================\n";
+    os << "Group A (Advantaged): " << n_a << " observations\n";
+    os << "Group B (Reference):  " << n_b << " observations\n";
+    os << "Total Gap: " << fmt(total_gap, 4) << "\n\n";
+    os << "Two-Fold Decomposition\n";
+    table(os, "Component", "Estimate", two_fold.aggregate);
+    os << "\nDetailed Decomposition (Explained)\n";
+    table(os, "Variable", "Contribution", two_fold.detailed_explained);
+    os << "\nDetailed Decomposition (Unexplained)\n";
+    table(os, "Variable", "Contribution", two_fold.detailed_unexplained);
+}
+
+static void jnum(std::ostream& os, double v) {   // serde_json: non-finite -> null
+    if (!std::isfinite(v)) { os << "null"; return; }
+    char b[40]; snprintf(b, sizeof b, "%.17g", v); os << b;
+}
+static void jstr(std::ostream& os, const std::string& s) {
+    os << '"';
+    for (char ch : s) { if (ch == '"' || ch == '\\') os << '\\'; os << ch; }
+    os << '"';
+}
+static void jcomps(std::ostream& os, const std::vector<ComponentResult>& v) {
+    os << '[';
+    for (size_t i = 0; i < v.size(); ++i) {
+        if (i) os << ',';
+        os << "{\"name\":"; jstr(os, v[i].name);
+        os << ",\"estimate\":"; jnum(os, v[i].estimate); os << ",\"std_err\":"; jnum(os, v[i].std_err);
+        os << ",\"t_stat\":"; jnum(os, v[i].t_stat); os << ",\"p_value\":"; jnum(os, v[i].p_value);
+        os << ",\"ci_lower\":"; jnum(os, v[i].ci_lower); os << ",\"ci_upper\":"; jnum(os, v[i].ci_upper); os << '}';
+    }
+    os << ']';
+}
+static void jvec(std::ostream& os, const std::vector<double>& v) {
+    os << '[';
+    for (size_t i = 0; i < v.size(); ++i) { if (i) os << ','; jnum(os, v[i]); }
+    os << ']';
+}
+
+std::string OaxacaResults::to_json(bool with_residuals, bool with_extra) const {   // serde layout of types.rs:10-47
+    std::ostringstream os;
+    os << "{\"total_gap\":"; jnum(os, total_gap);
+    os << ",\"two_fold\":{\"aggregate\":"; jcomps(os, two_fold.aggregate);
+    os << ",\"detailed_explained\":"; jcomps(os, two_fold.detailed_explained);
+    os << ",\"detailed_unexplained\":"; jcomps(os, two_fold.detailed_unexplained);
+    os << ",\"detailed_selection\":"; jcomps(os, two_fold.detailed_selection);
+    os << "},\"three_fold\":{\"aggregate\":"; jcomps(os, three_fold.aggregate);
+    os << ",\"detailed\":"; jcomps(os, three_fold.detailed);
+    os << "},\"n_a\":" << n_a << ",\"n_b\":" << n_b;
+    if (with_residuals) { os << ",\"residuals\":"; jvec(os, residuals); }
+    if (with_extra) {   // #[serde(skip)] fields + replicate bookkeeping, for the Python mirror and tests
+        os << ",\"xa_mean\":"; jvec(os, xa_mean); os << ",\"xb_mean\":"; jvec(os, xb_mean);
+        os << ",\"beta_star\":"; jvec(os, beta_star);
+        os << ",\"bootstrap_reps\":" << bootstrap_reps << ",\"successful_bootstraps\":" << successful_bootstraps;
+        os << ",\"predictor_names\":[";
+        for (size_t i = 0; i < predictor_names.size(); ++i) { if (i) os << ','; jstr(os, predictor_names[i]); }
+        os << "],\"ms_total\":"; jnum(os, ms_total); os << ",\"ms_gram\":"; jnum(os, ms_gram);
+    }
+    os << '}';
+    return os.str();
+}
+
+std::string OaxacaResults::to_markdown() const {
+    std::ostringstream os;
+    os << "# Oaxaca-Blinder Decomposition Results\n\n";
+    os << "- Group A: " << n_a << " observations\n- Group B: " << n_b << " observations\n- Total Gap: " << fmt(total_gap, 4) << "\n\n";
+    auto tab = [&](const char* title, const std::vector<ComponentResult>& rows) {
+        os << "## " << title << "\n\n| Component | Estimate | Std. Err. | p-value | 95% CI |\n|---|---|---|---|---|\n";
+        for (const auto& c : rows)
+            os << "| " << c.name << " | " << fmt(c.estimate, 4) << " | " << fmt(c.std_err, 4) << " | " << fmt(c.p_value, 4)
+               << " | [" << fmt(c.ci_lower, 3) << ", " << fmt(c.ci_upper, 3) << "] |\n";
+        os << "\n";
+    };
+    tab("Two-Fold Decomposition", two_fold.aggregate);
+    tab("Detailed Decomposition (Explained)", two_fold.detailed_explained);
+    tab("Detailed Decomposition (Unexplained)", two_fold.detailed_unexplained);
+    return os.str();
+}
+
+}  // namespace ob

@@ -1,0 +1,106 @@
+"""Host-side OaxacaBuilder mirror (C++ csrc/host/builder.cc through include/obboot_builder.h), CPU only:
+cleaning, dummy coding, group rule, names, .normalize membership, formula parsing, error variants --
+against the Python restatement of builder.rs in oracle/builder_oracle.py and the reference's own tests."""
+import numpy as np
+import pytest
+
+import oaxaca_blinder_rs_b200 as ob
+from oracle import builder_oracle as bo
+
+
+def frame_with_everything():
+    rng = np.random.default_rng(3)
+    n = 60
+    return {
+        "wage": [None if i == 7 else float(v) for i, v in enumerate(rng.normal(20, 3, n))],
+        "education": [None if i == 11 else float(v) for i, v in enumerate(rng.normal(13, 2, n))],
+        "experience": list(map(float, rng.uniform(0, 40, n))),
+        "gender": [None if i == 13 else ("M", "F", "X")[i % 3 if i % 10 == 0 else i % 2] for i in range(n)],
+        "sector": [("tech", "agri", "serv", "manu")[i % 4] for i in range(n)],
+        "sector_size": list(map(float, rng.uniform(1, 9, n))),     # swept in by the "sector_" prefix
+        "region": [("north", "south")[i % 2] for i in range(n)],
+        "w": list(map(float, rng.uniform(0.5, 3.0, n))),
+    }
+
+
+def test_describe_matches_builder_rules():
+    f = frame_with_everything()
+    b = ob.OaxacaBuilder(f, "wage", "gender", "F")
+    b.predictors(["education", "experience", "sector_size"]).categorical_predictors(["sector", "region"]) \
+        .normalize(["sector", "region", "experience"]).weights("w")
+    d = b.describe()
+    e = bo.prepare(f, "wage", "gender", "F", ["education", "experience", "sector_size"], ["sector", "region"],
+                   ["sector", "region", "experience"], "w")
+    assert d["names"] == e["names"] == ["__ob_intercept__", "education", "experience", "sector_size", "sector_manu",
+                                        "sector_serv", "sector_tech", "region_south"]
+    assert d["base_names"] == e["base_names"] == ["sector_agri", "region_north"]
+    assert d["rows"] == e["rows"] == 57 and d["group"] == list(e["group"])
+    assert (d["n_a"], d["n_b"]) == (len(e["ya"]), len(e["yb"]))
+    assert d["cat_levels"] == [4, 2]
+    # name-prefix membership: "sector_" also matches the continuous predictor sector_size (normalization.rs:14-20);
+    # "experience" is not categorical: no dummies -> m = 0 + 1, no base row (builder.rs:636-640)
+    off = d["norm_off"]
+    got = [dict(m=d["norm_m"][v], idx=d["norm_idx"][off[v]:off[v + 1]], has_base=bool(d["norm_has_base"][v])) for v in range(3)]
+    assert got == e["norm"]
+    assert got[0]["idx"] == [3, 4, 5, 6] and got[2] == dict(m=1, idx=[], has_base=False)
+
+
+def test_group_a_is_first_sorted_non_reference_value():
+    f = {"y": [1.0, 2.0, 3.0, 4.0, 5.0, 6.0], "g": ["b", "c", "a", "a", "b", "c"], "x": [1.0, 2.0, 3.0, 4.0, 5.0, 7.0]}
+    d = ob.OaxacaBuilder(f, "y", "g", "a").predictors(["x"]).describe()
+    assert d["group"] == [0, 2, 1, 1, 0, 2]           # A = "b" (first sorted value that is not the reference), "c" ignored
+    d = ob.OaxacaBuilder(f, "y", "g", "c").predictors(["x"]).describe()
+    assert d["group"] == [2, 1, 0, 0, 2, 1]           # A = "a"
+
+
+def test_null_handling_counts(golden):
+    k = golden["KAT"]["null_handling"]                 # null_handling_test.rs:4-64
+    f = {"outcome": k["outcome"], "group": k["group"], "education": k["education"]}
+    d = ob.OaxacaBuilder(f, "outcome", "group", "B").predictors(["education"]).describe()
+    assert (d["n_a"], d["n_b"]) == (k["n_a"], k["n_b"]) == (3, 3)
+
+
+def test_error_variants():
+    f = {"y": [1.0, 2.0], "g": ["a", "b"], "x": [1.0, 2.0], "s": ["u", "v"]}
+    with pytest.raises(ob.OaxacaError) as e:           # builder.rs:776
+        ob.OaxacaBuilder(f, "y", "g", "a").predictors(["missing"]).describe()
+    assert e.value.kind == "ColumnNotFound" and str(e.value) == "Column not found: missing"
+    with pytest.raises(ob.OaxacaError) as e:           # builder.rs:67-71
+        ob.OaxacaBuilder({"y": [1.0, 2.0], "g": ["a", "a"], "x": [1.0, 2.0]}, "y", "g", "a").predictors(["x"]).describe()
+    assert e.value.kind == "InvalidGroupVariable" and "Not enough groups" in str(e.value)
+    with pytest.raises(ob.OaxacaError) as e:           # outcome must be Float64 (builder.rs:308)
+        ob.OaxacaBuilder(f, "s", "g", "a").predictors(["x"]).describe()
+    assert e.value.kind == "PolarsError"
+    with pytest.raises(ob.OaxacaError) as e:           # group must be String (builder.rs:75)
+        ob.OaxacaBuilder(f, "y", "x", "a").predictors(["x"]).describe()
+    assert e.value.kind == "PolarsError"
+
+
+@pytest.mark.parametrize("formula,exp", [
+    ("wage ~ education + experience + C(sector)", ("wage", ["education", "experience"], ["sector"])),
+    ("y~ a+factor( b )+C(c)", ("y", ["a"], ["b", "c"])),
+])
+def test_formula(formula, exp):                        # formula.rs:12-60, formula_test.rs:4-27
+    cols = {n: [1.0, 2.0] for n in ["wage", "education", "experience", "y", "a"]}
+    cols.update({n: ["p", "q"] for n in ["sector", "b", "c", "g"]})
+    d = ob.OaxacaBuilder.from_formula(cols, formula, "g", "p").describe()
+    outcome, preds, cats = exp
+    assert d["names"][1:1 + len(preds)] == preds and len(d["cat_levels"]) == len(cats)
+
+
+@pytest.mark.parametrize("bad", ["wage education", "~ x", "y ~ ", "a ~ b ~ c"])
+def test_formula_errors(bad):
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.OaxacaBuilder.from_formula({"y": [1.0]}, bad, "g", "p")
+    assert e.value.kind == "InvalidGroupVariable"
+
+
+def test_builder_symbols_exported():
+    import os, re
+    from oaxaca_blinder_rs_b200 import _native, builder
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "obboot_builder.h")).read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(ob_[a-z0-9_]+)\s*\(", src)))
+    assert declared == sorted(builder.BUILDER_SYMBOLS)
+    for s in declared:
+        assert hasattr(_native.lib(), s), s
