@@ -102,13 +102,15 @@ ob_status guarded(ob_ctx* ctx, F&& f) {
 
 int64_t pad_rows(int64_t n) { return std::max<int64_t>(KT, (n + KT - 1) / KT * KT); }
 
-void alloc_group(GroupData& g, int64_t n, int ldx, bool weighted) {
+// zero-fill on the context's (non-blocking) stream: a legacy-default-stream cudaMemset would not be ordered
+// before the copies / pack kernels that follow on that stream
+void alloc_group(GroupData& g, int64_t n, int ldx, bool weighted, cudaStream_t st) {
     g.n = n; g.n_pad = pad_rows(n);
     OB_CUDA(cudaMalloc(&g.X, sizeof(double) * (size_t)g.n_pad * ldx));
-    OB_CUDA(cudaMemset(g.X, 0, sizeof(double) * (size_t)g.n_pad * ldx));
+    OB_CUDA(cudaMemsetAsync(g.X, 0, sizeof(double) * (size_t)g.n_pad * ldx, st));
     if (weighted) {
         OB_CUDA(cudaMalloc(&g.w, sizeof(double) * (size_t)g.n_pad));
-        OB_CUDA(cudaMemset(g.w, 0, sizeof(double) * (size_t)g.n_pad));
+        OB_CUDA(cudaMemsetAsync(g.w, 0, sizeof(double) * (size_t)g.n_pad, st));
     }
 }
 
@@ -220,7 +222,7 @@ ob_status ob_design_from_dense(ob_ctx* ctx, int32_t K, int32_t n_cont,
         const double* Xs[2] = {Xa, Xb};
         const double* ys[2] = {ya, yb};
         for (int g = 0; g < 2; ++g) {
-            alloc_group(d->g[g], ns[g], d->ldx, d->weighted);
+            alloc_group(d->g[g], ns[g], d->ldx, d->weighted, ctx->stream);
             if (ns[g] == 0) continue;
             OB_CUDA(cudaMemcpy2DAsync(d->g[g].X, sizeof(double) * d->ldx, Xs[g], sizeof(double) * K, sizeof(double) * K,
                                       (size_t)ns[g], cudaMemcpyHostToDevice, ctx->stream));
@@ -300,8 +302,8 @@ ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
         std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
         d->device = ctx->device; d->K = K; d->n_cont = f->n_cont; d->V = K + 1; d->ldx = pa.ldx;
         d->weighted = f->weights != nullptr;
-        alloc_group(d->g[0], tot[0], d->ldx, d->weighted);
-        alloc_group(d->g[1], tot[1], d->ldx, d->weighted);
+        alloc_group(d->g[0], tot[0], d->ldx, d->weighted, st);
+        alloc_group(d->g[1], tot[1], d->ldx, d->weighted, st);
         pack_scatter(pa, d_bc.as<long long>(), d->g[0], d->g[1], d_flags.as<int>(), st);
         OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
         OB_CUDA(cudaStreamSynchronize(st));

@@ -15,10 +15,10 @@ def frame_with_everything():
         "wage": [None if i == 7 else float(v) for i, v in enumerate(rng.normal(20, 3, n))],
         "education": [None if i == 11 else float(v) for i, v in enumerate(rng.normal(13, 2, n))],
         "experience": list(map(float, rng.uniform(0, 40, n))),
-        "gender": [None if i == 13 else ("M", "F", "X")[i % 3 if i % 10 == 0 else i % 2] for i in range(n)],
+        "gender": [None if i == 13 else ("X" if i % 19 == 5 else ("M", "F")[int(v)]) for i, v in enumerate(rng.integers(0, 2, n))],
         "sector": [("tech", "agri", "serv", "manu")[i % 4] for i in range(n)],
         "sector_size": list(map(float, rng.uniform(1, 9, n))),     # swept in by the "sector_" prefix
-        "region": [("north", "south")[i % 2] for i in range(n)],
+        "region": [("north", "south")[(i // 3) % 2] for i in range(n)],
         "w": list(map(float, rng.uniform(0.5, 3.0, n))),
     }
 
