@@ -18,6 +18,8 @@ struct ob_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaMemPool_t pool = nullptr;   // stream-ordered workspace pool: freed blocks stay cached between calls
+    cudaMemPool_t pool_pack = nullptr;   // separate pool for the pack's column staging, so its many small blocks do
+                                         // not fragment the bootstrap workspace (20 GB count buffer at n = 1e7)
     std::string err;
 };
 
@@ -34,15 +36,17 @@ namespace {
 // multi-GB multiplicity / partial buffers are reused across calls instead of paying cudaMalloc/cudaFree
 // (hundreds of ms at n = 1e7) every bootstrap.
 thread_local ob_ctx* g_alloc_ctx = nullptr;
+thread_local bool g_alloc_pack = false;
 
 struct DevBuf {
     void* p = nullptr; size_t bytes = 0;
     ob_ctx* ctx = nullptr;
-    DevBuf() : ctx(g_alloc_ctx) {}
-    explicit DevBuf(size_t b) : ctx(g_alloc_ctx) { alloc(b); }
+    bool pack = false;
+    DevBuf() : ctx(g_alloc_ctx), pack(g_alloc_pack) {}
+    explicit DevBuf(size_t b) : ctx(g_alloc_ctx), pack(g_alloc_pack) { alloc(b); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), ctx(o.ctx) { o.p = nullptr; o.bytes = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), ctx(o.ctx), pack(o.pack) { o.p = nullptr; o.bytes = 0; }
     ~DevBuf() { release(); }
     void release() {
         if (p) { cudaFreeAsync(p, ctx->stream); p = nullptr; }
@@ -51,7 +55,7 @@ struct DevBuf {
     void alloc(size_t b) {
         release();
         bytes = b;
-        if (b) OB_CUDA(cudaMallocFromPoolAsync(&p, b, ctx->pool, ctx->stream));
+        if (b) OB_CUDA(cudaMallocFromPoolAsync(&p, b, pack ? ctx->pool_pack : ctx->pool, ctx->stream));
     }
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
@@ -79,6 +83,7 @@ ob_status guarded(ob_ctx* ctx, F&& f) {
     try {
         if (ctx) OB_CUDA(cudaSetDevice(ctx->device));
         g_alloc_ctx = ctx;
+        g_alloc_pack = false;
         f();
         return OB_OK;
     } catch (const CudaError& e) {
@@ -111,6 +116,7 @@ void alloc_group(GroupData& g, int64_t n, int ldx, bool weighted, cudaStream_t s
     if (weighted) {
         OB_CUDA(cudaMalloc(&g.w, sizeof(double) * (size_t)g.n_pad));
         OB_CUDA(cudaMemsetAsync(g.w, 0, sizeof(double) * (size_t)g.n_pad, st));
+        OB_CUDA(cudaMalloc(&g.Xs, sizeof(double) * (size_t)g.n_pad * ldx));
     }
 }
 
@@ -158,8 +164,10 @@ ob_status ob_ctx_create(int32_t device, ob_ctx** out) {
         props.location.type = cudaMemLocationTypeDevice;
         props.location.id = device;
         OB_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
+        OB_CUDA(cudaMemPoolCreate(&ctx->pool_pack, &props));
         unsigned long long keep = ~0ull;   // never trim on synchronisation: the workspace is reused by the next call
         OB_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        OB_CUDA(cudaMemPoolSetAttribute(ctx->pool_pack, cudaMemPoolAttrReleaseThreshold, &keep));
     });
     if (st != OB_OK) return st;
     *out = ctx.release();
@@ -171,6 +179,7 @@ void ob_ctx_destroy(ob_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+    if (ctx->pool_pack) cudaMemPoolDestroy(ctx->pool_pack);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -186,7 +195,7 @@ int32_t ob_num_stats(int32_t K, int32_t n_norm, const int32_t* norm_has_base) {
 void ob_design_destroy(ob_design* d) {
     if (!d) return;
     cudaSetDevice(d->device);
-    for (auto& g : d->g) { if (g.X) cudaFree(g.X); if (g.w) cudaFree(g.w); }
+    for (auto& g : d->g) { if (g.X) cudaFree(g.X); if (g.w) cudaFree(g.w); if (g.Xs) cudaFree(g.Xs); }
     delete d;
 }
 
@@ -231,6 +240,7 @@ ob_status ob_design_from_dense(ob_ctx* ctx, int32_t K, int32_t n_cont,
             if (d->weighted && ws[g])
                 OB_CUDA(cudaMemcpyAsync(d->g[g].w, ws[g], sizeof(double) * (size_t)ns[g], cudaMemcpyHostToDevice, ctx->stream));
         }
+        for (int g = 0; g < 2; ++g) scale_rows_launch(d->g[g], d->ldx, ctx->stream);
         OB_CUDA(cudaStreamSynchronize(ctx->stream));
         *out = d.release();
     });
@@ -252,6 +262,7 @@ ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
         if (K + 1 > 91) fail(OB_ERR_UNSUPPORTED, "design wider than 90 columns is not supported by the solve kernel");
         cudaStream_t st = ctx->stream;
         const int64_t n = f->n;
+        g_alloc_pack = true;
         // ---- stage the frame columns in HBM ----
         std::vector<DevBuf> cols(f->n_cont), cats(f->n_cat);
         std::vector<const double*> h_cont(std::max(f->n_cont, 1), nullptr);
@@ -305,6 +316,7 @@ ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
         alloc_group(d->g[0], tot[0], d->ldx, d->weighted, st);
         alloc_group(d->g[1], tot[1], d->ldx, d->weighted, st);
         pack_scatter(pa, d_bc.as<long long>(), d->g[0], d->g[1], d_flags.as<int>(), st);
+        for (int g = 0; g < 2; ++g) scale_rows_launch(d->g[g], d->ldx, st);
         OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
         OB_CUDA(cudaStreamSynchronize(st));
         if (flags[1]) fail(OB_ERR_INVALID_ARG, "categorical code outside [0, levels)");
@@ -337,6 +349,7 @@ ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau) {
             const size_t sb = rif_scratch_bytes(d->g[g].n);
             DevBuf scratch(sb);
             rif_transform(d->g[g], d->K, d->ldx, tau, scratch.p, sb, ctx->stream);
+            scale_rows_launch(d->g[g], d->ldx, ctx->stream);   // the RIF outcome is weighted like any outcome
             OB_CUDA(cudaStreamSynchronize(ctx->stream));
         }
     });
@@ -463,7 +476,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 }
                 Timer t_gram(st, &res->ms_gram);
                 GramArgs ga;
-                for (int g = 0; g < 2; ++g) { ga.X[g] = d->g[g].X; ga.w[g] = d->weighted ? d->g[g].w : nullptr; ga.C[g] = d_C[g].p; }
+                for (int g = 0; g < 2; ++g) { ga.X[g] = d->g[g].gram_operand(); ga.C[g] = d_C[g].p; }
                 ga.count_bytes = count_bytes; ga.partials = d_partials.as<double>();
                 ga.d_pairs = d_pairs.as<uint16_t>(); ga.gram = d_gram.as<double>();
                 cudaEvent_t ev0, ev1;

@@ -4,13 +4,14 @@
 // estimation.rs:56-71).
 //
 // Contraction:  [slots x n] (multiplicities, A operand)  x  [n x P'] (Z, B operand), per group.
-//   * A[i][b] = c[i,b] * w_i : counts arrive as uint8/uint16 tiles by TMA bulk copy and are widened
-//     once per CTA tile into an fp64 shared-memory tile (exact: magic-number int->double, one FMA).
+//   * A[i][b] = c[i,b]: counts arrive as uint8/uint16 tiles by TMA bulk copy and are widened once per
+//     CTA tile into an fp64 shared-memory tile (table lookup / exact magic-number conversion).  Sample
+//     weights live in the B operand: the design rows are sqrt(w)-scaled once at pack time (ols.rs:68-78).
 //   * Z is never materialised (110 GB at n=1e7,K=51): z_i[(j,l)] = x_ij * x_il is formed in
 //     registers from the staged design rows while loading B fragments (one DMUL per fragment
 //     element, 1/64 of the DMMA work).  Column (j,l) order = row-major upper triangle of
 //     [x|y][x|y]^T, so G, X'Wy, the column sums (means) and sum(w) all come out of one pass.
-//   * CTA tile 128 slots x 128 columns, 8 warps (2 x 4), warp tile 64 x 32 = 8 x 4 DMMA sub-tiles,
+//   * CTA tile 128 slots x 128 columns, 8 warps (1 x 8), warp tile 128 x 16 = 16 x 2 DMMA sub-tiles,
 //     KT = 32 rows per stage, 3-4 stage TMA/mbarrier pipeline.
 //   * Split-n: the rows of a group are cut into `segs` fixed segments whose size depends only on the
 //     group's row count.  Work unit = (group, panel, column tile, segment): accumulated from zero,
@@ -29,8 +30,7 @@ namespace ob {
 constexpr int LDA = BM + 4;  // fp64 A tile row stride: 132 = 4 mod 16 -> conflict-free fragment loads
 
 struct GramKernelParams {
-    const double* X[2];
-    const double* w[2];
+    const double* X[2];     // per group: (sqrt(w)-scaled) design rows [n_pad][ldx]
     const void* C[2];
     long long n_pad[2];
     int segs[2];            // row segments per tile
@@ -42,53 +42,51 @@ struct GramKernelParams {
     const uint16_t* pairs;
 };
 
-// Widening of the count tile.  With T threads, thread (r = tid / (T/32), q = tid % (T/32)) converts columns
-// {2(T/32) e + 2q, +1} of row r for e = 0 .. 4096/(2T) - 1.  One (LDS.U16/U32 -> 2 DFMA -> STS.128) step per
-// e, so the steps of the NEXT stage are interleaved with the k-steps of the current stage's DMMA loop.
-template <typename CountT, int CSTRIDE>
+// Widening of the count tile.  Thread (r = tid / 8, q = tid % 8) converts columns {16 e + 2q, +1} of row r for
+// e = 0..7: one (LDS.U16/U32 -> 2 x int->fp64 -> STS.128) step per e, so the eight steps of the NEXT stage are
+// interleaved with the eight k-steps of the current stage's DMMA loop.  uint8 counts go through a 256-entry fp64
+// table in shared memory (no FP64-pipe work: that pipe is what the DMMAs need); uint16 counts use the exact
+// magic-number conversion (2^52 + c) - 2^52.  Sample weights are NOT applied here: the design rows are already
+// sqrt(w)-scaled (ols.rs:68-78), so A is the bare multiplicity.
+template <typename CountT>
 __device__ __forceinline__ void widen_step(const CountT* __restrict__ src, double* __restrict__ dst, int e,
-                                           double wr, double off) {
-    unsigned c0, c1;
-    if (sizeof(CountT) == 1) {
-        const unsigned v = *reinterpret_cast<const uint16_t*>(src + e * CSTRIDE);
-        c0 = v & 0xFFu; c1 = v >> 8;
-    } else {
-        const unsigned v = *reinterpret_cast<const uint32_t*>(src + e * CSTRIDE);
-        c0 = v & 0xFFFFu; c1 = v >> 16;
-    }
-    // (2^52 + c) is exact in fp64; fma(2^52 + c, w, -2^52 w) = round(c * w) in one operation
+                                           const double* __restrict__ tab) {
     double2 o;
-    o.x = fma(__hiloint2double(0x43300000, (int)c0), wr, off);
-    o.y = fma(__hiloint2double(0x43300000, (int)c1), wr, off);
-    *reinterpret_cast<double2*>(dst + e * CSTRIDE) = o;
+    if (sizeof(CountT) == 1) {
+        const unsigned v = *reinterpret_cast<const uint16_t*>(src + e * 16);
+        o.x = tab[v & 0xFFu]; o.y = tab[v >> 8];
+    } else {
+        const unsigned v = *reinterpret_cast<const uint32_t*>(src + e * 16);
+        const double two52 = 4503599627370496.0;
+        o.x = __hiloint2double(0x43300000, (int)(v & 0xFFFFu)) - two52;
+        o.y = __hiloint2double(0x43300000, (int)(v >> 16)) - two52;
+    }
+    *reinterpret_cast<double2*>(dst + e * 16) = o;
 }
 
-// NWM warps along M (slots) x 4 warps along N (columns); warp tile (128/NWM) x 32 = MI x 4 DMMA sub-tiles.
-//   NWM = 2: 8 warps, 64 x 32 warp tiles (fewest shared-memory reads per DMMA)
-//   NWM = 4: 16 warps, 32 x 32 warp tiles (4 warps per scheduler: more latency cover)
-template <typename CountT, int NWM>
-__global__ void __launch_bounds__(NWM * 128, 1) gram_kernel(const GramKernelParams p) {
-    constexpr int T = NWM * 128;            // threads
-    constexpr int MI = BM / NWM / 8;        // m sub-tiles per warp
-    constexpr int TPR = T / 32;             // widening threads per row
-    constexpr int WSTEPS = BM / (2 * TPR);  // widening steps per thread per stage
-    constexpr int CSTRIDE = 2 * TPR;
+// 8 warps; warp tile (MI*8) x (NI*8) DMMA sub-tiles:
+//   MI = 16, NI = 2: 1 x 8 warps, 128 x 16 warp tiles -- every B-fragment product x_j * x_l is formed by exactly
+//                    one warp (half the DMULs of the 2 x 4 layout); measured best (profiles/r01_gram_probe2.json)
+//   MI = 8,  NI = 4: 2 x 4 warps, 64 x 32 warp tiles  -- fewest shared-memory loads per DMMA
+template <typename CountT, int MI, int NI>
+__global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelParams p) {
+    constexpr int NWN = BN / (NI * 8);      // warps along N
+    static_assert((BM / (MI * 8)) * NWN == GRAM_THREADS / 32, "warp layout must cover the CTA tile");
     constexpr int KSTEPS = KT / 4;
-    static_assert(WSTEPS <= KSTEPS, "widening must fit in the k-step loop");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = warp / NWN, wn = warp % NWN;
     const int lk = lane & 3, lg = lane >> 2;
     const int ldx = p.ldx, NST = p.stages;
-    const bool weighted = p.w[0] != nullptr;
 
     // ---- shared memory carve-up (all regions 16-B aligned) ----
     double* As = reinterpret_cast<double*>(smem_raw);                   // [2][KT*LDA]
-    double* Xs = As + 2 * KT * LDA;                                     // [NST][KT*ldx]
-    double* Ws = Xs + (size_t)NST * KT * ldx;                           // [NST][KT]
-    CountT* Cr = reinterpret_cast<CountT*>(Ws + (size_t)NST * KT);      // [NST][KT*BM]
+    double* Tab = As + 2 * KT * LDA;                                    // [256] int -> fp64
+    double* Xs = Tab + 256;                                             // [NST][KT*ldx]
+    CountT* Cr = reinterpret_cast<CountT*>(Xs + (size_t)NST * KT * ldx);   // [NST][KT*BM]
     uint64_t* full = reinterpret_cast<uint64_t*>(Cr + (size_t)NST * KT * BM);  // [NST]
 
+    Tab[tid] = (double)tid;
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
@@ -97,11 +95,9 @@ __global__ void __launch_bounds__(NWM * 128, 1) gram_kernel(const GramKernelPara
 
     const long long u0 = p.units_total * (long long)blockIdx.x / gridDim.x;
     const long long u1 = p.units_total * (long long)(blockIdx.x + 1) / gridDim.x;
-    const uint32_t stage_bytes = (uint32_t)(KT * ldx * sizeof(double) + KT * BM * sizeof(CountT) +
-                                            (weighted ? KT * sizeof(double) : 0));
+    const uint32_t stage_bytes = (uint32_t)(KT * ldx * sizeof(double) + KT * BM * sizeof(CountT));
     uint32_t it_base = 0;  // pipeline stage counter across units (slot = it % NST, parity = (it / NST) & 1)
-    const double two52 = 4503599627370496.0;
-    const int cr = tid / TPR, cq = tid % TPR;   // widening role of this thread
+    const int cr = tid >> 3, cq = tid & 7;   // widening role of this thread
 
     for (long long u = u0; u < u1; ++u) {
         const int g = (u >= p.units0) ? 1 : 0;
@@ -117,7 +113,6 @@ __global__ void __launch_bounds__(NWM * 128, 1) gram_kernel(const GramKernelPara
 
         const double* Xg = (g ? p.X[1] : p.X[0]) + row0 * ldx;
         const CountT* Cg = reinterpret_cast<const CountT*>(g ? p.C[1] : p.C[0]) + ((long long)panel * n_pad + row0) * BM;
-        const double* wg = weighted ? (g ? p.w[1] : p.w[0]) + row0 : nullptr;
 
         auto issue = [&](int s) {  // thread 0 only
             const uint32_t it = it_base + (uint32_t)s;
@@ -126,69 +121,66 @@ __global__ void __launch_bounds__(NWM * 128, 1) gram_kernel(const GramKernelPara
             mbar_expect_tx(&full[slot], stage_bytes);
             tma_load_1d(Xs + (size_t)slot * KT * ldx, Xg + (long long)s * KT * ldx, KT * ldx * sizeof(double), &full[slot]);
             tma_load_1d(Cr + (size_t)slot * KT * BM, Cg + (long long)s * KT * BM, KT * BM * sizeof(CountT), &full[slot]);
-            if (weighted) tma_load_1d(Ws + (size_t)slot * KT, wg + (long long)s * KT, KT * sizeof(double), &full[slot]);
         };
-        auto widen_setup = [&](int s, const CountT*& src, double*& dst, double& wr, double& off) {
+        auto widen_setup = [&](int s, const CountT*& src, double*& dst) {
             const int slot = (int)((it_base + (uint32_t)s) % (uint32_t)NST);
             src = Cr + (size_t)slot * KT * BM + cr * BM + cq * 2;
             dst = As + (s & 1) * KT * LDA + cr * LDA + cq * 2;
-            wr = weighted ? Ws[(size_t)slot * KT + cr] : 1.0;
-            off = -two52 * wr;
         };
         auto wait_stage = [&](int s) {
             const uint32_t it = it_base + (uint32_t)s;
             mbar_wait(&full[it % (uint32_t)NST], (it / (uint32_t)NST) & 1u);
         };
 
-        // column pair (j,l) offsets of this thread's four B sub-tiles
-        int oj[4], ol[4];
+        // column pair (j,l) offsets of this thread's B sub-tiles
+        int oj[NI], ol[NI];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int col = nt * BN + wn * 32 + s * 8 + lg;
+        for (int s = 0; s < NI; ++s) {
+            const int col = nt * BN + wn * (NI * 8) + s * 8 + lg;
             const uint32_t pr = *reinterpret_cast<const uint32_t*>(p.pairs + 2 * col);
             oj[s] = pr & 0xFFFFu; ol[s] = pr >> 16;
         }
 
-        double acc[MI][4][2];
+        double acc[MI][NI][2];
 #pragma unroll
         for (int i = 0; i < MI; ++i)
 #pragma unroll
-            for (int s = 0; s < 4; ++s) { acc[i][s][0] = 0.0; acc[i][s][1] = 0.0; }
+            for (int s = 0; s < NI; ++s) { acc[i][s][0] = 0.0; acc[i][s][1] = 0.0; }
 
         // prologue: fill the pipeline, widen stage 0 (the only exposed widening of the unit)
         if (tid == 0)
             for (int s = 0; s < NST && s < nstages; ++s) issue(s);
         {
             wait_stage(0);
-            const CountT* src; double* dst; double wr, off;
-            widen_setup(0, src, dst, wr, off);
+            const CountT* src; double* dst;
+            widen_setup(0, src, dst);
 #pragma unroll
-            for (int e = 0; e < WSTEPS; ++e) widen_step<CountT, CSTRIDE>(src, dst, e, wr, off);
+            for (int e = 0; e < KSTEPS; ++e) widen_step<CountT>(src, dst, e, Tab);
         }
         __syncthreads();
 
         for (int s = 0; s < nstages; ++s) {
             const int slot = (int)((it_base + (uint32_t)s) % (uint32_t)NST);
             const bool has_next = s + 1 < nstages;
-            const CountT* nsrc = nullptr; double* ndst = nullptr; double nwr = 1.0, noff = 0.0;
-            if (has_next) { wait_stage(s + 1); widen_setup(s + 1, nsrc, ndst, nwr, noff); }
+            const CountT* nsrc = nullptr; double* ndst = nullptr;
+            if (has_next) { wait_stage(s + 1); widen_setup(s + 1, nsrc, ndst); }
 
             const double* abase = As + (s & 1) * KT * LDA + lk * LDA + wm * (MI * 8) + lg;
             const double* xbase = Xs + (size_t)slot * KT * ldx + lk * ldx;
 #pragma unroll
             for (int kk = 0; kk < KSTEPS; ++kk) {
-                double a[MI], b[4];
+                double a[MI], b[NI];
                 const double* arow = abase + kk * 4 * LDA;
                 const double* xrow = xbase + kk * 4 * ldx;
 #pragma unroll
                 for (int i = 0; i < MI; ++i) a[i] = arow[i * 8];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) b[t] = xrow[oj[t]] * xrow[ol[t]];
-                if (has_next && kk < WSTEPS) widen_step<CountT, CSTRIDE>(nsrc, ndst, kk, nwr, noff);  // next A tile, in the DMMA shadow
+                for (int t = 0; t < NI; ++t) b[t] = xrow[oj[t]] * xrow[ol[t]];
+                if (has_next) widen_step<CountT>(nsrc, ndst, kk, Tab);   // next stage's A tile, in the DMMA shadow
 #pragma unroll
                 for (int i = 0; i < MI; ++i)
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) dmma884(acc[i][t][0], acc[i][t][1], a[i], b[t]);
+                    for (int t = 0; t < NI; ++t) dmma884(acc[i][t][0], acc[i][t][1], a[i], b[t]);
             }
             __syncthreads();  // stage s fully consumed (X rows, its A tile) and stage s+1's A tile complete
             if (tid == 0 && s + NST < nstages) issue(s + NST);   // refill the slot stage s just released
@@ -200,8 +192,8 @@ __global__ void __launch_bounds__(NWM * 128, 1) gram_kernel(const GramKernelPara
 #pragma unroll
         for (int i = 0; i < MI; ++i)
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int m = wm * (MI * 8) + i * 8 + lg, n = wn * 32 + t * 8 + 2 * lk;
+            for (int t = 0; t < NI; ++t) {
+                const int m = wm * (MI * 8) + i * 8 + lg, n = wn * (NI * 8) + t * 8 + 2 * lk;
                 *reinterpret_cast<double2*>(out + m * BN + n) = make_double2(acc[i][t][0], acc[i][t][1]);
             }
     }
@@ -239,7 +231,7 @@ std::vector<uint16_t> gram_pair_table(int V, int ntiles) {
 }
 
 static size_t gram_smem(int ldx, int stages, int count_bytes) {
-    return sizeof(double) * (2 * KT * LDA + (size_t)stages * KT * ldx + (size_t)stages * KT) +
+    return sizeof(double) * (2 * KT * LDA + 256 + (size_t)stages * KT * ldx) +
            (size_t)stages * KT * BM * count_bytes + sizeof(uint64_t) * stages;
 }
 
@@ -270,15 +262,15 @@ GramPlan gram_make_plan(int V, int panels, const int64_t n_pad[2], int count_byt
     while (pl.stages > 2 && gram_smem(pl.ldx, pl.stages, count_bytes) > 220 * 1024) --pl.stages;
     pl.smem_bytes = gram_smem(pl.ldx, pl.stages, count_bytes);
     pl.num_partials = (int64_t)total;
-    const char* v = getenv("OBBOOT_GRAM_WARPS_M");   // tuning knob (2 or 4); default chosen by measurement
-    pl.warps_m = (v && atoi(v) == 4) ? 4 : 2;
+    const char* v = getenv("OBBOOT_GRAM_TILE");   // tuning knob: 1 = 64x32 warp tiles; default 128x16 (measured best)
+    pl.tile_variant = (v && atoi(v) == 1) ? 1 : 0;
     return pl;
 }
 
 void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEvent_t ev_main_begin, cudaEvent_t ev_main_end) {
     GramKernelParams p;
     for (int g = 0; g < 2; ++g) {
-        p.X[g] = a.X[g]; p.w[g] = a.w[g]; p.C[g] = a.C[g];
+        p.X[g] = a.X[g]; p.C[g] = a.C[g];
         p.n_pad[g] = pl.n_pad[g]; p.segs[g] = pl.segs[g]; p.seg_rows[g] = pl.seg_rows[g];
     }
     p.units0 = pl.units[0];
@@ -286,14 +278,14 @@ void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEve
     p.ldx = pl.ldx; p.panels = pl.panels; p.ntiles = pl.ntiles; p.stages = pl.stages;
     p.partials = a.partials; p.pairs = a.d_pairs;
     if (ev_main_begin) OB_CUDA(cudaEventRecord(ev_main_begin, st));
-    auto launch = [&](auto kernel, int threads) {
+    auto launch = [&](auto kernel) {
         OB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-        kernel<<<pl.grid, threads, pl.smem_bytes, st>>>(p);
+        kernel<<<pl.grid, GRAM_THREADS, pl.smem_bytes, st>>>(p);
     };
-    if (pl.warps_m == 4) {
-        if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 4>, 512); else launch(gram_kernel<uint16_t, 4>, 512);
+    if (pl.tile_variant == 1) {
+        if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 8, 4>); else launch(gram_kernel<uint16_t, 8, 4>);
     } else {
-        if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 2>, 256); else launch(gram_kernel<uint16_t, 2>, 256);
+        if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 16, 2>); else launch(gram_kernel<uint16_t, 16, 2>);
     }
     OB_CUDA(cudaGetLastError());
     if (ev_main_end) OB_CUDA(cudaEventRecord(ev_main_end, st));

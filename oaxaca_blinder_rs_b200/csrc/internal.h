@@ -40,6 +40,8 @@ struct GroupData {               // one group's packed design in HBM
     int64_t n_pad = 0;           // rows padded to a multiple of KT (zero rows)
     double* X = nullptr;         // [n_pad][ldx]: cols 0..K-1 design (intercept first), col K outcome, rest 0
     double* w = nullptr;         // [n_pad] sample weights (0 on padding) or nullptr
+    double* Xs = nullptr;        // weighted only: sqrt(w_i) * X[i][:] (ols.rs:68-78), the operand of the Gram contraction
+    const double* gram_operand() const { return Xs ? Xs : X; }
 };
 
 // ---- resample.cu ----
@@ -67,11 +69,11 @@ struct GramPlan {
     int grid;
     int64_t num_partials;         // = units[0] + units[1]
     size_t smem_bytes; int stages;
-    int warps_m;                  // 2: 8 warps (64x32 warp tiles), 4: 16 warps (32x32 warp tiles)
+    int tile_variant;             // 0: 1x8 warps, 128x16 warp tiles (default); 1: 2x4 warps, 64x32 warp tiles
 };
 GramPlan gram_make_plan(int V, int panels, const int64_t n_pad[2], int count_bytes, bool weighted, int num_sms);
 struct GramArgs {
-    const double* X[2]; const double* w[2]; const void* C[2];
+    const double* X[2]; const void* C[2];     // X: the (sqrt(w)-scaled when weighted) design
     int count_bytes;
     double* partials;            // [num_partials][BM*BN]
     const uint16_t* d_pairs;     // [ntiles*BN][2] column offsets (j,l) within a design row
@@ -123,6 +125,8 @@ void pack_count_scan(const PackArgs& a, long long* d_block_counts, long long* d_
 // pass 3: staged transpose/scatter of the rows into the packed per-group designs
 void pack_scatter(const PackArgs& a, const long long* d_block_base, GroupData ga, GroupData gb, int* d_flags,
                   cudaStream_t st);
+// Xs[i][:] = sqrt(w[i]) * X[i][:] for all V = K+1 columns (WLS as OLS on sqrt(w)-scaled data, ols.rs:68-78)
+void scale_rows_launch(const GroupData& g, int ldx, cudaStream_t st);
 // residuals of the point estimate: r = y - X beta (ols.rs:118-119) for one group
 void residuals_launch(const GroupData& g, int K, int ldx, const double* d_beta, double* d_out, cudaStream_t st);
 

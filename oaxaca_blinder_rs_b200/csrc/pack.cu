@@ -14,6 +14,8 @@
 #include "common.cuh"
 #include "internal.h"
 
+#include <algorithm>
+
 namespace ob {
 
 constexpr int PK_ROWS = 128;   // rows per block
@@ -169,6 +171,22 @@ void pack_scatter(const PackArgs& a, const long long* d_block_base, GroupData ga
     const size_t smem = sizeof(double) * (size_t)PK_ROWS * (V | 1);
     OB_CUDA(cudaFuncSetAttribute(pack_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pack_scatter_kernel<<<nb, PK_THREADS, smem, st>>>(p);
+    OB_CUDA(cudaGetLastError());
+}
+
+// ---- WLS pre-scaling: the reference runs OLS on sqrt(w)-scaled rows (ols.rs:68-78); done once here ----
+__global__ void __launch_bounds__(256) scale_rows_kernel(const double* __restrict__ X, const double* __restrict__ w,
+                                                         double* __restrict__ Xs, long long total, int ldx) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / ldx;
+        Xs[e] = sqrt(w[row]) * X[e];
+    }
+}
+
+void scale_rows_launch(const GroupData& g, int ldx, cudaStream_t st) {
+    if (!g.Xs) return;
+    const long long total = g.n_pad * (long long)ldx;
+    scale_rows_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 32), 256, 0, st>>>(g.X, g.w, g.Xs, total, ldx);
     OB_CUDA(cudaGetLastError());
 }
 
