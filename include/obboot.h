@@ -44,7 +44,8 @@ typedef enum ob_status {
 typedef enum ob_ref_kind { OB_REF_GROUP_A = 0, OB_REF_GROUP_B = 1, OB_REF_POOLED = 2, OB_REF_WEIGHTED = 3 } ob_ref_kind;
 
 typedef struct ob_ctx ob_ctx;        /* device, streams, workspace; one per calling thread (run(&self) is re-entrant) */
-typedef struct ob_design ob_design;  /* packed design of both groups, resident in HBM */
+typedef struct ob_design ob_design;  /* packed design of both groups, resident in HBM; owned by the context that
+                                        created it: destroy designs before their context */
 
 ob_status ob_device_count(int32_t* n_out);
 ob_status ob_ctx_create(int32_t device, ob_ctx** out);

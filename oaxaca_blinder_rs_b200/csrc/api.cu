@@ -20,10 +20,12 @@ struct ob_ctx {
     cudaMemPool_t pool = nullptr;   // stream-ordered workspace pool: freed blocks stay cached between calls
     cudaMemPool_t pool_pack = nullptr;   // separate pool for the pack's column staging, so its many small blocks do
                                          // not fragment the bootstrap workspace (20 GB count buffer at n = 1e7)
+    cudaMemPool_t pool_design = nullptr; // packed designs (outlive a call): their own pool, so re-packing reuses the blocks
     std::string err;
 };
 
 struct ob_design {
+    cudaStream_t stream = nullptr;   // owning context's stream: buffers come from its pack pool and are freed on it
     int device = 0;
     int K = 0, n_cont = 0, V = 0, ldx = 0;
     bool weighted = false;
@@ -109,14 +111,17 @@ int64_t pad_rows(int64_t n) { return std::max<int64_t>(KT, (n + KT - 1) / KT * K
 
 // zero-fill on the context's (non-blocking) stream: a legacy-default-stream cudaMemset would not be ordered
 // before the copies / pack kernels that follow on that stream
-void alloc_group(GroupData& g, int64_t n, int ldx, bool weighted, cudaStream_t st) {
+// Design buffers come from the context's pack pool (stream-ordered): re-packing the same shapes reuses the
+// blocks instead of paying multi-GB cudaMalloc/cudaFree (random 100s-of-ms stalls) on every call.
+void alloc_group(ob_ctx* ctx, GroupData& g, int64_t n, int ldx, bool weighted) {
+    cudaStream_t st = ctx->stream;
     g.n = n; g.n_pad = pad_rows(n);
-    OB_CUDA(cudaMalloc(&g.X, sizeof(double) * (size_t)g.n_pad * ldx));
+    OB_CUDA(cudaMallocFromPoolAsync((void**)&g.X, sizeof(double) * (size_t)g.n_pad * ldx, ctx->pool_design, st));
     OB_CUDA(cudaMemsetAsync(g.X, 0, sizeof(double) * (size_t)g.n_pad * ldx, st));
     if (weighted) {
-        OB_CUDA(cudaMalloc(&g.w, sizeof(double) * (size_t)g.n_pad));
+        OB_CUDA(cudaMallocFromPoolAsync((void**)&g.w, sizeof(double) * (size_t)g.n_pad, ctx->pool_design, st));
         OB_CUDA(cudaMemsetAsync(g.w, 0, sizeof(double) * (size_t)g.n_pad, st));
-        OB_CUDA(cudaMalloc(&g.Xs, sizeof(double) * (size_t)g.n_pad * ldx));
+        OB_CUDA(cudaMallocFromPoolAsync((void**)&g.Xs, sizeof(double) * (size_t)g.n_pad * ldx, ctx->pool_design, st));
     }
 }
 
@@ -165,9 +170,11 @@ ob_status ob_ctx_create(int32_t device, ob_ctx** out) {
         props.location.id = device;
         OB_CUDA(cudaMemPoolCreate(&ctx->pool, &props));
         OB_CUDA(cudaMemPoolCreate(&ctx->pool_pack, &props));
+        OB_CUDA(cudaMemPoolCreate(&ctx->pool_design, &props));
         unsigned long long keep = ~0ull;   // never trim on synchronisation: the workspace is reused by the next call
         OB_CUDA(cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep));
         OB_CUDA(cudaMemPoolSetAttribute(ctx->pool_pack, cudaMemPoolAttrReleaseThreshold, &keep));
+        OB_CUDA(cudaMemPoolSetAttribute(ctx->pool_design, cudaMemPoolAttrReleaseThreshold, &keep));
     });
     if (st != OB_OK) return st;
     *out = ctx.release();
@@ -180,6 +187,7 @@ void ob_ctx_destroy(ob_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->pool_pack) cudaMemPoolDestroy(ctx->pool_pack);
+    if (ctx->pool_design) cudaMemPoolDestroy(ctx->pool_design);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -195,7 +203,8 @@ int32_t ob_num_stats(int32_t K, int32_t n_norm, const int32_t* norm_has_base) {
 void ob_design_destroy(ob_design* d) {
     if (!d) return;
     cudaSetDevice(d->device);
-    for (auto& g : d->g) { if (g.X) cudaFree(g.X); if (g.w) cudaFree(g.w); if (g.Xs) cudaFree(g.Xs); }
+    cudaStream_t st = d->stream;
+    for (auto& g : d->g) { if (g.X) cudaFreeAsync(g.X, st); if (g.w) cudaFreeAsync(g.w, st); if (g.Xs) cudaFreeAsync(g.Xs, st); }
     delete d;
 }
 
@@ -226,12 +235,12 @@ ob_status ob_design_from_dense(ob_ctx* ctx, int32_t K, int32_t n_cont,
                 for (int64_t i = 0; i < ns[g]; ++i)
                     if (ws[g][i] < 0.0) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: Weights cannot be negative");  // ols.rs:60-66
         std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
-        d->device = ctx->device; d->K = K; d->n_cont = n_cont; d->V = K + 1; d->ldx = design_ldx(K + 1);
+        d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = n_cont; d->V = K + 1; d->ldx = design_ldx(K + 1);
         d->weighted = (wa != nullptr) || (wb != nullptr);
         const double* Xs[2] = {Xa, Xb};
         const double* ys[2] = {ya, yb};
         for (int g = 0; g < 2; ++g) {
-            alloc_group(d->g[g], ns[g], d->ldx, d->weighted, ctx->stream);
+            alloc_group(ctx, d->g[g], ns[g], d->ldx, d->weighted);
             if (ns[g] == 0) continue;
             OB_CUDA(cudaMemcpy2DAsync(d->g[g].X, sizeof(double) * d->ldx, Xs[g], sizeof(double) * K, sizeof(double) * K,
                                       (size_t)ns[g], cudaMemcpyHostToDevice, ctx->stream));
@@ -311,10 +320,10 @@ ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
         if (flags[0]) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: Weights cannot be negative");
 
         std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
-        d->device = ctx->device; d->K = K; d->n_cont = f->n_cont; d->V = K + 1; d->ldx = pa.ldx;
+        d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = f->n_cont; d->V = K + 1; d->ldx = pa.ldx;
         d->weighted = f->weights != nullptr;
-        alloc_group(d->g[0], tot[0], d->ldx, d->weighted, st);
-        alloc_group(d->g[1], tot[1], d->ldx, d->weighted, st);
+        alloc_group(ctx, d->g[0], tot[0], d->ldx, d->weighted);
+        alloc_group(ctx, d->g[1], tot[1], d->ldx, d->weighted);
         pack_scatter(pa, d_bc.as<long long>(), d->g[0], d->g[1], d_flags.as<int>(), st);
         for (int g = 0; g < 2; ++g) scale_rows_launch(d->g[g], d->ldx, st);
         OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));

@@ -68,7 +68,7 @@ __device__ __forceinline__ void widen_step(const CountT* __restrict__ src, doubl
 //   MI = 16, NI = 2: 1 x 8 warps, 128 x 16 warp tiles -- every B-fragment product x_j * x_l is formed by exactly
 //                    one warp (half the DMULs of the 2 x 4 layout); measured best (profiles/r01_gram_probe2.json)
 //   MI = 8,  NI = 4: 2 x 4 warps, 64 x 32 warp tiles  -- fewest shared-memory loads per DMMA
-template <typename CountT, int MI, int NI>
+template <typename CountT, int MI, int NI, int LDXC>
 __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelParams p) {
     constexpr int NWN = BN / (NI * 8);      // warps along N
     static_assert((BM / (MI * 8)) * NWN == GRAM_THREADS / 32, "warp layout must cover the CTA tile");
@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / NWN, wn = warp % NWN;
     const int lk = lane & 3, lg = lane >> 2;
-    const int ldx = p.ldx, NST = p.stages;
+    const int ldx = LDXC ? LDXC : p.ldx;   // compile-time row stride when specialised: immediate LDS offsets
+    const int NST = p.stages;
 
     // ---- shared memory carve-up (all regions 16-B aligned) ----
     double* As = reinterpret_cast<double*>(smem_raw);                   // [2][KT*LDA]
@@ -263,7 +264,7 @@ GramPlan gram_make_plan(int V, int panels, const int64_t n_pad[2], int count_byt
     pl.smem_bytes = gram_smem(pl.ldx, pl.stages, count_bytes);
     pl.num_partials = (int64_t)total;
     const char* v = getenv("OBBOOT_GRAM_TILE");   // tuning knob: 1 = 64x32 warp tiles; default 128x16 (measured best)
-    pl.tile_variant = (v && atoi(v) == 1) ? 1 : 0;
+    pl.tile_variant = v ? atoi(v) : 0;   // 0: 128x16 + compile-time stride, 1: 64x32, 2: 128x16 runtime stride
     return pl;
 }
 
@@ -282,11 +283,20 @@ void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEve
         OB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
         kernel<<<pl.grid, GRAM_THREADS, pl.smem_bytes, st>>>(p);
     };
+    // row stride specialisations (ldx = 4 mod 8): the common design widths get immediate shared-memory offsets
+#define OB_GRAM_CASE(L) case L: if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 16, 2, L>); else launch(gram_kernel<uint16_t, 16, 2, L>); break;
     if (pl.tile_variant == 1) {
-        if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 8, 4>); else launch(gram_kernel<uint16_t, 8, 4>);
+        if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 8, 4, 0>); else launch(gram_kernel<uint16_t, 8, 4, 0>);
+    } else if (pl.tile_variant == 2) {
+        if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 16, 2, 0>); else launch(gram_kernel<uint16_t, 16, 2, 0>);
     } else {
-        if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 16, 2>); else launch(gram_kernel<uint16_t, 16, 2>);
+        switch (pl.ldx) {
+            OB_GRAM_CASE(12) OB_GRAM_CASE(20) OB_GRAM_CASE(28) OB_GRAM_CASE(36) OB_GRAM_CASE(44) OB_GRAM_CASE(52)
+            OB_GRAM_CASE(60) OB_GRAM_CASE(68) OB_GRAM_CASE(76) OB_GRAM_CASE(84) OB_GRAM_CASE(92)
+            default: if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 16, 2, 0>); else launch(gram_kernel<uint16_t, 16, 2, 0>);
+        }
     }
+#undef OB_GRAM_CASE
     OB_CUDA(cudaGetLastError());
     if (ev_main_end) OB_CUDA(cudaEventRecord(ev_main_end, st));
     dim3 rg(2 * pl.panels * pl.ntiles, 4);
