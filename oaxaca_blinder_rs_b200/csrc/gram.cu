@@ -27,7 +27,15 @@
 
 namespace ob {
 
-constexpr int LDA = BM + 4;  // fp64 A tile row stride: 132 = 4 mod 16 -> conflict-free fragment loads
+constexpr int LDA = BM + 4;  // fp64 A tile row stride (64x32 layout): 132 = 4 mod 16 -> conflict-free fragment loads
+// 128x16 warp tiles read the WHOLE A tile in every warp, so its layout is fragment-major there:
+//   As[k][lg][i] = A[k][m = 8 i + lg],  offset k * LDA2 + lg * LGS + i
+// -> the 16 values a thread needs for one k-step are contiguous: 8 x LDS.128 instead of 16 x LDS.64.
+// LGS = 18 and LDA2 = 148 (LDA2 / 2 = 2 mod 8) keep both the LDS.128 fragment loads and the STS.128 widening
+// stores bank-conflict free.
+constexpr int LGS = 18;
+constexpr int LDA2 = 148;
+constexpr int A_TILE = KT * LDA2;   // doubles per A buffer (covers both layouts: KT * LDA <= KT * LDA2)
 
 struct GramKernelParams {
     const double* X[2];     // per group: (sqrt(w)-scaled) design rows [n_pad][ldx]
@@ -49,6 +57,13 @@ struct GramKernelParams {
 // magic-number conversion (2^52 + c) - 2^52.  Sample weights are NOT applied here: the design rows are already
 // sqrt(w)-scaled (ols.rs:68-78), so A is the bare multiplicity.
 template <typename CountT>
+__device__ __forceinline__ double count_to_f64(unsigned c, const double* __restrict__ tab) {
+    if (sizeof(CountT) == 1) return tab[c];
+    return __hiloint2double(0x43300000, (int)c) - 4503599627370496.0;
+}
+
+// row-major A layout (64x32 warp tiles): thread (r = tid/8, q = tid%8) converts columns {16 e + 2q, +1}
+template <typename CountT>
 __device__ __forceinline__ void widen_step(const CountT* __restrict__ src, double* __restrict__ dst, int e,
                                            const double* __restrict__ tab) {
     double2 o;
@@ -57,11 +72,20 @@ __device__ __forceinline__ void widen_step(const CountT* __restrict__ src, doubl
         o.x = tab[v & 0xFFu]; o.y = tab[v >> 8];
     } else {
         const unsigned v = *reinterpret_cast<const uint32_t*>(src + e * 16);
-        const double two52 = 4503599627370496.0;
-        o.x = __hiloint2double(0x43300000, (int)(v & 0xFFFFu)) - two52;
-        o.y = __hiloint2double(0x43300000, (int)(v >> 16)) - two52;
+        o.x = count_to_f64<CountT>(v & 0xFFFFu, tab); o.y = count_to_f64<CountT>(v >> 16, tab);
     }
     *reinterpret_cast<double2*>(dst + e * 16) = o;
+}
+
+// fragment-major A layout (128x16 warp tiles): thread (r = tid/8, lg = tid%8) converts columns m = 8 i + lg for
+// i = 2e, 2e+1 and stores them side by side (one STS.128 at As[r][lg][2e])
+template <typename CountT>
+__device__ __forceinline__ void widen_step_fm(const CountT* __restrict__ src, double* __restrict__ dst, int e,
+                                              const double* __restrict__ tab) {
+    double2 o;
+    o.x = count_to_f64<CountT>(src[e * 16], tab);
+    o.y = count_to_f64<CountT>(src[e * 16 + 8], tab);
+    *reinterpret_cast<double2*>(dst + e * 2) = o;
 }
 
 // 8 warps; warp tile (MI*8) x (NI*8) DMMA sub-tiles:
@@ -73,6 +97,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
     constexpr int NWN = BN / (NI * 8);      // warps along N
     static_assert((BM / (MI * 8)) * NWN == GRAM_THREADS / 32, "warp layout must cover the CTA tile");
     constexpr int KSTEPS = KT / 4;
+    constexpr bool FM = (MI == 16);         // fragment-major A tile (one warp row: every warp reads all of A)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / NWN, wn = warp % NWN;
@@ -81,8 +106,8 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
     const int NST = p.stages;
 
     // ---- shared memory carve-up (all regions 16-B aligned) ----
-    double* As = reinterpret_cast<double*>(smem_raw);                   // [2][KT*LDA]
-    double* Tab = As + 2 * KT * LDA;                                    // [256] int -> fp64
+    double* As = reinterpret_cast<double*>(smem_raw);                   // [2][A_TILE]
+    double* Tab = As + 2 * A_TILE;                                    // [256] int -> fp64
     double* Xs = Tab + 256;                                             // [NST][KT*ldx]
     CountT* Cr = reinterpret_cast<CountT*>(Xs + (size_t)NST * KT * ldx);   // [NST][KT*BM]
     uint64_t* full = reinterpret_cast<uint64_t*>(Cr + (size_t)NST * KT * BM);  // [NST]
@@ -125,8 +150,8 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
         };
         auto widen_setup = [&](int s, const CountT*& src, double*& dst) {
             const int slot = (int)((it_base + (uint32_t)s) % (uint32_t)NST);
-            src = Cr + (size_t)slot * KT * BM + cr * BM + cq * 2;
-            dst = As + (s & 1) * KT * LDA + cr * LDA + cq * 2;
+            src = Cr + (size_t)slot * KT * BM + cr * BM + (FM ? cq : cq * 2);
+            dst = As + (s & 1) * A_TILE + (FM ? cr * LDA2 + cq * LGS : cr * LDA + cq * 2);
         };
         auto wait_stage = [&](int s) {
             const uint32_t it = it_base + (uint32_t)s;
@@ -156,7 +181,9 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
             const CountT* src; double* dst;
             widen_setup(0, src, dst);
 #pragma unroll
-            for (int e = 0; e < KSTEPS; ++e) widen_step<CountT>(src, dst, e, Tab);
+            for (int e = 0; e < KSTEPS; ++e) {
+                if (FM) widen_step_fm<CountT>(src, dst, e, Tab); else widen_step<CountT>(src, dst, e, Tab);
+            }
         }
         __syncthreads();
 
@@ -166,18 +193,28 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
             const CountT* nsrc = nullptr; double* ndst = nullptr;
             if (has_next) { wait_stage(s + 1); widen_setup(s + 1, nsrc, ndst); }
 
-            const double* abase = As + (s & 1) * KT * LDA + lk * LDA + wm * (MI * 8) + lg;
+            const double* abase = As + (s & 1) * A_TILE + (FM ? lk * LDA2 + lg * LGS : lk * LDA + wm * (MI * 8) + lg);
             const double* xbase = Xs + (size_t)slot * KT * ldx + lk * ldx;
 #pragma unroll
             for (int kk = 0; kk < KSTEPS; ++kk) {
                 double a[MI], b[NI];
-                const double* arow = abase + kk * 4 * LDA;
+                const double* arow = abase + kk * 4 * (FM ? LDA2 : LDA);
                 const double* xrow = xbase + kk * 4 * ldx;
+                if (FM) {
 #pragma unroll
-                for (int i = 0; i < MI; ++i) a[i] = arow[i * 8];
+                    for (int i = 0; i < MI; i += 2) {
+                        const double2 v = *reinterpret_cast<const double2*>(arow + i);
+                        a[i] = v.x; a[i + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) a[i] = arow[i * 8];
+                }
 #pragma unroll
                 for (int t = 0; t < NI; ++t) b[t] = xrow[oj[t]] * xrow[ol[t]];
-                if (has_next) widen_step<CountT>(nsrc, ndst, kk, Tab);   // next stage's A tile, in the DMMA shadow
+                if (has_next) {   // next stage's A tile, in the DMMA shadow
+                    if (FM) widen_step_fm<CountT>(nsrc, ndst, kk, Tab); else widen_step<CountT>(nsrc, ndst, kk, Tab);
+                }
 #pragma unroll
                 for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -232,7 +269,7 @@ std::vector<uint16_t> gram_pair_table(int V, int ntiles) {
 }
 
 static size_t gram_smem(int ldx, int stages, int count_bytes) {
-    return sizeof(double) * (2 * KT * LDA + 256 + (size_t)stages * KT * ldx) +
+    return sizeof(double) * (2 * A_TILE + 256 + (size_t)stages * KT * ldx) +
            (size_t)stages * KT * BM * count_bytes + sizeof(uint64_t) * stages;
 }
 
