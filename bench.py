@@ -28,9 +28,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (n, n_cont, cat_levels, weights, normalize, reps, ref_kind)
-    "config3_n10M_k50_wls_yun_B2000": (10_000_000, 44, (4, 4), True, True, 2000, 0),
-    "config2_n1M_k20_B1000": (1_000_000, 20, (), False, False, 1000, 0),
+    # name: (n, n_cont, cat_levels, weights, normalize, reps, ref_kind)   [BASELINE.json configs]
+    "config3_n10M_k50_wls_yun_B2000": (10_000_000, 44, (4, 4), True, True, 2000, 0),   # configs[2]: the headline
+    "config2_n1M_k20_B1000": (1_000_000, 20, (), False, False, 1000, 0),               # configs[1]
+    "config1_n10k_wage_B500": (10_000, 2, (4,), False, False, 500, 0),                 # configs[0]: the CPU-runnable case
+    "config4_n5M_k30_rif_B1000": (5_000_000, 30, (), False, False, 1000, 0),           # configs[3]: one tau per step (--rif-tau)
+    "config5_n100M_k16_B10000": (100_000_000, 16, (), False, False, 10000, 0),         # configs[4]
     "smoke_n200k_k50_B256": (200_000, 44, (4, 4), True, True, 256, 0),
     "probe_n1M_k50_B255": (1_000_000, 44, (4, 4), True, True, 255, 0),   # ncu-sized: two full panels
 }
@@ -69,7 +72,7 @@ class ClockSampler(threading.Thread):
                  nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
-        while not self.stop_flag.is_set():
+        while True:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -78,7 +81,9 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            # NVML calls contend with the CUDA driver lock: sample sparsely (>= 1 sample is always taken under load)
+            if self.stop_flag.wait(0.5):
+                break
 
     def summary(self):
         if not self.samples:
@@ -94,11 +99,13 @@ def make_data(name):
     return d, norm, reps, ref
 
 
-def cpu_baseline(d, norm, ref, threads, reps_cpu):
+def cpu_baseline(d, norm, ref, threads, reps_cpu, rif_tau=None):
     """Times the oracle port (reference-shaped arithmetic) on `threads` host threads over reps_cpu replicates."""
     from oracle import pyoracle as orc
     from oaxaca_blinder_rs_b200 import synth
     Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
+    if rif_tau is not None:             # decompose_quantile: RIF outcome computed once per group (builder.rs:721-737)
+        ya, yb = orc.rif(ya, rif_tau), orc.rif(yb, rif_tau)
     K = Xa.shape[1]
     spec = orc.Spec(K=K, n_cont=len(d["cont"]), ref_kind=ref, norm=[orc.NormVar(m, i) for m, i in norm])
     t0 = time.perf_counter()
@@ -128,7 +135,8 @@ def run_reference(args, name):
     reps_cpu = max(threads - 1, 1)          # + the point pass = `threads` passes, one per thread
     vals = []
     for it in range(args.warmup + args.steps):
-        v, dt, _ = cpu_baseline(d, norm, ref, threads, reps_cpu)
+        v, dt, _ = cpu_baseline(d, norm, ref, threads, reps_cpu,
+                                args.rif_tau if args.rif_tau is not None else (0.5 if name.startswith("config4") else None))
         if it >= args.warmup:
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
@@ -153,6 +161,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config3_n10M_k50_wls_yun_B2000", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rif-tau", type=float, default=None, help="RIF-regression outcome at this quantile (config 4)")
     args = ap.parse_args()
     name = args.workload
     if args.impl == "reference":
@@ -189,10 +198,15 @@ def main():
     h2d = sum(t.numel() * t.element_size() for t in pinned["cont"] + pinned["cat"] + [pinned["y"], pinned["g"]]
               + ([pinned["w"]] if pinned["w"] is not None else []))
 
+    rif_tau = args.rif_tau if args.rif_tau is not None else (0.5 if name.startswith("config4") else None)
+
     def pack():
-        return ob.Design.pack(ctx, [t.numpy() for t in pinned["cont"]], [t.numpy() for t in pinned["cat"]],
-                              d["cat_levels"], pinned["y"].numpy(), None if pinned["w"] is None else pinned["w"].numpy(),
-                              pinned["g"].numpy())
+        des = ob.Design.pack(ctx, [t.numpy() for t in pinned["cont"]], [t.numpy() for t in pinned["cat"]],
+                             d["cat_levels"], pinned["y"].numpy(), None if pinned["w"] is None else pinned["w"].numpy(),
+                             pinned["g"].numpy())
+        if rif_tau is not None:          # decompose_quantile: RIF pre-step on the device (builder.rs:721-737)
+            des.apply_rif(rif_tau)
+        return des
 
     def step(design):
         if world == 1:
@@ -258,8 +272,10 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": name, "n": n, "k": K - 1, "K": K, "P": P, "reps": reps,
-                           "wls": d["weights"] is not None, "yun": bool(norm), "parallelism": f"replicate-shard x{world}",
-                           "l2": "inputs larger than L2 (design 4.2 GB, multiplicities 20 GB per step)"},
+                           "wls": d["weights"] is not None, "yun": bool(norm), "rif_tau": rif_tau,
+                           "parallelism": f"replicate-shard x{world}",
+                           "l2": "inputs larger than L2 (design %.2f GB, multiplicities %.1f GB per step)"
+                                 % (n * (K + 1) * 8 / 1e9, n * (reps / world + 1) / 1e9)},
                 "e2e": {"value": reps * args.steps / dt_e, "unit": "reps/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
@@ -276,7 +292,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cores, threads = host_threads_and_sample(d, K)
             reps_cpu = max(threads - 1, 1)
-            v, cdt, _ = cpu_baseline(d, norm, ref, threads, reps_cpu)
+            v, cdt, _ = cpu_baseline(d, norm, ref, threads, reps_cpu, rif_tau)
             line["cpu_baseline"] = {"value": v, "unit": "reps/s", "cores": threads, "kind": "port",
                                     "sample": f"{reps_cpu} replicates + point pass, full n, {cdt:.1f} s on {threads} of {cores} cores"}
         print(json.dumps(line), flush=True)
