@@ -162,6 +162,8 @@ def main():
     ap.add_argument("--workload", default="config3_n10M_k50_wls_yun_B2000", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rif-tau", type=float, default=None, help="RIF-regression outcome at this quantile (config 4)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "reps", "rows"],
+                    help="N > 1: shard replicates (mode R; every GPU holds the design) or rows (mode N; config 5)")
     args = ap.parse_args()
     name = args.workload
     if args.impl == "reference":
@@ -182,11 +184,22 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    d, norm, reps, ref = make_data(name)
-    n = d["n"]
+    shard_rows = world > 1 and (args.shard == "rows" or (args.shard == "auto" and name.startswith("config5")))
+    ctx = ob.Context(local)
+    if shard_rows:
+        # mode N: this rank generates and holds only its rows; the library exchanges column sums and per-rank Gram
+        # sums over its own NCCL communicator (results are bit-identical to one GPU)
+        from oaxaca_blinder_rs_b200 import synth
+        n_, n_cont_, cats_, wts_, normalize_, reps, ref = WORKLOADS[name]
+        d = synth.make_wage_rows(n_, n_cont_, cat_levels=cats_, weights=wts_, rank=rank, world=world)
+        norm = synth.norm_spec(d) if normalize_ else []
+        n = n_
+        ctx.init_nccl(rank, world)
+    else:
+        d, norm, reps, ref = make_data(name)
+        n = d["n"]
     K = 1 + len(d["cont"]) + sum(m - 1 for m in d["cat_levels"])
     normv = [ob.NormVar(m, i) for m, i in norm]
-    ctx = ob.Context(local)
 
     # pinned host columns for the end-to-end leg
     def pin(a):
@@ -204,12 +217,14 @@ def main():
         des = ob.Design.pack(ctx, [t.numpy() for t in pinned["cont"]], [t.numpy() for t in pinned["cat"]],
                              d["cat_levels"], pinned["y"].numpy(), None if pinned["w"] is None else pinned["w"].numpy(),
                              pinned["g"].numpy())
+        if shard_rows:
+            des.set_row_shard(d["n_a_global"], d["n_b_global"], world, rank)
         if rif_tau is not None:          # decompose_quantile: RIF pre-step on the device (builder.rs:721-737)
             des.apply_rif(rif_tau)
         return des
 
     def step(design):
-        if world == 1:
+        if world == 1 or shard_rows:
             return ob.bootstrap(design, reps, ref_kind=ref, norm=normv, seed=2026)
         return obd.bootstrap_sharded(design, reps, device=torch.device("cuda", local), ref_kind=ref, norm=normv, seed=2026)
 
@@ -273,9 +288,9 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": name, "n": n, "k": K - 1, "K": K, "P": P, "reps": reps,
                            "wls": d["weights"] is not None, "yun": bool(norm), "rif_tau": rif_tau,
-                           "parallelism": f"replicate-shard x{world}",
-                           "l2": "inputs larger than L2 (design %.2f GB, multiplicities %.1f GB per step)"
-                                 % (n * (K + 1) * 8 / 1e9, n * (reps / world + 1) / 1e9)},
+                           "parallelism": (f"row-shard x{world}" if shard_rows else f"replicate-shard x{world}"),
+                           "l2": "inputs larger than L2 (design %.2f GB, multiplicities %.1f GB per GPU per step)"
+                                 % (n * (K + 1) * 8 / 1e9 / (world if shard_rows else 1), n * (reps + 1) / world / 1e9)},
                 "e2e": {"value": reps * args.steps / dt_e, "unit": "reps/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define OBBOOT_ABI_VERSION 1
+#define OBBOOT_ABI_VERSION 2
 
 /* ---- errors: OaxacaError variants (error.rs:6-19) + device errors ------------------------- */
 typedef enum ob_status {
@@ -145,6 +145,7 @@ typedef struct ob_result {
     double ms_counts, ms_gram, ms_solve, ms_reduce, ms_total;
     double ms_gram_kernel;   /* the DMMA contraction kernel alone (ms_gram also covers the split-n partial reduction) */
     int32_t gpu_launches;    /* kernels launched by this call */
+    double ms_comm;          /* row-sharded runs: time inside the collectives (also contained in ms_counts / ms_total) */
 } ob_result;
 
 int32_t ob_num_stats(int32_t K, int32_t n_norm, const int32_t* norm_has_base);
@@ -156,6 +157,36 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* design, const ob_boot_o
 ob_status ob_reduce_stats(ob_ctx* ctx, const double* rep_stats, const int32_t* rep_status, int64_t reps, int32_t S,
                           const double* point_stats, int64_t* n_ok, double* std_err, double* p_value,
                           double* ci_lower, double* ci_upper, double* t_stat);
+
+/* ---- multi-GPU ---------------------------------------------------------------------------------
+ * Mode R (replicate sharding, the default): every GPU holds the whole design and runs ob_bootstrap_run on
+ * its [rep_begin, rep_end) with skip_reduce = 1; the host gathers the replicate rows and calls
+ * ob_reduce_stats.  No communicator is needed inside the library.
+ *
+ * Mode N (row sharding, for n too large for one HBM; BASELINE config 5): the rows of each group are cut
+ * by ob_row_shard_plan into `world` contiguous ranges (world a power of two <= 64; the cut follows the
+ * fixed summation tree of the Gram contraction, so results are bit-identical for every world size).  Rank r
+ * packs only its rows, marks the design with ob_design_set_row_shard and attaches a communicator to its
+ * context; ob_bootstrap_run then exchanges, per panel batch, the replicate column sums (all-reduce) and the
+ * per-rank Gram sums (all-gather) and returns identical statistics on every rank (residuals_b covers the
+ * local rows of group B only).  An explicit index stream, if given, holds GLOBAL row positions.
+ *
+ * Communicators: NCCL over NVLink/NVSwitch for one process per GPU (libnccl.so.2 is opened at run time;
+ * rank 0 creates the id, the host broadcasts its 128 bytes), or an in-process group for several contexts
+ * (threads) of one process. */
+#define OB_COMM_ID_BYTES 128
+ob_status ob_comm_unique_id(uint8_t* id128);
+ob_status ob_comm_init_nccl(ob_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world);
+typedef struct ob_local_group ob_local_group;
+ob_status ob_local_group_create(int32_t world, ob_local_group** out);
+void ob_local_group_destroy(ob_local_group* group);
+ob_status ob_comm_init_local(ob_ctx* ctx, ob_local_group* group, int32_t rank);
+void ob_comm_destroy(ob_ctx* ctx);
+/* rows [row_begin, row_end) of a group of n_group rows (positions within the group, frame order) that rank holds */
+ob_status ob_row_shard_plan(int64_t n_group, int32_t world, int32_t rank, int64_t* row_begin, int64_t* row_end);
+/* declares a packed design to be rank's shard of groups of n_a_global / n_b_global rows (its local row counts
+ * must equal the plan's) */
+ob_status ob_design_set_row_shard(ob_design* d, int64_t n_a_global, int64_t n_b_global, int32_t world, int32_t rank);
 
 /* Multiplicity counts of one replicate of the native stream (for the statistical validation
  * tests): counts_out [n] for group g (0 = A, 1 = B) of design d. */

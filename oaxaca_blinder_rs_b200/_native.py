@@ -21,7 +21,9 @@ STATUS_NAMES = {0: "Ok", 1: "PolarsError", 2: "ColumnNotFound", 3: "InvalidGroup
 # every symbol include/obboot.h declares (checked by tests/test_abi.py against the header)
 SYMBOLS = ["ob_abi_version", "ob_device_count", "ob_ctx_create", "ob_ctx_destroy", "ob_last_error",
            "ob_design_pack", "ob_design_from_dense", "ob_design_destroy", "ob_design_shape", "ob_design_download",
-           "ob_design_apply_rif", "ob_num_stats", "ob_bootstrap_run", "ob_reduce_stats", "ob_debug_counts"]
+           "ob_design_apply_rif", "ob_num_stats", "ob_bootstrap_run", "ob_reduce_stats", "ob_debug_counts",
+           "ob_comm_unique_id", "ob_comm_init_nccl", "ob_local_group_create", "ob_local_group_destroy",
+           "ob_comm_init_local", "ob_comm_destroy", "ob_row_shard_plan", "ob_design_set_row_shard"]
 
 
 class FrameView(C.Structure):
@@ -44,7 +46,7 @@ class Result(C.Structure):
                 ("t_stat", _DP), ("rep_stats", _DP), ("rep_status", _IP), ("rep_beta_a", _DP), ("rep_beta_b", _DP),
                 ("ms_counts", C.c_double), ("ms_gram", C.c_double), ("ms_solve", C.c_double),
                 ("ms_reduce", C.c_double), ("ms_total", C.c_double), ("ms_gram_kernel", C.c_double),
-                ("gpu_launches", C.c_int32)]
+                ("gpu_launches", C.c_int32), ("ms_comm", C.c_double)]
 
 
 def build(force: bool = False) -> str:
@@ -87,5 +89,16 @@ def lib() -> C.CDLL:
                                       _DP, _DP, _DP, _DP, _DP]
         L.ob_debug_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64, C.c_int32,
                                       C.POINTER(C.c_uint16)]
+        _U8P = C.POINTER(C.c_uint8)
+        L.ob_comm_unique_id.argtypes = [_U8P]
+        L.ob_comm_init_nccl.argtypes = [C.c_void_p, _U8P, C.c_int32, C.c_int32]
+        L.ob_local_group_create.argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
+        L.ob_local_group_destroy.argtypes = [C.c_void_p]
+        L.ob_local_group_destroy.restype = None
+        L.ob_comm_init_local.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.ob_comm_destroy.argtypes = [C.c_void_p]
+        L.ob_comm_destroy.restype = None
+        L.ob_row_shard_plan.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.ob_design_set_row_shard.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32]
         _lib = L
     return _lib

@@ -49,6 +49,29 @@ class Context:
         if st != 0:
             raise OaxacaError(st, N.lib().ob_last_error(self._h).decode())
 
+    # ---- communicators for row sharding (mode N) ----
+    def init_nccl(self, rank: int, world: int, group=None):
+        """ob_comm_init_nccl: rank 0 creates the ncclUniqueId, torch.distributed only carries its 128 bytes."""
+        import torch.distributed as dist
+        ident = (C.c_uint8 * 128)()
+        if rank == 0:
+            st = N.lib().ob_comm_unique_id(ident)
+            if st != 0:
+                raise OaxacaError(st, "ob_comm_unique_id failed (libnccl.so.2 not loadable)")
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        self.check(N.lib().ob_comm_init_nccl(self._h, ident, rank, world))
+
+    def init_local(self, group: "LocalGroup", rank: int):
+        """ob_comm_init_local: one of several contexts (threads) of this process."""
+        self.check(N.lib().ob_comm_init_local(self._h, group._h, rank))
+        self._local_group = group          # keep the group alive as long as the communicator
+
+    def comm_destroy(self):
+        if self._h:
+            N.lib().ob_comm_destroy(self._h)
+
     def close(self):
         if self._h:
             N.lib().ob_ctx_destroy(self._h)
@@ -59,6 +82,34 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class LocalGroup:
+    """ob_local_group: rendezvous of `world` contexts inside one process (threads)."""
+
+    def __init__(self, world: int):
+        self._h = C.c_void_p()
+        st = N.lib().ob_local_group_create(world, C.byref(self._h))
+        if st != 0:
+            raise OaxacaError(st, "ob_local_group_create: world must be a power of two <= 64")
+        self.world = world
+
+    def __del__(self):
+        try:
+            if self._h:
+                N.lib().ob_local_group_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+def row_shard_plan(n_group: int, world: int, rank: int):
+    """ob_row_shard_plan: [begin, end) positions (within the group, frame order) of the rows `rank` holds."""
+    b, e = C.c_int64(), C.c_int64()
+    st = N.lib().ob_row_shard_plan(n_group, world, rank, C.byref(b), C.byref(e))
+    if st != 0:
+        raise OaxacaError(st, "ob_row_shard_plan: world must be a power of two <= 64, 0 <= rank < world")
+    return b.value, e.value
 
 
 @dataclass
@@ -76,6 +127,7 @@ class Design:
         na, nb, K, nc = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
         N.lib().ob_design_shape(self._h, C.byref(na), C.byref(nb), C.byref(K), C.byref(nc))
         self.n_a, self.n_b, self.K, self.n_cont = na.value, nb.value, K.value, nc.value
+        self.n_a_global, self.n_b_global, self.world, self.rank = self.n_a, self.n_b, 1, 0
 
     @classmethod
     def from_dense(cls, ctx: Context, Xa, ya, wa, Xb, yb, wb, n_cont: int) -> "Design":
@@ -120,6 +172,14 @@ class Design:
         ya, yb, wa, wb = np.empty(self.n_a), np.empty(self.n_b), np.full(self.n_a, np.nan), np.full(self.n_b, np.nan)
         self.ctx.check(N.lib().ob_design_download(self.ctx._h, self._h, _dp(Xa), _dp(ya), _dp(wa), _dp(Xb), _dp(yb), _dp(wb)))
         return Xa, ya, wa, Xb, yb, wb
+
+    def set_row_shard(self, n_a_global: int, n_b_global: int, world: int, rank: int):
+        """ob_design_set_row_shard: this design holds rank's rows (row_shard_plan) of a world-way row split."""
+        st = N.lib().ob_design_set_row_shard(self._h, n_a_global, n_b_global, world, rank)
+        if st != 0:
+            raise OaxacaError(st, f"ob_design_set_row_shard: local rows ({self.n_a}, {self.n_b}) do not match the plan "
+                                  f"for rank {rank} of {world}")
+        self.n_a_global, self.n_b_global, self.world, self.rank = n_a_global, n_b_global, world, rank
 
     def apply_rif(self, tau: float):
         self.ctx.check(N.lib().ob_design_apply_rif(self.ctx._h, self._h, float(tau)))
@@ -168,7 +228,7 @@ def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequ
     if idx_a is not None:
         idx_a = np.ascontiguousarray(idx_a, dtype=np.uint32)
         idx_b = np.ascontiguousarray(idx_b, dtype=np.uint32)
-        assert idx_a.shape == (reps, design.n_a) and idx_b.shape == (reps, design.n_b)
+        assert idx_a.shape == (reps, design.n_a_global) and idx_b.shape == (reps, design.n_b_global)
         o.idx_a, o.idx_b = idx_a.ctypes.data_as(N._U32P), idx_b.ctypes.data_as(N._U32P)
     o.rep_begin, o.rep_end = rep_begin, rep_end
     o.skip_reduce, o.count_bits, o.max_workspace_bytes = int(skip_reduce), count_bits, max_workspace_bytes
@@ -195,7 +255,7 @@ def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequ
     out.update(total_gap=r.total_gap, n_ok=int(r.n_ok), S=S,
                two_fold=a["point_stats"][:2].copy(), three_fold=a["point_stats"][2:5].copy(),
                timings_ms=dict(counts=r.ms_counts, gram=r.ms_gram, gram_main=r.ms_gram_kernel, solve=r.ms_solve,
-                               reduce=r.ms_reduce, total=r.ms_total),
+                               reduce=r.ms_reduce, total=r.ms_total, comm=r.ms_comm),
                gpu_launches=int(r.gpu_launches))
     D = (S - 5) // 2
     out["det_expl"], out["det_unexpl"] = a["point_stats"][5:5 + D].copy(), a["point_stats"][5 + D:].copy()

@@ -21,14 +21,18 @@ struct ob_ctx {
     cudaMemPool_t pool_pack = nullptr;   // separate pool for the pack's column staging, so its many small blocks do
                                          // not fragment the bootstrap workspace (20 GB count buffer at n = 1e7)
     cudaMemPool_t pool_design = nullptr; // packed designs (outlive a call): their own pool, so re-packing reuses the blocks
+    std::unique_ptr<Comm> comm;          // row-sharding collectives (mode N); null = single GPU
     std::string err;
 };
+
+struct ob_local_group { LocalGroup* g = nullptr; int world = 0; };
 
 struct ob_design {
     cudaStream_t stream = nullptr;   // owning context's stream: buffers come from its pack pool and are freed on it
     int device = 0;
     int K = 0, n_cont = 0, V = 0, ldx = 0;
     bool weighted = false;
+    int world = 1, rank = 0;         // row sharding (mode N): this design holds rank's rows of a world-way split
     GroupData g[2];
 };
 
@@ -107,8 +111,6 @@ ob_status guarded(ob_ctx* ctx, F&& f) {
 
 [[noreturn]] void fail(ob_status c, const std::string& m) { throw StatusError{c, m}; }
 
-int64_t pad_rows(int64_t n) { return std::max<int64_t>(KT, (n + KT - 1) / KT * KT); }
-
 // zero-fill on the context's (non-blocking) stream: a legacy-default-stream cudaMemset would not be ordered
 // before the copies / pack kernels that follow on that stream
 // Design buffers come from the context's pack pool (stream-ordered): re-packing the same shapes reuses the
@@ -116,6 +118,7 @@ int64_t pad_rows(int64_t n) { return std::max<int64_t>(KT, (n + KT - 1) / KT * K
 void alloc_group(ob_ctx* ctx, GroupData& g, int64_t n, int ldx, bool weighted) {
     cudaStream_t st = ctx->stream;
     g.n = n; g.n_pad = pad_rows(n);
+    g.shard = row_shard(n, 0, 1);
     OB_CUDA(cudaMallocFromPoolAsync((void**)&g.X, sizeof(double) * (size_t)g.n_pad * ldx, ctx->pool_design, st));
     OB_CUDA(cudaMemsetAsync(g.X, 0, sizeof(double) * (size_t)g.n_pad * ldx, st));
     if (weighted) {
@@ -185,6 +188,7 @@ void ob_ctx_destroy(ob_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->comm.reset();
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->pool_pack) cudaMemPoolDestroy(ctx->pool_pack);
     if (ctx->pool_design) cudaMemPoolDestroy(ctx->pool_design);
@@ -198,6 +202,68 @@ int32_t ob_num_stats(int32_t K, int32_t n_norm, const int32_t* norm_has_base) {
     int nb = 0;
     for (int v = 0; v < n_norm; ++v) nb += (norm_has_base && norm_has_base[v]) ? 1 : 0;
     return 5 + 2 * (K + nb);
+}
+
+// ---- multi-GPU: communicators and row sharding (mode N) ----
+ob_status ob_comm_unique_id(uint8_t* id128) {
+    if (!id128) return OB_ERR_INVALID_ARG;
+    try { nccl_unique_id(id128); } catch (const StatusError&) { return OB_ERR_NCCL; } catch (const CudaError&) { return OB_ERR_CUDA; }
+    return OB_OK;
+}
+
+ob_status ob_comm_init_nccl(ob_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world) {
+    if (!ctx || !id128) return OB_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        if (world < 1 || world > MAX_SEGS || (world & (world - 1)) || rank < 0 || rank >= world)
+            fail(OB_ERR_INVALID_ARG, "world must be a power of two <= 64 and 0 <= rank < world");
+        ctx->comm.reset(comm_create_nccl(id128, rank, world));
+    });
+}
+
+ob_status ob_local_group_create(int32_t world, ob_local_group** out) {
+    if (!out || world < 1 || world > MAX_SEGS || (world & (world - 1))) return OB_ERR_INVALID_ARG;
+    auto* g = new ob_local_group;
+    g->g = local_group_create(world); g->world = world;
+    *out = g;
+    return OB_OK;
+}
+
+void ob_local_group_destroy(ob_local_group* g) {
+    if (!g) return;
+    local_group_destroy(g->g);
+    delete g;
+}
+
+ob_status ob_comm_init_local(ob_ctx* ctx, ob_local_group* group, int32_t rank) {
+    if (!ctx || !group) return OB_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        if (rank < 0 || rank >= group->world) fail(OB_ERR_INVALID_ARG, "rank outside the group");
+        ctx->comm.reset(comm_create_local(group->g, rank, ctx->device));
+    });
+}
+
+void ob_comm_destroy(ob_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->comm.reset();
+}
+
+ob_status ob_row_shard_plan(int64_t n_group, int32_t world, int32_t rank, int64_t* row_begin, int64_t* row_end) {
+    if (n_group < 0 || world < 1 || world > MAX_SEGS || (world & (world - 1)) || rank < 0 || rank >= world) return OB_ERR_INVALID_ARG;
+    const RowShard r = row_shard(n_group, rank, world);
+    if (row_begin) *row_begin = r.row_begin;
+    if (row_end) *row_end = r.row_begin + r.n_local;
+    return OB_OK;
+}
+
+ob_status ob_design_set_row_shard(ob_design* d, int64_t n_a_global, int64_t n_b_global, int32_t world, int32_t rank) {
+    if (!d || world < 1 || world > MAX_SEGS || (world & (world - 1)) || rank < 0 || rank >= world) return OB_ERR_INVALID_ARG;
+    const RowShard ra = row_shard(n_a_global, rank, world), rb = row_shard(n_b_global, rank, world);
+    if (ra.n_local != d->g[0].n || rb.n_local != d->g[1].n) return OB_ERR_INVALID_ARG;   // rows must follow ob_row_shard_plan
+    d->g[0].shard = ra; d->g[1].shard = rb;
+    d->world = world; d->rank = rank;
+    return OB_OK;
 }
 
 void ob_design_destroy(ob_design* d) {
@@ -354,6 +420,7 @@ ob_status ob_design_download(ob_ctx* ctx, const ob_design* d, double* Xa, double
 ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau) {
     if (!ctx || !d) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
+        if (d->world > 1) fail(OB_ERR_UNSUPPORTED, "RIF pre-step on a row-sharded design (the quantile needs all rows of a group)");
         for (int g = 0; g < 2; ++g) {
             const size_t sb = rif_scratch_bytes(d->g[g].n);
             DevBuf scratch(sb);
@@ -375,7 +442,12 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         if (rb < 0 || re < rb || re > o->reps) fail(OB_ERR_INVALID_ARG, "bad replicate shard");
         const int64_t nrep = re - rb;
         // builder.rs:431-435 (either group empty)
-        if (d->g[0].n == 0 || d->g[1].n == 0) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: One group has no data");
+        if (d->g[0].shard.n_global == 0 || d->g[1].shard.n_global == 0) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: One group has no data");
+        // mode N: this design is one row shard; the context must carry the matching communicator
+        Comm* comm = d->world > 1 ? ctx->comm.get() : nullptr;
+        if (d->world > 1 && (!comm || comm->world != d->world || comm->rank != d->rank))
+            fail(OB_ERR_NCCL, "row-sharded design needs ob_comm_init_* on this context with the same world/rank");
+        const int world = d->world;
         int n_base = 0, n_idx = 0;
         for (int v = 0; v < o->n_norm; ++v) {
             n_base += o->norm_has_base[v] ? 1 : 0;
@@ -390,7 +462,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         if (o->count_bits != 0 && o->count_bits != 8 && o->count_bits != 16) fail(OB_ERR_INVALID_ARG, "count_bits must be 0, 8 or 16");
         int count_bytes = o->count_bits == 16 ? 2 : 1;
 
-        res->ms_counts = res->ms_gram = res->ms_solve = res->ms_reduce = res->ms_total = res->ms_gram_kernel = 0.0;
+        res->ms_counts = res->ms_gram = res->ms_solve = res->ms_reduce = res->ms_total = res->ms_gram_kernel = res->ms_comm = 0.0;
         res->gpu_launches = 0;
         res->n_ok = 0;
         Timer t_total(st, &res->ms_total);
@@ -418,22 +490,38 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         const int Pld = ntiles * BN;
         const int64_t panels_total = (slots + BM - 1) / BM;
         const int64_t n_pad[2] = {d->g[0].n_pad, d->g[1].n_pad};
+        const int64_t n_glob[2] = {d->g[0].shard.n_global, d->g[1].shard.n_global};
+        int ranks_with_rows[2];
+        for (int g = 0; g < 2; ++g)
+            ranks_with_rows[g] = (d->g[g].shard.segs + d->g[g].shard.leaf_span - 1) / d->g[g].shard.leaf_span;
         size_t free_b = 0, total_b = 0;
         OB_CUDA(cudaMemGetInfo(&free_b, &total_b));
         const double budget = o->max_workspace_bytes > 0 ? (double)o->max_workspace_bytes
                                                          : 0.6 * ((double)free_b + (double)pool_idle_bytes(ctx));
+        const int64_t local_leaves = (int64_t)(d->g[0].shard.leaf_hi - d->g[0].shard.leaf_lo) +
+                                     (d->g[1].shard.leaf_hi - d->g[1].shard.leaf_lo);
+        DevBuf d_agree(sizeof(long long));
 
         for (int attempt = 0; attempt < 2; ++attempt) {  // second attempt only widens uint8 -> uint16 after saturation
             const double per_panel = (double)(n_pad[0] + n_pad[1]) * BM * count_bytes +
-                                     (index_mode ? (double)(d->g[0].n + d->g[1].n) * BM * 4.0 : 0.0) +
-                                     2.0 * BM * Pld * 8.0 + 2.0 * 64.0 * ntiles * (BM * BN * 8.0);
-            const double fixed = 0.0;
-            int64_t ppb = (int64_t)std::floor((budget - fixed) / per_panel);
+                                     (index_mode ? (double)(n_glob[0] + n_glob[1]) * BM * 4.0 : 0.0) +
+                                     2.0 * BM * Pld * 8.0 * (comm ? world + 2 : 1) +
+                                     (double)local_leaves * ntiles * (BM * BN * 8.0) + 2.0 * BM * 8.0;
+            int64_t ppb = (int64_t)std::floor(budget / per_panel);
             ppb = std::max<int64_t>(1, std::min<int64_t>(ppb, panels_total));
-            // reduction kernel caps a batch? no: batches only bound workspace
-            DevBuf d_C[2], d_idx[2], d_colsum(sizeof(long long) * (size_t)ppb * BM);
+            if (comm) {   // every rank must cut the same batches: the collectives run once per batch
+                long long v = ppb;
+                OB_CUDA(cudaMemcpyAsync(d_agree.p, &v, sizeof v, cudaMemcpyHostToDevice, st));
+                comm->allreduce(d_agree.p, 1, CommDType::I64, CommOp::MIN, st);
+                OB_CUDA(cudaMemcpyAsync(&v, d_agree.p, sizeof v, cudaMemcpyDeviceToHost, st));
+                OB_CUDA(cudaStreamSynchronize(st));
+                ppb = v;
+            }
+            DevBuf d_C[2], d_idx[2], d_colsum(sizeof(long long) * 2 * (size_t)ppb * BM);
             for (int g = 0; g < 2; ++g) d_C[g].alloc((size_t)ppb * n_pad[g] * BM * count_bytes);
-            DevBuf d_gram(sizeof(double) * 2 * (size_t)ppb * BM * Pld);
+            const size_t gram_elems = 2 * (size_t)ppb * BM * Pld;      // [2][slots_pad][Pld]
+            DevBuf d_gram(sizeof(double) * gram_elems);
+            DevBuf d_gram_local(comm ? sizeof(double) * gram_elems : 0), d_gathered(comm ? sizeof(double) * gram_elems * world : 0);
             bool saturated = false;
 
             GramPlan plan; int64_t plan_panels = -1;
@@ -456,43 +544,69 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
 
                 // (2) replicate generation
                 Timer t_counts(st, &res->ms_counts);
+                CountsArgs ca[2];
                 for (int g = 0; g < 2; ++g) {
-                    CountsArgs ca;
-                    ca.C = d_C[g].p; ca.count_bytes = count_bytes; ca.n = d->g[g].n; ca.n_pad = n_pad[g];
-                    ca.panels = (int)pn; ca.slots = bslots; ca.first_slot = first_slot; ca.rep0 = rep0;
-                    ca.group = g; ca.seed = o->seed;
-                    if (index_mode) {
+                    ca[g].C = d_C[g].p; ca[g].count_bytes = count_bytes; ca[g].n = d->g[g].n; ca[g].n_pad = n_pad[g];
+                    ca[g].n_global = n_glob[g]; ca[g].row_begin = d->g[g].shard.row_begin;
+                    ca[g].panels = (int)pn; ca[g].slots = bslots; ca[g].first_slot = first_slot; ca[g].rep0 = rep0;
+                    ca[g].group = g; ca[g].seed = o->seed;
+                }
+                if (index_mode) {
+                    for (int g = 0; g < 2; ++g) {
                         const uint32_t* h = (g == 0 ? o->idx_a : o->idx_b);
-                        const size_t nb = sizeof(uint32_t) * (size_t)std::max<int64_t>(brep, 1) * d->g[g].n;
+                        const size_t nb = sizeof(uint32_t) * (size_t)std::max<int64_t>(brep, 1) * n_glob[g];
                         if (d_idx[g].bytes < nb) d_idx[g].alloc(nb);
                         if (brep > 0)
-                            OB_CUDA(cudaMemcpyAsync(d_idx[g].p, h + (size_t)(rep0 + first_slot) * d->g[g].n,
-                                                    sizeof(uint32_t) * (size_t)brep * d->g[g].n, cudaMemcpyHostToDevice, st));
-                        counts_from_indices(ca, d_idx[g].as<uint32_t>(), d_flags.as<int>(), st);
+                            OB_CUDA(cudaMemcpyAsync(d_idx[g].p, h + (size_t)(rep0 + first_slot) * n_glob[g],
+                                                    sizeof(uint32_t) * (size_t)brep * n_glob[g], cudaMemcpyHostToDevice, st));
+                        counts_from_indices(ca[g], d_idx[g].as<uint32_t>(), d_flags.as<int>(), st);
                         res->gpu_launches += 1 + (brep > 0 ? (int)((brep + 32767) / 32768) : 0);
-                    } else {
-                        counts_philox(ca, d_colsum.as<long long>(), d_flags.as<int>(), st);
-                        res->gpu_launches += 1 + (brep > 0 ? 1 : 0);
+                    }
+                } else {
+                    OB_CUDA(cudaMemsetAsync(d_colsum.p, 0, d_colsum.bytes, st));
+                    for (int g = 0; g < 2; ++g) {
+                        counts_philox_body_launch(ca[g], d_colsum.as<long long>() + (size_t)g * ppb * BM, st);
+                        res->gpu_launches += 1;
+                    }
+                    // the fix-up tops every replicate up to exactly n_g draws: it needs the column sums over ALL row shards
+                    if (comm) {
+                        Timer t_c(st, &res->ms_comm);
+                        comm->allreduce(d_colsum.p, 2 * (size_t)ppb * BM, CommDType::I64, CommOp::SUM, st);
+                        t_c.stop(); OB_CUDA(cudaStreamSynchronize(st)); t_c.collect();
+                    }
+                    for (int g = 0; g < 2; ++g) {
+                        counts_philox_fixup_launch(ca[g], d_colsum.as<long long>() + (size_t)g * ppb * BM, d_flags.as<int>(), st);
+                        res->gpu_launches += brep > 0 ? 1 : 0;
                     }
                 }
                 t_counts.stop();
 
                 // (3) Gram / cross-product contraction
                 if (plan_panels != pn) {
-                    plan = gram_make_plan(V, (int)pn, n_pad, count_bytes, d->weighted, ctx->num_sms);
+                    plan = gram_make_plan(V, (int)pn, d->g, count_bytes, ctx->num_sms);
                     plan_panels = pn;
-                    d_partials.alloc(sizeof(double) * (size_t)plan.num_partials * BM * BN);
+                    d_partials.alloc(sizeof(double) * (size_t)std::max<int64_t>(plan.num_partials, 1) * BM * BN);
                 }
                 Timer t_gram(st, &res->ms_gram);
                 GramArgs ga;
                 for (int g = 0; g < 2; ++g) { ga.X[g] = d->g[g].gram_operand(); ga.C[g] = d_C[g].p; }
                 ga.count_bytes = count_bytes; ga.partials = d_partials.as<double>();
-                ga.d_pairs = d_pairs.as<uint16_t>(); ga.gram = d_gram.as<double>();
+                ga.d_pairs = d_pairs.as<uint16_t>(); ga.gram = comm ? d_gram_local.as<double>() : d_gram.as<double>();
                 cudaEvent_t ev0, ev1;
                 OB_CUDA(cudaEventCreate(&ev0)); OB_CUDA(cudaEventCreate(&ev1));
                 gram_launch(plan, ga, st, ev0, ev1);
                 res->gpu_launches += 2;
                 t_gram.stop();
+                if (comm) {
+                    // every rank's subtree sums -> all ranks; the top of the summation tree is then evaluated in fixed
+                    // order on each rank (bit-identical to the single-GPU reduction)
+                    Timer t_c(st, &res->ms_comm);
+                    const size_t batch_elems = 2 * (size_t)pn * BM * Pld;
+                    comm->allgather(d_gram_local.p, d_gathered.p, sizeof(double) * batch_elems, st);
+                    gram_combine_launch(d_gathered.as<double>(), world, ranks_with_rows, (int64_t)pn * BM * Pld, d_gram.as<double>(), st);
+                    res->gpu_launches += 1;
+                    t_c.stop(); OB_CUDA(cudaStreamSynchronize(st)); t_c.collect();
+                }
 
                 // (4) solves + decomposition epilogue
                 Timer t_solve(st, &res->ms_solve);
@@ -502,7 +616,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 sa.n_norm = o->n_norm; sa.d_norm_m = d_nm.as<int>(); sa.d_norm_off = d_noff.as<int>();
                 sa.d_norm_idx = d_nidx.as<int>(); sa.d_norm_has_base = d_nhb.as<int>();
                 sa.n_base = n_base; sa.S = S; sa.weighted = d->weighted ? 1 : 0;
-                sa.na = (double)d->g[0].n; sa.nb = (double)d->g[1].n;
+                sa.na = (double)n_glob[0]; sa.nb = (double)n_glob[1];
                 sa.stats = d_stats.as<double>() + (size_t)slot_lo * S;
                 sa.status = d_status.as<int>() + slot_lo;
                 sa.beta_a = want_beta ? d_ba.as<double>() + (size_t)slot_lo * K : nullptr;
@@ -512,6 +626,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 res->gpu_launches += 1;
                 t_solve.stop();
 
+                if (comm) comm->allreduce(d_flags.p, 4, CommDType::I32, CommOp::MAX, st);   // all ranks take the same exit
                 int flags[4];
                 OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
                 OB_CUDA(cudaStreamSynchronize(st));
@@ -526,7 +641,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
             }
             if (!saturated) break;
             count_bytes = 2;  // widen and redo
-            res->ms_counts = res->ms_gram = res->ms_solve = res->ms_gram_kernel = 0.0;
+            res->ms_counts = res->ms_gram = res->ms_solve = res->ms_gram_kernel = res->ms_comm = 0.0;
         }
 
         // ---- point estimate (builder.rs:810-811): a failure here is a hard error ----
@@ -620,7 +735,11 @@ ob_status ob_debug_counts(ob_ctx* ctx, const ob_design* d, uint64_t seed, int64_
         CountsArgs ca;
         ca.C = d_C.p; ca.count_bytes = 2; ca.n = G.n; ca.n_pad = G.n_pad; ca.panels = 1; ca.slots = 2;
         ca.first_slot = 1; ca.rep0 = rep - 1; ca.group = group; ca.seed = seed;
-        counts_philox(ca, d_colsum.as<long long>(), d_flags.as<int>(), st);
+        ca.n_global = G.shard.n_global; ca.row_begin = G.shard.row_begin;
+        if (d->world > 1) fail(OB_ERR_UNSUPPORTED, "ob_debug_counts on a row-sharded design");
+        OB_CUDA(cudaMemsetAsync(d_colsum.p, 0, d_colsum.bytes, st));
+        counts_philox_body_launch(ca, d_colsum.as<long long>(), st);
+        counts_philox_fixup_launch(ca, d_colsum.as<long long>(), d_flags.as<int>(), st);
         // slot 1 column of the single panel
         OB_CUDA(cudaMemcpy2DAsync(counts_out, sizeof(uint16_t), d_C.as<uint16_t>() + 1, sizeof(uint16_t) * BM,
                                   sizeof(uint16_t), (size_t)G.n, cudaMemcpyDeviceToHost, st));

@@ -237,9 +237,38 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
     }
 }
 
-// out[g][panel*BM + m][nt*BN + n] = sum over the tile's segment partials in ascending segment order
+// Aligned binary summation tree over LEN consecutive leaves starting at `lo` (lo < cnt): leaves >= cnt are absent
+// and skipped.  The tree shape depends on the leaf indices only, so any aligned sub-range reduced on another GPU
+// (mode N) yields the very same intermediate sums.
+template <int LEN>
+__device__ __forceinline__ double2 tree_sum(const double2* __restrict__ base, size_t stride, int lo, int cnt) {
+    if constexpr (LEN == 1) {
+        return base[(size_t)lo * stride];
+    } else {
+        double2 a = tree_sum<LEN / 2>(base, stride, lo, cnt);
+        if (lo + LEN / 2 < cnt) {
+            const double2 b = tree_sum<LEN / 2>(base, stride, lo + LEN / 2, cnt);
+            a.x += b.x; a.y += b.y;
+        }
+        return a;
+    }
+}
+
+__device__ __forceinline__ double2 tree_sum_span(const double2* __restrict__ base, size_t stride, int cnt, int span) {
+    switch (span) {
+    case 64: return tree_sum<64>(base, stride, 0, cnt);
+    case 32: return tree_sum<32>(base, stride, 0, cnt);
+    case 16: return tree_sum<16>(base, stride, 0, cnt);
+    case 8: return tree_sum<8>(base, stride, 0, cnt);
+    case 4: return tree_sum<4>(base, stride, 0, cnt);
+    case 2: return tree_sum<2>(base, stride, 0, cnt);
+    default: return tree_sum<1>(base, stride, 0, cnt);
+    }
+}
+
+// out[g][panel*BM + m][nt*BN + n] = tree sum over the tile's leaf partials held here (span = MAX_SEGS / world)
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ partials, int segs0, int segs1,
-                                                          double* __restrict__ gram, int panels, int ntiles) {
+                                                          double* __restrict__ gram, int panels, int ntiles, int span) {
     const int tile_id = blockIdx.x;
     const int tiles_g = panels * ntiles;
     const int g = tile_id / tiles_g, t = tile_id - g * tiles_g;
@@ -249,13 +278,24 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restri
     const size_t slots_pad = (size_t)panels * BM, Pld = (size_t)ntiles * BN;
     for (int e = threadIdx.x + blockIdx.y * blockDim.x; e < BM * BN / 2; e += blockDim.x * gridDim.y) {
         double2 s = make_double2(0.0, 0.0);
-        for (int q = 0; q < cnt; ++q) {
-            const double2 v = reinterpret_cast<const double2*>(partials + (first + q) * (BM * BN))[e];
-            s.x += v.x; s.y += v.y;
-        }
+        if (cnt > 0) s = tree_sum_span(reinterpret_cast<const double2*>(partials + first * (BM * BN)) + e, BM * BN / 2, cnt, span);
         const int m = (2 * e) / BN, n = (2 * e) % BN;
         double* dst = gram + ((size_t)g * slots_pad + (size_t)panel * BM + m) * Pld + (size_t)nt * BN + n;
         *reinterpret_cast<double2*>(dst) = s;
+    }
+}
+
+// mode N: the upper levels of the same tree, over the per-rank sums gathered from all GPUs
+__global__ void __launch_bounds__(256) gram_combine_kernel(const double* __restrict__ gathered, int world, int ranks0,
+                                                           int ranks1, long long per_group2, double* __restrict__ gram) {
+    // gathered [world][2][per_group] doubles; per_group2 = per_group / 2 double2 elements
+    const long long total = 2 * per_group2;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int g = e >= per_group2 ? 1 : 0;
+        const int cnt = g ? ranks1 : ranks0;
+        double2 s = make_double2(0.0, 0.0);
+        if (cnt > 0) s = tree_sum_span(reinterpret_cast<const double2*>(gathered) + e, (size_t)total, cnt, world);
+        reinterpret_cast<double2*>(gram)[e] = s;
     }
 }
 
@@ -273,25 +313,16 @@ static size_t gram_smem(int ldx, int stages, int count_bytes) {
            (size_t)stages * KT * BM * count_bytes + sizeof(uint64_t) * stages;
 }
 
-// Segment count depends on the group's (padded) row count only -- never on panels, batch or grid --
-// so the per-entry summation order is a function of the data shape alone.
-static void segment_rows(int64_t n_pad, int& segs, int& seg_rows) {
-    const int64_t stages = n_pad / KT;
-    int64_t s = std::min<int64_t>(64, std::max<int64_t>(1, stages / 4));
-    int64_t per = (stages + s - 1) / s;           // stages per segment
-    s = (stages + per - 1) / per;
-    segs = (int)s; seg_rows = (int)(per * KT);
-}
-
-GramPlan gram_make_plan(int V, int panels, const int64_t n_pad[2], int count_bytes, bool weighted, int num_sms) {
-    (void)weighted;
+GramPlan gram_make_plan(int V, int panels, const GroupData gd[2], int count_bytes, int num_sms) {
     GramPlan pl;
     pl.V = V; pl.ldx = design_ldx(V); pl.panels = panels;
     pl.ntiles = (int)((num_pairs(V) + BN - 1) / BN);
     int64_t total = 0;
+    pl.leaf_span = gd[0].shard.leaf_span;
     for (int g = 0; g < 2; ++g) {
-        pl.n_pad[g] = n_pad[g];
-        segment_rows(n_pad[g], pl.segs[g], pl.seg_rows[g]);
+        pl.n_pad[g] = gd[g].n_pad;
+        pl.segs[g] = gd[g].shard.leaf_hi - gd[g].shard.leaf_lo;     // leaves held here (fixed by the global row count)
+        pl.seg_rows[g] = gd[g].shard.seg_rows;
         pl.units[g] = (int64_t)pl.segs[g] * panels * pl.ntiles;
         total += pl.units[g];
     }
@@ -337,7 +368,15 @@ void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEve
     OB_CUDA(cudaGetLastError());
     if (ev_main_end) OB_CUDA(cudaEventRecord(ev_main_end, st));
     dim3 rg(2 * pl.panels * pl.ntiles, 4);
-    gram_reduce_kernel<<<rg, 256, 0, st>>>(a.partials, pl.segs[0], pl.segs[1], a.gram, pl.panels, pl.ntiles);
+    gram_reduce_kernel<<<rg, 256, 0, st>>>(a.partials, pl.segs[0], pl.segs[1], a.gram, pl.panels, pl.ntiles, pl.leaf_span);
+    OB_CUDA(cudaGetLastError());
+}
+
+void gram_combine_launch(const double* gathered, int world, const int ranks_with_rows[2], int64_t per_group_elems,
+                         double* gram, cudaStream_t st) {
+    const long long per2 = per_group_elems / 2;
+    const unsigned blocks = (unsigned)std::min<long long>((2 * per2 + 255) / 256, 148 * 8);
+    gram_combine_kernel<<<std::max(blocks, 1u), 256, 0, st>>>(gathered, world, ranks_with_rows[0], ranks_with_rows[1], per2, gram);
     OB_CUDA(cudaGetLastError());
 }
 

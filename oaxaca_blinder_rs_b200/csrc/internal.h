@@ -35,9 +35,50 @@ inline int design_ldx(int V) { int l = V; while ((l & 7) != 4) ++l; return l; }
 // index of pair (j,l), j <= l < V, in the row-major upper triangle
 inline int64_t pair_index(int V, int j, int l) { return (int64_t)j * V - (int64_t)j * (j - 1) / 2 + (l - j); }
 
-struct GroupData {               // one group's packed design in HBM
-    int64_t n = 0;               // valid rows
+// ---- fixed row segmentation of a group (the summation tree of the split-n Gram) ----
+// A group's padded rows are cut into `segs` <= MAX_SEGS leaf segments of seg_rows rows each (the last one
+// may be short).  Both numbers depend on the group's GLOBAL row count only -- never on panels, batches, grid
+// shape or the number of GPUs.  A tile's leaf partials are summed by the aligned binary tree over the leaf
+// index space [0, MAX_SEGS) (absent leaves are skipped), see gram_reduce in gram.cu.  Under row sharding
+// (mode N) rank r of a power-of-two world owns the aligned leaf range
+// [r * MAX_SEGS / world, (r+1) * MAX_SEGS / world): a complete subtree, so the per-rank sums combine to
+// bit-identical results for any world size.
+constexpr int MAX_SEGS = 64;
+inline int64_t pad_rows(int64_t n) { return n <= KT ? KT : (n + KT - 1) / KT * KT; }
+inline void segment_rows(int64_t n_pad, int& segs, int& seg_rows) {
+    const int64_t stages = n_pad / KT;
+    int64_t s = stages / 4 < 1 ? 1 : (stages / 4 > MAX_SEGS ? MAX_SEGS : stages / 4);
+    const int64_t per = (stages + s - 1) / s;     // stages per segment
+    s = (stages + per - 1) / per;
+    segs = (int)s; seg_rows = (int)(per * KT);
+}
+struct RowShard {
+    int64_t n_global = 0;        // rows of the whole group
+    int64_t row_begin = 0;       // position (within the group, frame order) of this shard's first row
+    int64_t n_local = 0;         // valid rows held here
+    int segs = 1, seg_rows = KT; // global segmentation
+    int leaf_lo = 0, leaf_hi = 1;// leaves owned here: [leaf_lo, leaf_hi) (possibly empty), leaf_lo aligned to MAX_SEGS / world
+    int leaf_span = MAX_SEGS;    // MAX_SEGS / world
+};
+inline RowShard row_shard(int64_t n_global, int rank, int world) {
+    RowShard r;
+    r.n_global = n_global;
+    const int64_t n_pad = pad_rows(n_global);
+    segment_rows(n_pad, r.segs, r.seg_rows);
+    r.leaf_span = MAX_SEGS / world;
+    r.leaf_lo = rank * r.leaf_span < r.segs ? rank * r.leaf_span : r.segs;
+    r.leaf_hi = (rank + 1) * r.leaf_span < r.segs ? (rank + 1) * r.leaf_span : r.segs;
+    const int64_t lo = (int64_t)r.leaf_lo * r.seg_rows, hi = (int64_t)r.leaf_hi * r.seg_rows;
+    r.row_begin = lo < n_global ? lo : n_global;
+    const int64_t row_end = hi < n_global ? hi : n_global;
+    r.n_local = row_end - r.row_begin;
+    return r;
+}
+
+struct GroupData {               // one group's packed design in HBM (the rows this GPU holds)
+    int64_t n = 0;               // valid rows held here
     int64_t n_pad = 0;           // rows padded to a multiple of KT (zero rows)
+    RowShard shard;              // how these rows sit inside the whole group (world = 1: everything)
     double* X = nullptr;         // [n_pad][ldx]: cols 0..K-1 design (intercept first), col K outcome, rest 0
     double* w = nullptr;         // [n_pad] sample weights (0 on padding) or nullptr
     double* Xs = nullptr;        // weighted only: sqrt(w_i) * X[i][:] (ols.rs:68-78), the operand of the Gram contraction
@@ -48,7 +89,9 @@ struct GroupData {               // one group's packed design in HBM
 // counts layout per group: [panels][n_pad][BM] of count_t (uint8_t or uint16_t); slot 0 of panel 0
 // is the point estimate (all ones on valid rows).
 struct CountsArgs {
-    void* C; int count_bytes; int64_t n; int64_t n_pad; int panels;
+    void* C; int count_bytes; int64_t n; int64_t n_pad; int panels;   // n, n_pad: rows held here
+    int64_t n_global = 0;         // rows of the whole group (draws per replicate); row_begin: global position of local row 0
+    int64_t row_begin = 0;
     int64_t slots;                // valid slots in this batch
     int first_slot;               // 1: slot 0 is the point estimate, replicates start at slot 1; 0: replicates from slot 0
     int64_t rep0;                 // global replicate id of local slot 0 (-1.. for the point slot)
@@ -57,21 +100,25 @@ struct CountsArgs {
 void counts_clear(const CountsArgs& a, cudaStream_t st);
 // index-stream mode: idx [reps][n] u32 on device; overflow_flag (device int) set when a count saturates
 void counts_from_indices(const CountsArgs& a, const uint32_t* d_idx, int* d_overflow, cudaStream_t st);
-// native mode: Poisson(lambda) body + exact fix-up draws; d_colsum [slots] int64 scratch; d_flags[2] ints
-void counts_philox(const CountsArgs& a, long long* d_colsum, int* d_flags, cudaStream_t st);
+// native mode, two phases: Poisson(lambda) body over the local rows (accumulates the local column sums into
+// d_colsum [panels*BM] int64, zeroed by the caller), then -- after d_colsum has been summed over all row shards --
+// the exact fix-up draws.  d_flags[0] = body overshoot, d_flags[1] = count saturated.
+void counts_philox_body_launch(const CountsArgs& a, long long* d_colsum, cudaStream_t st);
+void counts_philox_fixup_launch(const CountsArgs& a, const long long* d_colsum, int* d_flags, cudaStream_t st);
 
 // ---- gram.cu ----
 struct GramPlan {
     int V, ldx, panels, ntiles;
-    int64_t n_pad[2];
-    int segs[2], seg_rows[2];     // fixed row segmentation per group (function of n_pad only)
+    int64_t n_pad[2];             // local padded rows
+    int segs[2], seg_rows[2];     // leaves held here and rows per leaf (RowShard: function of the global row count only)
+    int leaf_span;                // MAX_SEGS / world: size of the aligned subtree this GPU reduces
     int64_t units[2];             // panels * ntiles * segs
     int grid;
     int64_t num_partials;         // = units[0] + units[1]
     size_t smem_bytes; int stages;
     int tile_variant;             // 0: 1x8 warps, 128x16 warp tiles (default); 1: 2x4 warps, 64x32 warp tiles
 };
-GramPlan gram_make_plan(int V, int panels, const int64_t n_pad[2], int count_bytes, bool weighted, int num_sms);
+GramPlan gram_make_plan(int V, int panels, const GroupData g[2], int count_bytes, int num_sms);
 struct GramArgs {
     const double* X[2]; const void* C[2];     // X: the (sqrt(w)-scaled when weighted) design
     int count_bytes;
@@ -81,6 +128,10 @@ struct GramArgs {
 };
 void gram_launch(const GramPlan& plan, const GramArgs& args, cudaStream_t st, cudaEvent_t ev_main_begin = nullptr,
                  cudaEvent_t ev_main_end = nullptr);
+// mode N: gram = aligned-tree sum over ranks of gathered [world][2][slots_pad*Pld] per-rank sums; ranks_with_rows[g]
+// = number of leading ranks that hold leaves of group g
+void gram_combine_launch(const double* gathered, int world, const int ranks_with_rows[2], int64_t per_group_elems,
+                         double* gram, cudaStream_t st);
 std::vector<uint16_t> gram_pair_table(int V, int ntiles);
 
 // ---- solve.cu ----
@@ -129,6 +180,28 @@ void pack_scatter(const PackArgs& a, const long long* d_block_base, GroupData ga
 void scale_rows_launch(const GroupData& g, int ldx, cudaStream_t st);
 // residuals of the point estimate: r = y - X beta (ols.rs:118-119) for one group
 void residuals_launch(const GroupData& g, int K, int ldx, const double* d_beta, double* d_out, cudaStream_t st);
+
+// ---- comm.cu: collectives between the GPUs of one box (mode N row sharding) ----
+// Two transports behind one interface: NCCL over NVLink/NVSwitch (one process per GPU; libnccl is dlopen'ed, the
+// communicator is bootstrapped from an ncclUniqueId the host layer broadcasts), and an in-process transport for
+// several contexts of ONE process (threads; device-to-device copies), used when a single host process drives
+// all GPUs and by the single-GPU tests of the sharded path.
+enum class CommDType { I32, I64, F64 };
+enum class CommOp { SUM, MAX, MIN };
+struct Comm {
+    int rank = 0, world = 1;
+    virtual ~Comm() = default;
+    // in place, on device memory, ordered on stream st; returns only after the result is usable on st
+    virtual void allreduce(void* buf, size_t count, CommDType dt, CommOp op, cudaStream_t st) = 0;
+    // recv [world][bytes] <- every rank's send [bytes]
+    virtual void allgather(const void* send, void* recv, size_t bytes, cudaStream_t st) = 0;
+};
+struct LocalGroup;                       // shared state of an in-process group (ob_local_group)
+LocalGroup* local_group_create(int world);
+void local_group_destroy(LocalGroup* g);
+Comm* comm_create_local(LocalGroup* g, int rank, int device);
+void nccl_unique_id(uint8_t* id128);
+Comm* comm_create_nccl(const uint8_t* id128, int rank, int world);
 
 // ---- rif.cu ----
 // in-place RIF transform (math/rif.rs:14-88) of the outcome column (col K) of a packed group

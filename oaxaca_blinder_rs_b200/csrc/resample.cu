@@ -69,7 +69,8 @@ template <typename CountT, int SH>
 __global__ void __launch_bounds__(256) counts_philox_body(CountT* __restrict__ C, long long n, long long n_pad,
                                                           long long slots, long long rep0, int first_slot, int group,
                                                           uint32_t k0, uint32_t k1, const PoissonTable tab,
-                                                          long long* __restrict__ colsum, int rows_per_block) {
+                                                          long long* __restrict__ colsum, int rows_per_block,
+                                                          long long row_begin_global) {
     const int panel = blockIdx.y;
     const int q = threadIdx.x & 7;           // 16-slot group within the panel
     const int rl = threadIdx.x >> 3;         // row lane 0..31
@@ -96,19 +97,20 @@ __global__ void __launch_bounds__(256) counts_philox_body(CountT* __restrict__ C
 #pragma unroll
         for (int e = 0; e < 16; ++e) cnt[e] = 0;
         if (row < n) {
-            const uint32_t c1 = c1base | (uint32_t)((unsigned long long)row >> 32);
+            const unsigned long long grow = (unsigned long long)(row + row_begin_global);   // streams are keyed by the GLOBAL row
+            const uint32_t c1 = c1base | (uint32_t)(grow >> 32);
             if (!tab.lambda_zero && valid) {
                 uint32_t u[20];
 #pragma unroll
                 for (int gidx = 0; gidx < (SH ? 5 : 4); ++gidx) {
                     const long long q4 = q4_first + gidx;
-                    const Philox4 r = philox4x32_10((uint32_t)row, c1, (uint32_t)q4, STREAM_BODY ^ (uint32_t)(q4 >> 32), k0, k1);
+                    const Philox4 r = philox4x32_10((uint32_t)grow, c1, (uint32_t)q4, STREAM_BODY ^ (uint32_t)(q4 >> 32), k0, k1);
                     u[4 * gidx] = r.x; u[4 * gidx + 1] = r.y; u[4 * gidx + 2] = r.z; u[4 * gidx + 3] = r.w;
                 }
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
                     if (valid & (1u << e))
-                        cnt[e] = (unsigned)poisson_draw(u[SH + e], th, tab, (uint64_t)row, c1, (uint64_t)(rep_lo + e), k0, k1);
+                        cnt[e] = (unsigned)poisson_draw(u[SH + e], th, tab, (uint64_t)grow, c1, (uint64_t)(rep_lo + e), k0, k1);
             }
             if (slot0 == 0 && first_slot == 1) cnt[0] = 1;  // point estimate
 #pragma unroll
@@ -166,10 +168,11 @@ template <typename CountT>
 __global__ void __launch_bounds__(256) counts_philox_fixup(CountT* __restrict__ C, long long n, long long n_pad,
                                                            long long slots, long long rep0, int first_slot, int group,
                                                            uint32_t k0, uint32_t k1,
-                                                           const long long* __restrict__ colsum, int* __restrict__ flags) {
+                                                           const long long* __restrict__ colsum, int* __restrict__ flags,
+                                                           long long n_global, long long row_begin_global) {
     const long long slot = first_slot + blockIdx.x;
     if (slot >= slots) return;
-    const long long need = n - colsum[slot];
+    const long long need = n_global - colsum[slot];    // colsum: summed over all row shards
     if (need < 0) { if (threadIdx.x == 0 && blockIdx.y == 0) atomicOr(&flags[0], 1); return; }
     const long long rep = rep0 + slot;
     const long long panel = slot / BM, col = slot % BM;
@@ -178,7 +181,9 @@ __global__ void __launch_bounds__(256) counts_philox_fixup(CountT* __restrict__ 
         const Philox4 r = philox4x32_10((uint32_t)j, c1base | (uint32_t)((unsigned long long)j >> 32), (uint32_t)rep,
                                         STREAM_FIXUP ^ (uint32_t)((unsigned long long)rep >> 32), k0, k1);
         const unsigned long long U = ((unsigned long long)r.x << 32) | r.y;
-        const long long row = (long long)__umul64hi(U, (unsigned long long)n);  // uniform on [0, n), bias < n / 2^64
+        // uniform on [0, n_global), bias < n / 2^64; rows outside this shard belong to another GPU
+        const long long row = (long long)__umul64hi(U, (unsigned long long)n_global) - row_begin_global;
+        if (row < 0 || row >= n) continue;
         if (bump_count<CountT>(C, (panel * n_pad + row) * BM + col)) atomicOr(&flags[1], 1);
     }
 }
@@ -192,12 +197,15 @@ __global__ void __launch_bounds__(256) counts_point_kernel(CountT* __restrict__ 
 template <typename CountT>
 __global__ void __launch_bounds__(256) counts_index_kernel(CountT* __restrict__ C, long long n, long long n_pad,
                                                            long long r0, int first_slot,
-                                                           const uint32_t* __restrict__ idx, int* __restrict__ flags) {
+                                                           const uint32_t* __restrict__ idx, int* __restrict__ flags,
+                                                           long long n_global, long long row_begin_global) {
     const long long r = r0 + blockIdx.y;  // replicate of this batch -> slot first_slot + r
     const long long slot = first_slot + r, panel = slot / BM, col = slot % BM;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const long long row = idx[r * n + i];
-        if (row >= n) { atomicOr(&flags[2], 1); continue; }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_global; i += (long long)gridDim.x * blockDim.x) {
+        long long row = idx[r * n_global + i];
+        if (row >= n_global) { atomicOr(&flags[2], 1); continue; }
+        row -= row_begin_global;
+        if (row < 0 || row >= n) continue;             // drawn row lives on another GPU
         if (bump_count<CountT>(C, (panel * n_pad + row) * BM + col)) atomicOr(&flags[1], 1);
     }
 }
@@ -209,19 +217,22 @@ void counts_clear(const CountsArgs& a, cudaStream_t st) {
 void counts_from_indices(const CountsArgs& a, const uint32_t* d_idx, int* d_flags, cudaStream_t st) {
     counts_clear(a, st);
     const int pb = (int)((a.n + 255) / 256);
+    const int pbg = (int)std::max<long long>((a.n_global + 255) / 256, 1);
     const long long reps = a.slots - a.first_slot;
-    if (a.first_slot == 1) {
+    if (a.first_slot == 1 && pb > 0) {
         if (a.count_bytes == 1) counts_point_kernel<uint8_t><<<pb, 256, 0, st>>>((uint8_t*)a.C, a.n);
         else counts_point_kernel<uint16_t><<<pb, 256, 0, st>>>((uint16_t*)a.C, a.n);
         OB_CUDA(cudaGetLastError());
     }
     for (long long done = 0; done < reps; done += 32768) {  // gridDim.y <= 65535
         const long long nb = std::min<long long>(reps - done, 32768);
-        dim3 grid((unsigned)std::min<long long>(pb, 1024), (unsigned)nb);
+        dim3 grid((unsigned)std::min<long long>(pbg, 1024), (unsigned)nb);
         if (a.count_bytes == 1)
-            counts_index_kernel<uint8_t><<<grid, 256, 0, st>>>((uint8_t*)a.C, a.n, a.n_pad, done, a.first_slot, d_idx, d_flags);
+            counts_index_kernel<uint8_t><<<grid, 256, 0, st>>>((uint8_t*)a.C, a.n, a.n_pad, done, a.first_slot, d_idx, d_flags,
+                                                               a.n_global, a.row_begin);
         else
-            counts_index_kernel<uint16_t><<<grid, 256, 0, st>>>((uint16_t*)a.C, a.n, a.n_pad, done, a.first_slot, d_idx, d_flags);
+            counts_index_kernel<uint16_t><<<grid, 256, 0, st>>>((uint16_t*)a.C, a.n, a.n_pad, done, a.first_slot, d_idx, d_flags,
+                                                                a.n_global, a.row_begin);
         OB_CUDA(cudaGetLastError());
     }
 }
@@ -244,27 +255,34 @@ static PoissonTable make_table(long long n) {
     return t;
 }
 
-void counts_philox(const CountsArgs& a, long long* d_colsum, int* d_flags, cudaStream_t st) {
-    const PoissonTable tab = make_table(a.n);
+void counts_philox_body_launch(const CountsArgs& a, long long* d_colsum, cudaStream_t st) {
+    const PoissonTable tab = make_table(a.n_global);       // lambda from the whole group's row count
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
-    OB_CUDA(cudaMemsetAsync(d_colsum, 0, sizeof(long long) * (size_t)a.panels * BM, st));
     const int rows_per_block = 2048;
     dim3 grid((unsigned)((a.n_pad + rows_per_block - 1) / rows_per_block), (unsigned)a.panels);
-    const long long nrep = a.slots - a.first_slot;
-    dim3 fgrid((unsigned)std::max<long long>(nrep, 1), 16);
     const int sh = (int)(((a.rep0 % 4) + 4) % 4);
     auto body = [&](auto ct) {
         using CT = decltype(ct);
 #define OB_BODY(SHV) counts_philox_body<CT, SHV><<<grid, 256, 0, st>>>((CT*)a.C, a.n, a.n_pad, a.slots, a.rep0, \
-            a.first_slot, a.group, k0, k1, tab, d_colsum, rows_per_block)
+            a.first_slot, a.group, k0, k1, tab, d_colsum, rows_per_block, a.row_begin)
         switch (sh) { case 0: OB_BODY(0); break; case 1: OB_BODY(1); break; case 2: OB_BODY(2); break; default: OB_BODY(3); }
 #undef OB_BODY
-        OB_CUDA(cudaGetLastError());
-        if (nrep > 0)
-            counts_philox_fixup<CT><<<fgrid, 256, 0, st>>>((CT*)a.C, a.n, a.n_pad, a.slots, a.rep0, a.first_slot,
-                                                           a.group, k0, k1, d_colsum, d_flags);
     };
     if (a.count_bytes == 1) body(uint8_t{}); else body(uint16_t{});
+    OB_CUDA(cudaGetLastError());
+}
+
+void counts_philox_fixup_launch(const CountsArgs& a, const long long* d_colsum, int* d_flags, cudaStream_t st) {
+    const long long nrep = a.slots - a.first_slot;
+    if (nrep <= 0) return;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    dim3 fgrid((unsigned)nrep, 16);
+    if (a.count_bytes == 1)
+        counts_philox_fixup<uint8_t><<<fgrid, 256, 0, st>>>((uint8_t*)a.C, a.n, a.n_pad, a.slots, a.rep0, a.first_slot,
+                                                            a.group, k0, k1, d_colsum, d_flags, a.n_global, a.row_begin);
+    else
+        counts_philox_fixup<uint16_t><<<fgrid, 256, 0, st>>>((uint16_t*)a.C, a.n, a.n_pad, a.slots, a.rep0, a.first_slot,
+                                                             a.group, k0, k1, d_colsum, d_flags, a.n_global, a.row_begin);
     OB_CUDA(cudaGetLastError());
 }
 

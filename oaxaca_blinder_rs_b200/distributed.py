@@ -1,7 +1,13 @@
-"""Replicate sharding across GPUs (mode R): one process per GPU, every rank holds the
-full packed design, rank r computes a contiguous range of global replicate ids with the counter-based
-stream keyed by global id, one all-gather of the [reps_r x S] statistics block, then every rank reduces
-the identical gathered array.  Plumbing only (torch.distributed: NCCL on GPUs, gloo in CPU tests).
+"""Multi-GPU plumbing; one process per GPU.
+
+Mode R, replicate sharding: every rank holds the full packed design, rank r computes a contiguous range of
+global replicate ids with the counter-based stream keyed by global id, one all-gather of the
+[reps_r x S] statistics block, then every rank reduces the identical gathered array (torch.distributed:
+NCCL on GPUs, gloo in CPU tests).
+
+Mode N, row sharding (n too large for one HBM): shard_frame() selects the rows of each group that
+ob_row_shard_plan assigns to this rank; the packed shard is marked with set_row_shard and the library itself
+exchanges column sums and per-rank Gram sums over its own NCCL communicator (Context.init_nccl).
 """
 from __future__ import annotations
 
@@ -64,3 +70,30 @@ def bootstrap_sharded(design, reps: int, group=None, device=None, **kw) -> dict:
     out.update(red)
     out["rep_stats"], out["rep_status"] = stats, status
     return out
+
+
+def shard_frame(d: dict, rank: int, world: int) -> dict:
+    """Rows of the frame `d` (synth.make_wage layout) that rank holds under row sharding: for each group the
+    contiguous range ob_row_shard_plan gives, in frame order.  Adds n_a_global / n_b_global."""
+    from . import core
+    grp = d["group"]
+    pos_a = np.cumsum(grp == 0) - 1          # position of each row inside its group (frame order)
+    pos_b = np.cumsum(grp == 1) - 1
+    na, nb = int((grp == 0).sum()), int((grp == 1).sum())
+    a0, a1 = core.row_shard_plan(na, world, rank)
+    b0, b1 = core.row_shard_plan(nb, world, rank)
+    keep = ((grp == 0) & (pos_a >= a0) & (pos_a < a1)) | ((grp == 1) & (pos_b >= b0) & (pos_b < b1))
+    out = dict(n=int(keep.sum()), cont=[c[keep] for c in d["cont"]], cat_codes=[c[keep] for c in d["cat_codes"]],
+               cat_levels=list(d["cat_levels"]), outcome=d["outcome"][keep],
+               weights=None if d["weights"] is None else d["weights"][keep], group=grp[keep],
+               n_a_global=na, n_b_global=nb)
+    return out
+
+
+def pack_row_shard(ctx, d: dict, rank: int, world: int):
+    """Packs this rank's rows and marks the design as a row shard (mode N)."""
+    from . import core
+    loc = d if "n_a_global" in d else shard_frame(d, rank, world)
+    des = core.Design.pack(ctx, loc["cont"], loc["cat_codes"], loc["cat_levels"], loc["outcome"], loc["weights"], loc["group"])
+    des.set_row_shard(loc["n_a_global"], loc["n_b_global"], world, rank)
+    return des

@@ -1,0 +1,181 @@
+"""Row sharding (mode N).
+
+CPU part: ob_row_shard_plan (pure host function of the C ABI) tiles every group contiguously, follows the
+fixed summation tree (cuts at multiples of the leaf size, identical for every world size), and
+distributed.shard_frame selects exactly those rows -- also checked across 2 gloo ranks.
+
+GPU part (one device is enough): `world` contexts of one process (threads, in-process communicator) each hold
+one row shard; statistics must be BIT-IDENTICAL to the unsharded run on the same device, for the native
+Philox stream and for an explicit index stream, including when the workspace budget forces several batches.
+"""
+import os
+import sys
+import threading
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_version_and_plan_tiles_rows():
+    from oaxaca_blinder_rs_b200 import core, _native
+    _native.build()
+    for n in (0, 1, 31, 32, 33, 1000, 4096, 8191, 8192, 8193, 100_003, 5_000_000, 49_999_871):
+        for world in (1, 2, 4, 8, 16, 64):
+            cuts = [core.row_shard_plan(n, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:])), (n, world, cuts)
+            assert all(0 <= b <= e <= n for b, e in cuts)
+            # cuts of a coarser world are a subset of the cuts of a finer one (aligned subtrees)
+            if world > 1:
+                coarse = {c[0] for c in (core.row_shard_plan(n, world // 2, r) for r in range(world // 2))}
+                assert coarse <= {c[0] for c in cuts}
+            # interior cuts are multiples of the pipeline stage (32 rows)
+            assert all(b % 32 == 0 or b == n for b, _ in cuts)
+    # large groups are spread evenly (within one leaf)
+    cuts = [core.row_shard_plan(50_000_000, 8, r) for r in range(8)]
+    sizes = [e - b for b, e in cuts]
+    assert max(sizes) - min(sizes) <= 50_000_000 // 64 + 64
+
+
+def test_plan_rejects_bad_worlds():
+    from oaxaca_blinder_rs_b200 import core
+    for world, rank in ((3, 0), (0, 0), (128, 0), (2, 2), (2, -1)):
+        with pytest.raises(core.OaxacaError):
+            core.row_shard_plan(1000, world, rank)
+
+
+def _gloo_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from oaxaca_blinder_rs_b200 import distributed as obd, synth
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    d = synth.make_wage(20_011, 3, cat_levels=(3,), weights=True, seed=5)
+    loc = obd.shard_frame(d, rank, world)
+    # every rank reports its local group sizes and a checksum of its rows; the union must be the frame
+    t = torch.tensor([float((loc["group"] == 0).sum()), float((loc["group"] == 1).sum()), float(loc["outcome"].sum()),
+                      float(loc["weights"].sum())], dtype=torch.float64)
+    parts = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    q.put((rank, [p.tolist() for p in parts], loc["n_a_global"], loc["n_b_global"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_frame_partitions_the_frame_gloo():
+    from oaxaca_blinder_rs_b200 import synth
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    d = synth.make_wage(20_011, 3, cat_levels=(3,), weights=True, seed=5)
+    na, nb = int((d["group"] == 0).sum()), int((d["group"] == 1).sum())
+    for rank, parts, nag, nbg in got:
+        assert (nag, nbg) == (na, nb)
+        assert sum(p[0] for p in parts) == na and sum(p[1] for p in parts) == nb
+        assert abs(sum(p[2] for p in parts) - d["outcome"].sum()) < 1e-6
+        assert abs(sum(p[3] for p in parts) - d["weights"].sum()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------- GPU
+def _run_sharded(d, world, reps, norm, ref_kind, seed=None, idx=None, max_ws=0):
+    """`world` threads, one context + one row shard each, in-process communicator; returns rank outputs."""
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import core, distributed as obd
+    grp = core.LocalGroup(world)
+    outs, errs = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            ctx = ob.Context(0)
+            ctx.init_local(grp, r)
+            des = obd.pack_row_shard(ctx, d, r, world)
+            kw = dict(seed=seed) if idx is None else dict(idx_a=idx[0], idx_b=idx[1])
+            outs[r] = ob.bootstrap(des, reps, ref_kind=ref_kind, norm=norm, want_rep=True, max_workspace_bytes=max_ws, **kw)
+            des.close()
+            ctx.close()
+        except Exception as e:  # noqa: BLE001
+            errs[r] = e
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert all(e is None for e in errs), errs
+    return outs
+
+
+def _same(a, b):
+    return np.array_equal(np.nan_to_num(np.asarray(a), nan=-7.0), np.nan_to_num(np.asarray(b), nan=-7.0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_row_sharded_native_stream_is_bit_identical(world):
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(60_000, 4, cat_levels=(4,), weights=True, seed=11)
+    norm = [ob.NormVar(m, i) for m, i in synth.norm_spec(d)]
+    reps = 300
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+    one = ob.bootstrap(des, reps, ref_kind=ob.REF_POOLED, norm=norm, seed=77, want_rep=True)
+    des.close(); ctx.close()
+    # small budget -> 1-2 panels per batch on the shards -> 2-3 batches, exercising the per-batch collectives
+    outs = _run_sharded(d, world, reps, norm, ob.REF_POOLED, seed=77, max_ws=16_000_000)
+    for o in outs:
+        assert o["n_ok"] == one["n_ok"] == reps
+        for k in ("point_stats", "rep_stats", "rep_beta_a", "rep_beta_b", "std_err", "ci_lower", "ci_upper", "p_value"):
+            assert _same(o[k], one[k]), k
+        assert o["total_gap"] == one["total_gap"]
+    # residuals_b of the shards concatenate to the unsharded vector
+    assert _same(np.concatenate([o["residuals_b"] for o in outs]), one["residuals_b"])
+
+
+@pytest.mark.gpu
+def test_row_sharded_batched_and_uneven(orc):
+    """Tiny uneven groups (the last ranks hold few or no rows), several panel batches, explicit index stream:
+    bit-identical to one GPU and within 1e-10 of the oracle."""
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(3_001, 2, cat_levels=(), weights=False, seed=3)
+    Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
+    reps = 260
+    ia, ib = orc.index_stream(5, reps, 0, len(ya)), orc.index_stream(5, reps, 1, len(yb))
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+    one = ob.bootstrap(des, reps, idx_a=ia, idx_b=ib, want_rep=True)
+    des.close(); ctx.close()
+    outs = _run_sharded(d, 4, reps, [], ob.REF_GROUP_A, idx=(ia, ib), max_ws=6_000_000)
+    for o in outs:
+        for k in ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper"):
+            assert _same(o[k], one[k]), k
+    spec = orc.Spec(K=des.K, n_cont=2)
+    ref = orc.run(spec, Xa, ya, None, Xb, yb, None, reps, ia, ib, nthreads=4)
+    err = np.max(np.abs(outs[0]["rep_stats"] - ref["rep_stats"])) / max(1.0, np.max(np.abs(ref["rep_stats"])))
+    assert err <= 1e-10, err      # north_star tolerance: 1e-10 relative
+
+
+@pytest.mark.gpu
+def test_sharded_design_without_communicator_fails_loudly():
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import synth, distributed as obd
+    d = synth.make_wage(5_000, 2, seed=1)
+    ctx = ob.Context(0)
+    des = obd.pack_row_shard(ctx, d, 0, 2)
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.bootstrap(des, 8, seed=1)
+    assert e.value.kind == "NcclError"
+    with pytest.raises(ob.OaxacaError):
+        des.set_row_shard(des.n_a_global + 5, des.n_b_global, 2, 0)     # local rows no longer match the plan
+    des.close(); ctx.close()
