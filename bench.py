@@ -36,6 +36,7 @@ WORKLOADS = {
     "config5_n100M_k16_B10000": (100_000_000, 16, (), False, False, 10000, 0),         # configs[4]
     "smoke_n200k_k50_B256": (200_000, 44, (4, 4), True, True, 256, 0),
     "probe_n1M_k50_B255": (1_000_000, 44, (4, 4), True, True, 255, 0),   # ncu-sized: two full panels
+    "probe5_n20M_k16_B2000": (20_000_000, 16, (), False, False, 2000, 0),  # config-5 column shape (1 full + 1 half tile)
 }
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool (profiles/r01_fp64_peaks.json): DMMA.8x8x4 issue peak
 FP64_CUBLAS_DGEMM_TFLOPS = 35.4  # measured on this pool (profiles/r01_dgemm_peak.json): cuBLAS DGEMM 8192^3

@@ -486,8 +486,8 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         DevBuf d_flags(sizeof(int) * 4);
 
         // ---- batch the multiplicity matrix by panels under the workspace budget ----
-        const int ntiles = (int)((num_pairs(V) + BN - 1) / BN);
-        const int Pld = ntiles * BN;
+        const int ntiles = gram_ntiles(V);
+        const int Pld = gram_pld(V);
         const int64_t panels_total = (slots + BM - 1) / BM;
         const int64_t n_pad[2] = {d->g[0].n_pad, d->g[1].n_pad};
         const int64_t n_glob[2] = {d->g[0].shard.n_global, d->g[1].shard.n_global};

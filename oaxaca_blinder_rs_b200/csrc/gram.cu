@@ -12,13 +12,15 @@
 //     element, 1/64 of the DMMA work).  Column (j,l) order = row-major upper triangle of
 //     [x|y][x|y]^T, so G, X'Wy, the column sums (means) and sum(w) all come out of one pass.
 //   * CTA tile 128 slots x 128 columns, 8 warps (1 x 8), warp tile 128 x 16 = 16 x 2 DMMA sub-tiles,
-//     KT = 32 rows per stage, 3-4 stage TMA/mbarrier pipeline.
-//   * Split-n: the rows of a group are cut into `segs` fixed segments whose size depends only on the
-//     group's row count.  Work unit = (group, panel, column tile, segment): accumulated from zero,
-//     flushed as one partial tile.  A persistent grid of one CTA per SM walks equal contiguous unit
-//     ranges; gram_reduce sums a tile's partials in ascending segment order.  The summation tree of
-//     every Gram entry is therefore fixed by (n_g, K) alone: results are bit-identical run to run and
-//     do not depend on how replicates are batched or sharded over GPUs.
+//     KT = 32 rows per stage, 3-4 stage TMA/mbarrier pipeline.  When the last column tile would be less
+//     than half full it is a half-width tile (128 x 64, warp tile 128 x 8): K = 17 costs 1.5 tiles, not 2.
+//   * Split-n: the rows of a group are cut into <= 64 fixed leaf segments whose size depends only on the
+//     group's GLOBAL row count.  Work unit = (group, panel, segment, column tile): accumulated from zero,
+//     flushed as one partial tile.  A persistent grid of one CTA per SM walks cost-balanced contiguous
+//     unit ranges; gram_reduce sums a tile's leaf partials by a fixed aligned binary tree.  The summation
+//     tree of every Gram entry is therefore fixed by (n_g, K) alone: results are bit-identical run to
+//     run and do not depend on how replicates are batched, or on how replicates (mode R) or rows (mode
+//     N: each GPU reduces an aligned subtree, gram_combine evaluates the top levels) are sharded.
 #include "common.cuh"
 #include "internal.h"
 
@@ -27,58 +29,42 @@
 
 namespace ob {
 
-constexpr int LDA = BM + 4;  // fp64 A tile row stride (64x32 layout): 132 = 4 mod 16 -> conflict-free fragment loads
-// 128x16 warp tiles read the WHOLE A tile in every warp, so its layout is fragment-major there:
+// Every warp reads A fragments of 8 k-rows x (MI*8) slots, so the fp64 A tile is fragment-major:
 //   As[k][lg][i] = A[k][m = 8 i + lg],  offset k * LDA2 + lg * LGS + i
-// -> the 16 values a thread needs for one k-step are contiguous: 8 x LDS.128 instead of 16 x LDS.64.
+// -> the MI values a thread needs for one k-step are contiguous: MI/2 x LDS.128 instead of MI x LDS.64.
 // LGS = 18 and LDA2 = 148 (LDA2 / 2 = 2 mod 8) keep both the LDS.128 fragment loads and the STS.128 widening
 // stores bank-conflict free.
 constexpr int LGS = 18;
 constexpr int LDA2 = 148;
-constexpr int A_TILE = KT * LDA2;   // doubles per A buffer (covers both layouts: KT * LDA <= KT * LDA2)
+constexpr int A_TILE = KT * LDA2;   // doubles per A buffer
+constexpr int BNH = BN / 2;         // width of the optional half-width tail tile
 
 struct GramKernelParams {
     const double* X[2];     // per group: (sqrt(w)-scaled) design rows [n_pad][ldx]
     const void* C[2];
     long long n_pad[2];
-    int segs[2];            // row segments per tile
+    int segs[2];            // row segments (leaves) held here, per group
     int seg_rows[2];        // rows per segment (multiple of KT)
     long long units0;       // units of group 0 = panels * ntiles * segs[0]
     long long units_total;
     int ldx, panels, ntiles, stages;
-    double* partials;       // [units_total][BM*BN], unit-major
+    int nfull, has_half;    // column tiling: nfull tiles of BN columns + (has_half ? one tile of BN/2 : none)
+    double* partials;       // [units_total][BM*BN], unit-major (a half tile uses the first BM*BN/2 doubles, stride BN/2)
     const uint16_t* pairs;
 };
 
-// Widening of the count tile.  Thread (r = tid / 8, q = tid % 8) converts columns {16 e + 2q, +1} of row r for
-// e = 0..7: one (LDS.U16/U32 -> 2 x int->fp64 -> STS.128) step per e, so the eight steps of the NEXT stage are
-// interleaved with the eight k-steps of the current stage's DMMA loop.  uint8 counts go through a 256-entry fp64
-// table in shared memory (no FP64-pipe work: that pipe is what the DMMAs need); uint16 counts use the exact
-// magic-number conversion (2^52 + c) - 2^52.  Sample weights are NOT applied here: the design rows are already
-// sqrt(w)-scaled (ols.rs:68-78), so A is the bare multiplicity.
+// Widening of the count tile.  Thread (r = tid / 8, lg = tid % 8) converts slots m = 8 i + lg of row r, two i per
+// step (one STS.128 at As[r][lg][2e]), so the eight steps of the NEXT stage are interleaved with the eight k-steps
+// of the current stage's DMMA loop.  uint8 counts go through a 256-entry fp64 table in shared memory (no FP64-pipe
+// work: that pipe is what the DMMAs need); uint16 counts use the exact magic-number conversion (2^52 + c) - 2^52.
+// Sample weights are NOT applied here: the design rows are already sqrt(w)-scaled (ols.rs:68-78), so A is the
+// bare multiplicity.
 template <typename CountT>
 __device__ __forceinline__ double count_to_f64(unsigned c, const double* __restrict__ tab) {
     if (sizeof(CountT) == 1) return tab[c];
     return __hiloint2double(0x43300000, (int)c) - 4503599627370496.0;
 }
 
-// row-major A layout (64x32 warp tiles): thread (r = tid/8, q = tid%8) converts columns {16 e + 2q, +1}
-template <typename CountT>
-__device__ __forceinline__ void widen_step(const CountT* __restrict__ src, double* __restrict__ dst, int e,
-                                           const double* __restrict__ tab) {
-    double2 o;
-    if (sizeof(CountT) == 1) {
-        const unsigned v = *reinterpret_cast<const uint16_t*>(src + e * 16);
-        o.x = tab[v & 0xFFu]; o.y = tab[v >> 8];
-    } else {
-        const unsigned v = *reinterpret_cast<const uint32_t*>(src + e * 16);
-        o.x = count_to_f64<CountT>(v & 0xFFFFu, tab); o.y = count_to_f64<CountT>(v >> 16, tab);
-    }
-    *reinterpret_cast<double2*>(dst + e * 16) = o;
-}
-
-// fragment-major A layout (128x16 warp tiles): thread (r = tid/8, lg = tid%8) converts columns m = 8 i + lg for
-// i = 2e, 2e+1 and stores them side by side (one STS.128 at As[r][lg][2e])
 template <typename CountT>
 __device__ __forceinline__ void widen_step_fm(const CountT* __restrict__ src, double* __restrict__ dst, int e,
                                               const double* __restrict__ tab) {
@@ -88,152 +74,179 @@ __device__ __forceinline__ void widen_step_fm(const CountT* __restrict__ src, do
     *reinterpret_cast<double2*>(dst + e * 2) = o;
 }
 
-// 8 warps; warp tile (MI*8) x (NI*8) DMMA sub-tiles:
-//   MI = 16, NI = 2: 1 x 8 warps, 128 x 16 warp tiles -- every B-fragment product x_j * x_l is formed by exactly
-//                    one warp (half the DMULs of the 2 x 4 layout); measured best (profiles/r01_gram_probe2.json)
-//   MI = 8,  NI = 4: 2 x 4 warps, 64 x 32 warp tiles  -- fewest shared-memory loads per DMMA
-template <typename CountT, int MI, int NI, int LDXC>
-__global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelParams p) {
-    constexpr int NWN = BN / (NI * 8);      // warps along N
-    static_assert((BM / (MI * 8)) * NWN == GRAM_THREADS / 32, "warp layout must cover the CTA tile");
+// shared-memory view + pipeline state of a CTA
+template <typename CountT>
+struct GramCta {
+    double* As; double* Tab; double* Xs; CountT* Cr; uint64_t* full;
+    int NST; int ldx; uint32_t stage_bytes; uint32_t it_base;
+};
+
+// One work unit = (group, panel, column tile, row segment): accumulate from zero over the segment's rows, flush one
+// partial tile.  8 warps as (16/MI) x (8 / (16/MI)); warp tile (MI*8) slots x (NI*8) columns:
+//   MI = 16, NI = 2: 1 x 8 warps, 128 x 16 warp tiles, CTA tile 128 x 128 -- every B-fragment product x_j * x_l is
+//                    formed by exactly one warp; measured best for full tiles (profiles/r01_gram_probe2.json)
+//   MI = 16, NI = 1: 1 x 8 warps, 128 x 8 warp tiles, CTA tile 128 x 64  -- the half-width tail tile (measured 2 %
+//                    faster than 2 x 4 warps of 64 x 16: profiles/r01_half_tile_variants.json)
+template <typename CountT, int LDXC, int MI, int NI>
+__device__ __forceinline__ void gram_unit(GramCta<CountT>& c, const GramKernelParams& p, const double* __restrict__ Xg,
+                                          const CountT* __restrict__ Cg, int nstages, int col_base,
+                                          double* __restrict__ out) {
+    constexpr int NWM = 16 / MI, NWN = (GRAM_THREADS / 32) / NWM;
+    constexpr int TW = NWN * NI * 8;        // tile width in columns
     constexpr int KSTEPS = KT / 4;
-    constexpr bool FM = (MI == 16);         // fragment-major A tile (one warp row: every warp reads all of A)
-    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / NWN, wn = warp % NWN;
     const int lk = lane & 3, lg = lane >> 2;
-    const int ldx = LDXC ? LDXC : p.ldx;   // compile-time row stride when specialised: immediate LDS offsets
-    const int NST = p.stages;
+    const int ldx = LDXC ? LDXC : c.ldx;   // compile-time row stride when specialised: immediate LDS offsets
+    const int NST = c.NST;
+    const int cr = tid >> 3, cq = tid & 7;   // widening role of this thread
+    const uint32_t it_base = c.it_base;
 
+    auto issue = [&](int s) {  // thread 0 only
+        const uint32_t it = it_base + (uint32_t)s;
+        const int slot = (int)(it % (uint32_t)NST);
+        fence_proxy_async();
+        mbar_expect_tx(&c.full[slot], c.stage_bytes);
+        tma_load_1d(c.Xs + (size_t)slot * KT * ldx, Xg + (long long)s * KT * ldx, KT * ldx * sizeof(double), &c.full[slot]);
+        tma_load_1d(c.Cr + (size_t)slot * KT * BM, Cg + (long long)s * KT * BM, KT * BM * sizeof(CountT), &c.full[slot]);
+    };
+    auto widen_setup = [&](int s, const CountT*& src, double*& dst) {
+        const int slot = (int)((it_base + (uint32_t)s) % (uint32_t)NST);
+        src = c.Cr + (size_t)slot * KT * BM + cr * BM + cq;
+        dst = c.As + (s & 1) * A_TILE + cr * LDA2 + cq * LGS;
+    };
+    auto wait_stage = [&](int s) {
+        const uint32_t it = it_base + (uint32_t)s;
+        mbar_wait(&c.full[it % (uint32_t)NST], (it / (uint32_t)NST) & 1u);
+    };
+
+    // column pair (j,l) offsets of this thread's B sub-tiles
+    int oj[NI], ol[NI];
+#pragma unroll
+    for (int s = 0; s < NI; ++s) {
+        const int col = col_base + wn * (NI * 8) + s * 8 + lg;
+        const uint32_t pr = *reinterpret_cast<const uint32_t*>(p.pairs + 2 * col);
+        oj[s] = pr & 0xFFFFu; ol[s] = pr >> 16;
+    }
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int s = 0; s < NI; ++s) { acc[i][s][0] = 0.0; acc[i][s][1] = 0.0; }
+
+    // prologue: fill the pipeline, widen stage 0 (the only exposed widening of the unit)
+    if (tid == 0)
+        for (int s = 0; s < NST && s < nstages; ++s) issue(s);
+    {
+        wait_stage(0);
+        const CountT* src; double* dst;
+        widen_setup(0, src, dst);
+#pragma unroll
+        for (int e = 0; e < KSTEPS; ++e) widen_step_fm<CountT>(src, dst, e, c.Tab);
+    }
+    __syncthreads();
+
+    for (int s = 0; s < nstages; ++s) {
+        const int slot = (int)((it_base + (uint32_t)s) % (uint32_t)NST);
+        const bool has_next = s + 1 < nstages;
+        const CountT* nsrc = nullptr; double* ndst = nullptr;
+        if (has_next) { wait_stage(s + 1); widen_setup(s + 1, nsrc, ndst); }
+
+        const double* abase = c.As + (s & 1) * A_TILE + lk * LDA2 + lg * LGS + wm * MI;
+        const double* xbase = c.Xs + (size_t)slot * KT * ldx + lk * ldx;
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+            double a[MI], b[NI];
+            const double* arow = abase + kk * 4 * LDA2;
+            const double* xrow = xbase + kk * 4 * ldx;
+#pragma unroll
+            for (int i = 0; i < MI; i += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(arow + i);
+                a[i] = v.x; a[i + 1] = v.y;
+            }
+#pragma unroll
+            for (int t = 0; t < NI; ++t) b[t] = xrow[oj[t]] * xrow[ol[t]];
+            if (has_next) widen_step_fm<CountT>(nsrc, ndst, kk, c.Tab);   // next stage's A tile, in the DMMA shadow
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int t = 0; t < NI; ++t) dmma884(acc[i][t][0], acc[i][t][1], a[i], b[t]);
+        }
+        __syncthreads();  // stage s fully consumed (X rows, its A tile) and stage s+1's A tile complete
+        if (tid == 0 && s + NST < nstages) issue(s + NST);   // refill the slot stage s just released
+    }
+    c.it_base = it_base + (uint32_t)nstages;
+
+    // flush the partial tile [BM][TW] row-major
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int t = 0; t < NI; ++t) {
+            const int m = wm * (MI * 8) + i * 8 + lg, n = wn * (NI * 8) + t * 8 + 2 * lk;
+            *reinterpret_cast<double2*>(out + m * TW + n) = make_double2(acc[i][t][0], acc[i][t][1]);
+        }
+}
+
+// Units are walked in (group, panel, segment, column tile) order: consecutive units of a CTA sweep the column tiles
+// over the SAME rows (their X / count tiles stay in L2), and every CTA's contiguous range holds the same mix of
+// full and half-width tiles whatever their relative cost.  A half-width tile is budgeted as half a full one; CTA b
+// takes the units whose cumulative cost starts in [W b / grid, W (b+1) / grid): first unit at or after cost w --
+__device__ __forceinline__ long long unit_at_cost(const GramKernelParams& p, long long w) {
+    const long long wt = 2 * p.nfull + p.has_half;          // cost of one (panel, segment) sweep over the column tiles
+    const long long W0 = (long long)p.panels * p.segs[0] * wt;
+    long long base = 0;
+    if (w >= W0) { w -= W0; base = p.units0; }
+    const long long sweep = w / wt, r = w - sweep * wt;
+    const long long i = r < 2LL * p.nfull ? (r + 1) / 2 : (long long)p.nfull;
+    return min(base + sweep * p.ntiles + i, p.units_total);
+}
+
+template <typename CountT, int LDXC>
+__global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    GramCta<CountT> c;
+    c.ldx = LDXC ? LDXC : p.ldx;
+    c.NST = p.stages;
     // ---- shared memory carve-up (all regions 16-B aligned) ----
-    double* As = reinterpret_cast<double*>(smem_raw);                   // [2][A_TILE]
-    double* Tab = As + 2 * A_TILE;                                    // [256] int -> fp64
-    double* Xs = Tab + 256;                                             // [NST][KT*ldx]
-    CountT* Cr = reinterpret_cast<CountT*>(Xs + (size_t)NST * KT * ldx);   // [NST][KT*BM]
-    uint64_t* full = reinterpret_cast<uint64_t*>(Cr + (size_t)NST * KT * BM);  // [NST]
+    c.As = reinterpret_cast<double*>(smem_raw);                                     // [2][A_TILE]
+    c.Tab = c.As + 2 * A_TILE;                                                      // [256] int -> fp64
+    c.Xs = c.Tab + 256;                                                             // [NST][KT*ldx]
+    c.Cr = reinterpret_cast<CountT*>(c.Xs + (size_t)c.NST * KT * c.ldx);            // [NST][KT*BM]
+    c.full = reinterpret_cast<uint64_t*>(c.Cr + (size_t)c.NST * KT * BM);           // [NST]
+    c.stage_bytes = (uint32_t)(KT * c.ldx * sizeof(double) + KT * BM * sizeof(CountT));
+    c.it_base = 0;  // pipeline stage counter across units (slot = it % NST, parity = (it / NST) & 1)
 
-    Tab[tid] = (double)tid;
+    c.Tab[tid] = (double)tid;
     if (tid == 0) {
-        for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < c.NST; ++s) mbar_init(&c.full[s], 1);
         mbar_fence_init();
     }
     __syncthreads();
 
-    const long long u0 = p.units_total * (long long)blockIdx.x / gridDim.x;
-    const long long u1 = p.units_total * (long long)(blockIdx.x + 1) / gridDim.x;
-    const uint32_t stage_bytes = (uint32_t)(KT * ldx * sizeof(double) + KT * BM * sizeof(CountT));
-    uint32_t it_base = 0;  // pipeline stage counter across units (slot = it % NST, parity = (it / NST) & 1)
-    const int cr = tid >> 3, cq = tid & 7;   // widening role of this thread
+    const long long wt = 2 * p.nfull + p.has_half;
+    const long long W = (long long)p.panels * (p.segs[0] + p.segs[1]) * wt;
+    const long long u0 = unit_at_cost(p, W * (long long)blockIdx.x / gridDim.x);
+    const long long u1 = blockIdx.x + 1 == gridDim.x ? p.units_total : unit_at_cost(p, W * (long long)(blockIdx.x + 1) / gridDim.x);
 
     for (long long u = u0; u < u1; ++u) {
         const int g = (u >= p.units0) ? 1 : 0;
         const long long ug = u - (g ? p.units0 : 0);
         const int segs = g ? p.segs[1] : p.segs[0], seg_rows = g ? p.seg_rows[1] : p.seg_rows[0];
         const long long n_pad = g ? p.n_pad[1] : p.n_pad[0];
-        const long long tile = ug / segs;
-        const int seg = (int)(ug - tile * segs);
+        const long long sweep = ug / p.ntiles;
+        const int nt = (int)(ug - sweep * p.ntiles);
+        const int panel = (int)(sweep / segs), seg = (int)(sweep - (long long)panel * segs);
         const long long row0 = (long long)seg * seg_rows;
         const long long row1 = min(row0 + seg_rows, n_pad);
         const int nstages = (int)((row1 - row0) / KT);
-        const int panel = (int)(tile / p.ntiles), nt = (int)(tile - (long long)panel * p.ntiles);
 
-        const double* Xg = (g ? p.X[1] : p.X[0]) + row0 * ldx;
+        const double* Xg = (g ? p.X[1] : p.X[0]) + row0 * c.ldx;
         const CountT* Cg = reinterpret_cast<const CountT*>(g ? p.C[1] : p.C[0]) + ((long long)panel * n_pad + row0) * BM;
-
-        auto issue = [&](int s) {  // thread 0 only
-            const uint32_t it = it_base + (uint32_t)s;
-            const int slot = (int)(it % (uint32_t)NST);
-            fence_proxy_async();
-            mbar_expect_tx(&full[slot], stage_bytes);
-            tma_load_1d(Xs + (size_t)slot * KT * ldx, Xg + (long long)s * KT * ldx, KT * ldx * sizeof(double), &full[slot]);
-            tma_load_1d(Cr + (size_t)slot * KT * BM, Cg + (long long)s * KT * BM, KT * BM * sizeof(CountT), &full[slot]);
-        };
-        auto widen_setup = [&](int s, const CountT*& src, double*& dst) {
-            const int slot = (int)((it_base + (uint32_t)s) % (uint32_t)NST);
-            src = Cr + (size_t)slot * KT * BM + cr * BM + (FM ? cq : cq * 2);
-            dst = As + (s & 1) * A_TILE + (FM ? cr * LDA2 + cq * LGS : cr * LDA + cq * 2);
-        };
-        auto wait_stage = [&](int s) {
-            const uint32_t it = it_base + (uint32_t)s;
-            mbar_wait(&full[it % (uint32_t)NST], (it / (uint32_t)NST) & 1u);
-        };
-
-        // column pair (j,l) offsets of this thread's B sub-tiles
-        int oj[NI], ol[NI];
-#pragma unroll
-        for (int s = 0; s < NI; ++s) {
-            const int col = nt * BN + wn * (NI * 8) + s * 8 + lg;
-            const uint32_t pr = *reinterpret_cast<const uint32_t*>(p.pairs + 2 * col);
-            oj[s] = pr & 0xFFFFu; ol[s] = pr >> 16;
-        }
-
-        double acc[MI][NI][2];
-#pragma unroll
-        for (int i = 0; i < MI; ++i)
-#pragma unroll
-            for (int s = 0; s < NI; ++s) { acc[i][s][0] = 0.0; acc[i][s][1] = 0.0; }
-
-        // prologue: fill the pipeline, widen stage 0 (the only exposed widening of the unit)
-        if (tid == 0)
-            for (int s = 0; s < NST && s < nstages; ++s) issue(s);
-        {
-            wait_stage(0);
-            const CountT* src; double* dst;
-            widen_setup(0, src, dst);
-#pragma unroll
-            for (int e = 0; e < KSTEPS; ++e) {
-                if (FM) widen_step_fm<CountT>(src, dst, e, Tab); else widen_step<CountT>(src, dst, e, Tab);
-            }
-        }
-        __syncthreads();
-
-        for (int s = 0; s < nstages; ++s) {
-            const int slot = (int)((it_base + (uint32_t)s) % (uint32_t)NST);
-            const bool has_next = s + 1 < nstages;
-            const CountT* nsrc = nullptr; double* ndst = nullptr;
-            if (has_next) { wait_stage(s + 1); widen_setup(s + 1, nsrc, ndst); }
-
-            const double* abase = As + (s & 1) * A_TILE + (FM ? lk * LDA2 + lg * LGS : lk * LDA + wm * (MI * 8) + lg);
-            const double* xbase = Xs + (size_t)slot * KT * ldx + lk * ldx;
-#pragma unroll
-            for (int kk = 0; kk < KSTEPS; ++kk) {
-                double a[MI], b[NI];
-                const double* arow = abase + kk * 4 * (FM ? LDA2 : LDA);
-                const double* xrow = xbase + kk * 4 * ldx;
-                if (FM) {
-#pragma unroll
-                    for (int i = 0; i < MI; i += 2) {
-                        const double2 v = *reinterpret_cast<const double2*>(arow + i);
-                        a[i] = v.x; a[i + 1] = v.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < MI; ++i) a[i] = arow[i * 8];
-                }
-#pragma unroll
-                for (int t = 0; t < NI; ++t) b[t] = xrow[oj[t]] * xrow[ol[t]];
-                if (has_next) {   // next stage's A tile, in the DMMA shadow
-                    if (FM) widen_step_fm<CountT>(nsrc, ndst, kk, Tab); else widen_step<CountT>(nsrc, ndst, kk, Tab);
-                }
-#pragma unroll
-                for (int i = 0; i < MI; ++i)
-#pragma unroll
-                    for (int t = 0; t < NI; ++t) dmma884(acc[i][t][0], acc[i][t][1], a[i], b[t]);
-            }
-            __syncthreads();  // stage s fully consumed (X rows, its A tile) and stage s+1's A tile complete
-            if (tid == 0 && s + NST < nstages) issue(s + NST);   // refill the slot stage s just released
-        }
-        it_base += (uint32_t)nstages;
-
-        // flush the partial tile [BM][BN] row-major
         double* out = p.partials + (size_t)u * (BM * BN);
-#pragma unroll
-        for (int i = 0; i < MI; ++i)
-#pragma unroll
-            for (int t = 0; t < NI; ++t) {
-                const int m = wm * (MI * 8) + i * 8 + lg, n = wn * (NI * 8) + t * 8 + 2 * lk;
-                *reinterpret_cast<double2*>(out + m * BN + n) = make_double2(acc[i][t][0], acc[i][t][1]);
-            }
+        if (p.has_half && nt == p.ntiles - 1) gram_unit<CountT, LDXC, 16, 1>(c, p, Xg, Cg, nstages, nt * BN, out);
+        else gram_unit<CountT, LDXC, 16, 2>(c, p, Xg, Cg, nstages, nt * BN, out);
     }
 }
 
@@ -268,19 +281,22 @@ __device__ __forceinline__ double2 tree_sum_span(const double2* __restrict__ bas
 
 // out[g][panel*BM + m][nt*BN + n] = tree sum over the tile's leaf partials held here (span = MAX_SEGS / world)
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ partials, int segs0, int segs1,
-                                                          double* __restrict__ gram, int panels, int ntiles, int span) {
+                                                          double* __restrict__ gram, int panels, int ntiles, int span,
+                                                          int Pld, int has_half) {
     const int tile_id = blockIdx.x;
     const int tiles_g = panels * ntiles;
     const int g = tile_id / tiles_g, t = tile_id - g * tiles_g;
     const int panel = t / ntiles, nt = t - panel * ntiles;
     const int cnt = g ? segs1 : segs0;
-    const size_t first = g ? (size_t)tiles_g * segs0 + (size_t)t * segs1 : (size_t)t * segs0;
-    const size_t slots_pad = (size_t)panels * BM, Pld = (size_t)ntiles * BN;
-    for (int e = threadIdx.x + blockIdx.y * blockDim.x; e < BM * BN / 2; e += blockDim.x * gridDim.y) {
+    // partial of (g, panel, nt, seg) sits at unit base_g + (panel * segs_g + seg) * ntiles + nt
+    const size_t first = (g ? (size_t)tiles_g * segs0 : 0) + (size_t)panel * cnt * ntiles + nt;
+    const size_t slots_pad = (size_t)panels * BM;
+    const int tw = (has_half && nt == ntiles - 1) ? BNH : BN;     // this tile's width
+    for (int e = threadIdx.x + blockIdx.y * blockDim.x; e < BM * tw / 2; e += blockDim.x * gridDim.y) {
         double2 s = make_double2(0.0, 0.0);
-        if (cnt > 0) s = tree_sum_span(reinterpret_cast<const double2*>(partials + first * (BM * BN)) + e, BM * BN / 2, cnt, span);
-        const int m = (2 * e) / BN, n = (2 * e) % BN;
-        double* dst = gram + ((size_t)g * slots_pad + (size_t)panel * BM + m) * Pld + (size_t)nt * BN + n;
+        if (cnt > 0) s = tree_sum_span(reinterpret_cast<const double2*>(partials + first * (BM * BN)) + e, (size_t)ntiles * (BM * BN / 2), cnt, span);
+        const int m = (2 * e) / tw, n = (2 * e) % tw;
+        double* dst = gram + ((size_t)g * slots_pad + (size_t)panel * BM + m) * (size_t)Pld + (size_t)nt * BN + n;
         *reinterpret_cast<double2*>(dst) = s;
     }
 }
@@ -316,7 +332,9 @@ static size_t gram_smem(int ldx, int stages, int count_bytes) {
 GramPlan gram_make_plan(int V, int panels, const GroupData gd[2], int count_bytes, int num_sms) {
     GramPlan pl;
     pl.V = V; pl.ldx = design_ldx(V); pl.panels = panels;
-    pl.ntiles = (int)((num_pairs(V) + BN - 1) / BN);
+    gram_col_tiling(V, pl.nfull, pl.has_half);
+    pl.ntiles = pl.nfull + pl.has_half;
+    pl.Pld = pl.nfull * BN + pl.has_half * BNH;
     int64_t total = 0;
     pl.leaf_span = gd[0].shard.leaf_span;
     for (int g = 0; g < 2; ++g) {
@@ -331,8 +349,6 @@ GramPlan gram_make_plan(int V, int panels, const GroupData gd[2], int count_byte
     while (pl.stages > 2 && gram_smem(pl.ldx, pl.stages, count_bytes) > 220 * 1024) --pl.stages;
     pl.smem_bytes = gram_smem(pl.ldx, pl.stages, count_bytes);
     pl.num_partials = (int64_t)total;
-    const char* v = getenv("OBBOOT_GRAM_TILE");   // tuning knob: 1 = 64x32 warp tiles; default 128x16 (measured best)
-    pl.tile_variant = v ? atoi(v) : 0;   // 0: 128x16 + compile-time stride, 1: 64x32, 2: 128x16 runtime stride
     return pl;
 }
 
@@ -345,6 +361,7 @@ void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEve
     p.units0 = pl.units[0];
     p.units_total = pl.units[0] + pl.units[1];
     p.ldx = pl.ldx; p.panels = pl.panels; p.ntiles = pl.ntiles; p.stages = pl.stages;
+    p.nfull = pl.nfull; p.has_half = pl.has_half;
     p.partials = a.partials; p.pairs = a.d_pairs;
     if (ev_main_begin) OB_CUDA(cudaEventRecord(ev_main_begin, st));
     auto launch = [&](auto kernel) {
@@ -352,23 +369,18 @@ void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEve
         kernel<<<pl.grid, GRAM_THREADS, pl.smem_bytes, st>>>(p);
     };
     // row stride specialisations (ldx = 4 mod 8): the common design widths get immediate shared-memory offsets
-#define OB_GRAM_CASE(L) case L: if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 16, 2, L>); else launch(gram_kernel<uint16_t, 16, 2, L>); break;
-    if (pl.tile_variant == 1) {
-        if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 8, 4, 0>); else launch(gram_kernel<uint16_t, 8, 4, 0>);
-    } else if (pl.tile_variant == 2) {
-        if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 16, 2, 0>); else launch(gram_kernel<uint16_t, 16, 2, 0>);
-    } else {
-        switch (pl.ldx) {
-            OB_GRAM_CASE(12) OB_GRAM_CASE(20) OB_GRAM_CASE(28) OB_GRAM_CASE(36) OB_GRAM_CASE(44) OB_GRAM_CASE(52)
-            OB_GRAM_CASE(60) OB_GRAM_CASE(68) OB_GRAM_CASE(76) OB_GRAM_CASE(84) OB_GRAM_CASE(92)
-            default: if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 16, 2, 0>); else launch(gram_kernel<uint16_t, 16, 2, 0>);
-        }
+#define OB_GRAM_CASE(L) case L: if (a.count_bytes == 1) launch(gram_kernel<uint8_t, L>); else launch(gram_kernel<uint16_t, L>); break;
+    switch (pl.ldx) {
+        OB_GRAM_CASE(12) OB_GRAM_CASE(20) OB_GRAM_CASE(28) OB_GRAM_CASE(36) OB_GRAM_CASE(44) OB_GRAM_CASE(52)
+        OB_GRAM_CASE(60) OB_GRAM_CASE(68) OB_GRAM_CASE(76) OB_GRAM_CASE(84) OB_GRAM_CASE(92)
+        default: if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 0>); else launch(gram_kernel<uint16_t, 0>);
     }
 #undef OB_GRAM_CASE
     OB_CUDA(cudaGetLastError());
     if (ev_main_end) OB_CUDA(cudaEventRecord(ev_main_end, st));
     dim3 rg(2 * pl.panels * pl.ntiles, 4);
-    gram_reduce_kernel<<<rg, 256, 0, st>>>(a.partials, pl.segs[0], pl.segs[1], a.gram, pl.panels, pl.ntiles, pl.leaf_span);
+    gram_reduce_kernel<<<rg, 256, 0, st>>>(a.partials, pl.segs[0], pl.segs[1], a.gram, pl.panels, pl.ntiles, pl.leaf_span,
+                                           pl.Pld, pl.has_half);
     OB_CUDA(cudaGetLastError());
 }
 

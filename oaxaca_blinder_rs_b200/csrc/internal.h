@@ -109,6 +109,7 @@ void counts_philox_fixup_launch(const CountsArgs& a, const long long* d_colsum, 
 // ---- gram.cu ----
 struct GramPlan {
     int V, ldx, panels, ntiles;
+    int nfull, has_half, Pld;     // column tiling (gram_col_tiling) and the row stride of the reduced Gram
     int64_t n_pad[2];             // local padded rows
     int segs[2], seg_rows[2];     // leaves held here and rows per leaf (RowShard: function of the global row count only)
     int leaf_span;                // MAX_SEGS / world: size of the aligned subtree this GPU reduces
@@ -116,8 +117,18 @@ struct GramPlan {
     int grid;
     int64_t num_partials;         // = units[0] + units[1]
     size_t smem_bytes; int stages;
-    int tile_variant;             // 0: 1x8 warps, 128x16 warp tiles (default); 1: 2x4 warps, 64x32 warp tiles
 };
+// Column tiling of the P' = V(V+1)/2 sufficient-statistic columns: nfull tiles of BN columns and, when the remainder
+// fits, one half-width tail tile (P' = 171 at K = 17 costs 1.5 tiles instead of 2).
+inline void gram_col_tiling(int V, int& nfull, int& has_half) {
+    const int64_t P = num_pairs(V);
+    nfull = (int)(P / BN);
+    const int rem = (int)(P - (int64_t)nfull * BN);
+    has_half = 0;
+    if (rem > BN / 2) ++nfull; else if (rem > 0) has_half = 1;
+}
+inline int gram_ntiles(int V) { int f, h; gram_col_tiling(V, f, h); return f + h; }
+inline int gram_pld(int V) { int f, h; gram_col_tiling(V, f, h); return f * BN + h * (BN / 2); }
 GramPlan gram_make_plan(int V, int panels, const GroupData g[2], int count_bytes, int num_sms);
 struct GramArgs {
     const double* X[2]; const void* C[2];     // X: the (sqrt(w)-scaled when weighted) design
