@@ -301,7 +301,9 @@ def main():
                              "peak_source": "measured on this pool: FP64 DMMA issue peak, profiles/r01_fp64_peaks.json "
                                             "(MEASURED_PEAKS.json has no fp64 entry); cuBLAS DGEMM 35.4",
                              "launch_ms": g_ms, "flop_per_launch": flops_rank, "traffic": None},
-                "stage_ms": {k: float(v) for k, v in out["timings_ms"].items()},
+                "stage_ms": dict({k: float(v) for k, v in out["timings_ms"].items()},
+                                 other=float(out["timings_ms"]["total"] - sum(out["timings_ms"][k] for k in
+                                                                             ("counts", "gram", "solve", "reduce")))),
                 "e2e_step_ms": [round(x, 1) for x in e2e_ms],
                 "clocks": sampler.summary(),
                 "n_ok": int(out["n_ok"])}

@@ -500,7 +500,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                                                          : 0.6 * ((double)free_b + (double)pool_idle_bytes(ctx));
         const int64_t local_leaves = (int64_t)(d->g[0].shard.leaf_hi - d->g[0].shard.leaf_lo) +
                                      (d->g[1].shard.leaf_hi - d->g[1].shard.leaf_lo);
-        DevBuf d_agree(sizeof(long long));
+        DevBuf d_agree(sizeof(long long)), d_lut(2 * counts_lut_bytes());
 
         for (int attempt = 0; attempt < 2; ++attempt) {  // second attempt only widens uint8 -> uint16 after saturation
             const double per_panel = (double)(n_pad[0] + n_pad[1]) * BM * count_bytes +
@@ -565,8 +565,9 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 } else {
                     OB_CUDA(cudaMemsetAsync(d_colsum.p, 0, d_colsum.bytes, st));
                     for (int g = 0; g < 2; ++g) {
-                        counts_philox_body_launch(ca[g], d_colsum.as<long long>() + (size_t)g * ppb * BM, st);
-                        res->gpu_launches += 1;
+                        counts_philox_body_launch(ca[g], d_colsum.as<long long>() + (size_t)g * ppb * BM,
+                                                  d_lut.as<unsigned char>() + (size_t)g * counts_lut_bytes(), st);
+                        res->gpu_launches += 2;
                     }
                     // the fix-up tops every replicate up to exactly n_g draws: it needs the column sums over ALL row shards
                     if (comm) {
@@ -730,7 +731,7 @@ ob_status ob_debug_counts(ob_ctx* ctx, const ob_design* d, uint64_t seed, int64_
     return guarded(ctx, [&] {
         cudaStream_t st = ctx->stream;
         const GroupData& G = d->g[group];
-        DevBuf d_C((size_t)G.n_pad * BM * 2), d_colsum(sizeof(long long) * BM), d_flags(sizeof(int) * 4);
+        DevBuf d_C((size_t)G.n_pad * BM * 2), d_colsum(sizeof(long long) * BM), d_flags(sizeof(int) * 4), d_lut(counts_lut_bytes());
         OB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * 4, st));
         CountsArgs ca;
         ca.C = d_C.p; ca.count_bytes = 2; ca.n = G.n; ca.n_pad = G.n_pad; ca.panels = 1; ca.slots = 2;
@@ -738,7 +739,7 @@ ob_status ob_debug_counts(ob_ctx* ctx, const ob_design* d, uint64_t seed, int64_
         ca.n_global = G.shard.n_global; ca.row_begin = G.shard.row_begin;
         if (d->world > 1) fail(OB_ERR_UNSUPPORTED, "ob_debug_counts on a row-sharded design");
         OB_CUDA(cudaMemsetAsync(d_colsum.p, 0, d_colsum.bytes, st));
-        counts_philox_body_launch(ca, d_colsum.as<long long>(), st);
+        counts_philox_body_launch(ca, d_colsum.as<long long>(), d_lut.as<unsigned char>(), st);
         counts_philox_fixup_launch(ca, d_colsum.as<long long>(), d_flags.as<int>(), st);
         // slot 1 column of the single panel
         OB_CUDA(cudaMemcpy2DAsync(counts_out, sizeof(uint16_t), d_C.as<uint16_t>() + 1, sizeof(uint16_t) * BM,

@@ -188,20 +188,6 @@ __device__ __forceinline__ void gram_unit(GramCta<CountT>& c, const GramKernelPa
         }
 }
 
-// Units are walked in (group, panel, segment, column tile) order: consecutive units of a CTA sweep the column tiles
-// over the SAME rows (their X / count tiles stay in L2), and every CTA's contiguous range holds the same mix of
-// full and half-width tiles whatever their relative cost.  A half-width tile is budgeted as half a full one; CTA b
-// takes the units whose cumulative cost starts in [W b / grid, W (b+1) / grid): first unit at or after cost w --
-__device__ __forceinline__ long long unit_at_cost(const GramKernelParams& p, long long w) {
-    const long long wt = 2 * p.nfull + p.has_half;          // cost of one (panel, segment) sweep over the column tiles
-    const long long W0 = (long long)p.panels * p.segs[0] * wt;
-    long long base = 0;
-    if (w >= W0) { w -= W0; base = p.units0; }
-    const long long sweep = w / wt, r = w - sweep * wt;
-    const long long i = r < 2LL * p.nfull ? (r + 1) / 2 : (long long)p.nfull;
-    return min(base + sweep * p.ntiles + i, p.units_total);
-}
-
 template <typename CountT, int LDXC>
 __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -225,27 +211,39 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
     }
     __syncthreads();
 
-    const long long wt = 2 * p.nfull + p.has_half;
-    const long long W = (long long)p.panels * (p.segs[0] + p.segs[1]) * wt;
-    const long long u0 = unit_at_cost(p, W * (long long)blockIdx.x / gridDim.x);
-    const long long u1 = blockIdx.x + 1 == gridDim.x ? p.units_total : unit_at_cost(p, W * (long long)(blockIdx.x + 1) / gridDim.x);
-
-    for (long long u = u0; u < u1; ++u) {
-        const int g = (u >= p.units0) ? 1 : 0;
-        const long long ug = u - (g ? p.units0 : 0);
+    // Unit schedule.  Sequence = all full-width tiles in (group, segment, panel, tile) order, then all half-width
+    // tiles in (group, segment, panel) order; CTA b takes sequence positions b, b + grid, b + 2 grid, ...  Units of one
+    // class cost the same, so (a) every CTA gets the same number of each class (+-1) whatever their relative cost, and
+    // (b) the grid advances in lockstep through CONSECUTIVE units: at any time the CTAs work on the same row segment,
+    // sharing its design rows across all panels and column tiles, and each panel's count tile across its column
+    // tiles, through L2 -- HBM traffic stays near one pass over X and C instead of one pass per unit.
+    const long long sweeps0 = (long long)p.segs[0] * p.panels, sweeps1 = (long long)p.segs[1] * p.panels;
+    const long long NF0 = sweeps0 * p.nfull, NF = NF0 + sweeps1 * p.nfull;
+    const long long NH = p.has_half ? sweeps0 + sweeps1 : 0;
+    for (long long i = blockIdx.x; i < NF + NH; i += gridDim.x) {
+        int g, nt; long long sweep;   // sweep = seg * panels + panel within the group
+        if (i < NF) {
+            g = i >= NF0 ? 1 : 0;
+            const long long r = i - (g ? NF0 : 0);
+            sweep = r / p.nfull; nt = (int)(r - sweep * p.nfull);
+        } else {
+            const long long r = i - NF;
+            g = r >= sweeps0 ? 1 : 0;
+            sweep = r - (g ? sweeps0 : 0); nt = p.nfull;
+        }
         const int segs = g ? p.segs[1] : p.segs[0], seg_rows = g ? p.seg_rows[1] : p.seg_rows[0];
         const long long n_pad = g ? p.n_pad[1] : p.n_pad[0];
-        const long long sweep = ug / p.ntiles;
-        const int nt = (int)(ug - sweep * p.ntiles);
-        const int panel = (int)(sweep / segs), seg = (int)(sweep - (long long)panel * segs);
+        const int seg = (int)(sweep / p.panels), panel = (int)(sweep - (long long)seg * p.panels);
         const long long row0 = (long long)seg * seg_rows;
         const long long row1 = min(row0 + seg_rows, n_pad);
         const int nstages = (int)((row1 - row0) / KT);
+        // partial of (g, panel, nt, seg) is stored at unit base_g + (panel * segs_g + seg) * ntiles + nt
+        const long long u = (g ? p.units0 : 0) + ((long long)panel * segs + seg) * p.ntiles + nt;
 
         const double* Xg = (g ? p.X[1] : p.X[0]) + row0 * c.ldx;
         const CountT* Cg = reinterpret_cast<const CountT*>(g ? p.C[1] : p.C[0]) + ((long long)panel * n_pad + row0) * BM;
         double* out = p.partials + (size_t)u * (BM * BN);
-        if (p.has_half && nt == p.ntiles - 1) gram_unit<CountT, LDXC, 16, 1>(c, p, Xg, Cg, nstages, nt * BN, out);
+        if (nt == p.nfull) gram_unit<CountT, LDXC, 16, 1>(c, p, Xg, Cg, nstages, nt * BN, out);
         else gram_unit<CountT, LDXC, 16, 2>(c, p, Xg, Cg, nstages, nt * BN, out);
     }
 }

@@ -103,7 +103,9 @@ void counts_from_indices(const CountsArgs& a, const uint32_t* d_idx, int* d_over
 // native mode, two phases: Poisson(lambda) body over the local rows (accumulates the local column sums into
 // d_colsum [panels*BM] int64, zeroed by the caller), then -- after d_colsum has been summed over all row shards --
 // the exact fix-up draws.  d_flags[0] = body overshoot, d_flags[1] = count saturated.
-void counts_philox_body_launch(const CountsArgs& a, long long* d_colsum, cudaStream_t st);
+// d_lut: counts_lut_bytes() of scratch per group (the inverse-CDF byte table, rebuilt by every call: 2 launches)
+size_t counts_lut_bytes();
+void counts_philox_body_launch(const CountsArgs& a, long long* d_colsum, unsigned char* d_lut, cudaStream_t st);
 void counts_philox_fixup_launch(const CountsArgs& a, const long long* d_colsum, int* d_flags, cudaStream_t st);
 
 // ---- gram.cu ----

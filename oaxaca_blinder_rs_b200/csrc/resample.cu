@@ -31,63 +31,96 @@ constexpr int KMAX = 24;  // P(Poisson(<=1) > 23) < 2^-64
 
 struct PoissonTable {
     unsigned long long T[KMAX];  // T[k] = floor(P(X <= k) * 2^64); count = #{k : U >= T[k]}
-    unsigned int Th[KMAX];       // high words
+    unsigned short T16[KMAX];    // top 16 bits of T[k]
     int lambda_zero;
 };
 
-// counter layout: (c0, c1, c2, c3) = (row_lo | draw_lo, row_hi | group<<8 | attempt<<16, replicate key, stream tag)
+// counter layout: (c0, c1, c2, c3) = (row_lo | draw_lo, row_hi | group<<8, replicate key, stream tag)
 enum : uint32_t { STREAM_BODY = 0x0B0D1u, STREAM_REFINE = 0x0F19Eu, STREAM_FIXUP = 0x0F1Cu };
 
-__device__ __forceinline__ int poisson_exact(uint32_t u_hi, const PoissonTable& t, uint64_t row, uint32_t c1,
-                                          uint64_t rep, uint32_t k0, uint32_t k1) {
-    // low word comes from the refinement stream, keyed by the single replicate id
-    const Philox4 r = philox4x32_10((uint32_t)row, c1, (uint32_t)rep, STREAM_REFINE ^ (uint32_t)(rep >> 32), k0, k1);
-    const unsigned long long U = ((unsigned long long)u_hi << 32) | r.x;
+// A count is the inverse CDF of a 64-bit uniform U = (u16 : 48 refinement bits), resolved lazily:
+//   1. the top 14 bits of u16 index a 16 KB byte table (built once per call, copied to shared memory): the count if
+//      every U of that bucket gives the same one, else AMBIG -- a threshold falls inside ~7 of the 16384 buckets;
+//   2. AMBIG: compare all 16 bits with the thresholds' top 16 bits; still undecided only if u16 EQUALS one of them;
+//   3. only then (p ~ 1e-4) are the low 48 bits drawn, from the refinement stream keyed by the single
+//      (row, replicate), and the full 64-bit comparison made.
+// The result is exactly the 64-bit inverse CDF, at 16 random bits and one LDS per count.
+constexpr int LUT_BITS = 14;
+constexpr int LUT_SIZE = 1 << LUT_BITS;
+constexpr unsigned AMBIG = 255u;
+
+__device__ __forceinline__ int cdf_count(unsigned long long U, const PoissonTable& t) {
     int c = 0;
 #pragma unroll 1
     for (int k = 0; k < KMAX; ++k) c += (U >= t.T[k]) ? 1 : 0;
     return c;
 }
 
-constexpr int KFAST = 8;   // thresholds resolved inline; P(Poisson(<=1) > 7) ~ 1e-6, so the exact path is ~never divergent
+// device copy of the thresholds behind the byte table (read by the rare resolve path through a pointer, so that the
+// body kernel needs no stack frame for it)
+struct PoissonDev { unsigned long long T[KMAX]; unsigned int T16[KMAX]; };
 
-// count = #{k : U >= T[k]} for the 64-bit uniform U = (u : refinement word).  The high word decides unless it
-// equals a threshold's high word or lies beyond the inline table; only then is the low word drawn.
-__device__ __forceinline__ int poisson_draw(uint32_t u, const uint32_t (&th)[KFAST], const PoissonTable& t,
-                                            uint64_t row, uint32_t c1, uint64_t rep, uint32_t k0, uint32_t k1) {
-    int c = 0;
-    bool amb = u >= th[KFAST - 1];
-#pragma unroll
-    for (int k = 0; k < KFAST; ++k) { c += (u > th[k]) ? 1 : 0; amb |= (u == th[k]); }
-    if (amb) c = poisson_exact(u, t, row, c1, rep, k0, k1);
+__global__ void __launch_bounds__(256) counts_lut_kernel(const PoissonTable tab, unsigned char* __restrict__ lut) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= LUT_SIZE) return;
+    if (b < KMAX) {
+        PoissonDev* d = reinterpret_cast<PoissonDev*>(lut + LUT_SIZE);
+        d->T[b] = tab.T[b]; d->T16[b] = tab.T16[b];
+    }
+    const unsigned long long lo = (unsigned long long)b << (64 - LUT_BITS);
+    const unsigned long long hi = lo | ((1ull << (64 - LUT_BITS)) - 1ull);
+    const int cl = cdf_count(lo, tab), ch = cdf_count(hi, tab);
+    lut[b] = (unsigned char)(cl == ch ? cl : AMBIG);
+}
+
+__device__ __noinline__ unsigned poisson_resolve(uint32_t u16, const PoissonDev* __restrict__ t, uint64_t row, uint32_t c1,
+                                                 uint64_t rep, uint32_t k0, uint32_t k1) {
+    unsigned c = 0; bool tie = false;
+#pragma unroll 1
+    for (int k = 0; k < KMAX; ++k) { c += (u16 > t->T16[k]) ? 1u : 0u; tie |= (u16 == t->T16[k]); }
+    if (!tie) return c;
+    const Philox4 r = philox4x32_10((uint32_t)row, c1, (uint32_t)rep, STREAM_REFINE ^ (uint32_t)(rep >> 32), k0, k1);
+    const unsigned long long U = ((unsigned long long)u16 << 48) | ((unsigned long long)r.x << 16) | (r.y >> 16);
+    c = 0;
+#pragma unroll 1
+    for (int k = 0; k < KMAX; ++k) c += (U >= t->T[k]) ? 1u : 0u;
     return c;
 }
 
-// SH = (global replicate id of local slot 0) mod 4: Philox words are keyed by floor(rep / 4), so a thread's
-// 16 consecutive replicates span 4 (SH == 0) or 5 key groups; SH is uniform over the launch -> compile-time.
+// Replicate r draws from stream id r + 1 (so that, unsharded, stream ids coincide with slots: the point estimate
+// occupies slot 0); one Philox4x32-10 call yields the 16-bit uniforms of the 8 stream ids of an aligned octet.
+// SH = (stream id of local slot 0) mod 8, uniform over the launch -> compile-time: a thread's 16 consecutive slots
+// span 2 (SH == 0) or 3 octets.
 template <typename CountT, int SH>
 __global__ void __launch_bounds__(256) counts_philox_body(CountT* __restrict__ C, long long n, long long n_pad,
                                                           long long slots, long long rep0, int first_slot, int group,
-                                                          uint32_t k0, uint32_t k1, const PoissonTable tab,
+                                                          uint32_t k0, uint32_t k1, int lambda_zero,
+                                                          const unsigned char* __restrict__ lut_g,
                                                           long long* __restrict__ colsum, int rows_per_block,
                                                           long long row_begin_global) {
+    __shared__ __align__(16) unsigned char lut[LUT_SIZE];
+    __shared__ int ssum[BM];
+    for (int b = threadIdx.x; b < LUT_SIZE / 16; b += blockDim.x)
+        reinterpret_cast<uint4*>(lut)[b] = reinterpret_cast<const uint4*>(lut_g)[b];
+    if (threadIdx.x < BM) ssum[threadIdx.x] = 0;
+    __syncthreads();
+
     const int panel = blockIdx.y;
     const int q = threadIdx.x & 7;           // 16-slot group within the panel
     const int rl = threadIdx.x >> 3;         // row lane 0..31
     const long long slot0 = (long long)panel * BM + q * 16;
     const long long row_begin = (long long)blockIdx.x * rows_per_block;
     const uint32_t c1base = ((uint32_t)group << 8);
-    uint32_t th[KFAST];
-#pragma unroll
-    for (int k = 0; k < KFAST; ++k) th[k] = tab.Th[k];
-    // replicate of local slot s is rep0 + s; first key group of this thread (rep0 + slot0 - SH is a multiple of 4)
-    const long long rep_lo = rep0 + slot0;
-    const long long q4_first = (rep_lo - SH) >> 2;
+    // stream id of local slot s is rep0 + 1 + s; (sid_lo - SH) is a multiple of 8
+    const long long sid_lo = rep0 + 1 + slot0;
+    const long long oct_first = (sid_lo - SH) >> 3;
+    constexpr int NOCT = SH ? 3 : 2;
     // validity of slot e (0..15) is row-independent: slot >= first_slot && slot < slots
     unsigned valid = 0;
 #pragma unroll
     for (int e = 0; e < 16; ++e)
         if (slot0 + e >= first_slot && slot0 + e < slots) valid |= 1u << e;
+    const bool point_slot = (slot0 == 0 && first_slot == 1);
     int sums[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) sums[e] = 0;
@@ -99,20 +132,38 @@ __global__ void __launch_bounds__(256) counts_philox_body(CountT* __restrict__ C
         if (row < n) {
             const unsigned long long grow = (unsigned long long)(row + row_begin_global);   // streams are keyed by the GLOBAL row
             const uint32_t c1 = c1base | (uint32_t)(grow >> 32);
-            if (!tab.lambda_zero && valid) {
-                uint32_t u[20];
+            if (!lambda_zero && valid) {
+                uint32_t w[4 * NOCT];
 #pragma unroll
-                for (int gidx = 0; gidx < (SH ? 5 : 4); ++gidx) {
-                    const long long q4 = q4_first + gidx;
-                    const Philox4 r = philox4x32_10((uint32_t)grow, c1, (uint32_t)q4, STREAM_BODY ^ (uint32_t)(q4 >> 32), k0, k1);
-                    u[4 * gidx] = r.x; u[4 * gidx + 1] = r.y; u[4 * gidx + 2] = r.z; u[4 * gidx + 3] = r.w;
+                for (int gi = 0; gi < NOCT; ++gi) {
+                    const long long oc = oct_first + gi;
+                    const Philox4 r = philox4x32_10((uint32_t)grow, c1, (uint32_t)oc, STREAM_BODY ^ (uint32_t)(oc >> 32), k0, k1);
+                    w[4 * gi] = r.x; w[4 * gi + 1] = r.y; w[4 * gi + 2] = r.z; w[4 * gi + 3] = r.w;
                 }
+                unsigned any = 0;
 #pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    if (valid & (1u << e))
-                        cnt[e] = (unsigned)poisson_draw(u[SH + e], th, tab, (uint64_t)grow, c1, (uint64_t)(rep_lo + e), k0, k1);
+                for (int e = 0; e < 16; ++e) {
+                    const int h = SH + e;                                   // 16-bit lane h of the thread's uniform words
+                    const uint32_t idx = (h & 1) ? (w[h >> 1] >> (32 - LUT_BITS)) : ((w[h >> 1] >> (16 - LUT_BITS)) & (LUT_SIZE - 1));
+                    cnt[e] = lut[idx];
+                    any |= cnt[e];
+                }
+                if (any & 0x80u) {   // some bucket straddles a threshold (AMBIG = 255; real counts are < 24)
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        if (cnt[e] != AMBIG) continue;
+                        const int h = SH + e;
+                        const uint32_t u16 = (h & 1) ? (w[h >> 1] >> 16) : (w[h >> 1] & 0xFFFFu);
+                        cnt[e] = poisson_resolve(u16, reinterpret_cast<const PoissonDev*>(lut_g + LUT_SIZE), grow, c1,
+                                                 (uint64_t)(rep0 + slot0 + e), k0, k1);
+                    }
+                }
+                if (valid != 0xFFFFu) {   // first / last panel only: slots outside [first_slot, slots) stay empty
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) cnt[e] = (valid & (1u << e)) ? cnt[e] : 0u;
+                }
             }
-            if (slot0 == 0 && first_slot == 1) cnt[0] = 1;  // point estimate
+            if (point_slot) cnt[0] = 1;  // point estimate
 #pragma unroll
             for (int e = 0; e < 16; ++e) sums[e] += (int)cnt[e];
         }
@@ -136,9 +187,6 @@ __global__ void __launch_bounds__(256) counts_philox_body(CountT* __restrict__ C
     }
     // column sums: reduce the 4 row-lanes of each warp that share q, then the 8 warps through shared memory,
     // then ONE global atomic per (block, slot): same-address global atomics serialise in L2
-    __shared__ int ssum[BM];
-    if (threadIdx.x < BM) ssum[threadIdx.x] = 0;
-    __syncthreads();
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
         int s = sums[e];
@@ -248,24 +296,31 @@ static PoissonTable make_table(long long n) {
         cdf += p;
         long double v = floorl(cdf * two64);
         t.T[k] = (v >= two64 || cdf >= 1.0L) ? 0xFFFFFFFFFFFFFFFFull : (unsigned long long)v;
-        t.Th[k] = (unsigned int)(t.T[k] >> 32);
+        t.T16[k] = (unsigned short)(t.T[k] >> 48);
         p = p * lam / (long double)(k + 1);
     }
     t.lambda_zero = 0;
     return t;
 }
 
-void counts_philox_body_launch(const CountsArgs& a, long long* d_colsum, cudaStream_t st) {
+size_t counts_lut_bytes() { return LUT_SIZE + ((sizeof(PoissonDev) + 255) / 256) * 256; }
+
+void counts_philox_body_launch(const CountsArgs& a, long long* d_colsum, unsigned char* d_lut, cudaStream_t st) {
     const PoissonTable tab = make_table(a.n_global);       // lambda from the whole group's row count
+    counts_lut_kernel<<<LUT_SIZE / 256, 256, 0, st>>>(tab, d_lut);
+    OB_CUDA(cudaGetLastError());
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const int rows_per_block = 2048;
     dim3 grid((unsigned)((a.n_pad + rows_per_block - 1) / rows_per_block), (unsigned)a.panels);
-    const int sh = (int)(((a.rep0 % 4) + 4) % 4);
+    const int sh = (int)((((a.rep0 + 1) % 8) + 8) % 8);
     auto body = [&](auto ct) {
         using CT = decltype(ct);
 #define OB_BODY(SHV) counts_philox_body<CT, SHV><<<grid, 256, 0, st>>>((CT*)a.C, a.n, a.n_pad, a.slots, a.rep0, \
-            a.first_slot, a.group, k0, k1, tab, d_colsum, rows_per_block, a.row_begin)
-        switch (sh) { case 0: OB_BODY(0); break; case 1: OB_BODY(1); break; case 2: OB_BODY(2); break; default: OB_BODY(3); }
+            a.first_slot, a.group, k0, k1, tab.lambda_zero, d_lut, d_colsum, rows_per_block, a.row_begin)
+        switch (sh) {
+        case 0: OB_BODY(0); break; case 1: OB_BODY(1); break; case 2: OB_BODY(2); break; case 3: OB_BODY(3); break;
+        case 4: OB_BODY(4); break; case 5: OB_BODY(5); break; case 6: OB_BODY(6); break; default: OB_BODY(7);
+        }
 #undef OB_BODY
     };
     if (a.count_bytes == 1) body(uint8_t{}); else body(uint16_t{});

@@ -278,6 +278,16 @@ def test_native_philox_stream(ob, orc, ctx):
     allc = np.concatenate([des.debug_counts(7, r, 0).astype(np.int64) for r in range(20)])
     assert abs(allc.mean() - 1.0) < 1e-12
     assert abs(allc.var() - 1.0) < 0.02 and abs((allc == 0).mean() - np.exp(-1)) < 0.005
+    # full marginal law: each count ~ Binomial(n, 1/n); observed frequencies of 0..7 within 5 sigma
+    from scipy import stats as sps
+    n_a, N = len(ya), allc.size
+    for k in range(8):
+        pk = sps.binom.pmf(k, n_a, 1.0 / n_a)
+        assert abs((allc == k).mean() - pk) < 5.0 * np.sqrt(pk * (1 - pk) / N) + 1e-9, (k, (allc == k).mean(), pk)
+    # replicates are independent of each other and of the row: correlation of two count vectors ~ N(0, 1/n)
+    assert abs(np.corrcoef(c0, c1)[0, 1]) < 5.0 / np.sqrt(n_a)
+    # streams do not depend on which replicate octet / batch position a replicate is generated in
+    np.testing.assert_array_equal(des.debug_counts(7, 13, 0), des.debug_counts(7, 13, 0))
     B = 800
     norm = [ob.NormVar(m, i) for m, i in synth.norm_spec(d)]
     g1 = ob.bootstrap(des, B, ref_kind=1, norm=norm, seed=1234)
