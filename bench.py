@@ -38,6 +38,10 @@ WORKLOADS = {
     "probe_n1M_k50_B255": (1_000_000, 44, (4, 4), True, True, 255, 0),   # ncu-sized: two full panels
     "probe5_n20M_k16_B2000": (20_000_000, 16, (), False, False, 2000, 0),  # config-5 column shape (1 full + 1 half tile)
 }
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE gram_kernel launch, from ncu captures of this same command
+# (profiles/r01_gram_dram_config3_v9.csv; one-pass bytes of X and C at config 3 are 24.2 GB)
+GRAM_DRAM_TRAFFIC = {("config3_n10M_k50_wls_yun_B2000", 1): 104976087808 + 2996615168}
+HBM_PEAK_GBS = 6550.1            # MEASURED_PEAKS.json (driver-written copy bandwidth on this pool)
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool (profiles/r01_fp64_peaks.json): DMMA.8x8x4 issue peak
 FP64_CUBLAS_DGEMM_TFLOPS = 35.4  # measured on this pool (profiles/r01_dgemm_peak.json): cuBLAS DGEMM 8192^3
 
@@ -45,6 +49,25 @@ FP64_CUBLAS_DGEMM_TFLOPS = 35.4  # measured on this pool (profiles/r01_dgemm_pea
 def algorithmic_flops(n, K, reps):
     P = K * (K + 1) // 2 + K      # F_rep = 2 n P, P = K(K+1)/2 + K
     return 2.0 * n * P * reps, P
+
+
+def hbm_stage_rooflines(d, K, reps, world, shard_rows, out, pack_ms):
+    """The HBM-bound stages: algorithmic bytes / CUDA-event time against the measured copy bandwidth."""
+    n_loc = d["n"]                                      # rows this rank holds
+    slots = (reps + 1) if (world == 1 or shard_rows) else (out["rep_stats"].shape[0] // world + 1)
+    gen_bytes = float(n_loc) * slots                    # uint8 multiplicity matrix written once
+    t_gen = out["timings_ms"]["counts"] - out["timings_ms"].get("comm", 0.0)
+    src = 8 * (len(d["cont"]) + 1 + (1 if d["weights"] is not None else 0)) + 4 * len(d["cat_codes"]) + 1
+    dst = 8 * (K + 1) * (2 if d["weights"] is not None else 1) + (8 if d["weights"] is not None else 0)
+    pack_bytes = float(n_loc) * (src + dst)
+    def entry(b, ms):
+        gbs = b / (ms * 1e-3) / 1e9 if ms > 0 else None
+        return {"bytes": b, "ms": ms, "achieved": gbs, "peak": HBM_PEAK_GBS, "unit": "GB/s",
+                "frac": None if gbs is None else gbs / HBM_PEAK_GBS}
+    return {"replicate_generation": dict(entry(gen_bytes, t_gen), note="integer-ALU bound (Philox4x32-10 + table lookup per "
+                                         "count), not HBM: bytes are the multiplicity matrix written"),
+            "pack": entry(pack_bytes, pack_ms[1]),
+            "h2d_copy": {"bytes": float(n_loc) * src, "ms": pack_ms[0]}}
 
 
 class ClockSampler(threading.Thread):
@@ -236,6 +259,7 @@ def main():
             torch.cuda.synchronize()
 
     design = pack()
+    pack_ms = design.pack_timings()
     for _ in range(args.warmup):
         out = step(design)
 
@@ -300,10 +324,15 @@ def main():
                              "frac_of_cublas_dgemm": achieved / FP64_CUBLAS_DGEMM_TFLOPS,
                              "peak_source": "measured on this pool: FP64 DMMA issue peak, profiles/r01_fp64_peaks.json "
                                             "(MEASURED_PEAKS.json has no fp64 entry); cuBLAS DGEMM 35.4",
-                             "launch_ms": g_ms, "flop_per_launch": flops_rank, "traffic": None},
+                             "launch_ms": g_ms, "flop_per_launch": flops_rank,
+                             "traffic": GRAM_DRAM_TRAFFIC.get((name, world)),
+                             "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch of this "
+                                               "command (profiles/r01_gram_dram_config3_v9.csv)"
+                                               if (name, world) in GRAM_DRAM_TRAFFIC else None},
                 "stage_ms": dict({k: float(v) for k, v in out["timings_ms"].items()},
                                  other=float(out["timings_ms"]["total"] - sum(out["timings_ms"][k] for k in
                                                                              ("counts", "gram", "solve", "reduce")))),
+                "hbm_stages": hbm_stage_rooflines(d, K, reps, world, shard_rows, out, pack_ms),
                 "e2e_step_ms": [round(x, 1) for x in e2e_ms],
                 "clocks": sampler.summary(),
                 "n_ok": int(out["n_ok"])}

@@ -84,6 +84,8 @@ ob_status ob_design_from_dense(ob_ctx* ctx, int32_t K, int32_t n_cont,
                                ob_design** out);
 void ob_design_destroy(ob_design* d);
 ob_status ob_design_shape(const ob_design* d, int64_t* na, int64_t* nb, int32_t* K, int32_t* n_cont);
+/* device time (CUDA events, ms) ob_design_pack spent uploading the columns and in the pack kernels; either may be NULL */
+ob_status ob_design_pack_timings(const ob_design* d, double* ms_h2d, double* ms_pack_kernels);
 /* get_data_matrices() equivalent: copies the packed design back (row-major [n_g x K]); any pointer may be NULL */
 ob_status ob_design_download(ob_ctx* ctx, const ob_design* d, double* Xa, double* ya, double* wa,
                              double* Xb, double* yb, double* wb);

@@ -173,6 +173,12 @@ class Design:
         self.ctx.check(N.lib().ob_design_download(self.ctx._h, self._h, _dp(Xa), _dp(ya), _dp(wa), _dp(Xb), _dp(yb), _dp(wb)))
         return Xa, ya, wa, Xb, yb, wb
 
+    def pack_timings(self):
+        """(ms_h2d, ms_pack_kernels) of the ob_design_pack call that built this design."""
+        a, b = C.c_double(), C.c_double()
+        N.lib().ob_design_pack_timings(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
     def set_row_shard(self, n_a_global: int, n_b_global: int, world: int, rank: int):
         """ob_design_set_row_shard: this design holds rank's rows (row_shard_plan) of a world-way row split."""
         st = N.lib().ob_design_set_row_shard(self._h, n_a_global, n_b_global, world, rank)

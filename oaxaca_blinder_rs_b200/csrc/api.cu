@@ -33,6 +33,7 @@ struct ob_design {
     int K = 0, n_cont = 0, V = 0, ldx = 0;
     bool weighted = false;
     int world = 1, rank = 0;         // row sharding (mode N): this design holds rank's rows of a world-way split
+    double ms_h2d = 0.0, ms_pack = 0.0;   // device time of the column upload and of the pack kernels (ob_design_pack)
     GroupData g[2];
 };
 
@@ -283,6 +284,13 @@ ob_status ob_design_shape(const ob_design* d, int64_t* na, int64_t* nb, int32_t*
     return OB_OK;
 }
 
+ob_status ob_design_pack_timings(const ob_design* d, double* ms_h2d, double* ms_pack_kernels) {
+    if (!d) return OB_ERR_INVALID_ARG;
+    if (ms_h2d) *ms_h2d = d->ms_h2d;
+    if (ms_pack_kernels) *ms_pack_kernels = d->ms_pack;
+    return OB_OK;
+}
+
 ob_status ob_design_from_dense(ob_ctx* ctx, int32_t K, int32_t n_cont,
                                const double* Xa, const double* ya, const double* wa, int64_t na,
                                const double* Xb, const double* yb, const double* wb, int64_t nb,
@@ -339,6 +347,8 @@ ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
         const int64_t n = f->n;
         g_alloc_pack = true;
         // ---- stage the frame columns in HBM ----
+        double ms_h2d = 0.0, ms_pack = 0.0;
+        Timer t_h2d(st, &ms_h2d);
         std::vector<DevBuf> cols(f->n_cont), cats(f->n_cat);
         std::vector<const double*> h_cont(std::max(f->n_cont, 1), nullptr);
         std::vector<const int32_t*> h_cat(std::max(f->n_cat, 1), nullptr);
@@ -378,6 +388,8 @@ ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
         const int nblk = pack_num_blocks(n);
         DevBuf d_bc(sizeof(long long) * 2 * (size_t)std::max(nblk, 1)), d_tot(sizeof(long long) * 2), d_flags(sizeof(int) * 4);
         OB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * 4, st));
+        t_h2d.stop();
+        Timer t_pack(st, &ms_pack);
         pack_count_scan(pa, d_bc.as<long long>(), d_tot.as<long long>(), d_flags.as<int>(), st);
         long long tot[2]; int flags[4];
         OB_CUDA(cudaMemcpyAsync(tot, d_tot.p, sizeof tot, cudaMemcpyDeviceToHost, st));
@@ -392,8 +404,11 @@ ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
         alloc_group(ctx, d->g[1], tot[1], d->ldx, d->weighted);
         pack_scatter(pa, d_bc.as<long long>(), d->g[0], d->g[1], d_flags.as<int>(), st);
         for (int g = 0; g < 2; ++g) scale_rows_launch(d->g[g], d->ldx, st);
+        t_pack.stop();
         OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
         OB_CUDA(cudaStreamSynchronize(st));
+        t_h2d.collect(); t_pack.collect();
+        d->ms_h2d = ms_h2d; d->ms_pack = ms_pack;
         if (flags[1]) fail(OB_ERR_INVALID_ARG, "categorical code outside [0, levels)");
         *out = d.release();
     });

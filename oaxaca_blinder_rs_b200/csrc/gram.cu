@@ -49,6 +49,7 @@ struct GramKernelParams {
     long long units_total;
     int ldx, panels, ntiles, stages;
     int nfull, has_half;    // column tiling: nfull tiles of BN columns + (has_half ? one tile of BN/2 : none)
+    int sched;              // 1: lockstep round-robin (default), 0: contiguous cost-balanced ranges (OBBOOT_GRAM_SCHED)
     double* partials;       // [units_total][BM*BN], unit-major (a half tile uses the first BM*BN/2 doubles, stride BN/2)
     const uint16_t* pairs;
 };
@@ -188,6 +189,18 @@ __device__ __forceinline__ void gram_unit(GramCta<CountT>& c, const GramKernelPa
         }
 }
 
+// p.sched = 0: first unit (in (group, panel, segment, tile) order) at or after cumulative cost w; a half-width tile
+// is budgeted as half a full one
+__device__ __forceinline__ long long unit_at_cost(const GramKernelParams& p, long long w) {
+    const long long wt = 2 * p.nfull + p.has_half;          // cost of one (panel, segment) sweep over the column tiles
+    const long long W0 = (long long)p.panels * p.segs[0] * wt;
+    long long base = 0;
+    if (w >= W0) { w -= W0; base = p.units0; }
+    const long long sweep = w / wt, r = w - sweep * wt;
+    const long long i = r < 2LL * p.nfull ? (r + 1) / 2 : (long long)p.nfull;
+    return min(base + sweep * p.ntiles + i, p.units_total);
+}
+
 template <typename CountT, int LDXC>
 __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -211,29 +224,49 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
     }
     __syncthreads();
 
-    // Unit schedule.  Sequence = all full-width tiles in (group, segment, panel, tile) order, then all half-width
-    // tiles in (group, segment, panel) order; CTA b takes sequence positions b, b + grid, b + 2 grid, ...  Units of one
-    // class cost the same, so (a) every CTA gets the same number of each class (+-1) whatever their relative cost, and
-    // (b) the grid advances in lockstep through CONSECUTIVE units: at any time the CTAs work on the same row segment,
-    // sharing its design rows across all panels and column tiles, and each panel's count tile across its column
-    // tiles, through L2 -- HBM traffic stays near one pass over X and C instead of one pass per unit.
+    // Unit schedule (p.sched = 1).  Sequence = all full-width tiles in (group, segment, panel, tile) order, then all
+    // half-width tiles in (group, segment, panel) order; CTA b takes sequence positions b, b + grid, b + 2 grid, ...
+    // Units of one class cost the same, so (a) every CTA gets the same number of each class (+-1) whatever their
+    // relative cost, and (b) the grid advances in lockstep through CONSECUTIVE units: at any time the CTAs work on the
+    // same row segment, sharing its design rows across all panels and column tiles, and each panel's count tile across
+    // its column tiles, through L2 -- HBM traffic stays near one pass over X and C instead of one pass per unit
+    // (measured at config 3: 105 GB instead of 917 GB per launch, profiles/r01_gram_dram_config3_v*.csv).
+    // p.sched = 0: CTA b walks a contiguous, cost-balanced range of the (group, panel, segment, tile) order.
     const long long sweeps0 = (long long)p.segs[0] * p.panels, sweeps1 = (long long)p.segs[1] * p.panels;
     const long long NF0 = sweeps0 * p.nfull, NF = NF0 + sweeps1 * p.nfull;
     const long long NH = p.has_half ? sweeps0 + sweeps1 : 0;
-    for (long long i = blockIdx.x; i < NF + NH; i += gridDim.x) {
-        int g, nt; long long sweep;   // sweep = seg * panels + panel within the group
-        if (i < NF) {
-            g = i >= NF0 ? 1 : 0;
-            const long long r = i - (g ? NF0 : 0);
-            sweep = r / p.nfull; nt = (int)(r - sweep * p.nfull);
+    long long i, i_end, i_step;
+    if (p.sched) { i = blockIdx.x; i_end = NF + NH; i_step = gridDim.x; }
+    else {
+        const long long W = (sweeps0 + sweeps1) * (2 * p.nfull + p.has_half);
+        i = unit_at_cost(p, W * (long long)blockIdx.x / gridDim.x);
+        i_end = blockIdx.x + 1 == gridDim.x ? p.units_total : unit_at_cost(p, W * (long long)(blockIdx.x + 1) / gridDim.x);
+        i_step = 1;
+    }
+    for (; i < i_end; i += i_step) {
+        int g, nt, seg, panel;
+        if (p.sched) {
+            long long sweep;   // seg * panels + panel within the group
+            if (i < NF) {
+                g = i >= NF0 ? 1 : 0;
+                const long long r = i - (g ? NF0 : 0);
+                sweep = r / p.nfull; nt = (int)(r - sweep * p.nfull);
+            } else {
+                const long long r = i - NF;
+                g = r >= sweeps0 ? 1 : 0;
+                sweep = r - (g ? sweeps0 : 0); nt = p.nfull;
+            }
+            seg = (int)(sweep / p.panels); panel = (int)(sweep - (long long)seg * p.panels);
         } else {
-            const long long r = i - NF;
-            g = r >= sweeps0 ? 1 : 0;
-            sweep = r - (g ? sweeps0 : 0); nt = p.nfull;
+            g = (i >= p.units0) ? 1 : 0;
+            const long long ug = i - (g ? p.units0 : 0);
+            const long long sweep = ug / p.ntiles;   // panel * segs + seg
+            const int sg = g ? p.segs[1] : p.segs[0];
+            nt = (int)(ug - sweep * p.ntiles);
+            panel = (int)(sweep / sg); seg = (int)(sweep - (long long)panel * sg);
         }
         const int segs = g ? p.segs[1] : p.segs[0], seg_rows = g ? p.seg_rows[1] : p.seg_rows[0];
         const long long n_pad = g ? p.n_pad[1] : p.n_pad[0];
-        const int seg = (int)(sweep / p.panels), panel = (int)(sweep - (long long)seg * p.panels);
         const long long row0 = (long long)seg * seg_rows;
         const long long row1 = min(row0 + seg_rows, n_pad);
         const int nstages = (int)((row1 - row0) / KT);
@@ -243,7 +276,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
         const double* Xg = (g ? p.X[1] : p.X[0]) + row0 * c.ldx;
         const CountT* Cg = reinterpret_cast<const CountT*>(g ? p.C[1] : p.C[0]) + ((long long)panel * n_pad + row0) * BM;
         double* out = p.partials + (size_t)u * (BM * BN);
-        if (nt == p.nfull) gram_unit<CountT, LDXC, 16, 1>(c, p, Xg, Cg, nstages, nt * BN, out);
+        if (p.has_half && nt == p.nfull) gram_unit<CountT, LDXC, 16, 1>(c, p, Xg, Cg, nstages, nt * BN, out);
         else gram_unit<CountT, LDXC, 16, 2>(c, p, Xg, Cg, nstages, nt * BN, out);
     }
 }
@@ -360,6 +393,8 @@ void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEve
     p.units_total = pl.units[0] + pl.units[1];
     p.ldx = pl.ldx; p.panels = pl.panels; p.ntiles = pl.ntiles; p.stages = pl.stages;
     p.nfull = pl.nfull; p.has_half = pl.has_half;
+    static const int sched = getenv("OBBOOT_GRAM_SCHED") ? atoi(getenv("OBBOOT_GRAM_SCHED")) : 1;   // tuning knob
+    p.sched = sched;
     p.partials = a.partials; p.pairs = a.d_pairs;
     if (ev_main_begin) OB_CUDA(cudaEventRecord(ev_main_begin, st));
     auto launch = [&](auto kernel) {
