@@ -247,10 +247,15 @@ def main():
             des.apply_rif(rif_tau)
         return des
 
+    res_buf = {}
+
     def step(design):
+        # OaxacaResults.residuals goes into a caller-owned buffer reused across steps (as a Rust caller would reuse a Vec)
+        rb = res_buf.setdefault(design.n_b, np.empty(design.n_b))
         if world == 1 or shard_rows:
-            return ob.bootstrap(design, reps, ref_kind=ref, norm=normv, seed=2026)
-        return obd.bootstrap_sharded(design, reps, device=torch.device("cuda", local), ref_kind=ref, norm=normv, seed=2026)
+            return ob.bootstrap(design, reps, ref_kind=ref, norm=normv, seed=2026, residuals_out=rb)
+        return obd.bootstrap_sharded(design, reps, device=torch.device("cuda", local), ref_kind=ref, norm=normv, seed=2026,
+                                     residuals_out=rb if rank == 0 else None)
 
     def sync():
         torch.cuda.synchronize()
@@ -296,7 +301,7 @@ def main():
     sync()
     dt_e = time.perf_counter() - t1
     S = out["S"]
-    d2h = 8 * (S * 6 + 3 * K + 1) + 8 * out["residuals_b"].size
+    d2h = 8 * (S * 6 + 3 * K + 1) + 8 * (out["residuals_b"].size if "residuals_b" in out else 0)
 
     times = torch.tensor([dt, dt_e], dtype=torch.float64, device="cuda")
     if dist is not None:

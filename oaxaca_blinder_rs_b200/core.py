@@ -216,8 +216,10 @@ def num_stats(K: int, norm: Sequence[NormVar]) -> int:
 def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequence[NormVar] = (),
               seed: int = 0, idx_a=None, idx_b=None, rep_begin: int = 0, rep_end: int = 0,
               skip_reduce: bool = False, count_bits: int = 0, max_workspace_bytes: int = 0,
-              want_rep: bool = False, want_residuals: bool = True) -> dict:
-    """ob_bootstrap_run.  Returns point estimates, per-statistic SE/p/CI/t and (optionally) replicate detail."""
+              want_rep: bool = False, want_residuals: bool = True, residuals_out: Optional[np.ndarray] = None) -> dict:
+    """ob_bootstrap_run.  Returns point estimates, per-statistic SE/p/CI/t and (optionally) replicate detail.
+    residuals_out: optional preallocated float64 [n_b] buffer for OaxacaResults.residuals (reusing one across calls
+    avoids first-touch page faults on a fresh 8 n_b byte array during the device-to-host copy)."""
     ctx, K = design.ctx, design.K
     norm = list(norm)
     S = num_stats(K, norm)
@@ -245,7 +247,9 @@ def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequ
              beta_a=np.empty(K), beta_b=np.empty(K), std_err=np.full(S, np.nan), p_value=np.full(S, np.nan),
              ci_lower=np.full(S, np.nan), ci_upper=np.full(S, np.nan), t_stat=np.zeros(S))
     if want_residuals:
-        a["residuals_b"] = np.empty(design.n_b)
+        if residuals_out is not None:
+            assert residuals_out.dtype == np.float64 and residuals_out.shape == (design.n_b,) and residuals_out.flags.c_contiguous
+        a["residuals_b"] = residuals_out if residuals_out is not None else np.empty(design.n_b)
     if want_rep or skip_reduce:
         a["rep_stats"] = np.empty((max(nrep, 1), S))
         a["rep_status"] = np.zeros(max(nrep, 1), dtype=np.int32)

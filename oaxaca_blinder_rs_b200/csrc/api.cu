@@ -6,6 +6,7 @@
 #include "internal.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -83,6 +84,21 @@ struct Timer {
     void stop() { cudaEventRecord(b, st); }
     void collect() { float ms = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b); *acc += ms; }
     ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+
+// OBBOOT_TRACE=1: host wall-clock marks of ob_bootstrap_run's phases on stderr (diagnosing per-call fixed costs)
+struct Trace {
+    bool on; std::chrono::steady_clock::time_point t0, last;
+    Trace() : on(getenv("OBBOOT_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), last(t0) {}
+    void mark(const char* what, cudaStream_t st = nullptr, bool sync = false) {
+        if (!on) return;
+        if (sync) cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[obboot] %-28s +%8.3f ms  (t = %9.3f ms)\n", what,
+                std::chrono::duration<double, std::milli>(now - last).count(),
+                std::chrono::duration<double, std::milli>(now - t0).count());
+        last = now;
+    }
 };
 
 template <typename F>
@@ -481,6 +497,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         res->gpu_launches = 0;
         res->n_ok = 0;
         Timer t_total(st, &res->ms_total);
+        Trace tr;
 
         // ---- normalisation spec on the device ----
         const int nn = std::max(o->n_norm, 1);
@@ -532,6 +549,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 OB_CUDA(cudaStreamSynchronize(st));
                 ppb = v;
             }
+            tr.mark("setup", st, true);
             DevBuf d_C[2], d_idx[2], d_colsum(sizeof(long long) * 2 * (size_t)ppb * BM);
             for (int g = 0; g < 2; ++g) d_C[g].alloc((size_t)ppb * n_pad[g] * BM * count_bytes);
             const size_t gram_elems = 2 * (size_t)ppb * BM * Pld;      // [2][slots_pad][Pld]
@@ -548,6 +566,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 OB_CUDA(cudaStreamSynchronize(st));
             }
 
+            tr.mark("workspace + pair table", st, true);
             for (int64_t p0 = 0; p0 < panels_total && !saturated; p0 += ppb) {
                 const int64_t pn = std::min(ppb, panels_total - p0);
                 const int64_t slot_lo = p0 * BM, slot_hi = std::min(slots, (p0 + pn) * BM);
@@ -596,6 +615,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                     }
                 }
                 t_counts.stop();
+                tr.mark("counts", st, true);
 
                 // (3) Gram / cross-product contraction
                 if (plan_panels != pn) {
@@ -613,6 +633,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 gram_launch(plan, ga, st, ev0, ev1);
                 res->gpu_launches += 2;
                 t_gram.stop();
+                tr.mark("gram", st, true);
                 if (comm) {
                     // every rank's subtree sums -> all ranks; the top of the summation tree is then evaluated in fixed
                     // order on each rank (bit-identical to the single-GPU reduction)
@@ -646,6 +667,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 int flags[4];
                 OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
                 OB_CUDA(cudaStreamSynchronize(st));
+                tr.mark("solve + flags", st, false);
                 t_counts.collect(); t_gram.collect(); t_solve.collect();
                 { float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1); res->ms_gram_kernel += ms; cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
                 if (flags[2]) fail(OB_ERR_INVALID_ARG, "resample index out of range");
@@ -660,6 +682,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
             res->ms_counts = res->ms_gram = res->ms_solve = res->ms_gram_kernel = res->ms_comm = 0.0;
         }
 
+        tr.mark("batches done (buffers freed)", st, true);
         // ---- point estimate (builder.rs:810-811): a failure here is a hard error ----
         int point_status = 0;
         std::vector<double> point(5 * (size_t)K + 1);
@@ -682,6 +705,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
             OB_CUDA(cudaStreamSynchronize(st));
         }
 
+        tr.mark("point + residuals", st, true);
         // ---- (5) reduction to standard errors / p-values / percentile CIs ----
         if (!o->skip_reduce) {
             DevBuf d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long));
@@ -710,6 +734,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         t_total.stop();
         OB_CUDA(cudaStreamSynchronize(st));
         t_total.collect();
+        tr.mark("reduce + replicate D2H", st, false);
     });
 }
 

@@ -57,6 +57,7 @@ def bootstrap_sharded(design, reps: int, group=None, device=None, **kw) -> dict:
     from . import core
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     b, e = shard_range(rank, world, reps)
+    kw.setdefault("want_residuals", rank == 0)     # OaxacaResults.residuals (builder.rs:946) is fetched once, on rank 0
     part = core.bootstrap(design, reps, rep_begin=b, rep_end=e, skip_reduce=True, **kw) if e > b else \
         core.bootstrap(design, 0, skip_reduce=True, **{k: v for k, v in kw.items() if k not in ("idx_a", "idx_b")})
     S = part["S"]
