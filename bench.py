@@ -222,6 +222,8 @@ def main():
     else:
         d, norm, reps, ref = make_data(name)
         n = d["n"]
+        if world > 1:
+            ctx.init_nccl(rank, world)       # mode R: only the upload uses it (frame slices gathered over NVLink)
     K = 1 + len(d["cont"]) + sum(m - 1 for m in d["cat_levels"])
     normv = [ob.NormVar(m, i) for m, i in norm]
 
@@ -234,10 +236,21 @@ def main():
                   w=pin(d["weights"]) if d["weights"] is not None else None, g=pin(d["group"]))
     h2d = sum(t.numel() * t.element_size() for t in pinned["cont"] + pinned["cat"] + [pinned["y"], pinned["g"]]
               + ([pinned["w"]] if pinned["w"] is not None else []))
+    if world > 1 and not shard_rows:
+        h2d //= world                       # each rank uploads its frame slice only
 
     rif_tau = args.rif_tau if args.rif_tau is not None else (0.5 if name.startswith("config4") else None)
 
     def pack():
+        if world > 1 and not shard_rows:
+            # mode R: this rank uploads 1/world of the frame; the packed rows are all-gathered over NVLink
+            fr = dict(n=n, cont=[t.numpy() for t in pinned["cont"]], cat_codes=[t.numpy() for t in pinned["cat"]],
+                      cat_levels=d["cat_levels"], outcome=pinned["y"].numpy(),
+                      weights=None if pinned["w"] is None else pinned["w"].numpy(), group=pinned["g"].numpy())
+            des = obd.pack_replicated(ctx, fr, rank, world)
+            if rif_tau is not None:
+                des.apply_rif(rif_tau)
+            return des
         des = ob.Design.pack(ctx, [t.numpy() for t in pinned["cont"]], [t.numpy() for t in pinned["cat"]],
                              d["cat_levels"], pinned["y"].numpy(), None if pinned["w"] is None else pinned["w"].numpy(),
                              pinned["g"].numpy())

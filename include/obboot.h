@@ -190,6 +190,12 @@ ob_status ob_row_shard_plan(int64_t n_group, int32_t world, int32_t rank, int64_
  * must equal the plan's) */
 ob_status ob_design_set_row_shard(ob_design* d, int64_t n_a_global, int64_t n_b_global, int32_t world, int32_t rank);
 
+/* Mode R with a distributed upload: every rank packed a CONTIGUOUS SLICE of the frame (ob_design_pack on rows
+ * [n r / world, n (r+1) / world), slices in rank order); assembles the full per-group designs on every rank with one
+ * variable-size all-gather over the context's communicator (NVLink), so that a rank moves only 1/world of the frame
+ * over PCIe.  The result equals ob_design_pack of the whole frame bit for bit. */
+ob_status ob_design_allgather_rows(ob_ctx* ctx, const ob_design* local_slice, ob_design** out);
+
 /* Multiplicity counts of one replicate of the native stream (for the statistical validation
  * tests): counts_out [n] for group g (0 = A, 1 = B) of design d. */
 ob_status ob_debug_counts(ob_ctx* ctx, const ob_design* d, uint64_t seed, int64_t rep, int32_t group,

@@ -173,6 +173,13 @@ class Design:
         self.ctx.check(N.lib().ob_design_download(self.ctx._h, self._h, _dp(Xa), _dp(ya), _dp(wa), _dp(Xb), _dp(yb), _dp(wb)))
         return Xa, ya, wa, Xb, yb, wb
 
+    def allgather_rows(self) -> "Design":
+        """ob_design_allgather_rows: this design holds rank's contiguous frame slice; returns the full design
+        (identical on every rank) assembled over the context's communicator."""
+        h = C.c_void_p()
+        self.ctx.check(N.lib().ob_design_allgather_rows(self.ctx._h, self._h, C.byref(h)))
+        return Design(self.ctx, h)
+
     def pack_timings(self):
         """(ms_h2d, ms_pack_kernels) of the ob_design_pack call that built this design."""
         a, b = C.c_double(), C.c_double()

@@ -283,6 +283,52 @@ ob_status ob_design_set_row_shard(ob_design* d, int64_t n_a_global, int64_t n_b_
     return OB_OK;
 }
 
+// Mode R with a distributed upload: every rank packed a contiguous slice of the frame (slices in rank order); the
+// full per-group designs are assembled on every rank by one variable-size all-gather over NVLink, so a rank moves
+// only 1/world of the frame across PCIe.
+ob_status ob_design_allgather_rows(ob_ctx* ctx, const ob_design* local, ob_design** out) {
+    if (!ctx || !local || !out) return OB_ERR_INVALID_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        Comm* comm = ctx->comm.get();
+        if (!comm) fail(OB_ERR_NCCL, "ob_design_allgather_rows needs ob_comm_init_* on this context");
+        if (local->world != 1) fail(OB_ERR_INVALID_ARG, "the local design is a row shard (mode N); gather applies to frame slices");
+        cudaStream_t st = ctx->stream;
+        const int world = comm->world;
+        // row counts of every rank's slice, per group (+ a consistency word: K, n_cont, weighted)
+        std::vector<long long> mine = {(long long)local->g[0].n, (long long)local->g[1].n,
+                                       ((long long)local->K << 32) | ((long long)local->n_cont << 1) | (local->weighted ? 1 : 0)};
+        DevBuf d_mine(sizeof(long long) * 3), d_all(sizeof(long long) * 3 * world);
+        OB_CUDA(cudaMemcpyAsync(d_mine.p, mine.data(), sizeof(long long) * 3, cudaMemcpyHostToDevice, st));
+        comm->allgather(d_mine.p, d_all.p, sizeof(long long) * 3, st);
+        std::vector<long long> all(3 * (size_t)world);
+        OB_CUDA(cudaMemcpyAsync(all.data(), d_all.p, sizeof(long long) * 3 * world, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        for (int r = 0; r < world; ++r)
+            if (all[3 * r + 2] != mine[2]) fail(OB_ERR_INVALID_ARG, "ranks disagree on the design shape (K, n_cont, weights)");
+
+        std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
+        d->stream = ctx->stream; d->device = ctx->device; d->K = local->K; d->n_cont = local->n_cont; d->V = local->V;
+        d->ldx = local->ldx; d->weighted = local->weighted;
+        for (int g = 0; g < 2; ++g) {
+            std::vector<size_t> off_x(world), sz_x(world), off_w(world), sz_w(world);
+            long long total = 0;
+            for (int r = 0; r < world; ++r) {
+                const long long nr = all[3 * r + g];
+                off_x[r] = (size_t)total * d->ldx * sizeof(double); sz_x[r] = (size_t)nr * d->ldx * sizeof(double);
+                off_w[r] = (size_t)total * sizeof(double);          sz_w[r] = (size_t)nr * sizeof(double);
+                total += nr;
+            }
+            alloc_group(ctx, d->g[g], total, d->ldx, d->weighted);
+            comm->allgatherv(local->g[g].X, d->g[g].X, off_x.data(), sz_x.data(), st);
+            if (d->weighted) comm->allgatherv(local->g[g].w, d->g[g].w, off_w.data(), sz_w.data(), st);
+            scale_rows_launch(d->g[g], d->ldx, st);
+        }
+        OB_CUDA(cudaStreamSynchronize(st));
+        *out = d.release();
+    });
+}
+
 void ob_design_destroy(ob_design* d) {
     if (!d) return;
     cudaSetDevice(d->device);

@@ -38,6 +38,9 @@ struct NcclApi {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 
@@ -59,8 +62,12 @@ NcclApi& nccl_api() {
         api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
         api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.handle, "ncclAllGather"));
         api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
+        api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(api.handle, "ncclBroadcast"));
+        api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(api.handle, "ncclGroupStart"));
+        api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(api.handle, "ncclGroupEnd"));
     });
-    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.AllGather)
+    if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.AllGather || !api.Broadcast ||
+        !api.GroupStart || !api.GroupEnd)
         comm_fail("libnccl.so.2 could not be loaded (set OBBOOT_NCCL_LIB to its path)");
     return api;
 }
@@ -81,6 +88,17 @@ struct NcclComm final : Comm {
     }
     void allgather(const void* send, void* recv, size_t bytes, cudaStream_t st) override {
         nccl_check(nccl_api().AllGather(send, recv, bytes, NCCL_INT8, comm, st), "ncclAllGather");
+    }
+    void allgatherv(const void* send, void* recv, const size_t* offsets, const size_t* sizes, cudaStream_t st) override {
+        // one broadcast per root, fused into a single NCCL group: every block travels once over NVLink into place
+        NcclApi& a = nccl_api();
+        nccl_check(a.GroupStart(), "ncclGroupStart");
+        for (int r = 0; r < world; ++r) {
+            if (sizes[r] == 0) continue;
+            char* dst = static_cast<char*>(recv) + offsets[r];
+            nccl_check(a.Broadcast(r == rank ? send : dst, dst, sizes[r], NCCL_INT8, r, comm, st), "ncclBroadcast");
+        }
+        nccl_check(a.GroupEnd(), "ncclGroupEnd");
     }
 };
 
@@ -149,6 +167,16 @@ struct LocalComm final : Comm {
         OB_CUDA(cudaGetLastError());
     }
     void allgather(const void* send, void* recv, size_t bytes, cudaStream_t st) override { pull_all(send, recv, bytes, st); }
+    void allgatherv(const void* send, void* recv, const size_t* offsets, const size_t* sizes, cudaStream_t st) override {
+        OB_CUDA(cudaStreamSynchronize(st));
+        grp->ptrs[(size_t)rank] = send;
+        grp->barrier();
+        for (int r = 0; r < world; ++r)
+            if (sizes[r])
+                OB_CUDA(cudaMemcpyAsync(static_cast<char*>(recv) + offsets[r], grp->ptrs[(size_t)r], sizes[r], cudaMemcpyDefault, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        grp->barrier();
+    }
 };
 
 }  // namespace

@@ -208,6 +208,8 @@ struct Comm {
     virtual void allreduce(void* buf, size_t count, CommDType dt, CommOp op, cudaStream_t st) = 0;
     // recv [world][bytes] <- every rank's send [bytes]
     virtual void allgather(const void* send, void* recv, size_t bytes, cudaStream_t st) = 0;
+    // variable sizes: rank r's `sizes[r]` bytes (its `send`) land at recv + offsets[r] on every rank
+    virtual void allgatherv(const void* send, void* recv, const size_t* offsets, const size_t* sizes, cudaStream_t st) = 0;
 };
 struct LocalGroup;                       // shared state of an in-process group (ob_local_group)
 LocalGroup* local_group_create(int world);

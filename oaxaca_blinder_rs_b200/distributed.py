@@ -98,3 +98,23 @@ def pack_row_shard(ctx, d: dict, rank: int, world: int):
     des = core.Design.pack(ctx, loc["cont"], loc["cat_codes"], loc["cat_levels"], loc["outcome"], loc["weights"], loc["group"])
     des.set_row_shard(loc["n_a_global"], loc["n_b_global"], world, rank)
     return des
+
+
+def frame_slice(d: dict, rank: int, world: int) -> dict:
+    """Contiguous rows [n r / world, n (r+1) / world) of the frame (views, no copy)."""
+    n = d["n"]
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    return dict(n=hi - lo, cont=[c[lo:hi] for c in d["cont"]], cat_codes=[c[lo:hi] for c in d["cat_codes"]],
+                cat_levels=list(d["cat_levels"]), outcome=d["outcome"][lo:hi],
+                weights=None if d["weights"] is None else d["weights"][lo:hi], group=d["group"][lo:hi])
+
+
+def pack_replicated(ctx, d: dict, rank: int, world: int):
+    """Mode R upload: this rank sends only its frame slice over PCIe and packs it; the full design is assembled on
+    every GPU by ob_design_allgather_rows (needs Context.init_nccl / init_local).  Equals Design.pack(whole frame)."""
+    from . import core
+    sl = frame_slice(d, rank, world)
+    loc = core.Design.pack(ctx, sl["cont"], sl["cat_codes"], sl["cat_levels"], sl["outcome"], sl["weights"], sl["group"])
+    full = loc.allgather_rows()
+    loc.close()
+    return full

@@ -179,3 +179,44 @@ def test_sharded_design_without_communicator_fails_loudly():
     with pytest.raises(ob.OaxacaError):
         des.set_row_shard(des.n_a_global + 5, des.n_b_global, 2, 0)     # local rows no longer match the plan
     des.close(); ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("weighted", [False, True])
+def test_allgather_rows_equals_whole_frame_pack(weighted):
+    """Mode R upload: each context packs a contiguous frame slice; the gathered design equals the whole-frame pack."""
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import core, synth, distributed as obd
+    d = synth.make_wage(30_011, 3, cat_levels=(3,), weights=weighted, seed=9)
+    ctx = ob.Context(0)
+    whole = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+    ref = whole.download()
+    ref_run = ob.bootstrap(whole, 40, seed=3, want_rep=True)
+    whole.close(); ctx.close()
+    world = 4
+    grp = core.LocalGroup(world)
+    outs, errs = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            c = ob.Context(0)
+            c.init_local(grp, r)
+            full = obd.pack_replicated(c, d, r, world)
+            b, e = obd.shard_range(r, world, 40)
+            outs[r] = (full.download(), ob.bootstrap(full, 40, seed=3, rep_begin=b, rep_end=e, skip_reduce=True))
+            full.close(); c.close()
+        except Exception as ex:  # noqa: BLE001
+            errs[r] = ex
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert all(e is None for e in errs), errs
+    for r, (mats, part) in enumerate(outs):
+        for a, b_ in zip(mats, ref):
+            if weighted or not np.all(np.isnan(b_)):
+                assert np.array_equal(a, b_, equal_nan=True)
+        b, e = obd.shard_range(r, world, 40)
+        assert _same(part["rep_stats"], ref_run["rep_stats"][b:e])
+        assert _same(part["point_stats"], ref_run["point_stats"])

@@ -26,12 +26,19 @@ def _worker(rank, world, port, q):
     des = obd.pack_row_shard(ctx, loc, rank, world)
     out = ob.bootstrap(des, reps, ref_kind=ob.REF_WEIGHTED, norm=norm, seed=5, want_rep=True, max_workspace_bytes=80_000_000)
     des.close()
+    # mode R upload over the same communicator: frame slices packed per rank, full design gathered over NVLink
+    rep = obd.pack_replicated(ctx, full, rank, world)
+    gathered = rep.download()
+    rep.close()
     ctx.comm_destroy()
     one = None
     if rank == 0:
         des1 = ob.Design.pack(ctx, full["cont"], full["cat_codes"], full["cat_levels"], full["outcome"], full["weights"], full["group"])
         one = ob.bootstrap(des1, reps, ref_kind=ob.REF_WEIGHTED, norm=norm, seed=5, want_rep=True)
+        whole = des1.download()
         des1.close()
+        for a, b_ in zip(gathered, whole):
+            assert np.array_equal(a, b_, equal_nan=True)
     keys = ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper", "p_value")
     q.put((rank, {k: out[k] for k in keys}, None if one is None else {k: one[k] for k in keys}, out["timings_ms"]))
     dist.barrier()
