@@ -89,6 +89,12 @@ ob_status ob_design_pack_timings(const ob_design* d, double* ms_h2d, double* ms_
 /* get_data_matrices() equivalent: copies the packed design back (row-major [n_g x K]); any pointer may be NULL */
 ob_status ob_design_download(ob_ctx* ctx, const ob_design* d, double* Xa, double* ya, double* wa,
                              double* Xb, double* yb, double* wb);
+/* Outcome refresh for callers that re-run the decomposition on the SAME predictors with another outcome (JMP's two
+ * runs, jmp.rs:44-106; the engine's perturbed-wage sweeps, engine/src/analysis.rs:871-914): replaces the outcome
+ * column of the packed design by y_frame (host, one value per row of the frame the design was packed from, nulls
+ * not allowed), keeping X, the weights and the group split resident.  8 n bytes over PCIe instead of the whole frame.
+ * Undoes a previous ob_design_apply_rif.  For ob_design_from_dense designs the "frame" is [y_a ; y_b]. */
+ob_status ob_design_update_outcome(ob_ctx* ctx, ob_design* d, const double* y_frame, int64_t n_frame);
 /* decompose_quantile pre-step (builder.rs:721-737 -> math/rif.rs:14-88): replaces each group's
  * outcome by its RIF at quantile tau, computed on the device, unweighted, per group. */
 ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau);

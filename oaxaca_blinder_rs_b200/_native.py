@@ -24,7 +24,7 @@ SYMBOLS = ["ob_abi_version", "ob_device_count", "ob_ctx_create", "ob_ctx_destroy
            "ob_design_apply_rif", "ob_num_stats", "ob_bootstrap_run", "ob_reduce_stats", "ob_debug_counts",
            "ob_comm_unique_id", "ob_comm_init_nccl", "ob_local_group_create", "ob_local_group_destroy",
            "ob_comm_init_local", "ob_comm_destroy", "ob_row_shard_plan", "ob_design_set_row_shard",
-           "ob_design_pack_timings", "ob_design_allgather_rows"]
+           "ob_design_pack_timings", "ob_design_allgather_rows", "ob_design_update_outcome"]
 
 
 class FrameView(C.Structure):
@@ -103,5 +103,6 @@ def lib() -> C.CDLL:
         L.ob_design_set_row_shard.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32]
         L.ob_design_pack_timings.argtypes = [C.c_void_p, _DP, _DP]
         L.ob_design_allgather_rows.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ob_design_update_outcome.argtypes = [C.c_void_p, C.c_void_p, _DP, C.c_int64]
         _lib = L
     return _lib

@@ -194,6 +194,11 @@ class Design:
                                   f"for rank {rank} of {world}")
         self.n_a_global, self.n_b_global, self.world, self.rank = n_a_global, n_b_global, world, rank
 
+    def update_outcome(self, y_frame):
+        """ob_design_update_outcome: new outcome (one value per frame row), X / weights / group split stay resident."""
+        y = np.ascontiguousarray(y_frame, dtype=np.float64)
+        self.ctx.check(N.lib().ob_design_update_outcome(self.ctx._h, self._h, _dp(y), y.shape[0]))
+
     def apply_rif(self, tau: float):
         self.ctx.check(N.lib().ob_design_apply_rif(self.ctx._h, self._h, float(tau)))
 

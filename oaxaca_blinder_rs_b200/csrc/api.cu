@@ -33,6 +33,7 @@ struct ob_design {
     int device = 0;
     int K = 0, n_cont = 0, V = 0, ldx = 0;
     bool weighted = false;
+    int64_t n_frame = 0;             // rows of the frame the design was packed from (ob_design_update_outcome)
     int world = 1, rank = 0;         // row sharding (mode N): this design holds rank's rows of a world-way split
     double ms_h2d = 0.0, ms_pack = 0.0;   // device time of the column upload and of the pack kernels (ob_design_pack)
     GroupData g[2];
@@ -143,6 +144,7 @@ void alloc_group(ob_ctx* ctx, GroupData& g, int64_t n, int ldx, bool weighted) {
         OB_CUDA(cudaMemsetAsync(g.w, 0, sizeof(double) * (size_t)g.n_pad, st));
         OB_CUDA(cudaMallocFromPoolAsync((void**)&g.Xs, sizeof(double) * (size_t)g.n_pad * ldx, ctx->pool_design, st));
     }
+    OB_CUDA(cudaMallocFromPoolAsync((void**)&g.src, sizeof(uint32_t) * (size_t)g.n_pad, ctx->pool_design, st));
 }
 
 const char* status_text(int s) {
@@ -320,6 +322,7 @@ ob_status ob_design_allgather_rows(ob_ctx* ctx, const ob_design* local, ob_desig
                 total += nr;
             }
             alloc_group(ctx, d->g[g], total, d->ldx, d->weighted);
+            cudaFreeAsync(d->g[g].src, st); d->g[g].src = nullptr;   // frame-row map is not gathered
             comm->allgatherv(local->g[g].X, d->g[g].X, off_x.data(), sz_x.data(), st);
             if (d->weighted) comm->allgatherv(local->g[g].w, d->g[g].w, off_w.data(), sz_w.data(), st);
             scale_rows_launch(d->g[g], d->ldx, st);
@@ -333,7 +336,12 @@ void ob_design_destroy(ob_design* d) {
     if (!d) return;
     cudaSetDevice(d->device);
     cudaStream_t st = d->stream;
-    for (auto& g : d->g) { if (g.X) cudaFreeAsync(g.X, st); if (g.w) cudaFreeAsync(g.w, st); if (g.Xs) cudaFreeAsync(g.Xs, st); }
+    for (auto& g : d->g) {
+        if (g.X) cudaFreeAsync(g.X, st);
+        if (g.w) cudaFreeAsync(g.w, st);
+        if (g.Xs) cudaFreeAsync(g.Xs, st);
+        if (g.src) cudaFreeAsync(g.src, st);
+    }
     delete d;
 }
 
@@ -384,7 +392,9 @@ ob_status ob_design_from_dense(ob_ctx* ctx, int32_t K, int32_t n_cont,
                                       (size_t)ns[g], cudaMemcpyHostToDevice, ctx->stream));
             if (d->weighted && ws[g])
                 OB_CUDA(cudaMemcpyAsync(d->g[g].w, ws[g], sizeof(double) * (size_t)ns[g], cudaMemcpyHostToDevice, ctx->stream));
+            iota_launch(d->g[g].src, ns[g], (uint32_t)(g == 0 ? 0 : na), ctx->stream);
         }
+        d->n_frame = na + nb;
         for (int g = 0; g < 2; ++g) scale_rows_launch(d->g[g], d->ldx, ctx->stream);
         OB_CUDA(cudaStreamSynchronize(ctx->stream));
         *out = d.release();
@@ -462,6 +472,8 @@ ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
         std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
         d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = f->n_cont; d->V = K + 1; d->ldx = pa.ldx;
         d->weighted = f->weights != nullptr;
+        d->n_frame = n;
+        if (n > 0xFFFFFFFFll) fail(OB_ERR_UNSUPPORTED, "frames beyond 2^32 rows (IdxSize is u32 in the reference too)");
         alloc_group(ctx, d->g[0], tot[0], d->ldx, d->weighted);
         alloc_group(ctx, d->g[1], tot[1], d->ldx, d->weighted);
         pack_scatter(pa, d_bc.as<long long>(), d->g[0], d->g[1], d_flags.as<int>(), st);
@@ -490,6 +502,19 @@ ob_status ob_design_download(ob_ctx* ctx, const ob_design* d, double* Xa, double
                                                  (size_t)G.n, cudaMemcpyDeviceToHost, ctx->stream));
             if (ws[g] && G.w) OB_CUDA(cudaMemcpyAsync(ws[g], G.w, sizeof(double) * (size_t)G.n, cudaMemcpyDeviceToHost, ctx->stream));
         }
+        OB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+ob_status ob_design_update_outcome(ob_ctx* ctx, ob_design* d, const double* y_frame, int64_t n_frame) {
+    if (!ctx || !d || !y_frame) return OB_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        if (n_frame != d->n_frame) fail(OB_ERR_INVALID_ARG, "outcome length differs from the frame the design was packed from");
+        if (!d->g[0].src || !d->g[1].src) fail(OB_ERR_UNSUPPORTED, "this design carries no frame-row map (gathered design)");
+        g_alloc_pack = true;
+        DevBuf d_y(sizeof(double) * (size_t)std::max<int64_t>(n_frame, 1));
+        OB_CUDA(cudaMemcpyAsync(d_y.p, y_frame, sizeof(double) * (size_t)n_frame, cudaMemcpyHostToDevice, ctx->stream));
+        for (int g = 0; g < 2; ++g) update_outcome_launch(d->g[g], d->K, d->ldx, d_y.as<double>(), ctx->stream);
         OB_CUDA(cudaStreamSynchronize(ctx->stream));
     });
 }

@@ -82,6 +82,7 @@ struct GroupData {               // one group's packed design in HBM (the rows t
     double* X = nullptr;         // [n_pad][ldx]: cols 0..K-1 design (intercept first), col K outcome, rest 0
     double* w = nullptr;         // [n_pad] sample weights (0 on padding) or nullptr
     double* Xs = nullptr;        // weighted only: sqrt(w_i) * X[i][:] (ols.rs:68-78), the operand of the Gram contraction
+    uint32_t* src = nullptr;     // [n] frame row each packed row came from (ob_design_update_outcome)
     const double* gram_operand() const { return Xs ? Xs : X; }
 };
 
@@ -189,6 +190,10 @@ void pack_count_scan(const PackArgs& a, long long* d_block_counts, long long* d_
 // pass 3: staged transpose/scatter of the rows into the packed per-group designs
 void pack_scatter(const PackArgs& a, const long long* d_block_base, GroupData ga, GroupData gb, int* d_flags,
                   cudaStream_t st);
+// src[i] = first + i (designs built from dense per-group matrices: the "frame" is group A's rows, then group B's)
+void iota_launch(uint32_t* dst, int64_t n, uint32_t first, cudaStream_t st);
+// outcome refresh: X[r][K] = y[src[r]] (and Xs[r][K] = sqrt(w[r]) * y[src[r]]) for every packed row of the group
+void update_outcome_launch(const GroupData& g, int K, int ldx, const double* d_y_frame, cudaStream_t st);
 // Xs[i][:] = sqrt(w[i]) * X[i][:] for all V = K+1 columns (WLS as OLS on sqrt(w)-scaled data, ols.rs:68-78)
 void scale_rows_launch(const GroupData& g, int ldx, cudaStream_t st);
 // residuals of the point estimate: r = y - X beta (ols.rs:118-119) for one group

@@ -74,6 +74,7 @@ struct PackKernelParams {
     const double* y; const double* w; const uint8_t* group;
     const long long* block_base;   // [nblocks][2] exclusive scan
     double* XA; double* XB; double* wA; double* wB;
+    uint32_t* srcA; uint32_t* srcB;
     int* flags;
 };
 
@@ -145,6 +146,9 @@ __global__ void __launch_bounds__(PK_THREADS) pack_scatter_kernel(const PackKern
         for (int r = tid; r < cnt[0]; r += PK_THREADS) p.wA[baseA + r] = p.w[row0 + srcA[r]];
         for (int r = tid; r < cnt[1]; r += PK_THREADS) p.wB[baseB + r] = p.w[row0 + srcB[r]];
     }
+    // frame row of every packed row: lets a caller refresh the outcome column without re-packing
+    for (int r = tid; r < cnt[0]; r += PK_THREADS) p.srcA[baseA + r] = (uint32_t)(row0 + srcA[r]);
+    for (int r = tid; r < cnt[1]; r += PK_THREADS) p.srcB[baseB + r] = (uint32_t)(row0 + srcB[r]);
 }
 
 int pack_num_blocks(int64_t n) { return (int)((n + PK_ROWS - 1) / PK_ROWS); }
@@ -166,7 +170,7 @@ void pack_scatter(const PackArgs& a, const long long* d_block_base, GroupData ga
     p.n = a.n; p.n_cont = a.n_cont; p.n_cat = a.n_cat; p.K = a.K; p.ldx = a.ldx;
     p.cont = a.d_cont; p.cat = a.d_cat; p.cat_levels = a.d_cat_levels; p.dummy_start = a.d_dummy_start;
     p.y = a.d_y; p.w = a.d_w; p.group = a.d_group; p.block_base = d_block_base;
-    p.XA = ga.X; p.XB = gb.X; p.wA = ga.w; p.wB = gb.w; p.flags = d_flags;
+    p.XA = ga.X; p.XB = gb.X; p.wA = ga.w; p.wB = gb.w; p.srcA = ga.src; p.srcB = gb.src; p.flags = d_flags;
     const int V = a.K + 1;
     const size_t smem = sizeof(double) * (size_t)PK_ROWS * (V | 1);
     OB_CUDA(cudaFuncSetAttribute(pack_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -187,6 +191,36 @@ void scale_rows_launch(const GroupData& g, int ldx, cudaStream_t st) {
     if (!g.Xs) return;
     const long long total = g.n_pad * (long long)ldx;
     scale_rows_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 32), 256, 0, st>>>(g.X, g.w, g.Xs, total, ldx);
+    OB_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ dst, long long n, uint32_t first) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = first + (uint32_t)i;
+}
+
+void iota_launch(uint32_t* dst, int64_t n, uint32_t first, cudaStream_t st) {
+    if (n == 0) return;
+    iota_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, st>>>(dst, n, first);
+    OB_CUDA(cudaGetLastError());
+}
+
+// ---- outcome refresh (callers that re-run the decomposition on the same X with another y: JMP's two runs,
+//      jmp.rs:44-106; the engine's perturbed-wage sweeps, engine/src/analysis.rs:871-914) ----
+__global__ void __launch_bounds__(256) update_outcome_kernel(double* __restrict__ X, double* __restrict__ Xs,
+                                                             const double* __restrict__ w, const uint32_t* __restrict__ src,
+                                                             const double* __restrict__ y, long long n, int K, int ldx) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        const double v = y[src[r]];
+        X[r * ldx + K] = v;
+        if (Xs) Xs[r * ldx + K] = sqrt(w[r]) * v;
+    }
+}
+
+void update_outcome_launch(const GroupData& g, int K, int ldx, const double* d_y_frame, cudaStream_t st) {
+    if (g.n == 0) return;
+    update_outcome_kernel<<<(unsigned)std::min<long long>((g.n + 255) / 256, 148 * 16), 256, 0, st>>>(g.X, g.Xs, g.w, g.src, d_y_frame,
+                                                                                                     g.n, K, ldx);
     OB_CUDA(cudaGetLastError());
 }
 

@@ -329,3 +329,38 @@ def test_rif_prestep(ob, orc, ctx, tau):
     _, ga, _, _, gb, _ = des.download()
     assert relerr(ga, orc.rif(ya, tau)) <= RTOL and relerr(gb, orc.rif(yb, tau)) <= RTOL
     des.close()
+
+
+def test_outcome_refresh_equals_repack(ob, ctx):
+    """ob_design_update_outcome (callers re-running on the same X with another y: jmp.rs:44-106,
+    engine/src/analysis.rs:871-914): bit-identical to packing the frame again with the new outcome."""
+    from oaxaca_blinder_rs_b200 import synth
+    for weighted in (False, True):
+        d = synth.make_wage(40_003, 5, cat_levels=(3,), weights=weighted, seed=13)
+        norm = [ob.NormVar(m, i) for m, i in synth.norm_spec(d)]
+        y2 = d["outcome"] * 1.5 - np.sin(d["cont"][0])
+        des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+        first = ob.bootstrap(des, 60, ref_kind=2, norm=norm, seed=4, want_rep=True)
+        des.update_outcome(y2)
+        refreshed = ob.bootstrap(des, 60, ref_kind=2, norm=norm, seed=4, want_rep=True)
+        fresh_des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], y2, d["weights"], d["group"])
+        fresh = ob.bootstrap(fresh_des, 60, ref_kind=2, norm=norm, seed=4, want_rep=True)
+        for k in ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper", "residuals_b"):
+            np.testing.assert_array_equal(refreshed[k], fresh[k])
+        assert not np.array_equal(first["point_stats"], refreshed["point_stats"])
+        # back to the original outcome: identical to the first run
+        des.update_outcome(d["outcome"])
+        again = ob.bootstrap(des, 60, ref_kind=2, norm=norm, seed=4, want_rep=True)
+        np.testing.assert_array_equal(again["rep_stats"], first["rep_stats"])
+        with pytest.raises(ob.OaxacaError):
+            des.update_outcome(y2[:-1])
+        des.close(); fresh_des.close()
+    # dense designs: the frame is [y_a ; y_b]
+    d = synth.make_wage(5_000, 2, seed=2)
+    Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
+    des = ob.Design.from_dense(ctx, Xa, ya, wa, Xb, yb, wb, 2)
+    des.update_outcome(np.concatenate([2 * ya, 2 * yb]))
+    got = des.download()
+    np.testing.assert_array_equal(got[1], 2 * ya)
+    np.testing.assert_array_equal(got[4], 2 * yb)
+    des.close()
