@@ -75,6 +75,41 @@ typedef struct ob_frame_view {
 
 ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* frame, ob_design** out);
 
+/* ---- (0) ingest: cleaning and coding on the device --------------------------------------------
+ * What the reference does on the host between run()'s clone of the frame (builder.rs:788) and the group split:
+ * clean_dataframe (:760-784: drop every row with a null in any used column), create_dummies_manual (:380-418: levels =
+ * sorted unique values of the CLEANED frame, first level = base) and split_groups' coding (:61-102).  String columns
+ * arrive dictionary-encoded (Arrow DictionaryArray / polars Categorical physical codes / pandas Categorical): an int32
+ * code per row (< 0 = null) and a dictionary the HOST keeps, in any order.  Two calls, because only the host can
+ * compare strings:
+ *   ob_ingest_begin   uploads the columns, computes row validity and which dictionary entries occur among valid rows
+ *   (host)            sorts the present entries -> group map (0 = group A, 1 = reference_group, other = ignored) and,
+ *                     per categorical, dictionary code -> level code (0 = base); rows_kept < 1 / < 2 groups -> errors
+ *   ob_ingest_finish  applies the maps on the device and packs (== ob_design_pack of the cleaned, coded frame)
+ * No O(n) work is left on the host. */
+typedef struct ob_raw_f64 { const double* data; const uint8_t* valid; } ob_raw_f64;       /* valid NULL = no nulls; valid[i] == 0 = null */
+typedef struct ob_raw_dict { const int32_t* codes; int32_t dict_size; } ob_raw_dict;      /* codes[i] < 0 = null */
+typedef struct ob_raw_frame {
+    int64_t n;
+    int32_t n_cont; const ob_raw_f64* cont;
+    int32_t n_cat;  const ob_raw_dict* cat;
+    ob_raw_f64 outcome;
+    ob_raw_f64 weights;          /* data NULL = unweighted */
+    ob_raw_dict group;
+    int32_t nan_is_null;         /* 1: a NaN in a numeric column is a null too (numpy / pandas frames), tested on the device */
+} ob_raw_frame;
+typedef struct ob_ingest ob_ingest;
+ob_status ob_ingest_begin(ob_ctx* ctx, const ob_raw_frame* frame, ob_ingest** out);
+ob_status ob_ingest_rows_kept(const ob_ingest* ing, int64_t* rows_kept);
+/* present_out [dict_size]: 1 if the entry occurs in a kept row; column = categorical index, or -1 for the group column */
+ob_status ob_ingest_presence(const ob_ingest* ing, int32_t column, uint8_t* present_out);
+/* group_map [group dict_size]; cat_remap [n_cat][dict_size] (entries absent from the cleaned frame: any value < 0);
+ * cat_levels [n_cat] level counts incl. base.  May be called once per ingest object (codes are remapped in place);
+ * destroy the object afterwards. */
+ob_status ob_ingest_finish(ob_ctx* ctx, ob_ingest* ing, const int32_t* group_map, const int32_t* const* cat_remap,
+                           const int32_t* cat_levels, ob_design** out);
+void ob_ingest_destroy(ob_ingest* ing);
+
 /* Same, from the dense matrices get_data_matrices() returns (builder.rs:252-291): row-major
  * X_g [n_g x K] incl. the intercept column, y_g, optional w_g.  n_cont fixes the pooled
  * indicator position (builder.rs:560-564). */

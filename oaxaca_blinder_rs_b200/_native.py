@@ -24,13 +24,28 @@ SYMBOLS = ["ob_abi_version", "ob_device_count", "ob_ctx_create", "ob_ctx_destroy
            "ob_design_apply_rif", "ob_num_stats", "ob_bootstrap_run", "ob_reduce_stats", "ob_debug_counts",
            "ob_comm_unique_id", "ob_comm_init_nccl", "ob_local_group_create", "ob_local_group_destroy",
            "ob_comm_init_local", "ob_comm_destroy", "ob_row_shard_plan", "ob_design_set_row_shard",
-           "ob_design_pack_timings", "ob_design_allgather_rows", "ob_design_update_outcome"]
+           "ob_design_pack_timings", "ob_design_allgather_rows", "ob_design_update_outcome",
+           "ob_ingest_begin", "ob_ingest_rows_kept", "ob_ingest_presence", "ob_ingest_finish", "ob_ingest_destroy"]
 
 
 class FrameView(C.Structure):
     _fields_ = [("n", C.c_int64), ("n_cont", C.c_int32), ("cont", C.POINTER(_DP)), ("n_cat", C.c_int32),
                 ("cat_codes", C.POINTER(_IP)), ("cat_levels", _IP), ("outcome", _DP), ("weights", _DP),
                 ("group", C.POINTER(C.c_uint8))]
+
+
+class RawF64(C.Structure):
+    _fields_ = [("data", _DP), ("valid", C.POINTER(C.c_uint8))]
+
+
+class RawDict(C.Structure):
+    _fields_ = [("codes", _IP), ("dict_size", C.c_int32)]
+
+
+class RawFrame(C.Structure):
+    _fields_ = [("n", C.c_int64), ("n_cont", C.c_int32), ("cont", C.POINTER(RawF64)), ("n_cat", C.c_int32),
+                ("cat", C.POINTER(RawDict)), ("outcome", RawF64), ("weights", RawF64), ("group", RawDict),
+                ("nan_is_null", C.c_int32)]
 
 
 class BootOpts(C.Structure):
@@ -104,5 +119,11 @@ def lib() -> C.CDLL:
         L.ob_design_pack_timings.argtypes = [C.c_void_p, _DP, _DP]
         L.ob_design_allgather_rows.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.ob_design_update_outcome.argtypes = [C.c_void_p, C.c_void_p, _DP, C.c_int64]
+        L.ob_ingest_begin.argtypes = [C.c_void_p, C.POINTER(RawFrame), C.POINTER(C.c_void_p)]
+        L.ob_ingest_rows_kept.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.ob_ingest_presence.argtypes = [C.c_void_p, C.c_int32, _U8P]
+        L.ob_ingest_finish.argtypes = [C.c_void_p, C.c_void_p, _IP, C.POINTER(_IP), _IP, C.POINTER(C.c_void_p)]
+        L.ob_ingest_destroy.argtypes = [C.c_void_p]
+        L.ob_ingest_destroy.restype = None
         _lib = L
     return _lib

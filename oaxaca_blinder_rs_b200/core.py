@@ -221,6 +221,85 @@ class Design:
             pass
 
 
+def ingest(ctx: Context, cont, cat, outcome, weights, group, reference_group: str):
+    """Device-side cleaning + coding + pack of a raw frame (ob_ingest_begin / ob_ingest_finish; builder.rs:760-806,
+    :61-102).  Numeric columns: float64 arrays (NaN = null) or (array, valid_bytes) pairs (NaN or valid == 0 = null).  String columns come
+    dictionary-encoded as (codes int32 with < 0 = null, dictionary list of str) -- e.g. pandas
+    `Categorical.codes / .categories`, pyarrow `DictionaryArray.indices / .dictionary`.
+    Returns (Design, meta) with meta = dict(rows_kept, group_a, levels per categorical (sorted; [0] is the base))."""
+    U8P = C.POINTER(C.c_uint8)
+    keep = []          # keep numpy temporaries alive across the calls
+
+    def f64(col):
+        if isinstance(col, tuple):
+            data, valid = col
+            data = np.ascontiguousarray(data, dtype=np.float64)
+            valid = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+        else:
+            data = np.ascontiguousarray(col, dtype=np.float64)     # NaN = null, detected on the device (nan_is_null)
+            valid = None
+        keep.extend([data, valid])
+        r = N.RawF64()
+        r.data = _dp(data)
+        r.valid = None if valid is None else valid.ctypes.data_as(U8P)
+        return r, data.shape[0]
+
+    def dct(col):
+        codes, dictionary = col
+        codes = np.ascontiguousarray(codes, dtype=np.int32)
+        keep.append(codes)
+        r = N.RawDict()
+        r.codes, r.dict_size = _ip(codes), len(dictionary)
+        return r, [str(s) for s in dictionary]
+
+    fr = N.RawFrame()
+    fr.nan_is_null = 1
+    conts = [f64(c)[0] for c in cont]
+    cats, dicts = zip(*[dct(c) for c in cat]) if cat else ((), ())
+    fr.outcome, n = f64(outcome)
+    fr.n, fr.n_cont, fr.n_cat = n, len(conts), len(cats)
+    cont_arr = (N.RawF64 * max(len(conts), 1))(*conts)
+    cat_arr = (N.RawDict * max(len(cats), 1))(*cats)
+    fr.cont, fr.cat = cont_arr, cat_arr
+    if weights is not None:
+        fr.weights = f64(weights)[0]
+    fr.group, gdict = dct(group)
+    h = C.c_void_p()
+    ctx.check(N.lib().ob_ingest_begin(ctx._h, C.byref(fr), C.byref(h)))
+    try:
+        kept = C.c_int64()
+        N.lib().ob_ingest_rows_kept(h, C.byref(kept))
+
+        def present(col, size):
+            out = np.zeros(max(size, 1), dtype=np.uint8)
+            N.lib().ob_ingest_presence(h, col, out.ctypes.data_as(U8P))
+            return out[:size].astype(bool)
+        # split_groups (builder.rs:61-102): sorted unique values of the cleaned frame; A = first one that is not the reference
+        gp = present(-1, len(gdict))
+        groups = sorted({gdict[i] for i in np.flatnonzero(gp)})
+        if len(groups) < 2:
+            raise OaxacaError(3, "Invalid group variable: Not enough groups for comparison")
+        group_a = groups[0] if groups[0] != reference_group else groups[1]
+        gmap = np.array([0 if s == group_a else (1 if s == reference_group else 2) for s in gdict] + [2], dtype=np.int32)
+        # create_dummies_manual (builder.rs:380-418): levels sorted ascending, first = base
+        levels, remaps = [], []
+        for q, dq in enumerate(dicts):
+            pq = present(q, len(dq))
+            lv = sorted({dq[i] for i in np.flatnonzero(pq)})
+            if not lv:
+                raise OaxacaError(3, "Invalid group variable: Could not get reference category")
+            code = {s: i for i, s in enumerate(lv)}
+            remaps.append(np.array([code[s] if pq[i] else -1 for i, s in enumerate(dq)] + [-1], dtype=np.int32))
+            levels.append(lv)
+        remap_arr = (N._IP * max(len(remaps), 1))(*[_ip(r) for r in remaps])
+        lvl = np.array([len(lv) for lv in levels] + [0], dtype=np.int32)
+        dh = C.c_void_p()
+        ctx.check(N.lib().ob_ingest_finish(ctx._h, h, _ip(gmap), remap_arr, _ip(lvl), C.byref(dh)))
+    finally:
+        N.lib().ob_ingest_destroy(h)
+    return Design(ctx, dh), dict(rows_kept=int(kept.value), group_a=group_a, levels=levels)
+
+
 def num_stats(K: int, norm: Sequence[NormVar]) -> int:
     return 5 + 2 * (K + sum(1 for v in norm if v.has_base))
 

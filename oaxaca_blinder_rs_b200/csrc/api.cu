@@ -401,91 +401,258 @@ ob_status ob_design_from_dense(ob_ctx* ctx, int32_t K, int32_t n_cont,
     });
 }
 
+}  // extern "C"
+
+namespace {
+
+// the cleaned, coded frame staged in HBM (input of the pack kernels)
+struct StagedFrame {
+    int64_t n = 0; int n_cont = 0, n_cat = 0;
+    std::vector<DevBuf> cols, cats;     // [n] f64 / int32 level codes
+    DevBuf y, w, grp;                   // outcome, weights (optional), group byte
+    bool weighted = false;
+    double ms_h2d = 0.0;
+};
+
+// pack kernels over a staged frame -> resident design (prepare_data + split_groups, once)
+std::unique_ptr<ob_design, void (*)(ob_design*)> pack_staged(ob_ctx* ctx, StagedFrame& sf, const int32_t* cat_levels) {
+    cudaStream_t st = ctx->stream;
+    const int64_t n = sf.n;
+    int K = 1 + sf.n_cont;
+    std::vector<int32_t> dummy_start(std::max(sf.n_cat, 1), 0);
+    for (int q = 0; q < sf.n_cat; ++q) {
+        if (cat_levels[q] < 1) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: Could not get reference category");  // builder.rs:392-399
+        dummy_start[q] = K;
+        K += cat_levels[q] - 1;
+    }
+    if (K + 1 > 91) fail(OB_ERR_UNSUPPORTED, "design wider than 90 columns is not supported by the solve kernel");
+    if (n > 0xFFFFFFFFll) fail(OB_ERR_UNSUPPORTED, "frames beyond 2^32 rows (IdxSize is u32 in the reference too)");
+    g_alloc_pack = true;
+    std::vector<const double*> h_cont(std::max(sf.n_cont, 1), nullptr);
+    std::vector<const int32_t*> h_cat(std::max(sf.n_cat, 1), nullptr);
+    for (int c = 0; c < sf.n_cont; ++c) h_cont[c] = sf.cols[c].as<double>();
+    for (int q = 0; q < sf.n_cat; ++q) h_cat[q] = sf.cats[q].as<int32_t>();
+    DevBuf d_cont_ptrs(sizeof(void*) * h_cont.size()), d_cat_ptrs(sizeof(void*) * h_cat.size());
+    DevBuf d_levels(sizeof(int32_t) * std::max(sf.n_cat, 1)), d_dstart(sizeof(int32_t) * dummy_start.size());
+    OB_CUDA(cudaMemcpyAsync(d_cont_ptrs.p, h_cont.data(), sizeof(void*) * h_cont.size(), cudaMemcpyHostToDevice, st));
+    OB_CUDA(cudaMemcpyAsync(d_cat_ptrs.p, h_cat.data(), sizeof(void*) * h_cat.size(), cudaMemcpyHostToDevice, st));
+    if (sf.n_cat) OB_CUDA(cudaMemcpyAsync(d_levels.p, cat_levels, sizeof(int32_t) * sf.n_cat, cudaMemcpyHostToDevice, st));
+    OB_CUDA(cudaMemcpyAsync(d_dstart.p, dummy_start.data(), sizeof(int32_t) * dummy_start.size(), cudaMemcpyHostToDevice, st));
+
+    PackArgs pa;
+    pa.n = n; pa.n_cont = sf.n_cont; pa.n_cat = sf.n_cat;
+    pa.d_cont = d_cont_ptrs.as<const double*>(); pa.d_cat = d_cat_ptrs.as<const int32_t*>();
+    pa.d_cat_levels = d_levels.as<int32_t>(); pa.d_dummy_start = d_dstart.as<int32_t>();
+    pa.d_y = sf.y.as<double>(); pa.d_w = sf.weighted ? sf.w.as<double>() : nullptr; pa.d_group = sf.grp.as<uint8_t>();
+    pa.K = K; pa.ldx = design_ldx(K + 1);
+
+    const int nblk = pack_num_blocks(n);
+    DevBuf d_bc(sizeof(long long) * 2 * (size_t)std::max(nblk, 1)), d_tot(sizeof(long long) * 2), d_flags(sizeof(int) * 4);
+    OB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * 4, st));
+    double ms_pack = 0.0;
+    Timer t_pack(st, &ms_pack);
+    pack_count_scan(pa, d_bc.as<long long>(), d_tot.as<long long>(), d_flags.as<int>(), st);
+    long long tot[2]; int flags[4];
+    OB_CUDA(cudaMemcpyAsync(tot, d_tot.p, sizeof tot, cudaMemcpyDeviceToHost, st));
+    OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+    OB_CUDA(cudaStreamSynchronize(st));
+    if (flags[0]) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: Weights cannot be negative");
+
+    std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
+    d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = sf.n_cont; d->V = K + 1; d->ldx = pa.ldx;
+    d->weighted = sf.weighted;
+    d->n_frame = n;
+    alloc_group(ctx, d->g[0], tot[0], d->ldx, d->weighted);
+    alloc_group(ctx, d->g[1], tot[1], d->ldx, d->weighted);
+    pack_scatter(pa, d_bc.as<long long>(), d->g[0], d->g[1], d_flags.as<int>(), st);
+    for (int g = 0; g < 2; ++g) scale_rows_launch(d->g[g], d->ldx, st);
+    t_pack.stop();
+    OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+    OB_CUDA(cudaStreamSynchronize(st));
+    t_pack.collect();
+    d->ms_h2d = sf.ms_h2d; d->ms_pack = ms_pack;
+    if (flags[1]) fail(OB_ERR_INVALID_ARG, "categorical code outside [0, levels)");
+    return d;
+}
+
+template <typename T>
+void stage_column(DevBuf& buf, const T* host, int64_t n, cudaStream_t st) {
+    buf.alloc(sizeof(T) * (size_t)std::max<int64_t>(n, 1));
+    if (n) OB_CUDA(cudaMemcpyAsync(buf.p, host, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, st));
+}
+
+}  // namespace
+
+// raw frame staged on the device between ob_ingest_begin and ob_ingest_finish
+struct ob_ingest {
+    ob_ctx* ctx = nullptr;
+    StagedFrame sf;
+    std::vector<DevBuf> valid;            // validity bytes of numeric columns that carry nulls
+    DevBuf group_codes, row_valid;
+    std::vector<DevBuf> present;          // per dictionary column (categoricals.., group)
+    std::vector<int32_t> dict_size;
+    std::vector<std::vector<uint8_t>> h_present;
+    int64_t kept = 0;
+};
+
+extern "C" {
+
 ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
     if (!ctx || !f || !out) return OB_ERR_INVALID_ARG;
     *out = nullptr;
     return guarded(ctx, [&] {
         if (f->n < 0 || f->n_cont < 0 || f->n_cat < 0) fail(OB_ERR_INVALID_ARG, "bad frame shape");
         if (f->n && (!f->outcome || !f->group)) fail(OB_ERR_INVALID_ARG, "null frame column");
-        int K = 1 + f->n_cont;
-        std::vector<int32_t> dummy_start(std::max(f->n_cat, 1), 0);
-        for (int q = 0; q < f->n_cat; ++q) {
-            if (f->cat_levels[q] < 1) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: Could not get reference category");  // builder.rs:392-399
-            dummy_start[q] = K;
-            K += f->cat_levels[q] - 1;
-        }
-        if (K + 1 > 91) fail(OB_ERR_UNSUPPORTED, "design wider than 90 columns is not supported by the solve kernel");
         cudaStream_t st = ctx->stream;
-        const int64_t n = f->n;
         g_alloc_pack = true;
-        // ---- stage the frame columns in HBM ----
-        double ms_h2d = 0.0, ms_pack = 0.0;
-        Timer t_h2d(st, &ms_h2d);
-        std::vector<DevBuf> cols(f->n_cont), cats(f->n_cat);
-        std::vector<const double*> h_cont(std::max(f->n_cont, 1), nullptr);
-        std::vector<const int32_t*> h_cat(std::max(f->n_cat, 1), nullptr);
+        StagedFrame sf;
+        sf.n = f->n; sf.n_cont = f->n_cont; sf.n_cat = f->n_cat; sf.weighted = f->weights != nullptr;
+        sf.cols.resize(f->n_cont); sf.cats.resize(f->n_cat);
+        Timer t_h2d(st, &sf.ms_h2d);
         for (int c = 0; c < f->n_cont; ++c) {
             if (!f->cont[c]) fail(OB_ERR_INVALID_ARG, "null predictor column");
-            cols[c].alloc(sizeof(double) * (size_t)std::max<int64_t>(n, 1));
-            OB_CUDA(cudaMemcpyAsync(cols[c].p, f->cont[c], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
-            h_cont[c] = cols[c].as<double>();
+            stage_column(sf.cols[c], f->cont[c], f->n, st);
         }
         for (int q = 0; q < f->n_cat; ++q) {
             if (!f->cat_codes[q]) fail(OB_ERR_INVALID_ARG, "null categorical column");
-            cats[q].alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(n, 1));
-            OB_CUDA(cudaMemcpyAsync(cats[q].p, f->cat_codes[q], sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
-            h_cat[q] = cats[q].as<int32_t>();
+            stage_column(sf.cats[q], f->cat_codes[q], f->n, st);
         }
-        DevBuf d_y(sizeof(double) * (size_t)std::max<int64_t>(n, 1)), d_grp((size_t)std::max<int64_t>(n, 1)), d_w;
-        OB_CUDA(cudaMemcpyAsync(d_y.p, f->outcome, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
-        OB_CUDA(cudaMemcpyAsync(d_grp.p, f->group, (size_t)n, cudaMemcpyHostToDevice, st));
-        if (f->weights) {
-            d_w.alloc(sizeof(double) * (size_t)std::max<int64_t>(n, 1));
-            OB_CUDA(cudaMemcpyAsync(d_w.p, f->weights, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
-        }
-        DevBuf d_cont_ptrs(sizeof(void*) * h_cont.size()), d_cat_ptrs(sizeof(void*) * h_cat.size());
-        DevBuf d_levels(sizeof(int32_t) * std::max(f->n_cat, 1)), d_dstart(sizeof(int32_t) * dummy_start.size());
-        OB_CUDA(cudaMemcpyAsync(d_cont_ptrs.p, h_cont.data(), sizeof(void*) * h_cont.size(), cudaMemcpyHostToDevice, st));
-        OB_CUDA(cudaMemcpyAsync(d_cat_ptrs.p, h_cat.data(), sizeof(void*) * h_cat.size(), cudaMemcpyHostToDevice, st));
-        if (f->n_cat) OB_CUDA(cudaMemcpyAsync(d_levels.p, f->cat_levels, sizeof(int32_t) * f->n_cat, cudaMemcpyHostToDevice, st));
-        OB_CUDA(cudaMemcpyAsync(d_dstart.p, dummy_start.data(), sizeof(int32_t) * dummy_start.size(), cudaMemcpyHostToDevice, st));
-
-        PackArgs pa;
-        pa.n = n; pa.n_cont = f->n_cont; pa.n_cat = f->n_cat;
-        pa.d_cont = d_cont_ptrs.as<const double*>(); pa.d_cat = d_cat_ptrs.as<const int32_t*>();
-        pa.d_cat_levels = d_levels.as<int32_t>(); pa.d_dummy_start = d_dstart.as<int32_t>();
-        pa.d_y = d_y.as<double>(); pa.d_w = d_w.as<double>(); pa.d_group = d_grp.as<uint8_t>();
-        pa.K = K; pa.ldx = design_ldx(K + 1);
-
-        const int nblk = pack_num_blocks(n);
-        DevBuf d_bc(sizeof(long long) * 2 * (size_t)std::max(nblk, 1)), d_tot(sizeof(long long) * 2), d_flags(sizeof(int) * 4);
-        OB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * 4, st));
+        stage_column(sf.y, f->outcome, f->n, st);
+        stage_column(sf.grp, f->group, f->n, st);
+        if (f->weights) stage_column(sf.w, f->weights, f->n, st);
         t_h2d.stop();
-        Timer t_pack(st, &ms_pack);
-        pack_count_scan(pa, d_bc.as<long long>(), d_tot.as<long long>(), d_flags.as<int>(), st);
-        long long tot[2]; int flags[4];
-        OB_CUDA(cudaMemcpyAsync(tot, d_tot.p, sizeof tot, cudaMemcpyDeviceToHost, st));
-        OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
         OB_CUDA(cudaStreamSynchronize(st));
-        if (flags[0]) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: Weights cannot be negative");
-
-        std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
-        d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = f->n_cont; d->V = K + 1; d->ldx = pa.ldx;
-        d->weighted = f->weights != nullptr;
-        d->n_frame = n;
-        if (n > 0xFFFFFFFFll) fail(OB_ERR_UNSUPPORTED, "frames beyond 2^32 rows (IdxSize is u32 in the reference too)");
-        alloc_group(ctx, d->g[0], tot[0], d->ldx, d->weighted);
-        alloc_group(ctx, d->g[1], tot[1], d->ldx, d->weighted);
-        pack_scatter(pa, d_bc.as<long long>(), d->g[0], d->g[1], d_flags.as<int>(), st);
-        for (int g = 0; g < 2; ++g) scale_rows_launch(d->g[g], d->ldx, st);
-        t_pack.stop();
-        OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
-        OB_CUDA(cudaStreamSynchronize(st));
-        t_h2d.collect(); t_pack.collect();
-        d->ms_h2d = ms_h2d; d->ms_pack = ms_pack;
-        if (flags[1]) fail(OB_ERR_INVALID_ARG, "categorical code outside [0, levels)");
-        *out = d.release();
+        t_h2d.collect();
+        *out = pack_staged(ctx, sf, f->cat_levels).release();
     });
+}
+
+// ---- ingest: null filter + dictionary coding on the device ----
+ob_status ob_ingest_begin(ob_ctx* ctx, const ob_raw_frame* f, ob_ingest** out) {
+    if (!ctx || !f || !out) return OB_ERR_INVALID_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        if (f->n < 0 || f->n_cont < 0 || f->n_cat < 0) fail(OB_ERR_INVALID_ARG, "bad frame shape");
+        if (f->n_cont + 2 > INGEST_MAX_COLS || f->n_cat + 1 > INGEST_MAX_COLS) fail(OB_ERR_UNSUPPORTED, "too many columns");
+        if (f->n && (!f->outcome.data || !f->group.codes)) fail(OB_ERR_INVALID_ARG, "null frame column");
+        if (f->n > 0xFFFFFFFFll) fail(OB_ERR_UNSUPPORTED, "frames beyond 2^32 rows");
+        cudaStream_t st = ctx->stream;
+        g_alloc_pack = true;
+        std::unique_ptr<ob_ingest> ing(new ob_ingest);
+        ing->ctx = ctx;
+        StagedFrame& sf = ing->sf;
+        const int64_t n = f->n;
+        sf.n = n; sf.n_cont = f->n_cont; sf.n_cat = f->n_cat; sf.weighted = f->weights.data != nullptr;
+        sf.cols.resize(f->n_cont); sf.cats.resize(f->n_cat);
+        Timer t_h2d(st, &sf.ms_h2d);
+        IngestScanArgs a{};
+        a.n = n;
+        auto add_f64 = [&](const ob_raw_f64& c, DevBuf& dst) {
+            if (n && !c.data) fail(OB_ERR_INVALID_ARG, "null numeric column");
+            stage_column(dst, c.data, n, st);
+            if (f->nan_is_null) a.nan_cols[a.n_nan++] = dst.as<double>();
+            if (c.valid) {
+                ing->valid.emplace_back();
+                stage_column(ing->valid.back(), c.valid, n, st);
+                a.valid[a.n_valid++] = ing->valid.back().as<uint8_t>();
+            }
+        };
+        ing->valid.reserve((size_t)f->n_cont + 2);
+        for (int c = 0; c < f->n_cont; ++c) add_f64(f->cont[c], sf.cols[c]);
+        add_f64(f->outcome, sf.y);
+        if (sf.weighted) add_f64(f->weights, sf.w);
+        ing->present.resize((size_t)f->n_cat + 1);
+        auto add_dict = [&](const ob_raw_dict& c, DevBuf& dst) {
+            if (n && !c.codes) fail(OB_ERR_INVALID_ARG, "null dictionary column");
+            if (c.dict_size < 0) fail(OB_ERR_INVALID_ARG, "negative dictionary size");
+            stage_column(dst, c.codes, n, st);
+            DevBuf& pr = ing->present[(size_t)a.n_dict];
+            pr.alloc((size_t)std::max(c.dict_size, 1));
+            OB_CUDA(cudaMemsetAsync(pr.p, 0, pr.bytes, st));
+            a.codes[a.n_dict] = dst.as<int32_t>(); a.dict_size[a.n_dict] = c.dict_size; a.present[a.n_dict] = pr.as<uint8_t>();
+            ing->dict_size.push_back(c.dict_size);
+            ++a.n_dict;
+        };
+        for (int q = 0; q < f->n_cat; ++q) add_dict(f->cat[q], sf.cats[q]);
+        add_dict(f->group, ing->group_codes);
+        t_h2d.stop();
+        ing->row_valid.alloc((size_t)std::max<int64_t>(n, 1));
+        sf.grp.alloc((size_t)std::max<int64_t>(n, 1));
+        DevBuf d_kept(sizeof(long long)), d_flags(sizeof(int) * 4);
+        OB_CUDA(cudaMemsetAsync(d_kept.p, 0, sizeof(long long), st));
+        OB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * 4, st));
+        a.row_valid = ing->row_valid.as<uint8_t>(); a.kept = d_kept.as<long long>(); a.flags = d_flags.as<int>();
+        ingest_scan_launch(a, st);
+        long long kept = 0; int flags[4];
+        OB_CUDA(cudaMemcpyAsync(&kept, d_kept.p, sizeof kept, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+        ing->h_present.resize(ing->present.size());
+        for (size_t c = 0; c < ing->present.size(); ++c) {
+            ing->h_present[c].assign((size_t)std::max(ing->dict_size[c], 1), 0);
+            OB_CUDA(cudaMemcpyAsync(ing->h_present[c].data(), ing->present[c].p, ing->h_present[c].size(), cudaMemcpyDeviceToHost, st));
+        }
+        OB_CUDA(cudaStreamSynchronize(st));
+        t_h2d.collect();
+        if (flags[0] & 1) fail(OB_ERR_POLARS, "Polars error: dictionary code outside the dictionary");
+        ing->kept = kept;
+        *out = ing.release();
+    });
+}
+
+ob_status ob_ingest_rows_kept(const ob_ingest* ing, int64_t* rows_kept) {
+    if (!ing || !rows_kept) return OB_ERR_INVALID_ARG;
+    *rows_kept = ing->kept;
+    return OB_OK;
+}
+
+ob_status ob_ingest_presence(const ob_ingest* ing, int32_t column, uint8_t* present_out) {
+    if (!ing || !present_out) return OB_ERR_INVALID_ARG;
+    const int n_cat = ing->sf.n_cat;
+    const int c = column < 0 ? n_cat : column;            // -1 = the group column
+    if (c < 0 || c > n_cat) return OB_ERR_INVALID_ARG;
+    memcpy(present_out, ing->h_present[(size_t)c].data(), (size_t)ing->dict_size[(size_t)c]);
+    return OB_OK;
+}
+
+ob_status ob_ingest_finish(ob_ctx* ctx, ob_ingest* ing, const int32_t* group_map, const int32_t* const* cat_remap,
+                           const int32_t* cat_levels, ob_design** out) {
+    if (!ctx || !ing || !group_map || !out || ing->ctx != ctx) return OB_ERR_INVALID_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        cudaStream_t st = ctx->stream;
+        g_alloc_pack = true;
+        StagedFrame& sf = ing->sf;
+        if (sf.n_cat && (!cat_remap || !cat_levels)) fail(OB_ERR_INVALID_ARG, "categorical remap tables missing");
+        IngestApplyArgs a{};
+        a.n = sf.n; a.n_cat = sf.n_cat;
+        std::vector<int32_t> remap;
+        for (int q = 0; q < sf.n_cat; ++q) {
+            a.remap_off[q] = (int)remap.size();
+            remap.insert(remap.end(), cat_remap[q], cat_remap[q] + ing->dict_size[(size_t)q]);
+            a.cat_codes[q] = sf.cats[q].as<int32_t>();
+        }
+        const int gsize = ing->dict_size[(size_t)sf.n_cat];
+        DevBuf d_remap(sizeof(int32_t) * std::max<size_t>(remap.size(), 1)), d_gmap(sizeof(int32_t) * std::max(gsize, 1)), d_flags(sizeof(int) * 4);
+        if (!remap.empty()) OB_CUDA(cudaMemcpyAsync(d_remap.p, remap.data(), sizeof(int32_t) * remap.size(), cudaMemcpyHostToDevice, st));
+        if (gsize) OB_CUDA(cudaMemcpyAsync(d_gmap.p, group_map, sizeof(int32_t) * gsize, cudaMemcpyHostToDevice, st));
+        OB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * 4, st));
+        a.row_valid = ing->row_valid.as<uint8_t>(); a.group_codes = ing->group_codes.as<int32_t>();
+        a.group_map = d_gmap.as<int32_t>(); a.remap = d_remap.as<int32_t>(); a.group_out = sf.grp.as<uint8_t>();
+        a.flags = d_flags.as<int>();
+        ingest_apply_launch(a, st);
+        int flags[4];
+        OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        if (flags[0] & 2) fail(OB_ERR_INVALID_ARG, "a categorical value present in the cleaned frame has no level code");
+        *out = pack_staged(ctx, sf, cat_levels).release();
+    });
+}
+
+void ob_ingest_destroy(ob_ingest* ing) {
+    if (!ing) return;
+    cudaSetDevice(ing->ctx->device);
+    g_alloc_ctx = ing->ctx;            // DevBuf destructors free on the owning context's stream
+    delete ing;
 }
 
 ob_status ob_design_download(ob_ctx* ctx, const ob_design* d, double* Xa, double* ya, double* wa,

@@ -1,6 +1,8 @@
 // csrc/host/builder.cc -- see builder.h.  Citations: file:line under oaxaca_blinder/src/ of the reference.
 #include "builder.h"
 
+#include <unordered_map>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -166,6 +168,23 @@ static void require_str(const Column* c) {
                         "invalid series dtype: expected `String`, got `f64` for series with name `" + c->name + "`"));
 }
 
+// .normalize(): membership by name prefix "{var}_" over ALL predictor names (normalization.rs:14-20)
+void OaxacaBuilder::fill_norm_spec(Prepared& p) const {
+    p.norm_off.push_back(0);
+    for (const auto& var : normalization_vars_) {
+        const std::string prefix = var + "_";
+        int cnt = 0;
+        for (size_t i = 0; i < p.names.size(); ++i)
+            if (p.names[i].rfind(prefix, 0) == 0) { p.norm_idx.push_back((int32_t)i); ++cnt; }
+        p.norm_off.push_back((int32_t)p.norm_idx.size());
+        auto cc = p.category_counts.find(var);
+        p.norm_m.push_back(cc != p.category_counts.end() ? (int32_t)cc->second : cnt + 1);   // normalization.rs:31-34
+        auto bc = p.base_categories.find(var);
+        p.norm_has_base.push_back(bc != p.base_categories.end() ? 1 : 0);                     // builder.rs:636-640
+        if (bc != p.base_categories.end()) p.base_names.push_back(bc->second);
+    }
+}
+
 OaxacaBuilder::Prepared OaxacaBuilder::prepare() const {
     Prepared p;
     // clean_dataframe (builder.rs:760-784): existence check in this order, then drop rows with a null in any used column
@@ -248,20 +267,7 @@ OaxacaBuilder::Prepared OaxacaBuilder::prepare() const {
         p.group[r] = g == a_name ? 0 : (g == reference_group_ ? 1 : 2);   // rows of any third group are ignored (:85-94)
     }
 
-    // .normalize(): membership by name prefix "{var}_" over ALL predictor names (normalization.rs:14-20)
-    p.norm_off.push_back(0);
-    for (const auto& var : normalization_vars_) {
-        const std::string prefix = var + "_";
-        int cnt = 0;
-        for (size_t i = 0; i < p.names.size(); ++i)
-            if (p.names[i].rfind(prefix, 0) == 0) { p.norm_idx.push_back((int32_t)i); ++cnt; }
-        p.norm_off.push_back((int32_t)p.norm_idx.size());
-        auto cc = p.category_counts.find(var);
-        p.norm_m.push_back(cc != p.category_counts.end() ? (int32_t)cc->second : cnt + 1);   // normalization.rs:31-34
-        auto bc = p.base_categories.find(var);
-        p.norm_has_base.push_back(bc != p.base_categories.end() ? 1 : 0);                     // builder.rs:636-640
-        if (bc != p.base_categories.end()) p.base_names.push_back(bc->second);
-    }
+    fill_norm_spec(p);
     return p;
 }
 
@@ -278,6 +284,125 @@ void check(ob_ctx* ctx, ob_status st) {
 }
 }  // namespace
 
+
+// The production path of run() / decompose_quantile() / get_data_matrices(): the same cleaning and coding as
+// prepare(), but with the O(n) work on the device (ob_ingest_begin / ob_ingest_finish).  The host only
+// dictionary-encodes the string columns (what a polars Categorical / Arrow dictionary column already is) and sorts
+// the handful of values that occur.  Fills the metadata of `p` (names, levels, normalize spec, n); returns the design.
+ob_design* OaxacaBuilder::ingest_on_device(ob_ctx* ctx, Prepared& p, bool with_weights) const {
+    std::vector<std::string> cols = {outcome_, group_};
+    cols.insert(cols.end(), predictors_.begin(), predictors_.end());
+    cols.insert(cols.end(), categorical_.begin(), categorical_.end());
+    if (has_weights_) cols.push_back(weights_col_);
+    if (has_selection_) cols.push_back(selection_outcome_);
+    cols.insert(cols.end(), selection_predictors_.begin(), selection_predictors_.end());
+    for (const auto& c : cols)
+        if (!dataframe_.find(c)) throw OaxacaError(OB_ERR_COLUMN_NOT_FOUND, OaxacaError::display(OB_ERR_COLUMN_NOT_FOUND, c));
+    const int64_t n = (int64_t)dataframe_.height();
+
+    struct Dict { std::vector<int32_t> codes; std::vector<std::string> values; };
+    auto encode = [&](const Column* c) {                       // first-seen order, null -> -1
+        Dict d; d.codes.resize((size_t)n);
+        std::unordered_map<std::string, int32_t> idx;
+        for (int64_t i = 0; i < n; ++i) {
+            if (!c->is_valid((size_t)i)) { d.codes[(size_t)i] = -1; continue; }
+            auto it = idx.find(c->str[(size_t)i]);
+            if (it == idx.end()) { it = idx.emplace(c->str[(size_t)i], (int32_t)d.values.size()).first; d.values.push_back(c->str[(size_t)i]); }
+            d.codes[(size_t)i] = it->second;
+        }
+        return d;
+    };
+    auto raw_f64 = [&](const Column* c) {
+        ob_raw_f64 r{};
+        r.data = c->f64.data();
+        r.valid = c->valid.empty() ? nullptr : c->valid.data();
+        return r;
+    };
+    std::vector<Dict> cat_dicts;
+    for (const auto& cat : categorical_) { const Column* c = dataframe_.find(cat); require_str(c); cat_dicts.push_back(encode(c)); }
+    const Column* yc = dataframe_.find(outcome_);
+    require_f64(yc);
+    std::vector<ob_raw_f64> cont;
+    for (const auto& pr : predictors_) { const Column* c = dataframe_.find(pr); require_f64(c); cont.push_back(raw_f64(c)); }
+    ob_raw_frame fr{};
+    fr.n = n;
+    fr.outcome = raw_f64(yc);
+    // columns that only take part in the null filter (clean_dataframe covers every configured column, builder.rs:760-784):
+    // their validity is folded into the outcome's
+    std::vector<const Column*> filter_only;
+    if (has_weights_) {
+        const Column* c = dataframe_.find(weights_col_);
+        require_f64(c);
+        if (with_weights) fr.weights = raw_f64(c); else filter_only.push_back(c);
+    }
+    if (has_selection_) filter_only.push_back(dataframe_.find(selection_outcome_));
+    for (const auto& sp : selection_predictors_) filter_only.push_back(dataframe_.find(sp));
+    std::vector<uint8_t> merged_valid;
+    for (const Column* c : filter_only) {
+        if (c->valid.empty()) continue;
+        if (merged_valid.empty()) merged_valid = yc->valid.empty() ? std::vector<uint8_t>((size_t)n, 1) : yc->valid;
+        for (int64_t i = 0; i < n; ++i) merged_valid[(size_t)i] &= c->valid[(size_t)i];
+    }
+    if (!merged_valid.empty()) fr.outcome.valid = merged_valid.data();
+    const Column* gc = dataframe_.find(group_);
+    require_str(gc);
+    Dict gd = encode(gc);
+    std::vector<ob_raw_dict> cats;
+    for (auto& d : cat_dicts) cats.push_back(ob_raw_dict{d.codes.data(), (int32_t)d.values.size()});
+    fr.n_cont = (int32_t)cont.size(); fr.cont = cont.data();
+    fr.n_cat = (int32_t)cats.size(); fr.cat = cats.data();
+    fr.group = ob_raw_dict{gd.codes.data(), (int32_t)gd.values.size()};
+
+    ob_ingest* ing = nullptr;
+    check(ctx, ob_ingest_begin(ctx, &fr, &ing));
+    struct IngGuard { ob_ingest* i; ~IngGuard() { ob_ingest_destroy(i); } } guard{ing};
+    int64_t kept = 0;
+    ob_ingest_rows_kept(ing, &kept);
+    p.n = (size_t)kept;
+
+    // create_dummies_manual (builder.rs:380-418) on the cleaned frame: levels sorted ascending, first = base
+    p.names.push_back("__ob_intercept__");
+    for (const auto& pr : predictors_) p.names.push_back(pr);
+    std::vector<std::vector<int32_t>> remaps;
+    for (size_t q = 0; q < categorical_.size(); ++q) {
+        const std::string& cat = categorical_[q];
+        std::vector<uint8_t> present(std::max<size_t>(cat_dicts[q].values.size(), 1), 0);
+        ob_ingest_presence(ing, (int32_t)q, present.data());
+        std::vector<std::string> levels;
+        for (size_t i = 0; i < cat_dicts[q].values.size(); ++i) if (present[i]) levels.push_back(cat_dicts[q].values[i]);
+        std::sort(levels.begin(), levels.end());
+        if (levels.empty())
+            throw OaxacaError(OB_ERR_INVALID_GROUP, OaxacaError::display(OB_ERR_INVALID_GROUP, "Could not get reference category for " + cat));
+        std::vector<int32_t> remap(std::max<size_t>(cat_dicts[q].values.size(), 1), -1);
+        for (size_t i = 0; i < cat_dicts[q].values.size(); ++i)
+            if (present[i]) remap[i] = (int32_t)(std::lower_bound(levels.begin(), levels.end(), cat_dicts[q].values[i]) - levels.begin());
+        remaps.push_back(std::move(remap));
+        p.cat_levels.push_back((int32_t)levels.size());
+        p.category_counts[cat] = levels.size();
+        p.base_categories[cat] = cat + "_" + levels[0];
+        for (size_t l = 1; l < levels.size(); ++l) p.names.push_back(cat + "_" + levels[l]);
+    }
+    // split_groups (builder.rs:61-102)
+    std::vector<uint8_t> gpresent(std::max<size_t>(gd.values.size(), 1), 0);
+    ob_ingest_presence(ing, -1, gpresent.data());
+    std::set<std::string> ug;
+    for (size_t i = 0; i < gd.values.size(); ++i) if (gpresent[i]) ug.insert(gd.values[i]);
+    if (ug.size() < 2)
+        throw OaxacaError(OB_ERR_INVALID_GROUP, OaxacaError::display(OB_ERR_INVALID_GROUP, "Not enough groups for comparison"));
+    auto it = ug.begin();
+    std::string a_name = *it;
+    if (a_name == reference_group_) a_name = *(++it);
+    std::vector<int32_t> gmap(std::max<size_t>(gd.values.size(), 1), 2);
+    for (size_t i = 0; i < gd.values.size(); ++i) gmap[i] = gd.values[i] == a_name ? 0 : (gd.values[i] == reference_group_ ? 1 : 2);
+    fill_norm_spec(p);
+
+    std::vector<const int32_t*> remap_ptrs(std::max<size_t>(remaps.size(), 1), nullptr);
+    for (size_t q = 0; q < remaps.size(); ++q) remap_ptrs[q] = remaps[q].data();
+    ob_design* des = nullptr;
+    check(ctx, ob_ingest_finish(ctx, ing, gmap.data(), remap_ptrs.data(), p.cat_levels.data(), &des));
+    return des;
+}
+
 OaxacaResults OaxacaBuilder::run() const { return run_impl(false, 0.0); }
 
 OaxacaResults OaxacaBuilder::decompose_quantile(double quantile) const {
@@ -292,20 +417,11 @@ OaxacaResults OaxacaBuilder::run_impl(bool rif, double tau) const {
     if (has_selection_)
         throw OaxacaError(OB_ERR_UNSUPPORTED, "heckman_selection: the Heckman estimator is outside the B200 bootstrap path "
                                               "(SURVEY.md 8f); no CPU fallback is provided");
-    Prepared p = prepare();
+    Prepared p;
     CtxGuard g;
     ob_status st = ob_ctx_create(device_, &g.ctx);
     if (st != OB_OK) throw OaxacaError(st, "no usable CUDA device (B200 / sm_100a required; there is no CPU fallback)");
-
-    std::vector<const double*> cont(std::max<size_t>(p.cont.size(), 1), nullptr);
-    for (size_t c = 0; c < p.cont.size(); ++c) cont[c] = p.cont[c].data();
-    std::vector<const int32_t*> cats(std::max<size_t>(p.cat_codes.size(), 1), nullptr);
-    for (size_t c = 0; c < p.cat_codes.size(); ++c) cats[c] = p.cat_codes[c].data();
-    ob_frame_view fv{};
-    fv.n = (int64_t)p.n; fv.n_cont = (int32_t)p.cont.size(); fv.cont = cont.data();
-    fv.n_cat = (int32_t)p.cat_codes.size(); fv.cat_codes = cats.data(); fv.cat_levels = p.cat_levels.data();
-    fv.outcome = p.y.data(); fv.weights = has_weights_ ? p.w.data() : nullptr; fv.group = p.group.data();
-    check(g.ctx, ob_design_pack(g.ctx, &fv, &g.des));
+    g.des = ingest_on_device(g.ctx, p, has_weights_);
     if (rif) check(g.ctx, ob_design_apply_rif(g.ctx, g.des, tau));
 
     int64_t na = 0, nb = 0; int32_t K = 0, nc = 0;
@@ -360,19 +476,11 @@ OaxacaResults OaxacaBuilder::run_impl(bool rif, double tau) const {
 }
 
 DataMatrices OaxacaBuilder::get_data_matrices() const {   // builder.rs:252-291
-    Prepared p = prepare();
+    Prepared p;
     CtxGuard g;
     ob_status st = ob_ctx_create(device_, &g.ctx);
     if (st != OB_OK) throw OaxacaError(st, "no usable CUDA device (B200 / sm_100a required; there is no CPU fallback)");
-    std::vector<const double*> cont(std::max<size_t>(p.cont.size(), 1), nullptr);
-    for (size_t c = 0; c < p.cont.size(); ++c) cont[c] = p.cont[c].data();
-    std::vector<const int32_t*> cats(std::max<size_t>(p.cat_codes.size(), 1), nullptr);
-    for (size_t c = 0; c < p.cat_codes.size(); ++c) cats[c] = p.cat_codes[c].data();
-    ob_frame_view fv{};
-    fv.n = (int64_t)p.n; fv.n_cont = (int32_t)p.cont.size(); fv.cont = cont.data();
-    fv.n_cat = (int32_t)p.cat_codes.size(); fv.cat_codes = cats.data(); fv.cat_levels = p.cat_levels.data();
-    fv.outcome = p.y.data(); fv.weights = nullptr; fv.group = p.group.data();
-    check(g.ctx, ob_design_pack(g.ctx, &fv, &g.des));
+    g.des = ingest_on_device(g.ctx, p, false);
     int64_t na = 0, nb = 0; int32_t K = 0, nc = 0;
     ob_design_shape(g.des, &na, &nb, &K, &nc);
     DataMatrices m;

@@ -110,7 +110,9 @@ public:
 
 private:
     struct Prepared;
-    Prepared prepare() const;
+    Prepared prepare() const;                                    // host-only restatement (describe(), CPU tests)
+    void fill_norm_spec(Prepared& p) const;
+    ob_design* ingest_on_device(ob_ctx* ctx, Prepared& meta, bool with_weights) const;   // production path
     OaxacaResults run_impl(bool rif, double tau) const;
 
     DataFrame dataframe_;

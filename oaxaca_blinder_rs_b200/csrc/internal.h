@@ -199,6 +199,31 @@ void scale_rows_launch(const GroupData& g, int ldx, cudaStream_t st);
 // residuals of the point estimate: r = y - X beta (ols.rs:118-119) for one group
 void residuals_launch(const GroupData& g, int K, int ldx, const double* d_beta, double* d_out, cudaStream_t st);
 
+// ---- ingest.cu ----
+constexpr int INGEST_MAX_COLS = 96;
+struct IngestScanArgs {
+    long long n;
+    int n_valid; const uint8_t* valid[INGEST_MAX_COLS];      // validity bytes of the numeric columns that carry nulls
+    int n_nan; const double* nan_cols[INGEST_MAX_COLS];      // numeric columns in which a NaN counts as null (nan_is_null)
+    int n_dict; const int32_t* codes[INGEST_MAX_COLS];       // dictionary columns: categoricals.., group last
+    int dict_size[INGEST_MAX_COLS];
+    uint8_t* present[INGEST_MAX_COLS];                       // [dict_size] per dictionary column, zeroed by the caller
+    uint8_t* row_valid;                                      // [n] out
+    long long* kept;                                         // out: rows kept (zeroed by the caller)
+    int* flags;                                              // bit 0: code >= dict_size
+};
+struct IngestApplyArgs {
+    long long n; int n_cat;
+    const uint8_t* row_valid;
+    const int32_t* group_codes; const int32_t* group_map;    // dictionary code -> 0 (A) / 1 (reference) / anything else
+    int32_t* cat_codes[INGEST_MAX_COLS];                     // in place: dictionary code -> level code
+    const int32_t* remap; int remap_off[INGEST_MAX_COLS];    // concatenated per-categorical tables
+    uint8_t* group_out;                                      // [n]
+    int* flags;                                              // bit 1: a valid row maps to an absent level
+};
+void ingest_scan_launch(const IngestScanArgs& a, cudaStream_t st);
+void ingest_apply_launch(const IngestApplyArgs& a, cudaStream_t st);
+
 // ---- comm.cu: collectives between the GPUs of one box (mode N row sharding) ----
 // Two transports behind one interface: NCCL over NVLink/NVSwitch (one process per GPU; libnccl is dlopen'ed, the
 // communicator is bootstrapped from an ncclUniqueId the host layer broadcasts), and an in-process transport for

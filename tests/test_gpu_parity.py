@@ -364,3 +364,55 @@ def test_outcome_refresh_equals_repack(ob, ctx):
     np.testing.assert_array_equal(got[1], 2 * ya)
     np.testing.assert_array_equal(got[4], 2 * yb)
     des.close()
+
+
+def test_ingest_matches_host_cleaning(ob, ctx):
+    """ob_ingest_begin/finish (device-side clean_dataframe + create_dummies_manual + split_groups coding,
+    builder.rs:760-806, :61-102) against the same steps restated with numpy/python on the host: nulls in every kind
+    of column, an unsorted dictionary, a level that only occurs in dropped rows, a third group, unused entries."""
+    from oaxaca_blinder_rs_b200 import core
+    rng = np.random.default_rng(17)
+    n = 50_021
+    x1 = rng.normal(size=n); x2 = rng.normal(size=n)
+    y = 1 + x1 - 0.5 * x2 + rng.normal(size=n)
+    w = rng.uniform(0.5, 2.0, n)
+    sector_dict = ["tech", "agri", "zzz_unused", "serv", "manu", "only_in_null_rows"]       # arbitrary order
+    sector = rng.choice([0, 1, 3, 4], size=n).astype(np.int32)
+    group_dict = ["M", "other", "F"]
+    group = rng.choice([0, 1, 2], size=n, p=[0.45, 0.1, 0.45]).astype(np.int32)
+    # nulls
+    x1[rng.choice(n, 300, replace=False)] = np.nan
+    y[rng.choice(n, 200, replace=False)] = np.nan
+    w[rng.choice(n, 100, replace=False)] = np.nan
+    sector[rng.choice(n, 250, replace=False)] = -1
+    group[rng.choice(n, 150, replace=False)] = -1
+    rare = rng.choice(n, 40, replace=False)
+    sector[rare] = 5; x2[rare] = np.nan                                       # that level exists only in dropped rows
+    des, meta = core.ingest(ctx, [x1, x2], [(sector, sector_dict)], y, w, (group, group_dict), reference_group="F")
+    # host restatement
+    ok = ~(np.isnan(x1) | np.isnan(x2) | np.isnan(y) | np.isnan(w)) & (sector >= 0) & (group >= 0)
+    assert meta["rows_kept"] == int(ok.sum())
+    lv = sorted({sector_dict[c] for c in sector[ok]})
+    assert meta["levels"] == [lv] and lv == ["agri", "manu", "serv", "tech"] and meta["group_a"] == "M"
+    sec_names = np.array(sector_dict)[np.where(sector >= 0, sector, 0)]
+    cols = [np.ones(n), x1, x2] + [(sec_names == s).astype(float) for s in lv[1:]]
+    X = np.stack(cols, 1)
+    gname = np.array(group_dict)[np.where(group >= 0, group, 0)]
+    A, B = ok & (gname == "M"), ok & (gname == "F")
+    Xa, ya, wa, Xb, yb, wb = des.download()
+    np.testing.assert_array_equal(Xa, X[A]); np.testing.assert_array_equal(Xb, X[B])
+    np.testing.assert_array_equal(ya, y[A]); np.testing.assert_array_equal(yb, y[B])
+    np.testing.assert_array_equal(wa, w[A]); np.testing.assert_array_equal(wb, w[B])
+    # and the bootstrap on it equals the one on a host-cleaned, host-coded frame packed the ordinary way
+    code = {s: i for i, s in enumerate(lv)}
+    keep = np.flatnonzero(ok)
+    des2 = ob.Design.pack(ctx, [x1[keep], x2[keep]], [np.array([code[s] for s in sec_names[keep]], dtype=np.int32)], [len(lv)],
+                          y[keep], w[keep], np.where(gname[keep] == "M", 0, np.where(gname[keep] == "F", 1, 2)).astype(np.uint8))
+    r1 = ob.bootstrap(des, 50, seed=3, want_rep=True)
+    r2 = ob.bootstrap(des2, 50, seed=3, want_rep=True)
+    np.testing.assert_array_equal(r1["rep_stats"], r2["rep_stats"])
+    des.close(); des2.close()
+    # fewer than two groups after cleaning -> InvalidGroupVariable (builder.rs:67-71)
+    with pytest.raises(ob.OaxacaError) as e:
+        core.ingest(ctx, [x1, x2], [], y, None, (np.where(group == 2, 2, -1).astype(np.int32), group_dict), reference_group="F")
+    assert e.value.kind == "InvalidGroupVariable"
