@@ -281,6 +281,201 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelP
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-specialised variant (OBBOOT_GRAM_WS=1): 8 consumer warps issue nothing but fragment loads and DMMAs; a
+// producer warpgroup (4 warps) owns the TMA issue and the widening of the count tiles.  Ring of WS_R slots, each holding a stage's
+// raw counts, design rows and widened fp64 A tile; three mbarriers per slot:
+//   full[s]      TMA bytes landed             (producer lane 0 arms it; producer and consumers wait)
+//   ready[s]     A tile widened               (one arrival per producer warp; consumers wait)
+//   consumed[s]  stage finished by a warp     (one arrival per consumer warp; producer waits before reusing the slot)
+// Stage numbers run on across work units, so the producer prefetches and widens the next unit's first stages while
+// the consumers finish the current one: no per-unit pipeline fill, no CTA-wide barrier in the loop.
+constexpr int WS_R = 3;
+constexpr int WS_PRODUCER_WARPS = 4;                       // one warpgroup, so that setmaxnreg can rebalance registers
+constexpr int WS_THREADS = GRAM_THREADS + 32 * WS_PRODUCER_WARPS;
+// register budget: 384 threads x 168 at launch; the producer warpgroup drops to 56, the two consumer warpgroups rise to 224
+#define OB_WS_CONSUMER_REGS 224
+#define OB_WS_PRODUCER_REGS 56
+
+struct GramUnit { const double* Xg; const void* Cg; double* out; int nstages, nt; bool half; };
+
+__device__ __forceinline__ bool ws_decode(const GramKernelParams& p, long long i, int ldx, size_t count_bytes, GramUnit& u) {
+    const long long sweeps0 = (long long)p.segs[0] * p.panels, sweeps1 = (long long)p.segs[1] * p.panels;
+    const long long NF0 = sweeps0 * p.nfull, NF = NF0 + sweeps1 * p.nfull;
+    const long long NH = p.has_half ? sweeps0 + sweeps1 : 0;
+    if (i >= NF + NH) return false;
+    int g, nt; long long sweep;
+    if (i < NF) {
+        g = i >= NF0 ? 1 : 0;
+        const long long r = i - (g ? NF0 : 0);
+        sweep = r / p.nfull; nt = (int)(r - sweep * p.nfull);
+    } else {
+        const long long r = i - NF;
+        g = r >= sweeps0 ? 1 : 0;
+        sweep = r - (g ? sweeps0 : 0); nt = p.nfull;
+    }
+    const int seg = (int)(sweep / p.panels), panel = (int)(sweep - (long long)seg * p.panels);
+    const int segs = g ? p.segs[1] : p.segs[0], seg_rows = g ? p.seg_rows[1] : p.seg_rows[0];
+    const long long n_pad = g ? p.n_pad[1] : p.n_pad[0];
+    const long long row0 = (long long)seg * seg_rows;
+    const long long row1 = min(row0 + seg_rows, n_pad);
+    u.nstages = (int)((row1 - row0) / KT);
+    u.nt = nt; u.half = p.has_half && nt == p.nfull;
+    u.Xg = (g ? p.X[1] : p.X[0]) + row0 * ldx;
+    u.Cg = reinterpret_cast<const unsigned char*>(g ? p.C[1] : p.C[0]) + (((long long)panel * n_pad + row0) * BM) * (long long)count_bytes;
+    u.out = p.partials + (size_t)((g ? p.units0 : 0) + ((long long)panel * segs + seg) * p.ntiles + nt) * (BM * BN);
+    return true;
+}
+
+template <typename CountT, int LDXC, int NI>
+__device__ __forceinline__ void ws_consume_unit(const GramKernelParams& p, const GramUnit& u, const double* As, const double* Xs,
+                                                uint64_t* full, uint64_t* ready, uint64_t* consumed, int ldx_rt, uint32_t& jc) {
+    constexpr int MI = 16, KSTEPS = KT / 4;
+    constexpr int TW = 8 * NI * 8;
+    const int lane = threadIdx.x & 31, wn = threadIdx.x >> 5;
+    const int lk = lane & 3, lg = lane >> 2;
+    const int ldx = LDXC ? LDXC : ldx_rt;
+    int oj[NI], ol[NI];
+#pragma unroll
+    for (int s = 0; s < NI; ++s) {
+        const int col = u.nt * BN + wn * (NI * 8) + s * 8 + lg;
+        const uint32_t pr = *reinterpret_cast<const uint32_t*>(p.pairs + 2 * col);
+        oj[s] = pr & 0xFFFFu; ol[s] = pr >> 16;
+    }
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int s = 0; s < NI; ++s) { acc[i][s][0] = 0.0; acc[i][s][1] = 0.0; }
+
+    for (int s = 0; s < u.nstages; ++s) {
+        const uint32_t slot = jc % WS_R, par = (jc / WS_R) & 1u;
+        mbar_wait(&full[slot], par);       // design rows of this stage (TMA writes become visible to this thread)
+        mbar_wait(&ready[slot], par);      // widened A tile
+        const double* abase = As + (size_t)slot * A_TILE + lk * LDA2 + lg * LGS;
+        const double* xbase = Xs + (size_t)slot * KT * ldx + lk * ldx;
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+            double a[MI], b[NI];
+            const double* arow = abase + kk * 4 * LDA2;
+            const double* xrow = xbase + kk * 4 * ldx;
+#pragma unroll
+            for (int i = 0; i < MI; i += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(arow + i);
+                a[i] = v.x; a[i + 1] = v.y;
+            }
+#pragma unroll
+            for (int t = 0; t < NI; ++t) b[t] = xrow[oj[t]] * xrow[ol[t]];
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int t = 0; t < NI; ++t) dmma884(acc[i][t][0], acc[i][t][1], a[i], b[t]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&consumed[slot]);
+        ++jc;
+    }
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int t = 0; t < NI; ++t) {
+            const int m = i * 8 + lg, n = wn * (NI * 8) + t * 8 + 2 * lk;
+            *reinterpret_cast<double2*>(u.out + m * TW + n) = make_double2(acc[i][t][0], acc[i][t][1]);
+        }
+}
+
+template <typename CountT, int LDXC>
+__global__ void __launch_bounds__(WS_THREADS, 1) gram_ws_kernel(const GramKernelParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ldx = LDXC ? LDXC : p.ldx;
+    double* As = reinterpret_cast<double*>(smem_raw);                           // [WS_R][A_TILE]
+    double* Tab = As + WS_R * A_TILE;                                           // [256]
+    double* Xs = Tab + 256;                                                     // [WS_R][KT*ldx]
+    CountT* Cr = reinterpret_cast<CountT*>(Xs + (size_t)WS_R * KT * ldx);       // [WS_R][KT*BM]
+    uint64_t* full = reinterpret_cast<uint64_t*>(Cr + (size_t)WS_R * KT * BM);  // [WS_R]
+    uint64_t* ready = full + WS_R;
+    uint64_t* consumed = ready + WS_R;
+    if (tid < 256) Tab[tid] = (double)tid;
+    if (tid == 0) {
+        for (int s = 0; s < WS_R; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], WS_PRODUCER_WARPS); mbar_init(&consumed[s], GRAM_THREADS / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp < GRAM_THREADS / 32) {
+        // ---------------- consumers ----------------
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(OB_WS_CONSUMER_REGS));
+        uint32_t jc = 0;
+        GramUnit u;
+        for (long long i = blockIdx.x; ws_decode(p, i, ldx, sizeof(CountT), u); i += gridDim.x) {
+            if (u.half) ws_consume_unit<CountT, LDXC, 1>(p, u, As, Xs, full, ready, consumed, ldx, jc);
+            else ws_consume_unit<CountT, LDXC, 2>(p, u, As, Xs, full, ready, consumed, ldx, jc);
+        }
+    } else {
+        // ---------------- producers: TMA issue (warp 0 lane 0) + widening (4 warps x 8 rows) ----------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OB_WS_PRODUCER_REGS));
+        const int pw = warp - GRAM_THREADS / 32;
+        const uint32_t stage_bytes = (uint32_t)(KT * ldx * sizeof(double) + KT * BM * sizeof(CountT));
+        // two cursors over the (unit, stage) sequence: `is` = next stage to issue, `wi` = next stage to widen
+        long long is_i = blockIdx.x, wi_i = blockIdx.x;
+        int is_s = 0, wi_s = 0;
+        GramUnit is_u, wi_u;
+        bool is_ok = ws_decode(p, is_i, ldx, sizeof(CountT), is_u);
+        bool wi_ok = ws_decode(p, wi_i, ldx, sizeof(CountT), wi_u);
+        uint32_t ji = 0, jw = 0;
+        auto issue_next = [&]() {   // stage ji -> slot ji % WS_R
+            const uint32_t slot = ji % WS_R;
+            if (pw == 0 && lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&full[slot], stage_bytes);
+                tma_load_1d(Xs + (size_t)slot * KT * ldx, is_u.Xg + (long long)is_s * KT * ldx, KT * ldx * sizeof(double), &full[slot]);
+                tma_load_1d(Cr + (size_t)slot * KT * BM, reinterpret_cast<const CountT*>(is_u.Cg) + (long long)is_s * KT * BM,
+                            KT * BM * sizeof(CountT), &full[slot]);
+            }
+            ++ji;
+            if (++is_s == is_u.nstages) { is_s = 0; is_i += gridDim.x; is_ok = ws_decode(p, is_i, ldx, sizeof(CountT), is_u); }
+        };
+        while (is_ok && ji < (uint32_t)WS_R) issue_next();
+        while (wi_ok) {
+            const uint32_t slot = jw % WS_R, par = (jw / WS_R) & 1u;
+            mbar_wait(&full[slot], par);
+            // widen Cr[slot] (32 rows x 128 slots) -> As[slot], fragment-major; producer warp pw takes rows 8 pw .. 8 pw + 7
+            {
+                const CountT* src = Cr + (size_t)slot * KT * BM;
+                double* dst = As + (size_t)slot * A_TILE;
+                // item = (e, r, lg): slots m = 8 (2e) + lg and 8 (2e+1) + lg of row r -> one STS.128 at dst[r][lg][2e];
+                // consecutive lanes take consecutive lg (then r): conflict-free stores (LGS = 18, LDA2 = 148)
+#pragma unroll 4
+                for (int it = lane; it < (KT / WS_PRODUCER_WARPS) * 8 * 8; it += 32) {
+                    const int e = it >> 6, rem = it & 63, r = pw * (KT / WS_PRODUCER_WARPS) + (rem >> 3), lgq = rem & 7;
+                    const CountT* sp = src + r * BM + lgq;
+                    double2 o;
+                    o.x = count_to_f64<CountT>(sp[e * 16], Tab);
+                    o.y = count_to_f64<CountT>(sp[e * 16 + 8], Tab);
+                    *reinterpret_cast<double2*>(dst + r * LDA2 + lgq * LGS + e * 2) = o;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[slot]);
+            ++jw;
+            if (++wi_s == wi_u.nstages) { wi_s = 0; wi_i += gridDim.x; wi_ok = ws_decode(p, wi_i, ldx, sizeof(CountT), wi_u); }
+            // refill: stage ji reuses the slot of stage ji - WS_R, which the consumers must have finished (only the issuing
+            // warp waits; the other producer warps meet the new stage at its full[] barrier)
+            if (is_ok && ji <= jw + (uint32_t)(WS_R - 2)) {
+                const uint32_t prev = ji - WS_R;
+                if (pw == 0) mbar_wait(&consumed[prev % WS_R], (prev / WS_R) & 1u);
+                issue_next();
+            }
+        }
+    }
+}
+
+static size_t gram_ws_smem(int ldx, int count_bytes) {
+    return sizeof(double) * ((size_t)WS_R * A_TILE + 256 + (size_t)WS_R * KT * ldx) + (size_t)WS_R * KT * BM * count_bytes +
+           sizeof(uint64_t) * 3 * WS_R;
+}
+
 // Aligned binary summation tree over LEN consecutive leaves starting at `lo` (lo < cnt): leaves >= cnt are absent
 // and skipped.  The tree shape depends on the leaf indices only, so any aligned sub-range reduced on another GPU
 // (mode N) yields the very same intermediate sums.
@@ -397,6 +592,30 @@ void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEve
     p.sched = sched;
     p.partials = a.partials; p.pairs = a.d_pairs;
     if (ev_main_begin) OB_CUDA(cudaEventRecord(ev_main_begin, st));
+    // warp-specialised kernel (default; measured +6-11 % over the single-role kernel, profiles/r01_gram_ws_ab.json);
+    // OBBOOT_GRAM_WS=0 selects the single-role kernel
+    const size_t ws_smem = gram_ws_smem(pl.ldx, a.count_bytes);
+    static const int ws = getenv("OBBOOT_GRAM_WS") ? atoi(getenv("OBBOOT_GRAM_WS")) : 1;
+    if (ws && ws_smem <= 227 * 1024) {
+        auto launch_ws = [&](auto kernel) {
+            OB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem));
+            kernel<<<pl.grid, WS_THREADS, ws_smem, st>>>(p);
+        };
+#define OB_GRAM_WS_CASE(L) case L: if (a.count_bytes == 1) launch_ws(gram_ws_kernel<uint8_t, L>); else launch_ws(gram_ws_kernel<uint16_t, L>); break;
+        switch (pl.ldx) {
+            OB_GRAM_WS_CASE(12) OB_GRAM_WS_CASE(20) OB_GRAM_WS_CASE(28) OB_GRAM_WS_CASE(36) OB_GRAM_WS_CASE(44) OB_GRAM_WS_CASE(52)
+            OB_GRAM_WS_CASE(60) OB_GRAM_WS_CASE(68) OB_GRAM_WS_CASE(76) OB_GRAM_WS_CASE(84) OB_GRAM_WS_CASE(92)
+            default: if (a.count_bytes == 1) launch_ws(gram_ws_kernel<uint8_t, 0>); else launch_ws(gram_ws_kernel<uint16_t, 0>);
+        }
+#undef OB_GRAM_WS_CASE
+        OB_CUDA(cudaGetLastError());
+        if (ev_main_end) OB_CUDA(cudaEventRecord(ev_main_end, st));
+        dim3 rgw(2 * pl.panels * pl.ntiles, 4);
+        gram_reduce_kernel<<<rgw, 256, 0, st>>>(a.partials, pl.segs[0], pl.segs[1], a.gram, pl.panels, pl.ntiles, pl.leaf_span,
+                                                pl.Pld, pl.has_half);
+        OB_CUDA(cudaGetLastError());
+        return;
+    }
     auto launch = [&](auto kernel) {
         OB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
         kernel<<<pl.grid, GRAM_THREADS, pl.smem_bytes, st>>>(p);
