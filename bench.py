@@ -39,8 +39,8 @@ WORKLOADS = {
     "probe5_n20M_k16_B2000": (20_000_000, 16, (), False, False, 2000, 0),  # config-5 column shape (1 full + 1 half tile)
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE gram_kernel launch, from ncu captures of this same command
-# (profiles/r01_gram_dram_config3_v9.csv; one-pass bytes of X and C at config 3 are 24.2 GB)
-GRAM_DRAM_TRAFFIC = {("config3_n10M_k50_wls_yun_B2000", 1): 104976087808 + 2996615168}
+# (profiles/r01_gram_dram_config3_v14.csv; one-pass bytes of X and C at config 3 are 24.2 GB)
+GRAM_DRAM_TRAFFIC = {("config3_n10M_k50_wls_yun_B2000", 1): 32628926208 + 3051690240}
 HBM_PEAK_GBS = 6550.1            # MEASURED_PEAKS.json (driver-written copy bandwidth on this pool)
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool (profiles/r01_fp64_peaks.json): DMMA.8x8x4 issue peak
 FP64_CUBLAS_DGEMM_TFLOPS = 35.4  # measured on this pool (profiles/r01_dgemm_peak.json): cuBLAS DGEMM 8192^3
@@ -357,7 +357,7 @@ def main():
                     {"value": reps * args.steps / refresh, "unit": "reps/s", "h2d_bytes_per_step": int(8 * n),
                      "what": "ob_design_update_outcome (new y from pinned host memory, X resident) + bootstrap per step"},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "tensor", "kernel": "gram_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
+                "roofline": {"bound": "tensor", "kernel": "gram_ws_kernel (FP64 DMMA.8x8x4, warp-specialised)", "achieved": achieved,
                              "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
                              "frac_of_cublas_dgemm": achieved / FP64_CUBLAS_DGEMM_TFLOPS,
                              "peak_source": "measured on this pool: FP64 DMMA issue peak, profiles/r01_fp64_peaks.json "
@@ -365,7 +365,7 @@ def main():
                              "launch_ms": g_ms, "flop_per_launch": flops_rank,
                              "traffic": GRAM_DRAM_TRAFFIC.get((name, world)),
                              "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch of this "
-                                               "command (profiles/r01_gram_dram_config3_v9.csv)"
+                                               "command (profiles/r01_gram_dram_config3_v14.csv)"
                                                if (name, world) in GRAM_DRAM_TRAFFIC else None},
                 "stage_ms": dict({k: float(v) for k, v in out["timings_ms"].items()},
                                  other=float(out["timings_ms"]["total"] - sum(out["timings_ms"][k] for k in
