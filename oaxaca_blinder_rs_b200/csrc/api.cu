@@ -866,6 +866,10 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 for (int g = 0; g < 2; ++g) { ga.X[g] = d->g[g].gram_operand(); ga.C[g] = d_C[g].p; }
                 ga.count_bytes = count_bytes; ga.partials = d_partials.as<double>();
                 ga.d_pairs = d_pairs.as<uint16_t>(); ga.gram = comm ? d_gram_local.as<double>() : d_gram.as<double>();
+                {   // valid slots of this batch's last panel -> 8-slot groups, rounded up to a multiple of 4
+                    const int64_t last = bslots - (pn - 1) * BM;
+                    ga.tail_mi = (int)std::min<int64_t>(16, ((last + 7) / 8 + 3) / 4 * 4);
+                }
                 cudaEvent_t ev0, ev1;
                 OB_CUDA(cudaEventCreate(&ev0)); OB_CUDA(cudaEventCreate(&ev1));
                 gram_launch(plan, ga, st, ev0, ev1);

@@ -50,6 +50,8 @@ struct GramKernelParams {
     int ldx, panels, ntiles, stages;
     int nfull, has_half;    // column tiling: nfull tiles of BN columns + (has_half ? one tile of BN/2 : none)
     int sched;              // 1: lockstep round-robin (default), 0: contiguous cost-balanced ranges (OBBOOT_GRAM_SCHED)
+    int tail_mi;            // warp-specialised kernel: 8-slot groups of the LAST panel that hold valid slots, rounded up to
+                            // a multiple of 4 (16 = the panel is full): its units skip the DMMAs of the empty groups
     double* partials;       // [units_total][BM*BN], unit-major (a half tile uses the first BM*BN/2 doubles, stride BN/2)
     const uint16_t* pairs;
 };
@@ -297,40 +299,47 @@ constexpr int WS_THREADS = GRAM_THREADS + 32 * WS_PRODUCER_WARPS;
 #define OB_WS_CONSUMER_REGS 224
 #define OB_WS_PRODUCER_REGS 56
 
-struct GramUnit { const double* Xg; const void* Cg; double* out; int nstages, nt; bool half; };
+struct GramUnit { const double* Xg; const void* Cg; double* out; int nstages, nt, mi; bool half; };
 
+// Unit sequence of the warp-specialised kernel: four cost classes, each in (group, segment, panel, tile) order --
+// wide tiles of full panels, wide tiles of the tail panel, half-width tiles of full panels, half-width tiles of the
+// tail panel.  CTA b takes positions b, b + grid, ...: equal shares of every class, lockstep through consecutive units.
 __device__ __forceinline__ bool ws_decode(const GramKernelParams& p, long long i, int ldx, size_t count_bytes, GramUnit& u) {
-    const long long sweeps0 = (long long)p.segs[0] * p.panels, sweeps1 = (long long)p.segs[1] * p.panels;
-    const long long NF0 = sweeps0 * p.nfull, NF = NF0 + sweeps1 * p.nfull;
-    const long long NH = p.has_half ? sweeps0 + sweeps1 : 0;
-    if (i >= NF + NH) return false;
-    int g, nt; long long sweep;
-    if (i < NF) {
-        g = i >= NF0 ? 1 : 0;
-        const long long r = i - (g ? NF0 : 0);
-        sweep = r / p.nfull; nt = (int)(r - sweep * p.nfull);
-    } else {
-        const long long r = i - NF;
-        g = r >= sweeps0 ? 1 : 0;
-        sweep = r - (g ? sweeps0 : 0); nt = p.nfull;
-    }
-    const int seg = (int)(sweep / p.panels), panel = (int)(sweep - (long long)seg * p.panels);
+    const int pt = p.tail_mi < 16 ? 1 : 0, pf = p.panels - pt;            // tail / full panels of this batch
+    const long long segs01 = (long long)p.segs[0] + p.segs[1];
+    const long long n0 = segs01 * pf * p.nfull, n1 = segs01 * pt * p.nfull;
+    const long long n2 = p.has_half ? segs01 * pf : 0, n3 = p.has_half ? segs01 * pt : 0;
+    if (i >= n0 + n1 + n2 + n3) return false;
+    int np, p0, nt_cnt, nt0;          // panels / first panel / tiles per sweep / first tile of the class
+    if (i < n0) { np = pf; p0 = 0; nt_cnt = p.nfull; nt0 = 0; }
+    else if ((i -= n0) < n1) { np = pt; p0 = pf; nt_cnt = p.nfull; nt0 = 0; }
+    else if ((i -= n1) < n2) { np = pf; p0 = 0; nt_cnt = 1; nt0 = p.nfull; }
+    else { i -= n2; np = pt; p0 = pf; nt_cnt = 1; nt0 = p.nfull; }
+    const long long per_seg = (long long)np * nt_cnt;
+    const long long g0 = (long long)p.segs[0] * per_seg;
+    const int g = i >= g0 ? 1 : 0;
+    const long long r = i - (g ? g0 : 0);
+    const int seg = (int)(r / per_seg);
+    const long long r2 = r - (long long)seg * per_seg;
+    const int panel = p0 + (int)(r2 / nt_cnt), nt = nt0 + (int)(r2 % nt_cnt);
     const int segs = g ? p.segs[1] : p.segs[0], seg_rows = g ? p.seg_rows[1] : p.seg_rows[0];
     const long long n_pad = g ? p.n_pad[1] : p.n_pad[0];
     const long long row0 = (long long)seg * seg_rows;
     const long long row1 = min(row0 + seg_rows, n_pad);
     u.nstages = (int)((row1 - row0) / KT);
     u.nt = nt; u.half = p.has_half && nt == p.nfull;
+    u.mi = panel >= pf ? p.tail_mi : 16;
     u.Xg = (g ? p.X[1] : p.X[0]) + row0 * ldx;
     u.Cg = reinterpret_cast<const unsigned char*>(g ? p.C[1] : p.C[0]) + (((long long)panel * n_pad + row0) * BM) * (long long)count_bytes;
     u.out = p.partials + (size_t)((g ? p.units0 : 0) + ((long long)panel * segs + seg) * p.ntiles + nt) * (BM * BN);
     return true;
 }
 
-template <typename CountT, int LDXC, int NI>
+// MI = 8-slot groups of the panel this warp accumulates (16 = all 128 slots; 4 / 8 / 12 for a partly filled tail panel)
+template <typename CountT, int LDXC, int NI, int MI>
 __device__ __forceinline__ void ws_consume_unit(const GramKernelParams& p, const GramUnit& u, const double* As, const double* Xs,
                                                 uint64_t* full, uint64_t* ready, uint64_t* consumed, int ldx_rt, uint32_t& jc) {
-    constexpr int MI = 16, KSTEPS = KT / 4;
+    constexpr int KSTEPS = KT / 4;
     constexpr int TW = 8 * NI * 8;
     const int lane = threadIdx.x & 31, wn = threadIdx.x >> 5;
     const int lk = lane & 3, lg = lane >> 2;
@@ -375,6 +384,7 @@ __device__ __forceinline__ void ws_consume_unit(const GramKernelParams& p, const
         if (lane == 0) mbar_arrive(&consumed[slot]);
         ++jc;
     }
+    // rows of slot groups >= MI are not written: those slots do not exist (the solve never reads them)
 #pragma unroll
     for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -382,6 +392,17 @@ __device__ __forceinline__ void ws_consume_unit(const GramKernelParams& p, const
             const int m = i * 8 + lg, n = wn * (NI * 8) + t * 8 + 2 * lk;
             *reinterpret_cast<double2*>(u.out + m * TW + n) = make_double2(acc[i][t][0], acc[i][t][1]);
         }
+}
+
+template <typename CountT, int LDXC, int NI>
+__device__ __forceinline__ void ws_consume_dispatch(const GramKernelParams& p, const GramUnit& u, const double* As, const double* Xs,
+                                                    uint64_t* full, uint64_t* ready, uint64_t* consumed, int ldx_rt, uint32_t& jc) {
+    switch (u.mi) {
+    case 4: ws_consume_unit<CountT, LDXC, NI, 4>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
+    case 8: ws_consume_unit<CountT, LDXC, NI, 8>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
+    case 12: ws_consume_unit<CountT, LDXC, NI, 12>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
+    default: ws_consume_unit<CountT, LDXC, NI, 16>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
+    }
 }
 
 template <typename CountT, int LDXC>
@@ -409,8 +430,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gram_ws_kernel(const GramKernel
         uint32_t jc = 0;
         GramUnit u;
         for (long long i = blockIdx.x; ws_decode(p, i, ldx, sizeof(CountT), u); i += gridDim.x) {
-            if (u.half) ws_consume_unit<CountT, LDXC, 1>(p, u, As, Xs, full, ready, consumed, ldx, jc);
-            else ws_consume_unit<CountT, LDXC, 2>(p, u, As, Xs, full, ready, consumed, ldx, jc);
+            if (u.half) ws_consume_dispatch<CountT, LDXC, 1>(p, u, As, Xs, full, ready, consumed, ldx, jc);
+            else ws_consume_dispatch<CountT, LDXC, 2>(p, u, As, Xs, full, ready, consumed, ldx, jc);
         }
     } else {
         // ---------------- producers: TMA issue (warp 0 lane 0) + widening (4 warps x 8 rows) ----------------
@@ -591,6 +612,8 @@ void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEve
     static const int sched = getenv("OBBOOT_GRAM_SCHED") ? atoi(getenv("OBBOOT_GRAM_SCHED")) : 1;   // tuning knob
     p.sched = sched;
     p.partials = a.partials; p.pairs = a.d_pairs;
+    static const int tail = getenv("OBBOOT_GRAM_TAIL") ? atoi(getenv("OBBOOT_GRAM_TAIL")) : 1;   // tuning knob
+    p.tail_mi = tail && a.tail_mi >= 1 && a.tail_mi <= 16 ? a.tail_mi : 16;
     if (ev_main_begin) OB_CUDA(cudaEventRecord(ev_main_begin, st));
     // warp-specialised kernel (default; measured +6-11 % over the single-role kernel, profiles/r01_gram_ws_ab.json);
     // OBBOOT_GRAM_WS=0 selects the single-role kernel

@@ -138,7 +138,9 @@ struct GramArgs {
     int count_bytes;
     double* partials;            // [num_partials][BM*BN]
     const uint16_t* d_pairs;     // [ntiles*BN][2] column offsets (j,l) within a design row
-    double* gram;                // out: [2][panels*BM][ntiles*BN]
+    double* gram;                // out: [2][panels*BM][Pld]
+    int tail_mi = 16;            // 8-slot groups of the batch's last panel that hold valid slots, rounded up to a multiple
+                                 // of 4 (16 = full): lets the kernel skip the DMMAs of slot groups that do not exist
 };
 void gram_launch(const GramPlan& plan, const GramArgs& args, cudaStream_t st, cudaEvent_t ev_main_begin = nullptr,
                  cudaEvent_t ev_main_end = nullptr);
