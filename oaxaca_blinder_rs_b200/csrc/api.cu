@@ -950,10 +950,10 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         tr.mark("point + residuals", st, true);
         // ---- (5) reduction to standard errors / p-values / percentile CIs ----
         if (!o->skip_reduce) {
-            DevBuf d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long));
+            DevBuf d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long)), d_rs(reduce_stats_scratch_bytes(nrep, S));
             Timer t_red(st, &res->ms_reduce);
             reduce_stats_launch(d_stats.as<double>() + S, d_status.as<int>() + 1, nrep, S, d_stats.as<double>(),
-                                d_out.as<double>(), d_nok.as<long long>(), st);
+                                d_out.as<double>(), d_nok.as<long long>(), st, d_rs.as<double>());
             res->gpu_launches += 1;
             t_red.stop();
             std::vector<double> out5(5 * (size_t)S);
@@ -988,13 +988,14 @@ ob_status ob_reduce_stats(ob_ctx* ctx, const double* rep_stats, const int32_t* r
         cudaStream_t st = ctx->stream;
         DevBuf d_stats(sizeof(double) * (size_t)std::max<int64_t>(reps, 1) * S), d_status(sizeof(int) * (size_t)std::max<int64_t>(reps, 1));
         DevBuf d_point(sizeof(double) * S), d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long));
+        DevBuf d_rs(reduce_stats_scratch_bytes(reps, S));
         if (reps) {
             OB_CUDA(cudaMemcpyAsync(d_stats.p, rep_stats, sizeof(double) * (size_t)reps * S, cudaMemcpyHostToDevice, st));
             OB_CUDA(cudaMemcpyAsync(d_status.p, rep_status, sizeof(int) * (size_t)reps, cudaMemcpyHostToDevice, st));
         }
         OB_CUDA(cudaMemcpyAsync(d_point.p, point_stats, sizeof(double) * S, cudaMemcpyHostToDevice, st));
         reduce_stats_launch(d_stats.as<double>(), d_status.as<int>(), reps, S, d_point.as<double>(), d_out.as<double>(),
-                            d_nok.as<long long>(), st);
+                            d_nok.as<long long>(), st, d_rs.as<double>());
         std::vector<double> out5(5 * (size_t)S);
         long long nok = 0;
         OB_CUDA(cudaMemcpyAsync(out5.data(), d_out.p, d_out.bytes, cudaMemcpyDeviceToHost, st));

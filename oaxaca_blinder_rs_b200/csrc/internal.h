@@ -171,9 +171,13 @@ size_t solve_smem_bytes(int K, bool pooled, int n_norm);
 
 // ---- reduce_stats.cu ----
 // stats [reps][S] + status [reps] (device) -> se,p,lo,hi,t [S] each (device, contiguous 5*S) and n_ok
-void reduce_stats_launch(const double* stats, const int* status, int64_t reps, int S,
-                         const double* point_stats, double* out5S, long long* n_ok, cudaStream_t st);
+// up to REDUCE_MAX_REPS replicates the per-statistic sort runs in shared memory; beyond that in d_scratch
+// (reduce_stats_scratch_bytes(reps, S) bytes of device memory)
 constexpr int64_t REDUCE_MAX_REPS = 16384;
+void reduce_stats_launch(const double* stats, const int* status, int64_t reps, int S,
+                         const double* point_stats, double* out5S, long long* n_ok, cudaStream_t st,
+                         double* d_scratch = nullptr);
+size_t reduce_stats_scratch_bytes(int64_t reps, int S);
 
 // ---- pack.cu ----
 struct PackArgs {

@@ -5,7 +5,8 @@
 // masked out (filter_map, builder.rs:816-839), B' = number of successes.
 //   mean, sample SD (B'-1)      two-pass, fixed-order block reduction (deterministic)
 //   p = min(1, 2 min(#>=0, #<=0)/B')
-//   CI = sorted[floor(.025 B')], sorted[min(floor(.975 B'), B'-1)]   (in-smem bitonic sort)
+//   CI = sorted[floor(.025 B')], sorted[min(floor(.975 B'), B'-1)]   (bitonic sort: in shared memory up to 16384
+//        replicates, in a global scratch row per statistic beyond that)
 //   t = point/se if |se| > 1e-9 else 0;   B' = 0 -> all NaN, t = 0
 #include "common.cuh"
 #include "internal.h"
@@ -35,8 +36,9 @@ __global__ void __launch_bounds__(RS_THREADS) reduce_stats_kernel(const double* 
                                                                   const int* __restrict__ status, long long reps,
                                                                   int S, const double* __restrict__ point,
                                                                   double* __restrict__ out, long long* __restrict__ n_ok_out,
-                                                                  int npow2) {
-    extern __shared__ __align__(16) double v[];   // [npow2]
+                                                                  int npow2, double* __restrict__ gscratch) {
+    extern __shared__ __align__(16) double vs[];  // [npow2] when it fits
+    double* v = gscratch ? gscratch + (size_t)blockIdx.x * npow2 : vs;
     __shared__ double red[33];
     const int j = blockIdx.x, tid = threadIdx.x;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
@@ -96,14 +98,24 @@ __global__ void __launch_bounds__(RS_THREADS) reduce_stats_kernel(const double* 
 }
 
 void reduce_stats_launch(const double* stats, const int* status, int64_t reps, int S, const double* point_stats,
-                         double* out5S, long long* n_ok, cudaStream_t st) {
-    if (reps > REDUCE_MAX_REPS) throw StatusError{OB_ERR_UNSUPPORTED, "more than 16384 replicates in one reduction"};
+                         double* out5S, long long* n_ok, cudaStream_t st, double* d_scratch) {
+    if (reps > (1ll << 30)) throw StatusError{OB_ERR_UNSUPPORTED, "more than 2^30 replicates in one reduction"};
     int npow2 = 2;
     while (npow2 < reps) npow2 <<= 1;
-    const size_t smem = sizeof(double) * (size_t)npow2;
-    OB_CUDA(cudaFuncSetAttribute(reduce_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    reduce_stats_kernel<<<S, RS_THREADS, smem, st>>>(stats, status, (long long)reps, S, point_stats, out5S, n_ok, npow2);
+    if (reps > REDUCE_MAX_REPS && !d_scratch) throw StatusError{OB_ERR_INVALID_ARG, "reduction scratch missing"};
+    const bool in_smem = reps <= REDUCE_MAX_REPS;
+    const size_t smem = in_smem ? sizeof(double) * (size_t)npow2 : 0;
+    OB_CUDA(cudaFuncSetAttribute(reduce_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * REDUCE_MAX_REPS)));
+    reduce_stats_kernel<<<S, RS_THREADS, smem, st>>>(stats, status, (long long)reps, S, point_stats, out5S, n_ok, npow2,
+                                                     in_smem ? nullptr : d_scratch);
     OB_CUDA(cudaGetLastError());
+}
+
+size_t reduce_stats_scratch_bytes(int64_t reps, int S) {
+    if (reps <= REDUCE_MAX_REPS) return 0;
+    size_t npow2 = 2;
+    while ((int64_t)npow2 < reps) npow2 <<= 1;
+    return sizeof(double) * npow2 * (size_t)S;
 }
 
 }  // namespace ob

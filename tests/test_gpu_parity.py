@@ -416,3 +416,20 @@ def test_ingest_matches_host_cleaning(ob, ctx):
     with pytest.raises(ob.OaxacaError) as e:
         core.ingest(ctx, [x1, x2], [], y, None, (np.where(group == 2, 2, -1).astype(np.int32), group_dict), reference_group="F")
     assert e.value.kind == "InvalidGroupVariable"
+
+
+def test_reduction_beyond_16384_replicates(ob, orc, ctx):
+    """bootstrap_stats (inference.rs:4-34) over more replicates than the shared-memory sort holds: the per-statistic
+    sort then runs in a global scratch row; same numbers as the oracle's reduction."""
+    from oaxaca_blinder_rs_b200 import core
+    rng = np.random.default_rng(3)
+    reps, S = 40_000, 9
+    stats = rng.normal(size=(reps, S)) * np.arange(1, S + 1) + np.linspace(-1, 1, S)
+    status = (rng.random(reps) < 0.01).astype(np.int32) * 4            # ~1 % failed replicates (NalgebraError)
+    stats[status != 0] = np.nan
+    point = stats[0].copy(); point[np.isnan(point)] = 0.0
+    got = core.reduce_stats(ctx, np.nan_to_num(stats), status, point)
+    ref = orc.reduce(np.nan_to_num(stats), status, point)
+    assert got["n_ok"] == ref["n_ok"] == int((status == 0).sum())
+    for k, rk in (("std_err", "se"), ("p_value", "p"), ("ci_lower", "ci_lo"), ("ci_upper", "ci_hi"), ("t_stat", "t")):
+        assert relerr(got[k], ref[rk]) <= RTOL, k
