@@ -169,8 +169,9 @@ def run_reference(args, name):
     line = {"impl": "reference", "metric": "bootstrap_reps_per_sec", "value": value, "unit": "reps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "n": d["n"], "k": K - 1, "reps": reps, "wls": d["weights"] is not None,
-                       "yun": bool(norm)},
+            "config": {"workload": name, "n": d["n"], "k": K - 1, "K": K, "P": K * (K + 1) // 2 + K, "reps": reps,
+                       "wls": d["weights"] is not None, "yun": bool(norm),
+                       "rif_tau": args.rif_tau if args.rif_tau is not None else (0.5 if name.startswith("config4") else None)},
             "cpu_baseline": {"value": value, "unit": "reps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "reps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU restatement of the reference algorithm (oracle port), not the Rust binary"}
