@@ -131,7 +131,9 @@ ob_status ob_design_download(ob_ctx* ctx, const ob_design* d, double* Xa, double
  * Undoes a previous ob_design_apply_rif.  For ob_design_from_dense designs the "frame" is [y_a ; y_b]. */
 ob_status ob_design_update_outcome(ob_ctx* ctx, ob_design* d, const double* y_frame, int64_t n_frame);
 /* decompose_quantile pre-step (builder.rs:721-737 -> math/rif.rs:14-88): replaces each group's
- * outcome by its RIF at quantile tau, computed on the device, unweighted, per group. */
+ * outcome by its RIF at quantile tau, computed on the device, unweighted, per group.  The raw outcome is kept, so a
+ * quantile sweep (tau = 0.1, 0.5, 0.9 ...) packs once and calls apply_rif + ob_bootstrap_run per quantile: every call
+ * transforms the RAW outcome, never an earlier RIF. */
 ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau);
 
 /* ---- (2)-(5) bootstrap ---------------------------------------------------------------------*/

@@ -341,6 +341,7 @@ void ob_design_destroy(ob_design* d) {
         if (g.w) cudaFreeAsync(g.w, st);
         if (g.Xs) cudaFreeAsync(g.Xs, st);
         if (g.src) cudaFreeAsync(g.src, st);
+        if (g.y_raw) cudaFreeAsync(g.y_raw, st);
     }
     delete d;
 }
@@ -681,7 +682,10 @@ ob_status ob_design_update_outcome(ob_ctx* ctx, ob_design* d, const double* y_fr
         g_alloc_pack = true;
         DevBuf d_y(sizeof(double) * (size_t)std::max<int64_t>(n_frame, 1));
         OB_CUDA(cudaMemcpyAsync(d_y.p, y_frame, sizeof(double) * (size_t)n_frame, cudaMemcpyHostToDevice, ctx->stream));
-        for (int g = 0; g < 2; ++g) update_outcome_launch(d->g[g], d->K, d->ldx, d_y.as<double>(), ctx->stream);
+        for (int g = 0; g < 2; ++g) {
+            update_outcome_launch(d->g[g], d->K, d->ldx, d_y.as<double>(), ctx->stream);
+            if (d->g[g].y_raw) { cudaFreeAsync(d->g[g].y_raw, ctx->stream); d->g[g].y_raw = nullptr; }   // new raw outcome
+        }
         OB_CUDA(cudaStreamSynchronize(ctx->stream));
     });
 }
@@ -691,6 +695,12 @@ ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau) {
     return guarded(ctx, [&] {
         if (d->world > 1) fail(OB_ERR_UNSUPPORTED, "RIF pre-step on a row-sharded design (the quantile needs all rows of a group)");
         for (int g = 0; g < 2; ++g) {
+            GroupData& G = d->g[g];
+            if (!G.y_raw && G.n > 0) {   // first transform: keep the raw outcome, later quantiles start from it again
+                OB_CUDA(cudaMallocFromPoolAsync((void**)&G.y_raw, sizeof(double) * (size_t)G.n, ctx->pool_design, ctx->stream));
+                OB_CUDA(cudaMemcpy2DAsync(G.y_raw, sizeof(double), G.X + d->K, sizeof(double) * d->ldx, sizeof(double), (size_t)G.n,
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+            }
             const size_t sb = rif_scratch_bytes(d->g[g].n);
             DevBuf scratch(sb);
             rif_transform(d->g[g], d->K, d->ldx, tau, scratch.p, sb, ctx->stream);

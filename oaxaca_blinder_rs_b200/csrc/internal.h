@@ -83,6 +83,8 @@ struct GroupData {               // one group's packed design in HBM (the rows t
     double* w = nullptr;         // [n_pad] sample weights (0 on padding) or nullptr
     double* Xs = nullptr;        // weighted only: sqrt(w_i) * X[i][:] (ols.rs:68-78), the operand of the Gram contraction
     uint32_t* src = nullptr;     // [n] frame row each packed row came from (ob_design_update_outcome)
+    double* y_raw = nullptr;     // [n] the untransformed outcome, saved by the first ob_design_apply_rif so that further
+                                 // quantiles are computed from the raw y (a quantile sweep packs once)
     const double* gram_operand() const { return Xs ? Xs : X; }
 };
 

@@ -53,13 +53,14 @@ __device__ __forceinline__ void block_range(long long n, long long& lo, long lon
     lo = (long long)blockIdx.x * per; hi = min(lo + per, n);
 }
 
-__global__ void __launch_bounds__(RIF_THREADS) rif_extract_kernel(const double* __restrict__ X, long long n, int K, int ldx,
+// y_src / ystride: where the RAW outcome lives (the outcome column of X on the first transform, the saved copy after)
+__global__ void __launch_bounds__(RIF_THREADS) rif_extract_kernel(const double* __restrict__ y_src, long long ystride, long long n,
                                                                   unsigned long long* __restrict__ keys, RifState* s) {
     __shared__ double red[RIF_THREADS / 32];
     long long lo, hi; block_range(n, lo, hi);
     double sum = 0.0;
     for (long long i = lo + threadIdx.x; i < hi; i += RIF_THREADS) {
-        const double y = X[i * ldx + K];
+        const double y = y_src[i * ystride];
         keys[i] = to_key(y);
         sum += y;
     }
@@ -177,10 +178,11 @@ __global__ void rif_dens_final_kernel(RifState* s, long long n) {
 }
 
 __global__ void __launch_bounds__(RIF_THREADS) rif_apply_kernel(double* __restrict__ X, long long n, int K, int ldx,
+                                                                const double* __restrict__ y_src, long long ystride,
                                                                 const RifState* s, double tau) {
     const double q = s->q, dens = s->dens;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double y = X[i * ldx + K];
+        const double y = y_src[i * ystride];
         X[i * ldx + K] = q + (tau - (y <= q ? 1.0 : 0.0)) / dens;         // rif.rs:79-85
     }
 }
@@ -193,7 +195,9 @@ void rif_transform(const GroupData& g, int K, int ldx, double tau, void* d_scrat
     if (scratch_bytes < rif_scratch_bytes(n)) throw StatusError{OB_ERR_INVALID_ARG, "rif scratch too small"};
     unsigned long long* keys = static_cast<unsigned long long*>(d_scratch);
     RifState* s = reinterpret_cast<RifState*>(reinterpret_cast<char*>(d_scratch) + ((sizeof(unsigned long long) * (size_t)n + 255) / 256) * 256);
-    rif_extract_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(g.X, n, K, ldx, keys, s);
+    const double* y_src = g.y_raw ? g.y_raw : g.X + K;
+    const long long ystride = g.y_raw ? 1 : ldx;
+    rif_extract_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(y_src, ystride, n, keys, s);
     rif_init_kernel<<<1, 1, 0, st>>>(s, n, tau);
     rif_ss_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(keys, n, s);
     rif_sd_kernel<<<1, 1, 0, st>>>(s, n);
@@ -204,7 +208,7 @@ void rif_transform(const GroupData& g, int K, int ldx, double tau, void* d_scrat
     rif_params_kernel<<<1, 1, 0, st>>>(s, n, tau);
     rif_density_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(keys, n, s);
     rif_dens_final_kernel<<<1, 1, 0, st>>>(s, n);
-    rif_apply_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(g.X, n, K, ldx, s, tau);
+    rif_apply_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(g.X, n, K, ldx, y_src, ystride, s, tau);
     OB_CUDA(cudaGetLastError());
 }
 

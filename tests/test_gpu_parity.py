@@ -433,3 +433,22 @@ def test_reduction_beyond_16384_replicates(ob, orc, ctx):
     assert got["n_ok"] == ref["n_ok"] == int((status == 0).sum())
     for k, rk in (("std_err", "se"), ("p_value", "p"), ("ci_lower", "ci_lo"), ("ci_upper", "ci_hi"), ("t_stat", "t")):
         assert relerr(got[k], ref[rk]) <= RTOL, k
+
+
+def test_rif_quantile_sweep_on_one_design(ob, orc, ctx):
+    """BASELINE configs[3]: tau = 0.1 / 0.5 / 0.9 on the same frame.  apply_rif always transforms the RAW outcome, so one
+    packed design serves the whole sweep; update_outcome installs a new raw outcome."""
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(30_001, 3, weights=True, seed=8)
+    Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
+    des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+    for tau in (0.1, 0.5, 0.9, 0.5):
+        des.apply_rif(tau)
+        _, ga, _, _, gb, _ = des.download()
+        assert relerr(ga, orc.rif(ya, tau)) <= RTOL and relerr(gb, orc.rif(yb, tau)) <= RTOL, tau
+    y2 = 2.0 * d["outcome"] + 1.0
+    des.update_outcome(y2)
+    des.apply_rif(0.9)
+    _, ga, _, _, gb, _ = des.download()
+    assert relerr(ga, orc.rif(2.0 * ya + 1.0, 0.9)) <= RTOL
+    des.close()
