@@ -239,6 +239,13 @@ ob_status ob_design_set_row_shard(ob_design* d, int64_t n_a_global, int64_t n_b_
  * over PCIe.  The result equals ob_design_pack of the whole frame bit for bit. */
 ob_status ob_design_allgather_rows(ob_ctx* ctx, const ob_design* local_slice, ob_design** out);
 
+/* Host-only debugging aid (no device needed): the work-unit schedule of the Gram kernel for a problem shape -- out8
+ * receives up to cap rows of (cta, group, panel, column tile, row segment, pipeline stages, 8-slot groups, half-width);
+ * returns the total number of units or -1 on bad arguments.  The CPU tests use it to check that every
+ * (group, panel, tile, segment) is computed exactly once and that the CTAs get equal shares. */
+int64_t ob_debug_gram_schedule(int32_t K, int64_t n_a, int64_t n_b, int64_t slots, int32_t world, int32_t rank, int32_t grid,
+                               int64_t* out8, int64_t cap);
+
 /* Multiplicity counts of one replicate of the native stream (for the statistical validation
  * tests): counts_out [n] for group g (0 = A, 1 = B) of design d. */
 ob_status ob_debug_counts(ob_ctx* ctx, const ob_design* d, uint64_t seed, int64_t rep, int32_t group,

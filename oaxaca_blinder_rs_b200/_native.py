@@ -25,7 +25,8 @@ SYMBOLS = ["ob_abi_version", "ob_device_count", "ob_ctx_create", "ob_ctx_destroy
            "ob_comm_unique_id", "ob_comm_init_nccl", "ob_local_group_create", "ob_local_group_destroy",
            "ob_comm_init_local", "ob_comm_destroy", "ob_row_shard_plan", "ob_design_set_row_shard",
            "ob_design_pack_timings", "ob_design_allgather_rows", "ob_design_update_outcome",
-           "ob_ingest_begin", "ob_ingest_rows_kept", "ob_ingest_presence", "ob_ingest_finish", "ob_ingest_destroy"]
+           "ob_ingest_begin", "ob_ingest_rows_kept", "ob_ingest_presence", "ob_ingest_finish", "ob_ingest_destroy",
+           "ob_debug_gram_schedule"]
 
 
 class FrameView(C.Structure):
@@ -125,5 +126,8 @@ def lib() -> C.CDLL:
         L.ob_ingest_finish.argtypes = [C.c_void_p, C.c_void_p, _IP, C.POINTER(_IP), _IP, C.POINTER(C.c_void_p)]
         L.ob_ingest_destroy.argtypes = [C.c_void_p]
         L.ob_ingest_destroy.restype = None
+        L.ob_debug_gram_schedule.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                             C.POINTER(C.c_int64), C.c_int64]
+        L.ob_debug_gram_schedule.restype = C.c_int64
         _lib = L
     return _lib

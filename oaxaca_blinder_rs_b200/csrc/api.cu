@@ -1018,6 +1018,22 @@ ob_status ob_reduce_stats(ob_ctx* ctx, const double* rep_stats, const int32_t* r
     });
 }
 
+// Host-only: the unit schedule of the Gram kernel for a problem shape (no device needed; CPU tests).  out8 receives up to
+// cap rows of (cta, group, panel, tile, segment, stages, slot groups, half-width); returns the number of units.
+int64_t ob_debug_gram_schedule(int32_t K, int64_t n_a, int64_t n_b, int64_t slots, int32_t world, int32_t rank, int32_t grid,
+                               int64_t* out8, int64_t cap) {
+    if (K < 1 || n_a < 0 || n_b < 0 || slots < 1 || world < 1 || (world & (world - 1)) || world > MAX_SEGS || rank < 0 ||
+        rank >= world || grid < 1) return -1;
+    GroupData gd[2];
+    const int64_t ns[2] = {n_a, n_b};
+    for (int g = 0; g < 2; ++g) {
+        gd[g].shard = row_shard(ns[g], rank, world);
+        gd[g].n = gd[g].shard.n_local; gd[g].n_pad = pad_rows(gd[g].n);
+    }
+    const int64_t panels = (slots + BM - 1) / BM;
+    return gram_schedule_debug(K + 1, (int)panels, slots - (panels - 1) * BM, gd, grid, out8, cap);
+}
+
 ob_status ob_debug_counts(ob_ctx* ctx, const ob_design* d, uint64_t seed, int64_t rep, int32_t group,
                           uint16_t* counts_out) {
     if (!ctx || !d || !counts_out || group < 0 || group > 1 || rep < 0) return OB_ERR_INVALID_ARG;

@@ -304,7 +304,7 @@ struct GramUnit { const double* Xg; const void* Cg; double* out; int nstages, nt
 // Unit sequence of the warp-specialised kernel: four cost classes, each in (group, segment, panel, tile) order --
 // wide tiles of full panels, wide tiles of the tail panel, half-width tiles of full panels, half-width tiles of the
 // tail panel.  CTA b takes positions b, b + grid, ...: equal shares of every class, lockstep through consecutive units.
-__device__ __forceinline__ bool ws_decode(const GramKernelParams& p, long long i, int ldx, size_t count_bytes, GramUnit& u) {
+__host__ __device__ __forceinline__ bool ws_decode(const GramKernelParams& p, long long i, int ldx, size_t count_bytes, GramUnit& u) {
     const int pt = p.tail_mi < 16 ? 1 : 0, pf = p.panels - pt;            // tail / full panels of this batch
     const long long segs01 = (long long)p.segs[0] + p.segs[1];
     const long long n0 = segs01 * pf * p.nfull, n1 = segs01 * pt * p.nfull;
@@ -325,7 +325,7 @@ __device__ __forceinline__ bool ws_decode(const GramKernelParams& p, long long i
     const int segs = g ? p.segs[1] : p.segs[0], seg_rows = g ? p.seg_rows[1] : p.seg_rows[0];
     const long long n_pad = g ? p.n_pad[1] : p.n_pad[0];
     const long long row0 = (long long)seg * seg_rows;
-    const long long row1 = min(row0 + seg_rows, n_pad);
+    const long long row1 = row0 + seg_rows < n_pad ? row0 + seg_rows : n_pad;
     u.nstages = (int)((row1 - row0) / KT);
     u.nt = nt; u.half = p.has_half && nt == p.nfull;
     u.mi = panel >= pf ? p.tail_mi : 16;
@@ -665,6 +665,37 @@ void gram_combine_launch(const double* gathered, int world, const int ranks_with
     const unsigned blocks = (unsigned)std::min<long long>((2 * per2 + 255) / 256, 148 * 8);
     gram_combine_kernel<<<std::max(blocks, 1u), 256, 0, st>>>(gathered, world, ranks_with_rows[0], ranks_with_rows[1], per2, gram);
     OB_CUDA(cudaGetLastError());
+}
+
+// Host-side walk of the warp-specialised kernel's unit schedule (no device needed): for every CTA the units it takes,
+// as (group, panel, tile, segment, stages, mi, half).  Lets the CPU tests check that every unit is covered exactly once
+// and that CTAs get equal shares of every cost class, for any shape.
+int64_t gram_schedule_debug(int V, int panels, int64_t slots_last_panel, const GroupData gd[2], int grid, int64_t* out7, int64_t cap) {
+    GramPlan pl = gram_make_plan(V, panels, gd, 1, grid);
+    GramKernelParams p{};
+    for (int g = 0; g < 2; ++g) { p.n_pad[g] = pl.n_pad[g]; p.segs[g] = pl.segs[g]; p.seg_rows[g] = pl.seg_rows[g]; }
+    p.units0 = pl.units[0]; p.units_total = pl.units[0] + pl.units[1];
+    p.ldx = pl.ldx; p.panels = pl.panels; p.ntiles = pl.ntiles; p.nfull = pl.nfull; p.has_half = pl.has_half;
+    p.tail_mi = (int)std::min<int64_t>(16, ((slots_last_panel + 7) / 8 + 3) / 4 * 4);
+    p.partials = nullptr;
+    int64_t count = 0;
+    for (int b = 0; b < grid; ++b) {
+        GramUnit u;
+        for (long long i = b; ws_decode(p, i, pl.ldx, 1, u); i += grid) {
+            if (count < cap) {
+                // recover (g, panel, nt, seg) from the partial-tile index the unit writes to
+                const long long idx = (long long)(u.out - (double*)nullptr) / (BM * BN);
+                const int g = idx >= p.units0 ? 1 : 0;
+                const long long r = idx - (g ? p.units0 : 0);
+                const int segs = p.segs[g];
+                const long long sweep = r / p.ntiles;
+                int64_t* o = out7 + 8 * count;
+                o[0] = b; o[1] = g; o[2] = sweep / segs; o[3] = r % p.ntiles; o[4] = sweep % segs; o[5] = u.nstages; o[6] = u.mi; o[7] = u.half;
+            }
+            ++count;
+        }
+    }
+    return count;
 }
 
 }  // namespace ob

@@ -151,6 +151,7 @@ void gram_launch(const GramPlan& plan, const GramArgs& args, cudaStream_t st, cu
 void gram_combine_launch(const double* gathered, int world, const int ranks_with_rows[2], int64_t per_group_elems,
                          double* gram, cudaStream_t st);
 std::vector<uint16_t> gram_pair_table(int V, int ntiles);
+int64_t gram_schedule_debug(int V, int panels, int64_t slots_last_panel, const GroupData gd[2], int grid, int64_t* out8, int64_t cap);
 
 // ---- solve.cu ----
 struct SolveArgs {

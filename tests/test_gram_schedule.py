@@ -1,0 +1,76 @@
+"""The work-unit schedule of the warp-specialised Gram kernel, walked on the host (ob_debug_gram_schedule: no device):
+for every problem shape each (group, panel, column tile, row segment) must be computed exactly once, the row segments
+must tile the padded rows, CTAs must get equal shares (+-1) of every cost class, and a partly filled last panel must be
+the only one with fewer than 16 slot groups.  Also under row sharding (world > 1): the ranks' segments tile the group."""
+import ctypes as C
+from collections import Counter
+
+import numpy as np
+import pytest
+
+
+def schedule(K, na, nb, slots, world=1, rank=0, grid=148):
+    from oaxaca_blinder_rs_b200 import _native
+    _native.build()
+    L = _native.lib()
+    n = L.ob_debug_gram_schedule(K, na, nb, slots, world, rank, grid, None, 0)
+    assert n >= 0
+    out = np.zeros((max(n, 1), 8), dtype=np.int64)
+    m = L.ob_debug_gram_schedule(K, na, nb, slots, world, rank, grid, out.ctypes.data_as(C.POINTER(C.c_int64)), n)
+    assert m == n
+    return out[:n]
+
+
+SHAPES = [  # K, n_a, n_b, slots
+    (51, 5_000_000, 5_000_000, 2001),      # config 3
+    (21, 500_123, 499_877, 1001),          # config 2
+    (31, 2_500_000, 2_500_000, 1001),      # config 4: 4 wide tiles + a half tile
+    (17, 50_000_000, 50_000_000, 10001),   # config 5
+    (6, 5000, 5000, 501), (2, 3, 4, 1), (3, 40, 33, 129), (9, 100_000, 17, 128), (90, 70_000, 70_001, 257),
+]
+
+
+@pytest.mark.parametrize("K,na,nb,slots", SHAPES)
+def test_every_unit_once_and_balanced(K, na, nb, slots):
+    u = schedule(K, na, nb, slots)
+    V = K + 1
+    pairs = V * (V + 1) // 2
+    nfull, rem = divmod(pairs, 128)
+    has_half = 0
+    if rem > 64:
+        nfull += 1
+    elif rem > 0:
+        has_half = 1
+    ntiles = nfull + has_half
+    panels = -(-slots // 128)
+    keys = Counter(map(tuple, u[:, 1:5]))
+    assert all(c == 1 for c in keys.values())
+    segs = [int(u[u[:, 1] == g][:, 4].max()) + 1 if (u[:, 1] == g).any() else 0 for g in (0, 1)]
+    assert len(keys) == (segs[0] + segs[1]) * panels * ntiles
+    # segments tile the padded rows of each group: sum of stages * 32 over the segments of one (panel, tile)
+    for g, n in ((0, na), (1, nb)):
+        sel = u[(u[:, 1] == g) & (u[:, 2] == 0) & (u[:, 3] == 0)]
+        assert sel[:, 5].sum() * 32 == max(32, -(-n // 32) * 32) and (sel[:, 5] > 0).all()
+    # tail panel: only the last panel may have fewer slot groups, rounded up to 4 groups
+    last = slots - (panels - 1) * 128
+    mi = min(16, -(-(-(-last // 8)) // 4) * 4)
+    assert set(u[u[:, 2] == panels - 1][:, 6]) == {mi} and (panels == 1 or set(u[u[:, 2] < panels - 1][:, 6]) == {16})
+    assert set(u[u[:, 3] == nfull][:, 7]) <= {1} and set(u[u[:, 3] < nfull][:, 7]) <= {0}
+    # equal shares per cost class (half-width?, tail panel?) across CTAs
+    grid = min(148, len(u))
+    for half in (0, 1):
+        for tail in (0, 1):
+            cls = u[(u[:, 7] == half) & ((u[:, 6] < 16) == bool(tail))]
+            per = np.bincount(cls[:, 0], minlength=grid)
+            assert per.max() - per.min() <= 2, (half, tail, per.max(), per.min())     # +-1, plus the class boundary
+
+
+def test_row_shards_tile_the_group():
+    K, na, nb, slots = 17, 1_000_003, 999_999, 300
+    one = schedule(K, na, nb, slots)
+    tot = {g: one[(one[:, 1] == g) & (one[:, 2] == 0) & (one[:, 3] == 0)][:, 5].sum() for g in (0, 1)}
+    for world in (2, 4, 8):
+        parts = [schedule(K, na, nb, slots, world, r) for r in range(world)]
+        for g in (0, 1):
+            got = sum(p[(p[:, 1] == g) & (p[:, 2] == 0) & (p[:, 3] == 0)][:, 5].sum() for p in parts)
+            assert got == tot[g], (world, g)
