@@ -133,16 +133,21 @@ ob_status guarded(ob_ctx* ctx, F&& f) {
 // before the copies / pack kernels that follow on that stream
 // Design buffers come from the context's pack pool (stream-ordered): re-packing the same shapes reuses the
 // blocks instead of paying multi-GB cudaMalloc/cudaFree (random 100s-of-ms stalls) on every call.
-void alloc_group(ob_ctx* ctx, GroupData& g, int64_t n, int ldx, bool weighted) {
+// zero_all = false: the caller's pack kernel writes every column of every valid row (pad columns included), so only
+// the pad rows [n, n_pad) are cleared -- no multi-GB memset in front of the pack
+void alloc_group(ob_ctx* ctx, GroupData& g, int64_t n, int ldx, bool weighted, bool zero_all = true) {
     cudaStream_t st = ctx->stream;
     g.n = n; g.n_pad = pad_rows(n);
     g.shard = row_shard(n, 0, 1);
-    OB_CUDA(cudaMallocFromPoolAsync((void**)&g.X, sizeof(double) * (size_t)g.n_pad * ldx, ctx->pool_design, st));
-    OB_CUDA(cudaMemsetAsync(g.X, 0, sizeof(double) * (size_t)g.n_pad * ldx, st));
+    const size_t xbytes = sizeof(double) * (size_t)g.n_pad * ldx;
+    const size_t tail_off = zero_all ? 0 : sizeof(double) * (size_t)n * ldx;
+    OB_CUDA(cudaMallocFromPoolAsync((void**)&g.X, xbytes, ctx->pool_design, st));
+    OB_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(g.X) + tail_off, 0, xbytes - tail_off, st));
     if (weighted) {
         OB_CUDA(cudaMallocFromPoolAsync((void**)&g.w, sizeof(double) * (size_t)g.n_pad, ctx->pool_design, st));
         OB_CUDA(cudaMemsetAsync(g.w, 0, sizeof(double) * (size_t)g.n_pad, st));
-        OB_CUDA(cudaMallocFromPoolAsync((void**)&g.Xs, sizeof(double) * (size_t)g.n_pad * ldx, ctx->pool_design, st));
+        OB_CUDA(cudaMallocFromPoolAsync((void**)&g.Xs, xbytes, ctx->pool_design, st));
+        OB_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(g.Xs) + tail_off, 0, xbytes - tail_off, st));   // pad rows stay zero
     }
     OB_CUDA(cudaMallocFromPoolAsync((void**)&g.src, sizeof(uint32_t) * (size_t)g.n_pad, ctx->pool_design, st));
 }
@@ -463,10 +468,9 @@ std::unique_ptr<ob_design, void (*)(ob_design*)> pack_staged(ob_ctx* ctx, Staged
     d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = sf.n_cont; d->V = K + 1; d->ldx = pa.ldx;
     d->weighted = sf.weighted;
     d->n_frame = n;
-    alloc_group(ctx, d->g[0], tot[0], d->ldx, d->weighted);
-    alloc_group(ctx, d->g[1], tot[1], d->ldx, d->weighted);
-    pack_scatter(pa, d_bc.as<long long>(), d->g[0], d->g[1], d_flags.as<int>(), st);
-    for (int g = 0; g < 2; ++g) scale_rows_launch(d->g[g], d->ldx, st);
+    alloc_group(ctx, d->g[0], tot[0], d->ldx, d->weighted, false);
+    alloc_group(ctx, d->g[1], tot[1], d->ldx, d->weighted, false);
+    pack_scatter(pa, d_bc.as<long long>(), d->g[0], d->g[1], d_flags.as<int>(), st);   // writes X, w, src and the scaled copy
     t_pack.stop();
     OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
     OB_CUDA(cudaStreamSynchronize(st));

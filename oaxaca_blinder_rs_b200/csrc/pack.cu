@@ -74,16 +74,18 @@ struct PackKernelParams {
     const double* y; const double* w; const uint8_t* group;
     const long long* block_base;   // [nblocks][2] exclusive scan
     double* XA; double* XB; double* wA; double* wB;
+    double* XsA; double* XsB;      // sqrt(w)-scaled copies (weighted designs) or nullptr
     uint32_t* srcA; uint32_t* srcB;
     int* flags;
 };
 
 __global__ void __launch_bounds__(PK_THREADS) pack_scatter_kernel(const PackKernelParams p) {
-    extern __shared__ __align__(16) double tile[];      // [PK_ROWS][V + 1] (stride odd-ish padded)
+    extern __shared__ __align__(16) double tile[];      // [PK_ROWS][V | 1] (odd stride: conflict-free column writes)
     __shared__ int lrank[PK_ROWS];                      // local rank within the row's group, -1 = ignored row
     __shared__ uint8_t lgrp[PK_ROWS];
     __shared__ int srcA[PK_ROWS], srcB[PK_ROWS];
     __shared__ int cnt[2];
+    __shared__ const double* scont[96];                 // column base pointers: no dependent global load per element
     const int V = p.K + 1, ts = V | 1;
     const long long row0 = (long long)blockIdx.x * PK_ROWS;
     const int rows = (int)min((long long)PK_ROWS, p.n - row0);
@@ -98,6 +100,8 @@ __global__ void __launch_bounds__(PK_THREADS) pack_scatter_kernel(const PackKern
         const unsigned below = (1u << (tid & 31)) - 1u;
         lrank[tid] = g == 0 ? __popc(ma & below) : (g == 1 ? __popc(mb & below) : -1);
         if ((tid & 31) == 0) { wcount[tid >> 5][0] = __popc(ma); wcount[tid >> 5][1] = __popc(mb); }
+    } else if (tid - PK_ROWS < p.n_cont) {
+        scont[tid - PK_ROWS] = p.cont[tid - PK_ROWS];
     }
     __syncthreads();
     if (tid < PK_ROWS && lrank[tid] >= 0) {
@@ -112,43 +116,69 @@ __global__ void __launch_bounds__(PK_THREADS) pack_scatter_kernel(const PackKern
         cnt[0] = wcount[0][0] + wcount[1][0] + wcount[2][0] + wcount[3][0];
         cnt[1] = wcount[0][1] + wcount[1][1] + wcount[2][1] + wcount[3][1];
     }
-    // stage the block's rows: column-wise coalesced reads -> tile[row][col]
-    for (int e = tid; e < V * PK_ROWS; e += PK_THREADS) {
-        const int c = e / PK_ROWS, t = e - c * PK_ROWS;
-        double val = 0.0;
-        if (t < rows) {
-            const long long i = row0 + t;
-            if (c == 0) val = 1.0;                                       // __ob_intercept__ (builder.rs:330)
-            else if (c <= p.n_cont) val = p.cont[c - 1][i];
-            else if (c == p.K) val = p.y[i];
-            else {
-                int q = 0;
-                while (q + 1 < p.n_cat && c >= p.dummy_start[q + 1]) ++q;
-                const int code = p.cat[q][i];
-                if (code < 0 || code >= p.cat_levels[q]) atomicOr(&p.flags[1], 1);
-                val = (code == c - p.dummy_start[q] + 1) ? 1.0 : 0.0;    // builder.rs:402-409
+    // ---- stage the block's rows: column-wise coalesced reads -> tile[row][col] ----
+    // continuous predictors (the bulk of the bytes): 4 independent loads in flight per thread
+    {
+        const int lim = p.n_cont * PK_ROWS;
+        for (int base = tid; base < lim; base += PK_THREADS * 4) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = base + u * PK_THREADS;
+                const int c = e / PK_ROWS, t = e - c * PK_ROWS;
+                v[u] = (e < lim && t < rows) ? scont[c][row0 + t] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = base + u * PK_THREADS;
+                if (e < lim) { const int c = e / PK_ROWS, t = e - c * PK_ROWS; tile[t * ts + 1 + c] = v[u]; }
             }
         }
-        tile[t * ts + c] = val;
+    }
+    // intercept, outcome, dummies
+    for (int t = tid; t < PK_ROWS; t += PK_THREADS) {
+        tile[t * ts] = t < rows ? 1.0 : 0.0;                                  // __ob_intercept__ (builder.rs:330)
+        tile[t * ts + p.K] = t < rows ? p.y[row0 + t] : 0.0;
+    }
+    for (int e = tid; e < p.n_cat * PK_ROWS; e += PK_THREADS) {
+        const int q = e / PK_ROWS, t = e - q * PK_ROWS;
+        const int levels = p.cat_levels[q], start = p.dummy_start[q];
+        int code = 0;
+        if (t < rows) {
+            code = p.cat[q][row0 + t];
+            if (code < 0 || code >= levels) { atomicOr(&p.flags[1], 1); code = 0; }
+        }
+        for (int lv = 1; lv < levels; ++lv)                                   // builder.rs:402-409: level lv -> column start + lv - 1
+            tile[t * ts + start + lv - 1] = (t < rows && code == lv) ? 1.0 : 0.0;
     }
     __syncthreads();
     const long long baseA = p.block_base[2 * blockIdx.x], baseB = p.block_base[2 * blockIdx.x + 1];
-    // write out: consecutive threads -> consecutive columns of consecutive packed rows
-    for (int e = tid; e < cnt[0] * V; e += PK_THREADS) {
-        const int r = e / V, c = e - r * V;
-        p.XA[(baseA + r) * p.ldx + c] = tile[srcA[r] * ts + c];
+    // ---- write out: one warp per packed row, lanes over its V contiguous columns; the sqrt(w)-scaled copy
+    //      (ols.rs:68-78) is written in the same pass ----
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int g = 0; g < 2; ++g) {
+        double* X = g ? p.XB : p.XA;
+        double* Xs = g ? p.XsB : p.XsA;
+        double* W = g ? p.wB : p.wA;
+        uint32_t* SRC = g ? p.srcB : p.srcA;
+        const int* src = g ? srcB : srcA;
+        const long long base = g ? baseB : baseA;
+        for (int r = warp; r < cnt[g]; r += PK_THREADS / 32) {
+            const int t = src[r];
+            const double wv = p.w ? p.w[row0 + t] : 1.0;
+            const double sw = sqrt(wv);
+            double* xr = X + (base + r) * p.ldx;
+            for (int c = lane; c < p.ldx; c += 32) {          // pad columns [V, ldx) are written as zeros here
+                const double v = c < V ? tile[t * ts + c] : 0.0;
+                xr[c] = v;
+                if (Xs) Xs[(base + r) * p.ldx + c] = sw * v;
+            }
+            if (lane == 0) {
+                if (p.w) W[base + r] = wv;
+                SRC[base + r] = (uint32_t)(row0 + t);      // frame row of the packed row (ob_design_update_outcome)
+            }
+        }
     }
-    for (int e = tid; e < cnt[1] * V; e += PK_THREADS) {
-        const int r = e / V, c = e - r * V;
-        p.XB[(baseB + r) * p.ldx + c] = tile[srcB[r] * ts + c];
-    }
-    if (p.w) {
-        for (int r = tid; r < cnt[0]; r += PK_THREADS) p.wA[baseA + r] = p.w[row0 + srcA[r]];
-        for (int r = tid; r < cnt[1]; r += PK_THREADS) p.wB[baseB + r] = p.w[row0 + srcB[r]];
-    }
-    // frame row of every packed row: lets a caller refresh the outcome column without re-packing
-    for (int r = tid; r < cnt[0]; r += PK_THREADS) p.srcA[baseA + r] = (uint32_t)(row0 + srcA[r]);
-    for (int r = tid; r < cnt[1]; r += PK_THREADS) p.srcB[baseB + r] = (uint32_t)(row0 + srcB[r]);
 }
 
 int pack_num_blocks(int64_t n) { return (int)((n + PK_ROWS - 1) / PK_ROWS); }
@@ -170,7 +200,8 @@ void pack_scatter(const PackArgs& a, const long long* d_block_base, GroupData ga
     p.n = a.n; p.n_cont = a.n_cont; p.n_cat = a.n_cat; p.K = a.K; p.ldx = a.ldx;
     p.cont = a.d_cont; p.cat = a.d_cat; p.cat_levels = a.d_cat_levels; p.dummy_start = a.d_dummy_start;
     p.y = a.d_y; p.w = a.d_w; p.group = a.d_group; p.block_base = d_block_base;
-    p.XA = ga.X; p.XB = gb.X; p.wA = ga.w; p.wB = gb.w; p.srcA = ga.src; p.srcB = gb.src; p.flags = d_flags;
+    p.XA = ga.X; p.XB = gb.X; p.wA = ga.w; p.wB = gb.w; p.XsA = ga.Xs; p.XsB = gb.Xs;
+    p.srcA = ga.src; p.srcB = gb.src; p.flags = d_flags;
     const int V = a.K + 1;
     const size_t smem = sizeof(double) * (size_t)PK_ROWS * (V | 1);
     OB_CUDA(cudaFuncSetAttribute(pack_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
