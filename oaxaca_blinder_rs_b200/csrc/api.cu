@@ -884,9 +884,12 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                     const int64_t last = bslots - (pn - 1) * BM;
                     ga.tail_mi = (int)std::min<int64_t>(16, ((last + 7) / 8 + 3) / 4 * 4);
                 }
-                cudaEvent_t ev0, ev1;
-                OB_CUDA(cudaEventCreate(&ev0)); OB_CUDA(cudaEventCreate(&ev1));
-                gram_launch(plan, ga, st, ev0, ev1);
+                struct EventPair {   // RAII: an error thrown further down must not leak the events
+                    cudaEvent_t a = nullptr, b = nullptr;
+                    EventPair() { OB_CUDA(cudaEventCreate(&a)); OB_CUDA(cudaEventCreate(&b)); }
+                    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+                } ev;
+                gram_launch(plan, ga, st, ev.a, ev.b);
                 res->gpu_launches += 2;
                 t_gram.stop();
                 tr.mark("gram", st, true);
@@ -925,7 +928,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 OB_CUDA(cudaStreamSynchronize(st));
                 tr.mark("solve + flags", st, false);
                 t_counts.collect(); t_gram.collect(); t_solve.collect();
-                { float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1); res->ms_gram_kernel += ms; cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
+                { float ms = 0; cudaEventElapsedTime(&ms, ev.a, ev.b); res->ms_gram_kernel += ms; }
                 if (flags[2]) fail(OB_ERR_INVALID_ARG, "resample index out of range");
                 if (flags[0]) fail(OB_ERR_CUDA, "Poisson body overshot n (probability < 1e-15 per replicate); rerun with another seed");
                 if (flags[1]) {
