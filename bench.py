@@ -358,6 +358,10 @@ def main():
                     {"value": reps * args.steps / refresh, "unit": "reps/s", "h2d_bytes_per_step": int(8 * n),
                      "what": "ob_design_update_outcome (new y from pinned host memory, X resident) + bootstrap per step"},
                 "gpu_launches": int(launches),
+                "device_ms_per_step": float(np.mean(total_ms)),
+                "timing": "value: host clock between barrier + cuda synchronize brackets around exactly K steps, max over ranks "
+                          "(the library runs on its own stream, so torch.cuda.Event would not see it); device_ms_per_step and "
+                          "stage_ms: CUDA events recorded by the library on that stream",
                 "roofline": {"bound": "tensor", "kernel": "gram_ws_kernel (FP64 DMMA.8x8x4, warp-specialised)", "achieved": achieved,
                              "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS,
                              "frac_of_cublas_dgemm": achieved / FP64_CUBLAS_DGEMM_TFLOPS,

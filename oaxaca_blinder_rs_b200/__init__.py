@@ -7,7 +7,7 @@ include/obboot.h; this package is the host-side mirror of the reference's interf
 from .core import (REF_GROUP_A, REF_GROUP_B, REF_POOLED, REF_WEIGHTED, Context, Design, NormVar,
                    OaxacaError, bootstrap, num_stats, reduce_stats)
 
-from .builder import ComponentResult, OaxacaBlinder, OaxacaBuilder, OaxacaResults, ReferenceCoefficients
+from .builder import ComponentResult, OaxacaBlinder, OaxacaBuilder, OaxacaResults, ReferenceCoefficients, read_csv
 
 __all__ = ["ComponentResult", "OaxacaBlinder", "OaxacaBuilder", "OaxacaResults", "ReferenceCoefficients", "REF_GROUP_A", "REF_GROUP_B", "REF_POOLED", "REF_WEIGHTED", "Context", "Design", "NormVar",
-           "OaxacaError", "bootstrap", "num_stats", "reduce_stats"]
+           "OaxacaError", "bootstrap", "num_stats", "reduce_stats", "read_csv"]

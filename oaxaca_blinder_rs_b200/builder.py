@@ -95,6 +95,10 @@ def _columns(frame) -> dict:
 class _Frame:
     def __init__(self, frame):
         L = _blib()
+        if isinstance(frame, _Frame):                    # e.g. read_csv(): share the native frame
+            self._h, self._owner = frame._h, frame
+            return
+        self._owner = None
         self._h = C.c_void_p(L.ob_frame_new())
         for name, col in _columns(frame).items():
             vals = list(col) if not isinstance(col, np.ndarray) else col
@@ -117,10 +121,24 @@ class _Frame:
 
     def __del__(self):
         try:
-            if self._h:
+            if self._h and self._owner is None:
                 _blib().ob_frame_free(self._h)
         except Exception:
             pass
+
+
+def read_csv(path: str) -> _Frame:
+    """LazyCsvReader::new(path).with_has_header(true) (main.rs:161-165) through the native reader: a column is f64 if
+    every non-empty cell parses as a number, empty cells are nulls.  Pass the result as `dataframe`."""
+    L = _blib()
+    f = _Frame.__new__(_Frame)
+    f._owner = None
+    h, err = C.c_void_p(), C.create_string_buffer(512)
+    st = L.ob_frame_read_csv(str(path).encode(), C.byref(h), err, 512)
+    if st != 0:
+        raise OaxacaError(st, err.value.decode())
+    f._h = h
+    return f
 
 
 def _names(names: Iterable[str]):

@@ -2,6 +2,8 @@
 #include "builder.h"
 
 #include <unordered_map>
+#include <cstring>
+#include <charconv>
 
 #include <algorithm>
 #include <cmath>
@@ -47,39 +49,128 @@ static std::vector<std::string> split_csv_line(const std::string& line) {
     return out;
 }
 
+// One cell of a CSV line starting at p (end = end of line, exclusive).  Unquoted cells are returned as a view into the
+// buffer; quoted ones are unescaped into `tmp`.  Same grammar as split_csv_line: "" inside quotes is a quote, '\r' is dropped.
+static inline const char* next_cell(const char* p, const char* end, std::string& tmp, const char*& cb, const char*& ce) {
+    if (p < end && *p != '"') {                       // fast path: no quotes before the next comma
+        const char* q = p;
+        bool plain = true;
+        while (q < end && *q != ',') { if (*q == '"' || *q == '\r') plain = false; ++q; }
+        if (plain) { cb = p; ce = q; return q < end ? q + 1 : nullptr; }
+    }
+    tmp.clear();
+    bool quoted = false;
+    const char* q = p;
+    for (; q < end; ++q) {
+        const char ch = *q;
+        if (quoted) { if (ch == '"') { if (q + 1 < end && q[1] == '"') { tmp += '"'; ++q; } else quoted = false; } else tmp += ch; }
+        else if (ch == '"') quoted = true;
+        else if (ch == ',') break;
+        else if (ch != '\r') tmp += ch;
+    }
+    cb = tmp.data(); ce = tmp.data() + tmp.size();
+    return q < end ? q + 1 : nullptr;
+}
+
+// full-cell numeric parse with strtod's acceptance (from_chars first: no allocation, no locale)
+static inline bool parse_number(const char* b, const char* e, double& out) {
+    auto r = std::from_chars(b, e, out);
+    if (r.ec == std::errc() && r.ptr == e) return true;
+    std::string z(b, e);                              // rare: leading '+' / blanks, "inf", hex floats ...
+    char* endp = nullptr;
+    out = std::strtod(z.c_str(), &endp);
+    return endp != z.c_str() && *endp == '\0';
+}
+
 DataFrame DataFrame::read_csv(const std::string& path) {   // main.rs:161-165 (LazyCsvReader, has_header)
-    std::ifstream in(path);
-    if (!in) throw OaxacaError(OB_ERR_POLARS, "No such file or directory: " + path);
-    std::string line;
-    if (!std::getline(in, line)) throw OaxacaError(OB_ERR_POLARS, "empty CSV: " + path);
-    const std::vector<std::string> header = split_csv_line(line);
-    std::vector<std::vector<std::string>> cells(header.size());
-    while (std::getline(in, line)) {
-        if (line.empty() || line == "\r") continue;
-        std::vector<std::string> f = split_csv_line(line);
-        f.resize(header.size());
-        for (size_t c = 0; c < header.size(); ++c) cells[c].push_back(f[c]);
+    // Single pass over the file held in memory; numeric columns are parsed straight into doubles (no per-cell
+    // std::string), a column is f64 if every non-empty cell parses as a number (empty cell = null).
+    std::string buf;
+    {
+        std::ifstream in(path, std::ios::binary);
+        if (!in) throw OaxacaError(OB_ERR_POLARS, "No such file or directory: " + path);
+        in.seekg(0, std::ios::end);
+        const std::streamoff sz = in.tellg();
+        in.seekg(0, std::ios::beg);
+        buf.resize((size_t)std::max<std::streamoff>(sz, 0));
+        if (sz > 0) in.read(&buf[0], sz);
+    }
+    const char* p = buf.data();
+    const char* const fend = p + buf.size();
+    auto line_end = [&](const char* q) { const void* nl = memchr(q, '\n', (size_t)(fend - q)); return nl ? (const char*)nl : fend; };
+    if (p == fend) throw OaxacaError(OB_ERR_POLARS, "empty CSV: " + path);
+    const char* le = line_end(p);
+    const std::vector<std::string> header = split_csv_line(std::string(p, le));
+    const char* const data_begin = le < fend ? le + 1 : fend;
+    const size_t C = header.size();
+
+    enum Kind { UNKNOWN, NUM, STR };
+    struct ColState { Kind kind = UNKNOWN; std::vector<double> num; std::vector<std::string> str; std::vector<uint8_t> valid; bool has_null = false; };
+    std::vector<ColState> cols(C);
+    size_t rows = 0;
+    std::string tmp;
+
+    // a numeric column met a non-numeric cell at row `upto`: fetch its earlier cells as text again (rare)
+    auto refill_as_strings = [&](size_t c, size_t upto) {
+        ColState& cs = cols[c];
+        cs.str.assign(upto, std::string());
+        const char* q = data_begin; size_t r = 0; std::string t2;
+        while (q < fend && r < upto) {
+            const char* e = line_end(q);
+            const bool blank = (e == q) || (e - q == 1 && *q == '\r');
+            if (!blank) {
+                const char* cur = q; size_t ci = 0;
+                while (cur && ci <= c) {
+                    const char *cb, *ce;
+                    cur = next_cell(cur, e, t2, cb, ce);
+                    if (ci == c) cs.str[r].assign(cb, ce);
+                    ++ci;
+                }
+                ++r;
+            }
+            q = e < fend ? e + 1 : fend;
+        }
+        cs.num.clear(); cs.num.shrink_to_fit();
+        cs.kind = STR;
+    };
+
+    for (const char* q = data_begin; q < fend;) {
+        const char* e = line_end(q);
+        const bool blank = (e == q) || (e - q == 1 && *q == '\r');
+        if (!blank) {
+            const char* cur = q;
+            for (size_t c = 0; c < C; ++c) {
+                const char* cb = nullptr; const char* ce = nullptr;
+                if (cur) cur = next_cell(cur, e, tmp, cb, ce);            // short rows: missing cells are empty
+                ColState& cs = cols[c];
+                const bool empty = cb == ce;
+                cs.valid.push_back(empty ? 0 : 1);
+                cs.has_null |= empty;
+                if (cs.kind == STR) { cs.str.emplace_back(cb ? std::string(cb, ce) : std::string()); continue; }
+                double v = 0.0;
+                if (empty) { if (cs.kind == NUM) cs.num.push_back(0.0); continue; }
+                if (parse_number(cb, ce, v)) {
+                    if (cs.kind == UNKNOWN) { cs.num.assign(rows, 0.0); cs.kind = NUM; }
+                    cs.num.push_back(v);
+                } else {
+                    const std::string keep(cb, ce);                      // cb may point into tmp, which refill reuses? (it uses t2)
+                    if (cs.kind == NUM) refill_as_strings(c, rows);
+                    else { cs.str.assign(rows, std::string()); cs.kind = STR; }
+                    cs.str.push_back(keep);
+                }
+            }
+            ++rows;
+        }
+        q = e < fend ? e + 1 : fend;
     }
     DataFrame df;
-    for (size_t c = 0; c < header.size(); ++c) {
-        bool numeric = true, any = false;
-        for (const auto& s : cells[c]) {
-            if (s.empty()) continue;
-            any = true;
-            char* end = nullptr;
-            std::strtod(s.c_str(), &end);
-            if (end == s.c_str() || *end != '\0') { numeric = false; break; }
-        }
-        std::vector<uint8_t> valid(cells[c].size(), 1);
-        bool has_null = false;
-        for (size_t i = 0; i < cells[c].size(); ++i) if (cells[c][i].empty()) { valid[i] = 0; has_null = true; }
-        if (!has_null) valid.clear();
-        if (numeric && any) {
-            std::vector<double> v(cells[c].size(), 0.0);
-            for (size_t i = 0; i < v.size(); ++i) if (!cells[c][i].empty()) v[i] = std::strtod(cells[c][i].c_str(), nullptr);
-            df.add_f64(header[c], std::move(v), std::move(valid));
-        } else {
-            df.add_str(header[c], std::move(cells[c]), std::move(valid));
+    for (size_t c = 0; c < C; ++c) {
+        ColState& cs = cols[c];
+        if (!cs.has_null) cs.valid.clear();
+        if (cs.kind == NUM) df.add_f64(header[c], std::move(cs.num), std::move(cs.valid));
+        else {
+            if (cs.kind == UNKNOWN) cs.str.assign(rows, std::string());   // all cells empty: a string column of nulls
+            df.add_str(header[c], std::move(cs.str), std::move(cs.valid));
         }
     }
     return df;
@@ -496,13 +587,28 @@ std::string OaxacaBuilder::describe() const {
     size_t na = 0, nb = 0;
     for (uint8_t g : p.group) { na += g == 0; nb += g == 1; }
     auto ivec = [&](const std::vector<int32_t>& v) { os << '['; for (size_t i = 0; i < v.size(); ++i) { if (i) os << ','; os << v[i]; } os << ']'; };
-    auto svec = [&](const std::vector<std::string>& v) { os << '['; for (size_t i = 0; i < v.size(); ++i) { if (i) os << ','; os << '"' << v[i] << '"'; } os << ']'; };
+    auto svec = [&](const std::vector<std::string>& v) {
+        os << '[';
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (i) os << ',';
+            os << '"';
+            for (char ch : v[i]) { if (ch == '"' || ch == '\\') os << '\\'; os << ch; }   // JSON string escaping
+            os << '"';
+        }
+        os << ']';
+    };
     os << "{\"rows\":" << p.n << ",\"n_a\":" << na << ",\"n_b\":" << nb << ",\"names\":"; svec(p.names);
     os << ",\"base_names\":"; svec(p.base_names);
     os << ",\"cat_levels\":"; ivec(p.cat_levels);
     os << ",\"norm_m\":"; ivec(p.norm_m); os << ",\"norm_off\":"; ivec(p.norm_off);
     os << ",\"norm_idx\":"; ivec(p.norm_idx); os << ",\"norm_has_base\":"; ivec(p.norm_has_base);
-    os << ",\"group\":["; for (size_t i = 0; i < p.group.size(); ++i) { if (i) os << ','; os << (int)p.group[i]; } os << "]}";
+    os << ",\"group\":["; for (size_t i = 0; i < p.group.size(); ++i) { if (i) os << ','; os << (int)p.group[i]; } os << "]";
+    // sums of the kept rows of the outcome and of every continuous predictor (CSV / cleaning checks on the host)
+    os.precision(17);
+    auto dsum = [](const std::vector<double>& v) { long double t = 0; for (double x : v) t += x; return (double)t; };
+    os << ",\"outcome_sum\":" << dsum(p.y) << ",\"cont_sums\":[";
+    for (size_t c = 0; c < p.cont.size(); ++c) { if (c) os << ','; os << dsum(p.cont[c]); }
+    os << "]}";
     return os.str();
 }
 

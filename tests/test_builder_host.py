@@ -104,3 +104,50 @@ def test_builder_symbols_exported():
     assert declared == sorted(builder.BUILDER_SYMBOLS)
     for s in declared:
         assert hasattr(_native.lib(), s), s
+
+
+def test_csv_reader_matches_python_restatement(tmp_path):
+    """DataFrame::read_csv (single pass, numeric columns parsed straight to f64) against a restatement with the csv module:
+    quotes and escaped quotes, CRLF, blank lines, short rows, empty cells = nulls, '+1' / ' 2' / 'inf' accepted like strtod,
+    a column that turns out non-numeric late, an all-empty column."""
+    import csv
+    import io
+    import oaxaca_blinder_rs_b200 as ob
+    rng = np.random.default_rng(0)
+    n = 400
+    lines = ["wage,edu,exp,sector,gender,late,empty,\"quoted,name\""]
+    for i in range(n):
+        wage = f"{rng.normal(10, 2):.6f}"
+        edu = ["+12", " 13", "1.4e1", "15", ""][i % 5]                  # strtod-compatible spellings, a null
+        exp = f"{rng.uniform(0, 40):.3f}" if i % 37 else ""
+        sector = ['agri', '"ma""nu"', '"serv,ices"', 'tech'][i % 4]
+        gender = "M" if rng.random() < 0.5 else "F"
+        late = "7" if i < 300 else "seven"                              # numeric for 300 rows, then text
+        row = f"{wage},{edu},{exp},{sector},{gender},{late},,{i}"
+        if i % 50 == 49:
+            row = f"{wage},{edu},{exp},{sector},{gender}"                # short row: missing cells are nulls
+        lines.append(row + ("\r" if i % 3 == 0 else ""))
+        if i % 97 == 0:
+            lines.append("")                                             # blank line
+    path = tmp_path / "tricky.csv"
+    path.write_text("\n".join(lines) + "\n")
+    # python restatement
+    rows = [r for r in csv.reader(io.StringIO(path.read_text().replace("\r", ""))) if r]
+    hdr, rows = rows[0], [r + [""] * (8 - len(r)) for r in rows[1:]]
+    col = {h: [r[j] for r in rows] for j, h in enumerate(hdr)}
+    keep = [i for i in range(len(rows)) if all(col[c][i] != "" for c in ("wage", "gender", "edu", "exp", "sector", "late"))]
+    frame = ob.read_csv(str(path))
+    b = ob.OaxacaBuilder(frame, "wage", "gender", "F").predictors(["edu", "exp"]).categorical_predictors(["sector", "late"])
+    d = b.describe()
+    assert d["rows"] == len(keep)
+    assert d["names"] == ["__ob_intercept__", "edu", "exp", 'sector_ma"nu', "sector_serv,ices", "sector_tech", "late_seven"]
+    assert d["base_names"] == [] and d["cat_levels"] == [4, 2]
+    assert abs(d["outcome_sum"] - sum(float(col["wage"][i]) for i in keep)) < 1e-9
+    assert abs(d["cont_sums"][0] - sum(float(col["edu"][i]) for i in keep)) < 1e-9
+    assert abs(d["cont_sums"][1] - sum(float(col["exp"][i]) for i in keep)) < 1e-9
+    assert d["group"] == [0 if col["gender"][i] == "M" else 1 for i in keep]
+    # the all-empty column and the quoted header exist; using the empty one as a predictor drops every row
+    e = ob.OaxacaBuilder(frame, "wage", "gender", "F").predictors(["quoted,name"]).describe()
+    assert e["rows"] == len([i for i in range(len(rows)) if col["quoted,name"][i] != "" and col["wage"][i] != ""])
+    with pytest.raises(ob.OaxacaError):
+        ob.read_csv(str(tmp_path / "missing.csv"))
