@@ -238,14 +238,14 @@ ob_status ob_comm_unique_id(uint8_t* id128) {
 ob_status ob_comm_init_nccl(ob_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world) {
     if (!ctx || !id128) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
-        if (world < 1 || world > MAX_SEGS || (world & (world - 1)) || rank < 0 || rank >= world)
+        if (world < 1 || world > MAX_WORLD || (world & (world - 1)) || rank < 0 || rank >= world)
             fail(OB_ERR_INVALID_ARG, "world must be a power of two <= 64 and 0 <= rank < world");
         ctx->comm.reset(comm_create_nccl(id128, rank, world));
     });
 }
 
 ob_status ob_local_group_create(int32_t world, ob_local_group** out) {
-    if (!out || world < 1 || world > MAX_SEGS || (world & (world - 1))) return OB_ERR_INVALID_ARG;
+    if (!out || world < 1 || world > MAX_WORLD || (world & (world - 1))) return OB_ERR_INVALID_ARG;
     auto* g = new ob_local_group;
     g->g = local_group_create(world); g->world = world;
     *out = g;
@@ -274,7 +274,7 @@ void ob_comm_destroy(ob_ctx* ctx) {
 }
 
 ob_status ob_row_shard_plan(int64_t n_group, int32_t world, int32_t rank, int64_t* row_begin, int64_t* row_end) {
-    if (n_group < 0 || world < 1 || world > MAX_SEGS || (world & (world - 1)) || rank < 0 || rank >= world) return OB_ERR_INVALID_ARG;
+    if (n_group < 0 || world < 1 || world > MAX_WORLD || (world & (world - 1)) || rank < 0 || rank >= world) return OB_ERR_INVALID_ARG;
     const RowShard r = row_shard(n_group, rank, world);
     if (row_begin) *row_begin = r.row_begin;
     if (row_end) *row_end = r.row_begin + r.n_local;
@@ -282,7 +282,7 @@ ob_status ob_row_shard_plan(int64_t n_group, int32_t world, int32_t rank, int64_
 }
 
 ob_status ob_design_set_row_shard(ob_design* d, int64_t n_a_global, int64_t n_b_global, int32_t world, int32_t rank) {
-    if (!d || world < 1 || world > MAX_SEGS || (world & (world - 1)) || rank < 0 || rank >= world) return OB_ERR_INVALID_ARG;
+    if (!d || world < 1 || world > MAX_WORLD || (world & (world - 1)) || rank < 0 || rank >= world) return OB_ERR_INVALID_ARG;
     const RowShard ra = row_shard(n_a_global, rank, world), rb = row_shard(n_b_global, rank, world);
     if (ra.n_local != d->g[0].n || rb.n_local != d->g[1].n) return OB_ERR_INVALID_ARG;   // rows must follow ob_row_shard_plan
     d->g[0].shard = ra; d->g[1].shard = rb;
@@ -1029,7 +1029,7 @@ ob_status ob_reduce_stats(ob_ctx* ctx, const double* rep_stats, const int32_t* r
 // cap rows of (cta, group, panel, tile, segment, stages, slot groups, half-width); returns the number of units.
 int64_t ob_debug_gram_schedule(int32_t K, int64_t n_a, int64_t n_b, int64_t slots, int32_t world, int32_t rank, int32_t grid,
                                int64_t* out8, int64_t cap) {
-    if (K < 1 || n_a < 0 || n_b < 0 || slots < 1 || world < 1 || (world & (world - 1)) || world > MAX_SEGS || rank < 0 ||
+    if (K < 1 || n_a < 0 || n_b < 0 || slots < 1 || world < 1 || (world & (world - 1)) || world > MAX_WORLD || rank < 0 ||
         rank >= world || grid < 1) return -1;
     GroupData gd[2];
     const int64_t ns[2] = {n_a, n_b};

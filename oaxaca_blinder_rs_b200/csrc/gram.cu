@@ -14,7 +14,7 @@
 //   * CTA tile 128 slots x 128 columns, 8 warps (1 x 8), warp tile 128 x 16 = 16 x 2 DMMA sub-tiles,
 //     KT = 32 rows per stage, 3-4 stage TMA/mbarrier pipeline.  When the last column tile would be less
 //     than half full it is a half-width tile (128 x 64, warp tile 128 x 8): K = 17 costs 1.5 tiles, not 2.
-//   * Split-n: the rows of a group are cut into <= 64 fixed leaf segments whose size depends only on the
+//   * Split-n: the rows of a group are cut into <= 256 fixed leaf segments whose size depends only on the
 //     group's GLOBAL row count.  Work unit = (group, panel, segment, column tile): accumulated from zero,
 //     flushed as one partial tile.  A persistent grid of one CTA per SM walks cost-balanced contiguous
 //     unit ranges; gram_reduce sums a tile's leaf partials by a fixed aligned binary tree.  The summation
@@ -501,9 +501,23 @@ static size_t gram_ws_smem(int ldx, int count_bytes) {
 // and skipped.  The tree shape depends on the leaf indices only, so any aligned sub-range reduced on another GPU
 // (mode N) yields the very same intermediate sums.
 template <int LEN>
+__device__ __forceinline__ double2 tree_sum(const double2* __restrict__ base, size_t stride, int lo, int cnt);
+
+// a 64-leaf subtree as a real call: keeps the 128- and 256-leaf trees from being flattened into hundreds of loads in
+// flight at once (255 registers + spills); the tree shape is the same
+__device__ __noinline__ double2 tree_sum64_call(const double2* __restrict__ base, size_t stride, int lo, int cnt);
+
+template <int LEN>
 __device__ __forceinline__ double2 tree_sum(const double2* __restrict__ base, size_t stride, int lo, int cnt) {
     if constexpr (LEN == 1) {
         return base[(size_t)lo * stride];
+    } else if constexpr (LEN == 128) {
+        double2 a = tree_sum64_call(base, stride, lo, cnt);
+        if (lo + 64 < cnt) {
+            const double2 b = tree_sum64_call(base, stride, lo + 64, cnt);
+            a.x += b.x; a.y += b.y;
+        }
+        return a;
     } else {
         double2 a = tree_sum<LEN / 2>(base, stride, lo, cnt);
         if (lo + LEN / 2 < cnt) {
@@ -514,8 +528,14 @@ __device__ __forceinline__ double2 tree_sum(const double2* __restrict__ base, si
     }
 }
 
+__device__ __noinline__ double2 tree_sum64_call(const double2* __restrict__ base, size_t stride, int lo, int cnt) {
+    return tree_sum<64>(base, stride, lo, cnt);
+}
+
 __device__ __forceinline__ double2 tree_sum_span(const double2* __restrict__ base, size_t stride, int cnt, int span) {
     switch (span) {
+    case 256: return tree_sum<256>(base, stride, 0, cnt);
+    case 128: return tree_sum<128>(base, stride, 0, cnt);
     case 64: return tree_sum<64>(base, stride, 0, cnt);
     case 32: return tree_sum<32>(base, stride, 0, cnt);
     case 16: return tree_sum<16>(base, stride, 0, cnt);
@@ -633,7 +653,7 @@ void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEve
 #undef OB_GRAM_WS_CASE
         OB_CUDA(cudaGetLastError());
         if (ev_main_end) OB_CUDA(cudaEventRecord(ev_main_end, st));
-        dim3 rgw(2 * pl.panels * pl.ntiles, 4);
+        dim3 rgw(2 * pl.panels * pl.ntiles, 16);
         gram_reduce_kernel<<<rgw, 256, 0, st>>>(a.partials, pl.segs[0], pl.segs[1], a.gram, pl.panels, pl.ntiles, pl.leaf_span,
                                                 pl.Pld, pl.has_half);
         OB_CUDA(cudaGetLastError());
@@ -653,7 +673,7 @@ void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEve
 #undef OB_GRAM_CASE
     OB_CUDA(cudaGetLastError());
     if (ev_main_end) OB_CUDA(cudaEventRecord(ev_main_end, st));
-    dim3 rg(2 * pl.panels * pl.ntiles, 4);
+    dim3 rg(2 * pl.panels * pl.ntiles, 16);
     gram_reduce_kernel<<<rg, 256, 0, st>>>(a.partials, pl.segs[0], pl.segs[1], a.gram, pl.panels, pl.ntiles, pl.leaf_span,
                                            pl.Pld, pl.has_half);
     OB_CUDA(cudaGetLastError());

@@ -37,7 +37,7 @@ def test_abi_version_and_plan_tiles_rows():
     # large groups are spread evenly (within one leaf)
     cuts = [core.row_shard_plan(50_000_000, 8, r) for r in range(8)]
     sizes = [e - b for b, e in cuts]
-    assert max(sizes) - min(sizes) <= 50_000_000 // 64 + 64
+    assert max(sizes) - min(sizes) <= 50_000_000 // 64 + 64      # within one leaf (leaves are 1/256 of the group)
 
 
 def test_plan_rejects_bad_worlds():
