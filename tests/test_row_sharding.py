@@ -220,3 +220,32 @@ def test_allgather_rows_equals_whole_frame_pack(weighted):
         b, e = obd.shard_range(r, world, 40)
         assert _same(part["rep_stats"], ref_run["rep_stats"][b:e])
         assert _same(part["point_stats"], ref_run["point_stats"])
+
+
+def test_chunked_generator_shards_match_the_whole_frame():
+    """synth.make_wage_rows (the generator bench.py uses in mode N: every rank produces only its rows, chunk by chunk):
+    the ranks' rows, concatenated per group in rank order, are exactly the world = 1 frame."""
+    from oaxaca_blinder_rs_b200 import synth
+    kw = dict(n_cont=3, cat_levels=(4,), weights=True, chunk=1 << 14)
+    full = synth.make_wage_rows(150_001, **kw)
+    for world in (2, 8):
+        parts = [synth.make_wage_rows(150_001, rank=r, world=world, **kw) for r in range(world)]
+        assert sum(p["n"] for p in parts) == full["n"] == 150_001
+        for g in (0, 1):
+            sel = full["group"] == g
+            for key in ("outcome", "weights"):
+                np.testing.assert_array_equal(np.concatenate([p[key][p["group"] == g] for p in parts]), full[key][sel])
+            np.testing.assert_array_equal(np.concatenate([p["cont"][2][p["group"] == g] for p in parts]), full["cont"][2][sel])
+            np.testing.assert_array_equal(np.concatenate([p["cat_codes"][0][p["group"] == g] for p in parts]), full["cat_codes"][0][sel])
+        assert all(p["n_a_global"] == full["n_a_global"] and p["n_b_global"] == full["n_b_global"] for p in parts)
+
+
+def test_frame_slices_tile_the_frame():
+    from oaxaca_blinder_rs_b200 import distributed as obd, synth
+    d = synth.make_wage(10_007, 2, cat_levels=(3,), weights=True, seed=3)
+    for world in (1, 2, 3, 8):
+        sl = [obd.frame_slice(d, r, world) for r in range(world)]
+        assert sum(s["n"] for s in sl) == d["n"]
+        np.testing.assert_array_equal(np.concatenate([s["outcome"] for s in sl]), d["outcome"])
+        np.testing.assert_array_equal(np.concatenate([s["group"] for s in sl]), d["group"])
+        np.testing.assert_array_equal(np.concatenate([s["cat_codes"][0] for s in sl]), d["cat_codes"][0])
