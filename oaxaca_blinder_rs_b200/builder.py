@@ -88,7 +88,14 @@ def _columns(frame) -> dict:
     if hasattr(frame, "to_pydict"):                      # pyarrow.Table
         return frame.to_pydict()
     if hasattr(frame, "columns") and hasattr(frame, "__getitem__"):   # pandas.DataFrame
-        return {str(c): frame[c].tolist() for c in frame.columns}
+        out = {}
+        for c in frame.columns:
+            col = frame[c]
+            kind = getattr(getattr(col, "dtype", None), "kind", "O")
+            # numeric columns stay numpy arrays (NaN = null): no per-value Python objects for large frames
+            out[str(c)] = col.to_numpy(dtype=np.float64) if kind in "fiu" else \
+                [None if (v is None or (isinstance(v, float) and v != v)) else v for v in col.tolist()]
+        return out
     raise TypeError("dataframe must be a dict of columns, a pandas DataFrame or a pyarrow Table")
 
 
