@@ -38,9 +38,35 @@ WORKLOADS = {
     "probe_n1M_k50_B255": (1_000_000, 44, (4, 4), True, True, 255, 0),   # ncu-sized: two full panels
     "probe5_n20M_k16_B2000": (20_000_000, 16, (), False, False, 2000, 0),  # config-5 column shape (1 full + 1 half tile)
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE gram_kernel launch, from ncu captures of this same command
-# (profiles/r01_gram_dram_config3_v14.csv; one-pass bytes of X and C at config 3 are 24.2 GB)
-GRAM_DRAM_TRAFFIC = {("config3_n10M_k50_wls_yun_B2000", 1): 32628926208 + 3051690240}
+# roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE Gram launch, measured by ncu on THIS build of
+# the kernel: profiles/gram_traffic.json holds {workload, n_gpus, bytes, src_sha256, csv}; an entry counts only while the
+# hash of the kernel sources it was taken on equals the current sources -- otherwise the key is null, never stale.
+GRAM_SOURCES = ("oaxaca_blinder_rs_b200/csrc/gram.cu", "oaxaca_blinder_rs_b200/csrc/internal.h",
+                "oaxaca_blinder_rs_b200/csrc/common.cuh")
+
+
+def gram_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for f in GRAM_SOURCES:
+        with open(os.path.join(ROOT, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def measured_gram_traffic(name, world):
+    try:
+        with open(os.path.join(ROOT, "profiles", "gram_traffic.json")) as fh:
+            entries = json.load(fh)["entries"]
+    except (OSError, ValueError, KeyError):
+        return None, None
+    sha = gram_source_hash()
+    for e in entries:
+        if e.get("workload") == name and e.get("n_gpus") == world and e.get("src_sha256") == sha:
+            return int(e["bytes"]), e.get("csv")
+    return None, None
+
+
 HBM_PEAK_GBS = 6550.1            # MEASURED_PEAKS.json (driver-written copy bandwidth on this pool)
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool (profiles/r01_fp64_peaks.json): DMMA.8x8x4 issue peak
 FP64_CUBLAS_DGEMM_TFLOPS = 35.4  # measured on this pool (profiles/r01_dgemm_peak.json): cuBLAS DGEMM 8192^3
@@ -123,15 +149,65 @@ def make_data(name):
     return d, norm, reps, ref
 
 
-def cpu_baseline(d, norm, ref, threads, reps_cpu, rif_tau=None):
-    """Times the oracle port (reference-shaped arithmetic) on `threads` host threads over reps_cpu replicates."""
+def default_rif_tau(args, name):
+    return args.rif_tau if args.rif_tau is not None else (0.5 if name.startswith("config4") else None)
+
+
+def config_dict(name, world, shard_rows, rif_tau):
+    """`config` of the JSON line: identical for both arms (the driver compares them)."""
+    n, n_cont, cats, weights, normalize, reps, _ = WORKLOADS[name]
+    K = 1 + n_cont + sum(m - 1 for m in cats)
+    return {"workload": name, "n": n, "k": K - 1, "K": K, "P": K * (K + 1) // 2 + K, "reps": reps,
+            "wls": bool(weights), "yun": bool(normalize and cats), "rif_tau": rif_tau,
+            "parallelism": (f"row-shard x{world}" if shard_rows else f"replicate-shard x{world}"),
+            "l2": "inputs larger than L2 (design %.2f GB, multiplicities %.1f GB per GPU per step)"
+                  % (n * (K + 1) * 8 / 1e9 / (world if shard_rows else 1), n * (reps + 1) / world / 1e9)}
+
+
+def rows_sharded(args, name, world):
+    return world > 1 and (args.shard == "rows" or (args.shard == "auto" and name.startswith("config5")))
+
+
+README_SHAPE = dict(n=100_000, p=10, reps=500, published_s=3.11, source="/root/reference README.md:310-317 "
+                    "(\"100k rows x 10 predictors, 500 bootstrap reps: 3.11 s\"; hardware and core count not stated)")
+
+
+def readme_calibration_cpu(threads):
+    """The one shape the reference publishes a time for (n = 1e5, p = 10, B = 500: 3.11 s), run through the oracle port
+    in its reference-shaped mode on `threads` host threads: calibrates the port against the Rust binary's own number."""
+    from oracle import pyoracle as orc
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(README_SHAPE["n"], README_SHAPE["p"])
+    Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
+    spec = orc.Spec(K=Xa.shape[1], n_cont=README_SHAPE["p"], ref_kind=0, norm=[])
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        orc.run(spec, Xa, ya, wa, Xb, yb, wb, README_SHAPE["reps"], None, None, seed=1, nthreads=threads, precise=False,
+                want_rep=False)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"shape": "n=1e5, p=10, B=500, OLS", "port_seconds": best, "threads": threads,
+            "published_seconds": README_SHAPE["published_s"], "published_source": README_SHAPE["source"],
+            "port_over_published": best / README_SHAPE["published_s"]}
+
+
+def dense_for_cpu(d, rif_tau):
+    """Dense per-group matrices for the oracle port, built ONCE per run (the reference clones its frame once, too)."""
     from oracle import pyoracle as orc
     from oaxaca_blinder_rs_b200 import synth
     Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
     if rif_tau is not None:             # decompose_quantile: RIF outcome computed once per group (builder.rs:721-737)
         ya, yb = orc.rif(ya, rif_tau), orc.rif(yb, rif_tau)
-    K = Xa.shape[1]
-    spec = orc.Spec(K=K, n_cont=len(d["cont"]), ref_kind=ref, norm=[orc.NormVar(m, i) for m, i in norm])
+    return Xa, ya, wa, Xb, yb, wb
+
+
+def cpu_baseline(dense, n_cont, norm, ref, threads, reps_cpu):
+    """Times the oracle port (reference-shaped arithmetic) on `threads` host threads over reps_cpu replicates + the
+    point pass (reps_cpu + 1 passes, run concurrently)."""
+    from oracle import pyoracle as orc
+    Xa, ya, wa, Xb, yb, wb = dense
+    spec = orc.Spec(K=Xa.shape[1], n_cont=n_cont, ref_kind=ref, norm=[orc.NormVar(m, i) for m, i in norm])
     t0 = time.perf_counter()
     out = orc.run(spec, Xa, ya, wa, Xb, yb, wb, reps_cpu, None, None, seed=1, nthreads=threads, precise=False, want_rep=False)
     dt = time.perf_counter() - t0
@@ -157,25 +233,44 @@ def run_reference(args, name):
     K = 1 + len(d["cont"]) + sum(m - 1 for m in d["cat_levels"])
     cores, threads = host_threads_and_sample(d, K)
     reps_cpu = max(threads - 1, 1)          # + the point pass = `threads` passes, one per thread
+    rif_tau = default_rif_tau(args, name)
+    dense = dense_for_cpu(d, rif_tau)
+    n_cont = len(d["cont"])
+    del d
     vals = []
     for it in range(args.warmup + args.steps):
-        v, dt, _ = cpu_baseline(d, norm, ref, threads, reps_cpu,
-                                args.rif_tau if args.rif_tau is not None else (0.5 if name.startswith("config4") else None))
+        v, dt, _ = cpu_baseline(dense, n_cont, norm, ref, threads, reps_cpu)
         if it >= args.warmup:
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals])) * 1e3
     sample = f"{reps_cpu} replicates + point pass per step on {threads} OpenMP threads (of {cores} cores), full n"
+    world = max(args.gpus, 1)
     line = {"impl": "reference", "metric": "bootstrap_reps_per_sec", "value": value, "unit": "reps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "n": d["n"], "k": K - 1, "K": K, "P": K * (K + 1) // 2 + K, "reps": reps,
-                       "wls": d["weights"] is not None, "yun": bool(norm),
-                       "rif_tau": args.rif_tau if args.rif_tau is not None else (0.5 if name.startswith("config4") else None)},
+            "config": config_dict(name, world, rows_sharded(args, name, world), rif_tau),
             "cpu_baseline": {"value": value, "unit": "reps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "reps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "CPU restatement of the reference algorithm (oracle port), not the Rust binary"}
+            "readme_shape": readme_calibration_cpu(min(cores, 64)),
+            "note": "CPU restatement of the reference algorithm (oracle port: gather, sqrt(w) scaling, cache-blocked AVX2 "
+                    "X'X, Cholesky, residuals, inverse per replicate; OpenMP over replicates), not the Rust binary"}
     print(json.dumps(line), flush=True)
+
+
+def readme_shape_gpu(ob, ctx):
+    """Same README shape end to end on the GPU (host columns -> pack -> point + 500 replicates -> results), best of 3."""
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(README_SHAPE["n"], README_SHAPE["p"])
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+        ob.bootstrap(des, README_SHAPE["reps"], ref_kind=0, seed=1)
+        des.close()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best
 
 
 def main():
@@ -209,7 +304,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    shard_rows = world > 1 and (args.shard == "rows" or (args.shard == "auto" and name.startswith("config5")))
+    shard_rows = rows_sharded(args, name, world)
     ctx = ob.Context(local)
     if shard_rows:
         # mode N: this rank generates and holds only its rows; the library exchanges column sums and per-rank Gram
@@ -240,7 +335,7 @@ def main():
     if world > 1 and not shard_rows:
         h2d //= world                       # each rank uploads its frame slice only
 
-    rif_tau = args.rif_tau if args.rif_tau is not None else (0.5 if name.startswith("config4") else None)
+    rif_tau = default_rif_tau(args, name)
 
     def pack():
         if world > 1 and not shard_rows:
@@ -343,15 +438,12 @@ def main():
         flops, P = algorithmic_flops(n, K, reps)
         flops_rank = flops / world                        # replicates are sharded: per-launch algorithmic work
         g_ms = float(np.mean(gram_ms))
+        traffic, traffic_csv = measured_gram_traffic(name, world)
         achieved = flops_rank / (g_ms * 1e-3) / 1e12
         line = {"metric": "bootstrap_reps_per_sec", "value": reps * args.steps / dt, "unit": "reps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": name, "n": n, "k": K - 1, "K": K, "P": P, "reps": reps,
-                           "wls": d["weights"] is not None, "yun": bool(norm), "rif_tau": rif_tau,
-                           "parallelism": (f"row-shard x{world}" if shard_rows else f"replicate-shard x{world}"),
-                           "l2": "inputs larger than L2 (design %.2f GB, multiplicities %.1f GB per GPU per step)"
-                                 % (n * (K + 1) * 8 / 1e9 / (world if shard_rows else 1), n * (reps + 1) / world / 1e9)},
+                "config": config_dict(name, world, shard_rows, rif_tau),
                 "e2e": {"value": reps * args.steps / dt_e, "unit": "reps/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h)},
                 "e2e_outcome_refresh": None if not (refresh and world == 1) else
@@ -368,10 +460,10 @@ def main():
                              "peak_source": "measured on this pool: FP64 DMMA issue peak, profiles/r01_fp64_peaks.json "
                                             "(MEASURED_PEAKS.json has no fp64 entry); cuBLAS DGEMM 35.4",
                              "launch_ms": g_ms, "flop_per_launch": flops_rank,
-                             "traffic": GRAM_DRAM_TRAFFIC.get((name, world)),
-                             "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch of this "
-                                               "command (profiles/r01_gram_dram_config3_v14.csv)"
-                                               if (name, world) in GRAM_DRAM_TRAFFIC else None},
+                             "traffic": traffic,
+                             "traffic_source": None if traffic is None else
+                                 f"ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch of this command on this "
+                                 f"build of the kernel ({traffic_csv}; profiles/gram_traffic.json, keyed by the kernel-source hash)"},
                 "stage_ms": dict({k: float(v) for k, v in out["timings_ms"].items()},
                                  other=float(out["timings_ms"]["total"] - sum(out["timings_ms"][k] for k in
                                                                              ("counts", "gram", "solve", "reduce")))),
@@ -382,9 +474,13 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cores, threads = host_threads_and_sample(d, K)
             reps_cpu = max(threads - 1, 1)
-            v, cdt, _ = cpu_baseline(d, norm, ref, threads, reps_cpu, rif_tau)
+            dense = dense_for_cpu(d, rif_tau)
+            cpu_baseline(dense, len(d["cont"]), norm, ref, threads, reps_cpu)        # untimed: first-touch of the thread buffers
+            v, cdt, _ = cpu_baseline(dense, len(d["cont"]), norm, ref, threads, reps_cpu)
             line["cpu_baseline"] = {"value": v, "unit": "reps/s", "cores": threads, "kind": "port",
                                     "sample": f"{reps_cpu} replicates + point pass, full n, {cdt:.1f} s on {threads} of {cores} cores"}
+            line["readme_shape"] = readme_calibration_cpu(min(cores, 64))
+            line["readme_shape"]["gpu_seconds_e2e"] = readme_shape_gpu(ob, ctx)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -251,6 +251,14 @@ int64_t ob_debug_gram_schedule(int32_t K, int64_t n_a, int64_t n_b, int64_t slot
 ob_status ob_debug_counts(ob_ctx* ctx, const ob_design* d, uint64_t seed, int64_t rep, int32_t group,
                           uint16_t* counts_out);
 
+/* The multiplicity matrix ob_bootstrap_run builds from an explicit index stream (same kernel), read back for the
+ * bit-exactness tests: idx [reps x n_global] (host; global row positions within the group), counts_out
+ * [reps x n_local] (row-major by replicate; n_local = the rows of the group this design holds, all of them unless
+ * row-sharded), count_bits 8 or 16.  flags_out (may be NULL): bit 0 = a count saturated at the width, bit 1 = an
+ * index was >= n_global. */
+ob_status ob_debug_counts_from_indices(ob_ctx* ctx, const ob_design* d, int32_t group, const uint32_t* idx, int64_t reps,
+                                       int32_t count_bits, uint16_t* counts_out, int32_t* flags_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ SYMBOLS = ["ob_abi_version", "ob_device_count", "ob_ctx_create", "ob_ctx_destroy
            "ob_comm_init_local", "ob_comm_destroy", "ob_row_shard_plan", "ob_design_set_row_shard",
            "ob_design_pack_timings", "ob_design_allgather_rows", "ob_design_update_outcome",
            "ob_ingest_begin", "ob_ingest_rows_kept", "ob_ingest_presence", "ob_ingest_finish", "ob_ingest_destroy",
-           "ob_debug_gram_schedule"]
+           "ob_debug_gram_schedule", "ob_debug_counts_from_indices"]
 
 
 class FrameView(C.Structure):
@@ -68,7 +68,8 @@ class Result(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile libobboot.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "obboot.h")]
+    srcs = [os.path.join(dp, f) for dp, _, fs in os.walk(CSRC) for f in fs]
+    srcs += [os.path.join(_HERE, "..", "include", h) for h in ("obboot.h", "obboot_builder.h")]
     newest = max(os.path.getmtime(s) for s in srcs)
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
         subprocess.check_call(["make", "-C", CSRC, "-j8", "-s"])
@@ -129,5 +130,7 @@ def lib() -> C.CDLL:
         L.ob_debug_gram_schedule.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                              C.POINTER(C.c_int64), C.c_int64]
         L.ob_debug_gram_schedule.restype = C.c_int64
+        L.ob_debug_counts_from_indices.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, _U32P, C.c_int64, C.c_int32,
+                                                   C.POINTER(C.c_uint16), _IP]
         _lib = L
     return _lib

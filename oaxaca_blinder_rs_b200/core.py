@@ -209,6 +209,20 @@ class Design:
                                                out.ctypes.data_as(C.POINTER(C.c_uint16))))
         return out
 
+    def debug_counts_from_indices(self, idx, group: int, count_bits: int = 8):
+        """ob_debug_counts_from_indices: (counts [reps, n_local] uint16, flags) of an explicit index stream
+        idx [reps, n_global] through the production histogram kernel."""
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        n_loc = self.n_a if group == 0 else self.n_b
+        n_glob = self.n_a_global if group == 0 else self.n_b_global
+        assert idx.ndim == 2 and idx.shape[1] == n_glob
+        out = np.empty((idx.shape[0], n_loc), dtype=np.uint16)
+        flags = C.c_int32(0)
+        self.ctx.check(N.lib().ob_debug_counts_from_indices(self.ctx._h, self._h, group, idx.ctypes.data_as(N._U32P),
+                                                            idx.shape[0], count_bits,
+                                                            out.ctypes.data_as(C.POINTER(C.c_uint16)), C.byref(flags)))
+        return out, flags.value
+
     def close(self):
         if self._h:
             N.lib().ob_design_destroy(self._h)

@@ -1064,4 +1064,46 @@ ob_status ob_debug_counts(ob_ctx* ctx, const ob_design* d, uint64_t seed, int64_
     });
 }
 
+// The multiplicity matrix ob_bootstrap_run builds from an explicit index stream, read back (tests: np.bincount parity).
+ob_status ob_debug_counts_from_indices(ob_ctx* ctx, const ob_design* d, int32_t group, const uint32_t* idx, int64_t reps,
+                                       int32_t count_bits, uint16_t* counts_out, int32_t* flags_out) {
+    if (!ctx || !d || !counts_out || group < 0 || group > 1 || reps < 0 || (reps && !idx) || (count_bits != 8 && count_bits != 16))
+        return OB_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        cudaStream_t st = ctx->stream;
+        const GroupData& G = d->g[group];
+        const int cb = count_bits / 8;
+        const int64_t slots = 1 + reps, panels = (slots + BM - 1) / BM;
+        const int64_t n_glob = G.shard.n_global;
+        DevBuf d_C((size_t)panels * G.n_pad * BM * cb), d_flags(sizeof(int) * 4);
+        DevBuf d_idx(sizeof(uint32_t) * (size_t)std::max<int64_t>(reps * n_glob, 1));
+        OB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * 4, st));
+        if (reps) OB_CUDA(cudaMemcpyAsync(d_idx.p, idx, sizeof(uint32_t) * (size_t)reps * n_glob, cudaMemcpyHostToDevice, st));
+        CountsArgs ca;
+        ca.C = d_C.p; ca.count_bytes = cb; ca.n = G.n; ca.n_pad = G.n_pad; ca.panels = (int)panels; ca.slots = slots;
+        ca.first_slot = 1; ca.rep0 = -1; ca.group = group; ca.seed = 0;
+        ca.n_global = n_glob; ca.row_begin = G.shard.row_begin;
+        counts_from_indices(ca, d_idx.as<uint32_t>(), d_flags.as<int>(), st);   // the production kernel
+        std::vector<uint8_t> h((size_t)panels * G.n_pad * BM * cb);
+        int flags[4];
+        OB_CUDA(cudaMemcpyAsync(h.data(), d_C.p, h.size(), cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        for (int64_t r = 0; r < reps; ++r) {
+            const int64_t slot = 1 + r, panel = slot / BM, col = slot % BM;
+            for (int64_t i = 0; i < G.n; ++i) {
+                const size_t e = (size_t)(panel * G.n_pad + i) * BM + col;
+                counts_out[r * G.n + i] = cb == 1 ? (uint16_t)h[e] : reinterpret_cast<const uint16_t*>(h.data())[e];
+            }
+        }
+        // the point-estimate slot must hold exactly one of every valid row and nothing on the padding
+        for (int64_t i = 0; i < G.n_pad; ++i) {
+            const size_t e = (size_t)i * BM;
+            const unsigned v = cb == 1 ? h[e] : reinterpret_cast<const uint16_t*>(h.data())[e];
+            if (v != (i < G.n ? 1u : 0u)) fail(OB_ERR_CUDA, "point-estimate slot of the multiplicity matrix is not all ones");
+        }
+        if (flags_out) *flags_out = (flags[1] ? 1 : 0) | (flags[2] ? 2 : 0);   // 1 = a count saturated, 2 = index out of range
+    });
+}
+
 }  // extern "C"

@@ -4,8 +4,9 @@
  * Citations are file:line under /root/reference/oaxaca_blinder/src/.
  *
  * Two arithmetic modes:
- *   precise = 1  X'WX and X'Wy are accumulated in long double -> the oracle is the more accurate
- *                side of every GPU-vs-oracle comparison (checker mode).
+ *   precise = 1  X'WX and X'Wy are accumulated in double-double (exact products, compensated sums;
+ *                ~106 bits) -> the oracle is the more accurate side of every GPU-vs-oracle
+ *                comparison (checker mode).
  *   precise = 0  plain double, same algorithmic steps as the reference incl. the work it throws
  *                away per replicate (y_hat, residuals, (X'X)^-1; ols.rs:118-137) -> the CPU
  *                baseline that bench.py times.
@@ -90,6 +91,74 @@ static double chol_inverse_trace(const ld* L, int K) {
     return (double)tr;
 }
 
+/* ---- baseline-mode X'X and X'y (ols.rs:80-81, :88-89) --------------------------------------
+ * nalgebra's `x.transpose() * x` dispatches to the matrixmultiply crate: a cache-blocked,
+ * register-tiled SIMD dgemm (packed panels, 4 x 12-ish micro-kernel on AVX2/FMA), computing the
+ * FULL K x K product -- it does not know the result is symmetric.  This restates that algorithm
+ * shape: row blocks of X are packed into a zero-padded panel, and a 4 x 12 FMA micro-kernel
+ * (12 ymm accumulators) sweeps every (j-block, l-block) of the full product.  Plain double
+ * throughout, like the reference. */
+#if defined(__AVX2__) && defined(__FMA__)
+#include <immintrin.h>
+#define GB_KC 128
+static void gram_blocked(const double* X, const double* y, int64_t n, int K, double* G, double* r) {
+    const int Kj = (K + 3) / 4 * 4, Kl = (K + 11) / 12 * 12, ld = Kl;
+    double* P = (double*)aligned_alloc(64, sizeof(double) * (size_t)GB_KC * ld);
+    double* Gp = (double*)aligned_alloc(64, sizeof(double) * (size_t)Kj * Kl);
+    memset(Gp, 0, sizeof(double) * (size_t)Kj * Kl);
+    memset(P, 0, sizeof(double) * (size_t)GB_KC * ld);
+    for (int64_t i0 = 0; i0 < n; i0 += GB_KC) {
+        const int kc = (int)((n - i0 < GB_KC) ? n - i0 : GB_KC);
+        for (int k = 0; k < kc; ++k) memcpy(P + (size_t)k * ld, X + (i0 + k) * K, sizeof(double) * (size_t)K);   /* pack */
+        for (int jb = 0; jb < Kj; jb += 4) {
+            for (int lb = 0; lb < Kl; lb += 12) {
+                __m256d c00 = _mm256_setzero_pd(), c01 = c00, c02 = c00, c10 = c00, c11 = c00, c12 = c00;
+                __m256d c20 = c00, c21 = c00, c22 = c00, c30 = c00, c31 = c00, c32 = c00;
+                const double* pk = P;
+                for (int k = 0; k < kc; ++k, pk += ld) {
+                    const __m256d b0 = _mm256_load_pd(pk + lb), b1 = _mm256_load_pd(pk + lb + 4), b2 = _mm256_load_pd(pk + lb + 8);
+                    __m256d a = _mm256_broadcast_sd(pk + jb);
+                    c00 = _mm256_fmadd_pd(a, b0, c00); c01 = _mm256_fmadd_pd(a, b1, c01); c02 = _mm256_fmadd_pd(a, b2, c02);
+                    a = _mm256_broadcast_sd(pk + jb + 1);
+                    c10 = _mm256_fmadd_pd(a, b0, c10); c11 = _mm256_fmadd_pd(a, b1, c11); c12 = _mm256_fmadd_pd(a, b2, c12);
+                    a = _mm256_broadcast_sd(pk + jb + 2);
+                    c20 = _mm256_fmadd_pd(a, b0, c20); c21 = _mm256_fmadd_pd(a, b1, c21); c22 = _mm256_fmadd_pd(a, b2, c22);
+                    a = _mm256_broadcast_sd(pk + jb + 3);
+                    c30 = _mm256_fmadd_pd(a, b0, c30); c31 = _mm256_fmadd_pd(a, b1, c31); c32 = _mm256_fmadd_pd(a, b2, c32);
+                }
+                double* g = Gp + (size_t)jb * Kl + lb;
+#define GB_ACC(row, v0, v1, v2)                                                                  \
+    _mm256_store_pd(g + (row) * Kl, _mm256_add_pd(_mm256_load_pd(g + (row) * Kl), v0));            \
+    _mm256_store_pd(g + (row) * Kl + 4, _mm256_add_pd(_mm256_load_pd(g + (row) * Kl + 4), v1));    \
+    _mm256_store_pd(g + (row) * Kl + 8, _mm256_add_pd(_mm256_load_pd(g + (row) * Kl + 8), v2));
+                GB_ACC(0, c00, c01, c02) GB_ACC(1, c10, c11, c12) GB_ACC(2, c20, c21, c22) GB_ACC(3, c30, c31, c32)
+#undef GB_ACC
+            }
+        }
+        /* X'y: gemv over the packed block */
+        for (int k = 0; k < kc; ++k) {
+            const double yk = y[i0 + k];
+            const double* pk = P + (size_t)k * ld;
+            for (int j = 0; j < K; ++j) r[j] += pk[j] * yk;
+        }
+    }
+    for (int j = 0; j < K; ++j)
+        for (int l = 0; l < K; ++l) G[j * K + l] = Gp[(size_t)j * Kl + l];
+    free(P); free(Gp);
+}
+#else
+static void gram_blocked(const double* X, const double* y, int64_t n, int K, double* G, double* r) {
+    for (int64_t i = 0; i < n; ++i) {
+        const double* xi = X + i * K;
+        for (int j = 0; j < K; ++j) {
+            const double a = xi[j];
+            for (int l = 0; l < K; ++l) G[j * K + l] += a * xi[l];
+            r[j] += a * y[i];
+        }
+    }
+}
+#endif
+
 int orc_ols(const double* y, const double* X, const double* w, int64_t n, int32_t K,
             int precise, double* beta, double* resid) {
     if (w) { /* ols.rs:60-66 */
@@ -99,22 +168,44 @@ int orc_ols(const double* y, const double* X, const double* w, int64_t n, int32_
     ld* G = (ld*)calloc((size_t)K * K, sizeof(ld));
     ld* r = (ld*)calloc((size_t)K, sizeof(ld));
     if (precise) {
-        /* ols.rs:68-81 / :88-89 with the products formed as in the reference
-         * ((sqrt(w) x_j)(sqrt(w) x_l)) but summed in long double */
-        ld* xr = (ld*)malloc(sizeof(ld) * (size_t)K);
+        /* ols.rs:68-81 / :88-89 with the products formed as in the reference ((sqrt(w) x_j)(sqrt(w) x_l), each factor
+         * rounded to double first) but every product taken exactly (FMA two-product) and summed in double-double
+         * (two-sum): ~106 significant bits, i.e. more than long double, and vectorisable -- a 10M-row pass takes seconds
+         * instead of minutes, so the full-size parity tests can run the checker on the BASELINE shapes. */
+        const int Kp = (K + 3) / 4 * 4;
+        double* hi = (double*)aligned_alloc(64, sizeof(double) * (size_t)(K + 1) * Kp);
+        double* lo = (double*)aligned_alloc(64, sizeof(double) * (size_t)(K + 1) * Kp);
+        double* xr = (double*)aligned_alloc(64, sizeof(double) * (size_t)Kp);
+        memset(hi, 0, sizeof(double) * (size_t)(K + 1) * Kp);
+        memset(lo, 0, sizeof(double) * (size_t)(K + 1) * Kp);
+        memset(xr, 0, sizeof(double) * (size_t)Kp);
         for (int64_t i = 0; i < n; ++i) {
             const double* xi = X + i * K;
             const double sw = w ? sqrt(w[i]) : 1.0;
-            for (int j = 0; j < K; ++j) xr[j] = (ld)(w ? xi[j] * sw : xi[j]);
-            const ld yw = (ld)(w ? y[i] * sw : y[i]);
-            for (int j = 0; j < K; ++j) {
-                const ld a = xr[j];
-                ld* Gj = G + j * K;
-                for (int l = j; l < K; ++l) Gj[l] += a * xr[l];
-                r[j] += a * yw;
+            for (int j = 0; j < K; ++j) xr[j] = w ? xi[j] * sw : xi[j];
+            const double yw = w ? y[i] * sw : y[i];
+            for (int j = 0; j <= K; ++j) {      /* row K: the X'y products */
+                const double a = j < K ? xr[j] : yw;
+                double* restrict h = hi + (size_t)j * Kp;
+                double* restrict q = lo + (size_t)j * Kp;
+                const int l0 = j < K ? (j & ~3) : 0;   /* upper triangle, start rounded down to the vector width */
+                for (int l = l0; l < Kp; ++l) {
+                    const double b = xr[l];
+                    const double p = a * b;
+                    const double e = fma(a, b, -p);
+                    const double t = h[l] + p;
+                    const double bb = t - h[l];
+                    const double err = (h[l] - (t - bb)) + (p - bb);
+                    h[l] = t;
+                    q[l] += err + e;
+                }
             }
         }
-        free(xr);
+        for (int j = 0; j < K; ++j) {
+            for (int l = j; l < K; ++l) G[j * K + l] = (ld)hi[(size_t)j * Kp + l] + (ld)lo[(size_t)j * Kp + l];
+            r[j] = (ld)hi[(size_t)K * Kp + j] + (ld)lo[(size_t)K * Kp + j];
+        }
+        free(hi); free(lo); free(xr);
         for (int j = 0; j < K; ++j)
             for (int l = 0; l < j; ++l) G[j * K + l] = G[l * K + j];
     } else {
@@ -136,16 +227,7 @@ int orc_ols(const double* y, const double* X, const double* w, int64_t n, int32_
             Xs = Xw;
             ys = yw;
         }
-        for (int64_t i = 0; i < n; ++i) {
-            const double* xi = Xs + i * K;
-            const double yi = ys[i];
-            for (int j = 0; j < K; ++j) {
-                const double a = xi[j];
-                double* Gj = Gd + j * K;
-                for (int l = 0; l < K; ++l) Gj[l] += a * xi[l];
-                rd[j] += a * yi;
-            }
-        }
+        gram_blocked(Xs, ys, n, K, Gd, rd);   /* ols.rs:80-81 / :88-89: full K x K product, as nalgebra's gemm computes it */
         for (int j = 0; j < K * K; ++j) G[j] = Gd[j];
         for (int j = 0; j < K; ++j) r[j] = rd[j];
         free(Gd); free(rd); free(Xw); free(yw);
@@ -157,13 +239,24 @@ int orc_ols(const double* y, const double* X, const double* w, int64_t n, int32_
     for (int j = 0; j < K; ++j) beta[j] = (double)r[j];
     if (resid || !precise) { /* ols.rs:118-119 raw residuals y - X beta */
         double sse = 0.0;
-        for (int64_t i = 0; i < n; ++i) {
-            const double* xi = X + i * K;
-            ld yh = 0;
-            for (int j = 0; j < K; ++j) yh += (ld)xi[j] * (ld)beta[j];
-            const double e = (double)((ld)y[i] - yh);
-            if (resid) resid[i] = e;
-            sse += (w ? w[i] : 1.0) * e * e;
+        if (precise) {
+            for (int64_t i = 0; i < n; ++i) {
+                const double* xi = X + i * K;
+                ld yh = 0;
+                for (int j = 0; j < K; ++j) yh += (ld)xi[j] * (ld)beta[j];
+                const double e = (double)((ld)y[i] - yh);
+                if (resid) resid[i] = e;
+                sse += (w ? w[i] : 1.0) * e * e;
+            }
+        } else {   /* baseline: plain double gemv, like nalgebra's y - X * beta */
+            for (int64_t i = 0; i < n; ++i) {
+                const double* xi = X + i * K;
+                double yh = 0.0;
+                for (int j = 0; j < K; ++j) yh += xi[j] * beta[j];
+                const double e = y[i] - yh;
+                if (resid) resid[i] = e;
+                sse += (w ? w[i] : 1.0) * e * e;
+            }
         }
         if (!precise) { /* ols.rs:124-137, discarded by the caller exactly as in the reference */
             volatile double sink = sse / ((double)n - (double)K) * chol_inverse_trace(G, K);
@@ -493,9 +586,10 @@ int orc_run(const orc_spec* s,
             int64_t reps, const uint32_t* idx_a, const uint32_t* idx_b, uint64_t seed,
             int nthreads, int precise, orc_run_out* out) {
     const int K = s->K, S = orc_n_stats(s), D = K + orc_n_base(s);
-    /* point estimates: builder.rs:810-811; a failure here is a hard error */
-    int rc = orc_single_pass(s, Xa, ya, wa, na, Xb, yb, wb, nb, precise, &out->point);
-    if (rc != ORC_OK) return rc;
+    /* point estimates: builder.rs:810-811; a failure here is a hard error.  The pass runs as work item -1 of the
+     * replicate loop below (the point pass and the replicates are independent), so that a timed run of T-1 replicates
+     * on T threads costs one pass time, not two. */
+    int rc = ORC_OK;
     if (nthreads < 1) nthreads = 1;
 
 #pragma omp parallel num_threads(nthreads)
@@ -516,7 +610,8 @@ int orc_run(const orc_spec* s,
         po.beta_a = po.beta_star + K; po.beta_b = po.beta_a + K;
         double* st = (double*)malloc(sizeof(double) * (size_t)S);
 #pragma omp for schedule(dynamic, 1)
-        for (int64_t b = 0; b < reps; ++b) {
+        for (int64_t b = -1; b < reps; ++b) {
+            if (b < 0) { rc = orc_single_pass(s, Xa, ya, wa, na, Xb, yb, wb, nb, precise, &out->point); continue; }
             /* builder.rs:822-829: sample_n_literal(height, with_replacement) per group, vstack */
             const uint32_t* ja = idx_a ? idx_a + b * na : ia;
             const uint32_t* jb = idx_b ? idx_b + b * nb : ib;
@@ -551,6 +646,7 @@ int orc_run(const orc_spec* s,
         free(buf); free(st);
     }
 
+    if (rc != ORC_OK) return rc;
     if (out->rep_stats && out->rep_status && out->se) {
         double* pst = (double*)malloc(sizeof(double) * (size_t)S);
         orc_pass_to_stats(s, &out->point, pst);

@@ -1,6 +1,37 @@
 """Shared test helpers: host-side restatement of the frame -> design step for the small fixtures."""
 import numpy as np
 
+SMALL = 1e-6
+
+
+def relerr(a, b, small=SMALL):
+    """north_star's "within a relative 1e-10", read ELEMENT BY ELEMENT: max_ij |a_ij - b_ij| / den_ij with
+    den_ij = |b_ij| wherever |b_ij| >= small (1e-6), and the scale of the element's column, max_i |b_ij| (1-D arrays: of
+    the whole vector), only where the reference value itself is smaller than that -- an absolute floor is needed there
+    because such entries are differences of O(scale) terms (tolerance 1e-10 => floor 1e-10 x column scale).  NaN patterns must coincide."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    assert np.array_equal(nan_a, nan_b), "NaN pattern differs"
+    if a.size == 0 or nan_a.all():
+        return 0.0
+    absb = np.abs(np.where(nan_b, 0.0, b))
+    colscale = absb.max(axis=0, keepdims=True) if b.ndim >= 2 else absb.max()
+    # a column that is rounding noise throughout (every entry < 1e-6 of the array's largest value, e.g. the identically
+    # zero "explained" term of the intercept) is held to the array's scale instead of its own
+    colscale = np.maximum(colscale, small * absb.max())
+    den = np.where(absb >= small, absb, np.maximum(colscale, np.finfo(float).tiny))
+    err = np.abs(np.where(nan_a, 0.0, a) - np.where(nan_b, 0.0, b)) / den
+    return float(err.max())
+
+
+def relerr_to_scale(a, b, scale):
+    """|a - b| / scale for quantities that ARE differences of O(scale) numbers (residuals y - x.beta: scale = max |y|)."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    assert a.shape == b.shape
+    return float(np.max(np.abs(a - b)) / scale) if a.size else 0.0
+
+
 
 def fixture_design(fix, weighted=False):
     c = fix["columns"]

@@ -14,15 +14,7 @@ RTOL = 1e-10   # north_star: "within a relative 1e-10 (fp64 with a different sum
 REFS = {"A": 0, "B": 1, "pooled": 2, "weighted": 3}
 
 
-def relerr(a, b):
-    a, b = np.asarray(a, float), np.asarray(b, float)
-    assert a.shape == b.shape, (a.shape, b.shape)
-    nan_a, nan_b = np.isnan(a), np.isnan(b)
-    assert np.array_equal(nan_a, nan_b), "NaN pattern differs"
-    if a.size == 0 or nan_a.all():
-        return 0.0
-    scale = max(1.0, np.nanmax(np.abs(b)))
-    return float(np.nanmax(np.abs(a - b)) / scale)
+from helpers import relerr, relerr_to_scale  # noqa: E402  (elementwise-relative metric, tests/helpers.py)
 
 
 @pytest.fixture(scope="module")
@@ -60,9 +52,11 @@ def compare(gpu, ref, tol=RTOL, orc=None):
     p = ref["point"]
     assert abs(gpu["total_gap"] - p["total_gap"]) <= tol * max(1, abs(p["total_gap"]))
     for k_gpu, k_ref in (("point_stats", "stats"), ("xa_mean", "xa_mean"), ("xb_mean", "xb_mean"),
-                         ("beta_star", "beta_star"), ("beta_a", "beta_a"), ("beta_b", "beta_b"),
-                         ("residuals_b", "resid_b")):
+                         ("beta_star", "beta_star"), ("beta_a", "beta_a"), ("beta_b", "beta_b")):
         assert relerr(gpu[k_gpu], p[k_ref]) <= tol, k_gpu
+    # residuals y - x.beta are differences of O(|y|) numbers: their error is relative to that scale
+    yscale = max(1.0, float(np.max(np.abs(p["resid_b"]))), abs(p["total_gap"]))
+    assert relerr_to_scale(gpu["residuals_b"], p["resid_b"], yscale) <= tol, "residuals_b"
     well = ref["rep_min_pivot"] >= 1e-9
     np.testing.assert_array_equal(gpu["rep_status"][well], ref["rep_status"][well])
     assert relerr(gpu["rep_stats"][well], ref["rep_stats"][well]) <= tol
@@ -201,6 +195,48 @@ def test_count_width_and_saturation(ob, orc, ctx):
         ob.bootstrap(des, 3, idx_a=ia2, idx_b=ib2, count_bits=8)
     assert e.value.kind == "Unsupported"
     des.close()
+
+
+def test_index_stream_multiplicities_are_bit_exact(ob, orc, ctx):
+    """north_star's first correctness clause, asserted directly: fed an explicit resample index stream
+    (builder.rs:822-827), the multiplicity matrix the bootstrap contracts with equals np.bincount of that stream --
+    uint8 and uint16 widths, several panels (> 127 replicates), unsharded and on both halves of a 2-way row split."""
+    rng = np.random.default_rng(21)
+    na, nb = 5003, 4099                       # not multiples of the 32-row stage: padding rows must stay zero
+    X = np.c_[np.ones(na + nb), rng.normal(size=(na + nb, 2))]
+    y = rng.normal(size=na + nb)
+    des = ob.Design.from_dense(ctx, X[:na], y[:na], None, X[na:], y[na:], None, 2)
+    reps = 300                                # three panels of 128 slots (slot 0 = point estimate)
+    streams = {0: orc.index_stream(77, reps, 0, na), 1: orc.index_stream(77, reps, 1, nb)}
+    streams[0][5, :200] = 17                  # a heavy row: multiplicity ~ 200 still fits uint8
+    for g, n in ((0, na), (1, nb)):
+        want = np.stack([np.bincount(streams[g][r], minlength=n) for r in range(reps)])
+        for bits in (8, 16):
+            got, flags = des.debug_counts_from_indices(streams[g], g, count_bits=bits)
+            assert flags == 0
+            assert got.dtype == np.uint16 and np.array_equal(got, want), (g, bits)
+    # saturation is reported, not wrapped: 300 draws of one row at 8 bits
+    sat = streams[0][:2].copy(); sat[1, :300] = 3
+    got8, f8 = des.debug_counts_from_indices(sat, 0, count_bits=8)
+    got16, f16 = des.debug_counts_from_indices(sat, 0, count_bits=16)
+    assert f8 & 1 and f16 == 0 and np.array_equal(got16[1], np.bincount(sat[1], minlength=na))
+    # out-of-range index is flagged
+    bad = streams[1][:1].copy(); bad[0, 0] = nb
+    assert des.debug_counts_from_indices(bad, 1)[1] & 2
+    des.close()
+    # row-sharded: each shard histograms the GLOBAL stream and keeps its own rows
+    from oaxaca_blinder_rs_b200 import core
+    for world in (2, 4):
+        for rank in range(world):
+            a0, a1 = core.row_shard_plan(na, world, rank)
+            b0, b1 = core.row_shard_plan(nb, world, rank)
+            sh = ob.Design.from_dense(ctx, X[:na][a0:a1], y[:na][a0:a1], None, X[na:][b0:b1], y[na:][b0:b1], None, 2)
+            sh.set_row_shard(na, nb, world, rank)
+            for g, (lo, hi, n) in ((0, (a0, a1, na)), (1, (b0, b1, nb))):
+                got, flags = sh.debug_counts_from_indices(streams[g][:130], g)
+                want = np.stack([np.bincount(streams[g][r], minlength=n)[lo:hi] for r in range(130)])
+                assert flags == 0 and np.array_equal(got, want), (world, rank, g)
+            sh.close()
 
 
 def test_errors_match_reference_variants(ob, ctx):
