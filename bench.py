@@ -13,7 +13,8 @@ A "step" is one full bootstrap (point estimate + 2000 replicates + SE/CI reducti
 
 --impl reference times that CPU restatement on all host threads (the Rust reference cannot be built here:
 no cargo/rustc in the image, dependencies not vendored).  N > 1: one rank per GPU (torchrun), replicates
-sharded, one NCCL all-gather of the statistics block, reduction on every rank; total work fixed -> strong.
+sharded inside the library (ob_boot_opts.shard_replicates): one NCCL all-gather of the statistics block, device to
+device, reduction on every rank; total work fixed -> strong.
 """
 import argparse
 import json
@@ -80,7 +81,7 @@ def algorithmic_flops(n, K, reps):
 def hbm_stage_rooflines(d, K, reps, world, shard_rows, out, pack_ms):
     """The HBM-bound stages: algorithmic bytes / CUDA-event time against the measured copy bandwidth."""
     n_loc = d["n"]                                      # rows this rank holds
-    slots = (reps + 1) if (world == 1 or shard_rows) else (out["rep_stats"].shape[0] // world + 1)
+    slots = (reps + 1) if (world == 1 or shard_rows) else (-(-reps // world) + 1)
     gen_bytes = float(n_loc) * slots                    # uint8 multiplicity matrix written once
     t_gen = out["timings_ms"]["counts"] - out["timings_ms"].get("comm", 0.0)
     src = 8 * (len(d["cont"]) + 1 + (1 if d["weights"] is not None else 0)) + 4 * len(d["cat_codes"]) + 1
@@ -319,7 +320,7 @@ def main():
         d, norm, reps, ref = make_data(name)
         n = d["n"]
         if world > 1:
-            ctx.init_nccl(rank, world)       # mode R: only the upload uses it (frame slices gathered over NVLink)
+            ctx.init_nccl(rank, world)       # mode R: the statistics all-gather and the upload (frame slices over NVLink)
     K = 1 + len(d["cont"]) + sum(m - 1 for m in d["cat_levels"])
     normv = [ob.NormVar(m, i) for m, i in norm]
 
@@ -359,12 +360,17 @@ def main():
     res_buf = {}
 
     def step(design):
-        # OaxacaResults.residuals goes into a caller-owned buffer reused across steps (as a Rust caller would reuse a Vec)
-        rb = res_buf.setdefault(design.n_b, np.empty(design.n_b))
+        # OaxacaResults.residuals goes into a caller-owned, page-locked buffer reused across steps (ob_host_alloc: what a
+        # Rust caller would keep instead of a fresh Vec), so the 8 n_b byte D2H is one DMA on the library's side stream
+        if design.n_b not in res_buf:
+            res_buf[design.n_b] = ob.PinnedBuffer((design.n_b,))
+        rb = res_buf[design.n_b].array
         if world == 1 or shard_rows:
             return ob.bootstrap(design, reps, ref_kind=ref, norm=normv, seed=2026, residuals_out=rb)
-        return obd.bootstrap_sharded(design, reps, device=torch.device("cuda", local), ref_kind=ref, norm=normv, seed=2026,
-                                     residuals_out=rb if rank == 0 else None)
+        # mode R inside the library: replicate shard, NCCL all-gather of the statistics device to device, reduction on
+        # every rank (ob_boot_opts.shard_replicates); residuals are fetched once, on rank 0
+        return ob.bootstrap(design, reps, ref_kind=ref, norm=normv, seed=2026, shard_replicates=True,
+                            want_residuals=rank == 0, residuals_out=rb if rank == 0 else None)
 
     def sync():
         torch.cuda.synchronize()

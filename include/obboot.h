@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define OBBOOT_ABI_VERSION 2
+#define OBBOOT_ABI_VERSION 3
 
 /* ---- errors: OaxacaError variants (error.rs:6-19) + device errors ------------------------- */
 typedef enum ob_status {
@@ -48,6 +48,13 @@ typedef struct ob_design ob_design;  /* packed design of both groups, resident i
                                         created it: destroy designs before their context */
 
 ob_status ob_device_count(int32_t* n_out);
+/* Page-locked host memory for buffers the library copies to or from asynchronously (frame columns, residuals_b): DMA
+ * goes straight to the caller's buffer instead of through the driver's staging copy.  Plain malloc'ed memory works
+ * everywhere too, only slower.  ob_host_register pins an existing allocation (e.g. a Rust Vec) in place. */
+ob_status ob_host_alloc(size_t bytes, void** out);
+void ob_host_free(void* p);
+ob_status ob_host_register(void* p, size_t bytes);
+ob_status ob_host_unregister(void* p);
 ob_status ob_ctx_create(int32_t device, ob_ctx** out);
 void ob_ctx_destroy(ob_ctx* ctx);
 /* message of the last failing call on this context (owned by the context) */
@@ -158,6 +165,13 @@ typedef struct ob_boot_opts {
     int32_t skip_reduce;             /* 1: stop after per-replicate statistics (multi-GPU: gather first, then ob_reduce_stats) */
     int32_t count_bits;              /* 0 auto, 8 or 16: width of the multiplicity matrix */
     int64_t max_workspace_bytes;     /* 0 = default (60% of free HBM); bounds the multiplicity-matrix batch */
+    /* Mode R inside the library (replicate sharding): 1 = the context carries a communicator of `world`
+     * ranks (ob_comm_init_*), every rank holds the WHOLE design and makes this same call; the library computes the
+     * contiguous balanced shard of the global replicate ids that belongs to its rank (rep_begin / rep_end must be 0),
+     * all-gathers the replicate statistics device to device over the communicator (NVLink) and runs the reduction on
+     * every rank: identical results everywhere, bit-identical to one GPU.  rep_* outputs then cover ALL reps rows.
+     * An explicit index stream, if given, is the full [reps x n] stream on every rank. */
+    int32_t shard_replicates;
 } ob_boot_opts;
 
 /* Caller-allocated outputs (host memory).  D = K + n_base rows in each detailed list, where n_base =
@@ -204,9 +218,10 @@ ob_status ob_reduce_stats(ob_ctx* ctx, const double* rep_stats, const int32_t* r
                           double* ci_lower, double* ci_upper, double* t_stat);
 
 /* ---- multi-GPU ---------------------------------------------------------------------------------
- * Mode R (replicate sharding, the default): every GPU holds the whole design and runs ob_bootstrap_run on
- * its [rep_begin, rep_end) with skip_reduce = 1; the host gathers the replicate rows and calls
- * ob_reduce_stats.  No communicator is needed inside the library.
+ * Mode R (replicate sharding, the default): every GPU holds the whole design.  With a communicator attached to the
+ * context, ob_boot_opts.shard_replicates = 1 does everything inside the library: shard, device-to-device all-gather
+ * of the statistics over NVLink, reduction on every rank.  Without one, each GPU runs ob_bootstrap_run on its
+ * [rep_begin, rep_end) with skip_reduce = 1, the host gathers the replicate rows and calls ob_reduce_stats.
  *
  * Mode N (row sharding, for n too large for one HBM; BASELINE config 5): the rows of each group are cut
  * by ob_row_shard_plan into `world` contiguous ranges (world a power of two <= 64; the cut follows the
@@ -220,6 +235,9 @@ ob_status ob_reduce_stats(ob_ctx* ctx, const double* rep_stats, const int32_t* r
  * rank 0 creates the id, the host broadcasts its 128 bytes), or an in-process group for several contexts
  * (threads) of one process. */
 #define OB_COMM_ID_BYTES 128
+/* replicate shard [begin, end) of `rank` under shard_replicates (contiguous, balanced: the first reps % world ranks
+ * hold one replicate more) */
+ob_status ob_replicate_shard(int64_t reps, int32_t world, int32_t rank, int64_t* rep_begin, int64_t* rep_end);
 ob_status ob_comm_unique_id(uint8_t* id128);
 ob_status ob_comm_init_nccl(ob_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world);
 typedef struct ob_local_group ob_local_group;

@@ -26,7 +26,8 @@ SYMBOLS = ["ob_abi_version", "ob_device_count", "ob_ctx_create", "ob_ctx_destroy
            "ob_comm_init_local", "ob_comm_destroy", "ob_row_shard_plan", "ob_design_set_row_shard",
            "ob_design_pack_timings", "ob_design_allgather_rows", "ob_design_update_outcome",
            "ob_ingest_begin", "ob_ingest_rows_kept", "ob_ingest_presence", "ob_ingest_finish", "ob_ingest_destroy",
-           "ob_debug_gram_schedule", "ob_debug_counts_from_indices"]
+           "ob_debug_gram_schedule", "ob_debug_counts_from_indices", "ob_host_alloc", "ob_host_free",
+           "ob_host_register", "ob_host_unregister", "ob_replicate_shard"]
 
 
 class FrameView(C.Structure):
@@ -53,7 +54,8 @@ class BootOpts(C.Structure):
     _fields_ = [("ref_kind", C.c_int32), ("n_norm", C.c_int32), ("norm_m", _IP), ("norm_off", _IP),
                 ("norm_idx", _IP), ("norm_has_base", _IP), ("reps", C.c_int64), ("seed", C.c_uint64),
                 ("idx_a", _U32P), ("idx_b", _U32P), ("rep_begin", C.c_int64), ("rep_end", C.c_int64),
-                ("skip_reduce", C.c_int32), ("count_bits", C.c_int32), ("max_workspace_bytes", C.c_int64)]
+                ("skip_reduce", C.c_int32), ("count_bits", C.c_int32), ("max_workspace_bytes", C.c_int64),
+                ("shard_replicates", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -132,5 +134,11 @@ def lib() -> C.CDLL:
         L.ob_debug_gram_schedule.restype = C.c_int64
         L.ob_debug_counts_from_indices.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, _U32P, C.c_int64, C.c_int32,
                                                    C.POINTER(C.c_uint16), _IP]
+        L.ob_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        L.ob_host_free.argtypes = [C.c_void_p]
+        L.ob_host_free.restype = None
+        L.ob_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.ob_host_unregister.argtypes = [C.c_void_p]
+        L.ob_replicate_shard.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         _lib = L
     return _lib

@@ -93,8 +93,18 @@ def _columns(frame) -> dict:
             col = frame[c]
             kind = getattr(getattr(col, "dtype", None), "kind", "O")
             # numeric columns stay numpy arrays (NaN = null): no per-value Python objects for large frames
-            out[str(c)] = col.to_numpy(dtype=np.float64) if kind in "fiu" else \
-                [None if (v is None or (isinstance(v, float) and v != v)) else v for v in col.tolist()]
+            if kind in "fiu":
+                try:
+                    out[str(c)] = col.to_numpy(dtype=np.float64, na_value=np.nan)     # nullable Int64 / Float64 included
+                except TypeError:
+                    out[str(c)] = col.to_numpy(dtype=np.float64)
+                continue
+            # missing values as pandas itself sees them: None, NaN, pd.NA ('string' / nullable dtypes), NaT -- the
+            # reference drops such rows (clean_dataframe, builder.rs:760-784); str(pd.NA) must never become a level
+            mask = np.asarray(col.isna()) if hasattr(col, "isna") else None
+            vals = col.tolist()
+            out[str(c)] = [None if ((mask is not None and mask[i]) or v is None or (isinstance(v, float) and v != v)) else v
+                           for i, v in enumerate(vals)]
         return out
     raise TypeError("dataframe must be a dict of columns, a pandas DataFrame or a pyarrow Table")
 

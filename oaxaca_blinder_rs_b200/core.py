@@ -44,6 +44,7 @@ class Context:
             raise OaxacaError(st, f"ob_ctx_create(device={device}) failed: {N.STATUS_NAMES.get(st)} "
                                   f"(a B200 / sm_100a device is required; there is no CPU fallback)")
         self.device = device
+        self.comm_world, self.comm_rank = 1, 0      # set by init_nccl / init_local
 
     def check(self, st: int):
         if st != 0:
@@ -62,15 +63,18 @@ class Context:
         dist.broadcast_object_list(box, src=0, group=group)
         ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
         self.check(N.lib().ob_comm_init_nccl(self._h, ident, rank, world))
+        self.comm_world, self.comm_rank = world, rank
 
     def init_local(self, group: "LocalGroup", rank: int):
         """ob_comm_init_local: one of several contexts (threads) of this process."""
         self.check(N.lib().ob_comm_init_local(self._h, group._h, rank))
         self._local_group = group          # keep the group alive as long as the communicator
+        self.comm_world, self.comm_rank = group.world, rank
 
     def comm_destroy(self):
         if self._h:
             N.lib().ob_comm_destroy(self._h)
+        self.comm_world, self.comm_rank = 1, 0
 
     def close(self):
         if self._h:
@@ -91,7 +95,7 @@ class LocalGroup:
         self._h = C.c_void_p()
         st = N.lib().ob_local_group_create(world, C.byref(self._h))
         if st != 0:
-            raise OaxacaError(st, "ob_local_group_create: world must be a power of two <= 64")
+            raise OaxacaError(st, "ob_local_group_create: 1 <= world <= 64")
         self.world = world
 
     def __del__(self):
@@ -314,6 +318,40 @@ def ingest(ctx: Context, cont, cat, outcome, weights, group, reference_group: st
     return Design(ctx, dh), dict(rows_kept=int(kept.value), group_a=group_a, levels=levels)
 
 
+class PinnedBuffer:
+    """ob_host_alloc: page-locked host memory as a numpy array (.array); freed on close() / garbage collection."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self._p = C.c_void_p()
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        st = N.lib().ob_host_alloc(max(nbytes, 1), C.byref(self._p))
+        if st != 0:
+            raise OaxacaError(st, "ob_host_alloc failed")
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        if self._p:
+            self.array = None
+            N.lib().ob_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def replicate_shard(reps: int, world: int, rank: int):
+    """ob_replicate_shard: [begin, end) of the global replicate ids rank computes under shard_replicates."""
+    b, e = C.c_int64(), C.c_int64()
+    st = N.lib().ob_replicate_shard(reps, world, rank, C.byref(b), C.byref(e))
+    if st != 0:
+        raise OaxacaError(st, "ob_replicate_shard: bad arguments")
+    return b.value, e.value
+
+
 def num_stats(K: int, norm: Sequence[NormVar]) -> int:
     return 5 + 2 * (K + sum(1 for v in norm if v.has_base))
 
@@ -321,10 +359,14 @@ def num_stats(K: int, norm: Sequence[NormVar]) -> int:
 def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequence[NormVar] = (),
               seed: int = 0, idx_a=None, idx_b=None, rep_begin: int = 0, rep_end: int = 0,
               skip_reduce: bool = False, count_bits: int = 0, max_workspace_bytes: int = 0,
-              want_rep: bool = False, want_residuals: bool = True, residuals_out: Optional[np.ndarray] = None) -> dict:
+              want_rep: bool = False, want_residuals: bool = True, residuals_out: Optional[np.ndarray] = None,
+              shard_replicates: bool = False) -> dict:
     """ob_bootstrap_run.  Returns point estimates, per-statistic SE/p/CI/t and (optionally) replicate detail.
     residuals_out: optional preallocated float64 [n_b] buffer for OaxacaResults.residuals (reusing one across calls
-    avoids first-touch page faults on a fresh 8 n_b byte array during the device-to-host copy)."""
+    avoids first-touch page faults on a fresh 8 n_b byte array during the device-to-host copy; a page-locked one --
+    pinned_empty() -- takes the DMA directly).
+    shard_replicates: mode R inside the library -- the context carries a communicator (init_nccl / init_local), every
+    rank makes this same call on the whole design and gets the identical, gathered result (rep_* cover all reps)."""
     ctx, K = design.ctx, design.K
     norm = list(norm)
     S = num_stats(K, norm)
@@ -345,7 +387,8 @@ def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequ
         o.idx_a, o.idx_b = idx_a.ctypes.data_as(N._U32P), idx_b.ctypes.data_as(N._U32P)
     o.rep_begin, o.rep_end = rep_begin, rep_end
     o.skip_reduce, o.count_bits, o.max_workspace_bytes = int(skip_reduce), count_bits, max_workspace_bytes
-    nrep = (rep_end if rep_end > 0 else reps) - rep_begin
+    o.shard_replicates = int(shard_replicates)
+    nrep = (rep_end if rep_end > 0 else reps) - rep_begin     # shard_replicates: rep_* outputs cover all reps rows
 
     r = N.Result()
     a = dict(point_stats=np.empty(S), xa_mean=np.empty(K), xb_mean=np.empty(K), beta_star=np.empty(K),

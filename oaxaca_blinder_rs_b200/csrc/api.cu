@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <set>
 
 using namespace ob;
 
@@ -18,17 +20,24 @@ struct ob_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_side = nullptr;  // point-estimate residuals + their D2H, overlapped with the gather / reduction
     cudaMemPool_t pool = nullptr;   // stream-ordered workspace pool: freed blocks stay cached between calls
     cudaMemPool_t pool_pack = nullptr;   // separate pool for the pack's column staging, so its many small blocks do
                                          // not fragment the bootstrap workspace (20 GB count buffer at n = 1e7)
     cudaMemPool_t pool_design = nullptr; // packed designs (outlive a call): their own pool, so re-packing reuses the blocks
     std::unique_ptr<Comm> comm;          // row-sharding collectives (mode N); null = single GPU
     std::string err;
+    // designs created on this context and still alive.  ob_ctx_destroy releases their device memory (it dies with the
+    // context's pools anyway) and orphans them, so that an ob_design_destroy arriving late -- a garbage collector
+    // finalising objects in arbitrary order, possibly on another thread -- only frees the host struct.
+    std::mutex designs_mu;
+    std::set<ob_design*> designs;
 };
 
 struct ob_local_group { LocalGroup* g = nullptr; int world = 0; };
 
 struct ob_design {
+    ob_ctx* owner = nullptr;         // context that created the design; null once that context has been destroyed
     cudaStream_t stream = nullptr;   // owning context's stream: buffers come from its pack pool and are freed on it
     int device = 0;
     int K = 0, n_cont = 0, V = 0, ldx = 0;
@@ -152,6 +161,28 @@ void alloc_group(ob_ctx* ctx, GroupData& g, int64_t n, int ldx, bool weighted, b
     OB_CUDA(cudaMallocFromPoolAsync((void**)&g.src, sizeof(uint32_t) * (size_t)g.n_pad, ctx->pool_design, st));
 }
 
+void design_register(ob_ctx* ctx, ob_design* d) {
+    d->owner = ctx;
+    std::lock_guard<std::mutex> lk(ctx->designs_mu);
+    ctx->designs.insert(d);
+}
+
+void design_release_device(ob_design* d) {
+    cudaStream_t st = d->stream;
+    for (auto& g : d->g) {
+        if (g.X) cudaFreeAsync(g.X, st);
+        if (g.w) cudaFreeAsync(g.w, st);
+        if (g.Xs) cudaFreeAsync(g.Xs, st);
+        if (g.src) cudaFreeAsync(g.src, st);
+        if (g.y_raw) cudaFreeAsync(g.y_raw, st);
+        g.X = g.w = g.Xs = g.y_raw = nullptr; g.src = nullptr;
+    }
+}
+
+void design_alive(const ob_design* d) {
+    if (!d->owner) fail(OB_ERR_INVALID_ARG, "this design's context has been destroyed (designs die with their context)");
+}
+
 const char* status_text(int s) {
     switch (s) {
     case OB_ERR_INVALID_GROUP: return "Invalid group variable: No data in groups for weighted coefficients.";
@@ -190,6 +221,7 @@ ob_status ob_ctx_create(int32_t device, ob_ctx** out) {
         if (prop.major != 10) fail(OB_ERR_NO_DEVICE, "libobboot is built for sm_100a (B200) only");
         ctx->num_sms = prop.multiProcessorCount;
         OB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        OB_CUDA(cudaStreamCreateWithFlags(&ctx->stream_side, cudaStreamNonBlocking));
         cudaMemPoolProps props{};
         props.allocType = cudaMemAllocationTypePinned;
         props.handleTypes = cudaMemHandleTypeNone;
@@ -211,13 +243,52 @@ ob_status ob_ctx_create(int32_t device, ob_ctx** out) {
 void ob_ctx_destroy(ob_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    {   // designs that outlive their context: free their device memory now, leave the host structs to their owners
+        std::lock_guard<std::mutex> lk(ctx->designs_mu);
+        for (ob_design* d : ctx->designs) { design_release_device(d); d->owner = nullptr; d->stream = nullptr; }
+        ctx->designs.clear();
+    }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream_side) { cudaStreamSynchronize(ctx->stream_side); cudaStreamDestroy(ctx->stream_side); }
     ctx->comm.reset();
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->pool_pack) cudaMemPoolDestroy(ctx->pool_pack);
     if (ctx->pool_design) cudaMemPoolDestroy(ctx->pool_design);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+ob_status ob_host_alloc(size_t bytes, void** out) {
+    if (!out) return OB_ERR_INVALID_ARG;
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorNoDevice ? OB_ERR_NO_DEVICE : OB_ERR_CUDA; }
+    return OB_OK;
+}
+
+void ob_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+ob_status ob_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return OB_ERR_INVALID_ARG;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return OB_ERR_CUDA; }
+    return OB_OK;
+}
+
+ob_status ob_host_unregister(void* p) {
+    if (!p) return OB_ERR_INVALID_ARG;
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return OB_ERR_CUDA; }
+    return OB_OK;
+}
+
+ob_status ob_replicate_shard(int64_t reps, int32_t world, int32_t rank, int64_t* rep_begin, int64_t* rep_end) {
+    if (reps < 0 || world < 1 || rank < 0 || rank >= world) return OB_ERR_INVALID_ARG;
+    const int64_t base = reps / world, extra = reps % world;
+    const int64_t b = rank * base + std::min<int64_t>(rank, extra);
+    if (rep_begin) *rep_begin = b;
+    if (rep_end) *rep_end = b + base + (rank < extra ? 1 : 0);
+    return OB_OK;
 }
 
 const char* ob_last_error(const ob_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -238,14 +309,16 @@ ob_status ob_comm_unique_id(uint8_t* id128) {
 ob_status ob_comm_init_nccl(ob_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t world) {
     if (!ctx || !id128) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
-        if (world < 1 || world > MAX_WORLD || (world & (world - 1)) || rank < 0 || rank >= world)
-            fail(OB_ERR_INVALID_ARG, "world must be a power of two <= 64 and 0 <= rank < world");
+        // any world size shards replicates (mode R); row shards (mode N) additionally need a power of two,
+        // checked by ob_design_set_row_shard
+        if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world)
+            fail(OB_ERR_INVALID_ARG, "1 <= world <= 64 and 0 <= rank < world");
         ctx->comm.reset(comm_create_nccl(id128, rank, world));
     });
 }
 
 ob_status ob_local_group_create(int32_t world, ob_local_group** out) {
-    if (!out || world < 1 || world > MAX_WORLD || (world & (world - 1))) return OB_ERR_INVALID_ARG;
+    if (!out || world < 1 || world > MAX_WORLD) return OB_ERR_INVALID_ARG;
     auto* g = new ob_local_group;
     g->g = local_group_create(world); g->world = world;
     *out = g;
@@ -297,6 +370,7 @@ ob_status ob_design_allgather_rows(ob_ctx* ctx, const ob_design* local, ob_desig
     if (!ctx || !local || !out) return OB_ERR_INVALID_ARG;
     *out = nullptr;
     return guarded(ctx, [&] {
+        design_alive(local);
         Comm* comm = ctx->comm.get();
         if (!comm) fail(OB_ERR_NCCL, "ob_design_allgather_rows needs ob_comm_init_* on this context");
         if (local->world != 1) fail(OB_ERR_INVALID_ARG, "the local design is a row shard (mode N); gather applies to frame slices");
@@ -315,7 +389,7 @@ ob_status ob_design_allgather_rows(ob_ctx* ctx, const ob_design* local, ob_desig
             if (all[3 * r + 2] != mine[2]) fail(OB_ERR_INVALID_ARG, "ranks disagree on the design shape (K, n_cont, weights)");
 
         std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
-        d->stream = ctx->stream; d->device = ctx->device; d->K = local->K; d->n_cont = local->n_cont; d->V = local->V;
+        design_register(ctx, d.get()); d->stream = ctx->stream; d->device = ctx->device; d->K = local->K; d->n_cont = local->n_cont; d->V = local->V;
         d->ldx = local->ldx; d->weighted = local->weighted;
         for (int g = 0; g < 2; ++g) {
             std::vector<size_t> off_x(world), sz_x(world), off_w(world), sz_w(world);
@@ -339,14 +413,16 @@ ob_status ob_design_allgather_rows(ob_ctx* ctx, const ob_design* local, ob_desig
 
 void ob_design_destroy(ob_design* d) {
     if (!d) return;
-    cudaSetDevice(d->device);
-    cudaStream_t st = d->stream;
-    for (auto& g : d->g) {
-        if (g.X) cudaFreeAsync(g.X, st);
-        if (g.w) cudaFreeAsync(g.w, st);
-        if (g.Xs) cudaFreeAsync(g.Xs, st);
-        if (g.src) cudaFreeAsync(g.src, st);
-        if (g.y_raw) cudaFreeAsync(g.y_raw, st);
+    if (ob_ctx* ctx = d->owner) {      // orphaned designs (context already destroyed) hold no device memory any more
+        int prev = -1;
+        cudaGetDevice(&prev);          // may run on a foreign thread (finalisers): leave its current device as it was
+        cudaSetDevice(d->device);
+        {
+            std::lock_guard<std::mutex> lk(ctx->designs_mu);
+            ctx->designs.erase(d);
+        }
+        design_release_device(d);
+        if (prev >= 0 && prev != d->device) cudaSetDevice(prev);
     }
     delete d;
 }
@@ -385,7 +461,7 @@ ob_status ob_design_from_dense(ob_ctx* ctx, int32_t K, int32_t n_cont,
                 for (int64_t i = 0; i < ns[g]; ++i)
                     if (ws[g][i] < 0.0) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: Weights cannot be negative");  // ols.rs:60-66
         std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
-        d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = n_cont; d->V = K + 1; d->ldx = design_ldx(K + 1);
+        design_register(ctx, d.get()); d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = n_cont; d->V = K + 1; d->ldx = design_ldx(K + 1);
         d->weighted = (wa != nullptr) || (wb != nullptr);
         const double* Xs[2] = {Xa, Xb};
         const double* ys[2] = {ya, yb};
@@ -465,7 +541,7 @@ std::unique_ptr<ob_design, void (*)(ob_design*)> pack_staged(ob_ctx* ctx, Staged
     if (flags[0]) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: Weights cannot be negative");
 
     std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
-    d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = sf.n_cont; d->V = K + 1; d->ldx = pa.ldx;
+    design_register(ctx, d.get()); d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = sf.n_cont; d->V = K + 1; d->ldx = pa.ldx;
     d->weighted = sf.weighted;
     d->n_frame = n;
     alloc_group(ctx, d->g[0], tot[0], d->ldx, d->weighted, false);
@@ -664,6 +740,7 @@ ob_status ob_design_download(ob_ctx* ctx, const ob_design* d, double* Xa, double
                              double* Xb, double* yb, double* wb) {
     if (!ctx || !d) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
+        design_alive(d);
         double* Xs[2] = {Xa, Xb}; double* ys[2] = {ya, yb}; double* ws[2] = {wa, wb};
         for (int g = 0; g < 2; ++g) {
             const GroupData& G = d->g[g];
@@ -681,6 +758,7 @@ ob_status ob_design_download(ob_ctx* ctx, const ob_design* d, double* Xa, double
 ob_status ob_design_update_outcome(ob_ctx* ctx, ob_design* d, const double* y_frame, int64_t n_frame) {
     if (!ctx || !d || !y_frame) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
+        design_alive(d);
         if (n_frame != d->n_frame) fail(OB_ERR_INVALID_ARG, "outcome length differs from the frame the design was packed from");
         if (!d->g[0].src || !d->g[1].src) fail(OB_ERR_UNSUPPORTED, "this design carries no frame-row map (gathered design)");
         g_alloc_pack = true;
@@ -697,6 +775,7 @@ ob_status ob_design_update_outcome(ob_ctx* ctx, ob_design* d, const double* y_fr
 ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau) {
     if (!ctx || !d) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
+        design_alive(d);
         if (d->world > 1) fail(OB_ERR_UNSUPPORTED, "RIF pre-step on a row-sharded design (the quantile needs all rows of a group)");
         for (int g = 0; g < 2; ++g) {
             GroupData& G = d->g[g];
@@ -717,11 +796,18 @@ ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau) {
 ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_result* res) {
     if (!ctx || !d || !o || !res) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
+        design_alive(d);
         cudaStream_t st = ctx->stream;
         const int K = d->K, V = d->V;
         if (o->ref_kind < 0 || o->ref_kind > 3) fail(OB_ERR_INVALID_ARG, "ref_kind out of range");
         if (o->reps < 0 || o->n_norm < 0) fail(OB_ERR_INVALID_ARG, "negative reps / n_norm");
-        const int64_t rb = o->rep_begin, re = o->rep_end > 0 ? o->rep_end : o->reps;
+        // mode R inside the library: this rank's contiguous share of the global replicate ids
+        const bool shard_reps = o->shard_replicates != 0 && ctx->comm && ctx->comm->world > 1;
+        if (o->shard_replicates && d->world > 1) fail(OB_ERR_INVALID_ARG, "shard_replicates on a row-sharded design (its communicator shards rows)");
+        if (shard_reps && (o->rep_begin != 0 || o->rep_end != 0 || o->skip_reduce))
+            fail(OB_ERR_INVALID_ARG, "shard_replicates computes the shard itself: rep_begin / rep_end / skip_reduce must be 0");
+        int64_t rb = o->rep_begin, re = o->rep_end > 0 ? o->rep_end : o->reps;
+        if (shard_reps) ob_replicate_shard(o->reps, ctx->comm->world, ctx->comm->rank, &rb, &re);
         if (rb < 0 || re < rb || re > o->reps) fail(OB_ERR_INVALID_ARG, "bad replicate shard");
         const int64_t nrep = re - rb;
         // builder.rs:431-435 (either group empty)
@@ -786,6 +872,11 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                                      (d->g[1].shard.leaf_hi - d->g[1].shard.leaf_lo);
         DevBuf d_agree(sizeof(long long)), d_lut(2 * counts_lut_bytes());
 
+        std::vector<double> point(5 * (size_t)K + 1);
+        cudaEvent_t ev_point = nullptr;          // recorded on st once the point estimate's coefficients are on the device
+        struct EvGuard { cudaEvent_t& e; ~EvGuard() { if (e) cudaEventDestroy(e); } } ev_point_guard{ev_point};
+        OB_CUDA(cudaEventCreateWithFlags(&ev_point, cudaEventDisableTiming));
+        auto run_batches = [&] {
         for (int attempt = 0; attempt < 2; ++attempt) {  // second attempt only widens uint8 -> uint16 after saturation
             const double per_panel = (double)(n_pad[0] + n_pad[1]) * BM * count_bytes +
                                      (index_mode ? (double)(n_glob[0] + n_glob[1]) * BM * 4.0 : 0.0) +
@@ -944,32 +1035,88 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         tr.mark("batches done (buffers freed)", st, true);
         // ---- point estimate (builder.rs:810-811): a failure here is a hard error ----
         int point_status = 0;
-        std::vector<double> point(5 * (size_t)K + 1);
         OB_CUDA(cudaMemcpyAsync(&point_status, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         OB_CUDA(cudaMemcpyAsync(point.data(), d_point.p, sizeof(double) * point.size(), cudaMemcpyDeviceToHost, st));
         OB_CUDA(cudaStreamSynchronize(st));
         if (point_status != OB_OK) fail((ob_status)point_status, status_text(point_status));
+        };   // run_batches
+
+        if (shard_reps) {
+            // all ranks leave together: a rank that failed (rank-local workspace shortage, bad index, ...) must not leave
+            // its peers waiting inside the gather
+            int rc = OB_OK; std::string msg;
+            try { run_batches(); } catch (const StatusError& e) { rc = e.code; msg = e.msg; }
+            DevBuf d_rc(sizeof(int));
+            int agreed = rc;
+            OB_CUDA(cudaMemcpyAsync(d_rc.p, &agreed, sizeof(int), cudaMemcpyHostToDevice, st));
+            ctx->comm->allreduce(d_rc.p, 1, CommDType::I32, CommOp::MAX, st);
+            OB_CUDA(cudaMemcpyAsync(&agreed, d_rc.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            OB_CUDA(cudaStreamSynchronize(st));
+            if (rc != OB_OK) fail((ob_status)rc, msg);
+            if (agreed != OB_OK) fail((ob_status)agreed, std::string("another rank of the replicate-sharded run failed: ") + status_text(agreed));
+        } else {
+            run_batches();
+        }
         res->total_gap = point[5 * K];
         if (res->xa_mean) memcpy(res->xa_mean, point.data(), sizeof(double) * K);
         if (res->xb_mean) memcpy(res->xb_mean, point.data() + K, sizeof(double) * K);
         if (res->beta_star) memcpy(res->beta_star, point.data() + 2 * K, sizeof(double) * K);
+
+        // OaxacaResults.residuals (builder.rs:946: raw residuals of group B under its un-normalised fit) on the side
+        // stream: the kernel and its 8 n_b byte D2H overlap the gather and the reduction below.  A page-locked
+        // destination (ob_host_alloc / ob_host_register) takes the DMA directly.
+        DevBuf d_res;
+        struct SideJoin { cudaStream_t s; bool armed = false; ~SideJoin() { if (armed) cudaStreamSynchronize(s); } } side_join{ctx->stream_side};
+        if (res->residuals_b) {
+            side_join.armed = true;      // an error further down must not release d_res under the side stream
+            d_res.alloc(sizeof(double) * (size_t)std::max<int64_t>(d->g[1].n, 1));
+            cudaStream_t s2 = ctx->stream_side;
+            OB_CUDA(cudaEventRecord(ev_point, st));            // orders the allocation, too
+            OB_CUDA(cudaStreamWaitEvent(s2, ev_point, 0));
+            residuals_launch(d->g[1], K, d->ldx, d_point.as<double>() + 4 * K, d_res.as<double>(), s2);
+            res->gpu_launches += 1;
+            if (d->g[1].n) OB_CUDA(cudaMemcpyAsync(res->residuals_b, d_res.p, sizeof(double) * (size_t)d->g[1].n, cudaMemcpyDeviceToHost, s2));
+        }
         if (res->point_stats) OB_CUDA(cudaMemcpyAsync(res->point_stats, d_stats.p, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
         if (res->beta_a) OB_CUDA(cudaMemcpyAsync(res->beta_a, d_ba.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
         if (res->beta_b) OB_CUDA(cudaMemcpyAsync(res->beta_b, d_bb.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
-        if (res->residuals_b) {  // builder.rs:946: raw residuals of group B under its un-normalised fit
-            DevBuf d_res(sizeof(double) * (size_t)d->g[1].n);
-            residuals_launch(d->g[1], K, d->ldx, d_point.as<double>() + 4 * K, d_res.as<double>(), st);
-            res->gpu_launches += 1;
-            OB_CUDA(cudaMemcpyAsync(res->residuals_b, d_res.p, d_res.bytes, cudaMemcpyDeviceToHost, st));
-            OB_CUDA(cudaStreamSynchronize(st));
+        tr.mark("point + residuals queued", st, false);
+
+        // ---- mode R: replicate rows of all ranks, device to device, into global replicate order ----
+        const int64_t reps_all = shard_reps ? o->reps : nrep;
+        DevBuf d_gstats, d_gstatus, d_gba, d_gbb;
+        const double* stats_rows = d_stats.as<double>() + S;      // [reps_all][S]
+        const int* status_rows = d_status.as<int>() + 1;
+        const double* ba_rows = want_beta ? d_ba.as<double>() + K : nullptr;
+        const double* bb_rows = want_beta ? d_bb.as<double>() + K : nullptr;
+        if (shard_reps) {
+            Timer t_c(st, &res->ms_comm);
+            Comm* cm = ctx->comm.get();
+            const int w = cm->world;
+            std::vector<size_t> off(w), sz(w);
+            auto gather_rows = [&](const void* mine, DevBuf& all, size_t row_bytes) {
+                all.alloc(row_bytes * (size_t)std::max<int64_t>(reps_all, 1));
+                for (int r = 0; r < w; ++r) {
+                    int64_t b = 0, e = 0;
+                    ob_replicate_shard(o->reps, w, r, &b, &e);
+                    off[r] = (size_t)b * row_bytes; sz[r] = (size_t)(e - b) * row_bytes;
+                }
+                cm->allgatherv(mine, all.p, off.data(), sz.data(), st);
+            };
+            gather_rows(stats_rows, d_gstats, sizeof(double) * (size_t)S);
+            gather_rows(status_rows, d_gstatus, sizeof(int));
+            stats_rows = d_gstats.as<double>(); status_rows = d_gstatus.as<int>();
+            if (res->rep_beta_a) { gather_rows(ba_rows, d_gba, sizeof(double) * (size_t)K); ba_rows = d_gba.as<double>(); }
+            if (res->rep_beta_b) { gather_rows(bb_rows, d_gbb, sizeof(double) * (size_t)K); bb_rows = d_gbb.as<double>(); }
+            t_c.stop(); OB_CUDA(cudaStreamSynchronize(st)); t_c.collect();
+            tr.mark("replicate all-gather", st, false);
         }
 
-        tr.mark("point + residuals", st, true);
         // ---- (5) reduction to standard errors / p-values / percentile CIs ----
         if (!o->skip_reduce) {
-            DevBuf d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long)), d_rs(reduce_stats_scratch_bytes(nrep, S));
+            DevBuf d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long)), d_rs(reduce_stats_scratch_bytes(reps_all, S));
             Timer t_red(st, &res->ms_reduce);
-            reduce_stats_launch(d_stats.as<double>() + S, d_status.as<int>() + 1, nrep, S, d_stats.as<double>(),
+            reduce_stats_launch(stats_rows, status_rows, reps_all, S, d_stats.as<double>(),
                                 d_out.as<double>(), d_nok.as<long long>(), st, d_rs.as<double>());
             res->gpu_launches += 1;
             t_red.stop();
@@ -984,11 +1131,15 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
             for (int k = 0; k < 5; ++k)
                 if (dst[k]) memcpy(dst[k], out5.data() + (size_t)k * S, sizeof(double) * S);
         }
-        if (nrep > 0) {
-            if (res->rep_stats) OB_CUDA(cudaMemcpyAsync(res->rep_stats, d_stats.as<double>() + S, sizeof(double) * (size_t)nrep * S, cudaMemcpyDeviceToHost, st));
-            if (res->rep_status) OB_CUDA(cudaMemcpyAsync(res->rep_status, d_status.as<int>() + 1, sizeof(int) * (size_t)nrep, cudaMemcpyDeviceToHost, st));
-            if (res->rep_beta_a) OB_CUDA(cudaMemcpyAsync(res->rep_beta_a, d_ba.as<double>() + K, sizeof(double) * (size_t)nrep * K, cudaMemcpyDeviceToHost, st));
-            if (res->rep_beta_b) OB_CUDA(cudaMemcpyAsync(res->rep_beta_b, d_bb.as<double>() + K, sizeof(double) * (size_t)nrep * K, cudaMemcpyDeviceToHost, st));
+        if (reps_all > 0) {
+            if (res->rep_stats) OB_CUDA(cudaMemcpyAsync(res->rep_stats, stats_rows, sizeof(double) * (size_t)reps_all * S, cudaMemcpyDeviceToHost, st));
+            if (res->rep_status) OB_CUDA(cudaMemcpyAsync(res->rep_status, status_rows, sizeof(int) * (size_t)reps_all, cudaMemcpyDeviceToHost, st));
+            if (res->rep_beta_a) OB_CUDA(cudaMemcpyAsync(res->rep_beta_a, ba_rows, sizeof(double) * (size_t)reps_all * K, cudaMemcpyDeviceToHost, st));
+            if (res->rep_beta_b) OB_CUDA(cudaMemcpyAsync(res->rep_beta_b, bb_rows, sizeof(double) * (size_t)reps_all * K, cudaMemcpyDeviceToHost, st));
+        }
+        if (res->residuals_b) {   // the side stream rejoins before the call's end (and before d_res is released on st)
+            OB_CUDA(cudaEventRecord(ev_point, ctx->stream_side));
+            OB_CUDA(cudaStreamWaitEvent(st, ev_point, 0));
         }
         t_total.stop();
         OB_CUDA(cudaStreamSynchronize(st));
@@ -1045,6 +1196,7 @@ ob_status ob_debug_counts(ob_ctx* ctx, const ob_design* d, uint64_t seed, int64_
                           uint16_t* counts_out) {
     if (!ctx || !d || !counts_out || group < 0 || group > 1 || rep < 0) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
+        design_alive(d);
         cudaStream_t st = ctx->stream;
         const GroupData& G = d->g[group];
         DevBuf d_C((size_t)G.n_pad * BM * 2), d_colsum(sizeof(long long) * BM), d_flags(sizeof(int) * 4), d_lut(counts_lut_bytes());
@@ -1070,6 +1222,7 @@ ob_status ob_debug_counts_from_indices(ob_ctx* ctx, const ob_design* d, int32_t 
     if (!ctx || !d || !counts_out || group < 0 || group > 1 || reps < 0 || (reps && !idx) || (count_bits != 8 && count_bits != 16))
         return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
+        design_alive(d);
         cudaStream_t st = ctx->stream;
         const GroupData& G = d->g[group];
         const int cb = count_bits / 8;

@@ -43,13 +43,14 @@ struct GramKernelParams {
     const double* X[2];     // per group: (sqrt(w)-scaled) design rows [n_pad][ldx]
     const void* C[2];
     long long n_pad[2];
-    int segs[2];            // row segments (leaves) held here, per group
+    int segs[2];            // row segments (leaves) held here, per group: stride of the partial-tile index
+    int seg_lo[2], seg_n[2];// leaves [seg_lo, seg_lo + seg_n) this LAUNCH covers (all of them, or the part of the design that has
+                            // already arrived when the upload is still in flight: ob_design_pack_async)
     int seg_rows[2];        // rows per segment (multiple of KT)
     long long units0;       // units of group 0 = panels * ntiles * segs[0]
     long long units_total;
-    int ldx, panels, ntiles, stages;
+    int ldx, panels, ntiles;
     int nfull, has_half;    // column tiling: nfull tiles of BN columns + (has_half ? one tile of BN/2 : none)
-    int sched;              // 1: lockstep round-robin (default), 0: contiguous cost-balanced ranges (OBBOOT_GRAM_SCHED)
     int tail_mi;            // warp-specialised kernel: 8-slot groups of the LAST panel that hold valid slots, rounded up to
                             // a multiple of 4 (16 = the panel is full): its units skip the DMMAs of the empty groups
     double* partials;       // [units_total][BM*BN], unit-major (a half tile uses the first BM*BN/2 doubles, stride BN/2)
@@ -68,223 +69,8 @@ __device__ __forceinline__ double count_to_f64(unsigned c, const double* __restr
     return __hiloint2double(0x43300000, (int)c) - 4503599627370496.0;
 }
 
-template <typename CountT>
-__device__ __forceinline__ void widen_step_fm(const CountT* __restrict__ src, double* __restrict__ dst, int e,
-                                              const double* __restrict__ tab) {
-    double2 o;
-    o.x = count_to_f64<CountT>(src[e * 16], tab);
-    o.y = count_to_f64<CountT>(src[e * 16 + 8], tab);
-    *reinterpret_cast<double2*>(dst + e * 2) = o;
-}
-
-// shared-memory view + pipeline state of a CTA
-template <typename CountT>
-struct GramCta {
-    double* As; double* Tab; double* Xs; CountT* Cr; uint64_t* full;
-    int NST; int ldx; uint32_t stage_bytes; uint32_t it_base;
-};
-
-// One work unit = (group, panel, column tile, row segment): accumulate from zero over the segment's rows, flush one
-// partial tile.  8 warps as (16/MI) x (8 / (16/MI)); warp tile (MI*8) slots x (NI*8) columns:
-//   MI = 16, NI = 2: 1 x 8 warps, 128 x 16 warp tiles, CTA tile 128 x 128 -- every B-fragment product x_j * x_l is
-//                    formed by exactly one warp; measured best for full tiles (profiles/r01_gram_probe2.json)
-//   MI = 16, NI = 1: 1 x 8 warps, 128 x 8 warp tiles, CTA tile 128 x 64  -- the half-width tail tile (measured 2 %
-//                    faster than 2 x 4 warps of 64 x 16: profiles/r01_half_tile_variants.json)
-template <typename CountT, int LDXC, int MI, int NI>
-__device__ __forceinline__ void gram_unit(GramCta<CountT>& c, const GramKernelParams& p, const double* __restrict__ Xg,
-                                          const CountT* __restrict__ Cg, int nstages, int col_base,
-                                          double* __restrict__ out) {
-    constexpr int NWM = 16 / MI, NWN = (GRAM_THREADS / 32) / NWM;
-    constexpr int TW = NWN * NI * 8;        // tile width in columns
-    constexpr int KSTEPS = KT / 4;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp / NWN, wn = warp % NWN;
-    const int lk = lane & 3, lg = lane >> 2;
-    const int ldx = LDXC ? LDXC : c.ldx;   // compile-time row stride when specialised: immediate LDS offsets
-    const int NST = c.NST;
-    const int cr = tid >> 3, cq = tid & 7;   // widening role of this thread
-    const uint32_t it_base = c.it_base;
-
-    auto issue = [&](int s) {  // thread 0 only
-        const uint32_t it = it_base + (uint32_t)s;
-        const int slot = (int)(it % (uint32_t)NST);
-        fence_proxy_async();
-        mbar_expect_tx(&c.full[slot], c.stage_bytes);
-        tma_load_1d(c.Xs + (size_t)slot * KT * ldx, Xg + (long long)s * KT * ldx, KT * ldx * sizeof(double), &c.full[slot]);
-        tma_load_1d(c.Cr + (size_t)slot * KT * BM, Cg + (long long)s * KT * BM, KT * BM * sizeof(CountT), &c.full[slot]);
-    };
-    auto widen_setup = [&](int s, const CountT*& src, double*& dst) {
-        const int slot = (int)((it_base + (uint32_t)s) % (uint32_t)NST);
-        src = c.Cr + (size_t)slot * KT * BM + cr * BM + cq;
-        dst = c.As + (s & 1) * A_TILE + cr * LDA2 + cq * LGS;
-    };
-    auto wait_stage = [&](int s) {
-        const uint32_t it = it_base + (uint32_t)s;
-        mbar_wait(&c.full[it % (uint32_t)NST], (it / (uint32_t)NST) & 1u);
-    };
-
-    // column pair (j,l) offsets of this thread's B sub-tiles
-    int oj[NI], ol[NI];
-#pragma unroll
-    for (int s = 0; s < NI; ++s) {
-        const int col = col_base + wn * (NI * 8) + s * 8 + lg;
-        const uint32_t pr = *reinterpret_cast<const uint32_t*>(p.pairs + 2 * col);
-        oj[s] = pr & 0xFFFFu; ol[s] = pr >> 16;
-    }
-
-    double acc[MI][NI][2];
-#pragma unroll
-    for (int i = 0; i < MI; ++i)
-#pragma unroll
-        for (int s = 0; s < NI; ++s) { acc[i][s][0] = 0.0; acc[i][s][1] = 0.0; }
-
-    // prologue: fill the pipeline, widen stage 0 (the only exposed widening of the unit)
-    if (tid == 0)
-        for (int s = 0; s < NST && s < nstages; ++s) issue(s);
-    {
-        wait_stage(0);
-        const CountT* src; double* dst;
-        widen_setup(0, src, dst);
-#pragma unroll
-        for (int e = 0; e < KSTEPS; ++e) widen_step_fm<CountT>(src, dst, e, c.Tab);
-    }
-    __syncthreads();
-
-    for (int s = 0; s < nstages; ++s) {
-        const int slot = (int)((it_base + (uint32_t)s) % (uint32_t)NST);
-        const bool has_next = s + 1 < nstages;
-        const CountT* nsrc = nullptr; double* ndst = nullptr;
-        if (has_next) { wait_stage(s + 1); widen_setup(s + 1, nsrc, ndst); }
-
-        const double* abase = c.As + (s & 1) * A_TILE + lk * LDA2 + lg * LGS + wm * MI;
-        const double* xbase = c.Xs + (size_t)slot * KT * ldx + lk * ldx;
-#pragma unroll
-        for (int kk = 0; kk < KSTEPS; ++kk) {
-            double a[MI], b[NI];
-            const double* arow = abase + kk * 4 * LDA2;
-            const double* xrow = xbase + kk * 4 * ldx;
-#pragma unroll
-            for (int i = 0; i < MI; i += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(arow + i);
-                a[i] = v.x; a[i + 1] = v.y;
-            }
-#pragma unroll
-            for (int t = 0; t < NI; ++t) b[t] = xrow[oj[t]] * xrow[ol[t]];
-            if (has_next) widen_step_fm<CountT>(nsrc, ndst, kk, c.Tab);   // next stage's A tile, in the DMMA shadow
-#pragma unroll
-            for (int i = 0; i < MI; ++i)
-#pragma unroll
-                for (int t = 0; t < NI; ++t) dmma884(acc[i][t][0], acc[i][t][1], a[i], b[t]);
-        }
-        __syncthreads();  // stage s fully consumed (X rows, its A tile) and stage s+1's A tile complete
-        if (tid == 0 && s + NST < nstages) issue(s + NST);   // refill the slot stage s just released
-    }
-    c.it_base = it_base + (uint32_t)nstages;
-
-    // flush the partial tile [BM][TW] row-major
-#pragma unroll
-    for (int i = 0; i < MI; ++i)
-#pragma unroll
-        for (int t = 0; t < NI; ++t) {
-            const int m = wm * (MI * 8) + i * 8 + lg, n = wn * (NI * 8) + t * 8 + 2 * lk;
-            *reinterpret_cast<double2*>(out + m * TW + n) = make_double2(acc[i][t][0], acc[i][t][1]);
-        }
-}
-
-// p.sched = 0: first unit (in (group, panel, segment, tile) order) at or after cumulative cost w; a half-width tile
-// is budgeted as half a full one
-__device__ __forceinline__ long long unit_at_cost(const GramKernelParams& p, long long w) {
-    const long long wt = 2 * p.nfull + p.has_half;          // cost of one (panel, segment) sweep over the column tiles
-    const long long W0 = (long long)p.panels * p.segs[0] * wt;
-    long long base = 0;
-    if (w >= W0) { w -= W0; base = p.units0; }
-    const long long sweep = w / wt, r = w - sweep * wt;
-    const long long i = r < 2LL * p.nfull ? (r + 1) / 2 : (long long)p.nfull;
-    return min(base + sweep * p.ntiles + i, p.units_total);
-}
-
-template <typename CountT, int LDXC>
-__global__ void __launch_bounds__(GRAM_THREADS, 1) gram_kernel(const GramKernelParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int tid = threadIdx.x;
-    GramCta<CountT> c;
-    c.ldx = LDXC ? LDXC : p.ldx;
-    c.NST = p.stages;
-    // ---- shared memory carve-up (all regions 16-B aligned) ----
-    c.As = reinterpret_cast<double*>(smem_raw);                                     // [2][A_TILE]
-    c.Tab = c.As + 2 * A_TILE;                                                      // [256] int -> fp64
-    c.Xs = c.Tab + 256;                                                             // [NST][KT*ldx]
-    c.Cr = reinterpret_cast<CountT*>(c.Xs + (size_t)c.NST * KT * c.ldx);            // [NST][KT*BM]
-    c.full = reinterpret_cast<uint64_t*>(c.Cr + (size_t)c.NST * KT * BM);           // [NST]
-    c.stage_bytes = (uint32_t)(KT * c.ldx * sizeof(double) + KT * BM * sizeof(CountT));
-    c.it_base = 0;  // pipeline stage counter across units (slot = it % NST, parity = (it / NST) & 1)
-
-    c.Tab[tid] = (double)tid;
-    if (tid == 0) {
-        for (int s = 0; s < c.NST; ++s) mbar_init(&c.full[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    // Unit schedule (p.sched = 1).  Sequence = all full-width tiles in (group, segment, panel, tile) order, then all
-    // half-width tiles in (group, segment, panel) order; CTA b takes sequence positions b, b + grid, b + 2 grid, ...
-    // Units of one class cost the same, so (a) every CTA gets the same number of each class (+-1) whatever their
-    // relative cost, and (b) the grid advances in lockstep through CONSECUTIVE units: at any time the CTAs work on the
-    // same row segment, sharing its design rows across all panels and column tiles, and each panel's count tile across
-    // its column tiles, through L2 -- HBM traffic stays near one pass over X and C instead of one pass per unit
-    // (measured at config 3: 105 GB instead of 917 GB per launch, profiles/r01_gram_dram_config3_v*.csv).
-    // p.sched = 0: CTA b walks a contiguous, cost-balanced range of the (group, panel, segment, tile) order.
-    const long long sweeps0 = (long long)p.segs[0] * p.panels, sweeps1 = (long long)p.segs[1] * p.panels;
-    const long long NF0 = sweeps0 * p.nfull, NF = NF0 + sweeps1 * p.nfull;
-    const long long NH = p.has_half ? sweeps0 + sweeps1 : 0;
-    long long i, i_end, i_step;
-    if (p.sched) { i = blockIdx.x; i_end = NF + NH; i_step = gridDim.x; }
-    else {
-        const long long W = (sweeps0 + sweeps1) * (2 * p.nfull + p.has_half);
-        i = unit_at_cost(p, W * (long long)blockIdx.x / gridDim.x);
-        i_end = blockIdx.x + 1 == gridDim.x ? p.units_total : unit_at_cost(p, W * (long long)(blockIdx.x + 1) / gridDim.x);
-        i_step = 1;
-    }
-    for (; i < i_end; i += i_step) {
-        int g, nt, seg, panel;
-        if (p.sched) {
-            long long sweep;   // seg * panels + panel within the group
-            if (i < NF) {
-                g = i >= NF0 ? 1 : 0;
-                const long long r = i - (g ? NF0 : 0);
-                sweep = r / p.nfull; nt = (int)(r - sweep * p.nfull);
-            } else {
-                const long long r = i - NF;
-                g = r >= sweeps0 ? 1 : 0;
-                sweep = r - (g ? sweeps0 : 0); nt = p.nfull;
-            }
-            seg = (int)(sweep / p.panels); panel = (int)(sweep - (long long)seg * p.panels);
-        } else {
-            g = (i >= p.units0) ? 1 : 0;
-            const long long ug = i - (g ? p.units0 : 0);
-            const long long sweep = ug / p.ntiles;   // panel * segs + seg
-            const int sg = g ? p.segs[1] : p.segs[0];
-            nt = (int)(ug - sweep * p.ntiles);
-            panel = (int)(sweep / sg); seg = (int)(sweep - (long long)panel * sg);
-        }
-        const int segs = g ? p.segs[1] : p.segs[0], seg_rows = g ? p.seg_rows[1] : p.seg_rows[0];
-        const long long n_pad = g ? p.n_pad[1] : p.n_pad[0];
-        const long long row0 = (long long)seg * seg_rows;
-        const long long row1 = min(row0 + seg_rows, n_pad);
-        const int nstages = (int)((row1 - row0) / KT);
-        // partial of (g, panel, nt, seg) is stored at unit base_g + (panel * segs_g + seg) * ntiles + nt
-        const long long u = (g ? p.units0 : 0) + ((long long)panel * segs + seg) * p.ntiles + nt;
-
-        const double* Xg = (g ? p.X[1] : p.X[0]) + row0 * c.ldx;
-        const CountT* Cg = reinterpret_cast<const CountT*>(g ? p.C[1] : p.C[0]) + ((long long)panel * n_pad + row0) * BM;
-        double* out = p.partials + (size_t)u * (BM * BN);
-        if (p.has_half && nt == p.nfull) gram_unit<CountT, LDXC, 16, 1>(c, p, Xg, Cg, nstages, nt * BN, out);
-        else gram_unit<CountT, LDXC, 16, 2>(c, p, Xg, Cg, nstages, nt * BN, out);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------------
-// Warp-specialised variant (OBBOOT_GRAM_WS=1): 8 consumer warps issue nothing but fragment loads and DMMAs; a
+// Warp-specialised CTA: 8 consumer warps issue nothing but fragment loads and DMMAs; a
 // producer warpgroup (4 warps) owns the TMA issue and the widening of the count tiles.  Ring of WS_R slots, each holding a stage's
 // raw counts, design rows and widened fp64 A tile; three mbarriers per slot:
 //   full[s]      TMA bytes landed             (producer lane 0 arms it; producer and consumers wait)
@@ -306,7 +92,7 @@ struct GramUnit { const double* Xg; const void* Cg; double* out; int nstages, nt
 // tail panel.  CTA b takes positions b, b + grid, ...: equal shares of every class, lockstep through consecutive units.
 __host__ __device__ __forceinline__ bool ws_decode(const GramKernelParams& p, long long i, int ldx, size_t count_bytes, GramUnit& u) {
     const int pt = p.tail_mi < 16 ? 1 : 0, pf = p.panels - pt;            // tail / full panels of this batch
-    const long long segs01 = (long long)p.segs[0] + p.segs[1];
+    const long long segs01 = (long long)p.seg_n[0] + p.seg_n[1];
     const long long n0 = segs01 * pf * p.nfull, n1 = segs01 * pt * p.nfull;
     const long long n2 = p.has_half ? segs01 * pf : 0, n3 = p.has_half ? segs01 * pt : 0;
     if (i >= n0 + n1 + n2 + n3) return false;
@@ -316,11 +102,12 @@ __host__ __device__ __forceinline__ bool ws_decode(const GramKernelParams& p, lo
     else if ((i -= n1) < n2) { np = pf; p0 = 0; nt_cnt = 1; nt0 = p.nfull; }
     else { i -= n2; np = pt; p0 = pf; nt_cnt = 1; nt0 = p.nfull; }
     const long long per_seg = (long long)np * nt_cnt;
-    const long long g0 = (long long)p.segs[0] * per_seg;
+    const long long g0 = (long long)p.seg_n[0] * per_seg;
     const int g = i >= g0 ? 1 : 0;
     const long long r = i - (g ? g0 : 0);
-    const int seg = (int)(r / per_seg);
-    const long long r2 = r - (long long)seg * per_seg;
+    const int sidx = (int)(r / per_seg);
+    const long long r2 = r - (long long)sidx * per_seg;
+    const int seg = (g ? p.seg_lo[1] : p.seg_lo[0]) + sidx;
     const int panel = p0 + (int)(r2 / nt_cnt), nt = nt0 + (int)(r2 % nt_cnt);
     const int segs = g ? p.segs[1] : p.segs[0], seg_rows = g ? p.seg_rows[1] : p.seg_rows[0];
     const long long n_pad = g ? p.n_pad[1] : p.n_pad[0];
@@ -591,11 +378,6 @@ std::vector<uint16_t> gram_pair_table(int V, int ntiles) {
     return t;
 }
 
-static size_t gram_smem(int ldx, int stages, int count_bytes) {
-    return sizeof(double) * (2 * A_TILE + 256 + (size_t)stages * KT * ldx) +
-           (size_t)stages * KT * BM * count_bytes + sizeof(uint64_t) * stages;
-}
-
 GramPlan gram_make_plan(int V, int panels, const GroupData gd[2], int count_bytes, int num_sms) {
     GramPlan pl;
     pl.V = V; pl.ldx = design_ldx(V); pl.panels = panels;
@@ -612,71 +394,65 @@ GramPlan gram_make_plan(int V, int panels, const GroupData gd[2], int count_byte
         total += pl.units[g];
     }
     pl.grid = (int)std::min<int64_t>(num_sms, std::max<int64_t>(total, 1));
-    pl.stages = 4;
-    while (pl.stages > 2 && gram_smem(pl.ldx, pl.stages, count_bytes) > 220 * 1024) --pl.stages;
-    pl.smem_bytes = gram_smem(pl.ldx, pl.stages, count_bytes);
+    pl.smem_bytes = gram_ws_smem(pl.ldx, count_bytes);
     pl.num_partials = (int64_t)total;
     return pl;
 }
 
-void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEvent_t ev_main_begin, cudaEvent_t ev_main_end) {
+static GramKernelParams gram_params(const GramPlan& pl, const GramArgs& a, const int seg_lo[2], const int seg_n[2]) {
     GramKernelParams p;
     for (int g = 0; g < 2; ++g) {
         p.X[g] = a.X[g]; p.C[g] = a.C[g];
         p.n_pad[g] = pl.n_pad[g]; p.segs[g] = pl.segs[g]; p.seg_rows[g] = pl.seg_rows[g];
+        p.seg_lo[g] = seg_lo ? seg_lo[g] : 0; p.seg_n[g] = seg_n ? seg_n[g] : pl.segs[g];
     }
     p.units0 = pl.units[0];
     p.units_total = pl.units[0] + pl.units[1];
-    p.ldx = pl.ldx; p.panels = pl.panels; p.ntiles = pl.ntiles; p.stages = pl.stages;
+    p.ldx = pl.ldx; p.panels = pl.panels; p.ntiles = pl.ntiles;
     p.nfull = pl.nfull; p.has_half = pl.has_half;
-    static const int sched = getenv("OBBOOT_GRAM_SCHED") ? atoi(getenv("OBBOOT_GRAM_SCHED")) : 1;   // tuning knob
-    p.sched = sched;
     p.partials = a.partials; p.pairs = a.d_pairs;
-    static const int tail = getenv("OBBOOT_GRAM_TAIL") ? atoi(getenv("OBBOOT_GRAM_TAIL")) : 1;   // tuning knob
-    p.tail_mi = tail && a.tail_mi >= 1 && a.tail_mi <= 16 ? a.tail_mi : 16;
-    if (ev_main_begin) OB_CUDA(cudaEventRecord(ev_main_begin, st));
-    // warp-specialised kernel (default; measured +6-11 % over the single-role kernel, profiles/r01_gram_ws_ab.json);
-    // OBBOOT_GRAM_WS=0 selects the single-role kernel
-    const size_t ws_smem = gram_ws_smem(pl.ldx, a.count_bytes);
-    static const int ws = getenv("OBBOOT_GRAM_WS") ? atoi(getenv("OBBOOT_GRAM_WS")) : 1;
-    if (ws && ws_smem <= 227 * 1024) {
-        auto launch_ws = [&](auto kernel) {
-            OB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem));
-            kernel<<<pl.grid, WS_THREADS, ws_smem, st>>>(p);
-        };
-#define OB_GRAM_WS_CASE(L) case L: if (a.count_bytes == 1) launch_ws(gram_ws_kernel<uint8_t, L>); else launch_ws(gram_ws_kernel<uint16_t, L>); break;
-        switch (pl.ldx) {
-            OB_GRAM_WS_CASE(12) OB_GRAM_WS_CASE(20) OB_GRAM_WS_CASE(28) OB_GRAM_WS_CASE(36) OB_GRAM_WS_CASE(44) OB_GRAM_WS_CASE(52)
-            OB_GRAM_WS_CASE(60) OB_GRAM_WS_CASE(68) OB_GRAM_WS_CASE(76) OB_GRAM_WS_CASE(84) OB_GRAM_WS_CASE(92)
-            default: if (a.count_bytes == 1) launch_ws(gram_ws_kernel<uint8_t, 0>); else launch_ws(gram_ws_kernel<uint16_t, 0>);
-        }
-#undef OB_GRAM_WS_CASE
-        OB_CUDA(cudaGetLastError());
-        if (ev_main_end) OB_CUDA(cudaEventRecord(ev_main_end, st));
-        dim3 rgw(2 * pl.panels * pl.ntiles, 16);
-        gram_reduce_kernel<<<rgw, 256, 0, st>>>(a.partials, pl.segs[0], pl.segs[1], a.gram, pl.panels, pl.ntiles, pl.leaf_span,
-                                                pl.Pld, pl.has_half);
-        OB_CUDA(cudaGetLastError());
-        return;
-    }
-    auto launch = [&](auto kernel) {
-        OB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes));
-        kernel<<<pl.grid, GRAM_THREADS, pl.smem_bytes, st>>>(p);
+    p.tail_mi = a.tail_mi >= 1 && a.tail_mi <= 16 ? a.tail_mi : 16;
+    return p;
+}
+
+// The contraction over the leaves [seg_lo[g], seg_lo[g] + seg_n[g]) of each group (null = all leaves held here):
+// writes those leaves' partial tiles.  A design whose upload is still in flight is contracted in two such launches
+// (the rows that have arrived, then the rest); the partial tiles, hence every sum, are the same as from one launch.
+void gram_launch_leaves(const GramPlan& pl, const GramArgs& a, const int seg_lo[2], const int seg_n[2], cudaStream_t st) {
+    const GramKernelParams p = gram_params(pl, a, seg_lo, seg_n);
+    const int64_t units = ((int64_t)p.seg_n[0] + p.seg_n[1]) * pl.panels * pl.ntiles;
+    if (units <= 0) return;
+    const int grid = (int)std::min<int64_t>(pl.grid, units);
+    const size_t ws_smem = pl.smem_bytes;
+    if (ws_smem > 227 * 1024) throw StatusError{OB_ERR_UNSUPPORTED, "design too wide for the Gram kernel's shared-memory ring"};
+    auto launch_ws = [&](auto kernel) {
+        OB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem));
+        kernel<<<grid, WS_THREADS, ws_smem, st>>>(p);
     };
     // row stride specialisations (ldx = 4 mod 8): the common design widths get immediate shared-memory offsets
-#define OB_GRAM_CASE(L) case L: if (a.count_bytes == 1) launch(gram_kernel<uint8_t, L>); else launch(gram_kernel<uint16_t, L>); break;
+#define OB_GRAM_WS_CASE(L) case L: if (a.count_bytes == 1) launch_ws(gram_ws_kernel<uint8_t, L>); else launch_ws(gram_ws_kernel<uint16_t, L>); break;
     switch (pl.ldx) {
-        OB_GRAM_CASE(12) OB_GRAM_CASE(20) OB_GRAM_CASE(28) OB_GRAM_CASE(36) OB_GRAM_CASE(44) OB_GRAM_CASE(52)
-        OB_GRAM_CASE(60) OB_GRAM_CASE(68) OB_GRAM_CASE(76) OB_GRAM_CASE(84) OB_GRAM_CASE(92)
-        default: if (a.count_bytes == 1) launch(gram_kernel<uint8_t, 0>); else launch(gram_kernel<uint16_t, 0>);
+        OB_GRAM_WS_CASE(12) OB_GRAM_WS_CASE(20) OB_GRAM_WS_CASE(28) OB_GRAM_WS_CASE(36) OB_GRAM_WS_CASE(44) OB_GRAM_WS_CASE(52)
+        OB_GRAM_WS_CASE(60) OB_GRAM_WS_CASE(68) OB_GRAM_WS_CASE(76) OB_GRAM_WS_CASE(84) OB_GRAM_WS_CASE(92)
+        default: if (a.count_bytes == 1) launch_ws(gram_ws_kernel<uint8_t, 0>); else launch_ws(gram_ws_kernel<uint16_t, 0>);
     }
-#undef OB_GRAM_CASE
+#undef OB_GRAM_WS_CASE
     OB_CUDA(cudaGetLastError());
+}
+
+// fixed-tree sum of every tile's leaf partials -> gram [2][panels*BM][Pld]
+void gram_reduce_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st) {
+    dim3 rgw(2 * pl.panels * pl.ntiles, 16);
+    gram_reduce_kernel<<<rgw, 256, 0, st>>>(a.partials, pl.segs[0], pl.segs[1], a.gram, pl.panels, pl.ntiles, pl.leaf_span,
+                                            pl.Pld, pl.has_half);
+    OB_CUDA(cudaGetLastError());
+}
+
+void gram_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st, cudaEvent_t ev_main_begin, cudaEvent_t ev_main_end) {
+    if (ev_main_begin) OB_CUDA(cudaEventRecord(ev_main_begin, st));
+    gram_launch_leaves(pl, a, nullptr, nullptr, st);
     if (ev_main_end) OB_CUDA(cudaEventRecord(ev_main_end, st));
-    dim3 rg(2 * pl.panels * pl.ntiles, 16);
-    gram_reduce_kernel<<<rg, 256, 0, st>>>(a.partials, pl.segs[0], pl.segs[1], a.gram, pl.panels, pl.ntiles, pl.leaf_span,
-                                           pl.Pld, pl.has_half);
-    OB_CUDA(cudaGetLastError());
+    gram_reduce_launch(pl, a, st);
 }
 
 void gram_combine_launch(const double* gathered, int world, const int ranks_with_rows[2], int64_t per_group_elems,
@@ -693,7 +469,7 @@ void gram_combine_launch(const double* gathered, int world, const int ranks_with
 int64_t gram_schedule_debug(int V, int panels, int64_t slots_last_panel, const GroupData gd[2], int grid, int64_t* out7, int64_t cap) {
     GramPlan pl = gram_make_plan(V, panels, gd, 1, grid);
     GramKernelParams p{};
-    for (int g = 0; g < 2; ++g) { p.n_pad[g] = pl.n_pad[g]; p.segs[g] = pl.segs[g]; p.seg_rows[g] = pl.seg_rows[g]; }
+    for (int g = 0; g < 2; ++g) { p.n_pad[g] = pl.n_pad[g]; p.segs[g] = pl.segs[g]; p.seg_rows[g] = pl.seg_rows[g]; p.seg_lo[g] = 0; p.seg_n[g] = pl.segs[g]; }
     p.units0 = pl.units[0]; p.units_total = pl.units[0] + pl.units[1];
     p.ldx = pl.ldx; p.panels = pl.panels; p.ntiles = pl.ntiles; p.nfull = pl.nfull; p.has_half = pl.has_half;
     p.tail_mi = (int)std::min<int64_t>(16, ((slots_last_panel + 7) / 8 + 3) / 4 * 4);

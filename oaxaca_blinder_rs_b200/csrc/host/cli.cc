@@ -1,6 +1,7 @@
 // csrc/host/cli.cc -- `oaxaca-cli` front-end for the mean decomposition, same flags as the reference's clap
 // RunArgs (main.rs:44-128) and the same dispatch as run_mean_analysis (main.rs:175-232).  Analysis types other
 // than `mean` (Machado-Mata quantile, AKM, matching) are outside the B200 bootstrap path and are refused.
+#include <cerrno>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -14,6 +15,23 @@ static std::vector<std::string> split_commas(const std::string& s) {
     std::vector<std::string> out; std::stringstream ss(s); std::string t;
     while (std::getline(ss, t, ',')) if (!t.empty()) out.push_back(t);
     return out;
+}
+
+// clap's typed arguments reject what does not parse (exit code 2, "error: invalid value ... for '--flag <X>'")
+struct ArgError { std::string msg; };
+static unsigned long long parse_u64(const std::string& flag, const std::string& v) {
+    char* end = nullptr;
+    errno = 0;
+    const unsigned long long x = std::strtoull(v.c_str(), &end, 10);
+    if (v.empty() || v[0] == '-' || *end != '\0' || errno == ERANGE)
+        throw ArgError{"invalid value '" + v + "' for '--" + flag + "': not a non-negative integer"};
+    return x;
+}
+static double parse_f64(const std::string& flag, const std::string& v) {
+    char* end = nullptr;
+    const double x = std::strtod(v.c_str(), &end);
+    if (v.empty() || *end != '\0' || x != x) throw ArgError{"invalid value '" + v + "' for '--" + flag + "': not a number"};
+    return x;
 }
 
 static void usage() {
@@ -48,6 +66,28 @@ int main(int argc, char** argv) {
         if (k.rfind("--", 0) != 0 || i + 1 >= argc) { std::cerr << "Error: unexpected argument '" << k << "'\n\n"; usage(); return 2; }
         a[k.substr(2)] = argv[++i];
     }
+    // typed flags, validated before any work (clap ValueEnum / typed args, main.rs:44-128): a typo must not silently
+    // change which reference coefficients or how many replicates are used
+    ob::ReferenceCoefficients ref_kind = ob::ReferenceCoefficients::GroupB;
+    unsigned long long reps = 0, seed = 0;
+    double tau = 0.0;
+    try {
+        const std::string& rc = a["ref-coeffs"];
+        if (rc == "group-a") ref_kind = ob::ReferenceCoefficients::GroupA;
+        else if (rc == "group-b") ref_kind = ob::ReferenceCoefficients::GroupB;
+        else if (rc == "pooled") ref_kind = ob::ReferenceCoefficients::Pooled;
+        else if (rc == "weighted") ref_kind = ob::ReferenceCoefficients::Weighted;
+        else throw ArgError{"invalid value '" + rc + "' for '--ref-coeffs <KIND>'\n  [possible values: group-a, group-b, pooled, weighted]"};
+        reps = parse_u64("bootstrap-reps", a["bootstrap-reps"]);
+        if (a.count("seed")) seed = parse_u64("seed", a["seed"]);
+        if (a.count("rif-quantile")) {
+            tau = parse_f64("rif-quantile", a["rif-quantile"]);
+            if (!(tau > 0.0 && tau < 1.0)) throw ArgError{"invalid value '" + a["rif-quantile"] + "' for '--rif-quantile <TAU>': must lie in (0, 1)"};
+        }
+    } catch (const ArgError& e) {
+        std::cerr << "error: " << e.msg << "\n\nFor more information, try '--help'.\n";
+        return 2;
+    }
     try {
         for (const char* req : {"data", "outcome", "group", "reference"})
             if (!a.count(req) && !(std::string(req) == "outcome" && a.count("formula")))
@@ -63,17 +103,13 @@ int main(int argc, char** argv) {
             b.predictors(split_commas(a["predictors"]));
             b.categorical_predictors(split_commas(a["categorical"]));
         }
-        const std::string& rc = a["ref-coeffs"];
-        b.reference_coefficients(rc == "group-a" ? ob::ReferenceCoefficients::GroupA
-                                 : rc == "pooled" ? ob::ReferenceCoefficients::Pooled
-                                 : rc == "weighted" ? ob::ReferenceCoefficients::Weighted
-                                                    : ob::ReferenceCoefficients::GroupB);
-        b.bootstrap_reps((size_t)std::strtoull(a["bootstrap-reps"].c_str(), nullptr, 10));
+        b.reference_coefficients(ref_kind);
+        b.bootstrap_reps((size_t)reps);
         if (a.count("weights")) b.weights(a["weights"]);
         if (a.count("normalize")) b.normalize(split_commas(a["normalize"]));
-        if (a.count("seed")) b.seed(std::strtoull(a["seed"].c_str(), nullptr, 10));
+        if (a.count("seed")) b.seed(seed);
         if (a.count("selection-outcome")) b.heckman_selection(a["selection-outcome"], split_commas(a["selection-predictors"]));
-        const ob::OaxacaResults r = a.count("rif-quantile") ? b.decompose_quantile(std::strtod(a["rif-quantile"].c_str(), nullptr)) : b.run();
+        const ob::OaxacaResults r = a.count("rif-quantile") ? b.decompose_quantile(tau) : b.run();
         r.summary(std::cout);
         if (a.count("output-json")) { std::ofstream(a["output-json"]) << r.to_json(true, false); }
         if (a.count("output-markdown")) { std::ofstream(a["output-markdown"]) << r.to_markdown(); }

@@ -13,7 +13,7 @@ namespace ob {
 constexpr int BM = 128;        // replicate slots per panel (M tile)
 constexpr int BN = 128;        // sufficient-statistic columns per N tile
 constexpr int KT = 32;         // rows (contraction) per pipeline stage
-constexpr int GRAM_THREADS = 256;
+constexpr int GRAM_THREADS = 256;   // consumer threads of the Gram CTA (8 warps); + one producer warpgroup
 
 struct CudaError { cudaError_t code; const char* what; const char* file; int line; };
 
@@ -125,7 +125,7 @@ struct GramPlan {
     int64_t units[2];             // panels * ntiles * segs
     int grid;
     int64_t num_partials;         // = units[0] + units[1]
-    size_t smem_bytes; int stages;
+    size_t smem_bytes;
 };
 // Column tiling of the P' = V(V+1)/2 sufficient-statistic columns: nfull tiles of BN columns and, when the remainder
 // fits, one half-width tail tile (P' = 171 at K = 17 costs 1.5 tiles instead of 2).
@@ -150,6 +150,10 @@ struct GramArgs {
 };
 void gram_launch(const GramPlan& plan, const GramArgs& args, cudaStream_t st, cudaEvent_t ev_main_begin = nullptr,
                  cudaEvent_t ev_main_end = nullptr);
+// the two halves of gram_launch: the contraction over a sub-range of each group's leaves (null = all), and the
+// fixed-tree reduction of the partial tiles (once every leaf has been contracted)
+void gram_launch_leaves(const GramPlan& plan, const GramArgs& args, const int seg_lo[2], const int seg_n[2], cudaStream_t st);
+void gram_reduce_launch(const GramPlan& plan, const GramArgs& args, cudaStream_t st);
 // mode N: gram = aligned-tree sum over ranks of gathered [world][2][slots_pad*Pld] per-rank sums; ranks_with_rows[g]
 // = number of leading ranks that hold leaves of group g
 void gram_combine_launch(const double* gathered, int world, const int ranks_with_rows[2], int64_t per_group_elems,

@@ -2,8 +2,10 @@
 
 Mode R, replicate sharding: every rank holds the full packed design, rank r computes a contiguous range of
 global replicate ids with the counter-based stream keyed by global id, one all-gather of the
-[reps_r x S] statistics block, then every rank reduces the identical gathered array (torch.distributed:
-NCCL on GPUs, gloo in CPU tests).
+[reps_r x S] statistics block, then every rank reduces the identical gathered array.  With a communicator attached
+to the context (Context.init_nccl) all of that happens INSIDE the library (ob_boot_opts.shard_replicates: device-to-
+device all-gather over NVLink, no host hop, no torch); without one, gather_replicates() carries the rows through
+torch.distributed (gloo in the CPU tests) and ob_reduce_stats reduces them.
 
 Mode N, row sharding (n too large for one HBM): shard_frame() selects the rows of each group that
 ob_row_shard_plan assigns to this rank; the packed shard is marked with set_row_shard and the library itself
@@ -52,9 +54,14 @@ def gather_replicates(local_stats: np.ndarray, local_status: np.ndarray, reps: i
 
 
 def bootstrap_sharded(design, reps: int, group=None, device=None, **kw) -> dict:
-    """ob_bootstrap_run on this rank's replicate shard + all-gather + ob_reduce_stats (same result on all ranks)."""
-    import torch.distributed as dist
+    """ob_bootstrap_run on this rank's replicate shard + all-gather + reduction (same result on all ranks).
+    A context with a communicator does it all inside the library (shard_replicates); the host-gather path below is
+    for contexts without one."""
     from . import core
+    if design.ctx.comm_world > 1 and design.world == 1:
+        kw.setdefault("want_residuals", design.ctx.comm_rank == 0)
+        return core.bootstrap(design, reps, shard_replicates=True, **kw)
+    import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     b, e = shard_range(rank, world, reps)
     kw.setdefault("want_residuals", rank == 0)     # OaxacaResults.residuals (builder.rs:946) is fetched once, on rank 0

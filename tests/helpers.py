@@ -25,6 +25,20 @@ def relerr(a, b, small=SMALL):
     return float(err.max())
 
 
+def worst(a, b, small=SMALL):
+    """Where relerr(a, b) comes from, for assertion messages: (error, index, a value, b value, column scale)."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    if a.size == 0 or np.isnan(b).all():
+        return None
+    absb = np.abs(np.nan_to_num(b))
+    colscale = absb.max(axis=0, keepdims=True) if b.ndim >= 2 else absb.max()
+    colscale = np.broadcast_to(np.maximum(colscale, small * absb.max()), b.shape)
+    den = np.where(absb >= small, absb, np.maximum(colscale, np.finfo(float).tiny))
+    err = np.abs(np.nan_to_num(a) - np.nan_to_num(b)) / den
+    i = np.unravel_index(int(np.argmax(err)), err.shape)
+    return dict(err=float(err[i]), index=tuple(int(x) for x in i), got=float(a[i]), want=float(b[i]), col_scale=float(colscale[i]))
+
+
 def relerr_to_scale(a, b, scale):
     """|a - b| / scale for quantities that ARE differences of O(scale) numbers (residuals y - x.beta: scale = max |y|)."""
     a, b = np.asarray(a, float), np.asarray(b, float)

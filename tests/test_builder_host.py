@@ -151,3 +151,42 @@ def test_csv_reader_matches_python_restatement(tmp_path):
     assert e["rows"] == len([i for i in range(len(rows)) if col["quoted,name"][i] != "" and col["wage"][i] != ""])
     with pytest.raises(ob.OaxacaError):
         ob.read_csv(str(tmp_path / "missing.csv"))
+
+
+def test_pandas_missing_values_are_nulls_not_levels():
+    """pd.NA ('string' / nullable dtypes), NaN and None in string columns are nulls: the row is dropped
+    (clean_dataframe, builder.rs:760-784), never encoded as a level called "<NA>"."""
+    pd = pytest.importorskip("pandas")
+    n = 12
+    base = {"wage": [float(10 + i) for i in range(n)], "education": [float(8 + (i * 7) % 5) for i in range(n)],
+            "gender": ["M", "F"] * (n // 2), "sector": ["agri", "tech", "serv"] * (n // 3)}
+    ref = ob.OaxacaBuilder(dict(base, gender=[None if i == 2 else g for i, g in enumerate(base["gender"])],
+                                sector=[None if i == 5 else s for i, s in enumerate(base["sector"])]),
+                           "wage", "gender", "F").predictors(["education"]).categorical_predictors(["sector"]).describe()
+    for dtype in ("string", "object", "category"):
+        df = pd.DataFrame(base)
+        df["gender"] = df["gender"].astype(dtype)
+        df["sector"] = df["sector"].astype(dtype)
+        df.loc[2, "gender"] = pd.NA if dtype == "string" else None
+        df.loc[5, "sector"] = pd.NA if dtype == "string" else np.nan
+        df["education"] = df["education"].astype("Float64")        # nullable numeric, no nulls here
+        d = ob.OaxacaBuilder(df, "wage", "gender", "F").predictors(["education"]).categorical_predictors(["sector"]).describe()
+        assert d["rows"] == n - 2 and d["cat_levels"] == [3], dtype
+        assert d["names"] == ref["names"] and d["group"] == ref["group"] and (d["n_a"], d["n_b"]) == (ref["n_a"], ref["n_b"]), dtype
+        assert not any("<NA>" in nm or "nan" in nm.lower() for nm in d["names"] + d["base_names"]), dtype
+
+
+@pytest.mark.parametrize("flag,value", [("--ref-coeffs", "cotton"), ("--ref-coeffs", "Pooled"), ("--bootstrap-reps", "abc"),
+                                        ("--bootstrap-reps", "-5"), ("--rif-quantile", "1.5"), ("--rif-quantile", "x"),
+                                        ("--seed", "1e3")])
+def test_cli_rejects_untyped_values(flag, value):
+    """clap's ValueEnum / typed args (main.rs:44-128) reject these with exit code 2; a typo must never fall back
+    silently to another reference-coefficient kind or to zero replicates."""
+    import os
+    import subprocess
+    from oaxaca_blinder_rs_b200 import _native
+    _native.build()
+    cli = os.path.join(os.path.dirname(_native.LIB_PATH), "oaxaca-cli")
+    r = subprocess.run([cli, "--data", "nope.csv", "--outcome", "y", "--group", "g", "--reference", "r", flag, value],
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "invalid value" in r.stderr and value in r.stderr

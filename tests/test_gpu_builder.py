@@ -196,3 +196,21 @@ def test_cli_invalid_argument():                                   # cli_test.rs
     p = cli("--data", os.path.join(ROOT, "tests", "golden", "non_existent_file.csv"), "--outcome", "wage", "--group", "gender",
             "--reference", "F", "--predictors", "education")
     assert p.returncode != 0 and "Error:" in p.stderr
+
+
+def test_design_outliving_its_context_is_harmless():
+    """Finalisers run in arbitrary order (and on arbitrary threads): closing a context first must orphan its designs,
+    not leave them pointing at freed streams / pools."""
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(3_000, 2, seed=2)
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+    ctx.close()
+    ctx2 = ob.Context(0)
+    with pytest.raises(ob.OaxacaError) as e:
+        des.ctx = ctx2
+        ob.bootstrap(des, 4, seed=1)
+    assert e.value.kind == "InvalidArgument"
+    des.close()          # only frees the host struct
+    ctx2.close()

@@ -14,7 +14,7 @@ RTOL = 1e-10   # north_star: "within a relative 1e-10 (fp64 with a different sum
 REFS = {"A": 0, "B": 1, "pooled": 2, "weighted": 3}
 
 
-from helpers import relerr, relerr_to_scale  # noqa: E402  (elementwise-relative metric, tests/helpers.py)
+from helpers import relerr, relerr_to_scale, worst  # noqa: E402  (elementwise-relative metric, tests/helpers.py)
 
 
 @pytest.fixture(scope="module")
@@ -59,9 +59,9 @@ def compare(gpu, ref, tol=RTOL, orc=None):
     assert relerr_to_scale(gpu["residuals_b"], p["resid_b"], yscale) <= tol, "residuals_b"
     well = ref["rep_min_pivot"] >= 1e-9
     np.testing.assert_array_equal(gpu["rep_status"][well], ref["rep_status"][well])
-    assert relerr(gpu["rep_stats"][well], ref["rep_stats"][well]) <= tol
-    assert relerr(gpu["rep_beta_a"][well], ref["rep_beta_a"][well]) <= tol
-    assert relerr(gpu["rep_beta_b"][well], ref["rep_beta_b"][well]) <= tol
+    assert relerr(gpu["rep_stats"][well], ref["rep_stats"][well]) <= tol, worst(gpu["rep_stats"][well], ref["rep_stats"][well])
+    assert relerr(gpu["rep_beta_a"][well], ref["rep_beta_a"][well]) <= tol, worst(gpu["rep_beta_a"][well], ref["rep_beta_a"][well])
+    assert relerr(gpu["rep_beta_b"][well], ref["rep_beta_b"][well]) <= tol, worst(gpu["rep_beta_b"][well], ref["rep_beta_b"][well])
     if np.array_equal(gpu["rep_status"], ref["rep_status"]) and well.all():
         red = ref
     else:   # same replicate set as the GPU: oracle's bootstrap_stats over the GPU's successful replicates

@@ -29,6 +29,8 @@ def _worker(rank, world, port, q):
     # mode R upload over the same communicator: frame slices packed per rank, full design gathered over NVLink
     rep = obd.pack_replicated(ctx, full, rank, world)
     gathered = rep.download()
+    # mode R inside the library: replicate shards, statistics all-gathered device to device over NCCL
+    mode_r = ob.bootstrap(rep, reps, ref_kind=ob.REF_WEIGHTED, norm=norm, seed=5, want_rep=True, shard_replicates=True)
     rep.close()
     ctx.comm_destroy()
     one = None
@@ -40,7 +42,8 @@ def _worker(rank, world, port, q):
         for a, b_ in zip(gathered, whole):
             assert np.array_equal(a, b_, equal_nan=True)
     keys = ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper", "p_value")
-    q.put((rank, {k: out[k] for k in keys}, None if one is None else {k: one[k] for k in keys}, out["timings_ms"]))
+    q.put((rank, {k: out[k] for k in keys}, None if one is None else {k: one[k] for k in keys}, out["timings_ms"],
+           {k: mode_r[k] for k in keys}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -63,7 +66,8 @@ def test_nccl_row_sharding_matches_one_gpu_bit_for_bit():
         p.join(timeout=120)
         assert p.exitcode == 0
     one = got[0][2]
-    for rank, out, _, tm in got:
+    for rank, out, _, tm, mode_r in got:
         for k, v in out.items():
             assert np.array_equal(np.nan_to_num(v, nan=-7.0), np.nan_to_num(one[k], nan=-7.0)), (rank, k)
+            assert np.array_equal(np.nan_to_num(mode_r[k], nan=-7.0), np.nan_to_num(one[k], nan=-7.0)), ("mode R", rank, k)
         assert tm["comm"] > 0.0
