@@ -274,6 +274,100 @@ def readme_shape_gpu(ob, ctx):
     return best
 
 
+def nccl_selftest(ob, obd, ctx, rank, world, dist, torch):
+    """Before any multi-GPU timing: both sharding modes over the library's NCCL communicator must reproduce a one-GPU
+    run of the same frame BIT FOR BIT (statistics, SEs, CIs).  Small shape, a second of work.  Raises on mismatch."""
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(300_000, 6, cat_levels=(4,), weights=True, seed=5)
+    norm = [ob.NormVar(m, i) for m, i in synth.norm_spec(d)]
+    reps, kw = 200, dict(ref_kind=ob.REF_WEIGHTED, norm=norm, seed=5, want_rep=True)
+    whole = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+    one = ob.bootstrap(whole, reps, **kw)
+    mode_r = ob.bootstrap(whole, reps, shard_replicates=True, **kw)
+    whole.close()
+    keys = ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper", "p_value")
+    same = lambda a, b: bool(np.array_equal(np.nan_to_num(a, nan=-7.0), np.nan_to_num(b, nan=-7.0)))
+    ok_r = all(same(mode_r[k], one[k]) for k in keys)
+    ok_n = None
+    if world & (world - 1) == 0:
+        shard = obd.pack_row_shard_from_slice(ctx, d, rank, world)
+        mode_n = ob.bootstrap(shard, reps, max_workspace_bytes=200_000_000, **kw)      # several panel batches
+        shard.close()
+        ok_n = all(same(mode_n[k], one[k]) for k in keys)
+    flags = torch.tensor([int(ok_r), int(ok_n is not False)], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    ok_r, ok_n_all = bool(flags[0].item()), bool(flags[1].item())
+    if not (ok_r and ok_n_all):
+        raise SystemExit(f"NCCL self-test failed: mode R bit-identical = {ok_r}, mode N bit-identical = {ok_n_all}")
+    return {"mode_r_bit_identical_to_one_gpu": ok_r, "mode_n_bit_identical_to_one_gpu": None if ok_n is None else ok_n_all,
+            "shape": "n=300k, K=10, WLS + Yun, B=200, every rank compared with its own unsharded run"}
+
+
+def measure_also(name, ob, obd, ctx, torch, dist, rank, world, local, shard_rows, rif_tau, steps=2):
+    """A BASELINE config other than the headline one at the same N (the row-sharded config 5, the RIF config 4), so
+    that the driver's multi-GPU record holds them too: resident reps/s over `steps` steps after one warm-up, Gram
+    kernel fraction of the DMMA peak, and an end-to-end step from host columns."""
+    from oaxaca_blinder_rs_b200 import synth
+    n, n_cont, cats, wts, normalize, reps, ref = WORKLOADS[name]
+    if shard_rows:
+        d = synth.make_wage_rows(n, n_cont, cat_levels=cats, weights=wts, rank=rank, world=world)
+    else:
+        d = synth.make_wage(n, n_cont, cat_levels=cats, weights=wts)
+    norm = [ob.NormVar(m, i) for m, i in (synth.norm_spec(d) if normalize else [])]
+    K = 1 + n_cont + sum(m - 1 for m in cats)
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def pack():
+        if shard_rows:
+            return obd.pack_row_shard(ctx, d, rank, world)
+        if world > 1:
+            des = obd.pack_replicated(ctx, d, rank, world)
+        else:
+            des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+        if rif_tau is not None:
+            des.apply_rif(rif_tau)
+        return des
+
+    def step(des):
+        return ob.bootstrap(des, reps, ref_kind=ref, norm=norm, seed=2026, want_residuals=False,
+                            shard_replicates=(world > 1 and not shard_rows))
+    des = pack()
+    step(des)
+    sync()
+    t0 = time.perf_counter()
+    gram_ms = []
+    for _ in range(steps):
+        out = step(des)
+        gram_ms.append(out["timings_ms"]["gram_main"])
+    sync()
+    dt = time.perf_counter() - t0
+    des.close()
+    sync()
+    t1 = time.perf_counter()
+    des = pack()
+    step(des)
+    des.close()
+    sync()
+    dt_e = time.perf_counter() - t1
+    times = torch.tensor([dt, dt_e], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dt, dt_e = times.tolist()
+    flops, P = algorithmic_flops(n, K, reps)
+    g_ms = float(np.mean(gram_ms))
+    ach = flops / world / (g_ms * 1e-3) / 1e12
+    return {"config": config_dict(name, world, shard_rows, rif_tau), "value": reps * steps / dt, "unit": "reps/s", "steps": steps,
+            "warmup": 1, "ms_per_step": dt / steps * 1e3, "e2e": {"value": reps / dt_e, "unit": "reps/s", "steps": 1},
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": ach / FP64_DMMA_PEAK_TFLOPS, "launch_ms": g_ms},
+            "stage_ms": {k: float(v) for k, v in out["timings_ms"].items()}, "n_ok": int(out["n_ok"])}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -285,6 +379,12 @@ def main():
     ap.add_argument("--rif-tau", type=float, default=None, help="RIF-regression outcome at this quantile (config 4)")
     ap.add_argument("--shard", default="auto", choices=["auto", "reps", "rows"],
                     help="N > 1: shard replicates (mode R; every GPU holds the design) or rows (mode N; config 5)")
+    ap.add_argument("--e2e-upload", default="auto", choices=["auto", "gather", "rowshard"],
+                    help="N > 1, replicate-sharded workloads, end-to-end leg: every rank uploads 1/N of the frame, then either "
+                         "the packed rows are all-gathered so that every GPU holds the design (gather: mode R) or re-cut into "
+                         "row shards (rowshard: mode N, a rank never needs the other rows); auto = rowshard unless RIF")
+    ap.add_argument("--also", default="auto", choices=["auto", "on", "off"],
+                    help="N > 1: also measure the row-sharded config 5 and the RIF config 4 at the same N (key `also`)")
     args = ap.parse_args()
     name = args.workload
     if args.impl == "reference":
@@ -323,6 +423,8 @@ def main():
             ctx.init_nccl(rank, world)       # mode R: the statistics all-gather and the upload (frame slices over NVLink)
     K = 1 + len(d["cont"]) + sum(m - 1 for m in d["cat_levels"])
     normv = [ob.NormVar(m, i) for m, i in norm]
+    # multi-GPU: no timing before both sharding modes have reproduced a one-GPU run bit for bit over NCCL
+    selftest = nccl_selftest(ob, obd, ctx, rank, world, dist, torch) if world > 1 else None
 
     # pinned host columns for the end-to-end leg
     def pin(a):
@@ -338,19 +440,29 @@ def main():
 
     rif_tau = default_rif_tau(args, name)
 
-    def pack():
+    e2e_rowshard = (world > 1 and not shard_rows and world & (world - 1) == 0 and
+                    (args.e2e_upload == "rowshard" or (args.e2e_upload == "auto" and rif_tau is None)))
+
+    def pack(asynchronous=False, e2e=False):
         if world > 1 and not shard_rows:
-            # mode R: this rank uploads 1/world of the frame; the packed rows are all-gathered over NVLink
             fr = dict(n=n, cont=[t.numpy() for t in pinned["cont"]], cat_codes=[t.numpy() for t in pinned["cat"]],
                       cat_levels=d["cat_levels"], outcome=pinned["y"].numpy(),
                       weights=None if pinned["w"] is None else pinned["w"].numpy(), group=pinned["g"].numpy())
+            if e2e and e2e_rowshard:
+                # host frame -> this rank uploads 1/world of it, packs it, and the groups' rows are re-cut into row shards
+                # over NVLink (ob_design_redistribute_rows): no GPU ever needs the other ranks' rows, and the bootstrap
+                # runs row-sharded (mode N: bit-identical to one GPU, like mode R)
+                return obd.pack_row_shard_from_slice(ctx, fr, rank, world)
+            # mode R: this rank uploads 1/world of the frame; the packed rows are all-gathered over NVLink
             des = obd.pack_replicated(ctx, fr, rank, world)
             if rif_tau is not None:
                 des.apply_rif(rif_tau)
             return des
+        # ob_design_pack_async: the call returns once the group split is known; the chunked column upload and the pack
+        # run on the library's copy stream under the replicate generation and the first Gram launch of step()
         des = ob.Design.pack(ctx, [t.numpy() for t in pinned["cont"]], [t.numpy() for t in pinned["cat"]],
                              d["cat_levels"], pinned["y"].numpy(), None if pinned["w"] is None else pinned["w"].numpy(),
-                             pinned["g"].numpy())
+                             pinned["g"].numpy(), asynchronous=asynchronous and not shard_rows and rif_tau is None)
         if shard_rows:
             des.set_row_shard(d["n_a_global"], d["n_b_global"], world, rank)
         if rif_tau is not None:          # decompose_quantile: RIF pre-step on the device (builder.rs:721-737)
@@ -365,7 +477,7 @@ def main():
         if design.n_b not in res_buf:
             res_buf[design.n_b] = ob.PinnedBuffer((design.n_b,))
         rb = res_buf[design.n_b].array
-        if world == 1 or shard_rows:
+        if world == 1 or design.world > 1:       # one GPU, or a row shard (mode N: the library's collectives do the rest)
             return ob.bootstrap(design, reps, ref_kind=ref, norm=normv, seed=2026, residuals_out=rb)
         # mode R inside the library: replicate shard, NCCL all-gather of the statistics device to device, reduction on
         # every rank (ob_boot_opts.shard_replicates); residuals are fetched once, on rank 0
@@ -403,20 +515,22 @@ def main():
 
     # ---- end-to-end leg: pinned host columns -> H2D + pack + bootstrap + D2H, every step ----
     for _ in range(min(args.warmup, 2)):       # untimed: lets the allocator pools reach their steady state
-        dsg = pack(); step(dsg); dsg.close()
+        dsg = pack(True, e2e=True); step(dsg); dsg.close()
     sync()
     t1 = time.perf_counter()
     e2e_ms = []
     for _ in range(args.steps):
         ts = time.perf_counter()
-        dsg = pack()
+        dsg = pack(True, e2e=True)
         out_e = step(dsg)
-        if not (world > 1 and not shard_rows):
-            pack_ms = dsg.pack_timings()          # steady-state pack (the first one pays for the memory pools)
         dsg.close()
         e2e_ms.append((time.perf_counter() - ts) * 1e3)
     sync()
     dt_e = time.perf_counter() - t1
+    if not (world > 1 and not shard_rows):
+        dsg = pack(False)                         # one synchronous pack, untimed: the upload and the pack kernels alone,
+        pack_ms = dsg.pack_timings()              # steady state (the very first pack pays for the memory pools)
+        dsg.close()
     # ---- outcome-refresh leg (callers re-running on the same X with another y): 8 n bytes H2D per step ----
     refresh = None
     if world == 1 and rif_tau is None:
@@ -440,6 +554,21 @@ def main():
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dt, dt_e, refresh = times.tolist()
 
+    # the other multi-GPU configurations of BASELINE.json at the same N, so that the driver's record holds them
+    also = None
+    if world > 1 and args.also != "off" and name.startswith("config3"):
+        del pinned
+        d_keep = {k: d[k] for k in ("n", "cont", "cat_codes", "cat_levels", "weights")}     # hbm_stage_rooflines needs the shapes only
+        d_keep["cont"] = [c[:1] for c in d_keep["cont"]]; d_keep["cat_codes"] = [c[:1] for c in d_keep["cat_codes"]]
+        d_keep["weights"] = None if d_keep["weights"] is None else d_keep["weights"][:1]
+        d = d_keep
+        also = {}
+        also["config4_n5M_k30_rif_B1000"] = measure_also("config4_n5M_k30_rif_B1000", ob, obd, ctx, torch, dist, rank, world, local,
+                                                          shard_rows=False, rif_tau=0.5, steps=3)
+        if world & (world - 1) == 0:
+            also["config5_n100M_k16_B10000"] = measure_also("config5_n100M_k16_B10000", ob, obd, ctx, torch, dist, rank, world, local,
+                                                             shard_rows=True, rif_tau=None, steps=2)
+
     if rank == 0:
         flops, P = algorithmic_flops(n, K, reps)
         flops_rank = flops / world                        # replicates are sharded: per-launch algorithmic work
@@ -451,7 +580,16 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_dict(name, world, shard_rows, rif_tau),
                 "e2e": {"value": reps * args.steps / dt_e, "unit": "reps/s", "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h)},
+                        "d2h_bytes_per_step": int(d2h),
+                        "path": ("ob_design_pack_async (chunked upload + pack on the copy stream, under the replicate generation and "
+                                 "the first Gram launch) -> ob_bootstrap_run" if world == 1 and rif_tau is None else
+                                 "per rank: upload 1/N of the frame -> pack -> ob_design_redistribute_rows (NVLink) -> row-sharded "
+                                 "ob_bootstrap_run (mode N)" if e2e_rowshard else
+                                 "per rank: upload 1/N of the frame -> pack -> ob_design_allgather_rows (NVLink) -> replicate-sharded "
+                                 "ob_bootstrap_run (mode R)" if world > 1 and not shard_rows else
+                                 "ob_design_pack -> ob_bootstrap_run")},
+                "nccl_selftest": selftest,
+                "also": also,
                 "e2e_outcome_refresh": None if not (refresh and world == 1) else
                     {"value": reps * args.steps / refresh, "unit": "reps/s", "h2d_bytes_per_step": int(8 * n),
                      "what": "ob_design_update_outcome (new y from pinned host memory, X resident) + bootstrap per step"},

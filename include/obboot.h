@@ -82,6 +82,17 @@ typedef struct ob_frame_view {
 
 ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* frame, ob_design** out);
 
+/* Asynchronous variant for frames in page-locked memory (ob_host_alloc / ob_host_register; pageable memory works but
+ * overlaps nothing).  Returns as soon as the group split is known -- ob_design_shape answers -- while the columns are
+ * still being uploaded and packed, in row chunks, on the context's copy stream.  ob_bootstrap_run may be called at
+ * once: its replicate generation needs no design rows, and its Gram contraction starts on the rows that have arrived,
+ * so the PCIe transfer disappears under the first kernels.  Contract: the frame's buffers stay valid and unmodified
+ * until ob_design_wait() or the first call that uses the design (ob_bootstrap_run, ob_design_download, ...) has
+ * returned.  Errors found late (negative weight, ols.rs:60-66; code outside its levels) are reported by that call,
+ * and the design is unusable afterwards. */
+ob_status ob_design_pack_async(ob_ctx* ctx, const ob_frame_view* frame, ob_design** out);
+ob_status ob_design_wait(ob_ctx* ctx, ob_design* d);
+
 /* ---- (0) ingest: cleaning and coding on the device --------------------------------------------
  * What the reference does on the host between run()'s clone of the frame (builder.rs:788) and the group split:
  * clean_dataframe (:760-784: drop every row with a null in any used column), create_dummies_manual (:380-418: levels =
@@ -256,6 +267,16 @@ ob_status ob_design_set_row_shard(ob_design* d, int64_t n_a_global, int64_t n_b_
  * variable-size all-gather over the context's communicator (NVLink), so that a rank moves only 1/world of the frame
  * over PCIe.  The result equals ob_design_pack of the whole frame bit for bit. */
 ob_status ob_design_allgather_rows(ob_ctx* ctx, const ob_design* local_slice, ob_design** out);
+
+/* how a design sits inside the whole problem: global group sizes and (world, rank) of its row shard (1, 0 if unsharded) */
+ob_status ob_design_row_shard(const ob_design* d, int64_t* n_a_global, int64_t* n_b_global, int32_t* world, int32_t* rank);
+
+/* Mode N from frame slices: every rank packed a CONTIGUOUS SLICE of the frame (as for ob_design_allgather_rows);
+ * re-cuts each group's rows along ob_row_shard_plan and exchanges them over the communicator (NVLink; point-to-point,
+ * every row moves at most once, and hardly any when the groups are spread evenly over the frame).  The result is
+ * rank's row shard, already marked as such (ob_design_set_row_shard is not needed), bit-identical to packing exactly
+ * the plan's rows.  A rank then uploads 1/world of the frame and never holds more than 1/world of the design. */
+ob_status ob_design_redistribute_rows(ob_ctx* ctx, const ob_design* local_slice, ob_design** out);
 
 /* Host-only debugging aid (no device needed): the work-unit schedule of the Gram kernel for a problem shape -- out8
  * receives up to cap rows of (cta, group, panel, column tile, row segment, pipeline stages, 8-slot groups, half-width);

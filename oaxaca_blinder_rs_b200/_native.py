@@ -27,7 +27,8 @@ SYMBOLS = ["ob_abi_version", "ob_device_count", "ob_ctx_create", "ob_ctx_destroy
            "ob_design_pack_timings", "ob_design_allgather_rows", "ob_design_update_outcome",
            "ob_ingest_begin", "ob_ingest_rows_kept", "ob_ingest_presence", "ob_ingest_finish", "ob_ingest_destroy",
            "ob_debug_gram_schedule", "ob_debug_counts_from_indices", "ob_host_alloc", "ob_host_free",
-           "ob_host_register", "ob_host_unregister", "ob_replicate_shard"]
+           "ob_host_register", "ob_host_unregister", "ob_replicate_shard", "ob_design_pack_async", "ob_design_wait",
+           "ob_design_redistribute_rows", "ob_design_row_shard"]
 
 
 class FrameView(C.Structure):
@@ -134,6 +135,10 @@ def lib() -> C.CDLL:
         L.ob_debug_gram_schedule.restype = C.c_int64
         L.ob_debug_counts_from_indices.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, _U32P, C.c_int64, C.c_int32,
                                                    C.POINTER(C.c_uint16), _IP]
+        L.ob_design_pack_async.argtypes = [C.c_void_p, C.POINTER(FrameView), C.POINTER(C.c_void_p)]
+        L.ob_design_wait.argtypes = [C.c_void_p, C.c_void_p]
+        L.ob_design_row_shard.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _IP, _IP]
+        L.ob_design_redistribute_rows.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.ob_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
         L.ob_host_free.argtypes = [C.c_void_p]
         L.ob_host_free.restype = None

@@ -131,7 +131,10 @@ class Design:
         na, nb, K, nc = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
         N.lib().ob_design_shape(self._h, C.byref(na), C.byref(nb), C.byref(K), C.byref(nc))
         self.n_a, self.n_b, self.K, self.n_cont = na.value, nb.value, K.value, nc.value
-        self.n_a_global, self.n_b_global, self.world, self.rank = self.n_a, self.n_b, 1, 0
+        ga, gb, w, r = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
+        N.lib().ob_design_row_shard(self._h, C.byref(ga), C.byref(gb), C.byref(w), C.byref(r))
+        self.n_a_global, self.n_b_global, self.world, self.rank = ga.value, gb.value, w.value, r.value
+        self._inflight = None          # host columns an asynchronous pack is still reading
 
     @classmethod
     def from_dense(cls, ctx: Context, Xa, ya, wa, Xb, yb, wb, n_cont: int) -> "Design":
@@ -149,8 +152,11 @@ class Design:
 
     @classmethod
     def pack(cls, ctx: Context, cont: Sequence[np.ndarray], cat_codes: Sequence[np.ndarray],
-             cat_levels: Sequence[int], outcome, weights, group) -> "Design":
-        """ob_design_pack from host columns (the cleaned, coded frame at builder.rs:808)."""
+             cat_levels: Sequence[int], outcome, weights, group, asynchronous: bool = False) -> "Design":
+        """ob_design_pack from host columns (the cleaned, coded frame at builder.rs:808).
+        asynchronous=True: ob_design_pack_async -- returns once the group split is known; the columns (keep them alive
+        and unmodified, ideally in page-locked memory) are uploaded and packed under the first kernels of the next
+        bootstrap() call.  The design keeps references to the arrays until then."""
         outcome = np.ascontiguousarray(outcome, dtype=np.float64)
         n = outcome.shape[0]
         cont = [np.ascontiguousarray(c, dtype=np.float64) for c in cont]
@@ -167,8 +173,18 @@ class Design:
         fv.outcome, fv.weights = _dp(outcome), _dp(weights)
         fv.group = group.ctypes.data_as(C.POINTER(C.c_uint8))
         h = C.c_void_p()
+        if asynchronous:
+            ctx.check(N.lib().ob_design_pack_async(ctx._h, C.byref(fv), C.byref(h)))
+            des = cls(ctx, h)
+            des._inflight = (cont, cats, outcome, weights, group)     # the upload reads these until the first use / wait()
+            return des
         ctx.check(N.lib().ob_design_pack(ctx._h, C.byref(fv), C.byref(h)))
         return cls(ctx, h)
+
+    def wait(self):
+        """ob_design_wait: completes an asynchronous pack (raises its deferred errors)."""
+        self.ctx.check(N.lib().ob_design_wait(self.ctx._h, self._h))
+        self._inflight = None
 
     def download(self):
         """get_data_matrices() equivalent (builder.rs:252-291): (Xa, ya, wa, Xb, yb, wb) row-major."""
@@ -182,6 +198,13 @@ class Design:
         (identical on every rank) assembled over the context's communicator."""
         h = C.c_void_p()
         self.ctx.check(N.lib().ob_design_allgather_rows(self.ctx._h, self._h, C.byref(h)))
+        return Design(self.ctx, h)
+
+    def redistribute_rows(self) -> "Design":
+        """ob_design_redistribute_rows: this design holds rank's contiguous frame slice; returns rank's ROW SHARD (mode N),
+        the rows exchanged over the context's communicator."""
+        h = C.c_void_p()
+        self.ctx.check(N.lib().ob_design_redistribute_rows(self.ctx._h, self._h, C.byref(h)))
         return Design(self.ctx, h)
 
     def pack_timings(self):
@@ -405,7 +428,10 @@ def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequ
         a["rep_beta_b"] = np.empty((max(nrep, 1), K))
     for k, v in a.items():
         setattr(r, k, _ip(v) if v.dtype == np.int32 else _dp(v))
-    ctx.check(N.lib().ob_bootstrap_run(ctx._h, design._h, C.byref(o), C.byref(r)))
+    try:
+        ctx.check(N.lib().ob_bootstrap_run(ctx._h, design._h, C.byref(o), C.byref(r)))
+    finally:
+        design._inflight = None        # an asynchronous pack has completed (or failed) by now
     out = dict(a)
     for k in ("rep_stats", "rep_status", "rep_beta_a", "rep_beta_b"):
         if k in out:

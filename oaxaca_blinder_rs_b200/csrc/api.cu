@@ -21,6 +21,13 @@ struct ob_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_side = nullptr;  // point-estimate residuals + their D2H, overlapped with the gather / reduction
+    cudaStream_t stream_copy = nullptr;  // ob_design_pack_async: chunked column uploads + pack, under the bootstrap's first kernels
+    // page-locked landing slots for the deferred flags of asynchronous packs, allocated once per context: pinning and
+    // unpinning host memory per call (cudaHostAlloc / cudaFreeHost) costs milliseconds to hundreds of milliseconds
+    static constexpr int PACK_SLOTS = 8;
+    int* h_pack_flags = nullptr;         // [PACK_SLOTS][4]
+    ob_design* pack_slot_owner[PACK_SLOTS] = {};
+    unsigned pack_seq = 0;
     cudaMemPool_t pool = nullptr;   // stream-ordered workspace pool: freed blocks stay cached between calls
     cudaMemPool_t pool_pack = nullptr;   // separate pool for the pack's column staging, so its many small blocks do
                                          // not fragment the bootstrap workspace (20 GB count buffer at n = 1e7)
@@ -36,7 +43,12 @@ struct ob_ctx {
 
 struct ob_local_group { LocalGroup* g = nullptr; int world = 0; };
 
+struct PendingPack;   // an upload + pack still in flight on the copy stream (ob_design_pack_async)
+
 struct ob_design {
+    PendingPack* pending = nullptr;
+    ob_status failed = OB_OK;        // a deferred pack error (negative weight, bad code): the design is unusable
+    std::string fail_msg;
     ob_ctx* owner = nullptr;         // context that created the design; null once that context has been destroyed
     cudaStream_t stream = nullptr;   // owning context's stream: buffers come from its pack pool and are freed on it
     int device = 0;
@@ -77,6 +89,37 @@ struct DevBuf {
     }
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
+
+// the cleaned, coded frame staged in HBM (input of the pack kernels)
+struct StagedFrame {
+    int64_t n = 0; int n_cont = 0, n_cat = 0;
+    std::vector<DevBuf> cols, cats;     // [n] f64 / int32 level codes
+    DevBuf y, w, grp;                   // outcome, weights (optional), group byte
+    bool weighted = false;
+    double ms_h2d = 0.0;
+};
+
+}  // namespace
+
+// ob_design_pack_async: the frame is uploaded and packed in row chunks on the context's copy stream while the caller
+// goes on (typically straight into ob_bootstrap_run, whose replicate generation needs no design rows at all and whose
+// Gram contraction starts on the leaves that have arrived).  Everything the in-flight work touches lives here.
+struct PendingPack {
+    StagedFrame sf;
+    DevBuf d_bc, d_tot, d_flags, d_cont_ptrs, d_cat_ptrs, d_levels, d_dstart;
+    std::vector<cudaEvent_t> chunk_done;     // recorded on the copy stream after chunk c's rows are packed
+    std::vector<int64_t> rows_ready[2];      // rows of group g that are final once chunk c is done
+    cudaEvent_t ev_begin = nullptr, ev_h2d_end = nullptr;   // timing: first upload .. last pack kernel
+    int* h_flags = nullptr;                  // pinned [4] (a slot of the context's): pack flags, valid after the last chunk
+    int slot = -1;
+    ~PendingPack() {
+        for (cudaEvent_t e : chunk_done) cudaEventDestroy(e);
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_h2d_end) cudaEventDestroy(ev_h2d_end);
+    }
+};
+
+namespace {
 
 // bytes the pool holds but is not using: available to the next call in addition to cudaMemGetInfo's free
 size_t pool_idle_bytes(ob_ctx* ctx) {
@@ -179,8 +222,43 @@ void design_release_device(ob_design* d) {
     }
 }
 
+// Completes an asynchronous pack: waits for the copy stream, releases the staging buffers (on the context's stream,
+// ordered after the last pack kernel), collects timings and the deferred error flags.  quiet: never throws (destroy).
+void pending_finish(ob_design* d, bool quiet = false) {
+    PendingPack* P = d->pending;
+    if (!P) return;
+    ob_ctx* ctx = d->owner;
+    d->pending = nullptr;
+    cudaEvent_t last = P->chunk_done.back();
+    if (ctx) cudaStreamWaitEvent(ctx->stream, last, 0);      // the DevBufs of P are freed on ctx->stream
+    const cudaError_t e = cudaEventSynchronize(last);
+    float ms_all = 0, ms_h2d = 0;
+    cudaEventElapsedTime(&ms_all, P->ev_begin, last);
+    cudaEventElapsedTime(&ms_h2d, P->ev_begin, P->ev_h2d_end);
+    d->ms_h2d = ms_h2d; d->ms_pack = ms_all - ms_h2d;        // what follows the last upload: the exposed part of the pack
+    const int f0 = P->h_flags[0], f1 = P->h_flags[1];
+    if (ctx && P->slot >= 0 && ctx->pack_slot_owner[P->slot] == d) ctx->pack_slot_owner[P->slot] = nullptr;
+    g_alloc_ctx = ctx;
+    const auto t_del = std::chrono::steady_clock::now();
+    delete P;
+    if (getenv("OBBOOT_TRACE"))
+        fprintf(stderr, "[obboot] async pack: staging released in %.3f ms (host)\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_del).count());
+    if (e != cudaSuccess) { d->failed = OB_ERR_CUDA; d->fail_msg = std::string("asynchronous pack failed: ") + cudaGetErrorString(e); }
+    else if (f0) { d->failed = OB_ERR_INVALID_GROUP; d->fail_msg = "Invalid group variable: Weights cannot be negative"; }   // ols.rs:60-66
+    else if (f1) { d->failed = OB_ERR_INVALID_ARG; d->fail_msg = "categorical code outside [0, levels)"; }
+    if (d->failed != OB_OK && !quiet) fail(d->failed, d->fail_msg);
+}
+
 void design_alive(const ob_design* d) {
     if (!d->owner) fail(OB_ERR_INVALID_ARG, "this design's context has been destroyed (designs die with their context)");
+    if (d->failed != OB_OK) fail(d->failed, d->fail_msg);
+}
+
+// entry points that need every row: complete an asynchronous pack first
+void design_ready(const ob_design* d) {
+    design_alive(d);
+    pending_finish(const_cast<ob_design*>(d));
 }
 
 const char* status_text(int s) {
@@ -222,6 +300,8 @@ ob_status ob_ctx_create(int32_t device, ob_ctx** out) {
         ctx->num_sms = prop.multiProcessorCount;
         OB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         OB_CUDA(cudaStreamCreateWithFlags(&ctx->stream_side, cudaStreamNonBlocking));
+        OB_CUDA(cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking));
+        OB_CUDA(cudaHostAlloc((void**)&ctx->h_pack_flags, sizeof(int) * 4 * ob_ctx::PACK_SLOTS, cudaHostAllocDefault));
         cudaMemPoolProps props{};
         props.allocType = cudaMemAllocationTypePinned;
         props.handleTypes = cudaMemHandleTypeNone;
@@ -243,13 +323,16 @@ ob_status ob_ctx_create(int32_t device, ob_ctx** out) {
 void ob_ctx_destroy(ob_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->stream_copy) cudaStreamSynchronize(ctx->stream_copy);
     {   // designs that outlive their context: free their device memory now, leave the host structs to their owners
         std::lock_guard<std::mutex> lk(ctx->designs_mu);
-        for (ob_design* d : ctx->designs) { design_release_device(d); d->owner = nullptr; d->stream = nullptr; }
+        for (ob_design* d : ctx->designs) { pending_finish(d, true); design_release_device(d); d->owner = nullptr; d->stream = nullptr; }
         ctx->designs.clear();
     }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->stream_side) { cudaStreamSynchronize(ctx->stream_side); cudaStreamDestroy(ctx->stream_side); }
+    if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
+    if (ctx->h_pack_flags) cudaFreeHost(ctx->h_pack_flags);
     ctx->comm.reset();
     if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     if (ctx->pool_pack) cudaMemPoolDestroy(ctx->pool_pack);
@@ -356,6 +439,8 @@ ob_status ob_row_shard_plan(int64_t n_group, int32_t world, int32_t rank, int64_
 
 ob_status ob_design_set_row_shard(ob_design* d, int64_t n_a_global, int64_t n_b_global, int32_t world, int32_t rank) {
     if (!d || world < 1 || world > MAX_WORLD || (world & (world - 1)) || rank < 0 || rank >= world) return OB_ERR_INVALID_ARG;
+    if (d->pending) { cudaSetDevice(d->device); pending_finish(d, true); }
+    if (d->failed != OB_OK) return d->failed;
     const RowShard ra = row_shard(n_a_global, rank, world), rb = row_shard(n_b_global, rank, world);
     if (ra.n_local != d->g[0].n || rb.n_local != d->g[1].n) return OB_ERR_INVALID_ARG;   // rows must follow ob_row_shard_plan
     d->g[0].shard = ra; d->g[1].shard = rb;
@@ -370,7 +455,7 @@ ob_status ob_design_allgather_rows(ob_ctx* ctx, const ob_design* local, ob_desig
     if (!ctx || !local || !out) return OB_ERR_INVALID_ARG;
     *out = nullptr;
     return guarded(ctx, [&] {
-        design_alive(local);
+        design_ready(local);
         Comm* comm = ctx->comm.get();
         if (!comm) fail(OB_ERR_NCCL, "ob_design_allgather_rows needs ob_comm_init_* on this context");
         if (local->world != 1) fail(OB_ERR_INVALID_ARG, "the local design is a row shard (mode N); gather applies to frame slices");
@@ -411,12 +496,82 @@ ob_status ob_design_allgather_rows(ob_ctx* ctx, const ob_design* local, ob_desig
     });
 }
 
+// Frame slices -> row shards (mode N) without a host round trip: every rank packed a contiguous slice of the frame
+// (slices in rank order); the rows of each group are re-cut along ob_row_shard_plan and exchanged over the communicator
+// (NVLink).  When the groups are spread evenly over the frame almost nothing moves -- a slice already holds about the
+// rows its rank will own -- and a frame sorted by group still moves every row at most once.
+ob_status ob_design_redistribute_rows(ob_ctx* ctx, const ob_design* local, ob_design** out) {
+    if (!ctx || !local || !out) return OB_ERR_INVALID_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        design_ready(local);
+        Comm* comm = ctx->comm.get();
+        if (!comm) fail(OB_ERR_NCCL, "ob_design_redistribute_rows needs ob_comm_init_* on this context");
+        if (local->world != 1) fail(OB_ERR_INVALID_ARG, "the local design is already a row shard");
+        const int world = comm->world, me = comm->rank;
+        if (world & (world - 1)) fail(OB_ERR_INVALID_ARG, "row shards need a power-of-two world");
+        cudaStream_t st = ctx->stream;
+        std::vector<long long> mine = {(long long)local->g[0].n, (long long)local->g[1].n,
+                                       ((long long)local->K << 32) | ((long long)local->n_cont << 1) | (local->weighted ? 1 : 0),
+                                       (long long)local->n_frame};
+        DevBuf d_mine(sizeof(long long) * 4), d_all(sizeof(long long) * 4 * world);
+        OB_CUDA(cudaMemcpyAsync(d_mine.p, mine.data(), sizeof(long long) * 4, cudaMemcpyHostToDevice, st));
+        comm->allgather(d_mine.p, d_all.p, sizeof(long long) * 4, st);
+        std::vector<long long> all(4 * (size_t)world);
+        OB_CUDA(cudaMemcpyAsync(all.data(), d_all.p, sizeof(long long) * 4 * world, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        for (int r = 0; r < world; ++r)
+            if (all[4 * r + 2] != mine[2]) fail(OB_ERR_INVALID_ARG, "ranks disagree on the design shape (K, n_cont, weights)");
+
+        std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
+        design_register(ctx, d.get()); d->stream = ctx->stream; d->device = ctx->device; d->K = local->K; d->n_cont = local->n_cont; d->V = local->V;
+        d->ldx = local->ldx; d->weighted = local->weighted;
+        d->world = world; d->rank = me;
+        d->n_frame = 0;
+        for (int r = 0; r < world; ++r) d->n_frame += all[4 * r + 3];
+        for (int g = 0; g < 2; ++g) {
+            std::vector<long long> off((size_t)world + 1, 0);          // group rows held by the slices before rank r
+            for (int r = 0; r < world; ++r) off[r + 1] = off[r] + all[4 * r + g];
+            const long long n_glob = off[world];
+            std::vector<RowShard> plan((size_t)world);
+            for (int t = 0; t < world; ++t) plan[t] = row_shard(n_glob, t, world);
+            alloc_group(ctx, d->g[g], plan[me].n_local, d->ldx, d->weighted);
+            cudaFreeAsync(d->g[g].src, st); d->g[g].src = nullptr;      // the frame-row map does not travel
+            d->g[g].shard = plan[me];
+            std::vector<size_t> rows((size_t)world * world, 0), send_row((size_t)world, 0), recv_row((size_t)world, 0);
+            for (int sidx = 0; sidx < world; ++sidx)
+                for (int t = 0; t < world; ++t) {
+                    const long long lo = std::max<long long>(off[sidx], plan[t].row_begin);
+                    const long long hi = std::min<long long>(off[sidx + 1], plan[t].row_begin + plan[t].n_local);
+                    rows[(size_t)sidx * world + t] = hi > lo ? (size_t)(hi - lo) : 0;
+                }
+            for (int r = 0; r < world; ++r) {
+                send_row[r] = (size_t)(std::max<long long>(off[me], plan[r].row_begin) - off[me]);              // in my slice
+                recv_row[r] = (size_t)(std::max<long long>(off[r], plan[me].row_begin) - plan[me].row_begin);   // in my shard
+            }
+            auto exchange = [&](const void* sendbuf, void* recvbuf, size_t row_bytes) {
+                std::vector<size_t> b(rows.size()), so((size_t)world), ro((size_t)world);
+                for (size_t i = 0; i < rows.size(); ++i) b[i] = rows[i] * row_bytes;
+                for (int r = 0; r < world; ++r) { so[r] = send_row[r] * row_bytes; ro[r] = recv_row[r] * row_bytes; }
+                comm->alltoallv(sendbuf, so.data(), recvbuf, ro.data(), b.data(), st);
+                OB_CUDA(cudaStreamSynchronize(st));      // the offset tables live on this stack frame
+            };
+            exchange(local->g[g].X, d->g[g].X, sizeof(double) * (size_t)d->ldx);
+            if (d->weighted) exchange(local->g[g].w, d->g[g].w, sizeof(double));
+            scale_rows_launch(d->g[g], d->ldx, st);
+        }
+        OB_CUDA(cudaStreamSynchronize(st));
+        *out = d.release();
+    });
+}
+
 void ob_design_destroy(ob_design* d) {
     if (!d) return;
     if (ob_ctx* ctx = d->owner) {      // orphaned designs (context already destroyed) hold no device memory any more
         int prev = -1;
         cudaGetDevice(&prev);          // may run on a foreign thread (finalisers): leave its current device as it was
         cudaSetDevice(d->device);
+        pending_finish(d, true);
         {
             std::lock_guard<std::mutex> lk(ctx->designs_mu);
             ctx->designs.erase(d);
@@ -436,8 +591,18 @@ ob_status ob_design_shape(const ob_design* d, int64_t* na, int64_t* nb, int32_t*
     return OB_OK;
 }
 
+ob_status ob_design_row_shard(const ob_design* d, int64_t* n_a_global, int64_t* n_b_global, int32_t* world, int32_t* rank) {
+    if (!d) return OB_ERR_INVALID_ARG;
+    if (n_a_global) *n_a_global = d->g[0].shard.n_global;
+    if (n_b_global) *n_b_global = d->g[1].shard.n_global;
+    if (world) *world = d->world;
+    if (rank) *rank = d->rank;
+    return OB_OK;
+}
+
 ob_status ob_design_pack_timings(const ob_design* d, double* ms_h2d, double* ms_pack_kernels) {
     if (!d) return OB_ERR_INVALID_ARG;
+    if (d->pending) { cudaSetDevice(d->device); pending_finish(const_cast<ob_design*>(d), true); }
     if (ms_h2d) *ms_h2d = d->ms_h2d;
     if (ms_pack_kernels) *ms_pack_kernels = d->ms_pack;
     return OB_OK;
@@ -486,15 +651,6 @@ ob_status ob_design_from_dense(ob_ctx* ctx, int32_t K, int32_t n_cont,
 }  // extern "C"
 
 namespace {
-
-// the cleaned, coded frame staged in HBM (input of the pack kernels)
-struct StagedFrame {
-    int64_t n = 0; int n_cont = 0, n_cat = 0;
-    std::vector<DevBuf> cols, cats;     // [n] f64 / int32 level codes
-    DevBuf y, w, grp;                   // outcome, weights (optional), group byte
-    bool weighted = false;
-    double ms_h2d = 0.0;
-};
 
 // pack kernels over a staged frame -> resident design (prepare_data + split_groups, once)
 std::unique_ptr<ob_design, void (*)(ob_design*)> pack_staged(ob_ctx* ctx, StagedFrame& sf, const int32_t* cat_levels) {
@@ -606,6 +762,127 @@ ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
         t_h2d.collect();
         *out = pack_staged(ctx, sf, f->cat_levels).release();
     });
+}
+
+// Asynchronous pack.  Host part (about a millisecond): upload the group column, count and scan it, size and allocate
+// the design.  Everything else is queued on the copy stream in row chunks -- the column slices of a chunk, then the
+// pack kernel over its blocks -- with one event per chunk that ob_bootstrap_run waits on.
+ob_status ob_design_pack_async(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
+    if (!ctx || !f || !out) return OB_ERR_INVALID_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        if (f->n < 0 || f->n_cont < 0 || f->n_cat < 0) fail(OB_ERR_INVALID_ARG, "bad frame shape");
+        if (f->n && (!f->outcome || !f->group)) fail(OB_ERR_INVALID_ARG, "null frame column");
+        for (int c = 0; c < f->n_cont; ++c) if (!f->cont[c]) fail(OB_ERR_INVALID_ARG, "null predictor column");
+        for (int q = 0; q < f->n_cat; ++q) if (!f->cat_codes[q]) fail(OB_ERR_INVALID_ARG, "null categorical column");
+        const int64_t n = f->n;
+        int K = 1 + f->n_cont;
+        std::vector<int32_t> dummy_start(std::max(f->n_cat, 1), 0);
+        for (int q = 0; q < f->n_cat; ++q) {
+            if (f->cat_levels[q] < 1) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: Could not get reference category");
+            dummy_start[q] = K;
+            K += f->cat_levels[q] - 1;
+        }
+        if (K + 1 > 91) fail(OB_ERR_UNSUPPORTED, "design wider than 90 columns is not supported by the solve kernel");
+        if (n > 0xFFFFFFFFll) fail(OB_ERR_UNSUPPORTED, "frames beyond 2^32 rows (IdxSize is u32 in the reference too)");
+        cudaStream_t st = ctx->stream, sc = ctx->stream_copy;
+        g_alloc_pack = true;
+        std::unique_ptr<PendingPack> P(new PendingPack);
+        P->slot = (int)(ctx->pack_seq++ % ob_ctx::PACK_SLOTS);
+        if (ob_design* prev = ctx->pack_slot_owner[P->slot]) pending_finish(prev, true);   // 8 packs in flight: complete the oldest
+        P->h_flags = ctx->h_pack_flags + 4 * P->slot;
+        P->h_flags[0] = P->h_flags[1] = P->h_flags[2] = P->h_flags[3] = 0;
+        OB_CUDA(cudaEventCreate(&P->ev_begin)); OB_CUDA(cudaEventCreate(&P->ev_h2d_end));
+        StagedFrame& sf = P->sf;
+        sf.n = n; sf.n_cont = f->n_cont; sf.n_cat = f->n_cat; sf.weighted = f->weights != nullptr;
+        sf.cols.resize(f->n_cont); sf.cats.resize(f->n_cat);
+        const size_t nn = (size_t)std::max<int64_t>(n, 1);
+        for (int c = 0; c < f->n_cont; ++c) sf.cols[c].alloc(sizeof(double) * nn);
+        for (int q = 0; q < f->n_cat; ++q) sf.cats[q].alloc(sizeof(int32_t) * nn);
+        sf.y.alloc(sizeof(double) * nn); sf.grp.alloc(nn);
+        if (sf.weighted) sf.w.alloc(sizeof(double) * nn);
+        std::vector<const double*> h_cont(std::max(sf.n_cont, 1), nullptr);
+        std::vector<const int32_t*> h_cat(std::max(sf.n_cat, 1), nullptr);
+        for (int c = 0; c < sf.n_cont; ++c) h_cont[c] = sf.cols[c].as<double>();
+        for (int q = 0; q < sf.n_cat; ++q) h_cat[q] = sf.cats[q].as<int32_t>();
+        P->d_cont_ptrs.alloc(sizeof(void*) * h_cont.size()); P->d_cat_ptrs.alloc(sizeof(void*) * h_cat.size());
+        P->d_levels.alloc(sizeof(int32_t) * std::max(sf.n_cat, 1)); P->d_dstart.alloc(sizeof(int32_t) * dummy_start.size());
+        OB_CUDA(cudaMemcpyAsync(P->d_cont_ptrs.p, h_cont.data(), sizeof(void*) * h_cont.size(), cudaMemcpyHostToDevice, st));
+        OB_CUDA(cudaMemcpyAsync(P->d_cat_ptrs.p, h_cat.data(), sizeof(void*) * h_cat.size(), cudaMemcpyHostToDevice, st));
+        if (sf.n_cat) OB_CUDA(cudaMemcpyAsync(P->d_levels.p, f->cat_levels, sizeof(int32_t) * sf.n_cat, cudaMemcpyHostToDevice, st));
+        OB_CUDA(cudaMemcpyAsync(P->d_dstart.p, dummy_start.data(), sizeof(int32_t) * dummy_start.size(), cudaMemcpyHostToDevice, st));
+
+        PackArgs pa;
+        pa.n = n; pa.n_cont = sf.n_cont; pa.n_cat = sf.n_cat;
+        pa.d_cont = P->d_cont_ptrs.as<const double*>(); pa.d_cat = P->d_cat_ptrs.as<const int32_t*>();
+        pa.d_cat_levels = P->d_levels.as<int32_t>(); pa.d_dummy_start = P->d_dstart.as<int32_t>();
+        pa.d_y = sf.y.as<double>(); pa.d_w = nullptr; pa.d_group = sf.grp.as<uint8_t>();   // weights are checked by the pack kernel
+        pa.K = K; pa.ldx = design_ldx(K + 1);
+
+        // group column first: it alone fixes the group sizes and where every row goes
+        const int nblk = pack_num_blocks(n);
+        P->d_bc.alloc(sizeof(long long) * 2 * (size_t)std::max(nblk, 1)); P->d_tot.alloc(sizeof(long long) * 2); P->d_flags.alloc(sizeof(int) * 4);
+        OB_CUDA(cudaMemsetAsync(P->d_flags.p, 0, sizeof(int) * 4, st));
+        OB_CUDA(cudaEventRecord(P->ev_begin, st));
+        if (n) OB_CUDA(cudaMemcpyAsync(sf.grp.p, f->group, (size_t)n, cudaMemcpyHostToDevice, st));
+        pack_count_scan(pa, P->d_bc.as<long long>(), P->d_tot.as<long long>(), P->d_flags.as<int>(), st);
+        // row chunks (multiples of the pack kernel's 128-row blocks): a first quarter the Gram contraction can start on,
+        // then the rest; small frames go in one piece
+        std::vector<int> cut = {0};
+        if (n >= (1 << 18)) cut.push_back(nblk / 4);
+        cut.push_back(nblk);
+        const int nchunks = (int)cut.size() - 1;
+        long long tot[2];
+        std::vector<long long> base(2 * (size_t)nchunks, 0);
+        OB_CUDA(cudaMemcpyAsync(tot, P->d_tot.p, sizeof tot, cudaMemcpyDeviceToHost, st));
+        for (int c = 1; c < nchunks; ++c)     // rows of each group before the chunk boundary = exclusive scan at that block
+            OB_CUDA(cudaMemcpyAsync(&base[2 * (size_t)c], P->d_bc.as<long long>() + 2 * (size_t)cut[c], 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+
+        std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
+        design_register(ctx, d.get()); d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = sf.n_cont; d->V = K + 1; d->ldx = pa.ldx;
+        d->weighted = sf.weighted;
+        d->n_frame = n;
+        alloc_group(ctx, d->g[0], tot[0], d->ldx, d->weighted, false);
+        alloc_group(ctx, d->g[1], tot[1], d->ldx, d->weighted, false);
+        pa.d_w = sf.weighted ? sf.w.as<double>() : nullptr;
+        // an error from here on must not release buffers the copy stream is still writing
+        struct CopyJoin { cudaStream_t s; bool armed = true; ~CopyJoin() { if (armed) cudaStreamSynchronize(s); } } copy_join{sc};
+        // the copy stream starts once the allocations and the pad-row memsets are ordered before it
+        cudaEvent_t ev_alloc = nullptr;
+        OB_CUDA(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+        OB_CUDA(cudaEventRecord(ev_alloc, st));
+        OB_CUDA(cudaStreamWaitEvent(sc, ev_alloc, 0));
+        cudaEventDestroy(ev_alloc);
+        P->chunk_done.resize((size_t)nchunks, nullptr);
+        for (int c = 0; c < nchunks; ++c) {
+            const int64_t r0 = (int64_t)cut[c] * PACK_BLOCK_ROWS, r1 = std::min<int64_t>(n, (int64_t)cut[c + 1] * PACK_BLOCK_ROWS);
+            const size_t rows = (size_t)std::max<int64_t>(r1 - r0, 0);
+            if (rows) {
+                for (int k = 0; k < f->n_cont; ++k)
+                    OB_CUDA(cudaMemcpyAsync(sf.cols[k].as<double>() + r0, f->cont[k] + r0, sizeof(double) * rows, cudaMemcpyHostToDevice, sc));
+                for (int q = 0; q < f->n_cat; ++q)
+                    OB_CUDA(cudaMemcpyAsync(sf.cats[q].as<int32_t>() + r0, f->cat_codes[q] + r0, sizeof(int32_t) * rows, cudaMemcpyHostToDevice, sc));
+                OB_CUDA(cudaMemcpyAsync(sf.y.as<double>() + r0, f->outcome + r0, sizeof(double) * rows, cudaMemcpyHostToDevice, sc));
+                if (sf.weighted) OB_CUDA(cudaMemcpyAsync(sf.w.as<double>() + r0, f->weights + r0, sizeof(double) * rows, cudaMemcpyHostToDevice, sc));
+            }
+            if (c == nchunks - 1) OB_CUDA(cudaEventRecord(P->ev_h2d_end, sc));
+            pack_scatter(pa, P->d_bc.as<long long>(), d->g[0], d->g[1], P->d_flags.as<int>(), sc, cut[c], cut[c + 1]);
+            if (c == nchunks - 1) OB_CUDA(cudaMemcpyAsync(P->h_flags, P->d_flags.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, sc));
+            OB_CUDA(cudaEventCreate(&P->chunk_done[(size_t)c]));
+            OB_CUDA(cudaEventRecord(P->chunk_done[(size_t)c], sc));
+            for (int g = 0; g < 2; ++g) P->rows_ready[g].push_back(c == nchunks - 1 ? tot[g] : base[2 * (size_t)(c + 1) + g]);
+        }
+        ctx->pack_slot_owner[P->slot] = d.get();
+        d->pending = P.release();
+        copy_join.armed = false;
+        *out = d.release();
+    });
+}
+
+ob_status ob_design_wait(ob_ctx* ctx, ob_design* d) {
+    if (!ctx || !d) return OB_ERR_INVALID_ARG;
+    return guarded(ctx, [&] { design_ready(d); });
 }
 
 // ---- ingest: null filter + dictionary coding on the device ----
@@ -740,7 +1017,7 @@ ob_status ob_design_download(ob_ctx* ctx, const ob_design* d, double* Xa, double
                              double* Xb, double* yb, double* wb) {
     if (!ctx || !d) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
-        design_alive(d);
+        design_ready(d);
         double* Xs[2] = {Xa, Xb}; double* ys[2] = {ya, yb}; double* ws[2] = {wa, wb};
         for (int g = 0; g < 2; ++g) {
             const GroupData& G = d->g[g];
@@ -758,7 +1035,7 @@ ob_status ob_design_download(ob_ctx* ctx, const ob_design* d, double* Xa, double
 ob_status ob_design_update_outcome(ob_ctx* ctx, ob_design* d, const double* y_frame, int64_t n_frame) {
     if (!ctx || !d || !y_frame) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
-        design_alive(d);
+        design_ready(d);
         if (n_frame != d->n_frame) fail(OB_ERR_INVALID_ARG, "outcome length differs from the frame the design was packed from");
         if (!d->g[0].src || !d->g[1].src) fail(OB_ERR_UNSUPPORTED, "this design carries no frame-row map (gathered design)");
         g_alloc_pack = true;
@@ -775,7 +1052,7 @@ ob_status ob_design_update_outcome(ob_ctx* ctx, ob_design* d, const double* y_fr
 ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau) {
     if (!ctx || !d) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
-        design_alive(d);
+        design_ready(d);
         if (d->world > 1) fail(OB_ERR_UNSUPPORTED, "RIF pre-step on a row-sharded design (the quantile needs all rows of a group)");
         for (int g = 0; g < 2; ++g) {
             GroupData& G = d->g[g];
@@ -980,8 +1257,45 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                     EventPair() { OB_CUDA(cudaEventCreate(&a)); OB_CUDA(cudaEventCreate(&b)); }
                     ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
                 } ev;
-                gram_launch(plan, ga, st, ev.a, ev.b);
-                res->gpu_launches += 2;
+                ob_design* dm = const_cast<ob_design*>(d);
+                if (PendingPack* P = dm->pending) {
+                    // the design's upload is still in flight (ob_design_pack_async): contract the leaves whose rows the
+                    // first chunk delivered, then -- once everything has arrived -- the rest.  Same partial tiles, same
+                    // fixed-tree sums as one launch.
+                    int lo[2] = {0, 0}, na[2] = {0, 0}, nb[2];
+                    const bool split = P->chunk_done.size() > 1 && !comm;
+                    for (int g = 0; g < 2; ++g) {
+                        if (split) na[g] = (int)std::min<int64_t>(plan.segs[g], P->rows_ready[g][0] / plan.seg_rows[g]);
+                        nb[g] = plan.segs[g] - na[g];
+                    }
+                    EventPair evA, evB;        // OBBOOT_TRACE: where the two launches sit relative to the upload
+                    OB_CUDA(cudaEventRecord(ev.a, st));
+                    if (split && na[0] + na[1] > 0) {
+                        OB_CUDA(cudaStreamWaitEvent(st, P->chunk_done.front(), 0));
+                        if (tr.on) OB_CUDA(cudaEventRecord(evA.a, st));
+                        gram_launch_leaves(plan, ga, lo, na, st);
+                        if (tr.on) OB_CUDA(cudaEventRecord(evA.b, st));
+                        res->gpu_launches += 1;
+                    }
+                    OB_CUDA(cudaStreamWaitEvent(st, P->chunk_done.back(), 0));
+                    if (tr.on) OB_CUDA(cudaEventRecord(evB.a, st));
+                    gram_launch_leaves(plan, ga, na, nb, st);
+                    OB_CUDA(cudaEventRecord(ev.b, st));
+                    gram_reduce_launch(plan, ga, st);
+                    res->gpu_launches += 2;
+                    if (tr.on) {
+                        OB_CUDA(cudaEventSynchronize(ev.b));
+                        auto rel = [&](cudaEvent_t e) { float ms = -1.f; if (cudaEventElapsedTime(&ms, P->ev_begin, e) != cudaSuccess) { cudaGetLastError(); ms = -1.f; } return ms; };
+                        fprintf(stderr, "[obboot] async pack (ms after its start): chunk 0 packed %.1f, upload done %.1f, all packed %.1f | "
+                                        "gram A %.1f..%.1f (leaves %d+%d), gram B %.1f..%.1f (leaves %d+%d)\n",
+                                rel(P->chunk_done.front()), rel(P->ev_h2d_end), rel(P->chunk_done.back()), rel(evA.a), rel(evA.b), na[0], na[1],
+                                rel(evB.a), rel(ev.b), nb[0], nb[1]);
+                    }
+                    pending_finish(dm);       // host: waits for the copy stream, releases the staging, raises deferred errors
+                } else {
+                    gram_launch(plan, ga, st, ev.a, ev.b);
+                    res->gpu_launches += 2;
+                }
                 t_gram.stop();
                 tr.mark("gram", st, true);
                 if (comm) {
@@ -1196,7 +1510,7 @@ ob_status ob_debug_counts(ob_ctx* ctx, const ob_design* d, uint64_t seed, int64_
                           uint16_t* counts_out) {
     if (!ctx || !d || !counts_out || group < 0 || group > 1 || rep < 0) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
-        design_alive(d);
+        design_ready(d);
         cudaStream_t st = ctx->stream;
         const GroupData& G = d->g[group];
         DevBuf d_C((size_t)G.n_pad * BM * 2), d_colsum(sizeof(long long) * BM), d_flags(sizeof(int) * 4), d_lut(counts_lut_bytes());
@@ -1222,7 +1536,7 @@ ob_status ob_debug_counts_from_indices(ob_ctx* ctx, const ob_design* d, int32_t 
     if (!ctx || !d || !counts_out || group < 0 || group > 1 || reps < 0 || (reps && !idx) || (count_bits != 8 && count_bits != 16))
         return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
-        design_alive(d);
+        design_ready(d);
         cudaStream_t st = ctx->stream;
         const GroupData& G = d->g[group];
         const int cb = count_bits / 8;

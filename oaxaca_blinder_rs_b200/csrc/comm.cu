@@ -39,6 +39,8 @@ struct NcclApi {
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -63,11 +65,13 @@ NcclApi& nccl_api() {
         api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(api.handle, "ncclAllGather"));
         api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
         api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(api.handle, "ncclBroadcast"));
+        api.Send = reinterpret_cast<decltype(api.Send)>(dlsym(api.handle, "ncclSend"));
+        api.Recv = reinterpret_cast<decltype(api.Recv)>(dlsym(api.handle, "ncclRecv"));
         api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(api.handle, "ncclGroupStart"));
         api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(api.handle, "ncclGroupEnd"));
     });
     if (!api.handle || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.AllGather || !api.Broadcast ||
-        !api.GroupStart || !api.GroupEnd)
+        !api.GroupStart || !api.GroupEnd || !api.Send || !api.Recv)
         comm_fail("libnccl.so.2 could not be loaded (set OBBOOT_NCCL_LIB to its path)");
     return api;
 }
@@ -100,6 +104,23 @@ struct NcclComm final : Comm {
         }
         nccl_check(a.GroupEnd(), "ncclGroupEnd");
     }
+    void alltoallv(const void* send, const size_t* send_off, void* recv, const size_t* recv_off, const size_t* bytes,
+                   cudaStream_t st) override {
+        // point-to-point sends and receives of one NCCL group: every block crosses NVLink once, straight into place
+        NcclApi& a = nccl_api();
+        const size_t* mine = bytes + (size_t)rank * world;       // bytes[src * world + dst]
+        if (mine[rank])
+            OB_CUDA(cudaMemcpyAsync(static_cast<char*>(recv) + recv_off[rank], static_cast<const char*>(send) + send_off[rank], mine[rank],
+                                    cudaMemcpyDeviceToDevice, st));
+        nccl_check(a.GroupStart(), "ncclGroupStart");
+        for (int r = 0; r < world; ++r) {
+            if (r == rank) continue;
+            if (mine[r]) nccl_check(a.Send(static_cast<const char*>(send) + send_off[r], mine[r], NCCL_INT8, r, comm, st), "ncclSend");
+            const size_t in = bytes[(size_t)r * world + rank];
+            if (in) nccl_check(a.Recv(static_cast<char*>(recv) + recv_off[r], in, NCCL_INT8, r, comm, st), "ncclRecv");
+        }
+        nccl_check(a.GroupEnd(), "ncclGroupEnd");
+    }
 };
 
 // ------------------------------------------------------------------ in-process transport
@@ -124,7 +145,8 @@ struct LocalGroup {
     int arrived = 0;
     unsigned long long generation = 0;
     std::vector<const void*> ptrs;
-    explicit LocalGroup(int w) : world(w), ptrs((size_t)w, nullptr) {}
+    std::vector<const size_t*> offs;     // alltoallv: every rank's send offsets
+    explicit LocalGroup(int w) : world(w), ptrs((size_t)w, nullptr), offs((size_t)w, nullptr) {}
     void barrier() {
         std::unique_lock<std::mutex> lk(mu);
         const unsigned long long gen = generation;
@@ -174,6 +196,21 @@ struct LocalComm final : Comm {
         for (int r = 0; r < world; ++r)
             if (sizes[r])
                 OB_CUDA(cudaMemcpyAsync(static_cast<char*>(recv) + offsets[r], grp->ptrs[(size_t)r], sizes[r], cudaMemcpyDefault, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        grp->barrier();
+    }
+    void alltoallv(const void* send, const size_t* send_off, void* recv, const size_t* recv_off, const size_t* bytes,
+                   cudaStream_t st) override {
+        OB_CUDA(cudaStreamSynchronize(st));
+        grp->ptrs[(size_t)rank] = send;
+        grp->offs[(size_t)rank] = send_off;
+        grp->barrier();
+        for (int r = 0; r < world; ++r) {      // pull what rank r holds for me
+            const size_t in = bytes[(size_t)r * world + rank];
+            if (in)
+                OB_CUDA(cudaMemcpyAsync(static_cast<char*>(recv) + recv_off[r],
+                                        static_cast<const char*>(grp->ptrs[(size_t)r]) + grp->offs[(size_t)r][rank], in, cudaMemcpyDefault, st));
+        }
         OB_CUDA(cudaStreamSynchronize(st));
         grp->barrier();
     }

@@ -205,8 +205,10 @@ struct PackArgs {
 int pack_num_blocks(int64_t n);
 void pack_count_scan(const PackArgs& a, long long* d_block_counts, long long* d_totals, int* d_flags, cudaStream_t st);
 // pass 3: staged transpose/scatter of the rows into the packed per-group designs
+// blocks [blk0, blk1) of PK_ROWS = 128 frame rows each (blk1 < 0: to the end)
 void pack_scatter(const PackArgs& a, const long long* d_block_base, GroupData ga, GroupData gb, int* d_flags,
-                  cudaStream_t st);
+                  cudaStream_t st, int blk0 = 0, int blk1 = -1);
+constexpr int PACK_BLOCK_ROWS = 128;
 // src[i] = first + i (designs built from dense per-group matrices: the "frame" is group A's rows, then group B's)
 void iota_launch(uint32_t* dst, int64_t n, uint32_t first, cudaStream_t st);
 // outcome refresh: X[r][K] = y[src[r]] (and Xs[r][K] = sqrt(w[r]) * y[src[r]]) for every packed row of the group
@@ -257,6 +259,10 @@ struct Comm {
     virtual void allgather(const void* send, void* recv, size_t bytes, cudaStream_t st) = 0;
     // variable sizes: rank r's `sizes[r]` bytes (its `send`) land at recv + offsets[r] on every rank
     virtual void allgatherv(const void* send, void* recv, const size_t* offsets, const size_t* sizes, cudaStream_t st) = 0;
+    // personalised exchange: bytes[src * world + dst] (the same table on every rank) travel from src's
+    // send + send_off[dst] to dst's recv + recv_off[src]
+    virtual void alltoallv(const void* send, const size_t* send_off, void* recv, const size_t* recv_off, const size_t* bytes,
+                           cudaStream_t st) = 0;
 };
 struct LocalGroup;                       // shared state of an in-process group (ob_local_group)
 LocalGroup* local_group_create(int world);

@@ -73,6 +73,7 @@ struct PackKernelParams {
     const double* const* cont; const int32_t* const* cat; const int32_t* cat_levels; const int32_t* dummy_start;
     const double* y; const double* w; const uint8_t* group;
     const long long* block_base;   // [nblocks][2] exclusive scan
+    int blk0;                      // first block of this launch (chunked pack: ob_design_pack_async)
     double* XA; double* XB; double* wA; double* wB;
     double* XsA; double* XsB;      // sqrt(w)-scaled copies (weighted designs) or nullptr
     uint32_t* srcA; uint32_t* srcB;
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(PK_THREADS) pack_scatter_kernel(const PackKern
     __shared__ int cnt[2];
     __shared__ const double* scont[96];                 // column base pointers: no dependent global load per element
     const int V = p.K + 1, ts = V | 1;
-    const long long row0 = (long long)blockIdx.x * PK_ROWS;
+    const int blk = blockIdx.x + p.blk0;
+    const long long row0 = (long long)blk * PK_ROWS;
     const int rows = (int)min((long long)PK_ROWS, p.n - row0);
     const int tid = threadIdx.x;
 
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_scatter_kernel(const PackKern
             tile[t * ts + start + lv - 1] = (t < rows && code == lv) ? 1.0 : 0.0;
     }
     __syncthreads();
-    const long long baseA = p.block_base[2 * blockIdx.x], baseB = p.block_base[2 * blockIdx.x + 1];
+    const long long baseA = p.block_base[2 * blk], baseB = p.block_base[2 * blk + 1];
     // ---- write out: one warp per packed row, lanes over its V contiguous columns; the sqrt(w)-scaled copy
     //      (ols.rs:68-78) is written in the same pass ----
     const int warp = tid >> 5, lane = tid & 31;
@@ -166,6 +168,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_scatter_kernel(const PackKern
         for (int r = warp; r < cnt[g]; r += PK_THREADS / 32) {
             const int t = src[r];
             const double wv = p.w ? p.w[row0 + t] : 1.0;
+            if (wv < 0.0 && lane == 0) atomicOr(&p.flags[0], 1);   // ols.rs:60-66 (the chunked pack has no earlier look at w)
             const double sw = sqrt(wv);
             double* xr = X + (base + r) * p.ldx;
             for (int c = lane; c < p.ldx; c += 32) {          // pad columns [V, ldx) are written as zeros here
@@ -193,15 +196,15 @@ void pack_count_scan(const PackArgs& a, long long* d_block_counts, long long* d_
 }
 
 void pack_scatter(const PackArgs& a, const long long* d_block_base, GroupData ga, GroupData gb, int* d_flags,
-                  cudaStream_t st) {
-    const int nb = pack_num_blocks(a.n);
-    if (nb == 0) return;
+                  cudaStream_t st, int blk0, int blk1) {
+    const int nb = (blk1 < 0 ? pack_num_blocks(a.n) : blk1) - blk0;
+    if (nb <= 0) return;
     PackKernelParams p;
     p.n = a.n; p.n_cont = a.n_cont; p.n_cat = a.n_cat; p.K = a.K; p.ldx = a.ldx;
     p.cont = a.d_cont; p.cat = a.d_cat; p.cat_levels = a.d_cat_levels; p.dummy_start = a.d_dummy_start;
     p.y = a.d_y; p.w = a.d_w; p.group = a.d_group; p.block_base = d_block_base;
     p.XA = ga.X; p.XB = gb.X; p.wA = ga.w; p.wB = gb.w; p.XsA = ga.Xs; p.XsB = gb.Xs;
-    p.srcA = ga.src; p.srcB = gb.src; p.flags = d_flags;
+    p.srcA = ga.src; p.srcB = gb.src; p.flags = d_flags; p.blk0 = blk0;
     const int V = a.K + 1;
     const size_t smem = sizeof(double) * (size_t)PK_ROWS * (V | 1);
     OB_CUDA(cudaFuncSetAttribute(pack_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

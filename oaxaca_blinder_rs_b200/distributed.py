@@ -125,3 +125,15 @@ def pack_replicated(ctx, d: dict, rank: int, world: int):
     full = loc.allgather_rows()
     loc.close()
     return full
+
+
+def pack_row_shard_from_slice(ctx, d: dict, rank: int, world: int):
+    """Mode N upload without host-side row selection: this rank uploads and packs its contiguous frame slice, then
+    ob_design_redistribute_rows re-cuts the groups' rows along the row-shard plan over the communicator.  Equals
+    pack_row_shard (bit for bit) while the host touches only its 1/world of the frame."""
+    from . import core
+    sl = frame_slice(d, rank, world)
+    loc = core.Design.pack(ctx, sl["cont"], sl["cat_codes"], sl["cat_levels"], sl["outcome"], sl["weights"], sl["group"])
+    shard = loc.redistribute_rows()
+    loc.close()
+    return shard

@@ -42,7 +42,7 @@ def run_both(ob, orc, ctx, Xa, ya, wa, Xb, yb, wb, n_cont, ref, norm, reps, seed
     return gpu, ref_out
 
 
-def compare(gpu, ref, tol=RTOL, orc=None):
+def compare(gpu, ref, tol=RTOL, orc=None, cancel_floor=0.0):
     """Point estimates, every numerically well-posed replicate, and the reduction.
 
     A resample whose design is rank-deficient up to rounding (oracle's smallest relative Cholesky pivot
@@ -59,7 +59,8 @@ def compare(gpu, ref, tol=RTOL, orc=None):
     assert relerr_to_scale(gpu["residuals_b"], p["resid_b"], yscale) <= tol, "residuals_b"
     well = ref["rep_min_pivot"] >= 1e-9
     np.testing.assert_array_equal(gpu["rep_status"][well], ref["rep_status"][well])
-    assert relerr(gpu["rep_stats"][well], ref["rep_stats"][well]) <= tol, worst(gpu["rep_stats"][well], ref["rep_stats"][well])
+    assert relerr(gpu["rep_stats"][well], ref["rep_stats"][well], cancel_floor=cancel_floor) <= tol, \
+        worst(gpu["rep_stats"][well], ref["rep_stats"][well], cancel_floor=cancel_floor)
     assert relerr(gpu["rep_beta_a"][well], ref["rep_beta_a"][well]) <= tol, worst(gpu["rep_beta_a"][well], ref["rep_beta_a"][well])
     assert relerr(gpu["rep_beta_b"][well], ref["rep_beta_b"][well]) <= tol, worst(gpu["rep_beta_b"][well], ref["rep_beta_b"][well])
     if np.array_equal(gpu["rep_status"], ref["rep_status"]) and well.all():
@@ -95,7 +96,9 @@ def test_golden_fixtures_on_gpu(ob, orc, ctx, golden, fx, ref):
         np.testing.assert_allclose(gpu[k], exp[k], rtol=0, atol=1e-9, err_msg=k)
     assert abs(gpu["total_gap"] - 10.0) < 1e-9 and abs(gpu["two_fold"].sum() - gpu["total_gap"]) < 1e-9
     np.testing.assert_allclose(gpu["residuals_b"], exp["resid_b"], atol=1e-9)
-    compare(gpu, ref_out)
+    # 5 rows per group: resampled coefficients of the two groups can agree to ~6 digits, so a detailed term
+    # xbar_j (beta_a_j - beta*_j) cancels that far below its operands -- see helpers.relerr(cancel_floor)
+    compare(gpu, ref_out, cancel_floor=1e-3)
     assert 0 < gpu["n_ok"] <= 60
 
 

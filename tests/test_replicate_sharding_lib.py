@@ -87,8 +87,9 @@ def test_library_replicate_sharding_index_stream_and_failures(orc):
     from oaxaca_blinder_rs_b200 import synth
     from helpers import relerr
     d = synth.make_wage(600, 2, cat_levels=(4,), weights=False, seed=3)
-    rare = np.flatnonzero(d["cat_codes"][0] == 3)
-    d["cat_codes"][0][rare[2:]] = 0                    # level 3 survives in two rows only: many resamples lose it
+    for g in (0, 1):                                   # level 3 survives in two rows per group: many resamples lose it
+        rare = np.flatnonzero((d["cat_codes"][0] == 3) & (d["group"] == g))
+        d["cat_codes"][0][rare[2:]] = 0
     Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
     reps = 150
     ia, ib = orc.index_stream(8, reps, 0, len(ya)), orc.index_stream(8, reps, 1, len(yb))

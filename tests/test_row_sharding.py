@@ -249,3 +249,51 @@ def test_frame_slices_tile_the_frame():
         np.testing.assert_array_equal(np.concatenate([s["outcome"] for s in sl]), d["outcome"])
         np.testing.assert_array_equal(np.concatenate([s["group"] for s in sl]), d["group"])
         np.testing.assert_array_equal(np.concatenate([s["cat_codes"][0] for s in sl]), d["cat_codes"][0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,sort_by_group", [(2, False), (4, False), (4, True), (8, False)])
+def test_redistributed_slices_equal_row_shards(world, sort_by_group):
+    """ob_design_redistribute_rows: frame slices -> row shards over the communicator.  The shard equals packing exactly
+    the plan's rows (download bit-identical), and the sharded bootstrap equals one GPU -- also for a frame sorted by
+    group, where whole slices change hands."""
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import core, synth, distributed as obd
+    d = synth.make_wage(50_003, 3, cat_levels=(3,), weights=True, seed=13)
+    if sort_by_group:
+        order = np.argsort(d["group"], kind="stable")
+        for k in ("outcome", "weights", "group"):
+            d[k] = d[k][order]
+        d["cont"] = [c[order] for c in d["cont"]]
+        d["cat_codes"] = [c[order] for c in d["cat_codes"]]
+    norm = [ob.NormVar(m, i) for m, i in synth.norm_spec(d)]
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+    one = ob.bootstrap(des, 150, ref_kind=ob.REF_POOLED, norm=norm, seed=41, want_rep=True)
+    des.close(); ctx.close()
+    grp = core.LocalGroup(world)
+    outs, errs = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            c = ob.Context(0)
+            c.init_local(grp, r)
+            shard = obd.pack_row_shard_from_slice(c, d, r, world)
+            direct = obd.pack_row_shard(c, d, r, world)
+            assert (shard.world, shard.rank, shard.n_a_global, shard.n_b_global) == (world, r, direct.n_a_global, direct.n_b_global)
+            same = all(np.array_equal(a, b_, equal_nan=True) for a, b_ in zip(shard.download(), direct.download()))
+            direct.close()
+            outs[r] = (same, ob.bootstrap(shard, 150, ref_kind=ob.REF_POOLED, norm=norm, seed=41, want_rep=True))
+            shard.close(); c.close()
+        except Exception as ex:  # noqa: BLE001
+            errs[r] = ex
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert all(e is None for e in errs), errs
+    for same, o in outs:
+        assert same
+        for k in ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper", "p_value"):
+            assert _same(o[k], one[k]), k

@@ -25,6 +25,11 @@ def _worker(rank, world, port, q):
     loc = synth.make_wage_rows(400_000, 6, cat_levels=(4,), weights=True, chunk=1 << 16, rank=rank, world=world)
     des = obd.pack_row_shard(ctx, loc, rank, world)
     out = ob.bootstrap(des, reps, ref_kind=ob.REF_WEIGHTED, norm=norm, seed=5, want_rep=True, max_workspace_bytes=80_000_000)
+    # frame slices -> row shards over NCCL send/recv: the same shard, bit for bit
+    re = obd.pack_row_shard_from_slice(ctx, full, rank, world)
+    for a, b_ in zip(re.download(), des.download()):
+        assert np.array_equal(a, b_, equal_nan=True)
+    re.close()
     des.close()
     # mode R upload over the same communicator: frame slices packed per rank, full design gathered over NVLink
     rep = obd.pack_replicated(ctx, full, rank, world)
