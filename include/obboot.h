@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define OBBOOT_ABI_VERSION 3
+#define OBBOOT_ABI_VERSION 4
 
 /* ---- errors: OaxacaError variants (error.rs:6-19) + device errors ------------------------- */
 typedef enum ob_status {
@@ -153,6 +153,17 @@ ob_status ob_design_update_outcome(ob_ctx* ctx, ob_design* d, const double* y_fr
  * quantile sweep (tau = 0.1, 0.5, 0.9 ...) packs once and calls apply_rif + ob_bootstrap_run per quantile: every call
  * transforms the RAW outcome, never an earlier RIF. */
 ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau);
+/* Quantile sweep in one pass (decompose_quantile called for tau = 0.1, 0.5, 0.9 ..., builder.rs:711-757): the design
+ * gets one RIF outcome column per quantile (1 <= n_tau <= 8), side by side.  ob_bootstrap_run then contracts X'WX once
+ * and X'Wy once per quantile in the same pass (P = K(K+1)/2 + n_tau K Gram columns instead of n_tau (K(K+1)/2 + K)),
+ * factors each replicate's Gram once and solves n_tau right-hand sides.  Every per-outcome array of ob_result grows a
+ * leading quantile dimension: point_stats, std_err, p_value, ci_*, t_stat [n_tau x S]; beta_star, beta_a, beta_b
+ * [n_tau x K]; rep_stats [rows x n_tau x S]; rep_beta_* [rows x n_tau x K]; residuals_b [n_tau x n_b];
+ * total_gap_multi [n_tau].  All quantiles see the same resamples (the reference draws fresh ones per call; with a
+ * fixed seed ours are the same per call anyway), so each quantile's results equal a single-quantile run bit for bit.
+ * ob_design_apply_rif(tau) is the n_tau = 1 case; ob_design_update_outcome returns to one raw outcome. */
+ob_status ob_design_apply_rif_multi(ob_ctx* ctx, ob_design* d, const double* taus, int32_t n_tau);
+ob_status ob_design_num_outcomes(const ob_design* d, int32_t* n_out);
 
 /* ---- (2)-(5) bootstrap ---------------------------------------------------------------------*/
 typedef struct ob_boot_opts {
@@ -216,6 +227,7 @@ typedef struct ob_result {
     double ms_gram_kernel;   /* the DMMA contraction kernel alone (ms_gram also covers the split-n partial reduction) */
     int32_t gpu_launches;    /* kernels launched by this call */
     double ms_comm;          /* row-sharded runs: time inside the collectives (also contained in ms_counts / ms_total) */
+    double* total_gap_multi; /* [n_tau] optional: total gap per outcome of a multi-outcome design (total_gap = the first) */
 } ob_result;
 
 int32_t ob_num_stats(int32_t K, int32_t n_norm, const int32_t* norm_has_base);

@@ -28,7 +28,7 @@ SYMBOLS = ["ob_abi_version", "ob_device_count", "ob_ctx_create", "ob_ctx_destroy
            "ob_ingest_begin", "ob_ingest_rows_kept", "ob_ingest_presence", "ob_ingest_finish", "ob_ingest_destroy",
            "ob_debug_gram_schedule", "ob_debug_counts_from_indices", "ob_host_alloc", "ob_host_free",
            "ob_host_register", "ob_host_unregister", "ob_replicate_shard", "ob_design_pack_async", "ob_design_wait",
-           "ob_design_redistribute_rows", "ob_design_row_shard"]
+           "ob_design_redistribute_rows", "ob_design_row_shard", "ob_design_apply_rif_multi", "ob_design_num_outcomes"]
 
 
 class FrameView(C.Structure):
@@ -66,7 +66,7 @@ class Result(C.Structure):
                 ("t_stat", _DP), ("rep_stats", _DP), ("rep_status", _IP), ("rep_beta_a", _DP), ("rep_beta_b", _DP),
                 ("ms_counts", C.c_double), ("ms_gram", C.c_double), ("ms_solve", C.c_double),
                 ("ms_reduce", C.c_double), ("ms_total", C.c_double), ("ms_gram_kernel", C.c_double),
-                ("gpu_launches", C.c_int32), ("ms_comm", C.c_double)]
+                ("gpu_launches", C.c_int32), ("ms_comm", C.c_double), ("total_gap_multi", _DP)]
 
 
 def build(force: bool = False) -> str:
@@ -137,6 +137,8 @@ def lib() -> C.CDLL:
                                                    C.POINTER(C.c_uint16), _IP]
         L.ob_design_pack_async.argtypes = [C.c_void_p, C.POINTER(FrameView), C.POINTER(C.c_void_p)]
         L.ob_design_wait.argtypes = [C.c_void_p, C.c_void_p]
+        L.ob_design_apply_rif_multi.argtypes = [C.c_void_p, C.c_void_p, _DP, C.c_int32]
+        L.ob_design_num_outcomes.argtypes = [C.c_void_p, _IP]
         L.ob_design_row_shard.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _IP, _IP]
         L.ob_design_redistribute_rows.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.ob_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]

@@ -229,6 +229,18 @@ class Design:
     def apply_rif(self, tau: float):
         self.ctx.check(N.lib().ob_design_apply_rif(self.ctx._h, self._h, float(tau)))
 
+    def apply_rif_multi(self, taus: Sequence[float]):
+        """ob_design_apply_rif_multi: one RIF outcome column per quantile; the next bootstrap() contracts the Gram once
+        for all of them and returns every per-outcome array with a leading quantile dimension."""
+        t = np.ascontiguousarray(list(taus), dtype=np.float64)
+        self.ctx.check(N.lib().ob_design_apply_rif_multi(self.ctx._h, self._h, _dp(t), len(t)))
+
+    @property
+    def n_outcomes(self) -> int:
+        t = C.c_int32()
+        N.lib().ob_design_num_outcomes(self._h, C.byref(t))
+        return t.value
+
     def debug_counts(self, seed: int, rep: int, group: int) -> np.ndarray:
         n = self.n_a if group == 0 else self.n_b
         out = np.empty(n, dtype=np.uint16)
@@ -414,18 +426,21 @@ def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequ
     nrep = (rep_end if rep_end > 0 else reps) - rep_begin     # shard_replicates: rep_* outputs cover all reps rows
 
     r = N.Result()
-    a = dict(point_stats=np.empty(S), xa_mean=np.empty(K), xb_mean=np.empty(K), beta_star=np.empty(K),
-             beta_a=np.empty(K), beta_b=np.empty(K), std_err=np.full(S, np.nan), p_value=np.full(S, np.nan),
-             ci_lower=np.full(S, np.nan), ci_upper=np.full(S, np.nan), t_stat=np.zeros(S))
+    T = design.n_outcomes                  # > 1 after apply_rif_multi: a leading quantile dimension on per-outcome arrays
+    lead = (T,) if T > 1 else ()
+    a = dict(point_stats=np.empty(lead + (S,)), xa_mean=np.empty(K), xb_mean=np.empty(K), beta_star=np.empty(lead + (K,)),
+             beta_a=np.empty(lead + (K,)), beta_b=np.empty(lead + (K,)), std_err=np.full(lead + (S,), np.nan),
+             p_value=np.full(lead + (S,), np.nan), ci_lower=np.full(lead + (S,), np.nan), ci_upper=np.full(lead + (S,), np.nan),
+             t_stat=np.zeros(lead + (S,)), total_gap_multi=np.empty(T))
     if want_residuals:
         if residuals_out is not None:
-            assert residuals_out.dtype == np.float64 and residuals_out.shape == (design.n_b,) and residuals_out.flags.c_contiguous
-        a["residuals_b"] = residuals_out if residuals_out is not None else np.empty(design.n_b)
+            assert residuals_out.dtype == np.float64 and residuals_out.shape == lead + (design.n_b,) and residuals_out.flags.c_contiguous
+        a["residuals_b"] = residuals_out if residuals_out is not None else np.empty(lead + (design.n_b,))
     if want_rep or skip_reduce:
-        a["rep_stats"] = np.empty((max(nrep, 1), S))
+        a["rep_stats"] = np.empty((max(nrep, 1),) + lead + (S,))
         a["rep_status"] = np.zeros(max(nrep, 1), dtype=np.int32)
-        a["rep_beta_a"] = np.empty((max(nrep, 1), K))
-        a["rep_beta_b"] = np.empty((max(nrep, 1), K))
+        a["rep_beta_a"] = np.empty((max(nrep, 1),) + lead + (K,))
+        a["rep_beta_b"] = np.empty((max(nrep, 1),) + lead + (K,))
     for k, v in a.items():
         setattr(r, k, _ip(v) if v.dtype == np.int32 else _dp(v))
     try:
@@ -436,13 +451,14 @@ def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequ
     for k in ("rep_stats", "rep_status", "rep_beta_a", "rep_beta_b"):
         if k in out:
             out[k] = out[k][:nrep]
-    out.update(total_gap=r.total_gap, n_ok=int(r.n_ok), S=S,
-               two_fold=a["point_stats"][:2].copy(), three_fold=a["point_stats"][2:5].copy(),
+    ps = a["point_stats"]
+    out.update(total_gap=r.total_gap, n_ok=int(r.n_ok), S=S, n_outcomes=T,
+               two_fold=ps[..., :2].copy(), three_fold=ps[..., 2:5].copy(),
                timings_ms=dict(counts=r.ms_counts, gram=r.ms_gram, gram_main=r.ms_gram_kernel, solve=r.ms_solve,
                                reduce=r.ms_reduce, total=r.ms_total, comm=r.ms_comm),
                gpu_launches=int(r.gpu_launches))
     D = (S - 5) // 2
-    out["det_expl"], out["det_unexpl"] = a["point_stats"][5:5 + D].copy(), a["point_stats"][5 + D:].copy()
+    out["det_expl"], out["det_unexpl"] = ps[..., 5:5 + D].copy(), ps[..., 5 + D:].copy()
     return out
 
 

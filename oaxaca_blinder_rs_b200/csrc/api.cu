@@ -53,6 +53,7 @@ struct ob_design {
     cudaStream_t stream = nullptr;   // owning context's stream: buffers come from its pack pool and are freed on it
     int device = 0;
     int K = 0, n_cont = 0, V = 0, ldx = 0;
+    int T = 1;                       // outcome columns K .. K+T-1 of a design row (ob_design_apply_rif_multi: one per quantile)
     bool weighted = false;
     int64_t n_frame = 0;             // rows of the frame the design was packed from (ob_design_update_outcome)
     int world = 1, rank = 0;         // row sharding (mode N): this design holds rank's rows of a world-way split
@@ -1044,30 +1045,60 @@ ob_status ob_design_update_outcome(ob_ctx* ctx, ob_design* d, const double* y_fr
         for (int g = 0; g < 2; ++g) {
             update_outcome_launch(d->g[g], d->K, d->ldx, d_y.as<double>(), ctx->stream);
             if (d->g[g].y_raw) { cudaFreeAsync(d->g[g].y_raw, ctx->stream); d->g[g].y_raw = nullptr; }   // new raw outcome
+            d->T = 1; d->V = d->K + 1;      // back to a single outcome column
         }
         OB_CUDA(cudaStreamSynchronize(ctx->stream));
     });
 }
 
-ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau) {
-    if (!ctx || !d) return OB_ERR_INVALID_ARG;
+// One RIF outcome per quantile, side by side in the design rows (columns K .. K+T-1): a quantile sweep then costs ONE
+// pass of the Gram contraction -- X'WX is shared, only K more columns of X'Wy per extra quantile -- instead of T.
+ob_status ob_design_apply_rif_multi(ob_ctx* ctx, ob_design* d, const double* taus, int32_t n_tau) {
+    if (!ctx || !d || !taus) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
         design_ready(d);
+        if (n_tau < 1 || n_tau > 8) fail(OB_ERR_INVALID_ARG, "1 to 8 quantiles per pass");
         if (d->world > 1) fail(OB_ERR_UNSUPPORTED, "RIF pre-step on a row-sharded design (the quantile needs all rows of a group)");
+        if (d->K + n_tau > 91) fail(OB_ERR_UNSUPPORTED, "design plus outcome columns wider than 91");
+        cudaStream_t st = ctx->stream;
+        const int K = d->K;
+        const int ldx_new = std::max(d->ldx, design_ldx(K + n_tau));
         for (int g = 0; g < 2; ++g) {
             GroupData& G = d->g[g];
             if (!G.y_raw && G.n > 0) {   // first transform: keep the raw outcome, later quantiles start from it again
-                OB_CUDA(cudaMallocFromPoolAsync((void**)&G.y_raw, sizeof(double) * (size_t)G.n, ctx->pool_design, ctx->stream));
-                OB_CUDA(cudaMemcpy2DAsync(G.y_raw, sizeof(double), G.X + d->K, sizeof(double) * d->ldx, sizeof(double), (size_t)G.n,
-                                          cudaMemcpyDeviceToDevice, ctx->stream));
+                OB_CUDA(cudaMallocFromPoolAsync((void**)&G.y_raw, sizeof(double) * (size_t)G.n, ctx->pool_design, st));
+                OB_CUDA(cudaMemcpy2DAsync(G.y_raw, sizeof(double), G.X + K, sizeof(double) * d->ldx, sizeof(double), (size_t)G.n,
+                                          cudaMemcpyDeviceToDevice, st));
             }
+            if (ldx_new != d->ldx) {     // make room for the outcome columns: rows move to a wider stride, once
+                const size_t xbytes = sizeof(double) * (size_t)G.n_pad * ldx_new;
+                double* X2 = nullptr;
+                OB_CUDA(cudaMallocFromPoolAsync((void**)&X2, xbytes, ctx->pool_design, st));
+                relayout_launch(G.X, d->ldx, X2, ldx_new, G.n_pad, K, st);
+                cudaFreeAsync(G.X, st); G.X = X2;
+                if (G.Xs) {
+                    cudaFreeAsync(G.Xs, st); G.Xs = nullptr;
+                    OB_CUDA(cudaMallocFromPoolAsync((void**)&G.Xs, xbytes, ctx->pool_design, st));
+                }
+            }
+        }
+        d->ldx = ldx_new; d->T = n_tau; d->V = K + n_tau;
+        for (int g = 0; g < 2; ++g) {
             const size_t sb = rif_scratch_bytes(d->g[g].n);
             DevBuf scratch(sb);
-            rif_transform(d->g[g], d->K, d->ldx, tau, scratch.p, sb, ctx->stream);
-            scale_rows_launch(d->g[g], d->ldx, ctx->stream);   // the RIF outcome is weighted like any outcome
-            OB_CUDA(cudaStreamSynchronize(ctx->stream));
+            for (int t = 0; t < n_tau; ++t) rif_transform(d->g[g], K + t, d->ldx, taus[t], scratch.p, sb, st);
+            scale_rows_launch(d->g[g], d->ldx, st);   // the RIF outcomes are weighted like any outcome
+            OB_CUDA(cudaStreamSynchronize(st));
         }
     });
+}
+
+ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau) { return ob_design_apply_rif_multi(ctx, d, &tau, 1); }
+
+ob_status ob_design_num_outcomes(const ob_design* d, int32_t* n_out) {
+    if (!d || !n_out) return OB_ERR_INVALID_ARG;
+    *n_out = d->T;
+    return OB_OK;
 }
 
 ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_result* res) {
@@ -1075,7 +1106,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
     return guarded(ctx, [&] {
         design_alive(d);
         cudaStream_t st = ctx->stream;
-        const int K = d->K, V = d->V;
+        const int K = d->K, T = d->T;
         if (o->ref_kind < 0 || o->ref_kind > 3) fail(OB_ERR_INVALID_ARG, "ref_kind out of range");
         if (o->reps < 0 || o->n_norm < 0) fail(OB_ERR_INVALID_ARG, "negative reps / n_norm");
         // mode R inside the library: this rank's contiguous share of the global replicate ids
@@ -1103,6 +1134,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         for (int t = 0; t < n_idx; ++t)
             if (o->norm_idx[t] < 0 || o->norm_idx[t] >= K) fail(OB_ERR_INVALID_ARG, "norm_idx outside the design");
         const int D = K + n_base, S = 5 + 2 * D;
+        const int SE = T * S, KE = T * K;     // per slot: T outcomes (a quantile sweep) x S statistics / K coefficients
         const bool index_mode = o->idx_a != nullptr || o->idx_b != nullptr;
         if (index_mode && nrep > 0 && (!o->idx_a || !o->idx_b)) fail(OB_ERR_INVALID_ARG, "index stream needs both idx_a and idx_b");
         if (o->count_bits != 0 && o->count_bits != 8 && o->count_bits != 16) fail(OB_ERR_INVALID_ARG, "count_bits must be 0, 8 or 16");
@@ -1127,14 +1159,15 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         // ---- outputs over all slots of this shard (slot 0 = point estimate) ----
         const int64_t slots = 1 + nrep;
         const bool want_beta = res->rep_beta_a || res->rep_beta_b || res->beta_a || res->beta_b;
-        DevBuf d_stats(sizeof(double) * (size_t)slots * S), d_status(sizeof(int) * (size_t)slots);
-        DevBuf d_ba(want_beta ? sizeof(double) * (size_t)slots * K : 0), d_bb(want_beta ? sizeof(double) * (size_t)slots * K : 0);
-        DevBuf d_point(sizeof(double) * (5 * (size_t)K + 1));
+        DevBuf d_stats(sizeof(double) * (size_t)slots * SE), d_status(sizeof(int) * (size_t)slots);
+        DevBuf d_ba(want_beta ? sizeof(double) * (size_t)slots * KE : 0), d_bb(want_beta ? sizeof(double) * (size_t)slots * KE : 0);
+        const size_t PE = 5 * (size_t)K + 1;           // point_extra per outcome
+        DevBuf d_point(sizeof(double) * PE * T);
         DevBuf d_flags(sizeof(int) * 4);
 
         // ---- batch the multiplicity matrix by panels under the workspace budget ----
-        const int ntiles = gram_ntiles(V);
-        const int Pld = gram_pld(V);
+        const int ntiles = gram_ntiles(K, T);
+        const int Pld = gram_pld(K, T);
         const int64_t panels_total = (slots + BM - 1) / BM;
         const int64_t n_pad[2] = {d->g[0].n_pad, d->g[1].n_pad};
         const int64_t n_glob[2] = {d->g[0].shard.n_global, d->g[1].shard.n_global};
@@ -1149,7 +1182,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                                      (d->g[1].shard.leaf_hi - d->g[1].shard.leaf_lo);
         DevBuf d_agree(sizeof(long long)), d_lut(2 * counts_lut_bytes());
 
-        std::vector<double> point(5 * (size_t)K + 1);
+        std::vector<double> point(PE * T);
         cudaEvent_t ev_point = nullptr;          // recorded on st once the point estimate's coefficients are on the device
         struct EvGuard { cudaEvent_t& e; ~EvGuard() { if (e) cudaEventDestroy(e); } } ev_point_guard{ev_point};
         OB_CUDA(cudaEventCreateWithFlags(&ev_point, cudaEventDisableTiming));
@@ -1180,7 +1213,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
             GramPlan plan; int64_t plan_panels = -1;
             DevBuf d_partials, d_pairs;
             {
-                const std::vector<uint16_t> pairs = gram_pair_table(V, ntiles);
+                const std::vector<uint16_t> pairs = gram_pair_table(K, T, ntiles);
                 d_pairs.alloc(sizeof(uint16_t) * pairs.size());
                 OB_CUDA(cudaMemcpyAsync(d_pairs.p, pairs.data(), sizeof(uint16_t) * pairs.size(), cudaMemcpyHostToDevice, st));
                 OB_CUDA(cudaStreamSynchronize(st));
@@ -1239,7 +1272,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
 
                 // (3) Gram / cross-product contraction
                 if (plan_panels != pn) {
-                    plan = gram_make_plan(V, (int)pn, d->g, count_bytes, ctx->num_sms);
+                    plan = gram_make_plan(K, T, d->ldx, (int)pn, d->g, count_bytes, ctx->num_sms);
                     plan_panels = pn;
                     d_partials.alloc(sizeof(double) * (size_t)std::max<int64_t>(plan.num_partials, 1) * BM * BN);
                 }
@@ -1313,15 +1346,15 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 Timer t_solve(st, &res->ms_solve);
                 SolveArgs sa;
                 sa.gram = d_gram.as<double>(); sa.slots_pad = pn * BM; sa.Pld = Pld; sa.slots = bslots;
-                sa.K = K; sa.n_cont = d->n_cont; sa.ref_kind = o->ref_kind;
+                sa.K = K; sa.n_cont = d->n_cont; sa.ref_kind = o->ref_kind; sa.T = T;
                 sa.n_norm = o->n_norm; sa.d_norm_m = d_nm.as<int>(); sa.d_norm_off = d_noff.as<int>();
                 sa.d_norm_idx = d_nidx.as<int>(); sa.d_norm_has_base = d_nhb.as<int>();
                 sa.n_base = n_base; sa.S = S; sa.weighted = d->weighted ? 1 : 0;
                 sa.na = (double)n_glob[0]; sa.nb = (double)n_glob[1];
-                sa.stats = d_stats.as<double>() + (size_t)slot_lo * S;
+                sa.stats = d_stats.as<double>() + (size_t)slot_lo * SE;
                 sa.status = d_status.as<int>() + slot_lo;
-                sa.beta_a = want_beta ? d_ba.as<double>() + (size_t)slot_lo * K : nullptr;
-                sa.beta_b = want_beta ? d_bb.as<double>() + (size_t)slot_lo * K : nullptr;
+                sa.beta_a = want_beta ? d_ba.as<double>() + (size_t)slot_lo * KE : nullptr;
+                sa.beta_b = want_beta ? d_bb.as<double>() + (size_t)slot_lo * KE : nullptr;
                 sa.point_extra = (p0 == 0) ? d_point.as<double>() : nullptr;
                 solve_launch(sa, st);
                 res->gpu_launches += 1;
@@ -1374,7 +1407,10 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         res->total_gap = point[5 * K];
         if (res->xa_mean) memcpy(res->xa_mean, point.data(), sizeof(double) * K);
         if (res->xb_mean) memcpy(res->xb_mean, point.data() + K, sizeof(double) * K);
-        if (res->beta_star) memcpy(res->beta_star, point.data() + 2 * K, sizeof(double) * K);
+        for (int t = 0; t < T; ++t) {
+            if (res->beta_star) memcpy(res->beta_star + (size_t)t * K, point.data() + t * PE + 2 * K, sizeof(double) * K);
+            if (res->total_gap_multi) res->total_gap_multi[t] = point[t * PE + 5 * K];
+        }
 
         // OaxacaResults.residuals (builder.rs:946: raw residuals of group B under its un-normalised fit) on the side
         // stream: the kernel and its 8 n_b byte D2H overlap the gather and the reduction below.  A page-locked
@@ -1383,26 +1419,27 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         struct SideJoin { cudaStream_t s; bool armed = false; ~SideJoin() { if (armed) cudaStreamSynchronize(s); } } side_join{ctx->stream_side};
         if (res->residuals_b) {
             side_join.armed = true;      // an error further down must not release d_res under the side stream
-            d_res.alloc(sizeof(double) * (size_t)std::max<int64_t>(d->g[1].n, 1));
+            d_res.alloc(sizeof(double) * (size_t)std::max<int64_t>(d->g[1].n, 1) * T);
             cudaStream_t s2 = ctx->stream_side;
             OB_CUDA(cudaEventRecord(ev_point, st));            // orders the allocation, too
             OB_CUDA(cudaStreamWaitEvent(s2, ev_point, 0));
-            residuals_launch(d->g[1], K, d->ldx, d_point.as<double>() + 4 * K, d_res.as<double>(), s2);
-            res->gpu_launches += 1;
-            if (d->g[1].n) OB_CUDA(cudaMemcpyAsync(res->residuals_b, d_res.p, sizeof(double) * (size_t)d->g[1].n, cudaMemcpyDeviceToHost, s2));
+            for (int t = 0; t < T; ++t)     // outcome t sits in design column K + t
+                residuals_launch(d->g[1], K, K + t, d->ldx, d_point.as<double>() + t * PE + 4 * K, d_res.as<double>() + (size_t)t * d->g[1].n, s2);
+            res->gpu_launches += T;
+            if (d->g[1].n) OB_CUDA(cudaMemcpyAsync(res->residuals_b, d_res.p, sizeof(double) * (size_t)d->g[1].n * T, cudaMemcpyDeviceToHost, s2));
         }
-        if (res->point_stats) OB_CUDA(cudaMemcpyAsync(res->point_stats, d_stats.p, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
-        if (res->beta_a) OB_CUDA(cudaMemcpyAsync(res->beta_a, d_ba.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
-        if (res->beta_b) OB_CUDA(cudaMemcpyAsync(res->beta_b, d_bb.p, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
+        if (res->point_stats) OB_CUDA(cudaMemcpyAsync(res->point_stats, d_stats.p, sizeof(double) * SE, cudaMemcpyDeviceToHost, st));
+        if (res->beta_a) OB_CUDA(cudaMemcpyAsync(res->beta_a, d_ba.p, sizeof(double) * KE, cudaMemcpyDeviceToHost, st));
+        if (res->beta_b) OB_CUDA(cudaMemcpyAsync(res->beta_b, d_bb.p, sizeof(double) * KE, cudaMemcpyDeviceToHost, st));
         tr.mark("point + residuals queued", st, false);
 
         // ---- mode R: replicate rows of all ranks, device to device, into global replicate order ----
         const int64_t reps_all = shard_reps ? o->reps : nrep;
         DevBuf d_gstats, d_gstatus, d_gba, d_gbb;
-        const double* stats_rows = d_stats.as<double>() + S;      // [reps_all][S]
+        const double* stats_rows = d_stats.as<double>() + SE;     // [reps_all][T][S]
         const int* status_rows = d_status.as<int>() + 1;
-        const double* ba_rows = want_beta ? d_ba.as<double>() + K : nullptr;
-        const double* bb_rows = want_beta ? d_bb.as<double>() + K : nullptr;
+        const double* ba_rows = want_beta ? d_ba.as<double>() + KE : nullptr;
+        const double* bb_rows = want_beta ? d_bb.as<double>() + KE : nullptr;
         if (shard_reps) {
             Timer t_c(st, &res->ms_comm);
             Comm* cm = ctx->comm.get();
@@ -1417,24 +1454,25 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 }
                 cm->allgatherv(mine, all.p, off.data(), sz.data(), st);
             };
-            gather_rows(stats_rows, d_gstats, sizeof(double) * (size_t)S);
+            gather_rows(stats_rows, d_gstats, sizeof(double) * (size_t)SE);
             gather_rows(status_rows, d_gstatus, sizeof(int));
             stats_rows = d_gstats.as<double>(); status_rows = d_gstatus.as<int>();
-            if (res->rep_beta_a) { gather_rows(ba_rows, d_gba, sizeof(double) * (size_t)K); ba_rows = d_gba.as<double>(); }
-            if (res->rep_beta_b) { gather_rows(bb_rows, d_gbb, sizeof(double) * (size_t)K); bb_rows = d_gbb.as<double>(); }
+            if (res->rep_beta_a) { gather_rows(ba_rows, d_gba, sizeof(double) * (size_t)KE); ba_rows = d_gba.as<double>(); }
+            if (res->rep_beta_b) { gather_rows(bb_rows, d_gbb, sizeof(double) * (size_t)KE); bb_rows = d_gbb.as<double>(); }
             t_c.stop(); OB_CUDA(cudaStreamSynchronize(st)); t_c.collect();
             tr.mark("replicate all-gather", st, false);
         }
 
         // ---- (5) reduction to standard errors / p-values / percentile CIs ----
         if (!o->skip_reduce) {
-            DevBuf d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long)), d_rs(reduce_stats_scratch_bytes(reps_all, S));
+            // the T x S statistics of a slot reduce independently: one launch over T*S columns; outputs are [T][S]
+            DevBuf d_out(sizeof(double) * 5 * (size_t)SE), d_nok(sizeof(long long)), d_rs(reduce_stats_scratch_bytes(reps_all, SE));
             Timer t_red(st, &res->ms_reduce);
-            reduce_stats_launch(stats_rows, status_rows, reps_all, S, d_stats.as<double>(),
+            reduce_stats_launch(stats_rows, status_rows, reps_all, SE, d_stats.as<double>(),
                                 d_out.as<double>(), d_nok.as<long long>(), st, d_rs.as<double>());
             res->gpu_launches += 1;
             t_red.stop();
-            std::vector<double> out5(5 * (size_t)S);
+            std::vector<double> out5(5 * (size_t)SE);
             long long nok = 0;
             OB_CUDA(cudaMemcpyAsync(out5.data(), d_out.p, d_out.bytes, cudaMemcpyDeviceToHost, st));
             OB_CUDA(cudaMemcpyAsync(&nok, d_nok.p, sizeof nok, cudaMemcpyDeviceToHost, st));
@@ -1443,13 +1481,13 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
             res->n_ok = nok;
             double* dst[5] = {res->std_err, res->p_value, res->ci_lower, res->ci_upper, res->t_stat};
             for (int k = 0; k < 5; ++k)
-                if (dst[k]) memcpy(dst[k], out5.data() + (size_t)k * S, sizeof(double) * S);
+                if (dst[k]) memcpy(dst[k], out5.data() + (size_t)k * SE, sizeof(double) * SE);
         }
         if (reps_all > 0) {
-            if (res->rep_stats) OB_CUDA(cudaMemcpyAsync(res->rep_stats, stats_rows, sizeof(double) * (size_t)reps_all * S, cudaMemcpyDeviceToHost, st));
+            if (res->rep_stats) OB_CUDA(cudaMemcpyAsync(res->rep_stats, stats_rows, sizeof(double) * (size_t)reps_all * SE, cudaMemcpyDeviceToHost, st));
             if (res->rep_status) OB_CUDA(cudaMemcpyAsync(res->rep_status, status_rows, sizeof(int) * (size_t)reps_all, cudaMemcpyDeviceToHost, st));
-            if (res->rep_beta_a) OB_CUDA(cudaMemcpyAsync(res->rep_beta_a, ba_rows, sizeof(double) * (size_t)reps_all * K, cudaMemcpyDeviceToHost, st));
-            if (res->rep_beta_b) OB_CUDA(cudaMemcpyAsync(res->rep_beta_b, bb_rows, sizeof(double) * (size_t)reps_all * K, cudaMemcpyDeviceToHost, st));
+            if (res->rep_beta_a) OB_CUDA(cudaMemcpyAsync(res->rep_beta_a, ba_rows, sizeof(double) * (size_t)reps_all * KE, cudaMemcpyDeviceToHost, st));
+            if (res->rep_beta_b) OB_CUDA(cudaMemcpyAsync(res->rep_beta_b, bb_rows, sizeof(double) * (size_t)reps_all * KE, cudaMemcpyDeviceToHost, st));
         }
         if (res->residuals_b) {   // the side stream rejoins before the call's end (and before d_res is released on st)
             OB_CUDA(cudaEventRecord(ev_point, ctx->stream_side));
@@ -1503,7 +1541,7 @@ int64_t ob_debug_gram_schedule(int32_t K, int64_t n_a, int64_t n_b, int64_t slot
         gd[g].n = gd[g].shard.n_local; gd[g].n_pad = pad_rows(gd[g].n);
     }
     const int64_t panels = (slots + BM - 1) / BM;
-    return gram_schedule_debug(K + 1, (int)panels, slots - (panels - 1) * BM, gd, grid, out8, cap);
+    return gram_schedule_debug(K, (int)panels, slots - (panels - 1) * BM, gd, grid, out8, cap);
 }
 
 ob_status ob_debug_counts(ob_ctx* ctx, const ob_design* d, uint64_t seed, int64_t rep, int32_t group,

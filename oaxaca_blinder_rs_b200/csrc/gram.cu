@@ -369,19 +369,21 @@ __global__ void __launch_bounds__(256) gram_combine_kernel(const double* __restr
     }
 }
 
-std::vector<uint16_t> gram_pair_table(int V, int ntiles) {
+std::vector<uint16_t> gram_pair_table(int K, int T, int ntiles) {
     std::vector<uint16_t> t((size_t)ntiles * BN * 2);
     size_t c = 0;
-    for (int j = 0; j < V; ++j)
-        for (int l = j; l < V; ++l) { t[2 * c] = (uint16_t)j; t[2 * c + 1] = (uint16_t)l; ++c; }
-    for (; c < (size_t)ntiles * BN; ++c) { t[2 * c] = (uint16_t)(V - 1); t[2 * c + 1] = (uint16_t)(V - 1); }  // padding: harmless duplicates of (y,y)
+    for (int j = 0; j < K; ++j) {
+        for (int l = j; l < K; ++l) { t[2 * c] = (uint16_t)j; t[2 * c + 1] = (uint16_t)l; ++c; }
+        for (int o = 0; o < T; ++o) { t[2 * c] = (uint16_t)j; t[2 * c + 1] = (uint16_t)(K + o); ++c; }
+    }
+    for (; c < (size_t)ntiles * BN; ++c) { t[2 * c] = (uint16_t)K; t[2 * c + 1] = (uint16_t)K; }  // (y_0,y_0) and padding: harmless duplicates
     return t;
 }
 
-GramPlan gram_make_plan(int V, int panels, const GroupData gd[2], int count_bytes, int num_sms) {
+GramPlan gram_make_plan(int K, int T, int ldx, int panels, const GroupData gd[2], int count_bytes, int num_sms) {
     GramPlan pl;
-    pl.V = V; pl.ldx = design_ldx(V); pl.panels = panels;
-    gram_col_tiling(V, pl.nfull, pl.has_half);
+    pl.K = K; pl.T = T; pl.ldx = ldx; pl.panels = panels;
+    gram_col_tiling(K, T, pl.nfull, pl.has_half);
     pl.ntiles = pl.nfull + pl.has_half;
     pl.Pld = pl.nfull * BN + pl.has_half * BNH;
     int64_t total = 0;
@@ -466,8 +468,8 @@ void gram_combine_launch(const double* gathered, int world, const int ranks_with
 // Host-side walk of the warp-specialised kernel's unit schedule (no device needed): for every CTA the units it takes,
 // as (group, panel, tile, segment, stages, mi, half).  Lets the CPU tests check that every unit is covered exactly once
 // and that CTAs get equal shares of every cost class, for any shape.
-int64_t gram_schedule_debug(int V, int panels, int64_t slots_last_panel, const GroupData gd[2], int grid, int64_t* out7, int64_t cap) {
-    GramPlan pl = gram_make_plan(V, panels, gd, 1, grid);
+int64_t gram_schedule_debug(int K, int panels, int64_t slots_last_panel, const GroupData gd[2], int grid, int64_t* out7, int64_t cap) {
+    GramPlan pl = gram_make_plan(K, 1, design_ldx(K + 1), panels, gd, 1, grid);
     GramKernelParams p{};
     for (int g = 0; g < 2; ++g) { p.n_pad[g] = pl.n_pad[g]; p.segs[g] = pl.segs[g]; p.seg_rows[g] = pl.seg_rows[g]; p.seg_lo[g] = 0; p.seg_n[g] = pl.segs[g]; }
     p.units0 = pl.units[0]; p.units_total = pl.units[0] + pl.units[1];

@@ -25,15 +25,18 @@ struct CudaError { cudaError_t code; const char* what; const char* file; int lin
 
 struct StatusError { ob_status code; std::string msg; };
 
-// Number of variables V = K + 1 (design columns + outcome); sufficient-statistic columns
-// P' = V(V+1)/2 (upper triangle of [x|y][x|y]^T, row-major); P = P' - 1 are algorithmic
-// (the (y,y) cell rides along in the padding).
-inline int64_t num_pairs(int V) { return (int64_t)V * (V + 1) / 2; }
-// row stride (in doubles) of the packed design: >= V, congruent to 4 mod 8 so that the
+// A packed design row holds the K design columns followed by T >= 1 outcome columns (T = 1 for run(); a quantile
+// sweep carries one RIF outcome per tau, ob_design_apply_rif_multi).  Sufficient-statistic columns of the Gram
+// contraction, in this order: for j = 0..K-1 the pairs (j,j) (j,j+1) .. (j,K-1) (upper triangle of X'WX, row-major),
+// then (j, y_0) .. (j, y_{T-1}) (X'Wy per outcome); one trailing (y_0, y_0) cell keeps the T = 1 layout equal to the
+// row-major upper triangle of [x|y][x|y]^T.  P' = K(K+1)/2 + K T + 1, of which P = K(K+1)/2 + K T are algorithmic.
+inline int64_t num_pairs(int K, int T) { return (int64_t)K * (K + 1) / 2 + (int64_t)K * T + 1; }
+// row stride (in doubles) of the packed design: >= K + T, congruent to 4 mod 8 so that the
 // B-fragment shared-memory loads of gram.cu are bank-conflict free
 inline int design_ldx(int V) { int l = V; while ((l & 7) != 4) ++l; return l; }
-// index of pair (j,l), j <= l < V, in the row-major upper triangle
-inline int64_t pair_index(int V, int j, int l) { return (int64_t)j * V - (int64_t)j * (j - 1) / 2 + (l - j); }
+// index of the first pair of design column j; pair (j,l), l < K, sits at pair_base + (l - j), pair (j, y_t) at
+// pair_base + (K - j) + t
+inline int64_t pair_base(int K, int T, int j) { return (int64_t)j * (K + T) - (int64_t)j * (j - 1) / 2; }
 
 // ---- fixed row segmentation of a group (the summation tree of the split-n Gram) ----
 // A group's padded rows are cut into `segs` <= MAX_SEGS leaf segments of seg_rows rows each (the last one
@@ -117,7 +120,7 @@ void counts_philox_fixup_launch(const CountsArgs& a, const long long* d_colsum, 
 
 // ---- gram.cu ----
 struct GramPlan {
-    int V, ldx, panels, ntiles;
+    int K, T, ldx, panels, ntiles;
     int nfull, has_half, Pld;     // column tiling (gram_col_tiling) and the row stride of the reduced Gram
     int64_t n_pad[2];             // local padded rows
     int segs[2], seg_rows[2];     // leaves held here and rows per leaf (RowShard: function of the global row count only)
@@ -127,18 +130,18 @@ struct GramPlan {
     int64_t num_partials;         // = units[0] + units[1]
     size_t smem_bytes;
 };
-// Column tiling of the P' = V(V+1)/2 sufficient-statistic columns: nfull tiles of BN columns and, when the remainder
+// Column tiling of the P' sufficient-statistic columns: nfull tiles of BN columns and, when the remainder
 // fits, one half-width tail tile (P' = 171 at K = 17 costs 1.5 tiles instead of 2).
-inline void gram_col_tiling(int V, int& nfull, int& has_half) {
-    const int64_t P = num_pairs(V);
+inline void gram_col_tiling(int K, int T, int& nfull, int& has_half) {
+    const int64_t P = num_pairs(K, T);
     nfull = (int)(P / BN);
     const int rem = (int)(P - (int64_t)nfull * BN);
     has_half = 0;
     if (rem > BN / 2) ++nfull; else if (rem > 0) has_half = 1;
 }
-inline int gram_ntiles(int V) { int f, h; gram_col_tiling(V, f, h); return f + h; }
-inline int gram_pld(int V) { int f, h; gram_col_tiling(V, f, h); return f * BN + h * (BN / 2); }
-GramPlan gram_make_plan(int V, int panels, const GroupData g[2], int count_bytes, int num_sms);
+inline int gram_ntiles(int K, int T) { int f, h; gram_col_tiling(K, T, f, h); return f + h; }
+inline int gram_pld(int K, int T) { int f, h; gram_col_tiling(K, T, f, h); return f * BN + h * (BN / 2); }
+GramPlan gram_make_plan(int K, int T, int ldx, int panels, const GroupData g[2], int count_bytes, int num_sms);
 struct GramArgs {
     const double* X[2]; const void* C[2];     // X: the (sqrt(w)-scaled when weighted) design
     int count_bytes;
@@ -158,8 +161,8 @@ void gram_reduce_launch(const GramPlan& plan, const GramArgs& args, cudaStream_t
 // = number of leading ranks that hold leaves of group g
 void gram_combine_launch(const double* gathered, int world, const int ranks_with_rows[2], int64_t per_group_elems,
                          double* gram, cudaStream_t st);
-std::vector<uint16_t> gram_pair_table(int V, int ntiles);
-int64_t gram_schedule_debug(int V, int panels, int64_t slots_last_panel, const GroupData gd[2], int grid, int64_t* out8, int64_t cap);
+std::vector<uint16_t> gram_pair_table(int K, int T, int ntiles);
+int64_t gram_schedule_debug(int K, int panels, int64_t slots_last_panel, const GroupData gd[2], int grid, int64_t* out8, int64_t cap);
 
 // ---- solve.cu ----
 struct SolveArgs {
@@ -167,6 +170,7 @@ struct SolveArgs {
     int64_t slots_pad; int Pld;
     int64_t slots;           // valid slots in this batch (slot 0 = point estimate when has_point)
     int K, n_cont, ref_kind;
+    int T = 1;               // outcome columns: stats [slots][T][S], beta_a / beta_b [slots][T][K], point_extra [T][5K+1]
     int n_norm; const int* d_norm_m; const int* d_norm_off; const int* d_norm_idx; const int* d_norm_has_base;
     int n_base; int S;
     int weighted;
@@ -215,8 +219,10 @@ void iota_launch(uint32_t* dst, int64_t n, uint32_t first, cudaStream_t st);
 void update_outcome_launch(const GroupData& g, int K, int ldx, const double* d_y_frame, cudaStream_t st);
 // Xs[i][:] = sqrt(w[i]) * X[i][:] for all V = K+1 columns (WLS as OLS on sqrt(w)-scaled data, ols.rs:68-78)
 void scale_rows_launch(const GroupData& g, int ldx, cudaStream_t st);
-// residuals of the point estimate: r = y - X beta (ols.rs:118-119) for one group
-void residuals_launch(const GroupData& g, int K, int ldx, const double* d_beta, double* d_out, cudaStream_t st);
+// residuals of the point estimate: r = y - X beta (ols.rs:118-119) for one group; the outcome sits in column ycol
+void residuals_launch(const GroupData& g, int K, int ycol, int ldx, const double* d_beta, double* d_out, cudaStream_t st);
+// dst [rows][ld_dst] = design columns 0..K-1 of src [rows][ld_src], zeros from column K on
+void relayout_launch(const double* src, int ld_src, double* dst, int ld_dst, int64_t rows, int K, cudaStream_t st);
 
 // ---- ingest.cu ----
 constexpr int INGEST_MAX_COLS = 96;
@@ -272,8 +278,9 @@ void nccl_unique_id(uint8_t* id128);
 Comm* comm_create_nccl(const uint8_t* id128, int rank, int world);
 
 // ---- rif.cu ----
-// in-place RIF transform (math/rif.rs:14-88) of the outcome column (col K) of a packed group
-void rif_transform(const GroupData& g, int K, int ldx, double tau, void* d_scratch, size_t scratch_bytes,
+// RIF transform (math/rif.rs:14-88) of a packed group's raw outcome (g.y_raw if saved, else column ycol itself),
+// written to column ycol
+void rif_transform(const GroupData& g, int ycol, int ldx, double tau, void* d_scratch, size_t scratch_bytes,
                    cudaStream_t st);
 size_t rif_scratch_bytes(int64_t n);
 

@@ -258,8 +258,26 @@ void update_outcome_launch(const GroupData& g, int K, int ldx, const double* d_y
     OB_CUDA(cudaGetLastError());
 }
 
+// ---- re-layout of a packed design to a wider row stride (room for more outcome columns): design columns copied,
+//      everything from column K on zeroed ----
+__global__ void __launch_bounds__(256) relayout_kernel(const double* __restrict__ src, int ld_src, double* __restrict__ dst, int ld_dst,
+                                                       long long rows, int K) {
+    const long long total = rows * ld_dst;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / ld_dst; const int c = (int)(e - r * ld_dst);
+        dst[e] = c < K ? src[r * ld_src + c] : 0.0;
+    }
+}
+
+void relayout_launch(const double* src, int ld_src, double* dst, int ld_dst, int64_t rows, int K, cudaStream_t st) {
+    if (rows == 0) return;
+    const long long total = rows * (long long)ld_dst;
+    relayout_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 32), 256, 0, st>>>(src, ld_src, dst, ld_dst, rows, K);
+    OB_CUDA(cudaGetLastError());
+}
+
 // ---- point-estimate residuals r = y - X beta (ols.rs:118-119), one warp per row ----
-__global__ void __launch_bounds__(256) residuals_kernel(const double* __restrict__ X, long long n, int K, int ldx,
+__global__ void __launch_bounds__(256) residuals_kernel(const double* __restrict__ X, long long n, int K, int ycol, int ldx,
                                                         const double* __restrict__ beta, double* __restrict__ out) {
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -269,13 +287,13 @@ __global__ void __launch_bounds__(256) residuals_kernel(const double* __restrict
     for (int j = lane; j < K; j += 32) s += row[j] * beta[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) out[warp] = row[K] - s;
+    if (lane == 0) out[warp] = row[ycol] - s;
 }
 
-void residuals_launch(const GroupData& g, int K, int ldx, const double* d_beta, double* d_out, cudaStream_t st) {
+void residuals_launch(const GroupData& g, int K, int ycol, int ldx, const double* d_beta, double* d_out, cudaStream_t st) {
     if (g.n == 0) return;
     const long long threads = g.n * 32;
-    residuals_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(g.X, g.n, K, ldx, d_beta, d_out);
+    residuals_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(g.X, g.n, K, ycol, ldx, d_beta, d_out);
     OB_CUDA(cudaGetLastError());
 }
 

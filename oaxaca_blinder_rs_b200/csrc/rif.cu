@@ -189,13 +189,13 @@ __global__ void __launch_bounds__(RIF_THREADS) rif_apply_kernel(double* __restri
 
 size_t rif_scratch_bytes(int64_t n) { return sizeof(unsigned long long) * (size_t)std::max<int64_t>(n, 1) + sizeof(RifState) + 256; }
 
-void rif_transform(const GroupData& g, int K, int ldx, double tau, void* d_scratch, size_t scratch_bytes, cudaStream_t st) {
+void rif_transform(const GroupData& g, int ycol, int ldx, double tau, void* d_scratch, size_t scratch_bytes, cudaStream_t st) {
     const long long n = g.n;
     if ((double)n < 2.0) return;  // rif.rs:18-20
     if (scratch_bytes < rif_scratch_bytes(n)) throw StatusError{OB_ERR_INVALID_ARG, "rif scratch too small"};
     unsigned long long* keys = static_cast<unsigned long long*>(d_scratch);
     RifState* s = reinterpret_cast<RifState*>(reinterpret_cast<char*>(d_scratch) + ((sizeof(unsigned long long) * (size_t)n + 255) / 256) * 256);
-    const double* y_src = g.y_raw ? g.y_raw : g.X + K;
+    const double* y_src = g.y_raw ? g.y_raw : g.X + ycol;
     const long long ystride = g.y_raw ? 1 : ldx;
     rif_extract_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(y_src, ystride, n, keys, s);
     rif_init_kernel<<<1, 1, 0, st>>>(s, n, tau);
@@ -208,7 +208,7 @@ void rif_transform(const GroupData& g, int K, int ldx, double tau, void* d_scrat
     rif_params_kernel<<<1, 1, 0, st>>>(s, n, tau);
     rif_density_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(keys, n, s);
     rif_dens_final_kernel<<<1, 1, 0, st>>>(s, n);
-    rif_apply_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(g.X, n, K, ldx, y_src, ystride, s, tau);
+    rif_apply_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(g.X, n, ycol, ldx, y_src, ystride, s, tau);
     OB_CUDA(cudaGetLastError());
 }
 

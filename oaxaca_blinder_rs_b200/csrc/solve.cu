@@ -22,7 +22,7 @@ constexpr int SOLVE_THREADS = 128;
 
 struct SolveParams {
     const double* gram; long long slots_pad; int Pld; long long slots;
-    int K, n_cont, ref_kind;
+    int K, n_cont, ref_kind, T;
     int n_norm; const int* norm_m; const int* norm_off; const int* norm_idx; const int* norm_has_base;
     int n_base, S, weighted;
     double na, nb;
@@ -107,7 +107,7 @@ __device__ void yun_shift(const SolveParams& p, double* beta, int shift_from, do
 
 __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveParams p) {
     extern __shared__ __align__(16) double sm[];
-    const int K = p.K, V = K + 1, Kp = K + 1;
+    const int K = p.K, T = p.T, Kp = K + 1;
     const int ld = ld_of(K), ldp = ld_of(Kp);
     const long long slot = blockIdx.x;
     const int tid = threadIdx.x;
@@ -127,15 +127,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveParams 
     const double* gA = p.gram + (size_t)slot * p.Pld;
     const double* gB = p.gram + ((size_t)p.slots_pad + slot) * p.Pld;
     if (tid == 0) fail = 0;
-    // ---- unpack the packed upper triangle (pair (j,l), j <= l < V, row-major) ----
-    for (int j = 0; j < V; ++j) {
-        const long long base_idx = (long long)j * V - (long long)j * (j - 1) / 2 - j;  // index of (j,l) = base_idx + l
-        for (int l = j + tid; l < V; l += blockDim.x) {
+    // ---- unpack X'WX from the packed columns: pair (j,l), j <= l < K, at pair_base(j) + (l - j) ----
+    for (int j = 0; j < K; ++j) {
+        const long long base_idx = (long long)j * (K + T) - (long long)j * (j - 1) / 2 - j;  // index of (j,l) = base_idx + l
+        for (int l = j + tid; l < K; l += blockDim.x) {
             const double a = gA[base_idx + l], b = gB[base_idx + l];
-            if (l < K) {
-                GA[j * ld + l] = a; GA[l * ld + j] = a;
-                GB[j * ld + l] = b; GB[l * ld + j] = b;
-            } else if (j < K) { rA[j] = a; rB[j] = b; }
+            GA[j * ld + l] = a; GA[l * ld + j] = a;
+            GB[j * ld + l] = b; GB[l * ld + j] = b;
         }
     }
     __syncthreads();
@@ -147,10 +145,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveParams 
         xa[tid] = GA[tid] / GA[0];
         xb[tid] = GB[tid] / GB[0];
     }
-    if (tid == 0) { sums[0] = GA[0]; sums[1] = rA[0]; sums[2] = GB[0]; sums[3] = rB[0]; }
+    if (tid == 0) { sums[0] = GA[0]; sums[2] = GB[0]; }
+    const int ind = 1 + p.n_cont;
     if (pooled) {
         // builder.rs:548-566: rows of A and B stacked, indicator (1 on A rows) at column ind = 1 + n_cont
-        const int ind = 1 + p.n_cont;
         for (int e = tid; e < Kp * Kp; e += blockDim.x) {
             const int i = e / Kp, j = e - i * Kp;
             const int si = i < ind ? i : i - 1, sj = j < ind ? j : j - 1;  // source design columns
@@ -161,107 +159,124 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveParams 
             else v = GA[si * ld + sj] + GB[si * ld + sj];
             GP[i * ldp + j] = v;
         }
-        for (int i = tid; i < Kp; i += blockDim.x) {
-            const int si = i < ind ? i : i - 1;
-            rP[i] = (i == ind) ? rA[0] : rA[si] + rB[si];
-        }
     }
     __syncthreads();
 
+    // the factorisations do not depend on the outcome: once per slot, whatever T
     if (status == OB_OK) {
         if (!chol_factor(GA, K, ld, &fail)) status = OB_ERR_NALGEBRA;
     }
-    if (status == OB_OK) chol_solve(GA, K, ld, rA);
     if (status == OB_OK) {
         if (!chol_factor(GB, K, ld, &fail)) status = OB_ERR_NALGEBRA;
     }
-    if (status == OB_OK) chol_solve(GB, K, ld, rB);
     if (status == OB_OK && pooled) {
         if (p.na + p.nb <= (double)Kp) status = OB_ERR_INSUFFICIENT_DATA;
         else if (!chol_factor(GP, Kp, ldp, &fail)) status = OB_ERR_NALGEBRA;
-        if (status == OB_OK) chol_solve(GP, Kp, ldp, rP);
     }
 
-    // ---- scalar epilogue ----
     const int D = K + p.n_base;
-    double* out = p.stats + (size_t)slot * p.S;
-    if (tid == 0 && status == OB_OK) {
-        double* ba = rA; double* bb = rB;
-        for (int j = 0; j < K; ++j) { rawA[j] = ba[j]; rawB[j] = bb[j]; }
-        if (p.n_norm > 0) { yun_shift(p, ba, -1, baseA); yun_shift(p, bb, -1, baseB); }   // estimation.rs:76-91
-        switch (p.ref_kind) {  // builder.rs:538-621
-        case OB_REF_GROUP_A:
-            for (int j = 0; j < K; ++j) bs[j] = ba[j];
-            for (int v = 0; v < p.n_norm; ++v) baseS[v] = baseA[v];
-            break;
-        case OB_REF_GROUP_B:
-            for (int j = 0; j < K; ++j) bs[j] = bb[j];
-            for (int v = 0; v < p.n_norm; ++v) baseS[v] = baseB[v];
-            break;
-        case OB_REF_POOLED: {
-            const int ind = 1 + p.n_cont;
-            if (p.n_norm > 0) yun_shift(p, rP, ind, baseS);           // builder.rs:568-579
-            for (int j = 0; j < ind; ++j) bs[j] = rP[j];              // remove_row(ind) :580-589
-            for (int j = ind; j < K; ++j) bs[j] = rP[j + 1];
-            break;
+    for (int t = 0; t < T; ++t) {
+        double* out = p.stats + ((size_t)slot * T + t) * p.S;
+        const size_t brow = ((size_t)slot * T + t) * K;
+        // ---- X'Wy of outcome t: pair (j, y_t) at pair_base(j) + (K - j) + t ----
+        __syncthreads();
+        for (int j = tid; j < K; j += blockDim.x) {
+            const long long idx = (long long)j * (K + T) - (long long)j * (j - 1) / 2 + (K - j) + t;
+            rA[j] = gA[idx]; rB[j] = gB[idx];
         }
-        default: {  // Weighted | Cotton: builder.rs:591-620
-            const double n_a = p.weighted ? sums[0] : p.na;
-            const double n_b = p.weighted ? sums[2] : p.nb;
-            const double total = n_a + n_b;
-            if (total == 0.0) { status = OB_ERR_INVALID_GROUP; break; }
-            const double wA = n_a / total, wB = 1.0 - wA;
-            for (int v = 0; v < p.n_norm; ++v) baseS[v] = baseA[v] * wA + baseB[v] * wB;
-            for (int j = 0; j < K; ++j) bs[j] = ba[j] * wA + bb[j] * wB;
-            break;
-        }
-        }
+        __syncthreads();
+        if (tid == 0) { sums[1] = rA[0]; sums[3] = rB[0]; }
+        if (pooled)
+            for (int i = tid; i < Kp; i += blockDim.x) {
+                const int si = i < ind ? i : i - 1;
+                rP[i] = (i == ind) ? rA[0] : rA[si] + rB[si];
+            }
+        __syncthreads();
         if (status == OB_OK) {
-            // decomposition.rs:56-89
-            double en = 0.0, co = 0.0, in = 0.0, ex = 0.0, fa = 0.0, fb = 0.0;
-            for (int j = 0; j < K; ++j) {
-                const double dx = xa[j] - xb[j], db = ba[j] - bb[j];
-                en += dx * bb[j]; co += xb[j] * db; in += dx * db;
-                ex += dx * bs[j]; fa += xa[j] * ba[j]; fb += xb[j] * bb[j];
+            chol_solve(GA, K, ld, rA);
+            chol_solve(GB, K, ld, rB);
+            if (pooled) chol_solve(GP, Kp, ldp, rP);
+        }
+
+        // ---- scalar epilogue ----
+        int st_t = status;
+        if (tid == 0 && st_t == OB_OK) {
+            double* ba = rA; double* bb = rB;
+            for (int j = 0; j < K; ++j) { rawA[j] = ba[j]; rawB[j] = bb[j]; }
+            if (p.n_norm > 0) { yun_shift(p, ba, -1, baseA); yun_shift(p, bb, -1, baseB); }   // estimation.rs:76-91
+            switch (p.ref_kind) {  // builder.rs:538-621
+            case OB_REF_GROUP_A:
+                for (int j = 0; j < K; ++j) bs[j] = ba[j];
+                for (int v = 0; v < p.n_norm; ++v) baseS[v] = baseA[v];
+                break;
+            case OB_REF_GROUP_B:
+                for (int j = 0; j < K; ++j) bs[j] = bb[j];
+                for (int v = 0; v < p.n_norm; ++v) baseS[v] = baseB[v];
+                break;
+            case OB_REF_POOLED: {
+                if (p.n_norm > 0) yun_shift(p, rP, ind, baseS);           // builder.rs:568-579
+                for (int j = 0; j < ind; ++j) bs[j] = rP[j];              // remove_row(ind) :580-589
+                for (int j = ind; j < K; ++j) bs[j] = rP[j + 1];
+                break;
             }
-            double two0 = ex, two1 = (fa - fb) - ex;
-            for (int j = 0; j < K; ++j) {  // decomposition.rs:92-122
-                out[5 + j] = (xa[j] - xb[j]) * bs[j];
-                out[5 + D + j] = xa[j] * (ba[j] - bs[j]) + xb[j] * (bs[j] - bb[j]);
+            default: {  // Weighted | Cotton: builder.rs:591-620
+                const double n_a = p.weighted ? sums[0] : p.na;
+                const double n_b = p.weighted ? sums[2] : p.nb;
+                const double total = n_a + n_b;
+                if (total == 0.0) { st_t = OB_ERR_INVALID_GROUP; break; }
+                const double wA = n_a / total, wB = 1.0 - wA;
+                for (int v = 0; v < p.n_norm; ++v) baseS[v] = baseA[v] * wA + baseB[v] * wB;
+                for (int j = 0; j < K; ++j) bs[j] = ba[j] * wA + bb[j] * wB;
+                break;
             }
-            int row = K;
-            for (int v = 0; v < p.n_norm; ++v) {  // builder.rs:634-674
-                if (!p.norm_has_base[v]) continue;
-                double sa = 0.0, sb = 0.0;
-                for (int t = p.norm_off[v]; t < p.norm_off[v + 1]; ++t) { sa += xa[p.norm_idx[t]]; sb += xb[p.norm_idx[t]]; }
-                const double xab = 1.0 - sa, xbb = 1.0 - sb;
-                const double un = xab * (baseA[v] - baseS[v]) + xbb * (baseS[v] - baseB[v]);
-                const double e2 = (xab - xbb) * baseS[v];
-                out[5 + D + row] = un; out[5 + row] = e2;
-                two0 += e2; two1 += un;
-                ++row;
             }
-            out[0] = two0; out[1] = two1; out[2] = en; out[3] = co; out[4] = in;
-            if (p.beta_a) for (int j = 0; j < K; ++j) p.beta_a[(size_t)slot * K + j] = ba[j];
-            if (p.beta_b) for (int j = 0; j < K; ++j) p.beta_b[(size_t)slot * K + j] = bb[j];
-            if (p.point_extra && slot == 0) {
-                double* pe = p.point_extra;
+            if (st_t == OB_OK) {
+                // decomposition.rs:56-89
+                double en = 0.0, co = 0.0, in = 0.0, ex = 0.0, fa = 0.0, fb = 0.0;
                 for (int j = 0; j < K; ++j) {
-                    pe[j] = xa[j]; pe[K + j] = xb[j]; pe[2 * K + j] = bs[j];
-                    pe[3 * K + j] = rawA[j]; pe[4 * K + j] = rawB[j];
+                    const double dx = xa[j] - xb[j], db = ba[j] - bb[j];
+                    en += dx * bb[j]; co += xb[j] * db; in += dx * db;
+                    ex += dx * bs[j]; fa += xa[j] * ba[j]; fb += xb[j] * bb[j];
                 }
-                pe[5 * K] = sums[1] / sums[0] - sums[3] / sums[2];    // builder.rs:676-684
+                double two0 = ex, two1 = (fa - fb) - ex;
+                for (int j = 0; j < K; ++j) {  // decomposition.rs:92-122
+                    out[5 + j] = (xa[j] - xb[j]) * bs[j];
+                    out[5 + D + j] = xa[j] * (ba[j] - bs[j]) + xb[j] * (bs[j] - bb[j]);
+                }
+                int row = K;
+                for (int v = 0; v < p.n_norm; ++v) {  // builder.rs:634-674
+                    if (!p.norm_has_base[v]) continue;
+                    double sa = 0.0, sb = 0.0;
+                    for (int q = p.norm_off[v]; q < p.norm_off[v + 1]; ++q) { sa += xa[p.norm_idx[q]]; sb += xb[p.norm_idx[q]]; }
+                    const double xab = 1.0 - sa, xbb = 1.0 - sb;
+                    const double un = xab * (baseA[v] - baseS[v]) + xbb * (baseS[v] - baseB[v]);
+                    const double e2 = (xab - xbb) * baseS[v];
+                    out[5 + D + row] = un; out[5 + row] = e2;
+                    two0 += e2; two1 += un;
+                    ++row;
+                }
+                out[0] = two0; out[1] = two1; out[2] = en; out[3] = co; out[4] = in;
+                if (p.beta_a) for (int j = 0; j < K; ++j) p.beta_a[brow + j] = ba[j];
+                if (p.beta_b) for (int j = 0; j < K; ++j) p.beta_b[brow + j] = bb[j];
+                if (p.point_extra && slot == 0) {
+                    double* pe = p.point_extra + (size_t)t * (5 * K + 1);
+                    for (int j = 0; j < K; ++j) {
+                        pe[j] = xa[j]; pe[K + j] = xb[j]; pe[2 * K + j] = bs[j];
+                        pe[3 * K + j] = rawA[j]; pe[4 * K + j] = rawB[j];
+                    }
+                    pe[5 * K] = sums[1] / sums[0] - sums[3] / sums[2];    // builder.rs:676-684
+                }
             }
         }
-    }
-    if (tid == 0) {
-        if (status != OB_OK) {
-            const double nan = __longlong_as_double(0x7ff8000000000000LL);
-            for (int j = 0; j < p.S; ++j) out[j] = nan;
-            if (p.beta_a) for (int j = 0; j < K; ++j) p.beta_a[(size_t)slot * K + j] = nan;
-            if (p.beta_b) for (int j = 0; j < K; ++j) p.beta_b[(size_t)slot * K + j] = nan;
+        if (tid == 0) {
+            if (st_t != OB_OK) {
+                const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                for (int j = 0; j < p.S; ++j) out[j] = nan;
+                if (p.beta_a) for (int j = 0; j < K; ++j) p.beta_a[brow + j] = nan;
+                if (p.beta_b) for (int j = 0; j < K; ++j) p.beta_b[brow + j] = nan;
+            }
+            if (t == 0 || st_t != OB_OK) p.status[slot] = st_t;     // one status per slot (the fits fail or succeed together)
         }
-        p.status[slot] = status;
     }
 }
 
@@ -274,7 +289,7 @@ size_t solve_smem_bytes(int K, bool pooled, int n_norm) {
 void solve_launch(const SolveArgs& a, cudaStream_t st) {
     SolveParams p;
     p.gram = a.gram; p.slots_pad = a.slots_pad; p.Pld = a.Pld; p.slots = a.slots;
-    p.K = a.K; p.n_cont = a.n_cont; p.ref_kind = a.ref_kind;
+    p.K = a.K; p.n_cont = a.n_cont; p.ref_kind = a.ref_kind; p.T = a.T;
     p.n_norm = a.n_norm; p.norm_m = a.d_norm_m; p.norm_off = a.d_norm_off; p.norm_idx = a.d_norm_idx;
     p.norm_has_base = a.d_norm_has_base; p.n_base = a.n_base; p.S = a.S; p.weighted = a.weighted;
     p.na = a.na; p.nb = a.nb;
