@@ -132,8 +132,9 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            # NVML calls contend with the CUDA driver lock: sample sparsely (>= 1 sample is always taken under load)
-            if self.stop_flag.wait(0.5):
+            # NVML calls contend with the CUDA driver lock (measured: a host-side CUDA call of the step that coincides with
+            # a query stalls 8-22 ms): sample sparsely (>= 1 sample is always taken under load)
+            if self.stop_flag.wait(1.0):
                 break
 
     def summary(self):
@@ -346,6 +347,31 @@ def measure_also(name, ob, obd, ctx, torch, dist, rank, world, local, shard_rows
         gram_ms.append(out["timings_ms"]["gram_main"])
     sync()
     dt = time.perf_counter() - t0
+    sweep = None
+    if rif_tau is not None:        # BASELINE configs[3]: the tau = 0.1 / 0.5 / 0.9 sweep, as three runs and as one pass
+        taus = (0.1, 0.5, 0.9)
+
+        def run_sweep(multi):
+            sync()
+            t = time.perf_counter()
+            if multi:
+                des.apply_rif_multi(taus)
+                step(des)
+            else:
+                for tau in taus:
+                    des.apply_rif(tau)
+                    step(des)
+            sync()
+            return time.perf_counter() - t
+        run_sweep(False); run_sweep(True)
+        t3 = min(run_sweep(False) for _ in range(2))
+        t1s = min(run_sweep(True) for _ in range(2))
+        tt = torch.tensor([t3, t1s], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t3, t1s = tt.tolist()
+        sweep = {"taus": list(taus), "three_runs_s": t3, "one_pass_s": t1s, "speedup": t3 / t1s,
+                 "fits_per_s_one_pass": 3 * reps / t1s, "fits_per_s_three_runs": 3 * reps / t3}
     des.close()
     sync()
     t1 = time.perf_counter()
@@ -365,7 +391,7 @@ def measure_also(name, ob, obd, ctx, torch, dist, rank, world, local, shard_rows
             "warmup": 1, "ms_per_step": dt / steps * 1e3, "e2e": {"value": reps / dt_e, "unit": "reps/s", "steps": 1},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                          "frac": ach / FP64_DMMA_PEAK_TFLOPS, "launch_ms": g_ms},
-            "stage_ms": {k: float(v) for k, v in out["timings_ms"].items()}, "n_ok": int(out["n_ok"])}
+            "stage_ms": {k: float(v) for k, v in out["timings_ms"].items()}, "n_ok": int(out["n_ok"]), "quantile_sweep": sweep}
 
 
 def main():
@@ -554,6 +580,43 @@ def main():
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dt, dt_e, refresh = times.tolist()
 
+    # config 4 (BASELINE configs[3]: tau = 0.1 / 0.5 / 0.9): the sweep as three runs on a design packed once, and as ONE
+    # pass with three RIF outcome columns (ob_design_apply_rif_multi) -- both accountings of SURVEY 8d
+    sweep = None
+    if name.startswith("config4"):
+        taus = (0.1, 0.5, 0.9)
+        dsg = pack()
+
+        def run_sweep(multi):
+            sync()
+            t = time.perf_counter()
+            if multi:
+                dsg.apply_rif_multi(taus)
+                o = ob.bootstrap(dsg, reps, ref_kind=ref, norm=normv, seed=2026, want_residuals=False, shard_replicates=world > 1)
+            else:
+                for tau in taus:
+                    dsg.apply_rif(tau)
+                    o = ob.bootstrap(dsg, reps, ref_kind=ref, norm=normv, seed=2026, want_residuals=False, shard_replicates=world > 1)
+            sync()
+            return time.perf_counter() - t, o
+        run_sweep(False); run_sweep(True)                    # warm-up of both shapes
+        t3, o3 = min((run_sweep(False) for _ in range(3)), key=lambda r: r[0])
+        t1, o1 = min((run_sweep(True) for _ in range(3)), key=lambda r: r[0])
+        dsg.close()
+        tt = torch.tensor([t3, t1], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t3, t1 = tt.tolist()
+        Ksw = K
+        sweep = {"taus": list(taus), "reps_per_tau": reps,
+                 "three_runs": {"seconds": t3, "fits_per_s": 3 * reps / t3, "gram_columns": 3 * (Ksw * (Ksw + 1) // 2 + Ksw),
+                                "what": "apply_rif(tau) + ob_bootstrap_run per quantile on a design packed once"},
+                 "one_pass": {"seconds": t1, "fits_per_s": 3 * reps / t1, "gram_columns": Ksw * (Ksw + 1) // 2 + 3 * Ksw,
+                              "gram_ms": o1["timings_ms"]["gram_main"],
+                              "what": "apply_rif_multi(taus) + ONE ob_bootstrap_run: X'WX contracted once, three X'Wy column sets"},
+                 "speedup": t3 / t1,
+                 "identical": bool(np.array_equal(np.nan_to_num(o1["std_err"][2], nan=-7.0), np.nan_to_num(o3["std_err"], nan=-7.0)))}
+
     # the other multi-GPU configurations of BASELINE.json at the same N, so that the driver's record holds them
     also = None
     if world > 1 and args.also != "off" and name.startswith("config3"):
@@ -590,6 +653,7 @@ def main():
                                  "ob_design_pack -> ob_bootstrap_run")},
                 "nccl_selftest": selftest,
                 "also": also,
+                "quantile_sweep": sweep,
                 "e2e_outcome_refresh": None if not (refresh and world == 1) else
                     {"value": reps * args.steps / refresh, "unit": "reps/s", "h2d_bytes_per_step": int(8 * n),
                      "what": "ob_design_update_outcome (new y from pinned host memory, X resident) + bootstrap per step"},

@@ -37,7 +37,7 @@ typedef enum ob_status {
     OB_ERR_CUDA = 8,
     OB_ERR_NCCL = 9,
     OB_ERR_NO_DEVICE = 10,
-    OB_ERR_UNSUPPORTED = 11       /* shape outside what the kernels are built for (e.g. K+1 > 96) */
+    OB_ERR_UNSUPPORTED = 11       /* shape outside what the kernels are built for (e.g. K + outcome columns > 280) */
 } ob_status;
 
 /* ReferenceCoefficients (decomposition.rs:5-20).  Neumark == Pooled, Cotton == Weighted. */

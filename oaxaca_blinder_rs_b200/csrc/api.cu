@@ -16,6 +16,9 @@
 
 using namespace ob;
 
+// K + T <= 280: two 32-row stages of a design row block (plus the count and A tiles) must fit the Gram CTA's 227 KB
+static constexpr int MAX_DESIGN_COLS = 280;
+
 struct ob_ctx {
     int device = 0;
     int num_sms = 0;
@@ -463,16 +466,25 @@ ob_status ob_design_allgather_rows(ob_ctx* ctx, const ob_design* local, ob_desig
         cudaStream_t st = ctx->stream;
         const int world = comm->world;
         // row counts of every rank's slice, per group (+ a consistency word: K, n_cont, weighted)
+        // word 2: shape; bit 0 of word 3: the slice carries a frame-row map; rest of word 3: rows of the slice's frame
         std::vector<long long> mine = {(long long)local->g[0].n, (long long)local->g[1].n,
-                                       ((long long)local->K << 32) | ((long long)local->n_cont << 1) | (local->weighted ? 1 : 0)};
-        DevBuf d_mine(sizeof(long long) * 3), d_all(sizeof(long long) * 3 * world);
-        OB_CUDA(cudaMemcpyAsync(d_mine.p, mine.data(), sizeof(long long) * 3, cudaMemcpyHostToDevice, st));
-        comm->allgather(d_mine.p, d_all.p, sizeof(long long) * 3, st);
-        std::vector<long long> all(3 * (size_t)world);
-        OB_CUDA(cudaMemcpyAsync(all.data(), d_all.p, sizeof(long long) * 3 * world, cudaMemcpyDeviceToHost, st));
+                                       ((long long)local->K << 32) | ((long long)local->n_cont << 1) | (local->weighted ? 1 : 0),
+                                       ((long long)local->n_frame << 1) | ((local->g[0].src && local->g[1].src) ? 1 : 0)};
+        DevBuf d_mine(sizeof(long long) * 4), d_all(sizeof(long long) * 4 * world);
+        OB_CUDA(cudaMemcpyAsync(d_mine.p, mine.data(), sizeof(long long) * 4, cudaMemcpyHostToDevice, st));
+        comm->allgather(d_mine.p, d_all.p, sizeof(long long) * 4, st);
+        std::vector<long long> all4(4 * (size_t)world), all(3 * (size_t)world);
+        OB_CUDA(cudaMemcpyAsync(all4.data(), d_all.p, sizeof(long long) * 4 * world, cudaMemcpyDeviceToHost, st));
         OB_CUDA(cudaStreamSynchronize(st));
-        for (int r = 0; r < world; ++r)
+        bool have_src = true;
+        std::vector<long long> frame_off((size_t)world + 1, 0);
+        for (int r = 0; r < world; ++r) {
+            for (int k = 0; k < 3; ++k) all[3 * r + k] = all4[4 * r + k];
             if (all[3 * r + 2] != mine[2]) fail(OB_ERR_INVALID_ARG, "ranks disagree on the design shape (K, n_cont, weights)");
+            have_src = have_src && (all4[4 * r + 3] & 1);
+            frame_off[r + 1] = frame_off[r] + (all4[4 * r + 3] >> 1);
+        }
+        if (frame_off[world] > 0xFFFFFFFFll) have_src = false;
 
         std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
         design_register(ctx, d.get()); d->stream = ctx->stream; d->device = ctx->device; d->K = local->K; d->n_cont = local->n_cont; d->V = local->V;
@@ -487,11 +499,22 @@ ob_status ob_design_allgather_rows(ob_ctx* ctx, const ob_design* local, ob_desig
                 total += nr;
             }
             alloc_group(ctx, d->g[g], total, d->ldx, d->weighted);
-            cudaFreeAsync(d->g[g].src, st); d->g[g].src = nullptr;   // frame-row map is not gathered
             comm->allgatherv(local->g[g].X, d->g[g].X, off_x.data(), sz_x.data(), st);
             if (d->weighted) comm->allgatherv(local->g[g].w, d->g[g].w, off_w.data(), sz_w.data(), st);
+            if (have_src) {
+                // the frame-row map travels too (ob_design_update_outcome on the gathered design): a slice's rows point into
+                // its own frame slice, so rank r's block is shifted by the rows of the slices before it
+                std::vector<size_t> off_s(world), sz_s(world);
+                for (int r = 0; r < world; ++r) { off_s[r] = off_w[r] / 2; sz_s[r] = sz_w[r] / 2; }
+                comm->allgatherv(local->g[g].src, d->g[g].src, off_s.data(), sz_s.data(), st);
+                for (int r = 0; r < world; ++r)
+                    add_u32_launch(d->g[g].src + off_s[r] / sizeof(uint32_t), (int64_t)(sz_s[r] / sizeof(uint32_t)), (uint32_t)frame_off[r], st);
+            } else {
+                cudaFreeAsync(d->g[g].src, st); d->g[g].src = nullptr;
+            }
             scale_rows_launch(d->g[g], d->ldx, st);
         }
+        d->n_frame = frame_off[world];
         OB_CUDA(cudaStreamSynchronize(st));
         *out = d.release();
     });
@@ -514,22 +537,27 @@ ob_status ob_design_redistribute_rows(ob_ctx* ctx, const ob_design* local, ob_de
         cudaStream_t st = ctx->stream;
         std::vector<long long> mine = {(long long)local->g[0].n, (long long)local->g[1].n,
                                        ((long long)local->K << 32) | ((long long)local->n_cont << 1) | (local->weighted ? 1 : 0),
-                                       (long long)local->n_frame};
+                                       ((long long)local->n_frame << 1) | ((local->g[0].src && local->g[1].src) ? 1 : 0)};
         DevBuf d_mine(sizeof(long long) * 4), d_all(sizeof(long long) * 4 * world);
         OB_CUDA(cudaMemcpyAsync(d_mine.p, mine.data(), sizeof(long long) * 4, cudaMemcpyHostToDevice, st));
         comm->allgather(d_mine.p, d_all.p, sizeof(long long) * 4, st);
         std::vector<long long> all(4 * (size_t)world);
         OB_CUDA(cudaMemcpyAsync(all.data(), d_all.p, sizeof(long long) * 4 * world, cudaMemcpyDeviceToHost, st));
         OB_CUDA(cudaStreamSynchronize(st));
-        for (int r = 0; r < world; ++r)
+        bool have_src = true;
+        std::vector<long long> frame_off((size_t)world + 1, 0);
+        for (int r = 0; r < world; ++r) {
             if (all[4 * r + 2] != mine[2]) fail(OB_ERR_INVALID_ARG, "ranks disagree on the design shape (K, n_cont, weights)");
+            have_src = have_src && (all[4 * r + 3] & 1);
+            frame_off[r + 1] = frame_off[r] + (all[4 * r + 3] >> 1);
+        }
+        if (frame_off[world] > 0xFFFFFFFFll) have_src = false;
 
         std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
         design_register(ctx, d.get()); d->stream = ctx->stream; d->device = ctx->device; d->K = local->K; d->n_cont = local->n_cont; d->V = local->V;
         d->ldx = local->ldx; d->weighted = local->weighted;
         d->world = world; d->rank = me;
-        d->n_frame = 0;
-        for (int r = 0; r < world; ++r) d->n_frame += all[4 * r + 3];
+        d->n_frame = frame_off[world];
         for (int g = 0; g < 2; ++g) {
             std::vector<long long> off((size_t)world + 1, 0);          // group rows held by the slices before rank r
             for (int r = 0; r < world; ++r) off[r + 1] = off[r] + all[4 * r + g];
@@ -537,7 +565,6 @@ ob_status ob_design_redistribute_rows(ob_ctx* ctx, const ob_design* local, ob_de
             std::vector<RowShard> plan((size_t)world);
             for (int t = 0; t < world; ++t) plan[t] = row_shard(n_glob, t, world);
             alloc_group(ctx, d->g[g], plan[me].n_local, d->ldx, d->weighted);
-            cudaFreeAsync(d->g[g].src, st); d->g[g].src = nullptr;      // the frame-row map does not travel
             d->g[g].shard = plan[me];
             std::vector<size_t> rows((size_t)world * world, 0), send_row((size_t)world, 0), recv_row((size_t)world, 0);
             for (int sidx = 0; sidx < world; ++sidx)
@@ -559,6 +586,13 @@ ob_status ob_design_redistribute_rows(ob_ctx* ctx, const ob_design* local, ob_de
             };
             exchange(local->g[g].X, d->g[g].X, sizeof(double) * (size_t)d->ldx);
             if (d->weighted) exchange(local->g[g].w, d->g[g].w, sizeof(double));
+            if (have_src) {       // frame-row map (ob_design_update_outcome on the shard): blocks from rank r shift by its frame offset
+                exchange(local->g[g].src, d->g[g].src, sizeof(uint32_t));
+                for (int r = 0; r < world; ++r)
+                    add_u32_launch(d->g[g].src + recv_row[r], (int64_t)rows[(size_t)r * world + me], (uint32_t)frame_off[r], st);
+            } else {
+                cudaFreeAsync(d->g[g].src, st); d->g[g].src = nullptr;
+            }
             scale_rows_launch(d->g[g], d->ldx, st);
         }
         OB_CUDA(cudaStreamSynchronize(st));
@@ -619,7 +653,7 @@ ob_status ob_design_from_dense(ob_ctx* ctx, int32_t K, int32_t n_cont,
         if (K < 1 || n_cont < 0 || n_cont > K - 1 || na < 0 || nb < 0) fail(OB_ERR_INVALID_ARG, "bad design shape");
         if ((na && (!Xa || !ya)) || (nb && (!Xb || !yb))) fail(OB_ERR_INVALID_ARG, "null design pointer");
         if ((wa == nullptr) != (wb == nullptr) && na && nb) fail(OB_ERR_INVALID_ARG, "weights must be given for both groups or neither");
-        if (K + 1 > 91) fail(OB_ERR_UNSUPPORTED, "design wider than 90 columns is not supported by the solve kernel");
+        if (K + 1 > MAX_DESIGN_COLS) fail(OB_ERR_UNSUPPORTED, "design wider than 280 columns (the Gram kernel stages whole rows in shared memory)");
         const double* ws[2] = {wa, wb};
         const int64_t ns[2] = {na, nb};
         for (int g = 0; g < 2; ++g)
@@ -664,7 +698,7 @@ std::unique_ptr<ob_design, void (*)(ob_design*)> pack_staged(ob_ctx* ctx, Staged
         dummy_start[q] = K;
         K += cat_levels[q] - 1;
     }
-    if (K + 1 > 91) fail(OB_ERR_UNSUPPORTED, "design wider than 90 columns is not supported by the solve kernel");
+    if (K + 1 > MAX_DESIGN_COLS) fail(OB_ERR_UNSUPPORTED, "design wider than 280 columns (the Gram kernel stages whole rows in shared memory)");
     if (n > 0xFFFFFFFFll) fail(OB_ERR_UNSUPPORTED, "frames beyond 2^32 rows (IdxSize is u32 in the reference too)");
     g_alloc_pack = true;
     std::vector<const double*> h_cont(std::max(sf.n_cont, 1), nullptr);
@@ -784,7 +818,7 @@ ob_status ob_design_pack_async(ob_ctx* ctx, const ob_frame_view* f, ob_design** 
             dummy_start[q] = K;
             K += f->cat_levels[q] - 1;
         }
-        if (K + 1 > 91) fail(OB_ERR_UNSUPPORTED, "design wider than 90 columns is not supported by the solve kernel");
+        if (K + 1 > MAX_DESIGN_COLS) fail(OB_ERR_UNSUPPORTED, "design wider than 280 columns (the Gram kernel stages whole rows in shared memory)");
         if (n > 0xFFFFFFFFll) fail(OB_ERR_UNSUPPORTED, "frames beyond 2^32 rows (IdxSize is u32 in the reference too)");
         cudaStream_t st = ctx->stream, sc = ctx->stream_copy;
         g_alloc_pack = true;
@@ -1059,7 +1093,7 @@ ob_status ob_design_apply_rif_multi(ob_ctx* ctx, ob_design* d, const double* tau
         design_ready(d);
         if (n_tau < 1 || n_tau > 8) fail(OB_ERR_INVALID_ARG, "1 to 8 quantiles per pass");
         if (d->world > 1) fail(OB_ERR_UNSUPPORTED, "RIF pre-step on a row-sharded design (the quantile needs all rows of a group)");
-        if (d->K + n_tau > 91) fail(OB_ERR_UNSUPPORTED, "design plus outcome columns wider than 91");
+        if (d->K + n_tau > MAX_DESIGN_COLS) fail(OB_ERR_UNSUPPORTED, "design plus outcome columns wider than 280");
         cudaStream_t st = ctx->stream;
         const int K = d->K;
         const int ldx_new = std::max(d->ldx, design_ldx(K + n_tau));
@@ -1174,12 +1208,25 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
         int ranks_with_rows[2];
         for (int g = 0; g < 2; ++g)
             ranks_with_rows[g] = (d->g[g].shard.segs + d->g[g].shard.leaf_span - 1) / d->g[g].shard.leaf_span;
-        size_t free_b = 0, total_b = 0;
-        OB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        const double budget = o->max_workspace_bytes > 0 ? (double)o->max_workspace_bytes
-                                                         : 0.6 * ((double)free_b + (double)pool_idle_bytes(ctx));
         const int64_t local_leaves = (int64_t)(d->g[0].shard.leaf_hi - d->g[0].shard.leaf_lo) +
                                      (d->g[1].shard.leaf_hi - d->g[1].shard.leaf_lo);
+        double budget = (double)o->max_workspace_bytes;
+        if (o->max_workspace_bytes <= 0) {
+            // Steady state (the same problem again): the context's pool already holds the whole workspace -> no device
+            // query at all.  cudaMemGetInfo takes the driver's global lock and stalls for milliseconds whenever another
+            // thread (NVML monitoring, for one) holds it.
+            const double idle = (double)pool_idle_bytes(ctx);
+            const double need_all = ((double)(n_pad[0] + n_pad[1]) * BM * count_bytes +
+                                     (index_mode ? (double)(n_glob[0] + n_glob[1]) * BM * 4.0 : 0.0) +
+                                     2.0 * BM * Pld * 8.0 * (comm ? world + 2 : 1) +
+                                     (double)local_leaves * ntiles * (BM * BN * 8.0) + 2.0 * BM * 8.0) * (double)panels_total;
+            if (idle >= 1.02 * need_all) budget = 1.01 * need_all;      // every panel in one batch, from memory the pool holds
+            else {
+                size_t free_b = 0, total_b = 0;
+                OB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+                budget = 0.6 * ((double)free_b + idle);
+            }
+        }
         DevBuf d_agree(sizeof(long long)), d_lut(2 * counts_lut_bytes());
 
         std::vector<double> point(PE * T);
@@ -1356,6 +1403,8 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 sa.beta_a = want_beta ? d_ba.as<double>() + (size_t)slot_lo * KE : nullptr;
                 sa.beta_b = want_beta ? d_bb.as<double>() + (size_t)slot_lo * KE : nullptr;
                 sa.point_extra = (p0 == 0) ? d_point.as<double>() : nullptr;
+                DevBuf d_solve_scratch(solve_scratch_bytes(K, o->ref_kind == OB_REF_POOLED, o->n_norm, T, bslots));   // wide designs only
+                sa.scratch = d_solve_scratch.as<double>();
                 solve_launch(sa, st);
                 res->gpu_launches += 1;
                 t_solve.stop();

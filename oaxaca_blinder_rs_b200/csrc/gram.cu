@@ -78,7 +78,7 @@ __device__ __forceinline__ double count_to_f64(unsigned c, const double* __restr
 //   consumed[s]  stage finished by a warp     (one arrival per consumer warp; producer waits before reusing the slot)
 // Stage numbers run on across work units, so the producer prefetches and widens the next unit's first stages while
 // the consumers finish the current one: no per-unit pipeline fill, no CTA-wide barrier in the loop.
-constexpr int WS_R = 3;
+constexpr int WS_R = 3;   // ring depth; designs too wide for three stages in shared memory (K + T > ~120) run with two
 constexpr int WS_PRODUCER_WARPS = 4;                       // one warpgroup, so that setmaxnreg can rebalance registers
 constexpr int WS_THREADS = GRAM_THREADS + 32 * WS_PRODUCER_WARPS;
 // register budget: 384 threads x 168 at launch; the producer warpgroup drops to 56, the two consumer warpgroups rise to 224
@@ -123,7 +123,7 @@ __host__ __device__ __forceinline__ bool ws_decode(const GramKernelParams& p, lo
 }
 
 // MI = 8-slot groups of the panel this warp accumulates (16 = all 128 slots; 4 / 8 / 12 for a partly filled tail panel)
-template <typename CountT, int LDXC, int NI, int MI>
+template <typename CountT, int LDXC, int NI, int MI, int R>
 __device__ __forceinline__ void ws_consume_unit(const GramKernelParams& p, const GramUnit& u, const double* As, const double* Xs,
                                                 uint64_t* full, uint64_t* ready, uint64_t* consumed, int ldx_rt, uint32_t& jc) {
     constexpr int KSTEPS = KT / 4;
@@ -145,7 +145,7 @@ __device__ __forceinline__ void ws_consume_unit(const GramKernelParams& p, const
         for (int s = 0; s < NI; ++s) { acc[i][s][0] = 0.0; acc[i][s][1] = 0.0; }
 
     for (int s = 0; s < u.nstages; ++s) {
-        const uint32_t slot = jc % WS_R, par = (jc / WS_R) & 1u;
+        const uint32_t slot = jc % R, par = (jc / R) & 1u;
         mbar_wait(&full[slot], par);       // design rows of this stage (TMA writes become visible to this thread)
         mbar_wait(&ready[slot], par);      // widened A tile
         const double* abase = As + (size_t)slot * A_TILE + lk * LDA2 + lg * LGS;
@@ -181,32 +181,32 @@ __device__ __forceinline__ void ws_consume_unit(const GramKernelParams& p, const
         }
 }
 
-template <typename CountT, int LDXC, int NI>
+template <typename CountT, int LDXC, int NI, int R>
 __device__ __forceinline__ void ws_consume_dispatch(const GramKernelParams& p, const GramUnit& u, const double* As, const double* Xs,
                                                     uint64_t* full, uint64_t* ready, uint64_t* consumed, int ldx_rt, uint32_t& jc) {
     switch (u.mi) {
-    case 4: ws_consume_unit<CountT, LDXC, NI, 4>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
-    case 8: ws_consume_unit<CountT, LDXC, NI, 8>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
-    case 12: ws_consume_unit<CountT, LDXC, NI, 12>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
-    default: ws_consume_unit<CountT, LDXC, NI, 16>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
+    case 4: ws_consume_unit<CountT, LDXC, NI, 4, R>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
+    case 8: ws_consume_unit<CountT, LDXC, NI, 8, R>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
+    case 12: ws_consume_unit<CountT, LDXC, NI, 12, R>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
+    default: ws_consume_unit<CountT, LDXC, NI, 16, R>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
     }
 }
 
-template <typename CountT, int LDXC>
+template <typename CountT, int LDXC, int R = WS_R>
 __global__ void __launch_bounds__(WS_THREADS, 1) gram_ws_kernel(const GramKernelParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ldx = LDXC ? LDXC : p.ldx;
-    double* As = reinterpret_cast<double*>(smem_raw);                           // [WS_R][A_TILE]
-    double* Tab = As + WS_R * A_TILE;                                           // [256]
-    double* Xs = Tab + 256;                                                     // [WS_R][KT*ldx]
-    CountT* Cr = reinterpret_cast<CountT*>(Xs + (size_t)WS_R * KT * ldx);       // [WS_R][KT*BM]
-    uint64_t* full = reinterpret_cast<uint64_t*>(Cr + (size_t)WS_R * KT * BM);  // [WS_R]
-    uint64_t* ready = full + WS_R;
-    uint64_t* consumed = ready + WS_R;
+    double* As = reinterpret_cast<double*>(smem_raw);                           // [R][A_TILE]
+    double* Tab = As + R * A_TILE;                                           // [256]
+    double* Xs = Tab + 256;                                                     // [R][KT*ldx]
+    CountT* Cr = reinterpret_cast<CountT*>(Xs + (size_t)R * KT * ldx);       // [R][KT*BM]
+    uint64_t* full = reinterpret_cast<uint64_t*>(Cr + (size_t)R * KT * BM);  // [R]
+    uint64_t* ready = full + R;
+    uint64_t* consumed = ready + R;
     if (tid < 256) Tab[tid] = (double)tid;
     if (tid == 0) {
-        for (int s = 0; s < WS_R; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], WS_PRODUCER_WARPS); mbar_init(&consumed[s], GRAM_THREADS / 32); }
+        for (int s = 0; s < R; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], WS_PRODUCER_WARPS); mbar_init(&consumed[s], GRAM_THREADS / 32); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gram_ws_kernel(const GramKernel
         uint32_t jc = 0;
         GramUnit u;
         for (long long i = blockIdx.x; ws_decode(p, i, ldx, sizeof(CountT), u); i += gridDim.x) {
-            if (u.half) ws_consume_dispatch<CountT, LDXC, 1>(p, u, As, Xs, full, ready, consumed, ldx, jc);
-            else ws_consume_dispatch<CountT, LDXC, 2>(p, u, As, Xs, full, ready, consumed, ldx, jc);
+            if (u.half) ws_consume_dispatch<CountT, LDXC, 1, R>(p, u, As, Xs, full, ready, consumed, ldx, jc);
+            else ws_consume_dispatch<CountT, LDXC, 2, R>(p, u, As, Xs, full, ready, consumed, ldx, jc);
         }
     } else {
         // ---------------- producers: TMA issue (warp 0 lane 0) + widening (4 warps x 8 rows) ----------------
@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gram_ws_kernel(const GramKernel
         bool is_ok = ws_decode(p, is_i, ldx, sizeof(CountT), is_u);
         bool wi_ok = ws_decode(p, wi_i, ldx, sizeof(CountT), wi_u);
         uint32_t ji = 0, jw = 0;
-        auto issue_next = [&]() {   // stage ji -> slot ji % WS_R
-            const uint32_t slot = ji % WS_R;
+        auto issue_next = [&]() {   // stage ji -> slot ji % R
+            const uint32_t slot = ji % R;
             if (pw == 0 && lane == 0) {
                 fence_proxy_async();
                 mbar_expect_tx(&full[slot], stage_bytes);
@@ -244,9 +244,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gram_ws_kernel(const GramKernel
             ++ji;
             if (++is_s == is_u.nstages) { is_s = 0; is_i += gridDim.x; is_ok = ws_decode(p, is_i, ldx, sizeof(CountT), is_u); }
         };
-        while (is_ok && ji < (uint32_t)WS_R) issue_next();
+        while (is_ok && ji < (uint32_t)R) issue_next();
         while (wi_ok) {
-            const uint32_t slot = jw % WS_R, par = (jw / WS_R) & 1u;
+            const uint32_t slot = jw % R, par = (jw / R) & 1u;
             mbar_wait(&full[slot], par);
             // widen Cr[slot] (32 rows x 128 slots) -> As[slot], fragment-major; producer warp pw takes rows 8 pw .. 8 pw + 7
             {
@@ -268,21 +268,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gram_ws_kernel(const GramKernel
             if (lane == 0) mbar_arrive(&ready[slot]);
             ++jw;
             if (++wi_s == wi_u.nstages) { wi_s = 0; wi_i += gridDim.x; wi_ok = ws_decode(p, wi_i, ldx, sizeof(CountT), wi_u); }
-            // refill: stage ji reuses the slot of stage ji - WS_R, which the consumers must have finished (only the issuing
+            // refill: stage ji reuses the slot of stage ji - R, which the consumers must have finished (only the issuing
             // warp waits; the other producer warps meet the new stage at its full[] barrier)
-            if (is_ok && ji <= jw + (uint32_t)(WS_R - 2)) {
-                const uint32_t prev = ji - WS_R;
-                if (pw == 0) mbar_wait(&consumed[prev % WS_R], (prev / WS_R) & 1u);
+            if (is_ok && ji <= jw + (uint32_t)(R - 2)) {
+                const uint32_t prev = ji - R;
+                if (pw == 0) mbar_wait(&consumed[prev % R], (prev / R) & 1u);
                 issue_next();
             }
         }
     }
 }
 
-static size_t gram_ws_smem(int ldx, int count_bytes) {
-    return sizeof(double) * ((size_t)WS_R * A_TILE + 256 + (size_t)WS_R * KT * ldx) + (size_t)WS_R * KT * BM * count_bytes +
-           sizeof(uint64_t) * 3 * WS_R;
+static size_t gram_ws_smem(int ldx, int count_bytes, int ring = WS_R) {
+    return sizeof(double) * ((size_t)ring * A_TILE + 256 + (size_t)ring * KT * ldx) + (size_t)ring * KT * BM * count_bytes +
+           sizeof(uint64_t) * 3 * ring;
 }
+constexpr size_t GRAM_SMEM_MAX = 227 * 1024;
 
 // Aligned binary summation tree over LEN consecutive leaves starting at `lo` (lo < cnt): leaves >= cnt are absent
 // and skipped.  The tree shape depends on the leaf indices only, so any aligned sub-range reduced on another GPU
@@ -396,7 +397,8 @@ GramPlan gram_make_plan(int K, int T, int ldx, int panels, const GroupData gd[2]
         total += pl.units[g];
     }
     pl.grid = (int)std::min<int64_t>(num_sms, std::max<int64_t>(total, 1));
-    pl.smem_bytes = gram_ws_smem(pl.ldx, count_bytes);
+    pl.ring = gram_ws_smem(pl.ldx, count_bytes, WS_R) <= GRAM_SMEM_MAX ? WS_R : 2;
+    pl.smem_bytes = gram_ws_smem(pl.ldx, count_bytes, pl.ring);
     pl.num_partials = (int64_t)total;
     return pl;
 }
@@ -426,7 +428,7 @@ void gram_launch_leaves(const GramPlan& pl, const GramArgs& a, const int seg_lo[
     if (units <= 0) return;
     const int grid = (int)std::min<int64_t>(pl.grid, units);
     const size_t ws_smem = pl.smem_bytes;
-    if (ws_smem > 227 * 1024) throw StatusError{OB_ERR_UNSUPPORTED, "design too wide for the Gram kernel's shared-memory ring"};
+    if (ws_smem > GRAM_SMEM_MAX) throw StatusError{OB_ERR_UNSUPPORTED, "design too wide for the Gram kernel's shared-memory ring (K + outcomes <= 280)"};
     auto launch_ws = [&](auto kernel) {
         OB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem));
         kernel<<<grid, WS_THREADS, ws_smem, st>>>(p);
@@ -436,7 +438,9 @@ void gram_launch_leaves(const GramPlan& pl, const GramArgs& a, const int seg_lo[
     switch (pl.ldx) {
         OB_GRAM_WS_CASE(12) OB_GRAM_WS_CASE(20) OB_GRAM_WS_CASE(28) OB_GRAM_WS_CASE(36) OB_GRAM_WS_CASE(44) OB_GRAM_WS_CASE(52)
         OB_GRAM_WS_CASE(60) OB_GRAM_WS_CASE(68) OB_GRAM_WS_CASE(76) OB_GRAM_WS_CASE(84) OB_GRAM_WS_CASE(92)
-        default: if (a.count_bytes == 1) launch_ws(gram_ws_kernel<uint8_t, 0>); else launch_ws(gram_ws_kernel<uint16_t, 0>);
+        default:      // wider designs: run-time row stride; two ring stages when three do not fit
+            if (pl.ring == WS_R) { if (a.count_bytes == 1) launch_ws(gram_ws_kernel<uint8_t, 0, WS_R>); else launch_ws(gram_ws_kernel<uint16_t, 0, WS_R>); }
+            else { if (a.count_bytes == 1) launch_ws(gram_ws_kernel<uint8_t, 0, 2>); else launch_ws(gram_ws_kernel<uint16_t, 0, 2>); }
     }
 #undef OB_GRAM_WS_CASE
     OB_CUDA(cudaGetLastError());

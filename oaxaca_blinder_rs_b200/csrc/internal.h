@@ -128,7 +128,7 @@ struct GramPlan {
     int64_t units[2];             // panels * ntiles * segs
     int grid;
     int64_t num_partials;         // = units[0] + units[1]
-    size_t smem_bytes;
+    size_t smem_bytes; int ring;  // shared memory and pipeline depth of the Gram CTA
 };
 // Column tiling of the P' sufficient-statistic columns: nfull tiles of BN columns and, when the remainder
 // fits, one half-width tail tile (P' = 171 at K = 17 costs 1.5 tiles instead of 2).
@@ -180,9 +180,12 @@ struct SolveArgs {
     int* status;             // [slots]
     double* beta_a; double* beta_b;    // [slots][K] (post-Yun) or nullptr
     double* point_extra;     // slot 0 only: [xa_mean K | xb_mean K | beta_star K | raw beta_a K | raw beta_b K | total_gap] or nullptr
+    double* scratch = nullptr;   // solve_scratch_bytes(..) of device memory when that is non-zero (designs wider than ~160 columns)
 };
 void solve_launch(const SolveArgs& a, cudaStream_t st);
 size_t solve_smem_bytes(int K, bool pooled, int n_norm);
+// 0 while a (K+1) x (K+1) system fits shared memory; else the bytes of per-slot global scratch solve_launch needs
+size_t solve_scratch_bytes(int K, bool pooled, int n_norm, int T, int64_t slots);
 
 // ---- reduce_stats.cu ----
 // stats [reps][S] + status [reps] (device) -> se,p,lo,hi,t [S] each (device, contiguous 5*S) and n_ok
@@ -215,6 +218,8 @@ void pack_scatter(const PackArgs& a, const long long* d_block_base, GroupData ga
 constexpr int PACK_BLOCK_ROWS = 128;
 // src[i] = first + i (designs built from dense per-group matrices: the "frame" is group A's rows, then group B's)
 void iota_launch(uint32_t* dst, int64_t n, uint32_t first, cudaStream_t st);
+// p[i] += add (frame-row maps of frame slices become maps into the whole frame)
+void add_u32_launch(uint32_t* p, int64_t n, uint32_t add, cudaStream_t st);
 // outcome refresh: X[r][K] = y[src[r]] (and Xs[r][K] = sqrt(w[r]) * y[src[r]]) for every packed row of the group
 void update_outcome_launch(const GroupData& g, int K, int ldx, const double* d_y_frame, cudaStream_t st);
 // Xs[i][:] = sqrt(w[i]) * X[i][:] for all V = K+1 columns (WLS as OLS on sqrt(w)-scaled data, ols.rs:68-78)
@@ -225,7 +230,7 @@ void residuals_launch(const GroupData& g, int K, int ycol, int ldx, const double
 void relayout_launch(const double* src, int ld_src, double* dst, int ld_dst, int64_t rows, int K, cudaStream_t st);
 
 // ---- ingest.cu ----
-constexpr int INGEST_MAX_COLS = 96;
+constexpr int INGEST_MAX_COLS = 288;
 struct IngestScanArgs {
     long long n;
     int n_valid; const uint8_t* valid[INGEST_MAX_COLS];      // validity bytes of the numeric columns that carry nulls

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_scatter_kernel(const PackKern
     __shared__ uint8_t lgrp[PK_ROWS];
     __shared__ int srcA[PK_ROWS], srcB[PK_ROWS];
     __shared__ int cnt[2];
-    __shared__ const double* scont[96];                 // column base pointers: no dependent global load per element
+    __shared__ const double* scont[288];                // column base pointers: no dependent global load per element
     const int V = p.K + 1, ts = V | 1;
     const int blk = blockIdx.x + p.blk0;
     const long long row0 = (long long)blk * PK_ROWS;
@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(PK_THREADS) pack_scatter_kernel(const PackKern
         const unsigned below = (1u << (tid & 31)) - 1u;
         lrank[tid] = g == 0 ? __popc(ma & below) : (g == 1 ? __popc(mb & below) : -1);
         if ((tid & 31) == 0) { wcount[tid >> 5][0] = __popc(ma); wcount[tid >> 5][1] = __popc(mb); }
-    } else if (tid - PK_ROWS < p.n_cont) {
-        scont[tid - PK_ROWS] = p.cont[tid - PK_ROWS];
+    } else {
+        for (int c = tid - PK_ROWS; c < p.n_cont; c += PK_THREADS - PK_ROWS) scont[c] = p.cont[c];
     }
     __syncthreads();
     if (tid < PK_ROWS && lrank[tid] >= 0) {
@@ -231,6 +231,16 @@ void scale_rows_launch(const GroupData& g, int ldx, cudaStream_t st) {
 __global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ dst, long long n, uint32_t first) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dst[i] = first + (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) add_u32_kernel(uint32_t* __restrict__ p, long long n, uint32_t add) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] += add;
+}
+
+void add_u32_launch(uint32_t* p, int64_t n, uint32_t add, cudaStream_t st) {
+    if (n == 0 || add == 0) return;
+    add_u32_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 16), 256, 0, st>>>(p, n, add);
+    OB_CUDA(cudaGetLastError());
 }
 
 void iota_launch(uint32_t* dst, int64_t n, uint32_t first, cudaStream_t st) {

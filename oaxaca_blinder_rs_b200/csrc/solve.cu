@@ -27,6 +27,7 @@ struct SolveParams {
     int n_base, S, weighted;
     double na, nb;
     double* stats; int* status; double* beta_a; double* beta_b; double* point_extra;
+    double* gscratch;        // per-slot matrix buffer in global memory when it does not fit shared memory, else null
 };
 
 __device__ __forceinline__ int ld_of(int N) { return N | 1; }  // odd stride: conflict-free column walks
@@ -105,6 +106,15 @@ __device__ void yun_shift(const SolveParams& p, double* beta, int shift_from, do
     }
 }
 
+// index of pair (i,j), i <= j < K, among the packed Gram columns (internal.h: pair_base)
+__device__ __forceinline__ long long gidx(int K, int T, int i, int j) {
+    return (long long)i * (K + T) - (long long)i * (i - 1) / 2 + (j - i);
+}
+__device__ __forceinline__ double gsym(const double* g, int K, int T, int i, int j) { return i <= j ? g[gidx(K, T, i, j)] : g[gidx(K, T, j, i)]; }
+
+// One system at a time in the matrix buffer M -- group A, group B, then (Pooled) the stacked system with the group
+// indicator -- so that the buffer is a single (K+1) x (K+1) matrix: shared memory up to K+1 = 164, a per-slot global
+// scratch beyond (p.gscratch).  Each factor is used for all T right-hand sides before the buffer is reused.
 __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveParams p) {
     extern __shared__ __align__(16) double sm[];
     const int K = p.K, T = p.T, Kp = K + 1;
@@ -112,96 +122,86 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveParams 
     const long long slot = blockIdx.x;
     const int tid = threadIdx.x;
     const bool pooled = p.ref_kind == OB_REF_POOLED;
+    const int msize = pooled ? Kp * ldp : K * ld;
 
-    double* GA = sm;
-    double* GB = GA + K * ld;
-    double* GP = GB + K * ld;                       // pooled (K+1)x(K+1), only when pooled
-    double* vec = GP + (pooled ? Kp * ldp : 0);
-    double* rA = vec;            double* rB = rA + Kp;   double* rP = rB + Kp;
-    double* xa = rP + Kp;        double* xb = xa + Kp;
+    double* vec = sm;
+    double* M = p.gscratch ? p.gscratch + (size_t)slot * msize : sm;
+    if (!p.gscratch) vec = sm + msize;
+    double* xa = vec;            double* xb = xa + Kp;
     double* bs = xb + Kp;        double* rawA = bs + Kp; double* rawB = rawA + Kp;
     double* baseA = rawB + Kp;   double* baseB = baseA + p.n_norm + 1; double* baseS = baseB + p.n_norm + 1;
+    double* BA = baseS + p.n_norm + 1;     // [T][Kp] solutions of group A
+    double* BB = BA + (size_t)T * Kp;      // [T][Kp]
+    double* BP = BB + (size_t)T * Kp;      // [T][Kp] pooled (only when pooled)
     __shared__ int fail;
-    __shared__ double sums[4];   // sum(cw) and sum(cwy) per group
+    __shared__ double sums[4];   // sum(cw) per group and, per outcome, sum(cwy)
 
     const double* gA = p.gram + (size_t)slot * p.Pld;
     const double* gB = p.gram + ((size_t)p.slots_pad + slot) * p.Pld;
-    if (tid == 0) fail = 0;
-    // ---- unpack X'WX from the packed columns: pair (j,l), j <= l < K, at pair_base(j) + (l - j) ----
-    for (int j = 0; j < K; ++j) {
-        const long long base_idx = (long long)j * (K + T) - (long long)j * (j - 1) / 2 - j;  // index of (j,l) = base_idx + l
-        for (int l = j + tid; l < K; l += blockDim.x) {
-            const double a = gA[base_idx + l], b = gB[base_idx + l];
-            GA[j * ld + l] = a; GA[l * ld + j] = a;
-            GB[j * ld + l] = b; GB[l * ld + j] = b;
-        }
+    if (tid == 0) { fail = 0; sums[0] = gA[0]; sums[2] = gB[0]; }
+    for (int j = tid; j < K; j += blockDim.x) {  // estimation.rs:56-71: the intercept row of the Gram carries the column sums
+        xa[j] = gA[j] / gA[0];
+        xb[j] = gB[j] / gB[0];
     }
-    __syncthreads();
     int status = OB_OK;
     // ols.rs:96-105: n_obs (row count, not sum of weights) must exceed k; group A is fitted first
     if (p.na <= (double)K || p.nb <= (double)K) status = OB_ERR_INSUFFICIENT_DATA;
+    const int ind = 1 + p.n_cont;       // builder.rs:548-566: position of the group indicator in the pooled design
 
-    if (tid < K) {  // estimation.rs:56-71
-        xa[tid] = GA[tid] / GA[0];
-        xb[tid] = GB[tid] / GB[0];
-    }
-    if (tid == 0) { sums[0] = GA[0]; sums[2] = GB[0]; }
-    const int ind = 1 + p.n_cont;
-    if (pooled) {
-        // builder.rs:548-566: rows of A and B stacked, indicator (1 on A rows) at column ind = 1 + n_cont
-        for (int e = tid; e < Kp * Kp; e += blockDim.x) {
-            const int i = e / Kp, j = e - i * Kp;
-            const int si = i < ind ? i : i - 1, sj = j < ind ? j : j - 1;  // source design columns
-            double v;
-            if (i == ind && j == ind) v = GA[0];
-            else if (i == ind) v = GA[sj];        // sum over A rows of w * 1 * x_sj
-            else if (j == ind) v = GA[si];
-            else v = GA[si * ld + sj] + GB[si * ld + sj];
-            GP[i * ldp + j] = v;
+    for (int sys = 0; sys < (pooled ? 3 : 2); ++sys) {
+        const int N = sys == 2 ? Kp : K, ldm = sys == 2 ? ldp : ld;
+        double* B = sys == 0 ? BA : (sys == 1 ? BB : BP);
+        const double* g = sys == 1 ? gB : gA;
+        __syncthreads();
+        if (status != OB_OK) break;
+        if (sys < 2) {
+            // unpack X'WX of the group from the packed columns
+            for (int i = 0; i < K; ++i) {
+                const long long base_idx = gidx(K, T, i, i) - i;
+                for (int l = i + tid; l < K; l += blockDim.x) {
+                    const double v = g[base_idx + l];
+                    M[i * ldm + l] = v; M[l * ldm + i] = v;
+                }
+            }
+            for (int e = tid; e < T * K; e += blockDim.x) {  // X'Wy of outcome t: pair (j, y_t) at pair_base(j) + (K - j) + t
+                const int t = e / K, j = e - t * K;
+                B[t * Kp + j] = g[gidx(K, T, j, j) + (K - j) + t];
+            }
+        } else {
+            if (p.na + p.nb <= (double)Kp) { status = OB_ERR_INSUFFICIENT_DATA; break; }
+            // rows of A and B stacked, indicator (1 on A rows) at column ind
+            for (int e = tid; e < Kp * Kp; e += blockDim.x) {
+                const int i = e / Kp, j = e - i * Kp;
+                const int si = i < ind ? i : i - 1, sj = j < ind ? j : j - 1;  // source design columns
+                double v;
+                if (i == ind && j == ind) v = gA[0];
+                else if (i == ind) v = gA[sj];        // sum over A rows of w * 1 * x_sj
+                else if (j == ind) v = gA[si];
+                else v = gsym(gA, K, T, si, sj) + gsym(gB, K, T, si, sj);
+                M[i * ldm + j] = v;
+            }
+            for (int e = tid; e < T * Kp; e += blockDim.x) {
+                const int t = e / Kp, i = e - t * Kp;
+                const int si = i < ind ? i : i - 1;
+                const long long ya = gidx(K, T, 0, 0) + K + t;             // (0, y_t): sum over A rows of w y_t
+                B[e] = (i == ind) ? gA[ya] : gA[gidx(K, T, si, si) + (K - si) + t] + gB[gidx(K, T, si, si) + (K - si) + t];
+            }
         }
+        __syncthreads();
+        if (!chol_factor(M, N, ldm, &fail)) { status = OB_ERR_NALGEBRA; break; }
+        for (int t = 0; t < T; ++t) chol_solve(M, N, ldm, B + (size_t)t * Kp);
     }
     __syncthreads();
-
-    // the factorisations do not depend on the outcome: once per slot, whatever T
-    if (status == OB_OK) {
-        if (!chol_factor(GA, K, ld, &fail)) status = OB_ERR_NALGEBRA;
-    }
-    if (status == OB_OK) {
-        if (!chol_factor(GB, K, ld, &fail)) status = OB_ERR_NALGEBRA;
-    }
-    if (status == OB_OK && pooled) {
-        if (p.na + p.nb <= (double)Kp) status = OB_ERR_INSUFFICIENT_DATA;
-        else if (!chol_factor(GP, Kp, ldp, &fail)) status = OB_ERR_NALGEBRA;
-    }
 
     const int D = K + p.n_base;
     for (int t = 0; t < T; ++t) {
         double* out = p.stats + ((size_t)slot * T + t) * p.S;
         const size_t brow = ((size_t)slot * T + t) * K;
-        // ---- X'Wy of outcome t: pair (j, y_t) at pair_base(j) + (K - j) + t ----
-        __syncthreads();
-        for (int j = tid; j < K; j += blockDim.x) {
-            const long long idx = (long long)j * (K + T) - (long long)j * (j - 1) / 2 + (K - j) + t;
-            rA[j] = gA[idx]; rB[j] = gB[idx];
-        }
-        __syncthreads();
-        if (tid == 0) { sums[1] = rA[0]; sums[3] = rB[0]; }
-        if (pooled)
-            for (int i = tid; i < Kp; i += blockDim.x) {
-                const int si = i < ind ? i : i - 1;
-                rP[i] = (i == ind) ? rA[0] : rA[si] + rB[si];
-            }
-        __syncthreads();
-        if (status == OB_OK) {
-            chol_solve(GA, K, ld, rA);
-            chol_solve(GB, K, ld, rB);
-            if (pooled) chol_solve(GP, Kp, ldp, rP);
-        }
-
         // ---- scalar epilogue ----
         int st_t = status;
         if (tid == 0 && st_t == OB_OK) {
-            double* ba = rA; double* bb = rB;
+            double* ba = BA + (size_t)t * Kp; double* bb = BB + (size_t)t * Kp; double* rP = BP + (size_t)t * Kp;
+            sums[1] = gA[K + t]; sums[3] = gB[K + t];                      // pair (0, y_t)
             for (int j = 0; j < K; ++j) { rawA[j] = ba[j]; rawB[j] = bb[j]; }
             if (p.n_norm > 0) { yun_shift(p, ba, -1, baseA); yun_shift(p, bb, -1, baseB); }   // estimation.rs:76-91
             switch (p.ref_kind) {  // builder.rs:538-621
@@ -280,10 +280,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(const SolveParams 
     }
 }
 
+// shared memory of one solve CTA: the vectors always, the matrix buffer while it fits (else per-slot global scratch)
+static size_t solve_vec_doubles(int K, int n_norm, int T) { return (size_t)5 * (K + 1) + (size_t)3 * (n_norm + 1) + (size_t)3 * T * (K + 1); }
+static size_t solve_mat_doubles(int K, bool pooled) { const int Kp = K + 1; return pooled ? (size_t)Kp * (Kp | 1) : (size_t)K * (K | 1); }
+constexpr size_t SOLVE_SMEM_MAX = 227 * 1024;
+
 size_t solve_smem_bytes(int K, bool pooled, int n_norm) {
-    const int Kp = K + 1, ld = K | 1, ldp = Kp | 1;
-    size_t d = (size_t)2 * K * ld + (pooled ? (size_t)Kp * ldp : 0) + (size_t)8 * Kp + (size_t)3 * (n_norm + 1);
-    return d * sizeof(double);
+    return (solve_vec_doubles(K, n_norm, 1) + solve_mat_doubles(K, pooled)) * sizeof(double);
+}
+
+size_t solve_scratch_bytes(int K, bool pooled, int n_norm, int T, int64_t slots) {
+    const size_t in_smem = (solve_vec_doubles(K, n_norm, T) + solve_mat_doubles(K, pooled)) * sizeof(double);
+    return in_smem <= SOLVE_SMEM_MAX ? 0 : sizeof(double) * solve_mat_doubles(K, pooled) * (size_t)slots;
 }
 
 void solve_launch(const SolveArgs& a, cudaStream_t st) {
@@ -294,7 +302,12 @@ void solve_launch(const SolveArgs& a, cudaStream_t st) {
     p.norm_has_base = a.d_norm_has_base; p.n_base = a.n_base; p.S = a.S; p.weighted = a.weighted;
     p.na = a.na; p.nb = a.nb;
     p.stats = a.stats; p.status = a.status; p.beta_a = a.beta_a; p.beta_b = a.beta_b; p.point_extra = a.point_extra;
-    const size_t smem = solve_smem_bytes(a.K, a.ref_kind == OB_REF_POOLED, a.n_norm);
+    const bool pooled = a.ref_kind == OB_REF_POOLED;
+    const bool global = solve_scratch_bytes(a.K, pooled, a.n_norm, a.T, 1) != 0;
+    if (global && !a.scratch) throw StatusError{OB_ERR_INVALID_ARG, "solve scratch missing for a design this wide"};
+    p.gscratch = global ? a.scratch : nullptr;
+    const size_t smem = (solve_vec_doubles(a.K, a.n_norm, a.T) + (global ? 0 : solve_mat_doubles(a.K, pooled))) * sizeof(double);
+    if (smem > SOLVE_SMEM_MAX) throw StatusError{OB_ERR_UNSUPPORTED, "design too wide for the solve kernel"};
     OB_CUDA(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     solve_kernel<<<(unsigned)a.slots, SOLVE_THREADS, smem, st>>>(p);
     OB_CUDA(cudaGetLastError());

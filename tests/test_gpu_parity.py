@@ -491,3 +491,24 @@ def test_rif_quantile_sweep_on_one_design(ob, orc, ctx):
     _, ga, _, _, gb, _ = des.download()
     assert relerr(ga, orc.rif(2.0 * ya + 1.0, 0.9)) <= RTOL
     des.close()
+
+
+@pytest.mark.parametrize("n_cont,ref", [(100, "pooled"), (120, "A"), (170, "pooled"), (230, "weighted")])
+def test_wide_designs_beyond_90_columns(ob, orc, ctx, n_cont, ref):
+    """No K <= 90 limit any more: the Gram kernel takes any row stride (two ring stages once three no longer fit shared
+    memory), the solve keeps one system at a time in shared memory (global scratch beyond ~160 columns)."""
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(6_000, n_cont, cat_levels=(3,), weights=True, seed=n_cont)
+    Xa, ya, wa, Xb, yb, wb = synth.dense_design(d)
+    norm = synth.norm_spec(d)
+    assert Xa.shape[1] == n_cont + 3
+    gpu, ref_out = run_both(ob, orc, ctx, Xa, ya, wa, Xb, yb, wb, n_cont, REFS[ref], norm, reps=12)
+    compare(gpu, ref_out)
+    assert gpu["n_ok"] == 12
+
+
+def test_design_wider_than_the_kernels_is_refused(ob, ctx):
+    X = np.ones((50, 300))
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.Design.from_dense(ctx, X, np.ones(50), None, X, np.ones(50), None, 10)
+    assert e.value.kind == "Unsupported"

@@ -195,7 +195,11 @@ def test_allgather_rows_equals_whole_frame_pack(weighted):
     whole.close(); ctx.close()
     world = 4
     grp = core.LocalGroup(world)
-    outs, errs = [None] * world, [None] * world
+    outs, errs, refreshed = [None] * world, [None] * world, [None] * world
+    c0 = ob.Context(0)
+    w2 = ob.Design.pack(c0, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"] * 2.0 + 1.0, d["weights"], d["group"])
+    ref2 = w2.download()
+    w2.close(); c0.close()
 
     def work(r):
         try:
@@ -204,6 +208,9 @@ def test_allgather_rows_equals_whole_frame_pack(weighted):
             full = obd.pack_replicated(c, d, r, world)
             b, e = obd.shard_range(r, world, 40)
             outs[r] = (full.download(), ob.bootstrap(full, 40, seed=3, rep_begin=b, rep_end=e, skip_reduce=True))
+            # the frame-row map travelled with the rows: an outcome refresh on the gathered design equals a re-pack
+            full.update_outcome(d["outcome"] * 2.0 + 1.0)
+            refreshed[r] = full.download()
             full.close(); c.close()
         except Exception as ex:  # noqa: BLE001
             errs[r] = ex
@@ -220,6 +227,9 @@ def test_allgather_rows_equals_whole_frame_pack(weighted):
         b, e = obd.shard_range(r, world, 40)
         assert _same(part["rep_stats"], ref_run["rep_stats"][b:e])
         assert _same(part["point_stats"], ref_run["point_stats"])
+        for a, b_ in zip(refreshed[r], ref2):
+            if weighted or not np.all(np.isnan(b_)):
+                assert np.array_equal(a, b_, equal_nan=True)
 
 
 def test_chunked_generator_shards_match_the_whole_frame():
@@ -284,6 +294,13 @@ def test_redistributed_slices_equal_row_shards(world, sort_by_group):
             same = all(np.array_equal(a, b_, equal_nan=True) for a, b_ in zip(shard.download(), direct.download()))
             direct.close()
             outs[r] = (same, ob.bootstrap(shard, 150, ref_kind=ob.REF_POOLED, norm=norm, seed=41, want_rep=True))
+            # outcome refresh on the shard (whole-frame y on every rank) == a shard packed from the new outcome
+            y2 = d["outcome"] * 0.5 - 3.0
+            shard.update_outcome(y2)
+            d2 = dict(d, outcome=y2)
+            direct2 = obd.pack_row_shard(c, d2, r, world)
+            assert all(np.array_equal(a, b_, equal_nan=True) for a, b_ in zip(shard.download(), direct2.download()))
+            direct2.close()
             shard.close(); c.close()
         except Exception as ex:  # noqa: BLE001
             errs[r] = ex
