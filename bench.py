@@ -475,10 +475,11 @@ def main():
                       cat_levels=d["cat_levels"], outcome=pinned["y"].numpy(),
                       weights=None if pinned["w"] is None else pinned["w"].numpy(), group=pinned["g"].numpy())
             if e2e and e2e_rowshard:
-                # host frame -> this rank uploads 1/world of it, packs it, and the groups' rows are re-cut into row shards
-                # over NVLink (ob_design_redistribute_rows): no GPU ever needs the other ranks' rows, and the bootstrap
-                # runs row-sharded (mode N: bit-identical to one GPU, like mode R)
-                return obd.pack_row_shard_from_slice(ctx, fr, rank, world)
+                # host frame -> this rank uploads 1/world of it in chunks (ob_design_pack_row_shard_async): rows go straight
+                # to their place in the rank's row shard, the few rows other ranks own are exchanged over NVLink, and the
+                # row-sharded bootstrap (mode N: bit-identical to one GPU, like mode R) overlaps all of it with its
+                # replicate generation and a first Gram launch.  No GPU ever needs the other ranks' rows.
+                return obd.pack_row_shard_async(ctx, fr, rank, world)
             # mode R: this rank uploads 1/world of the frame; the packed rows are all-gathered over NVLink
             des = obd.pack_replicated(ctx, fr, rank, world)
             if rif_tau is not None:
@@ -646,7 +647,8 @@ def main():
                         "d2h_bytes_per_step": int(d2h),
                         "path": ("ob_design_pack_async (chunked upload + pack on the copy stream, under the replicate generation and "
                                  "the first Gram launch) -> ob_bootstrap_run" if world == 1 and rif_tau is None else
-                                 "per rank: upload 1/N of the frame -> pack -> ob_design_redistribute_rows (NVLink) -> row-sharded "
+                                 "per rank: ob_design_pack_row_shard_async (1/N of the frame uploaded in chunks, rows packed straight into "
+                                 "the rank's row shard, boundary rows exchanged over NVLink) overlapped with the row-sharded "
                                  "ob_bootstrap_run (mode N)" if e2e_rowshard else
                                  "per rank: upload 1/N of the frame -> pack -> ob_design_allgather_rows (NVLink) -> replicate-sharded "
                                  "ob_bootstrap_run (mode R)" if world > 1 and not shard_rows else

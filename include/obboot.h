@@ -92,6 +92,13 @@ ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* frame, ob_design** ou
  * and the design is unusable afterwards. */
 ob_status ob_design_pack_async(ob_ctx* ctx, const ob_frame_view* frame, ob_design** out);
 ob_status ob_design_wait(ob_ctx* ctx, ob_design* d);
+/* The same for mode N (a collective: every rank of the context's communicator calls it, with ITS contiguous slice of
+ * the frame, slices in rank order): the result is rank's ROW SHARD (as ob_design_redistribute_rows builds), but a
+ * row is written straight to its place in the shard while the slice is still uploading, only the rows another rank
+ * owns wait in an export buffer for one exchange over NVLink, and ob_bootstrap_run overlaps all of it with its
+ * replicate generation and a first Gram launch over the rows already in place.  The first call that uses the design
+ * performs the exchange and is therefore a collective too. */
+ob_status ob_design_pack_row_shard_async(ob_ctx* ctx, const ob_frame_view* slice, ob_design** out);
 
 /* ---- (0) ingest: cleaning and coding on the device --------------------------------------------
  * What the reference does on the host between run()'s clone of the frame (builder.rs:788) and the group split:

@@ -28,7 +28,8 @@ SYMBOLS = ["ob_abi_version", "ob_device_count", "ob_ctx_create", "ob_ctx_destroy
            "ob_ingest_begin", "ob_ingest_rows_kept", "ob_ingest_presence", "ob_ingest_finish", "ob_ingest_destroy",
            "ob_debug_gram_schedule", "ob_debug_counts_from_indices", "ob_host_alloc", "ob_host_free",
            "ob_host_register", "ob_host_unregister", "ob_replicate_shard", "ob_design_pack_async", "ob_design_wait",
-           "ob_design_redistribute_rows", "ob_design_row_shard", "ob_design_apply_rif_multi", "ob_design_num_outcomes"]
+           "ob_design_redistribute_rows", "ob_design_row_shard", "ob_design_apply_rif_multi", "ob_design_num_outcomes",
+           "ob_design_pack_row_shard_async"]
 
 
 class FrameView(C.Structure):
@@ -137,6 +138,7 @@ def lib() -> C.CDLL:
                                                    C.POINTER(C.c_uint16), _IP]
         L.ob_design_pack_async.argtypes = [C.c_void_p, C.POINTER(FrameView), C.POINTER(C.c_void_p)]
         L.ob_design_wait.argtypes = [C.c_void_p, C.c_void_p]
+        L.ob_design_pack_row_shard_async.argtypes = [C.c_void_p, C.POINTER(FrameView), C.POINTER(C.c_void_p)]
         L.ob_design_apply_rif_multi.argtypes = [C.c_void_p, C.c_void_p, _DP, C.c_int32]
         L.ob_design_num_outcomes.argtypes = [C.c_void_p, _IP]
         L.ob_design_row_shard.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _IP, _IP]

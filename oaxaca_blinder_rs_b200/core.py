@@ -152,7 +152,8 @@ class Design:
 
     @classmethod
     def pack(cls, ctx: Context, cont: Sequence[np.ndarray], cat_codes: Sequence[np.ndarray],
-             cat_levels: Sequence[int], outcome, weights, group, asynchronous: bool = False) -> "Design":
+             cat_levels: Sequence[int], outcome, weights, group, asynchronous: bool = False,
+             row_shard: bool = False) -> "Design":
         """ob_design_pack from host columns (the cleaned, coded frame at builder.rs:808).
         asynchronous=True: ob_design_pack_async -- returns once the group split is known; the columns (keep them alive
         and unmodified, ideally in page-locked memory) are uploaded and packed under the first kernels of the next
@@ -173,6 +174,12 @@ class Design:
         fv.outcome, fv.weights = _dp(outcome), _dp(weights)
         fv.group = group.ctypes.data_as(C.POINTER(C.c_uint8))
         h = C.c_void_p()
+        if row_shard:
+            # ob_design_pack_row_shard_async (collective): the columns are THIS RANK'S frame slice, the result its row shard
+            ctx.check(N.lib().ob_design_pack_row_shard_async(ctx._h, C.byref(fv), C.byref(h)))
+            des = cls(ctx, h)
+            des._inflight = (cont, cats, outcome, weights, group)
+            return des
         if asynchronous:
             ctx.check(N.lib().ob_design_pack_async(ctx._h, C.byref(fv), C.byref(h)))
             des = cls(ctx, h)

@@ -112,7 +112,14 @@ struct PendingPack {
     StagedFrame sf;
     DevBuf d_bc, d_tot, d_flags, d_cont_ptrs, d_cat_ptrs, d_levels, d_dstart;
     std::vector<cudaEvent_t> chunk_done;     // recorded on the copy stream after chunk c's rows are packed
-    std::vector<int64_t> rows_ready[2];      // rows of group g that are final once chunk c is done
+    int64_t ready_lo[2] = {0, 0};            // design rows [ready_lo[g], rows_ready[g][c]) of group g are final once chunk c is done
+    std::vector<int64_t> rows_ready[2];
+    // row-shard packs (ob_design_pack_row_shard_async): the slice's rows that belong to other ranks wait in export buffers
+    // for ONE exchange over the communicator (after the last chunk, on the context's stream, a collective)
+    bool exchange_pending = false;
+    DevBuf EX[2], Ew[2], Esrc[2];
+    std::vector<size_t> ex_rows[2], ex_send_row[2], ex_recv_row[2];   // rows[src * world + dst]; offsets in rows
+    std::vector<long long> ex_frame_off;
     cudaEvent_t ev_begin = nullptr, ev_h2d_end = nullptr;   // timing: first upload .. last pack kernel
     int* h_flags = nullptr;                  // pinned [4] (a slot of the context's): pack flags, valid after the last chunk
     int slot = -1;
@@ -226,12 +233,46 @@ void design_release_device(ob_design* d) {
     }
 }
 
+// The one exchange of an asynchronous row-shard pack: every rank sends the rows of its slice that other ranks own (they
+// sit in its export buffers) and receives its own from the slices of others, straight into place; then scales what it
+// imported.  Enqueued on the context's stream after the last chunk; a collective (all ranks, same order).
+void pending_exchange(ob_design* d) {
+    PendingPack* P = d->pending;
+    if (!P || !P->exchange_pending) return;
+    ob_ctx* ctx = d->owner;
+    Comm* comm = ctx->comm.get();
+    if (!comm) fail(OB_ERR_NCCL, "the communicator of an asynchronous row-shard pack was destroyed before its exchange");
+    cudaStream_t st = ctx->stream;
+    const int world = comm->world, me = comm->rank;
+    OB_CUDA(cudaStreamWaitEvent(st, P->chunk_done.back(), 0));
+    for (int g = 0; g < 2; ++g) {
+        GroupData& G = d->g[g];
+        auto exchange = [&](const void* sendbuf, void* recvbuf, size_t row_bytes) {
+            std::vector<size_t> b(P->ex_rows[g].size()), so((size_t)world), ro((size_t)world);
+            for (size_t i = 0; i < b.size(); ++i) b[i] = P->ex_rows[g][i] * row_bytes;
+            for (int r = 0; r < world; ++r) { so[r] = P->ex_send_row[g][r] * row_bytes; ro[r] = P->ex_recv_row[g][r] * row_bytes; }
+            comm->alltoallv(sendbuf, so.data(), recvbuf, ro.data(), b.data(), st);
+        };
+        exchange(P->EX[g].p, G.X, sizeof(double) * (size_t)d->ldx);
+        if (d->weighted) exchange(P->Ew[g].p, G.w, sizeof(double));
+        exchange(P->Esrc[g].p, G.src, sizeof(uint32_t));
+        for (int r = 0; r < world; ++r) {
+            const int64_t rows = (int64_t)P->ex_rows[g][(size_t)r * world + me];
+            if (!rows) continue;
+            scale_rows_range_launch(G, d->ldx, (int64_t)P->ex_recv_row[g][r], rows, st);
+        }
+    }
+    OB_CUDA(cudaStreamSynchronize(st));      // the byte tables of the exchange live on this stack frame
+    P->exchange_pending = false;
+}
+
 // Completes an asynchronous pack: waits for the copy stream, releases the staging buffers (on the context's stream,
 // ordered after the last pack kernel), collects timings and the deferred error flags.  quiet: never throws (destroy).
 void pending_finish(ob_design* d, bool quiet = false) {
     PendingPack* P = d->pending;
     if (!P) return;
     ob_ctx* ctx = d->owner;
+    if (P->exchange_pending && ctx && !quiet) pending_exchange(d);   // (a design destroyed unused skips the collective)
     d->pending = nullptr;
     cudaEvent_t last = P->chunk_done.back();
     if (ctx) cudaStreamWaitEvent(ctx->stream, last, 0);      // the DevBufs of P are freed on ctx->stream
@@ -802,10 +843,13 @@ ob_status ob_design_pack(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
 // Asynchronous pack.  Host part (about a millisecond): upload the group column, count and scan it, size and allocate
 // the design.  Everything else is queued on the copy stream in row chunks -- the column slices of a chunk, then the
 // pack kernel over its blocks -- with one event per chunk that ob_bootstrap_run waits on.
-ob_status ob_design_pack_async(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) {
+static ob_status pack_async_impl(ob_ctx* ctx, const ob_frame_view* f, bool shard, ob_design** out) {
     if (!ctx || !f || !out) return OB_ERR_INVALID_ARG;
     *out = nullptr;
     return guarded(ctx, [&] {
+        Comm* comm = shard ? ctx->comm.get() : nullptr;
+        if (shard && !comm) fail(OB_ERR_NCCL, "ob_design_pack_row_shard_async needs ob_comm_init_* on this context");
+        if (shard && (comm->world & (comm->world - 1))) fail(OB_ERR_INVALID_ARG, "row shards need a power-of-two world");
         if (f->n < 0 || f->n_cont < 0 || f->n_cat < 0) fail(OB_ERR_INVALID_ARG, "bad frame shape");
         if (f->n && (!f->outcome || !f->group)) fail(OB_ERR_INVALID_ARG, "null frame column");
         for (int c = 0; c < f->n_cont; ++c) if (!f->cont[c]) fail(OB_ERR_INVALID_ARG, "null predictor column");
@@ -878,8 +922,68 @@ ob_status ob_design_pack_async(ob_ctx* ctx, const ob_frame_view* f, ob_design** 
         design_register(ctx, d.get()); d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = sf.n_cont; d->V = K + 1; d->ldx = pa.ldx;
         d->weighted = sf.weighted;
         d->n_frame = n;
-        alloc_group(ctx, d->g[0], tot[0], d->ldx, d->weighted, false);
-        alloc_group(ctx, d->g[1], tot[1], d->ldx, d->weighted, false);
+        PackWindow win{};
+        const PackWindow* winp = nullptr;
+        if (!shard) {
+            alloc_group(ctx, d->g[0], tot[0], d->ldx, d->weighted, false);
+            alloc_group(ctx, d->g[1], tot[1], d->ldx, d->weighted, false);
+        } else {
+            // where this slice's rows sit inside the whole groups: every rank's group sizes, shape word and frame rows
+            const int world = comm->world, me = comm->rank;
+            std::vector<long long> mine = {tot[0], tot[1], ((long long)K << 32) | ((long long)sf.n_cont << 1) | (sf.weighted ? 1 : 0), (long long)n};
+            DevBuf d_mine(sizeof(long long) * 4), d_all(sizeof(long long) * 4 * world);
+            OB_CUDA(cudaMemcpyAsync(d_mine.p, mine.data(), sizeof(long long) * 4, cudaMemcpyHostToDevice, st));
+            comm->allgather(d_mine.p, d_all.p, sizeof(long long) * 4, st);
+            std::vector<long long> all(4 * (size_t)world);
+            OB_CUDA(cudaMemcpyAsync(all.data(), d_all.p, sizeof(long long) * 4 * world, cudaMemcpyDeviceToHost, st));
+            OB_CUDA(cudaStreamSynchronize(st));
+            P->ex_frame_off.assign((size_t)world + 1, 0);
+            for (int r = 0; r < world; ++r) {
+                if (all[4 * r + 2] != mine[2]) fail(OB_ERR_INVALID_ARG, "ranks disagree on the design shape (K, n_cont, weights)");
+                P->ex_frame_off[r + 1] = P->ex_frame_off[r] + all[4 * r + 3];
+            }
+            if (P->ex_frame_off[world] > 0xFFFFFFFFll) fail(OB_ERR_UNSUPPORTED, "frames beyond 2^32 rows");
+            d->n_frame = P->ex_frame_off[world];
+            d->world = world; d->rank = me;
+            win.src_add = (uint32_t)P->ex_frame_off[me];
+            for (int g = 0; g < 2; ++g) {
+                std::vector<long long> off((size_t)world + 1, 0);
+                for (int r = 0; r < world; ++r) off[r + 1] = off[r] + all[4 * r + g];
+                std::vector<RowShard> plan((size_t)world);
+                for (int t = 0; t < world; ++t) plan[t] = row_shard(off[world], t, world);
+                alloc_group(ctx, d->g[g], plan[me].n_local, d->ldx, d->weighted, false);
+                d->g[g].shard = plan[me];
+                const long long rb = plan[me].row_begin, re = rb + plan[me].n_local;
+                const long long lo_cnt = std::max<long long>(0, std::min<long long>(rb, off[me + 1]) - off[me]);   // my rows below my shard
+                const long long hi_cnt = std::max<long long>(0, off[me + 1] - std::max<long long>(re, off[me]));   // my rows above it
+                win.shift[g] = off[me] - rb; win.n_local[g] = plan[me].n_local;
+                win.lo_add[g] = rb - off[me];                                             // low-side rows keep their slice order from 0
+                win.hi_base[g] = lo_cnt - std::max<long long>(0, off[me] - re);             // high-side rows follow the low-side ones
+                const size_t erows = (size_t)std::max<long long>(lo_cnt + hi_cnt, 1);
+                P->EX[g].alloc(sizeof(double) * erows * d->ldx); P->Ew[g].alloc(sizeof(double) * erows); P->Esrc[g].alloc(sizeof(uint32_t) * erows);
+                win.EX[g] = P->EX[g].as<double>(); win.Ew[g] = P->Ew[g].as<double>(); win.Esrc[g] = P->Esrc[g].as<uint32_t>();
+                // exchange tables: rows[src * world + dst]; what a rank keeps (src == dst) was written in place by the pack
+                P->ex_rows[g].assign((size_t)world * world, 0); P->ex_send_row[g].assign((size_t)world, 0); P->ex_recv_row[g].assign((size_t)world, 0);
+                for (int sidx = 0; sidx < world; ++sidx)
+                    for (int t = 0; t < world; ++t) {
+                        if (sidx == t) continue;
+                        const long long lo = std::max<long long>(off[sidx], plan[t].row_begin);
+                        const long long hi = std::min<long long>(off[sidx + 1], plan[t].row_begin + plan[t].n_local);
+                        P->ex_rows[g][(size_t)sidx * world + t] = hi > lo ? (size_t)(hi - lo) : 0;
+                    }
+                for (int r = 0; r < world; ++r) {
+                    // position inside MY export buffer of the first row I hold for rank r: low-side rows keep their slice
+                    // order from 0, high-side rows follow at lo_cnt
+                    const long long first = std::max<long long>(off[me], plan[r].row_begin);      // global position
+                    P->ex_send_row[g][r] = (size_t)std::max<long long>(0, first < rb ? first - off[me] : lo_cnt + (first - std::max<long long>(re, off[me])));
+                    P->ex_recv_row[g][r] = (size_t)std::max<long long>(0, std::max<long long>(off[r], rb) - rb);                  // inside my shard
+                }
+                // rows the pack writes in place: [ready_lo, ..) in shard-local coordinates
+                P->ready_lo[g] = std::min<long long>(std::max<long long>(win.shift[g], 0), plan[me].n_local);
+            }
+            P->exchange_pending = true;
+            winp = &win;
+        }
         pa.d_w = sf.weighted ? sf.w.as<double>() : nullptr;
         // an error from here on must not release buffers the copy stream is still writing
         struct CopyJoin { cudaStream_t s; bool armed = true; ~CopyJoin() { if (armed) cudaStreamSynchronize(s); } } copy_join{sc};
@@ -902,11 +1006,15 @@ ob_status ob_design_pack_async(ob_ctx* ctx, const ob_frame_view* f, ob_design** 
                 if (sf.weighted) OB_CUDA(cudaMemcpyAsync(sf.w.as<double>() + r0, f->weights + r0, sizeof(double) * rows, cudaMemcpyHostToDevice, sc));
             }
             if (c == nchunks - 1) OB_CUDA(cudaEventRecord(P->ev_h2d_end, sc));
-            pack_scatter(pa, P->d_bc.as<long long>(), d->g[0], d->g[1], P->d_flags.as<int>(), sc, cut[c], cut[c + 1]);
+            pack_scatter(pa, P->d_bc.as<long long>(), d->g[0], d->g[1], P->d_flags.as<int>(), sc, cut[c], cut[c + 1], winp);
             if (c == nchunks - 1) OB_CUDA(cudaMemcpyAsync(P->h_flags, P->d_flags.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, sc));
             OB_CUDA(cudaEventCreate(&P->chunk_done[(size_t)c]));
             OB_CUDA(cudaEventRecord(P->chunk_done[(size_t)c], sc));
-            for (int g = 0; g < 2; ++g) P->rows_ready[g].push_back(c == nchunks - 1 ? tot[g] : base[2 * (size_t)(c + 1) + g]);
+            for (int g = 0; g < 2; ++g) {
+                const long long q = c == nchunks - 1 ? tot[g] : base[2 * (size_t)(c + 1) + g];     // slice rows of the group packed so far
+                // in place up to shard row q + shift (clamped); the last chunk of a shard still lacks the imported rows
+                P->rows_ready[g].push_back(shard ? std::min<long long>(std::max<long long>(q + win.shift[g], P->ready_lo[g]), win.n_local[g]) : q);
+            }
         }
         ctx->pack_slot_owner[P->slot] = d.get();
         d->pending = P.release();
@@ -914,6 +1022,10 @@ ob_status ob_design_pack_async(ob_ctx* ctx, const ob_frame_view* f, ob_design** 
         *out = d.release();
     });
 }
+
+ob_status ob_design_pack_async(ob_ctx* ctx, const ob_frame_view* f, ob_design** out) { return pack_async_impl(ctx, f, false, out); }
+
+ob_status ob_design_pack_row_shard_async(ob_ctx* ctx, const ob_frame_view* slice, ob_design** out) { return pack_async_impl(ctx, slice, true, out); }
 
 ob_status ob_design_wait(ob_ctx* ctx, ob_design* d) {
     if (!ctx || !d) return OB_ERR_INVALID_ARG;
@@ -1339,27 +1451,36 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 } ev;
                 ob_design* dm = const_cast<ob_design*>(d);
                 if (PendingPack* P = dm->pending) {
-                    // the design's upload is still in flight (ob_design_pack_async): contract the leaves whose rows the
-                    // first chunk delivered, then -- once everything has arrived -- the rest.  Same partial tiles, same
-                    // fixed-tree sums as one launch.
-                    int lo[2] = {0, 0}, na[2] = {0, 0}, nb[2];
-                    const bool split = P->chunk_done.size() > 1 && !comm;
+                    // the design's upload is still in flight (ob_design_pack_async / _row_shard_async): contract the leaves
+                    // whose rows the first chunk delivered, then -- once everything has arrived (row shards: once the rows
+                    // owned by other ranks have been exchanged) -- the rest.  Same partial tiles, same fixed-tree sums as
+                    // one launch.
+                    int la[2] = {0, 0}, na[2] = {0, 0};
+                    const bool split = P->chunk_done.size() > 1;
                     for (int g = 0; g < 2; ++g) {
-                        if (split) na[g] = (int)std::min<int64_t>(plan.segs[g], P->rows_ready[g][0] / plan.seg_rows[g]);
-                        nb[g] = plan.segs[g] - na[g];
+                        if (!split || plan.segs[g] == 0) continue;
+                        const int64_t sr = plan.seg_rows[g];
+                        const int64_t lo = (P->ready_lo[g] + sr - 1) / sr, hi = std::min<int64_t>(plan.segs[g], P->rows_ready[g][0] / sr);
+                        if (hi > lo) { la[g] = (int)lo; na[g] = (int)(hi - lo); }
                     }
-                    EventPair evA, evB;        // OBBOOT_TRACE: where the two launches sit relative to the upload
+                    EventPair evA, evB;        // OBBOOT_TRACE: where the launches sit relative to the upload
                     OB_CUDA(cudaEventRecord(ev.a, st));
-                    if (split && na[0] + na[1] > 0) {
+                    if (na[0] + na[1] > 0) {
                         OB_CUDA(cudaStreamWaitEvent(st, P->chunk_done.front(), 0));
                         if (tr.on) OB_CUDA(cudaEventRecord(evA.a, st));
-                        gram_launch_leaves(plan, ga, lo, na, st);
+                        gram_launch_leaves(plan, ga, la, na, st);
                         if (tr.on) OB_CUDA(cudaEventRecord(evA.b, st));
                         res->gpu_launches += 1;
                     }
                     OB_CUDA(cudaStreamWaitEvent(st, P->chunk_done.back(), 0));
+                    pending_exchange(dm);      // row shards: import the rows other ranks uploaded (a collective, on st)
                     if (tr.on) OB_CUDA(cudaEventRecord(evB.a, st));
-                    gram_launch_leaves(plan, ga, na, nb, st);
+                    {   // the leaves before and after the first launch's range
+                        int lo0[2] = {0, 0}, n0[2] = {na[0] ? la[0] : 0, na[1] ? la[1] : 0};
+                        int lo1[2] = {la[0] + na[0], la[1] + na[1]}, n1[2] = {plan.segs[0] - lo1[0], plan.segs[1] - lo1[1]};
+                        if (n0[0] + n0[1] > 0) { gram_launch_leaves(plan, ga, lo0, n0, st); res->gpu_launches += 1; }
+                        gram_launch_leaves(plan, ga, lo1, n1, st);
+                    }
                     OB_CUDA(cudaEventRecord(ev.b, st));
                     gram_reduce_launch(plan, ga, st);
                     res->gpu_launches += 2;
@@ -1367,9 +1488,9 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                         OB_CUDA(cudaEventSynchronize(ev.b));
                         auto rel = [&](cudaEvent_t e) { float ms = -1.f; if (cudaEventElapsedTime(&ms, P->ev_begin, e) != cudaSuccess) { cudaGetLastError(); ms = -1.f; } return ms; };
                         fprintf(stderr, "[obboot] async pack (ms after its start): chunk 0 packed %.1f, upload done %.1f, all packed %.1f | "
-                                        "gram A %.1f..%.1f (leaves %d+%d), gram B %.1f..%.1f (leaves %d+%d)\n",
+                                        "first gram launch %.1f..%.1f (leaves %d+%d of %d+%d), rest %.1f..%.1f\n",
                                 rel(P->chunk_done.front()), rel(P->ev_h2d_end), rel(P->chunk_done.back()), rel(evA.a), rel(evA.b), na[0], na[1],
-                                rel(evB.a), rel(ev.b), nb[0], nb[1]);
+                                plan.segs[0], plan.segs[1], rel(evB.a), rel(ev.b));
                     }
                     pending_finish(dm);       // host: waits for the copy stream, releases the staging, raises deferred errors
                 } else {

@@ -212,9 +212,17 @@ struct PackArgs {
 int pack_num_blocks(int64_t n);
 void pack_count_scan(const PackArgs& a, long long* d_block_counts, long long* d_totals, int* d_flags, cudaStream_t st);
 // pass 3: staged transpose/scatter of the rows into the packed per-group designs
+// Row-shard window of a pack (ob_design_pack_row_shard_async): the packed frame slice's row q of group g belongs at shard
+// row pos = q + shift[g]; rows outside [0, n_local[g]) are exported for the exchange: low side (pos < 0) at export row
+// pos + lo_add[g] (= q), high side at hi_base[g] + (pos - n_local[g]).
+struct PackWindow {
+    long long shift[2], n_local[2], lo_add[2], hi_base[2];
+    double* EX[2]; double* Ew[2]; uint32_t* Esrc[2];
+    uint32_t src_add;
+};
 // blocks [blk0, blk1) of PK_ROWS = 128 frame rows each (blk1 < 0: to the end)
 void pack_scatter(const PackArgs& a, const long long* d_block_base, GroupData ga, GroupData gb, int* d_flags,
-                  cudaStream_t st, int blk0 = 0, int blk1 = -1);
+                  cudaStream_t st, int blk0 = 0, int blk1 = -1, const PackWindow* win = nullptr);
 constexpr int PACK_BLOCK_ROWS = 128;
 // src[i] = first + i (designs built from dense per-group matrices: the "frame" is group A's rows, then group B's)
 void iota_launch(uint32_t* dst, int64_t n, uint32_t first, cudaStream_t st);
@@ -224,6 +232,7 @@ void add_u32_launch(uint32_t* p, int64_t n, uint32_t add, cudaStream_t st);
 void update_outcome_launch(const GroupData& g, int K, int ldx, const double* d_y_frame, cudaStream_t st);
 // Xs[i][:] = sqrt(w[i]) * X[i][:] for all V = K+1 columns (WLS as OLS on sqrt(w)-scaled data, ols.rs:68-78)
 void scale_rows_launch(const GroupData& g, int ldx, cudaStream_t st);
+void scale_rows_range_launch(const GroupData& g, int ldx, int64_t row0, int64_t rows, cudaStream_t st);
 // residuals of the point estimate: r = y - X beta (ols.rs:118-119) for one group; the outcome sits in column ycol
 void residuals_launch(const GroupData& g, int K, int ycol, int ldx, const double* d_beta, double* d_out, cudaStream_t st);
 // dst [rows][ld_dst] = design columns 0..K-1 of src [rows][ld_src], zeros from column K on

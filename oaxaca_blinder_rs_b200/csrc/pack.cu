@@ -78,6 +78,12 @@ struct PackKernelParams {
     double* XsA; double* XsB;      // sqrt(w)-scaled copies (weighted designs) or nullptr
     uint32_t* srcA; uint32_t* srcB;
     int* flags;
+    // row-shard window (ob_design_pack_row_shard_async; identity for an ordinary pack): a row of group g with rank q inside
+    // the packed frame slice belongs at shard row q + shift[g]; rows falling outside [0, n_local[g]) are another rank's and
+    // go to the export buffers instead (low side first, then high side), to be exchanged over the communicator
+    long long shift[2], n_local[2], lo_add[2], hi_base[2];
+    double* EX[2]; double* Ew[2]; uint32_t* Esrc[2];
+    uint32_t src_add;              // frame row of the slice's first row
 };
 
 __global__ void __launch_bounds__(PK_THREADS) pack_scatter_kernel(const PackKernelParams p) {
@@ -170,15 +176,22 @@ __global__ void __launch_bounds__(PK_THREADS) pack_scatter_kernel(const PackKern
             const double wv = p.w ? p.w[row0 + t] : 1.0;
             if (wv < 0.0 && lane == 0) atomicOr(&p.flags[0], 1);   // ols.rs:60-66 (the chunked pack has no earlier look at w)
             const double sw = sqrt(wv);
-            double* xr = X + (base + r) * p.ldx;
+            long long pos = base + r + p.shift[g];
+            const bool mine = pos >= 0 && pos < p.n_local[g];
+            double* xdst = X; double* xsdst = Xs; double* wdst = W; uint32_t* sdst = SRC;
+            if (!mine) {      // another rank's row: export buffer, no scaled copy (the receiver scales what it imports)
+                pos = pos < 0 ? pos + p.lo_add[g] : p.hi_base[g] + (pos - p.n_local[g]);
+                xdst = p.EX[g]; xsdst = nullptr; wdst = p.Ew[g]; sdst = p.Esrc[g];
+            }
+            double* xr = xdst + pos * p.ldx;
             for (int c = lane; c < p.ldx; c += 32) {          // pad columns [V, ldx) are written as zeros here
                 const double v = c < V ? tile[t * ts + c] : 0.0;
                 xr[c] = v;
-                if (Xs) Xs[(base + r) * p.ldx + c] = sw * v;
+                if (xsdst) xsdst[pos * p.ldx + c] = sw * v;
             }
             if (lane == 0) {
-                if (p.w) W[base + r] = wv;
-                SRC[base + r] = (uint32_t)(row0 + t);      // frame row of the packed row (ob_design_update_outcome)
+                if (p.w) wdst[pos] = wv;
+                sdst[pos] = p.src_add + (uint32_t)(row0 + t);      // frame row of the packed row (ob_design_update_outcome)
             }
         }
     }
@@ -196,7 +209,7 @@ void pack_count_scan(const PackArgs& a, long long* d_block_counts, long long* d_
 }
 
 void pack_scatter(const PackArgs& a, const long long* d_block_base, GroupData ga, GroupData gb, int* d_flags,
-                  cudaStream_t st, int blk0, int blk1) {
+                  cudaStream_t st, int blk0, int blk1, const PackWindow* win) {
     const int nb = (blk1 < 0 ? pack_num_blocks(a.n) : blk1) - blk0;
     if (nb <= 0) return;
     PackKernelParams p;
@@ -205,6 +218,14 @@ void pack_scatter(const PackArgs& a, const long long* d_block_base, GroupData ga
     p.y = a.d_y; p.w = a.d_w; p.group = a.d_group; p.block_base = d_block_base;
     p.XA = ga.X; p.XB = gb.X; p.wA = ga.w; p.wB = gb.w; p.XsA = ga.Xs; p.XsB = gb.Xs;
     p.srcA = ga.src; p.srcB = gb.src; p.flags = d_flags; p.blk0 = blk0;
+    for (int g = 0; g < 2; ++g) {
+        p.shift[g] = win ? win->shift[g] : 0;
+        p.n_local[g] = win ? win->n_local[g] : 0x7fffffffffffffffLL;
+        p.lo_add[g] = win ? win->lo_add[g] : 0;
+        p.hi_base[g] = win ? win->hi_base[g] : 0;
+        p.EX[g] = win ? win->EX[g] : nullptr; p.Ew[g] = win ? win->Ew[g] : nullptr; p.Esrc[g] = win ? win->Esrc[g] : nullptr;
+    }
+    p.src_add = win ? win->src_add : 0u;
     const int V = a.K + 1;
     const size_t smem = sizeof(double) * (size_t)PK_ROWS * (V | 1);
     OB_CUDA(cudaFuncSetAttribute(pack_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -225,6 +246,14 @@ void scale_rows_launch(const GroupData& g, int ldx, cudaStream_t st) {
     if (!g.Xs) return;
     const long long total = g.n_pad * (long long)ldx;
     scale_rows_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 32), 256, 0, st>>>(g.X, g.w, g.Xs, total, ldx);
+    OB_CUDA(cudaGetLastError());
+}
+
+void scale_rows_range_launch(const GroupData& g, int ldx, int64_t row0, int64_t rows, cudaStream_t st) {
+    if (!g.Xs || rows <= 0) return;
+    const long long total = rows * (long long)ldx;
+    scale_rows_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 32), 256, 0, st>>>(g.X + row0 * ldx, g.w + row0, g.Xs + row0 * ldx,
+                                                                                                  total, ldx);
     OB_CUDA(cudaGetLastError());
 }
 

@@ -137,3 +137,12 @@ def pack_row_shard_from_slice(ctx, d: dict, rank: int, world: int):
     shard = loc.redistribute_rows()
     loc.close()
     return shard
+
+
+def pack_row_shard_async(ctx, d: dict, rank: int, world: int):
+    """ob_design_pack_row_shard_async on this rank's frame slice: like pack_row_shard_from_slice, but rows go straight to
+    their place in the shard while the slice uploads, and the next bootstrap() overlaps upload, pack and the exchange
+    of the few rows other ranks own with its first kernels.  Collective."""
+    from . import core
+    sl = frame_slice(d, rank, world)
+    return core.Design.pack(ctx, sl["cont"], sl["cat_codes"], sl["cat_levels"], sl["outcome"], sl["weights"], sl["group"], row_shard=True)

@@ -314,3 +314,58 @@ def test_redistributed_slices_equal_row_shards(world, sort_by_group):
         assert same
         for k in ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper", "p_value"):
             assert _same(o[k], one[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,n,sort_by_group", [(2, 50_003, False), (4, 700_001, False), (4, 50_003, True), (8, 1_300_000, False),
+                                                  (2, 600_000, True)])
+def test_async_row_shard_pack_equals_row_shards(world, n, sort_by_group):
+    """ob_design_pack_row_shard_async: rows written straight into the shard while the slice uploads, one exchange of the
+    rows other ranks own, split Gram launches.  Shard (download) and sharded bootstrap equal the direct row shard / one
+    GPU bit for bit -- small slices (one chunk), large ones (two chunks: the first Gram launch runs before the exchange)
+    and a frame sorted by group (whole slices change hands; a rank may keep nothing of its own slice)."""
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import core, synth, distributed as obd
+    d = synth.make_wage(n, 3, cat_levels=(3,), weights=True, seed=19)
+    if sort_by_group:
+        order = np.argsort(d["group"], kind="stable")
+        for k in ("outcome", "weights", "group"):
+            d[k] = d[k][order]
+        d["cont"] = [c[order] for c in d["cont"]]
+        d["cat_codes"] = [c[order] for c in d["cat_codes"]]
+    norm = [ob.NormVar(m, i) for m, i in synth.norm_spec(d)]
+    reps = 140
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+    one = ob.bootstrap(des, reps, ref_kind=ob.REF_WEIGHTED, norm=norm, seed=43, want_rep=True)
+    des.close(); ctx.close()
+    grp = core.LocalGroup(world)
+    outs, errs = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            c = ob.Context(0)
+            c.init_local(grp, r)
+            sh = obd.pack_row_shard_async(c, d, r, world)          # straight into the bootstrap
+            o = ob.bootstrap(sh, reps, ref_kind=ob.REF_WEIGHTED, norm=norm, seed=43, want_rep=True)
+            direct = obd.pack_row_shard(c, d, r, world)
+            same = all(np.array_equal(a, b_, equal_nan=True) for a, b_ in zip(sh.download(), direct.download()))
+            sh.update_outcome(d["outcome"])                        # the frame-row map is global
+            same = same and all(np.array_equal(a, b_, equal_nan=True) for a, b_ in zip(sh.download(), direct.download()))
+            sh.close()
+            sh2 = obd.pack_row_shard_async(c, d, r, world)         # completed by download() instead (exchange inside)
+            same = same and all(np.array_equal(a, b_, equal_nan=True) for a, b_ in zip(sh2.download(), direct.download()))
+            sh2.close(); direct.close(); c.close()
+            outs[r] = (same, o)
+        except Exception as ex:  # noqa: BLE001
+            errs[r] = ex
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=600)
+    assert all(e is None for e in errs), errs
+    for same, o in outs:
+        assert same
+        for k in ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper", "p_value"):
+            assert _same(o[k], one[k]), k

@@ -30,6 +30,14 @@ def _worker(rank, world, port, q):
     for a, b_ in zip(re.download(), des.download()):
         assert np.array_equal(a, b_, equal_nan=True)
     re.close()
+    # the asynchronous variant (rows straight into the shard, one exchange, overlapped with the bootstrap) over NCCL
+    asy = obd.pack_row_shard_async(ctx, full, rank, world)
+    out_async = ob.bootstrap(asy, reps, ref_kind=ob.REF_WEIGHTED, norm=norm, seed=5, want_rep=True, max_workspace_bytes=80_000_000)
+    for a, b_ in zip(asy.download(), des.download()):
+        assert np.array_equal(a, b_, equal_nan=True)
+    for k in ("point_stats", "rep_stats", "std_err"):
+        assert np.array_equal(np.nan_to_num(out_async[k], nan=-7.0), np.nan_to_num(out[k], nan=-7.0)), k
+    asy.close()
     des.close()
     # mode R upload over the same communicator: frame slices packed per rank, full design gathered over NVLink
     rep = obd.pack_replicated(ctx, full, rank, world)
