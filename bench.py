@@ -42,8 +42,8 @@ WORKLOADS = {
 # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE Gram launch, measured by ncu on THIS build of
 # the kernel: profiles/gram_traffic.json holds {workload, n_gpus, bytes, src_sha256, csv}; an entry counts only while the
 # hash of the kernel sources it was taken on equals the current sources -- otherwise the key is null, never stale.
-GRAM_SOURCES = ("oaxaca_blinder_rs_b200/csrc/gram.cu", "oaxaca_blinder_rs_b200/csrc/internal.h",
-                "oaxaca_blinder_rs_b200/csrc/common.cuh")
+GRAM_SOURCES = ("oaxaca_blinder_rs_b200/csrc/gram.cu", "oaxaca_blinder_rs_b200/csrc/common.cuh")
+GRAM_GEOMETRY = "oaxaca_blinder_rs_b200/csrc/internal.h"      # only its constexpr lines (tile sizes, leaf count) shape the kernel
 
 
 def gram_source_hash():
@@ -52,6 +52,8 @@ def gram_source_hash():
     for f in GRAM_SOURCES:
         with open(os.path.join(ROOT, f), "rb") as fh:
             h.update(fh.read())
+    with open(os.path.join(ROOT, GRAM_GEOMETRY)) as fh:
+        h.update("".join(ln for ln in fh if ln.lstrip().startswith("constexpr")).encode())
     return h.hexdigest()
 
 

@@ -1362,20 +1362,43 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 ppb = v;
             }
             tr.mark("setup", st, true);
-            DevBuf d_C[2], d_idx[2], d_colsum(sizeof(long long) * 2 * (size_t)ppb * BM);
-            for (int g = 0; g < 2; ++g) d_C[g].alloc((size_t)ppb * n_pad[g] * BM * count_bytes);
+            DevBuf d_C[2], d_idx[2], d_colsum, d_gram, d_gram_local, d_gathered;
             const size_t gram_elems = 2 * (size_t)ppb * BM * Pld;      // [2][slots_pad][Pld]
-            DevBuf d_gram(sizeof(double) * gram_elems);
-            DevBuf d_gram_local(comm ? sizeof(double) * gram_elems : 0), d_gathered(comm ? sizeof(double) * gram_elems * world : 0);
             bool saturated = false;
-
             GramPlan plan; int64_t plan_panels = -1;
             DevBuf d_partials, d_pairs;
-            {
+            auto allocate_workspace = [&] {
+                d_colsum.alloc(sizeof(long long) * 2 * (size_t)ppb * BM);
+                for (int g = 0; g < 2; ++g) d_C[g].alloc((size_t)ppb * n_pad[g] * BM * count_bytes);
+                d_gram.alloc(sizeof(double) * gram_elems);
+                if (comm) { d_gram_local.alloc(sizeof(double) * gram_elems); d_gathered.alloc(sizeof(double) * gram_elems * world); }
+                plan = gram_make_plan(K, T, d->ldx, (int)std::min<int64_t>(ppb, panels_total), d->g, count_bytes, ctx->num_sms);
+                plan_panels = plan.panels;
+                d_partials.alloc(sizeof(double) * (size_t)std::max<int64_t>(plan.num_partials, 1) * BM * BN);
                 const std::vector<uint16_t> pairs = gram_pair_table(K, T, ntiles);
                 d_pairs.alloc(sizeof(uint16_t) * pairs.size());
                 OB_CUDA(cudaMemcpyAsync(d_pairs.p, pairs.data(), sizeof(uint16_t) * pairs.size(), cudaMemcpyHostToDevice, st));
                 OB_CUDA(cudaStreamSynchronize(st));
+            };
+            if (!comm) allocate_workspace();
+            else {
+                // row shards: a rank whose workspace cannot be had (its GPU is shared, say) must not leave its peers waiting
+                // in the first collective of the batch loop -- all ranks agree on the outcome of the allocation phase
+                int rc = OB_OK; std::string msg;
+                try { allocate_workspace(); }
+                catch (const StatusError& e) { rc = e.code; msg = e.msg; }
+                catch (const CudaError& e) {
+                    cudaGetLastError();
+                    if (e.code != cudaErrorMemoryAllocation) throw;
+                    rc = OB_ERR_CUDA; msg = "workspace allocation failed on this rank (out of device memory)";
+                }
+                int agreed = rc;
+                OB_CUDA(cudaMemcpyAsync(d_agree.p, &agreed, sizeof(int), cudaMemcpyHostToDevice, st));
+                comm->allreduce(d_agree.p, 1, CommDType::I32, CommOp::MAX, st);
+                OB_CUDA(cudaMemcpyAsync(&agreed, d_agree.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                OB_CUDA(cudaStreamSynchronize(st));
+                if (rc != OB_OK) fail((ob_status)rc, msg);
+                if (agreed != OB_OK) fail((ob_status)agreed, "another rank of the row-sharded run could not allocate its workspace");
             }
 
             tr.mark("workspace + pair table", st, true);
