@@ -375,11 +375,21 @@ def measure_also(name, ob, obd, ctx, torch, dist, rank, world, local, shard_rows
         sweep = {"taus": list(taus), "three_runs_s": t3, "one_pass_s": t1s, "speedup": t3 / t1s,
                  "fits_per_s_one_pass": 3 * reps / t1s, "fits_per_s_three_runs": 3 * reps / t3}
     des.close()
+
+    def e2e_step():
+        if world > 1 and not shard_rows and world & (world - 1) == 0:
+            dsg = obd.pack_row_shard_async(ctx, d, rank, world)        # host frame -> row shards, overlapped (mode N)
+            if rif_tau is not None:
+                dsg.apply_rif(rif_tau)
+            ob.bootstrap(dsg, reps, ref_kind=ref, norm=norm, seed=2026, want_residuals=False)
+        else:
+            dsg = pack()
+            step(dsg)
+        dsg.close()
+    e2e_step()                                   # warm-up of the pools this path uses
     sync()
     t1 = time.perf_counter()
-    des = pack()
-    step(des)
-    des.close()
+    e2e_step()
     sync()
     dt_e = time.perf_counter() - t1
     times = torch.tensor([dt, dt_e], dtype=torch.float64, device="cuda")
@@ -410,7 +420,7 @@ def main():
     ap.add_argument("--e2e-upload", default="auto", choices=["auto", "gather", "rowshard"],
                     help="N > 1, replicate-sharded workloads, end-to-end leg: every rank uploads 1/N of the frame, then either "
                          "the packed rows are all-gathered so that every GPU holds the design (gather: mode R) or re-cut into "
-                         "row shards (rowshard: mode N, a rank never needs the other rows); auto = rowshard unless RIF")
+                         "row shards (rowshard: mode N, a rank never needs the other rows); auto = rowshard")
     ap.add_argument("--also", default="auto", choices=["auto", "on", "off"],
                     help="N > 1: also measure the row-sharded config 5 and the RIF config 4 at the same N (key `also`)")
     args = ap.parse_args()
@@ -469,7 +479,7 @@ def main():
     rif_tau = default_rif_tau(args, name)
 
     e2e_rowshard = (world > 1 and not shard_rows and world & (world - 1) == 0 and
-                    (args.e2e_upload == "rowshard" or (args.e2e_upload == "auto" and rif_tau is None)))
+                    args.e2e_upload in ("rowshard", "auto"))
 
     def pack(asynchronous=False, e2e=False):
         if world > 1 and not shard_rows:
@@ -481,7 +491,10 @@ def main():
                 # to their place in the rank's row shard, the few rows other ranks own are exchanged over NVLink, and the
                 # row-sharded bootstrap (mode N: bit-identical to one GPU, like mode R) overlaps all of it with its
                 # replicate generation and a first Gram launch.  No GPU ever needs the other ranks' rows.
-                return obd.pack_row_shard_async(ctx, fr, rank, world)
+                des = obd.pack_row_shard_async(ctx, fr, rank, world)
+                if rif_tau is not None:          # RIF on the row shard: histograms / leaf sums all-reduced over NVLink
+                    des.apply_rif(rif_tau)
+                return des
             # mode R: this rank uploads 1/world of the frame; the packed rows are all-gathered over NVLink
             des = obd.pack_replicated(ctx, fr, rank, world)
             if rif_tau is not None:

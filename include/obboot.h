@@ -168,7 +168,9 @@ ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau);
  * [n_tau x K]; rep_stats [rows x n_tau x S]; rep_beta_* [rows x n_tau x K]; residuals_b [n_tau x n_b];
  * total_gap_multi [n_tau].  All quantiles see the same resamples (the reference draws fresh ones per call; with a
  * fixed seed ours are the same per call anyway), so each quantile's results equal a single-quantile run bit for bit.
- * ob_design_apply_rif(tau) is the n_tau = 1 case; ob_design_update_outcome returns to one raw outcome. */
+ * ob_design_apply_rif(tau) is the n_tau = 1 case; ob_design_update_outcome returns to one raw outcome.
+ * On a row shard (mode N) both are collectives: the radix-select histograms and the leaf partial sums of mean, SD and
+ * density are all-reduced over the context's communicator, and the RIF values are bit-identical to the unsharded ones. */
 ob_status ob_design_apply_rif_multi(ob_ctx* ctx, ob_design* d, const double* taus, int32_t n_tau);
 ob_status ob_design_num_outcomes(const ob_design* d, int32_t* n_out);
 

@@ -1204,7 +1204,11 @@ ob_status ob_design_apply_rif_multi(ob_ctx* ctx, ob_design* d, const double* tau
     return guarded(ctx, [&] {
         design_ready(d);
         if (n_tau < 1 || n_tau > 8) fail(OB_ERR_INVALID_ARG, "1 to 8 quantiles per pass");
-        if (d->world > 1) fail(OB_ERR_UNSUPPORTED, "RIF pre-step on a row-sharded design (the quantile needs all rows of a group)");
+        // a row shard: the order statistics, the bandwidth and the density need all rows of a group -- the library's
+        // communicator all-reduces the radix histograms and the leaf partial sums (a collective: every rank calls)
+        Comm* comm = d->world > 1 ? ctx->comm.get() : nullptr;
+        if (d->world > 1 && (!comm || comm->world != d->world || comm->rank != d->rank))
+            fail(OB_ERR_NCCL, "row-sharded design needs ob_comm_init_* on this context with the same world/rank");
         if (d->K + n_tau > MAX_DESIGN_COLS) fail(OB_ERR_UNSUPPORTED, "design plus outcome columns wider than 280");
         cudaStream_t st = ctx->stream;
         const int K = d->K;
@@ -1232,7 +1236,7 @@ ob_status ob_design_apply_rif_multi(ob_ctx* ctx, ob_design* d, const double* tau
         for (int g = 0; g < 2; ++g) {
             const size_t sb = rif_scratch_bytes(d->g[g].n);
             DevBuf scratch(sb);
-            for (int t = 0; t < n_tau; ++t) rif_transform(d->g[g], K + t, d->ldx, taus[t], scratch.p, sb, st);
+            for (int t = 0; t < n_tau; ++t) rif_transform(d->g[g], K + t, d->ldx, taus[t], scratch.p, sb, st, comm);
             scale_rows_launch(d->g[g], d->ldx, st);   // the RIF outcomes are weighted like any outcome
             OB_CUDA(cudaStreamSynchronize(st));
         }

@@ -294,8 +294,10 @@ Comm* comm_create_nccl(const uint8_t* id128, int rank, int world);
 // ---- rif.cu ----
 // RIF transform (math/rif.rs:14-88) of a packed group's raw outcome (g.y_raw if saved, else column ycol itself),
 // written to column ycol
+// comm: the row-sharding communicator when g is one rank's shard of the group (leaf partials and radix histograms are
+// all-reduced; results bit-identical to the unsharded transform), else null
 void rif_transform(const GroupData& g, int ycol, int ldx, double tau, void* d_scratch, size_t scratch_bytes,
-                   cudaStream_t st);
+                   cudaStream_t st, Comm* comm = nullptr);
 size_t rif_scratch_bytes(int64_t n);
 
 }  // namespace ob

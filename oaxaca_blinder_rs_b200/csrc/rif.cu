@@ -5,24 +5,33 @@
 //   q_tau   type-7 sample quantile (rif.rs:23-35)           -> 64-bit MSB radix SELECT of the four order
 //   IQR     sorted[ceil(.75n)-1] - sorted[ceil(.25n)-1]        statistics needed (no full sort), 8 passes of
 //                                                              8 bits over an orderable-key copy of y
-//   sd      two-pass sample SD (rif.rs:39-41)                -> fixed-order block partials
+//   sd      two-pass sample SD (rif.rs:39-41)                -> fixed-order partials, two per leaf segment of the group's
+//                                                              GLOBAL row segmentation (internal.h): the sums are the same
+//                                                              whether one GPU holds the group or its rows are sharded
 //   h       0.9 min(sd, IQR/1.34) n^-0.2 with fallbacks (rif.rs:51-59)
 //   f(q)    Gaussian KDE at one point (rif.rs:65-72), floor 1e-8 (:75)
 //   RIF_i   q + (tau - 1[y_i <= q]) / f (rif.rs:79-85), written back in place
 // HBM-bound: ~12 passes over n doubles.  No host synchronisation: scalars stay in a device state block.
+//
+// Row-sharded designs (mode N): every rank runs the same kernels over its rows; the leaf partials (disjoint support
+// across ranks, so the all-reduce adds zeros: exact) and the radix histograms (integers) are all-reduced over the
+// communicator, 11 small collectives per transform.  Quantile, bandwidth, density and hence every RIF value are
+// bit-identical to the unsharded transform.
 #include "common.cuh"
 #include "internal.h"
 
 namespace ob {
 
-constexpr int RIF_BLOCKS = 592;   // 4 x 148 SMs
+constexpr int RIF_BLOCKS = 592;   // 4 x 148 SMs (histogram / apply passes)
 constexpr int RIF_THREADS = 256;
+constexpr int RIF_SUB = 2;                        // reduction blocks per leaf
+constexpr int RIF_PARTS = MAX_SEGS * RIF_SUB;     // fixed-order partial sums of a group
 
 struct RifState {
     unsigned long long prefix[4];
     long long rank[4];
     unsigned int hist[4][256];
-    double partial[RIF_BLOCKS];
+    double partial[RIF_PARTS];
     double mean, sd, q, dens, bw;
     int active;   // 0 when n < 2: series returned unchanged (rif.rs:18-20)
 };
@@ -47,17 +56,31 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* red) {
     return t;  // valid on thread 0
 }
 
-// contiguous row range of each block: fixed partition -> deterministic partial sums
+// contiguous row range of each block (histogram pass: integer counts, any partition will do)
 __device__ __forceinline__ void block_range(long long n, long long& lo, long long& hi) {
     const long long per = (n + gridDim.x - 1) / gridDim.x;
     lo = (long long)blockIdx.x * per; hi = min(lo + per, n);
 }
 
+// where a group's rows sit: the global segmentation and the part held here
+struct RifRows { long long n_global, row_begin, n_local; int seg_rows; };
+
+// Reduction blocks: block b sums half (b % RIF_SUB) of leaf b / RIF_SUB of the group's GLOBAL segmentation -- the local
+// rows [lo, hi) of it, empty when the leaf lives on another rank.  The partition depends on the group size only.
+__device__ __forceinline__ void leaf_range(const RifRows& r, long long& lo, long long& hi) {
+    const long long leaf = blockIdx.x / RIF_SUB, sub = blockIdx.x % RIF_SUB;
+    const long long g0 = leaf * r.seg_rows, g1 = min(g0 + r.seg_rows, r.n_global);
+    if (g0 >= g1) { lo = hi = 0; return; }
+    const long long half = ((g1 - g0) / RIF_SUB + 31) / 32 * 32;
+    const long long a = sub == 0 ? g0 : min(g0 + half, g1), b = sub == 0 ? min(g0 + half, g1) : g1;
+    lo = min(max(a - r.row_begin, 0ll), r.n_local); hi = min(max(b - r.row_begin, 0ll), r.n_local);
+}
+
 // y_src / ystride: where the RAW outcome lives (the outcome column of X on the first transform, the saved copy after)
-__global__ void __launch_bounds__(RIF_THREADS) rif_extract_kernel(const double* __restrict__ y_src, long long ystride, long long n,
+__global__ void __launch_bounds__(RIF_THREADS) rif_extract_kernel(const double* __restrict__ y_src, long long ystride, RifRows rows,
                                                                   unsigned long long* __restrict__ keys, RifState* s) {
     __shared__ double red[RIF_THREADS / 32];
-    long long lo, hi; block_range(n, lo, hi);
+    long long lo, hi; leaf_range(rows, lo, hi);
     double sum = 0.0;
     for (long long i = lo + threadIdx.x; i < hi; i += RIF_THREADS) {
         const double y = y_src[i * ystride];
@@ -71,7 +94,7 @@ __global__ void __launch_bounds__(RIF_THREADS) rif_extract_kernel(const double* 
 __global__ void rif_init_kernel(RifState* s, long long n, double tau) {
     // runs after extract: mean from the ordered partials; select targets (rif.rs:25-28, :43-47)
     double sum = 0.0;
-    for (int i = 0; i < RIF_BLOCKS; ++i) sum += s->partial[i];
+    for (int i = 0; i < RIF_PARTS; ++i) sum += s->partial[i];
     const double nf = (double)n;
     s->mean = sum / nf;
     const double h = (nf - 1.0) * tau;
@@ -83,9 +106,9 @@ __global__ void rif_init_kernel(RifState* s, long long n, double tau) {
     for (int t = 0; t < 4; ++t) for (int b = 0; b < 256; ++b) s->hist[t][b] = 0;
 }
 
-__global__ void __launch_bounds__(RIF_THREADS) rif_ss_kernel(const unsigned long long* __restrict__ keys, long long n, RifState* s) {
+__global__ void __launch_bounds__(RIF_THREADS) rif_ss_kernel(const unsigned long long* __restrict__ keys, RifRows rows, RifState* s) {
     __shared__ double red[RIF_THREADS / 32];
-    long long lo, hi; block_range(n, lo, hi);
+    long long lo, hi; leaf_range(rows, lo, hi);
     const double mean = s->mean;
     double ss = 0.0;
     for (long long i = lo + threadIdx.x; i < hi; i += RIF_THREADS) { const double d = from_key(keys[i]) - mean; ss += d * d; }
@@ -95,7 +118,7 @@ __global__ void __launch_bounds__(RIF_THREADS) rif_ss_kernel(const unsigned long
 
 __global__ void rif_sd_kernel(RifState* s, long long n) {
     double ss = 0.0;
-    for (int i = 0; i < RIF_BLOCKS; ++i) ss += s->partial[i];
+    for (int i = 0; i < RIF_PARTS; ++i) ss += s->partial[i];
     s->sd = sqrt(ss / ((double)n - 1.0));
 }
 
@@ -156,9 +179,9 @@ __global__ void rif_params_kernel(RifState* s, long long n, double tau) {
     s->bw = 0.9 * spread * pow(nf, -0.2);                                 // rif.rs:59
 }
 
-__global__ void __launch_bounds__(RIF_THREADS) rif_density_kernel(const unsigned long long* __restrict__ keys, long long n, RifState* s) {
+__global__ void __launch_bounds__(RIF_THREADS) rif_density_kernel(const unsigned long long* __restrict__ keys, RifRows rows, RifState* s) {
     __shared__ double red[RIF_THREADS / 32];
-    long long lo, hi; block_range(n, lo, hi);
+    long long lo, hi; leaf_range(rows, lo, hi);
     const double q = s->q, bw = s->bw;
     const double c = 1.0 / sqrt(2.0 * 3.14159265358979323846);
     double acc = 0.0;
@@ -172,7 +195,7 @@ __global__ void __launch_bounds__(RIF_THREADS) rif_density_kernel(const unsigned
 
 __global__ void rif_dens_final_kernel(RifState* s, long long n) {
     double d = 0.0;
-    for (int i = 0; i < RIF_BLOCKS; ++i) d += s->partial[i];
+    for (int i = 0; i < RIF_PARTS; ++i) d += s->partial[i];
     d /= ((double)n * s->bw);
     s->dens = d < 1e-8 ? 1e-8 : d;                                        // rif.rs:75
 }
@@ -189,26 +212,33 @@ __global__ void __launch_bounds__(RIF_THREADS) rif_apply_kernel(double* __restri
 
 size_t rif_scratch_bytes(int64_t n) { return sizeof(unsigned long long) * (size_t)std::max<int64_t>(n, 1) + sizeof(RifState) + 256; }
 
-void rif_transform(const GroupData& g, int ycol, int ldx, double tau, void* d_scratch, size_t scratch_bytes, cudaStream_t st) {
-    const long long n = g.n;
-    if ((double)n < 2.0) return;  // rif.rs:18-20
+void rif_transform(const GroupData& g, int ycol, int ldx, double tau, void* d_scratch, size_t scratch_bytes, cudaStream_t st, Comm* comm) {
+    const long long n = g.n, n_glob = g.shard.n_global;
+    if ((double)n_glob < 2.0) return;  // rif.rs:18-20
     if (scratch_bytes < rif_scratch_bytes(n)) throw StatusError{OB_ERR_INVALID_ARG, "rif scratch too small"};
     unsigned long long* keys = static_cast<unsigned long long*>(d_scratch);
-    RifState* s = reinterpret_cast<RifState*>(reinterpret_cast<char*>(d_scratch) + ((sizeof(unsigned long long) * (size_t)n + 255) / 256) * 256);
+    RifState* s = reinterpret_cast<RifState*>(reinterpret_cast<char*>(d_scratch) + ((sizeof(unsigned long long) * (size_t)std::max<long long>(n, 1) + 255) / 256) * 256);
     const double* y_src = g.y_raw ? g.y_raw : g.X + ycol;
     const long long ystride = g.y_raw ? 1 : ldx;
-    rif_extract_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(y_src, ystride, n, keys, s);
-    rif_init_kernel<<<1, 1, 0, st>>>(s, n, tau);
-    rif_ss_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(keys, n, s);
-    rif_sd_kernel<<<1, 1, 0, st>>>(s, n);
+    const RifRows rows{n_glob, g.shard.row_begin, n, g.shard.seg_rows};
+    // leaf partials: every rank writes all RIF_PARTS entries (zeros for leaves it does not hold), so the all-reduce is exact
+    auto share_partials = [&] { if (comm) comm->allreduce(s->partial, RIF_PARTS, CommDType::F64, CommOp::SUM, st); };
+    rif_extract_kernel<<<RIF_PARTS, RIF_THREADS, 0, st>>>(y_src, ystride, rows, keys, s);
+    share_partials();
+    rif_init_kernel<<<1, 1, 0, st>>>(s, n_glob, tau);
+    rif_ss_kernel<<<RIF_PARTS, RIF_THREADS, 0, st>>>(keys, rows, s);
+    share_partials();
+    rif_sd_kernel<<<1, 1, 0, st>>>(s, n_glob);
     for (int pass = 0; pass < 8; ++pass) {
         rif_hist_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(keys, n, s, pass);
+        if (comm) comm->allreduce(&s->hist[0][0], 4 * 256, CommDType::I32, CommOp::SUM, st);
         rif_pick_kernel<<<1, 256, 0, st>>>(s, pass);
     }
-    rif_params_kernel<<<1, 1, 0, st>>>(s, n, tau);
-    rif_density_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(keys, n, s);
-    rif_dens_final_kernel<<<1, 1, 0, st>>>(s, n);
-    rif_apply_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(g.X, n, ycol, ldx, y_src, ystride, s, tau);
+    rif_params_kernel<<<1, 1, 0, st>>>(s, n_glob, tau);
+    rif_density_kernel<<<RIF_PARTS, RIF_THREADS, 0, st>>>(keys, rows, s);
+    share_partials();
+    rif_dens_final_kernel<<<1, 1, 0, st>>>(s, n_glob);
+    if (n > 0) rif_apply_kernel<<<RIF_BLOCKS, RIF_THREADS, 0, st>>>(g.X, n, ycol, ldx, y_src, ystride, s, tau);
     OB_CUDA(cudaGetLastError());
 }
 

@@ -369,3 +369,51 @@ def test_async_row_shard_pack_equals_row_shards(world, n, sort_by_group):
         assert same
         for k in ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper", "p_value"):
             assert _same(o[k], one[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_rif_on_row_shards_is_bit_identical(world, orc):
+    """decompose_quantile's RIF pre-step on a row-sharded design: radix-select histograms and leaf partial sums are
+    all-reduced over the communicator; the RIF outcome of every shard, and the sharded bootstrap of a one-pass quantile
+    sweep, equal the unsharded ones bit for bit (and the oracle's RIF within 1e-10)."""
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import core, synth, distributed as obd
+    from helpers import relerr
+    d = synth.make_wage(70_001, 3, cat_levels=(3,), weights=True, seed=23)
+    taus = (0.1, 0.5, 0.9)
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+    _, ya_raw, _, _, yb_raw, _ = des.download()
+    des.apply_rif(0.9)
+    _, ya9, _, _, yb9, _ = des.download()
+    assert relerr(ya9, orc.rif(ya_raw, 0.9)) <= 1e-10 and relerr(yb9, orc.rif(yb_raw, 0.9)) <= 1e-10
+    des.apply_rif_multi(taus)
+    one = ob.bootstrap(des, 120, ref_kind=ob.REF_GROUP_B, seed=8, want_rep=True)
+    des.close(); ctx.close()
+    grp = core.LocalGroup(world)
+    outs, errs = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            c = ob.Context(0)
+            c.init_local(grp, r)
+            sh = obd.pack_row_shard_async(c, d, r, world)
+            sh.apply_rif(0.9)
+            y9 = sh.download()
+            sh.apply_rif_multi(taus)
+            o = ob.bootstrap(sh, 120, ref_kind=ob.REF_GROUP_B, seed=8, want_rep=True)
+            sh.close(); c.close()
+            outs[r] = (y9[1], y9[4], o)
+        except Exception as ex:  # noqa: BLE001
+            errs[r] = ex
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert all(e is None for e in errs), errs
+    assert np.array_equal(np.concatenate([o[0] for o in outs]), ya9) and np.array_equal(np.concatenate([o[1] for o in outs]), yb9)
+    for _, _, o in outs:
+        for k in ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper", "p_value"):
+            assert _same(o[k], one[k]), k
