@@ -318,6 +318,8 @@ def measure_also(name, ob, obd, ctx, torch, dist, rank, world, local, shard_rows
         d = synth.make_wage(n, n_cont, cat_levels=cats, weights=wts)
     norm = [ob.NormVar(m, i) for m, i in (synth.norm_spec(d) if normalize else [])]
     K = 1 + n_cont + sum(m - 1 for m in cats)
+    # the frame's columns page-locked in place (ob_host_register), as a caller holding its own buffers would do
+    pinned_cols = ob.pin_in_place(list(d["cont"]) + list(d["cat_codes"]) + [d["outcome"], d["weights"], d["group"]])
 
     def sync():
         torch.cuda.synchronize()
@@ -325,9 +327,12 @@ def measure_also(name, ob, obd, ctx, torch, dist, rank, world, local, shard_rows
             dist.barrier()
             torch.cuda.synchronize()
 
-    def pack():
+    def pack(asynchronous=False):
         if shard_rows:
-            return obd.pack_row_shard(ctx, d, rank, world)
+            des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"],
+                                 asynchronous=asynchronous)
+            des.set_row_shard(d["n_a_global"], d["n_b_global"], world, rank)
+            return des
         if world > 1:
             des = obd.pack_replicated(ctx, d, rank, world)
         else:
@@ -383,7 +388,7 @@ def measure_also(name, ob, obd, ctx, torch, dist, rank, world, local, shard_rows
                 dsg.apply_rif(rif_tau)
             ob.bootstrap(dsg, reps, ref_kind=ref, norm=norm, seed=2026, want_residuals=False)
         else:
-            dsg = pack()
+            dsg = pack(asynchronous=rif_tau is None)
             step(dsg)
         dsg.close()
     e2e_step()                                   # warm-up of the pools this path uses
@@ -396,6 +401,7 @@ def measure_also(name, ob, obd, ctx, torch, dist, rank, world, local, shard_rows
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dt, dt_e = times.tolist()
+    ob.unpin(pinned_cols)
     flops, P = algorithmic_flops(n, K, reps)
     g_ms = float(np.mean(gram_ms))
     ach = flops / world / (g_ms * 1e-3) / 1e12
@@ -504,7 +510,7 @@ def main():
         # run on the library's copy stream under the replicate generation and the first Gram launch of step()
         des = ob.Design.pack(ctx, [t.numpy() for t in pinned["cont"]], [t.numpy() for t in pinned["cat"]],
                              d["cat_levels"], pinned["y"].numpy(), None if pinned["w"] is None else pinned["w"].numpy(),
-                             pinned["g"].numpy(), asynchronous=asynchronous and not shard_rows and rif_tau is None)
+                             pinned["g"].numpy(), asynchronous=asynchronous and rif_tau is None)
         if shard_rows:
             des.set_row_shard(d["n_a_global"], d["n_b_global"], world, rank)
         if rif_tau is not None:          # decompose_quantile: RIF pre-step on the device (builder.rs:721-737)

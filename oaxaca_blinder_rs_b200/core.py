@@ -385,6 +385,23 @@ class PinnedBuffer:
             pass
 
 
+def pin_in_place(arrays):
+    """ob_host_register on existing numpy arrays (what a Rust caller does with the Vecs it already holds): returns the
+    list of registered arrays; pass it to unpin() when done.  Arrays that cannot be registered are left pageable."""
+    done = []
+    for a in arrays:
+        if a is None or a.nbytes == 0:
+            continue
+        if N.lib().ob_host_register(a.ctypes.data_as(C.c_void_p), a.nbytes) == 0:
+            done.append(a)
+    return done
+
+
+def unpin(arrays):
+    for a in arrays:
+        N.lib().ob_host_unregister(a.ctypes.data_as(C.c_void_p))
+
+
 def replicate_shard(reps: int, world: int, rank: int):
     """ob_replicate_shard: [begin, end) of the global replicate ids rank computes under shard_replicates."""
     b, e = C.c_int64(), C.c_int64()

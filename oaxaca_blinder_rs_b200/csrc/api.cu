@@ -484,8 +484,10 @@ ob_status ob_row_shard_plan(int64_t n_group, int32_t world, int32_t rank, int64_
 
 ob_status ob_design_set_row_shard(ob_design* d, int64_t n_a_global, int64_t n_b_global, int32_t world, int32_t rank) {
     if (!d || world < 1 || world > MAX_WORLD || (world & (world - 1)) || rank < 0 || rank >= world) return OB_ERR_INVALID_ARG;
-    if (d->pending) { cudaSetDevice(d->device); pending_finish(d, true); }
+    // (a design whose asynchronous pack is still in flight can be marked: only the metadata changes, and the upload's
+    //  progress is tracked in local rows either way)
     if (d->failed != OB_OK) return d->failed;
+    if (d->pending && d->pending->exchange_pending) return OB_ERR_INVALID_ARG;    // already a row shard
     const RowShard ra = row_shard(n_a_global, rank, world), rb = row_shard(n_b_global, rank, world);
     if (ra.n_local != d->g[0].n || rb.n_local != d->g[1].n) return OB_ERR_INVALID_ARG;   // rows must follow ob_row_shard_plan
     d->g[0].shard = ra; d->g[1].shard = rb;

@@ -417,3 +417,41 @@ def test_rif_on_row_shards_is_bit_identical(world, orc):
     for _, _, o in outs:
         for k in ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper", "p_value"):
             assert _same(o[k], one[k]), k
+
+
+@pytest.mark.gpu
+def test_async_pack_marked_as_row_shard_while_in_flight():
+    """Rows selected on the host (ob_row_shard_plan), uploaded with ob_design_pack_async and marked with
+    ob_design_set_row_shard while the upload is still in flight: the sharded bootstrap overlaps it and equals one GPU."""
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import core, synth, distributed as obd
+    d = synth.make_wage(900_000, 3, cat_levels=(3,), weights=False, seed=29)
+    world, reps = 2, 130
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+    one = ob.bootstrap(des, reps, seed=9, want_rep=True)
+    des.close(); ctx.close()
+    grp = core.LocalGroup(world)
+    outs, errs = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            c = ob.Context(0)
+            c.init_local(grp, r)
+            loc = obd.shard_frame(d, r, world)
+            sh = ob.Design.pack(c, loc["cont"], loc["cat_codes"], loc["cat_levels"], loc["outcome"], loc["weights"], loc["group"],
+                                asynchronous=True)
+            sh.set_row_shard(loc["n_a_global"], loc["n_b_global"], world, r)
+            outs[r] = ob.bootstrap(sh, reps, seed=9, want_rep=True)
+            sh.close(); c.close()
+        except Exception as ex:  # noqa: BLE001
+            errs[r] = ex
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert all(e is None for e in errs), errs
+    for o in outs:
+        for k in ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper"):
+            assert _same(o[k], one[k]), k
