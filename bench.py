@@ -136,7 +136,7 @@ class ClockSampler(threading.Thread):
                 pass
             # NVML calls contend with the CUDA driver lock (measured: a host-side CUDA call of the step that coincides with
             # a query stalls 8-22 ms): sample sparsely (>= 1 sample is always taken under load)
-            if self.stop_flag.wait(1.0):
+            if self.stop_flag.wait(0.25 if len(self.samples) == 1 else 2.0):
                 break
 
     def summary(self):
