@@ -100,11 +100,18 @@ def hbm_stage_rooflines(d, K, reps, world, shard_rows, out, pack_ms):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML during the timed region."""
+    """Samples SM clock and throttle reasons through NVML during the timed region.
+
+    NVML queries take a driver lock that host-side CUDA calls need too: a call of the step that coincides with a query
+    stalls 8-22 ms (measured).  So the sampler does not free-run: the timed loop announces every step (`step_begins`),
+    and a sample is taken 40 ms into a step -- the host is then parked in the library's wait for the Gram contraction
+    (>= 170 ms at every bench workload that matters), the GPU is under load, and nothing of the step is delayed -- at
+    most once every 2 s.  Without announcements it falls back to one sample every 2 s."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.stop_flag = threading.Event()
+        self.step_flag = threading.Event()
         self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
         try:
             import pynvml
@@ -116,6 +123,9 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
+    def step_begins(self):
+        self.step_flag.set()
+
     def run(self):
         if not self.ok:
             return
@@ -125,7 +135,7 @@ class ClockSampler(threading.Thread):
                  nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                  nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
-        while True:
+        def sample():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -134,10 +144,21 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            # NVML calls contend with the CUDA driver lock (measured: a host-side CUDA call of the step that coincides with
-            # a query stalls 8-22 ms): sample sparsely (>= 1 sample is always taken under load)
-            if self.stop_flag.wait(0.25 if len(self.samples) == 1 else 2.0):
+        last = 0.0
+        while not self.stop_flag.is_set():
+            announced = self.step_flag.wait(2.0)
+            self.step_flag.clear()
+            if self.stop_flag.is_set():
                 break
+            if announced:
+                if time.perf_counter() - last < 2.0 and self.samples:
+                    continue
+                if self.stop_flag.wait(0.04):          # 40 ms into the step: the host sits in the Gram wait
+                    break
+            sample()
+            last = time.perf_counter()
+        if not self.samples:                           # a timed region shorter than 40 ms: one sample right at its end
+            sample()
 
     def summary(self):
         if not self.samples:
@@ -566,6 +587,7 @@ def main():
     t0 = time.perf_counter()
     gram_ms, total_ms, launches = [], [], 0
     for _ in range(args.steps):
+        sampler.step_begins()
         out = step(design)
         gram_ms.append(out["timings_ms"]["gram_main"] if "gram_main" in out["timings_ms"] else out["timings_ms"]["gram"])
         total_ms.append(out["timings_ms"]["total"])
@@ -573,6 +595,7 @@ def main():
     sync()
     dt = time.perf_counter() - t0
     sampler.stop_flag.set()
+    sampler.step_flag.set()
     sampler.join()
     design.close()
 
