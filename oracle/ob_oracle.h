@@ -137,6 +137,26 @@ void orc_reduce(const double* rep_stats, const int32_t* rep_status, int64_t reps
 double orc_last_min_pivot(void);
 void orc_reset_min_pivot(void);
 
+/* ---- Heckman two-step replicate (ob_oracle_heckman.c).  X [n x K] outcome design incl. intercept, Z [n x K1]
+ * selection design (intercept first), s [n] selection outcome (0 / 1), all rows of the group; the outcome equation uses
+ * the rows with s == 1.  Statistics: S = 5 + 2 (K + 1) + K1 =
+ * [explained, unexplained, endowments, coefficients, interaction, det_expl[K+1], det_unexpl[K+1] (IMR last), selection[K1]]. */
+int orc_probit(const double* y, const double* X, int64_t n, int32_t k, int32_t max_iter, double tol,
+               double* beta, int32_t* converged, int32_t* iterations);                     /* math/probit.rs:25-175 */
+int32_t orc_heckman_n_stats(int32_t K, int32_t K1);
+int orc_heckman_pass(int32_t K, int32_t K1, int32_t ref_kind,
+                     const double* Xa, const double* ya, const double* Za, const double* sa, int64_t na,
+                     const double* Xb, const double* yb, const double* Zb, const double* sb, int64_t nb,
+                     int precise, double* stats, double* beta_a, double* beta_b, double* gamma_a, double* gamma_b,
+                     double* total_gap);                                                    /* builder.rs:420-699, estimation.rs:114-269 */
+int orc_heckman_run(int32_t K, int32_t K1, int32_t ref_kind,
+                    const double* Xa, const double* ya, const double* Za, const double* sa, int64_t na,
+                    const double* Xb, const double* yb, const double* Zb, const double* sb, int64_t nb,
+                    int64_t reps, const uint32_t* idx_a, const uint32_t* idx_b, int nthreads, int precise,
+                    double* point_stats, double* point_beta_a, double* point_beta_b, double* point_gamma_a, double* point_gamma_b,
+                    double* total_gap, double* rep_stats, int32_t* rep_status, double* rep_gamma_a,
+                    int64_t* n_ok, double* se, double* p, double* ci_lo, double* ci_hi, double* t);
+
 /* flatten a pass into the S-vector layout */
 void orc_pass_to_stats(const orc_spec* s, const orc_pass_out* p, double* stats);
 

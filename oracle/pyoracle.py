@@ -23,7 +23,7 @@ ERR_NAMES = {0: "Ok", 1: "PolarsError", 2: "ColumnNotFound", 3: "InvalidGroupVar
 
 def build(force: bool = False) -> str:
     """Compile the oracle (gcc, a second or two).  Building the checker is not using it."""
-    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("ob_oracle.c", "ob_oracle.h"))
+    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("ob_oracle.c", "ob_oracle_heckman.c", "ob_oracle.h"))
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < src_m:
         subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "CC": "gcc"})
     return _LIB_PATH
@@ -275,3 +275,47 @@ def reduce(rep_stats, rep_status, point_stats) -> dict:
                                                                       ("se", "p", "ci_lo", "ci_hi", "t")])
     red["n_ok"] = int(n_ok.value)
     return red
+
+
+# ---- Heckman two-step replicate (ob_oracle_heckman.c) -------------------------------------------------------------
+def probit(y, X, max_iter: int = 100, tol: float = 1e-6):
+    """math/probit.rs:25-175 -> (beta, converged, iterations)."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    beta = np.empty(X.shape[1])
+    conv, it = C.c_int32(), C.c_int32()
+    rc = lib().orc_probit(_dp(y), _dp(X), C.c_int64(X.shape[0]), C.c_int32(X.shape[1]), C.c_int32(max_iter), C.c_double(tol),
+                          _dp(beta), C.byref(conv), C.byref(it))
+    if rc != 0:
+        raise RuntimeError(ERR_NAMES.get(rc, str(rc)))
+    return beta, bool(conv.value), it.value
+
+
+def heckman_run(ref_kind, Xa, ya, Za, sa, Xb, yb, Zb, sb, reps, idx_a, idx_b, nthreads=4, precise=True):
+    """builder.rs:787-951 with the HeckmanEstimator (estimation.rs:114-269) under an explicit index stream."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (Xa, ya, Za, sa, Xb, yb, Zb, sb)]
+    Xa, ya, Za, sa, Xb, yb, Zb, sb = arrs
+    K, K1, na, nb = Xa.shape[1], Za.shape[1], Xa.shape[0], Xb.shape[0]
+    L = lib()
+    L.orc_heckman_n_stats.restype = C.c_int32
+    S = L.orc_heckman_n_stats(C.c_int32(K), C.c_int32(K1))
+    idx_a = np.ascontiguousarray(idx_a if reps else np.zeros((0, na)), dtype=np.uint32)
+    idx_b = np.ascontiguousarray(idx_b if reps else np.zeros((0, nb)), dtype=np.uint32)
+    out = dict(point_stats=np.empty(S), beta_a=np.empty(K + 1), beta_b=np.empty(K + 1), gamma_a=np.empty(K1), gamma_b=np.empty(K1),
+               rep_stats=np.empty((max(reps, 1), S)), rep_status=np.zeros(max(reps, 1), dtype=np.int32),
+               rep_gamma_a=np.empty((max(reps, 1), K1)), se=np.empty(S), p=np.empty(S), ci_lo=np.empty(S), ci_hi=np.empty(S), t=np.empty(S))
+    gap, nok = C.c_double(), C.c_int64()
+    U32 = C.POINTER(C.c_uint32)
+    rc = L.orc_heckman_run(C.c_int32(K), C.c_int32(K1), C.c_int32(ref_kind), _dp(Xa), _dp(ya), _dp(Za), _dp(sa), C.c_int64(na),
+                           _dp(Xb), _dp(yb), _dp(Zb), _dp(sb), C.c_int64(nb), C.c_int64(reps), idx_a.ctypes.data_as(U32),
+                           idx_b.ctypes.data_as(U32), C.c_int(nthreads), C.c_int(int(precise)),
+                           _dp(out["point_stats"]), _dp(out["beta_a"]), _dp(out["beta_b"]), _dp(out["gamma_a"]), _dp(out["gamma_b"]),
+                           C.byref(gap), _dp(out["rep_stats"]), out["rep_status"].ctypes.data_as(C.POINTER(C.c_int32)),
+                           _dp(out["rep_gamma_a"]), C.byref(nok), _dp(out["se"]), _dp(out["p"]), _dp(out["ci_lo"]), _dp(out["ci_hi"]),
+                           _dp(out["t"]))
+    if rc != 0:
+        raise RuntimeError(ERR_NAMES.get(rc, str(rc)))
+    for k in ("rep_stats", "rep_status", "rep_gamma_a"):
+        out[k] = out[k][:reps]
+    out.update(total_gap=gap.value, n_ok=int(nok.value), S=S)
+    return out

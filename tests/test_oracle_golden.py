@@ -159,3 +159,30 @@ def test_zero_reps(orc, golden):
     Xa, ya, wa, Xb, yb, wb, norm, n_cont = _design(fix)
     res = orc.run(orc.Spec(K=2, n_cont=1), Xa, ya, wa, Xb, yb, wb, 0)
     assert res["n_ok"] == 0 and np.all(np.isnan(res["se"])) and np.all(res["t"] == 0.0)
+
+
+def test_heckman_oracle_matches_the_independent_numpy_restatement():
+    """oracle/ob_oracle_heckman.c (probit.rs:25-175, heckman.rs:38-108, estimation.rs:114-269, builder.rs:464-534) against
+    tests/golden/heckman_fixture.json, which tests/golden/make_heckman_golden.py computed with numpy / scipy alone."""
+    import json
+    import os
+    from oracle import pyoracle as orc
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "heckman_fixture.json")))
+    c = {k: np.array(v, float) for k, v in fx["columns"].items()}
+    X = np.c_[np.ones(len(c["y"])), c["x"], c["d"]]
+    Z = np.c_[np.ones(len(c["y"])), c["z"]]
+    A, B = c["group"] == 0, c["group"] == 1
+    for name, ref in (("A", 0), ("B", 1), ("weighted", 3)):
+        out = orc.heckman_run(ref, X[A], c["y"][A], Z[A], c["s"][A], X[B], c["y"][B], Z[B], c["s"][B], 0, None, None)
+        exp = fx["expected"][name]
+        np.testing.assert_allclose(out["point_stats"], exp["stats"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(out["beta_a"], exp["beta_a"], rtol=1e-10)
+        np.testing.assert_allclose(out["gamma_b"], exp["gamma_b"], rtol=1e-10)
+        assert abs(out["total_gap"] - exp["total_gap"]) < 1e-12
+    # the reference's own probit test (probit.rs:180-211): converges, positive slope
+    beta, conv, it = orc.probit([0, 1, 0, 1, 0, 1], [[1, -1.5], [1, -0.5], [1, 0], [1, 0.5], [1, 1], [1, 1.5]])
+    assert conv and it > 0 and beta[1] > 0
+    beta, conv, it = orc.probit([0, 0, 1, 1], [[1, -1], [1, -0.5], [1, 0.5], [1, 1]], max_iter=1, tol=1e-15)   # probit.rs:213-227
+    assert not conv and it == 1
+    with pytest.raises(RuntimeError):                   # Pooled: K vs K+1 coefficient vectors in the reference
+        orc.heckman_run(2, X[A], c["y"][A], Z[A], c["s"][A], X[B], c["y"][B], Z[B], c["s"][B], 0, None, None)
