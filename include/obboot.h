@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define OBBOOT_ABI_VERSION 4
+#define OBBOOT_ABI_VERSION 5
 
 /* ---- errors: OaxacaError variants (error.rs:6-19) + device errors ------------------------- */
 typedef enum ob_status {
@@ -174,6 +174,29 @@ ob_status ob_design_apply_rif(ob_ctx* ctx, ob_design* d, double tau);
 ob_status ob_design_apply_rif_multi(ob_ctx* ctx, ob_design* d, const double* taus, int32_t n_tau);
 ob_status ob_design_num_outcomes(const ob_design* d, int32_t* n_out);
 
+/* ---- Heckman selection (OaxacaBuilder::heckman_selection, builder.rs:236-246; HeckmanEstimator, estimation.rs:114-269) --
+ * Attaches the selection equation to a packed design: the binary selection outcome and the selection predictors, one
+ * value per row of the frame the design was packed from (host memory, frame order, nulls already dropped like every
+ * used column, builder.rs:760-784).  ob_bootstrap_run then runs the two-step estimator on every replicate: probit of
+ * the selection outcome on [1 | predictors] over all (resampled) rows of a group (math/probit.rs:25-175), inverse Mills
+ * ratio on the rows with selection == 1, OLS of the outcome on [X | IMR] over those rows (heckman.rs:38-108).  All
+ * coefficient and mean vectors get one more entry (IMR, last), and the statistics are
+ *   S = 5 + 2 (K + 1) + K1:  [explained, unexplained, endowments, coefficients, interaction,
+ *                            detailed_explained[K+1], detailed_unexplained[K+1], detailed_selection[K1]]
+ * with K1 = 1 + n_pred (builder.rs:464-534; the first selection row is the intercept's).  As in the reference, Yun
+ * normalisation is not applied under Heckman (estimation.rs:160-161, builder.rs:634) and residuals are zeros.
+ * Refused (OB_ERR_UNSUPPORTED): Pooled | Neumark reference coefficients (the reference's pooled regression yields K
+ * coefficients against K+1, builder.rs:548-589 vs estimation.rs:139-141), sample weights, row-sharded designs,
+ * more than 7 selection predictors. */
+typedef struct ob_selection_view {
+    int32_t n_pred;                  /* selection predictors, user order */
+    const double* const* pred;       /* [n_pred] columns of n_frame doubles */
+    const double* outcome;           /* [n_frame] selection outcome: 1 = the outcome is observed */
+} ob_selection_view;
+ob_status ob_design_attach_selection(ob_ctx* ctx, ob_design* d, const ob_selection_view* sel, int64_t n_frame);
+ob_status ob_design_selection_cols(const ob_design* d, int32_t* k1_out);     /* 0 = no selection equation attached */
+int32_t ob_num_stats_heckman(int32_t K, int32_t K1);
+
 /* ---- (2)-(5) bootstrap ---------------------------------------------------------------------*/
 typedef struct ob_boot_opts {
     int32_t ref_kind;                /* ob_ref_kind; builder default is GROUP_A (builder.rs:123) */
@@ -237,6 +260,8 @@ typedef struct ob_result {
     int32_t gpu_launches;    /* kernels launched by this call */
     double ms_comm;          /* row-sharded runs: time inside the collectives (also contained in ms_counts / ms_total) */
     double* total_gap_multi; /* [n_tau] optional: total gap per outcome of a multi-outcome design (total_gap = the first) */
+    double* sel_gamma_a;     /* [K1] optional, Heckman designs: probit coefficients of the point estimate, group A */
+    double* sel_gamma_b;     /* [K1] optional */
 } ob_result;
 
 int32_t ob_num_stats(int32_t K, int32_t n_norm, const int32_t* norm_has_base);

@@ -29,7 +29,7 @@ SYMBOLS = ["ob_abi_version", "ob_device_count", "ob_ctx_create", "ob_ctx_destroy
            "ob_debug_gram_schedule", "ob_debug_counts_from_indices", "ob_host_alloc", "ob_host_free",
            "ob_host_register", "ob_host_unregister", "ob_replicate_shard", "ob_design_pack_async", "ob_design_wait",
            "ob_design_redistribute_rows", "ob_design_row_shard", "ob_design_apply_rif_multi", "ob_design_num_outcomes",
-           "ob_design_pack_row_shard_async"]
+           "ob_design_pack_row_shard_async", "ob_design_attach_selection", "ob_design_selection_cols", "ob_num_stats_heckman"]
 
 
 class FrameView(C.Structure):
@@ -52,6 +52,10 @@ class RawFrame(C.Structure):
                 ("nan_is_null", C.c_int32)]
 
 
+class SelectionView(C.Structure):
+    _fields_ = [("n_pred", C.c_int32), ("pred", C.POINTER(_DP)), ("outcome", _DP)]
+
+
 class BootOpts(C.Structure):
     _fields_ = [("ref_kind", C.c_int32), ("n_norm", C.c_int32), ("norm_m", _IP), ("norm_off", _IP),
                 ("norm_idx", _IP), ("norm_has_base", _IP), ("reps", C.c_int64), ("seed", C.c_uint64),
@@ -67,7 +71,7 @@ class Result(C.Structure):
                 ("t_stat", _DP), ("rep_stats", _DP), ("rep_status", _IP), ("rep_beta_a", _DP), ("rep_beta_b", _DP),
                 ("ms_counts", C.c_double), ("ms_gram", C.c_double), ("ms_solve", C.c_double),
                 ("ms_reduce", C.c_double), ("ms_total", C.c_double), ("ms_gram_kernel", C.c_double),
-                ("gpu_launches", C.c_int32), ("ms_comm", C.c_double), ("total_gap_multi", _DP)]
+                ("gpu_launches", C.c_int32), ("ms_comm", C.c_double), ("total_gap_multi", _DP), ("sel_gamma_a", _DP), ("sel_gamma_b", _DP)]
 
 
 def build(force: bool = False) -> str:
@@ -141,6 +145,10 @@ def lib() -> C.CDLL:
         L.ob_design_pack_row_shard_async.argtypes = [C.c_void_p, C.POINTER(FrameView), C.POINTER(C.c_void_p)]
         L.ob_design_apply_rif_multi.argtypes = [C.c_void_p, C.c_void_p, _DP, C.c_int32]
         L.ob_design_num_outcomes.argtypes = [C.c_void_p, _IP]
+        L.ob_design_attach_selection.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(SelectionView), C.c_int64]
+        L.ob_design_selection_cols.argtypes = [C.c_void_p, _IP]
+        L.ob_num_stats_heckman.argtypes = [C.c_int32, C.c_int32]
+        L.ob_num_stats_heckman.restype = C.c_int32
         L.ob_design_row_shard.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _IP, _IP]
         L.ob_design_redistribute_rows.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.ob_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]

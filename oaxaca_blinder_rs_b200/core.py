@@ -242,6 +242,26 @@ class Design:
         t = np.ascontiguousarray(list(taus), dtype=np.float64)
         self.ctx.check(N.lib().ob_design_apply_rif_multi(self.ctx._h, self._h, _dp(t), len(t)))
 
+    def attach_selection(self, selection_outcome, selection_predictors: Sequence[np.ndarray]):
+        """ob_design_attach_selection (OaxacaBuilder::heckman_selection, builder.rs:236-246): the binary selection outcome
+        and the selection predictors, one value per row of the frame this design was packed from.  bootstrap() then runs
+        the Heckman two-step estimator per replicate; coefficient / mean vectors gain the IMR entry (last) and the
+        statistics the detailed_selection rows."""
+        s = np.ascontiguousarray(selection_outcome, dtype=np.float64)
+        preds = [np.ascontiguousarray(p, dtype=np.float64) for p in selection_predictors]
+        assert all(p.shape == s.shape for p in preds)
+        sv = N.SelectionView()
+        sv.n_pred = len(preds)
+        arr = (N._DP * max(len(preds), 1))(*[_dp(p) for p in preds])
+        sv.pred, sv.outcome = arr, _dp(s)
+        self.ctx.check(N.lib().ob_design_attach_selection(self.ctx._h, self._h, C.byref(sv), s.shape[0]))
+
+    @property
+    def selection_cols(self) -> int:
+        k1 = C.c_int32()
+        N.lib().ob_design_selection_cols(self._h, C.byref(k1))
+        return k1.value
+
     @property
     def n_outcomes(self) -> int:
         t = C.c_int32()
@@ -429,6 +449,10 @@ def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequ
     ctx, K = design.ctx, design.K
     norm = list(norm)
     S = num_stats(K, norm)
+    K1 = design.selection_cols
+    if K1:                      # Heckman: K + 1 coefficients (IMR last), no Yun rows, K1 detailed_selection rows
+        norm, K = [], K + 1
+        S = 5 + 2 * K + K1
     o = N.BootOpts()
     o.ref_kind, o.n_norm = ref_kind, len(norm)
     m = np.array([v.m for v in norm] + [0], dtype=np.int32)
@@ -456,6 +480,8 @@ def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequ
              beta_a=np.empty(lead + (K,)), beta_b=np.empty(lead + (K,)), std_err=np.full(lead + (S,), np.nan),
              p_value=np.full(lead + (S,), np.nan), ci_lower=np.full(lead + (S,), np.nan), ci_upper=np.full(lead + (S,), np.nan),
              t_stat=np.zeros(lead + (S,)), total_gap_multi=np.empty(T))
+    if K1:
+        a["sel_gamma_a"], a["sel_gamma_b"] = np.empty(K1), np.empty(K1)
     if want_residuals:
         if residuals_out is not None:
             assert residuals_out.dtype == np.float64 and residuals_out.shape == lead + (design.n_b,) and residuals_out.flags.c_contiguous
@@ -481,8 +507,10 @@ def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequ
                timings_ms=dict(counts=r.ms_counts, gram=r.ms_gram, gram_main=r.ms_gram_kernel, solve=r.ms_solve,
                                reduce=r.ms_reduce, total=r.ms_total, comm=r.ms_comm),
                gpu_launches=int(r.gpu_launches))
-    D = (S - 5) // 2
-    out["det_expl"], out["det_unexpl"] = ps[..., 5:5 + D].copy(), ps[..., 5 + D:].copy()
+    D = (S - 5 - K1) // 2
+    out["det_expl"], out["det_unexpl"] = ps[..., 5:5 + D].copy(), ps[..., 5 + D:5 + 2 * D].copy()
+    if K1:
+        out["det_selection"] = ps[..., 5 + 2 * D:].copy()
     return out
 
 

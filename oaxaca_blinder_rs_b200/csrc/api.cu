@@ -57,6 +57,7 @@ struct ob_design {
     int device = 0;
     int K = 0, n_cont = 0, V = 0, ldx = 0;
     int T = 1;                       // outcome columns K .. K+T-1 of a design row (ob_design_apply_rif_multi: one per quantile)
+    int K1 = 0;                      // selection-equation columns incl. the intercept (ob_design_attach_selection), 0 = none
     bool weighted = false;
     int64_t n_frame = 0;             // rows of the frame the design was packed from (ob_design_update_outcome)
     int world = 1, rank = 0;         // row sharding (mode N): this design holds rank's rows of a world-way split
@@ -229,7 +230,10 @@ void design_release_device(ob_design* d) {
         if (g.Xs) cudaFreeAsync(g.Xs, st);
         if (g.src) cudaFreeAsync(g.src, st);
         if (g.y_raw) cudaFreeAsync(g.y_raw, st);
-        g.X = g.w = g.Xs = g.y_raw = nullptr; g.src = nullptr;
+        if (g.hk_Z) cudaFreeAsync(g.hk_Z, st);
+        if (g.hk_sel) cudaFreeAsync(g.hk_sel, st);
+        if (g.hk_Xm) cudaFreeAsync(g.hk_Xm, st);
+        g.X = g.w = g.Xs = g.y_raw = g.hk_Z = g.hk_Xm = nullptr; g.src = nullptr; g.hk_sel = nullptr;
     }
 }
 
@@ -1194,6 +1198,7 @@ ob_status ob_design_update_outcome(ob_ctx* ctx, ob_design* d, const double* y_fr
             update_outcome_launch(d->g[g], d->K, d->ldx, d_y.as<double>(), ctx->stream);
             if (d->g[g].y_raw) { cudaFreeAsync(d->g[g].y_raw, ctx->stream); d->g[g].y_raw = nullptr; }   // new raw outcome
             d->T = 1; d->V = d->K + 1;      // back to a single outcome column
+            if (d->g[g].hk_Xm) hk_mask_launch(d->g[g].X, d->g[g].hk_sel, d->g[g].hk_Xm, d->g[g].n_pad, d->ldx, ctx->stream);
         }
         OB_CUDA(cudaStreamSynchronize(ctx->stream));
     });
@@ -1240,6 +1245,7 @@ ob_status ob_design_apply_rif_multi(ob_ctx* ctx, ob_design* d, const double* tau
             DevBuf scratch(sb);
             for (int t = 0; t < n_tau; ++t) rif_transform(d->g[g], K + t, d->ldx, taus[t], scratch.p, sb, st, comm);
             scale_rows_launch(d->g[g], d->ldx, st);   // the RIF outcomes are weighted like any outcome
+            if (d->g[g].hk_Xm) hk_mask_launch(d->g[g].X, d->g[g].hk_sel, d->g[g].hk_Xm, d->g[g].n_pad, d->ldx, st);
             OB_CUDA(cudaStreamSynchronize(st));
         }
     });
@@ -1253,10 +1259,294 @@ ob_status ob_design_num_outcomes(const ob_design* d, int32_t* n_out) {
     return OB_OK;
 }
 
+int32_t ob_num_stats_heckman(int32_t K, int32_t K1) { return 5 + 2 * (K + 1) + K1; }
+
+ob_status ob_design_selection_cols(const ob_design* d, int32_t* k1_out) {
+    if (!d || !k1_out) return OB_ERR_INVALID_ARG;
+    *k1_out = d->K1;
+    return OB_OK;
+}
+
+ob_status ob_design_attach_selection(ob_ctx* ctx, ob_design* d, const ob_selection_view* sv, int64_t n_frame) {
+    if (!ctx || !d || !sv) return OB_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        design_ready(d);
+        if (sv->n_pred < 0 || sv->n_pred + 1 > HK_MAX_SEL) fail(OB_ERR_UNSUPPORTED, "at most 7 selection predictors");
+        if (!sv->outcome || (sv->n_pred && !sv->pred)) fail(OB_ERR_INVALID_ARG, "null selection column");
+        if (n_frame != d->n_frame) fail(OB_ERR_INVALID_ARG, "selection columns differ in length from the frame the design was packed from");
+        if (d->world > 1) fail(OB_ERR_UNSUPPORTED, "Heckman selection on a row-sharded design");
+        if (d->weighted) fail(OB_ERR_UNSUPPORTED, "Heckman selection with sample weights (the reference's estimator ignores them, estimation.rs:132-133)");
+        if (!d->g[0].src || !d->g[1].src) fail(OB_ERR_UNSUPPORTED, "this design carries no frame-row map");
+        cudaStream_t st = ctx->stream;
+        g_alloc_pack = true;
+        const int K1 = 1 + sv->n_pred;
+        const size_t nn = (size_t)std::max<int64_t>(n_frame, 1);
+        std::vector<DevBuf> cols((size_t)sv->n_pred);
+        std::vector<const double*> h_ptrs((size_t)std::max(sv->n_pred, 1), nullptr);
+        for (int j = 0; j < sv->n_pred; ++j) {
+            if (!sv->pred[j]) fail(OB_ERR_INVALID_ARG, "null selection predictor column");
+            cols[(size_t)j].alloc(sizeof(double) * nn);
+            OB_CUDA(cudaMemcpyAsync(cols[(size_t)j].p, sv->pred[j], sizeof(double) * (size_t)n_frame, cudaMemcpyHostToDevice, st));
+            h_ptrs[(size_t)j] = cols[(size_t)j].as<double>();
+        }
+        DevBuf d_out(sizeof(double) * nn), d_ptrs(sizeof(void*) * h_ptrs.size()), d_flags(sizeof(int) * 4);
+        OB_CUDA(cudaMemcpyAsync(d_out.p, sv->outcome, sizeof(double) * (size_t)n_frame, cudaMemcpyHostToDevice, st));
+        OB_CUDA(cudaMemcpyAsync(d_ptrs.p, h_ptrs.data(), sizeof(void*) * h_ptrs.size(), cudaMemcpyHostToDevice, st));
+        OB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * 4, st));
+        for (int g = 0; g < 2; ++g) {
+            GroupData& G = d->g[g];
+            if (G.hk_Z) { cudaFreeAsync(G.hk_Z, st); G.hk_Z = nullptr; }
+            if (G.hk_sel) { cudaFreeAsync(G.hk_sel, st); G.hk_sel = nullptr; }
+            if (G.hk_Xm) { cudaFreeAsync(G.hk_Xm, st); G.hk_Xm = nullptr; }
+            OB_CUDA(cudaMallocFromPoolAsync((void**)&G.hk_Z, sizeof(double) * (size_t)std::max<int64_t>(G.n, 1) * K1, ctx->pool_design, st));
+            OB_CUDA(cudaMallocFromPoolAsync((void**)&G.hk_sel, (size_t)G.n_pad, ctx->pool_design, st));
+            OB_CUDA(cudaMallocFromPoolAsync((void**)&G.hk_Xm, sizeof(double) * (size_t)G.n_pad * d->ldx, ctx->pool_design, st));
+            OB_CUDA(cudaMemsetAsync(G.hk_sel, 0, (size_t)G.n_pad, st));
+            hk_gather_launch(G.src, G.n, K1, d_ptrs.as<const double*>(), d_out.as<double>(), G.hk_Z, G.hk_sel, d_flags.as<int>(), st);
+            hk_mask_launch(G.X, G.hk_sel, G.hk_Xm, G.n_pad, d->ldx, st);
+        }
+        int flags[4];
+        OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        d->K1 = K1;
+        if (flags[0]) { d->K1 = 0; fail(OB_ERR_INVALID_GROUP, "Invalid group variable: Selection outcome contains nulls"); }   // estimation.rs:179-185
+    });
+}
+
+}  // extern "C"
+
+namespace {
+
+// ob_bootstrap_run on a design with a selection equation: the Heckman two-step estimator per replicate (heckman.cu).
+void heckman_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_result* res) {
+    cudaStream_t st = ctx->stream;
+    const int K = d->K, Ka = K + 1, K1 = d->K1;
+    if (o->ref_kind < 0 || o->ref_kind > 3) fail(OB_ERR_INVALID_ARG, "ref_kind out of range");
+    if (o->ref_kind == OB_REF_POOLED)
+        fail(OB_ERR_UNSUPPORTED, "Pooled / Neumark reference coefficients with Heckman selection: the reference's pooled regression has K "
+                                 "coefficients, the Heckman fits K + 1 (builder.rs:548-589 vs estimation.rs:139-141)");
+    if (d->T != 1) fail(OB_ERR_UNSUPPORTED, "Heckman selection on a multi-outcome design");
+    if (o->shard_replicates && ctx->comm && ctx->comm->world > 1) fail(OB_ERR_UNSUPPORTED, "Heckman selection with replicate sharding");
+    if (o->reps < 0) fail(OB_ERR_INVALID_ARG, "negative reps");
+    const int64_t rb = o->rep_begin, re = o->rep_end > 0 ? o->rep_end : o->reps;
+    if (rb < 0 || re < rb || re > o->reps) fail(OB_ERR_INVALID_ARG, "bad replicate shard");
+    const int64_t nrep = re - rb;
+    if (d->g[0].n == 0 || d->g[1].n == 0) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: One group has no data");
+    const bool index_mode = o->idx_a != nullptr || o->idx_b != nullptr;
+    if (index_mode && nrep > 0 && (!o->idx_a || !o->idx_b)) fail(OB_ERR_INVALID_ARG, "index stream needs both idx_a and idx_b");
+    if (o->count_bits != 0 && o->count_bits != 8 && o->count_bits != 16) fail(OB_ERR_INVALID_ARG, "count_bits must be 0, 8 or 16");
+    int count_bytes = o->count_bits == 16 ? 2 : 1;
+    const int S = ob_num_stats_heckman(K, K1);
+
+    res->ms_counts = res->ms_gram = res->ms_solve = res->ms_reduce = res->ms_total = res->ms_gram_kernel = res->ms_comm = 0.0;
+    res->gpu_launches = 0; res->n_ok = 0;
+    Timer t_total(st, &res->ms_total);
+    const int64_t slots = 1 + nrep, panels_total = (slots + BM - 1) / BM;
+    const bool want_beta = res->rep_beta_a || res->rep_beta_b || res->beta_a || res->beta_b;
+    DevBuf d_stats(sizeof(double) * (size_t)slots * S), d_status(sizeof(int) * (size_t)slots);
+    DevBuf d_ba(want_beta ? sizeof(double) * (size_t)slots * Ka : 0), d_bb(want_beta ? sizeof(double) * (size_t)slots * Ka : 0);
+    const size_t PE = 3 * (size_t)Ka + 2 * (size_t)K1 + 1;
+    DevBuf d_point(sizeof(double) * PE), d_flags(sizeof(int) * 4), d_lut(2 * counts_lut_bytes()), d_nact(sizeof(int));
+    const int ntiles = gram_ntiles(K, 1), Pld = gram_pld(K, 1);
+    const int64_t n_pad[2] = {d->g[0].n_pad, d->g[1].n_pad}, n_g[2] = {d->g[0].n, d->g[1].n};
+    const int nch[2] = {hk_num_chunks(n_g[0]), hk_num_chunks(n_g[1])};
+    const int nacc_p = K1 + K1 * (K1 + 1) / 2, nacc_t = K1 + 5;
+    const int64_t leaves = (int64_t)d->g[0].shard.segs + d->g[1].shard.segs;
+
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        size_t free_b = 0, total_b = 0;
+        OB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const double budget = o->max_workspace_bytes > 0 ? (double)o->max_workspace_bytes : 0.6 * ((double)free_b + (double)pool_idle_bytes(ctx));
+        const double per_panel = (double)(n_pad[0] + n_pad[1]) * BM * (count_bytes + 8.0) +        // counts + L = c * IMR
+                                 (index_mode ? (double)(n_g[0] + n_g[1]) * BM * 4.0 : 0.0) + 2.0 * BM * Pld * 8.0 +
+                                 (double)leaves * ntiles * (BM * BN * 8.0) +
+                                 (double)(nch[0] + nch[1]) * BM * 8.0 * std::max(std::max(nacc_p, nacc_t), K);
+        int64_t ppb = std::max<int64_t>(1, std::min<int64_t>((int64_t)std::floor(budget / per_panel), panels_total));
+        DevBuf d_C[2], d_L[2], d_idx[2], d_colsum(sizeof(long long) * 2 * (size_t)ppb * BM);
+        DevBuf d_gamma[2], d_active[2], d_pst[2], d_terms[2], d_xterm[2];
+        for (int g = 0; g < 2; ++g) {
+            d_C[g].alloc((size_t)ppb * n_pad[g] * BM * count_bytes);
+            d_L[g].alloc(sizeof(double) * (size_t)ppb * n_pad[g] * BM);
+            d_gamma[g].alloc(sizeof(double) * (size_t)ppb * BM * HK_MAX_SEL);
+            d_active[g].alloc(sizeof(int) * (size_t)ppb * BM); d_pst[g].alloc(sizeof(int) * (size_t)ppb * BM);
+            d_terms[g].alloc(sizeof(double) * (size_t)nacc_t * ppb * BM); d_xterm[g].alloc(sizeof(double) * (size_t)K * ppb * BM);
+        }
+        DevBuf d_part(sizeof(double) * (size_t)std::max(nch[0], nch[1]) * ppb * BM * std::max(std::max(nacc_p, nacc_t), K));
+        DevBuf d_gram(sizeof(double) * 2 * (size_t)ppb * BM * Pld), d_partials, d_pairs;
+        {
+            const std::vector<uint16_t> pairs = gram_pair_table(K, 1, ntiles);
+            d_pairs.alloc(sizeof(uint16_t) * pairs.size());
+            OB_CUDA(cudaMemcpyAsync(d_pairs.p, pairs.data(), sizeof(uint16_t) * pairs.size(), cudaMemcpyHostToDevice, st));
+            OB_CUDA(cudaStreamSynchronize(st));
+        }
+        GramPlan plan; int64_t plan_panels = -1;
+        bool saturated = false;
+        for (int64_t p0 = 0; p0 < panels_total && !saturated; p0 += ppb) {
+            const int64_t pn = std::min(ppb, panels_total - p0);
+            const int64_t slot_lo = p0 * BM, slot_hi = std::min(slots, (p0 + pn) * BM), bslots = slot_hi - slot_lo;
+            const int first_slot = p0 == 0 ? 1 : 0;
+            const int64_t brep = bslots - first_slot, rep0 = rb + slot_lo - 1, slots_pad = pn * BM;
+            OB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * 4, st));
+            // (2) replicate generation: the same multiplicity matrix as the OLS path
+            Timer t_counts(st, &res->ms_counts);
+            CountsArgs ca[2];
+            for (int g = 0; g < 2; ++g) {
+                ca[g].C = d_C[g].p; ca[g].count_bytes = count_bytes; ca[g].n = n_g[g]; ca[g].n_pad = n_pad[g];
+                ca[g].n_global = n_g[g]; ca[g].row_begin = 0; ca[g].panels = (int)pn; ca[g].slots = bslots;
+                ca[g].first_slot = first_slot; ca[g].rep0 = rep0; ca[g].group = g; ca[g].seed = o->seed;
+            }
+            if (index_mode) {
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t* h = g == 0 ? o->idx_a : o->idx_b;
+                    const size_t nb = sizeof(uint32_t) * (size_t)std::max<int64_t>(brep, 1) * n_g[g];
+                    if (d_idx[g].bytes < nb) d_idx[g].alloc(nb);
+                    if (brep > 0) OB_CUDA(cudaMemcpyAsync(d_idx[g].p, h + (size_t)(rep0 + first_slot) * n_g[g], sizeof(uint32_t) * (size_t)brep * n_g[g], cudaMemcpyHostToDevice, st));
+                    counts_from_indices(ca[g], d_idx[g].as<uint32_t>(), d_flags.as<int>(), st);
+                    res->gpu_launches += 2;
+                }
+            } else {
+                OB_CUDA(cudaMemsetAsync(d_colsum.p, 0, d_colsum.bytes, st));
+                for (int g = 0; g < 2; ++g) {
+                    counts_philox_body_launch(ca[g], d_colsum.as<long long>() + (size_t)g * ppb * BM, d_lut.as<unsigned char>() + (size_t)g * counts_lut_bytes(), st);
+                    counts_philox_fixup_launch(ca[g], d_colsum.as<long long>() + (size_t)g * ppb * BM, d_flags.as<int>(), st);
+                    res->gpu_launches += 3;
+                }
+            }
+            t_counts.stop();
+
+            // (3a) probit of every slot, both groups: Fisher scoring until every slot has converged (<= 100 steps)
+            Timer t_solve(st, &res->ms_solve);
+            for (int g = 0; g < 2; ++g) {
+                const HkGroup hg{d->g[g].hk_Z, d->g[g].hk_sel, n_g[g], n_pad[g]};
+                std::vector<int> act((size_t)slots_pad, 0);
+                for (int64_t s_ = 0; s_ < bslots; ++s_) act[(size_t)s_] = 1;
+                OB_CUDA(cudaMemcpyAsync(d_active[g].p, act.data(), sizeof(int) * (size_t)slots_pad, cudaMemcpyHostToDevice, st));
+                OB_CUDA(cudaMemsetAsync(d_gamma[g].p, 0, sizeof(double) * (size_t)slots_pad * HK_MAX_SEL, st));     // probit.rs:41: start at 0
+                OB_CUDA(cudaMemsetAsync(d_pst[g].p, 0, sizeof(int) * (size_t)slots_pad, st));
+                for (int it = 0; it < 100; ++it) {                                                                  // heckman.rs:46: probit(.., 100, 1e-6)
+                    OB_CUDA(cudaMemsetAsync(d_nact.p, 0, sizeof(int), st));
+                    hk_probit_accum_launch(hg, K1, d_C[g].p, count_bytes, (int)pn, d_gamma[g].as<double>(), d_active[g].as<int>(), slots_pad, d_part.as<double>(), st);
+                    hk_probit_update_launch(d_part.as<double>(), nch[g], (int)pn, K1, bslots, 1e-6, it == 99, d_gamma[g].as<double>(), d_active[g].as<int>(),
+                                            d_pst[g].as<int>(), d_nact.as<int>(), st);
+                    res->gpu_launches += 2;
+                    int nact = 0;
+                    OB_CUDA(cudaMemcpyAsync(&nact, d_nact.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    OB_CUDA(cudaStreamSynchronize(st));
+                    if (nact == 0) break;
+                }
+                // (3b) inverse Mills ratio sums and the cross term X'(c IMR)
+                hk_terms_launch(hg, d->g[g].X, d->ldx, K, K1, d_C[g].p, count_bytes, (int)pn, d_gamma[g].as<double>(), d_L[g].as<double>(), d_part.as<double>(), st);
+                hk_reduce_launch(d_part.as<double>(), nch[g], (int)pn, nacc_t, d_terms[g].as<double>(), slots_pad, st);
+                hk_xterm_launch(hg, d->g[g].X, d->ldx, K, (int)pn, d_L[g].as<double>(), d_part.as<double>(), st);
+                hk_reduce_launch(d_part.as<double>(), nch[g], (int)pn, K, d_xterm[g].as<double>(), slots_pad, st);
+                res->gpu_launches += 4;
+            }
+            t_solve.stop();
+
+            // (3c) X'CX, X'Cy and column sums over the selected rows: the DMMA contraction on the masked design
+            if (plan_panels != pn) {
+                plan = gram_make_plan(K, 1, d->ldx, (int)pn, d->g, count_bytes, ctx->num_sms);
+                plan_panels = pn;
+                d_partials.alloc(sizeof(double) * (size_t)std::max<int64_t>(plan.num_partials, 1) * BM * BN);
+            }
+            Timer t_gram(st, &res->ms_gram);
+            GramArgs ga;
+            for (int g = 0; g < 2; ++g) { ga.X[g] = d->g[g].hk_Xm; ga.C[g] = d_C[g].p; }
+            ga.count_bytes = count_bytes; ga.partials = d_partials.as<double>(); ga.d_pairs = d_pairs.as<uint16_t>(); ga.gram = d_gram.as<double>();
+            { const int64_t last = bslots - (pn - 1) * BM; ga.tail_mi = (int)std::min<int64_t>(16, ((last + 7) / 8 + 3) / 4 * 4); }
+            gram_launch(plan, ga, st);
+            res->gpu_launches += 2;
+            t_gram.stop();
+
+            // (4) augmented solves + decomposition
+            Timer t_solve2(st, &res->ms_solve);
+            HkSolveArgs sa;
+            sa.gram = d_gram.as<double>(); sa.slots_pad = slots_pad; sa.Pld = Pld; sa.slots = bslots; sa.K = K; sa.K1 = K1; sa.ref_kind = o->ref_kind;
+            for (int g = 0; g < 2; ++g) { sa.terms[g] = d_terms[g].as<double>(); sa.xterm[g] = d_xterm[g].as<double>(); sa.gamma[g] = d_gamma[g].as<double>(); sa.pstatus[g] = d_pst[g].as<int>(); }
+            sa.na = (double)n_g[0]; sa.nb = (double)n_g[1]; sa.S = S;
+            sa.stats = d_stats.as<double>() + (size_t)slot_lo * S; sa.status = d_status.as<int>() + slot_lo;
+            sa.beta_a = want_beta ? d_ba.as<double>() + (size_t)slot_lo * Ka : nullptr;
+            sa.beta_b = want_beta ? d_bb.as<double>() + (size_t)slot_lo * Ka : nullptr;
+            sa.point_extra = p0 == 0 ? d_point.as<double>() : nullptr;
+            hk_solve_launch(sa, st);
+            res->gpu_launches += 1;
+            t_solve2.stop();
+            int flags[4];
+            OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+            OB_CUDA(cudaStreamSynchronize(st));
+            t_counts.collect(); t_solve.collect(); t_gram.collect(); t_solve2.collect();
+            if (flags[2]) fail(OB_ERR_INVALID_ARG, "resample index out of range");
+            if (flags[0]) fail(OB_ERR_CUDA, "Poisson body overshot n (probability < 1e-15 per replicate); rerun with another seed");
+            if (flags[1]) {
+                if (count_bytes == 2 || o->count_bits == 8) fail(OB_ERR_UNSUPPORTED, "row multiplicity overflows the count width");
+                saturated = true;
+            }
+        }
+        if (!saturated) break;
+        count_bytes = 2;
+        res->ms_counts = res->ms_gram = res->ms_solve = 0.0;
+    }
+
+    int point_status = 0;
+    std::vector<double> point(PE);
+    OB_CUDA(cudaMemcpyAsync(&point_status, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OB_CUDA(cudaMemcpyAsync(point.data(), d_point.p, sizeof(double) * PE, cudaMemcpyDeviceToHost, st));
+    OB_CUDA(cudaStreamSynchronize(st));
+    if (point_status != OB_OK)
+        fail((ob_status)point_status, point_status == OB_ERR_INVALID_GROUP ? "Invalid group variable: No observed outcomes in group" : status_text(point_status));
+    res->total_gap = point[3 * Ka + 2 * K1];
+    if (res->xa_mean) memcpy(res->xa_mean, point.data(), sizeof(double) * Ka);
+    if (res->xb_mean) memcpy(res->xb_mean, point.data() + Ka, sizeof(double) * Ka);
+    if (res->beta_star) memcpy(res->beta_star, point.data() + 2 * Ka, sizeof(double) * Ka);
+    if (res->sel_gamma_a) memcpy(res->sel_gamma_a, point.data() + 3 * Ka, sizeof(double) * K1);
+    if (res->sel_gamma_b) memcpy(res->sel_gamma_b, point.data() + 3 * Ka + K1, sizeof(double) * K1);
+    if (res->total_gap_multi) res->total_gap_multi[0] = res->total_gap;
+    if (res->residuals_b) memset(res->residuals_b, 0, sizeof(double) * (size_t)d->g[1].n);      // estimation.rs:156-157: zeros
+    if (res->point_stats) OB_CUDA(cudaMemcpyAsync(res->point_stats, d_stats.p, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
+    if (res->beta_a) OB_CUDA(cudaMemcpyAsync(res->beta_a, d_ba.p, sizeof(double) * Ka, cudaMemcpyDeviceToHost, st));
+    if (res->beta_b) OB_CUDA(cudaMemcpyAsync(res->beta_b, d_bb.p, sizeof(double) * Ka, cudaMemcpyDeviceToHost, st));
+    if (!o->skip_reduce) {
+        DevBuf d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long)), d_rs(reduce_stats_scratch_bytes(nrep, S));
+        Timer t_red(st, &res->ms_reduce);
+        reduce_stats_launch(d_stats.as<double>() + S, d_status.as<int>() + 1, nrep, S, d_stats.as<double>(), d_out.as<double>(),
+                            d_nok.as<long long>(), st, d_rs.as<double>());
+        res->gpu_launches += 1;
+        t_red.stop();
+        std::vector<double> out5(5 * (size_t)S);
+        long long nok = 0;
+        OB_CUDA(cudaMemcpyAsync(out5.data(), d_out.p, d_out.bytes, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(&nok, d_nok.p, sizeof nok, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        t_red.collect();
+        res->n_ok = nok;
+        double* dst[5] = {res->std_err, res->p_value, res->ci_lower, res->ci_upper, res->t_stat};
+        for (int k = 0; k < 5; ++k)
+            if (dst[k]) memcpy(dst[k], out5.data() + (size_t)k * S, sizeof(double) * S);
+    }
+    if (nrep > 0) {
+        if (res->rep_stats) OB_CUDA(cudaMemcpyAsync(res->rep_stats, d_stats.as<double>() + S, sizeof(double) * (size_t)nrep * S, cudaMemcpyDeviceToHost, st));
+        if (res->rep_status) OB_CUDA(cudaMemcpyAsync(res->rep_status, d_status.as<int>() + 1, sizeof(int) * (size_t)nrep, cudaMemcpyDeviceToHost, st));
+        if (res->rep_beta_a) OB_CUDA(cudaMemcpyAsync(res->rep_beta_a, d_ba.as<double>() + Ka, sizeof(double) * (size_t)nrep * Ka, cudaMemcpyDeviceToHost, st));
+        if (res->rep_beta_b) OB_CUDA(cudaMemcpyAsync(res->rep_beta_b, d_bb.as<double>() + Ka, sizeof(double) * (size_t)nrep * Ka, cudaMemcpyDeviceToHost, st));
+    }
+    t_total.stop();
+    OB_CUDA(cudaStreamSynchronize(st));
+    t_total.collect();
+}
+
+}  // namespace
+
+extern "C" {
+
 ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_result* res) {
     if (!ctx || !d || !o || !res) return OB_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
         design_alive(d);
+        if (d->K1 > 0) {                 // a selection equation is attached: the Heckman two-step estimator per replicate
+            design_ready(d);
+            heckman_run(ctx, d, o, res);
+            return;
+        }
         cudaStream_t st = ctx->stream;
         const int K = d->K, T = d->T;
         if (o->ref_kind < 0 || o->ref_kind > 3) fail(OB_ERR_INVALID_ARG, "ref_kind out of range");

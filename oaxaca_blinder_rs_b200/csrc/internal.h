@@ -92,6 +92,9 @@ struct GroupData {               // one group's packed design in HBM (the rows t
     uint32_t* src = nullptr;     // [n] frame row each packed row came from (ob_design_update_outcome)
     double* y_raw = nullptr;     // [n] the untransformed outcome, saved by the first ob_design_apply_rif so that further
                                  // quantiles are computed from the raw y (a quantile sweep packs once)
+    // Heckman selection equation (ob_design_attach_selection): Z [n][K1] row-major with the intercept first, sel [n] =
+    // (selection outcome == 1), Xm [n_pad][ldx] = the design with unselected rows zeroed (operand of the outcome Gram)
+    double* hk_Z = nullptr; uint8_t* hk_sel = nullptr; double* hk_Xm = nullptr;
     const double* gram_operand() const { return Xs ? Xs : X; }
 };
 
@@ -290,6 +293,34 @@ void local_group_destroy(LocalGroup* g);
 Comm* comm_create_local(LocalGroup* g, int rank, int device);
 void nccl_unique_id(uint8_t* id128);
 Comm* comm_create_nccl(const uint8_t* id128, int rank, int world);
+
+// ---- heckman.cu: Heckman two-step replicate ----
+constexpr int HK_MAX_SEL = 8;        // selection-equation columns incl. the intercept
+struct HkGroup { const double* Z; const uint8_t* sel; int64_t n, n_pad; };   // Z [n][K1] row-major (intercept first), sel [n]
+int hk_num_chunks(int64_t n);
+// frame-order selection columns -> packed group order through the frame-row map; flags[0] |= 1 on a NaN selection outcome
+void hk_gather_launch(const uint32_t* src, int64_t n, int K1, const double* const* d_pred, const double* d_outcome, double* Z, uint8_t* sel,
+                      int* d_flags, cudaStream_t st);
+// Xm = X with the rows of unselected observations zeroed (all ldx columns)
+void hk_mask_launch(const double* X, const uint8_t* sel, double* Xm, int64_t rows, int ldx, cudaStream_t st);
+// one Fisher-scoring step of every active slot: partial [chunks][panels][K1 + K1(K1+1)/2][BM], then the per-slot update
+void hk_probit_accum_launch(const HkGroup& g, int K1, const void* C, int count_bytes, int panels, const double* gamma, const int* active,
+                            int64_t slots_pad, double* partial, cudaStream_t st);
+void hk_probit_update_launch(const double* partial, int nchunks, int panels, int K1, int64_t slots, double tol, int last_iter, double* gamma,
+                             int* active, int* pstatus, int* n_active, cudaStream_t st);
+// IMR sums: partial [chunks][panels][K1 + 5][BM]; L [panels][n_pad][BM] = c * IMR
+void hk_terms_launch(const HkGroup& g, const double* X, int ldx, int ycol, int K1, const void* C, int count_bytes, int panels, const double* gamma,
+                     double* L, double* partial, cudaStream_t st);
+void hk_xterm_launch(const HkGroup& g, const double* X, int ldx, int K, int panels, const double* L, double* partial, cudaStream_t st);
+void hk_reduce_launch(const double* partial, int nchunks, int panels, int nacc, double* out, int64_t slots_pad, cudaStream_t st);
+struct HkSolveArgs {
+    const double* gram; int64_t slots_pad; int Pld; int64_t slots;
+    int K, K1, ref_kind;
+    const double* terms[2]; const double* xterm[2]; const double* gamma[2]; const int* pstatus[2];
+    double na, nb; int S;
+    double* stats; int* status; double* beta_a; double* beta_b; double* point_extra;
+};
+void hk_solve_launch(const HkSolveArgs& a, cudaStream_t st);
 
 // ---- rif.cu ----
 // RIF transform (math/rif.rs:14-88) of a packed group's raw outcome (g.y_raw if saved, else column ycol itself),
