@@ -505,21 +505,35 @@ OaxacaResults OaxacaBuilder::decompose_quantile(double quantile) const {
 }
 
 OaxacaResults OaxacaBuilder::run_impl(bool rif, double tau) const {
-    if (has_selection_)
-        throw OaxacaError(OB_ERR_UNSUPPORTED, "heckman_selection: the Heckman estimator is outside the B200 bootstrap path "
-                                              "(SURVEY.md 8f); no CPU fallback is provided");
     Prepared p;
     CtxGuard g;
     ob_status st = ob_ctx_create(device_, &g.ctx);
     if (st != OB_OK) throw OaxacaError(st, "no usable CUDA device (B200 / sm_100a required; there is no CPU fallback)");
+    // HeckmanEstimator (estimation.rs:114-269) ignores the sample weights in both of its steps; the library refuses the
+    // combination rather than guess what beta* = Weighted should weigh with
+    if (has_selection_ && has_weights_)
+        throw OaxacaError(OB_ERR_UNSUPPORTED, "heckman_selection together with weights is not supported on the B200 path");
     g.des = ingest_on_device(g.ctx, p, has_weights_);
     if (rif) check(g.ctx, ob_design_apply_rif(g.ctx, g.des, tau));
+    int K1 = 0;
+    if (has_selection_) {
+        // heckman_selection (builder.rs:236-246): the selection columns were part of the null filter already; hand them
+        // over in frame order (the design's frame-row map picks the kept rows)
+        const Column* so = dataframe_.find(selection_outcome_);
+        require_f64(so);
+        std::vector<const double*> preds;
+        for (const auto& sp : selection_predictors_) { const Column* c = dataframe_.find(sp); require_f64(c); preds.push_back(c->f64.data()); }
+        ob_selection_view sv{(int32_t)preds.size(), preds.data(), so->f64.data()};
+        check(g.ctx, ob_design_attach_selection(g.ctx, g.des, &sv, (int64_t)dataframe_.height()));
+        K1 = 1 + (int)preds.size();
+    }
 
     int64_t na = 0, nb = 0; int32_t K = 0, nc = 0;
     ob_design_shape(g.des, &na, &nb, &K, &nc);
-    const int n_norm = (int)normalization_vars_.size();
-    const int S = ob_num_stats(K, n_norm, p.norm_has_base.data());
-    const int D = (S - 5) / 2;
+    const int n_norm = has_selection_ ? 0 : (int)normalization_vars_.size();        // no Yun rows under Heckman (builder.rs:634)
+    const int Kc = has_selection_ ? K + 1 : K;                                      // coefficient vectors: IMR last (estimation.rs:139-151)
+    const int S = has_selection_ ? ob_num_stats_heckman(K, K1) : ob_num_stats(K, n_norm, p.norm_has_base.data());
+    const int D = has_selection_ ? Kc : (S - 5) / 2;
 
     ob_boot_opts o{};
     switch (reference_coeffs_) {
@@ -535,7 +549,7 @@ OaxacaResults OaxacaBuilder::run_impl(bool rif, double tau) const {
 
     OaxacaResults R;
     std::vector<double> point(S), se(S), pv(S), lo(S), hi(S), t(S);
-    R.xa_mean.resize(K); R.xb_mean.resize(K); R.beta_star.resize(K); R.residuals.resize((size_t)nb);
+    R.xa_mean.resize(Kc); R.xb_mean.resize(Kc); R.beta_star.resize(Kc); R.residuals.resize((size_t)nb);
     ob_result r{};
     r.point_stats = point.data(); r.xa_mean = R.xa_mean.data(); r.xb_mean = R.xb_mean.data(); r.beta_star = R.beta_star.data();
     r.residuals_b = R.residuals.data();
@@ -555,13 +569,19 @@ OaxacaResults OaxacaBuilder::run_impl(bool rif, double tau) const {
     R.two_fold.aggregate = {comp("explained", 0), comp("unexplained", 1)};                            // :867-884
     R.three_fold.aggregate = {comp("endowments", 2), comp("coefficients", 3), comp("interaction", 4)}; // :885-910
     std::vector<std::string> rows = p.names;
-    rows.insert(rows.end(), p.base_names.begin(), p.base_names.end());                                // :661-669
+    if (has_selection_) rows.push_back("IMR");                                                        // estimation.rs:153-154
+    else rows.insert(rows.end(), p.base_names.begin(), p.base_names.end());                           // :661-669
     for (int j = 0; j < D; ++j) {
         R.two_fold.detailed_explained.push_back(comp(rows[j], 5 + j));
         R.two_fold.detailed_unexplained.push_back(comp(rows[j], 5 + D + j));
     }
+    if (has_selection_) {                                                                             // builder.rs:507-534, :925-930
+        R.two_fold.detailed_selection.push_back(comp("__ob_intercept__", 5 + 2 * D));
+        for (size_t j = 0; j < selection_predictors_.size(); ++j)
+            R.two_fold.detailed_selection.push_back(comp(selection_predictors_[j], 5 + 2 * D + 1 + (int)j));
+    }
     R.n_a = (size_t)na; R.n_b = (size_t)nb;
-    R.predictor_names = p.names;
+    R.predictor_names = has_selection_ ? rows : p.names;
     R.ms_total = r.ms_total; R.ms_gram = r.ms_gram;
     return R;
 }

@@ -145,11 +145,42 @@ def test_builder_vs_oracle_with_index_stream(ob, orc):
     np.testing.assert_array_equal(xa, e["Xa"]); np.testing.assert_array_equal(yb, e["yb"])
 
 
-def test_heckman_is_refused_not_faked(ob, golden):
-    b = ob.OaxacaBuilder(sample_frame(golden), "wage", "gender", "F").predictors(["education"])
-    b.heckman_selection("education", ["education"])
+def test_heckman_selection_through_the_builder(ob):
+    """tests/heckman_test.rs: OaxacaBuilder + .heckman_selection(..) + bootstrap_reps(0) -> an "IMR" row in the detailed
+    decomposition.  Here also the numbers: against the oracle on the cleaned frame (nulls in the selection columns are part
+    of clean_dataframe's filter, builder.rs:760-784), plus the detailed_selection rows (builder.rs:507-534)."""
+    from oracle import pyoracle as orc
+    rng = np.random.default_rng(42)
+    n = 2000
+    z = rng.normal(size=n)
+    x = z + 0.5 * rng.normal(size=n)
+    u = rng.normal(size=n)
+    e = 0.8 * u + 0.6 * rng.normal(size=n)
+    s = (0.5 * z + u > 0).astype(float)
+    y = 1.0 + 2.0 * x + e
+    grp = np.where(rng.random(n) < 0.5, "A", "B")
+    zl = [None if i in (5, 77) else float(v) for i, v in enumerate(z)]        # nulls: those rows are dropped
+    sl = [None if i == 123 else float(v) for i, v in enumerate(s)]
+    frame = {"outcome": y.tolist(), "x": x.tolist(), "z": zl, "selection": sl, "group": grp.tolist()}
+    b = ob.OaxacaBuilder(frame, "outcome", "group", "B").predictors(["x"]).heckman_selection("selection", ["z"]).bootstrap_reps(40).seed(3)
+    r = b.run()
+    names = [c.name for c in r.two_fold.detailed_explained]
+    assert names == ["__ob_intercept__", "x", "IMR"]                          # heckman_test.rs: has_imr
+    assert [c.name for c in r.two_fold.detailed_selection] == ["__ob_intercept__", "z"]
+    keep = np.ones(n, bool); keep[[5, 77, 123]] = False
+    A, B = keep & (grp == "A"), keep & (grp == "B")
+    X = np.c_[np.ones(n), x]; Z = np.c_[np.ones(n), z]
+    o = orc.heckman_run(0, X[A], y[A], Z[A], s[A], X[B], y[B], Z[B], s[B], 0, None, None)     # builder default: GroupA
+    est = np.array([c.estimate for c in r.two_fold.aggregate + r.three_fold.aggregate + r.two_fold.detailed_explained
+                    + r.two_fold.detailed_unexplained + r.two_fold.detailed_selection])
+    np.testing.assert_allclose(est, o["point_stats"], rtol=1e-9, atol=1e-12)
+    assert abs(r.total_gap - o["total_gap"]) < 1e-12 and (r.n_a, r.n_b) == (int(A.sum()), int(B.sum()))
+    assert all(np.isfinite(c.std_err) and c.std_err > 0 for c in r.two_fold.aggregate)
+    assert all(v == 0.0 for v in r.residuals)                                 # estimation.rs:156-157
+    # Pooled with Heckman: K vs K+1 coefficient vectors in the reference -> refused, not faked
     with pytest.raises(ob.OaxacaError) as e:
-        b.run()
+        ob.OaxacaBuilder(frame, "outcome", "group", "B").predictors(["x"]).heckman_selection("selection", ["z"]) \
+            .reference_coefficients(ob.ReferenceCoefficients.Pooled).bootstrap_reps(0).run()
     assert e.value.kind == "Unsupported"
 
 
