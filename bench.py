@@ -43,7 +43,8 @@ WORKLOADS = {
 # the kernel: profiles/gram_traffic.json holds {workload, n_gpus, bytes, src_sha256, csv}; an entry counts only while the
 # hash of the kernel sources it was taken on equals the current sources -- otherwise the key is null, never stale.
 GRAM_SOURCES = ("oaxaca_blinder_rs_b200/csrc/gram.cu", "oaxaca_blinder_rs_b200/csrc/common.cuh")
-GRAM_GEOMETRY = "oaxaca_blinder_rs_b200/csrc/internal.h"      # only its constexpr lines (tile sizes, leaf count) shape the kernel
+GRAM_GEOMETRY = "oaxaca_blinder_rs_b200/csrc/internal.h"      # only the tile / leaf constants below shape the kernel
+GRAM_GEOMETRY_NAMES = ("constexpr int BM ", "constexpr int BN ", "constexpr int KT ", "constexpr int GRAM_THREADS ", "constexpr int MAX_SEGS ")
 
 
 def gram_source_hash():
@@ -53,7 +54,7 @@ def gram_source_hash():
         with open(os.path.join(ROOT, f), "rb") as fh:
             h.update(fh.read())
     with open(os.path.join(ROOT, GRAM_GEOMETRY)) as fh:
-        h.update("".join(ln for ln in fh if ln.lstrip().startswith("constexpr")).encode())
+        h.update("".join(ln for ln in fh if ln.lstrip().startswith(GRAM_GEOMETRY_NAMES)).encode())
     return h.hexdigest()
 
 
