@@ -245,3 +245,23 @@ def test_design_outliving_its_context_is_harmless():
     assert e.value.kind == "InvalidArgument"
     des.close()          # only frees the host struct
     ctx2.close()
+
+
+def test_cli_heckman_flags(tmp_path):
+    """--selection-outcome / --selection-predictors (main.rs RunArgs) reach heckman_selection: an IMR row is printed."""
+    rng = np.random.default_rng(9)
+    n = 1500
+    z = rng.normal(size=n); x = z + 0.5 * rng.normal(size=n); u = rng.normal(size=n)
+    s = (0.5 * z + u > 0).astype(int)
+    y = 1.0 + 2.0 * x + 0.8 * u + 0.6 * rng.normal(size=n)
+    g = np.where(rng.random(n) < 0.5, "A", "B")
+    path = tmp_path / "sel.csv"
+    with open(path, "w") as fh:
+        fh.write("outcome,x,z,selection,group\n")
+        for i in range(n):
+            fh.write(f"{y[i]:.10g},{x[i]:.10g},{z[i]:.10g},{s[i]},{g[i]}\n")
+    r = subprocess.run([CLI, "--data", str(path), "--outcome", "outcome", "--group", "group", "--reference", "B", "--predictors", "x",
+                        "--selection-outcome", "selection", "--selection-predictors", "z", "--bootstrap-reps", "20", "--seed", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "IMR" in r.stdout and "explained" in r.stdout

@@ -46,7 +46,7 @@ def _run_world(d, world, reps, **kw):
             ctx.close()
         except Exception as e:  # noqa: BLE001
             errs[r] = e
-    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
     for t in ts:
         t.start()
     for t in ts:

@@ -104,7 +104,7 @@ def test_multi_quantile_pass_replicate_sharded():
             dd.close(); c.close()
         except Exception as e:  # noqa: BLE001
             errs[r] = e
-    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
     for t in ts:
         t.start()
     for t in ts:

@@ -106,7 +106,7 @@ def _run_sharded(d, world, reps, norm, ref_kind, seed=None, idx=None, max_ws=0):
             ctx.close()
         except Exception as e:  # noqa: BLE001
             errs[r] = e
-    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
     for t in ts:
         t.start()
     for t in ts:
@@ -214,7 +214,7 @@ def test_allgather_rows_equals_whole_frame_pack(weighted):
             full.close(); c.close()
         except Exception as ex:  # noqa: BLE001
             errs[r] = ex
-    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
     for t in ts:
         t.start()
     for t in ts:
@@ -304,7 +304,7 @@ def test_redistributed_slices_equal_row_shards(world, sort_by_group):
             shard.close(); c.close()
         except Exception as ex:  # noqa: BLE001
             errs[r] = ex
-    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
     for t in ts:
         t.start()
     for t in ts:
@@ -359,7 +359,7 @@ def test_async_row_shard_pack_equals_row_shards(world, n, sort_by_group):
             outs[r] = (same, o)
         except Exception as ex:  # noqa: BLE001
             errs[r] = ex
-    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
     for t in ts:
         t.start()
     for t in ts:
@@ -407,7 +407,7 @@ def test_rif_on_row_shards_is_bit_identical(world, orc):
             outs[r] = (y9[1], y9[4], o)
         except Exception as ex:  # noqa: BLE001
             errs[r] = ex
-    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
     for t in ts:
         t.start()
     for t in ts:
@@ -446,7 +446,7 @@ def test_async_pack_marked_as_row_shard_while_in_flight():
             sh.close(); c.close()
         except Exception as ex:  # noqa: BLE001
             errs[r] = ex
-    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
     for t in ts:
         t.start()
     for t in ts:

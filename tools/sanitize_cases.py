@@ -67,7 +67,7 @@ def main():
             outs[r] = (o1, o2)
         except Exception as e:  # noqa: BLE001
             errs[r] = e
-    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
     for t in ts:
         t.start()
     for t in ts:
