@@ -1326,9 +1326,13 @@ void heckman_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_resu
         fail(OB_ERR_UNSUPPORTED, "Pooled / Neumark reference coefficients with Heckman selection: the reference's pooled regression has K "
                                  "coefficients, the Heckman fits K + 1 (builder.rs:548-589 vs estimation.rs:139-141)");
     if (d->T != 1) fail(OB_ERR_UNSUPPORTED, "Heckman selection on a multi-outcome design");
-    if (o->shard_replicates && ctx->comm && ctx->comm->world > 1) fail(OB_ERR_UNSUPPORTED, "Heckman selection with replicate sharding");
     if (o->reps < 0) fail(OB_ERR_INVALID_ARG, "negative reps");
-    const int64_t rb = o->rep_begin, re = o->rep_end > 0 ? o->rep_end : o->reps;
+    // mode R inside the library, as for the OLS path: this rank's contiguous share of the global replicate ids
+    const bool shard_reps = o->shard_replicates != 0 && ctx->comm && ctx->comm->world > 1;
+    if (shard_reps && (o->rep_begin != 0 || o->rep_end != 0 || o->skip_reduce))
+        fail(OB_ERR_INVALID_ARG, "shard_replicates computes the shard itself: rep_begin / rep_end / skip_reduce must be 0");
+    int64_t rb = o->rep_begin, re = o->rep_end > 0 ? o->rep_end : o->reps;
+    if (shard_reps) ob_replicate_shard(o->reps, ctx->comm->world, ctx->comm->rank, &rb, &re);
     if (rb < 0 || re < rb || re > o->reps) fail(OB_ERR_INVALID_ARG, "bad replicate shard");
     const int64_t nrep = re - rb;
     if (d->g[0].n == 0 || d->g[1].n == 0) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: One group has no data");
@@ -1353,6 +1357,8 @@ void heckman_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_resu
     const int nacc_p = K1 + K1 * (K1 + 1) / 2, nacc_t = K1 + 5;
     const int64_t leaves = (int64_t)d->g[0].shard.segs + d->g[1].shard.segs;
 
+    std::vector<double> point(PE);
+    auto run_batches = [&] {
     for (int attempt = 0; attempt < 2; ++attempt) {
         size_t free_b = 0, total_b = 0;
         OB_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -1486,14 +1492,27 @@ void heckman_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_resu
         count_bytes = 2;
         res->ms_counts = res->ms_gram = res->ms_solve = 0.0;
     }
-
     int point_status = 0;
-    std::vector<double> point(PE);
     OB_CUDA(cudaMemcpyAsync(&point_status, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     OB_CUDA(cudaMemcpyAsync(point.data(), d_point.p, sizeof(double) * PE, cudaMemcpyDeviceToHost, st));
     OB_CUDA(cudaStreamSynchronize(st));
     if (point_status != OB_OK)
         fail((ob_status)point_status, point_status == OB_ERR_INVALID_GROUP ? "Invalid group variable: No observed outcomes in group" : status_text(point_status));
+    };   // run_batches
+    if (shard_reps) {      // all ranks leave together (see ob_bootstrap_run)
+        int rc = OB_OK; std::string msg;
+        try { run_batches(); } catch (const StatusError& e) { rc = e.code; msg = e.msg; }
+        DevBuf d_rc(sizeof(int));
+        int agreed = rc;
+        OB_CUDA(cudaMemcpyAsync(d_rc.p, &agreed, sizeof(int), cudaMemcpyHostToDevice, st));
+        ctx->comm->allreduce(d_rc.p, 1, CommDType::I32, CommOp::MAX, st);
+        OB_CUDA(cudaMemcpyAsync(&agreed, d_rc.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        if (rc != OB_OK) fail((ob_status)rc, msg);
+        if (agreed != OB_OK) fail((ob_status)agreed, std::string("another rank of the replicate-sharded run failed: ") + status_text(agreed));
+    } else {
+        run_batches();
+    }
     res->total_gap = point[3 * Ka + 2 * K1];
     if (res->xa_mean) memcpy(res->xa_mean, point.data(), sizeof(double) * Ka);
     if (res->xb_mean) memcpy(res->xb_mean, point.data() + Ka, sizeof(double) * Ka);
@@ -1505,10 +1524,37 @@ void heckman_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_resu
     if (res->point_stats) OB_CUDA(cudaMemcpyAsync(res->point_stats, d_stats.p, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
     if (res->beta_a) OB_CUDA(cudaMemcpyAsync(res->beta_a, d_ba.p, sizeof(double) * Ka, cudaMemcpyDeviceToHost, st));
     if (res->beta_b) OB_CUDA(cudaMemcpyAsync(res->beta_b, d_bb.p, sizeof(double) * Ka, cudaMemcpyDeviceToHost, st));
+    const int64_t reps_all = shard_reps ? o->reps : nrep;
+    DevBuf d_gstats, d_gstatus, d_gba, d_gbb;
+    const double* stats_rows = d_stats.as<double>() + S;
+    const int* status_rows = d_status.as<int>() + 1;
+    const double* ba_rows = want_beta ? d_ba.as<double>() + Ka : nullptr;
+    const double* bb_rows = want_beta ? d_bb.as<double>() + Ka : nullptr;
+    if (shard_reps) {      // replicate rows of all ranks, device to device, into global replicate order
+        Timer t_c(st, &res->ms_comm);
+        Comm* cm = ctx->comm.get();
+        const int w = cm->world;
+        std::vector<size_t> off(w), sz(w);
+        auto gather_rows = [&](const void* mine, DevBuf& all, size_t row_bytes) {
+            all.alloc(row_bytes * (size_t)std::max<int64_t>(reps_all, 1));
+            for (int r = 0; r < w; ++r) {
+                int64_t b = 0, e = 0;
+                ob_replicate_shard(o->reps, w, r, &b, &e);
+                off[r] = (size_t)b * row_bytes; sz[r] = (size_t)(e - b) * row_bytes;
+            }
+            cm->allgatherv(mine, all.p, off.data(), sz.data(), st);
+        };
+        gather_rows(stats_rows, d_gstats, sizeof(double) * (size_t)S);
+        gather_rows(status_rows, d_gstatus, sizeof(int));
+        stats_rows = d_gstats.as<double>(); status_rows = d_gstatus.as<int>();
+        if (res->rep_beta_a) { gather_rows(ba_rows, d_gba, sizeof(double) * (size_t)Ka); ba_rows = d_gba.as<double>(); }
+        if (res->rep_beta_b) { gather_rows(bb_rows, d_gbb, sizeof(double) * (size_t)Ka); bb_rows = d_gbb.as<double>(); }
+        t_c.stop(); OB_CUDA(cudaStreamSynchronize(st)); t_c.collect();
+    }
     if (!o->skip_reduce) {
-        DevBuf d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long)), d_rs(reduce_stats_scratch_bytes(nrep, S));
+        DevBuf d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long)), d_rs(reduce_stats_scratch_bytes(reps_all, S));
         Timer t_red(st, &res->ms_reduce);
-        reduce_stats_launch(d_stats.as<double>() + S, d_status.as<int>() + 1, nrep, S, d_stats.as<double>(), d_out.as<double>(),
+        reduce_stats_launch(stats_rows, status_rows, reps_all, S, d_stats.as<double>(), d_out.as<double>(),
                             d_nok.as<long long>(), st, d_rs.as<double>());
         res->gpu_launches += 1;
         t_red.stop();
@@ -1523,11 +1569,11 @@ void heckman_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_resu
         for (int k = 0; k < 5; ++k)
             if (dst[k]) memcpy(dst[k], out5.data() + (size_t)k * S, sizeof(double) * S);
     }
-    if (nrep > 0) {
-        if (res->rep_stats) OB_CUDA(cudaMemcpyAsync(res->rep_stats, d_stats.as<double>() + S, sizeof(double) * (size_t)nrep * S, cudaMemcpyDeviceToHost, st));
-        if (res->rep_status) OB_CUDA(cudaMemcpyAsync(res->rep_status, d_status.as<int>() + 1, sizeof(int) * (size_t)nrep, cudaMemcpyDeviceToHost, st));
-        if (res->rep_beta_a) OB_CUDA(cudaMemcpyAsync(res->rep_beta_a, d_ba.as<double>() + Ka, sizeof(double) * (size_t)nrep * Ka, cudaMemcpyDeviceToHost, st));
-        if (res->rep_beta_b) OB_CUDA(cudaMemcpyAsync(res->rep_beta_b, d_bb.as<double>() + Ka, sizeof(double) * (size_t)nrep * Ka, cudaMemcpyDeviceToHost, st));
+    if (reps_all > 0) {
+        if (res->rep_stats) OB_CUDA(cudaMemcpyAsync(res->rep_stats, stats_rows, sizeof(double) * (size_t)reps_all * S, cudaMemcpyDeviceToHost, st));
+        if (res->rep_status) OB_CUDA(cudaMemcpyAsync(res->rep_status, status_rows, sizeof(int) * (size_t)reps_all, cudaMemcpyDeviceToHost, st));
+        if (res->rep_beta_a) OB_CUDA(cudaMemcpyAsync(res->rep_beta_a, ba_rows, sizeof(double) * (size_t)reps_all * Ka, cudaMemcpyDeviceToHost, st));
+        if (res->rep_beta_b) OB_CUDA(cudaMemcpyAsync(res->rep_beta_b, bb_rows, sizeof(double) * (size_t)reps_all * Ka, cudaMemcpyDeviceToHost, st));
     }
     t_total.stop();
     OB_CUDA(cudaStreamSynchronize(st));

@@ -133,3 +133,41 @@ def test_heckman_argument_checks():
     out = ob.bootstrap(des, 8, seed=1)
     assert out["S"] == 5 + 2 * des.K
     des.close(); ctx.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_heckman_replicate_sharded_is_bit_identical(world):
+    """Mode R inside the library carries the Heckman replicate rows like any others: every rank returns the one-GPU result."""
+    import threading
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import core
+    fr = make_selection_frame(5_000, 2, seed=21)
+    reps = 131
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, fr["cont"], [fr["cat"]], [3], fr["y"], None, fr["group"])
+    des.attach_selection(fr["s"], fr["z"])
+    one = ob.bootstrap(des, reps, ref_kind=3, seed=4, want_rep=True)
+    des.close(); ctx.close()
+    grp = core.LocalGroup(world)
+    outs, errs = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            c = ob.Context(0)
+            c.init_local(grp, r)
+            dd = ob.Design.pack(c, fr["cont"], [fr["cat"]], [3], fr["y"], None, fr["group"])
+            dd.attach_selection(fr["s"], fr["z"])
+            outs[r] = ob.bootstrap(dd, reps, ref_kind=3, seed=4, want_rep=True, shard_replicates=True)
+            dd.close(); c.close()
+        except Exception as e:  # noqa: BLE001
+            errs[r] = e
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert all(e is None for e in errs), errs
+    same = lambda a, b: np.array_equal(np.nan_to_num(a, nan=-7.0), np.nan_to_num(b, nan=-7.0))   # noqa: E731
+    for o in outs:
+        for k in ("point_stats", "rep_stats", "rep_status", "rep_beta_a", "std_err", "ci_lower", "ci_upper", "p_value", "sel_gamma_a"):
+            assert same(o[k], one[k]), k
