@@ -98,3 +98,31 @@ def test_async_pack_reports_deferred_errors():
         ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], w, d["group"])
     assert e.value.kind == "InvalidGroupVariable"
     ctx.close()
+
+
+def test_async_pack_edge_shapes():
+    """Tiny frames (one chunk, fewer rows than a pipeline stage), an empty group (the error arrives from the bootstrap,
+    the in-flight design is destroyed cleanly) and an empty frame."""
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import synth
+    ctx = ob.Context(0)
+    for n in (40, 33, 129):
+        d = synth.make_wage(n, 2, seed=n)
+        args = (d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+        s = ob.Design.pack(ctx, *args)
+        a = ob.Design.pack(ctx, *args, asynchronous=True)
+        rs, ra = ob.bootstrap(s, 50, seed=2, want_rep=True), ob.bootstrap(a, 50, seed=2, want_rep=True)
+        assert _same(rs["rep_stats"], ra["rep_stats"]) and _same(rs["std_err"], ra["std_err"])
+        s.close(); a.close()
+    d = synth.make_wage(5_000, 2, seed=1)
+    g = np.zeros_like(d["group"])                     # everybody in group A
+    a = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], g, asynchronous=True)
+    assert (a.n_a, a.n_b) == (5_000, 0)
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.bootstrap(a, 8, seed=1)
+    assert e.value.kind == "InvalidGroupVariable"
+    a.close()
+    e0 = ob.Design.pack(ctx, [np.empty(0)], [], [], np.empty(0), None, np.empty(0, dtype=np.uint8), asynchronous=True)
+    assert (e0.n_a, e0.n_b) == (0, 0)
+    e0.close()
+    ctx.close()

@@ -455,3 +455,38 @@ def test_async_pack_marked_as_row_shard_while_in_flight():
     for o in outs:
         for k in ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper"):
             assert _same(o[k], one[k]), k
+
+
+@pytest.mark.gpu
+def test_async_row_shard_pack_with_more_ranks_than_leaves():
+    """Eight ranks, 700 rows: the row-shard plan leaves most ranks without rows of one group or of both; every rank
+    still takes part in the exchange and the collectives, and the result equals one GPU."""
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import core, synth, distributed as obd
+    d = synth.make_wage(700, 2, cat_levels=(), weights=False, seed=31)
+    world, reps = 8, 70
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], d["weights"], d["group"])
+    one = ob.bootstrap(des, reps, seed=6, want_rep=True)
+    des.close(); ctx.close()
+    grp = core.LocalGroup(world)
+    outs, errs = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            c = ob.Context(0)
+            c.init_local(grp, r)
+            sh = obd.pack_row_shard_async(c, d, r, world)
+            outs[r] = ob.bootstrap(sh, reps, seed=6, want_rep=True)
+            sh.close(); c.close()
+        except Exception as ex:  # noqa: BLE001
+            errs[r] = ex
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert all(e is None for e in errs), errs
+    for o in outs:
+        for k in ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper"):
+            assert _same(o[k], one[k]), k
