@@ -71,7 +71,17 @@ def measured_gram_traffic(name, world):
     return None, None
 
 
-HBM_PEAK_GBS = 6550.1            # MEASURED_PEAKS.json (driver-written copy bandwidth on this pool)
+def _measured_hbm_peak():
+    """MEASURED_PEAKS.json (driver-written copy bandwidth on this pool); the value it held when this was written if the
+    file is absent."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"])
+    except (OSError, ValueError, KeyError, TypeError):
+        return 6550.1
+
+
+HBM_PEAK_GBS = _measured_hbm_peak()
 FP64_DMMA_PEAK_TFLOPS = 37.1     # measured on this pool (profiles/r01_fp64_peaks.json): DMMA.8x8x4 issue peak
 FP64_CUBLAS_DGEMM_TFLOPS = 35.4  # measured on this pool (profiles/r01_dgemm_peak.json): cuBLAS DGEMM 8192^3
 
