@@ -23,6 +23,8 @@
 #include "common.cuh"
 #include "internal.h"
 
+#include <cstdlib>
+
 #include <cmath>
 
 namespace ob {
@@ -91,8 +93,9 @@ __device__ __noinline__ unsigned poisson_resolve(uint32_t u16, const PoissonDev*
 // occupies slot 0); one Philox4x32-10 call yields the 16-bit uniforms of the 8 stream ids of an aligned octet.
 // SH = (stream id of local slot 0) mod 8, uniform over the launch -> compile-time: a thread's 16 consecutive slots
 // span 2 (SH == 0) or 3 octets.
+// 3 resident blocks per SM (80 registers, no spills): measured 4.5 % faster than 2 (113 registers) and than 4 (64, spills)
 template <typename CountT, int SH>
-__global__ void __launch_bounds__(256) counts_philox_body(CountT* __restrict__ C, long long n, long long n_pad,
+__global__ void __launch_bounds__(256, 3) counts_philox_body(CountT* __restrict__ C, long long n, long long n_pad,
                                                           long long slots, long long rep0, int first_slot, int group,
                                                           uint32_t k0, uint32_t k1, int lambda_zero,
                                                           const unsigned char* __restrict__ lut_g,
