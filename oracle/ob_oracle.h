@@ -157,6 +157,23 @@ int orc_heckman_run(int32_t K, int32_t K1, int32_t ref_kind,
                     double* total_gap, double* rep_stats, int32_t* rep_status, double* rep_gamma_a,
                     int64_t* n_ok, double* se, double* p, double* ci_lo, double* ci_hi, double* t);
 
+/* ---- Machado-Mata quantile decomposition (ob_oracle_mm.c) ----
+ * orc_qr: math/quantile_regression.rs:22-135 (the LP's vertex; c = optional multiplicities, NULL = 1);
+ * info [3] = {interior-point iterations, status 0 vertex verified / 1 interior-point solution only / 2 failed, rows used by the polish}.
+ * orc_mm_pass: run_single_pass, quantile_decomposition.rs:173-279; orc_mm_run: run(), :281-421.  Statistics per pass:
+ * [gap, characteristics, coefficients] per target quantile. */
+int orc_qr(const double* X, const double* y, const double* c, int64_t n, int32_t K, double tau, double* beta, int32_t* info);
+int orc_mm_pass(int32_t K, const double* Xa, const double* ya, int64_t na, const double* Xb, const double* yb, int64_t nb,
+                int32_t sims, const double* taus, const uint32_t* draw_a, const uint32_t* draw_b,
+                int32_t nq, const double* quantiles, double* stats,
+                double* betas_a, double* betas_b, int32_t* qr_status_a, int32_t* qr_status_b, int32_t* nsucc_out);
+int orc_mm_run(int32_t K, const double* Xa, const double* ya, int64_t na, const double* Xb, const double* yb, int64_t nb,
+               int32_t sims, int32_t nq, const double* quantiles, int64_t reps,
+               const uint32_t* idx_a, const uint32_t* idx_b, const double* taus, const uint32_t* draw_a, const uint32_t* draw_b,
+               int nthreads, double* point_stats, double* point_betas_a, double* point_betas_b,
+               double* rep_stats, int32_t* rep_status, int64_t* n_ok,
+               double* se, double* p, double* ci_lo, double* ci_hi, double* t);
+
 /* flatten a pass into the S-vector layout */
 void orc_pass_to_stats(const orc_spec* s, const orc_pass_out* p, double* stats);
 

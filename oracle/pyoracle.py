@@ -23,7 +23,7 @@ ERR_NAMES = {0: "Ok", 1: "PolarsError", 2: "ColumnNotFound", 3: "InvalidGroupVar
 
 def build(force: bool = False) -> str:
     """Compile the oracle (gcc, a second or two).  Building the checker is not using it."""
-    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("ob_oracle.c", "ob_oracle_heckman.c", "ob_oracle.h"))
+    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("ob_oracle.c", "ob_oracle_heckman.c", "ob_oracle_mm.c", "ob_oracle.h"))
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < src_m:
         subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "CC": "gcc"})
     return _LIB_PATH
@@ -318,4 +318,72 @@ def heckman_run(ref_kind, Xa, ya, Za, sa, Xb, yb, Zb, sb, reps, idx_a, idx_b, nt
     for k in ("rep_stats", "rep_status", "rep_gamma_a"):
         out[k] = out[k][:reps]
     out.update(total_gap=gap.value, n_ok=int(nok.value), S=S)
+    return out
+
+
+QR_VERTEX, QR_APPROX, QR_FAILED = 0, 1, 2
+
+
+def qr(X, y, tau: float, c=None):
+    """math/quantile_regression.rs:22-135 -> (beta, info) with info = dict(iters, status, ncand); the LP's vertex."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    cc = None if c is None else np.ascontiguousarray(c, dtype=np.float64)
+    beta = np.full(X.shape[1], np.nan)
+    info = np.zeros(3, dtype=np.int32)
+    lib().orc_qr(_dp(X), _dp(y), _dp(cc), C.c_int64(X.shape[0]), C.c_int32(X.shape[1]), C.c_double(tau), _dp(beta),
+                 info.ctypes.data_as(C.POINTER(C.c_int32)))
+    return beta, dict(iters=int(info[0]), status=int(info[1]), ncand=int(info[2]))
+
+
+def mm_pass(Xa, ya, Xb, yb, taus, draw_a, draw_b, quantiles):
+    """run_single_pass, quantile_decomposition.rs:173-279 -> dict(stats [nq x 3], betas_a, betas_b, status_a, status_b, nsucc)."""
+    Xa, ya, Xb, yb = [np.ascontiguousarray(a, dtype=np.float64) for a in (Xa, ya, Xb, yb)]
+    taus = np.ascontiguousarray(taus, dtype=np.float64)
+    quantiles = np.ascontiguousarray(quantiles, dtype=np.float64)
+    da = np.ascontiguousarray(draw_a, dtype=np.uint32)
+    db = np.ascontiguousarray(draw_b, dtype=np.uint32)
+    K, sims, nq = Xa.shape[1], len(taus), len(quantiles)
+    stats = np.full(3 * nq, np.nan)
+    ba, bb = np.empty((sims, K)), np.empty((sims, K))
+    sa, sb = np.zeros(sims, dtype=np.int32), np.zeros(sims, dtype=np.int32)
+    ns = C.c_int32()
+    U32, I32 = C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+    L = lib()
+    L.orc_mm_pass.restype = C.c_int
+    rc = L.orc_mm_pass(C.c_int32(K), _dp(Xa), _dp(ya), C.c_int64(Xa.shape[0]), _dp(Xb), _dp(yb), C.c_int64(Xb.shape[0]),
+                       C.c_int32(sims), _dp(taus), da.ctypes.data_as(U32), db.ctypes.data_as(U32), C.c_int32(nq), _dp(quantiles),
+                       _dp(stats), _dp(ba), _dp(bb), sa.ctypes.data_as(I32), sb.ctypes.data_as(I32), C.byref(ns))
+    return dict(rc=rc, stats=stats.reshape(nq, 3), betas_a=ba, betas_b=bb, status_a=sa, status_b=sb, nsucc=ns.value)
+
+
+def mm_run(Xa, ya, Xb, yb, sims, quantiles, reps, idx_a, idx_b, taus, draw_a, draw_b, nthreads=8):
+    """QuantileDecompositionBuilder::run, quantile_decomposition.rs:281-421, under explicit streams (see ob_oracle_mm.c)."""
+    Xa, ya, Xb, yb = [np.ascontiguousarray(a, dtype=np.float64) for a in (Xa, ya, Xb, yb)]
+    quantiles = np.ascontiguousarray(quantiles, dtype=np.float64)
+    K, na, nb, nq = Xa.shape[1], Xa.shape[0], Xb.shape[0], len(quantiles)
+    S = 3 * nq
+    taus = np.ascontiguousarray(taus, dtype=np.float64).reshape(reps + 1, sims)
+    da = np.ascontiguousarray(draw_a, dtype=np.uint32).reshape(reps + 1, sims)
+    db = np.ascontiguousarray(draw_b, dtype=np.uint32).reshape(reps + 1, sims)
+    idx_a = np.ascontiguousarray(idx_a if reps else np.zeros((0, na)), dtype=np.uint32)
+    idx_b = np.ascontiguousarray(idx_b if reps else np.zeros((0, nb)), dtype=np.uint32)
+    out = dict(point_stats=np.full(S, np.nan), betas_a=np.empty((sims, K)), betas_b=np.empty((sims, K)),
+               rep_stats=np.full((max(reps, 1), S), np.nan), rep_status=np.zeros(max(reps, 1), dtype=np.int32),
+               se=np.empty(S), p=np.empty(S), ci_lo=np.empty(S), ci_hi=np.empty(S), t=np.empty(S))
+    nok = C.c_int64()
+    U32 = C.POINTER(C.c_uint32)
+    L = lib()
+    L.orc_mm_run.restype = C.c_int
+    rc = L.orc_mm_run(C.c_int32(K), _dp(Xa), _dp(ya), C.c_int64(na), _dp(Xb), _dp(yb), C.c_int64(nb), C.c_int32(sims), C.c_int32(nq),
+                      _dp(quantiles), C.c_int64(reps), idx_a.ctypes.data_as(U32), idx_b.ctypes.data_as(U32), _dp(taus),
+                      da.ctypes.data_as(U32), db.ctypes.data_as(U32), C.c_int(nthreads), _dp(out["point_stats"]),
+                      _dp(out["betas_a"]), _dp(out["betas_b"]), _dp(out["rep_stats"]),
+                      out["rep_status"].ctypes.data_as(C.POINTER(C.c_int32)), C.byref(nok), _dp(out["se"]), _dp(out["p"]),
+                      _dp(out["ci_lo"]), _dp(out["ci_hi"]), _dp(out["t"]))
+    if rc != 0:
+        raise OracleError(rc)
+    for k in ("rep_stats", "rep_status"):
+        out[k] = out[k][:reps]
+    out.update(n_ok=int(nok.value), S=S)
     return out
