@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define OBBOOT_ABI_VERSION 5
+#define OBBOOT_ABI_VERSION 6
 
 /* ---- errors: OaxacaError variants (error.rs:6-19) + device errors ------------------------- */
 typedef enum ob_status {
@@ -273,6 +273,63 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* design, const ob_boot_o
 ob_status ob_reduce_stats(ob_ctx* ctx, const double* rep_stats, const int32_t* rep_status, int64_t reps, int32_t S,
                           const double* point_stats, int64_t* n_ok, double* std_err, double* p_value,
                           double* ci_lower, double* ci_upper, double* t_stat);
+
+/* ---- Machado-Mata quantile decomposition ------------------------------------------------
+ * QuantileDecompositionBuilder::run (quantile_decomposition.rs:281-421) from the group split on: the point pass and every
+ * bootstrap pass (resample both groups with replacement, :337-354) fit `simulations` quantile regressions per group at
+ * random quantiles tau ~ U(0.01, 0.99) (run_single_pass, :173-279; solve_qr, math/quantile_regression.rs:22-135), simulate
+ * y_aa = x_a'beta_a(tau), y_bb = x_b'beta_b(tau), y_ab = x_a'beta_b(tau) on one randomly drawn row of each group per
+ * simulation, and difference their empirical quantiles (:164-171) at the target quantiles:
+ *   statistics per pass  S = 3 n_quantiles:  [gap = q_aa - q_bb, characteristics = q_ab - q_bb, coefficients = q_aa - q_ab]
+ * per target quantile, reduced over the passes by bootstrap_stats (inference.rs:4-34; t = estimate / se when |se| > 1e-9).
+ * A pass is a column of the multiplicity matrix ob_bootstrap_run builds; each regression is solved on the device to the
+ * LP's optimal vertex (interior point + polish, csrc/mm.cu) -- the reference's clarabel solution is that vertex up to the
+ * solver's tolerance.  A regression that does not converge is dropped like a non-Solved clarabel status (:227-236), a
+ * pass with fewer than simulations / 2 fits in a group fails (:238-242) and is dropped from the reduction (:350-353);
+ * on the point pass that is OB_ERR_NALGEBRA.  The design must be unweighted with one raw outcome (the Machado-Mata
+ * builder has neither weights nor a RIF), K <= 47 columns; row-sharded designs are refused.
+ * Test-only explicit streams (the reference's are unseeded thread_rng draws): idx_a / idx_b as in ob_boot_opts; taus
+ * [(reps + 1) x simulations], pass 0 = point estimates; draw_a / draw_b [(reps + 1) x simulations] = position of the
+ * simulated row in the pass's (resampled) group frame (needs idx_* when reps > 0).  NULL = native Philox streams. */
+typedef struct ob_mm_opts {
+    int32_t simulations;             /* builder default 200 (quantile_decomposition.rs:58), <= 4096 */
+    int32_t n_quantiles;
+    const double* quantiles;         /* builder default 0.1 0.25 0.5 0.75 0.9 (:57) */
+    int64_t reps;                    /* bootstrap_reps, builder default 20 (:59) */
+    uint64_t seed;
+    const uint32_t* idx_a;
+    const uint32_t* idx_b;
+    const double* taus;
+    const uint32_t* draw_a;
+    const uint32_t* draw_b;
+    int64_t rep_begin;               /* replicate shard as in ob_boot_opts (rep_end = 0: all) */
+    int64_t rep_end;
+    int32_t skip_reduce;
+    int32_t count_bits;              /* 0 auto, 8 or 16 */
+    int64_t max_workspace_bytes;     /* 0 = default (60% of free HBM) */
+    int32_t shard_replicates;        /* mode R inside the library, as in ob_boot_opts */
+} ob_mm_opts;
+
+typedef struct ob_mm_result {
+    double* point_stats;             /* [n_quantiles x 3] */
+    int64_t n_ok;
+    double* std_err;                 /* [n_quantiles x 3] each */
+    double* p_value;
+    double* ci_lower;
+    double* ci_upper;
+    double* t_stat;
+    double* rep_stats;               /* [rows x n_quantiles x 3] optional, NaN rows for failed passes */
+    int32_t* rep_status;             /* [rows] optional */
+    double* point_betas_a;           /* [simulations x K] optional: the point pass's fitted coefficients (NaN rows = failed) */
+    double* point_betas_b;
+    int32_t* point_qr_info_a;        /* [simulations] optional: status (0 vertex verified, 1 interior-point solution only, */
+    int32_t* point_qr_info_b;        /*   2 failed) | interior-point iterations << 8 | rows used by the polish << 16 */
+    int64_t qr_total, qr_vertex, qr_approx, qr_failed, qr_iterations;   /* over the regressions of this call */
+    double ms_counts, ms_qr, ms_effects, ms_reduce, ms_total;
+    int32_t gpu_launches;
+} ob_mm_result;
+
+ob_status ob_mm_run(ob_ctx* ctx, const ob_design* design, const ob_mm_opts* opts, ob_mm_result* res);
 
 /* ---- multi-GPU ---------------------------------------------------------------------------------
  * Mode R (replicate sharding, the default): every GPU holds the whole design.  With a communicator attached to the

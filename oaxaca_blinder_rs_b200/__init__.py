@@ -5,9 +5,9 @@ decompose_quantile).  The compute path is hand-written sm_100a CUDA behind the C
 include/obboot.h; this package is the host-side mirror of the reference's interface.
 """
 from .core import (REF_GROUP_A, REF_GROUP_B, REF_POOLED, REF_WEIGHTED, Context, Design, NormVar,
-                   OaxacaError, PinnedBuffer, bootstrap, num_stats, pin_in_place, reduce_stats, replicate_shard, unpin)
+                   OaxacaError, PinnedBuffer, bootstrap, machado_mata, num_stats, pin_in_place, reduce_stats, replicate_shard, unpin)
 
 from .builder import ComponentResult, OaxacaBlinder, OaxacaBuilder, OaxacaResults, ReferenceCoefficients, read_csv
 
 __all__ = ["ComponentResult", "OaxacaBlinder", "OaxacaBuilder", "OaxacaResults", "ReferenceCoefficients", "REF_GROUP_A", "REF_GROUP_B", "REF_POOLED", "REF_WEIGHTED", "Context", "Design", "NormVar",
-           "OaxacaError", "PinnedBuffer", "pin_in_place", "unpin", "replicate_shard", "bootstrap", "num_stats", "reduce_stats", "read_csv"]
+           "OaxacaError", "PinnedBuffer", "pin_in_place", "unpin", "replicate_shard", "bootstrap", "machado_mata", "num_stats", "reduce_stats", "read_csv"]

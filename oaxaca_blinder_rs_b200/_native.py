@@ -29,7 +29,8 @@ SYMBOLS = ["ob_abi_version", "ob_device_count", "ob_ctx_create", "ob_ctx_destroy
            "ob_debug_gram_schedule", "ob_debug_counts_from_indices", "ob_host_alloc", "ob_host_free",
            "ob_host_register", "ob_host_unregister", "ob_replicate_shard", "ob_design_pack_async", "ob_design_wait",
            "ob_design_redistribute_rows", "ob_design_row_shard", "ob_design_apply_rif_multi", "ob_design_num_outcomes",
-           "ob_design_pack_row_shard_async", "ob_design_attach_selection", "ob_design_selection_cols", "ob_num_stats_heckman"]
+           "ob_design_pack_row_shard_async", "ob_design_attach_selection", "ob_design_selection_cols", "ob_num_stats_heckman",
+           "ob_mm_run"]
 
 
 class FrameView(C.Structure):
@@ -72,6 +73,22 @@ class Result(C.Structure):
                 ("ms_counts", C.c_double), ("ms_gram", C.c_double), ("ms_solve", C.c_double),
                 ("ms_reduce", C.c_double), ("ms_total", C.c_double), ("ms_gram_kernel", C.c_double),
                 ("gpu_launches", C.c_int32), ("ms_comm", C.c_double), ("total_gap_multi", _DP), ("sel_gamma_a", _DP), ("sel_gamma_b", _DP)]
+
+
+class MmOpts(C.Structure):
+    _fields_ = [("simulations", C.c_int32), ("n_quantiles", C.c_int32), ("quantiles", _DP), ("reps", C.c_int64),
+                ("seed", C.c_uint64), ("idx_a", _U32P), ("idx_b", _U32P), ("taus", _DP), ("draw_a", _U32P), ("draw_b", _U32P),
+                ("rep_begin", C.c_int64), ("rep_end", C.c_int64), ("skip_reduce", C.c_int32), ("count_bits", C.c_int32),
+                ("max_workspace_bytes", C.c_int64), ("shard_replicates", C.c_int32)]
+
+
+class MmResult(C.Structure):
+    _fields_ = [("point_stats", _DP), ("n_ok", C.c_int64), ("std_err", _DP), ("p_value", _DP), ("ci_lower", _DP),
+                ("ci_upper", _DP), ("t_stat", _DP), ("rep_stats", _DP), ("rep_status", _IP), ("point_betas_a", _DP),
+                ("point_betas_b", _DP), ("point_qr_info_a", _IP), ("point_qr_info_b", _IP), ("qr_total", C.c_int64),
+                ("qr_vertex", C.c_int64), ("qr_approx", C.c_int64), ("qr_failed", C.c_int64), ("qr_iterations", C.c_int64),
+                ("ms_counts", C.c_double), ("ms_qr", C.c_double), ("ms_effects", C.c_double), ("ms_reduce", C.c_double),
+                ("ms_total", C.c_double), ("gpu_launches", C.c_int32)]
 
 
 def build(force: bool = False) -> str:
@@ -156,6 +173,7 @@ def lib() -> C.CDLL:
         L.ob_host_free.restype = None
         L.ob_host_register.argtypes = [C.c_void_p, C.c_size_t]
         L.ob_host_unregister.argtypes = [C.c_void_p]
+        L.ob_mm_run.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(MmOpts), C.POINTER(MmResult)]
         L.ob_replicate_shard.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         _lib = L
     return _lib

@@ -514,6 +514,74 @@ def bootstrap(design: Design, reps: int, ref_kind: int = REF_GROUP_A, norm: Sequ
     return out
 
 
+QR_VERTEX, QR_APPROX, QR_FAILED = 0, 1, 2
+
+
+def machado_mata(design: Design, quantiles: Sequence[float] = (0.1, 0.25, 0.5, 0.75, 0.9), simulations: int = 200,
+                 reps: int = 20, seed: int = 0, idx_a=None, idx_b=None, taus=None, draw_a=None, draw_b=None,
+                 rep_begin: int = 0, rep_end: int = 0, skip_reduce: bool = False, count_bits: int = 0,
+                 max_workspace_bytes: int = 0, want_rep: bool = False, want_betas: bool = False,
+                 shard_replicates: bool = False) -> dict:
+    """ob_mm_run: the Machado-Mata quantile decomposition (QuantileDecompositionBuilder::run,
+    quantile_decomposition.rs:281-421) on a packed design.  Statistics per target quantile: (gap, characteristics,
+    coefficients).  Explicit streams (tests): idx_a / idx_b [reps x n_g]; taus, draw_a, draw_b [(reps + 1) x simulations]
+    (row 0 = the point pass; draws are positions in the pass's resampled group frame)."""
+    ctx, K = design.ctx, design.K
+    q = np.ascontiguousarray(quantiles, dtype=np.float64)
+    nq, S = len(q), 3 * len(q)
+    o = N.MmOpts()
+    o.simulations, o.n_quantiles, o.quantiles, o.reps, o.seed = simulations, nq, _dp(q), reps, seed
+    keep = []
+    if idx_a is not None:
+        idx_a = np.ascontiguousarray(idx_a, dtype=np.uint32)
+        idx_b = np.ascontiguousarray(idx_b, dtype=np.uint32)
+        assert idx_a.shape == (reps, design.n_a_global) and idx_b.shape == (reps, design.n_b_global)
+        o.idx_a, o.idx_b = idx_a.ctypes.data_as(N._U32P), idx_b.ctypes.data_as(N._U32P)
+    if taus is not None:
+        taus = np.ascontiguousarray(taus, dtype=np.float64)
+        assert taus.shape == (reps + 1, simulations)
+        o.taus = _dp(taus)
+    if draw_a is not None:
+        draw_a = np.ascontiguousarray(draw_a, dtype=np.uint32)
+        draw_b = np.ascontiguousarray(draw_b, dtype=np.uint32)
+        assert draw_a.shape == (reps + 1, simulations) and draw_b.shape == (reps + 1, simulations)
+        o.draw_a, o.draw_b = draw_a.ctypes.data_as(N._U32P), draw_b.ctypes.data_as(N._U32P)
+    keep += [idx_a, idx_b, taus, draw_a, draw_b]
+    o.rep_begin, o.rep_end = rep_begin, rep_end
+    o.skip_reduce, o.count_bits, o.max_workspace_bytes = int(skip_reduce), count_bits, max_workspace_bytes
+    o.shard_replicates = int(shard_replicates)
+    nrep = (rep_end if rep_end > 0 else reps) - rep_begin
+    r = N.MmResult()
+    a = dict(point_stats=np.empty(S), std_err=np.full(S, np.nan), p_value=np.full(S, np.nan), ci_lower=np.full(S, np.nan),
+             ci_upper=np.full(S, np.nan), t_stat=np.zeros(S))
+    if want_rep or skip_reduce:
+        a["rep_stats"] = np.empty((max(nrep, 1), S))
+        a["rep_status"] = np.zeros(max(nrep, 1), dtype=np.int32)
+    if want_betas:
+        a["point_betas_a"], a["point_betas_b"] = np.empty((simulations, K)), np.empty((simulations, K))
+        a["point_qr_info_a"], a["point_qr_info_b"] = np.zeros(simulations, dtype=np.int32), np.zeros(simulations, dtype=np.int32)
+    for k, v in a.items():
+        setattr(r, k, _ip(v) if v.dtype == np.int32 else _dp(v))
+    try:
+        ctx.check(N.lib().ob_mm_run(ctx._h, design._h, C.byref(o), C.byref(r)))
+    finally:
+        design._inflight = None
+    out = dict(a)
+    for k in ("rep_stats", "rep_status"):
+        if k in out:
+            out[k] = out[k][:nrep]
+    for k in ("point_stats", "std_err", "p_value", "ci_lower", "ci_upper", "t_stat"):
+        out[k] = out[k].reshape(nq, 3)
+    if "rep_stats" in out:
+        out["rep_stats"] = out["rep_stats"].reshape(-1, nq, 3)
+    out.update(n_ok=int(r.n_ok), S=S, quantiles=q,
+               qr=dict(total=int(r.qr_total), vertex=int(r.qr_vertex), approx=int(r.qr_approx), failed=int(r.qr_failed),
+                       iterations=int(r.qr_iterations)),
+               timings_ms=dict(counts=r.ms_counts, qr=r.ms_qr, effects=r.ms_effects, reduce=r.ms_reduce, total=r.ms_total),
+               gpu_launches=int(r.gpu_launches))
+    return out
+
+
 def reduce_stats(ctx: Context, rep_stats, rep_status, point_stats) -> dict:
     """ob_reduce_stats on host arrays gathered from several shards (replicate order)."""
     rep_stats = np.ascontiguousarray(rep_stats, dtype=np.float64)

@@ -1580,9 +1580,267 @@ void heckman_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_resu
     t_total.collect();
 }
 
+
+// ob_mm_run: the Machado-Mata passes (mm.cu) over columns of the same multiplicity matrix as the OLS bootstrap.
+void mm_run(ob_ctx* ctx, const ob_design* d, const ob_mm_opts* o, ob_mm_result* res) {
+    cudaStream_t st = ctx->stream;
+    const int K = d->K, sims = o->simulations, nq = o->n_quantiles, S = 3 * nq;
+    if (sims < 1 || sims > MM_MAX_SIMS) fail(OB_ERR_INVALID_ARG, "simulations must be in [1, 4096]");
+    if (nq < 1 || nq > 1024 || !o->quantiles) fail(OB_ERR_INVALID_ARG, "n_quantiles must be in [1, 1024]");
+    if (o->reps < 0) fail(OB_ERR_INVALID_ARG, "negative reps");
+    if (K > MM_MAX_COLS) fail(OB_ERR_UNSUPPORTED, "Machado-Mata: more than 47 design columns");
+    if (d->weighted) fail(OB_ERR_UNSUPPORTED, "Machado-Mata on a weighted design (QuantileDecompositionBuilder has no weights)");
+    if (d->T != 1 || d->g[0].y_raw || d->g[1].y_raw) fail(OB_ERR_UNSUPPORTED, "Machado-Mata needs the raw outcome (the design carries RIF outcomes)");
+    if (d->world > 1) fail(OB_ERR_UNSUPPORTED, "Machado-Mata on a row-sharded design");
+    if (d->g[0].n < 2 || d->g[1].n < 2) fail(OB_ERR_INVALID_GROUP, "Invalid group variable: One group has insufficient data");   // :210-214
+    const bool shard_reps = o->shard_replicates != 0 && ctx->comm && ctx->comm->world > 1;
+    if (shard_reps && (o->rep_begin != 0 || o->rep_end != 0 || o->skip_reduce))
+        fail(OB_ERR_INVALID_ARG, "shard_replicates computes the shard itself: rep_begin / rep_end / skip_reduce must be 0");
+    int64_t rb = o->rep_begin, re = o->rep_end > 0 ? o->rep_end : o->reps;
+    if (shard_reps) ob_replicate_shard(o->reps, ctx->comm->world, ctx->comm->rank, &rb, &re);
+    if (rb < 0 || re < rb || re > o->reps) fail(OB_ERR_INVALID_ARG, "bad replicate shard");
+    const int64_t nrep = re - rb;
+    const bool index_mode = o->idx_a != nullptr || o->idx_b != nullptr;
+    if (index_mode && nrep > 0 && (!o->idx_a || !o->idx_b)) fail(OB_ERR_INVALID_ARG, "index stream needs both idx_a and idx_b");
+    const bool draws_given = o->draw_a != nullptr || o->draw_b != nullptr;
+    if (draws_given && (!o->draw_a || !o->draw_b)) fail(OB_ERR_INVALID_ARG, "simulated-row stream needs both draw_a and draw_b");
+    if (draws_given && nrep > 0 && !index_mode)
+        fail(OB_ERR_INVALID_ARG, "draw_a / draw_b are positions in the resampled frames: they need the explicit resample stream idx_a / idx_b");
+    if (o->count_bits != 0 && o->count_bits != 8 && o->count_bits != 16) fail(OB_ERR_INVALID_ARG, "count_bits must be 0, 8 or 16");
+    for (int q = 0; q < nq; ++q)
+        if (!(o->quantiles[q] >= 0.0 && o->quantiles[q] <= 1.0)) fail(OB_ERR_INVALID_ARG, "target quantiles must lie in [0, 1]");
+    int count_bytes = o->count_bits == 16 ? 2 : 1;
+
+    res->ms_counts = res->ms_qr = res->ms_effects = res->ms_reduce = res->ms_total = 0.0;
+    res->gpu_launches = 0; res->n_ok = 0;
+    res->qr_total = res->qr_vertex = res->qr_approx = res->qr_failed = res->qr_iterations = 0;
+    Timer t_total(st, &res->ms_total);
+    const int64_t slots = 1 + nrep, panels_total = (slots + BM - 1) / BM;
+    const int64_t n_pad[2] = {d->g[0].n_pad, d->g[1].n_pad}, n_g[2] = {d->g[0].n, d->g[1].n};
+    DevBuf d_stats(sizeof(double) * (size_t)slots * S), d_status(sizeof(int) * (size_t)slots);
+    DevBuf d_q(sizeof(double) * (size_t)nq), d_flags(sizeof(int) * 4), d_lut(2 * counts_lut_bytes()), d_counter(sizeof(int));
+    OB_CUDA(cudaMemcpyAsync(d_q.p, o->quantiles, sizeof(double) * (size_t)nq, cudaMemcpyHostToDevice, st));
+    const int64_t stride = (std::max(n_g[0], n_g[1]) + 31) / 32 * 32;
+    std::vector<int> h_info;
+    std::vector<double> h_taus;
+    std::vector<uint32_t> h_rows[2];
+
+    auto run_batches = [&] {
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        size_t free_b = 0, total_b = 0;
+        OB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const double budget = o->max_workspace_bytes > 0 ? (double)o->max_workspace_bytes : 0.6 * ((double)free_b + (double)pool_idle_bytes(ctx));
+        // blocks in flight: two per SM unless their iterate slabs (6 vectors of the larger group) would take more than
+        // half of the budget
+        const double slab = 8.0 * mm_state_vectors() * (double)stride;
+        int grid = ctx->num_sms * mm_blocks_per_sm(K);
+        grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, (int64_t)std::floor(0.5 * budget / slab)));
+        const double per_panel = (double)(n_pad[0] + n_pad[1]) * BM * count_bytes + (index_mode ? (double)(n_g[0] + n_g[1]) * BM * 4.0 : 0.0) +
+                                 (double)BM * sims * (2.0 * K * 8.0 + 2.0 * 4.0 + 8.0 + 8.0);
+        int64_t ppb = std::max<int64_t>(1, std::min<int64_t>((int64_t)std::floor((budget - grid * slab) / per_panel), panels_total));
+        DevBuf d_C[2], d_idx[2], d_colsum(sizeof(long long) * 2 * (size_t)ppb * BM);
+        for (int g = 0; g < 2; ++g) d_C[g].alloc((size_t)ppb * n_pad[g] * BM * count_bytes);
+        const size_t bs_max = (size_t)std::min<int64_t>(ppb * BM, slots);
+        DevBuf d_state(sizeof(double) * (size_t)mm_state_vectors() * (size_t)stride * (size_t)grid);
+        DevBuf d_betas(sizeof(double) * 2 * bs_max * sims * K), d_info(sizeof(int) * 2 * bs_max * sims);
+        DevBuf d_taus(sizeof(double) * bs_max * sims), d_rows_a(sizeof(uint32_t) * bs_max * sims), d_rows_b(sizeof(uint32_t) * bs_max * sims);
+        bool saturated = false;
+        for (int64_t p0 = 0; p0 < panels_total && !saturated; p0 += ppb) {
+            const int64_t pn = std::min(ppb, panels_total - p0);
+            const int64_t slot_lo = p0 * BM, slot_hi = std::min(slots, (p0 + pn) * BM), bslots = slot_hi - slot_lo;
+            const int first_slot = p0 == 0 ? 1 : 0;
+            const int64_t brep = bslots - first_slot, rep0 = rb + slot_lo - 1;
+            OB_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int) * 4, st));
+            // (1) the passes' multiplicity columns: the same replicate generation as ob_bootstrap_run
+            Timer t_counts(st, &res->ms_counts);
+            CountsArgs ca[2];
+            for (int g = 0; g < 2; ++g) {
+                ca[g].C = d_C[g].p; ca[g].count_bytes = count_bytes; ca[g].n = n_g[g]; ca[g].n_pad = n_pad[g];
+                ca[g].n_global = n_g[g]; ca[g].row_begin = 0; ca[g].panels = (int)pn; ca[g].slots = bslots;
+                ca[g].first_slot = first_slot; ca[g].rep0 = rep0; ca[g].group = g; ca[g].seed = o->seed;
+            }
+            if (index_mode) {
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t* h = g == 0 ? o->idx_a : o->idx_b;
+                    const size_t nb = sizeof(uint32_t) * (size_t)std::max<int64_t>(brep, 1) * n_g[g];
+                    if (d_idx[g].bytes < nb) d_idx[g].alloc(nb);
+                    if (brep > 0) OB_CUDA(cudaMemcpyAsync(d_idx[g].p, h + (size_t)(rep0 + first_slot) * n_g[g], sizeof(uint32_t) * (size_t)brep * n_g[g], cudaMemcpyHostToDevice, st));
+                    counts_from_indices(ca[g], d_idx[g].as<uint32_t>(), d_flags.as<int>(), st);
+                    res->gpu_launches += 2;
+                }
+            } else {
+                OB_CUDA(cudaMemsetAsync(d_colsum.p, 0, d_colsum.bytes, st));
+                for (int g = 0; g < 2; ++g) {
+                    counts_philox_body_launch(ca[g], d_colsum.as<long long>() + (size_t)g * ppb * BM, d_lut.as<unsigned char>() + (size_t)g * counts_lut_bytes(), st);
+                    counts_philox_fixup_launch(ca[g], d_colsum.as<long long>() + (size_t)g * ppb * BM, d_flags.as<int>(), st);
+                    res->gpu_launches += 3;
+                }
+            }
+            t_counts.stop();
+            // (2) random quantiles and simulated rows of the batch's passes
+            MmArgs ma;
+            for (int g = 0; g < 2; ++g) { ma.X[g] = d->g[g].X; ma.C[g] = d_C[g].p; ma.n[g] = n_g[g]; ma.n_pad[g] = n_pad[g]; }
+            ma.ldx = d->ldx; ma.K = K; ma.count_bytes = count_bytes; ma.sims = sims; ma.slots = bslots;
+            ma.taus = d_taus.as<double>(); ma.state = d_state.as<double>(); ma.state_stride = stride;
+            ma.betas = d_betas.as<double>(); ma.info = d_info.as<int>(); ma.counter = d_counter.as<int>();
+            // global pass ids: 0 = point estimates (slot 0 of the first batch), r + 1 = replicate r.  With a replicate shard
+            // the batch's slots 1.. are replicates rb.., so consecutive only from slot 1 on: the point slot is special-cased
+            const int64_t gpass0 = rep0 + 1;          // pass id slot 0 of this batch WOULD have as a replicate slot
+            if (!o->taus || !draws_given) {
+                mm_streams_launch(ma, gpass0, first_slot, o->seed, d_taus.as<double>(), d_rows_a.as<uint32_t>(), d_rows_b.as<uint32_t>(), st);
+                res->gpu_launches += 1;
+            }
+            if (o->taus) {      // explicit quantiles: rows of the [(reps + 1) x sims] table, row 0 = point pass, row r + 1 = replicate r
+                h_taus.resize((size_t)bslots * sims);
+                for (int64_t s_ = 0; s_ < bslots; ++s_) {
+                    const int64_t pass = (p0 == 0 && s_ == 0) ? 0 : rep0 + s_ + 1;
+                    memcpy(h_taus.data() + (size_t)s_ * sims, o->taus + (size_t)pass * sims, sizeof(double) * (size_t)sims);
+                }
+                OB_CUDA(cudaMemcpyAsync(d_taus.p, h_taus.data(), sizeof(double) * h_taus.size(), cudaMemcpyHostToDevice, st));
+            }
+            if (draws_given) {  // positions in the resampled frame -> original rows through the resample stream
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t* dr = g == 0 ? o->draw_a : o->draw_b;
+                    const uint32_t* ix = g == 0 ? o->idx_a : o->idx_b;
+                    h_rows[g].resize((size_t)bslots * sims);
+                    for (int64_t s_ = 0; s_ < bslots; ++s_) {
+                        const int64_t pass = (p0 == 0 && s_ == 0) ? 0 : rep0 + s_ + 1;
+                        for (int i = 0; i < sims; ++i) {
+                            const uint32_t pos = dr[(size_t)pass * sims + i];
+                            if ((int64_t)pos >= n_g[g]) fail(OB_ERR_INVALID_ARG, "simulated-row position out of range");
+                            h_rows[g][(size_t)s_ * sims + i] = pass == 0 ? pos : ix[(size_t)(pass - 1) * n_g[g] + pos];
+                        }
+                    }
+                    OB_CUDA(cudaMemcpyAsync((g == 0 ? d_rows_a : d_rows_b).p, h_rows[g].data(), sizeof(uint32_t) * h_rows[g].size(), cudaMemcpyHostToDevice, st));
+                }
+            }
+            // (3) the quantile regressions: one block per (group, pass, simulation)
+            Timer t_qr(st, &res->ms_qr);
+            OB_CUDA(cudaMemsetAsync(d_counter.p, 0, sizeof(int), st));
+            const int64_t nprob = 2 * bslots * sims;
+            mm_qr_launch(ma, (int)std::min<int64_t>(grid, nprob), st);
+            res->gpu_launches += 1;
+            t_qr.stop();
+            // (4) simulation, empirical quantiles, effects
+            Timer t_eff(st, &res->ms_effects);
+            mm_effects_launch(ma, d_rows_a.as<uint32_t>(), d_rows_b.as<uint32_t>(), nq, d_q.as<double>(), d_stats.as<double>() + (size_t)slot_lo * S,
+                              d_status.as<int>() + slot_lo, nullptr, st);
+            res->gpu_launches += 1;
+            t_eff.stop();
+            int flags[4];
+            h_info.resize((size_t)2 * bslots * sims);
+            OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
+            OB_CUDA(cudaMemcpyAsync(h_info.data(), d_info.p, sizeof(int) * h_info.size(), cudaMemcpyDeviceToHost, st));
+            if (p0 == 0) {
+                const size_t nb = sizeof(double) * (size_t)sims * K;
+                if (res->point_betas_a) OB_CUDA(cudaMemcpyAsync(res->point_betas_a, d_betas.p, nb, cudaMemcpyDeviceToHost, st));
+                if (res->point_betas_b) OB_CUDA(cudaMemcpyAsync(res->point_betas_b, d_betas.as<double>() + (size_t)bslots * sims * K, nb, cudaMemcpyDeviceToHost, st));
+            }
+            OB_CUDA(cudaStreamSynchronize(st));
+            t_counts.collect(); t_qr.collect(); t_eff.collect();
+            if (flags[2]) fail(OB_ERR_INVALID_ARG, "resample index out of range");
+            if (flags[0]) fail(OB_ERR_CUDA, "Poisson body overshot n (probability < 1e-15 per replicate); rerun with another seed");
+            if (flags[1]) {
+                if (count_bytes == 2 || o->count_bits == 8) fail(OB_ERR_UNSUPPORTED, "row multiplicity overflows the count width");
+                saturated = true;
+                break;
+            }
+            for (size_t i = 0; i < h_info.size(); ++i) {
+                const int st_ = h_info[i] & 0xff;
+                ++res->qr_total;
+                if (st_ == 0) ++res->qr_vertex; else if (st_ == 1) ++res->qr_approx; else ++res->qr_failed;
+                res->qr_iterations += (h_info[i] >> 8) & 0xff;
+            }
+            if (p0 == 0) {
+                if (res->point_qr_info_a) memcpy(res->point_qr_info_a, h_info.data(), sizeof(int) * (size_t)sims);
+                if (res->point_qr_info_b) memcpy(res->point_qr_info_b, h_info.data() + (size_t)bslots * sims, sizeof(int) * (size_t)sims);
+            }
+        }
+        if (!saturated) break;
+        count_bytes = 2;
+        res->ms_counts = res->ms_qr = res->ms_effects = 0.0;
+        res->qr_total = res->qr_vertex = res->qr_approx = res->qr_failed = res->qr_iterations = 0;
+    }
+    int point_status = 0;
+    OB_CUDA(cudaMemcpyAsync(&point_status, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OB_CUDA(cudaStreamSynchronize(st));
+    if (point_status != OB_OK)
+        fail(OB_ERR_NALGEBRA, "Nalgebra error: Failed to estimate a sufficient number of quantile regressions.");      // :238-242
+    };   // run_batches
+    if (shard_reps) {      // all ranks leave together (see ob_bootstrap_run)
+        int rc = OB_OK; std::string msg;
+        try { run_batches(); } catch (const StatusError& e) { rc = e.code; msg = e.msg; }
+        DevBuf d_rc(sizeof(int));
+        int agreed = rc;
+        OB_CUDA(cudaMemcpyAsync(d_rc.p, &agreed, sizeof(int), cudaMemcpyHostToDevice, st));
+        ctx->comm->allreduce(d_rc.p, 1, CommDType::I32, CommOp::MAX, st);
+        OB_CUDA(cudaMemcpyAsync(&agreed, d_rc.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        if (rc != OB_OK) fail((ob_status)rc, msg);
+        if (agreed != OB_OK) fail((ob_status)agreed, std::string("another rank of the replicate-sharded run failed: ") + status_text(agreed));
+    } else {
+        run_batches();
+    }
+    if (res->point_stats) OB_CUDA(cudaMemcpyAsync(res->point_stats, d_stats.p, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
+    const int64_t reps_all = shard_reps ? o->reps : nrep;
+    DevBuf d_gstats, d_gstatus;
+    const double* stats_rows = d_stats.as<double>() + S;
+    const int* status_rows = d_status.as<int>() + 1;
+    if (shard_reps) {      // pass rows of all ranks, device to device, into global replicate order
+        Comm* cm = ctx->comm.get();
+        const int w = cm->world;
+        std::vector<size_t> off(w), sz(w);
+        auto gather_rows = [&](const void* mine, DevBuf& all, size_t row_bytes) {
+            all.alloc(row_bytes * (size_t)std::max<int64_t>(reps_all, 1));
+            for (int r = 0; r < w; ++r) {
+                int64_t b = 0, e = 0;
+                ob_replicate_shard(o->reps, w, r, &b, &e);
+                off[r] = (size_t)b * row_bytes; sz[r] = (size_t)(e - b) * row_bytes;
+            }
+            cm->allgatherv(mine, all.p, off.data(), sz.data(), st);
+        };
+        gather_rows(stats_rows, d_gstats, sizeof(double) * (size_t)S);
+        gather_rows(status_rows, d_gstatus, sizeof(int));
+        stats_rows = d_gstats.as<double>(); status_rows = d_gstatus.as<int>();
+    }
+    if (!o->skip_reduce) {
+        DevBuf d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long)), d_rs(reduce_stats_scratch_bytes(reps_all, S));
+        Timer t_red(st, &res->ms_reduce);
+        reduce_stats_launch(stats_rows, status_rows, reps_all, S, d_stats.as<double>(), d_out.as<double>(),
+                            d_nok.as<long long>(), st, d_rs.as<double>());
+        res->gpu_launches += 1;
+        t_red.stop();
+        std::vector<double> out5(5 * (size_t)S);
+        long long nok = 0;
+        OB_CUDA(cudaMemcpyAsync(out5.data(), d_out.p, d_out.bytes, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaMemcpyAsync(&nok, d_nok.p, sizeof nok, cudaMemcpyDeviceToHost, st));
+        OB_CUDA(cudaStreamSynchronize(st));
+        t_red.collect();
+        res->n_ok = nok;
+        double* dst[5] = {res->std_err, res->p_value, res->ci_lower, res->ci_upper, res->t_stat};
+        for (int k = 0; k < 5; ++k)
+            if (dst[k]) memcpy(dst[k], out5.data() + (size_t)k * S, sizeof(double) * S);
+    }
+    if (reps_all > 0) {
+        if (res->rep_stats) OB_CUDA(cudaMemcpyAsync(res->rep_stats, stats_rows, sizeof(double) * (size_t)reps_all * S, cudaMemcpyDeviceToHost, st));
+        if (res->rep_status) OB_CUDA(cudaMemcpyAsync(res->rep_status, status_rows, sizeof(int) * (size_t)reps_all, cudaMemcpyDeviceToHost, st));
+    }
+    t_total.stop();
+    OB_CUDA(cudaStreamSynchronize(st));
+    t_total.collect();
+}
+
 }  // namespace
 
 extern "C" {
+
+ob_status ob_mm_run(ob_ctx* ctx, const ob_design* d, const ob_mm_opts* o, ob_mm_result* res) {
+    if (!ctx || !d || !o || !res) return OB_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        design_ready(d);
+        mm_run(ctx, d, o, res);
+    });
+}
 
 ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_result* res) {
     if (!ctx || !d || !o || !res) return OB_ERR_INVALID_ARG;

@@ -322,6 +322,29 @@ struct HkSolveArgs {
 };
 void hk_solve_launch(const HkSolveArgs& a, cudaStream_t st);
 
+// ---- mm.cu: Machado-Mata quantile decomposition ----
+constexpr int MM_MAX_COLS = 47;      // design columns incl. the intercept
+constexpr int MM_MAX_SIMS = 4096;    // simulations per pass (the effects kernel sorts them in shared memory)
+struct MmArgs {
+    const double* X[2]; const void* C[2]; int64_t n[2], n_pad[2];   // unweighted designs, multiplicity matrices of this batch
+    int ldx, K, count_bytes, sims;
+    int64_t slots;                   // passes (columns of the multiplicity matrix) in this batch
+    const double* taus;              // [slots][sims] the random quantiles of every pass
+    double* state; int64_t state_stride;     // per block mm_state_vectors() vectors of state_stride doubles
+    double* betas; int* info;        // [2][slots][sims][K], [2][slots][sims] (status | iterations << 8 | candidates << 16)
+    int* counter;                    // work queue (zeroed by the caller)
+};
+int mm_state_vectors();
+int mm_blocks_per_sm(int K);
+// every (group, pass, simulation) quantile regression of the batch: interior point + vertex polish, one block per problem
+void mm_qr_launch(const MmArgs& m, int grid, cudaStream_t st);
+// native streams: taus [slots][sims], simulated original rows rows_a / rows_b [slots][sims]; global pass id of slot s =
+// pass0 + s, except that slot 0 is pass 0 (the point estimates) when first_slot is set
+void mm_streams_launch(const MmArgs& m, long long pass0, int first_slot, uint64_t seed, double* taus, uint32_t* rows_a, uint32_t* rows_b, cudaStream_t st);
+// simulation + empirical quantiles + effects per pass: stats [slots][3 nq], status [slots], nsucc [slots] (may be null)
+void mm_effects_launch(const MmArgs& m, const uint32_t* rows_a, const uint32_t* rows_b, int nq, const double* d_quantiles,
+                       double* stats, int* status, int* nsucc, cudaStream_t st);
+
 // ---- rif.cu ----
 // RIF transform (math/rif.rs:14-88) of a packed group's raw outcome (g.y_raw if saved, else column ycol itself),
 // written to column ycol

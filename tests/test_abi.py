@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/obboot.h but not exported by libobboot.so"
     assert sorted(_native.SYMBOLS) == [s for s in syms if s in _native.SYMBOLS]
-    assert lib.ob_abi_version() == 5
+    assert lib.ob_abi_version() == 6
 
 
 def test_no_cpu_fallback():

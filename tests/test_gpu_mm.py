@@ -1,0 +1,148 @@
+"""Machado-Mata quantile decomposition (quantile_decomposition.rs:173-421, math/quantile_regression.rs:22-135)
+on the GPU through the C ABI (ob_mm_run) vs the oracle (oracle/ob_oracle_mm.c, itself pinned against HiGHS dual-simplex
+vertices and the reference's known answers), under explicit streams: resample indices, random quantiles, simulated rows.
+Every quantile regression must land on the same LP vertex (coefficients within 1e-10), hence every effect, SE and CI."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import relerr
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def make_frame(n, n_x, seed, round_y=None):
+    rng = np.random.default_rng(seed)
+    grp = rng.integers(0, 2, n).astype(np.uint8)
+    xs = [rng.normal(12, 2, n) + 0.5 * (grp == 0)] + [rng.uniform(0, 30, n) for _ in range(n_x - 1)]
+    cat = rng.integers(0, 3, n).astype(np.int32)
+    y = 1.0 + 0.3 * (grp == 0) + (0.07 + 0.02 * (grp == 0)) * xs[0] + sum(0.01 * x for x in xs[1:]) + 0.1 * (cat == 1) \
+        - 0.15 * (cat == 2) + rng.standard_t(4, n) * 0.3 * (1 + 0.03 * xs[0])
+    if round_y is not None:
+        y = y.round(round_y)
+    return dict(group=grp, cont=xs, cat=cat, y=y)
+
+
+def dense(fr):
+    n = len(fr["y"])
+    X = np.c_[np.ones(n), np.stack(fr["cont"], 1), (fr["cat"] == 1).astype(float), (fr["cat"] == 2).astype(float)]
+    A, B = fr["group"] == 0, fr["group"] == 1
+    return (X[A], fr["y"][A]), (X[B], fr["y"][B])
+
+
+def streams(seed, reps, sims, na, nb):
+    rng = np.random.default_rng(seed)
+    return dict(taus=rng.uniform(0.01, 0.99, size=(reps + 1, sims)),
+                draw_a=rng.integers(0, na, size=(reps + 1, sims)).astype(np.uint32),
+                draw_b=rng.integers(0, nb, size=(reps + 1, sims)).astype(np.uint32),
+                idx_a=rng.integers(0, na, size=(reps, na)).astype(np.uint32),
+                idx_b=rng.integers(0, nb, size=(reps, nb)).astype(np.uint32))
+
+
+@pytest.mark.parametrize("n,n_x,sims,reps,round_y", [(600, 2, 40, 6, None), (4000, 3, 60, 8, None), (2500, 2, 50, 5, 2),
+                                                     (1500, 12, 30, 4, None)])
+def test_mm_matches_oracle(orc, n, n_x, sims, reps, round_y):
+    import oaxaca_blinder_rs_b200 as ob
+    fr = make_frame(n, n_x, seed=10 + n_x, round_y=round_y)
+    (Xa, ya), (Xb, yb) = dense(fr)
+    st = streams(5, reps, sims, len(ya), len(yb))
+    q = [0.1, 0.25, 0.5, 0.75, 0.9]
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, fr["cont"], [fr["cat"]], [3], fr["y"], None, fr["group"])
+    gpu = ob.machado_mata(des, q, simulations=sims, reps=reps, want_rep=True, want_betas=True, **st)
+    des.close(); ctx.close()
+    o = orc.mm_run(Xa, ya, Xb, yb, sims, q, reps, st["idx_a"], st["idx_b"], st["taus"], st["draw_a"], st["draw_b"], nthreads=8)
+    assert gpu["qr"]["failed"] == 0 and gpu["qr"]["total"] == 2 * (reps + 1) * sims, (gpu["qr"], gpu["point_qr_info_a"], gpu["point_qr_info_b"])
+    # the point pass's regressions, coefficient by coefficient: the same LP vertex
+    assert ((gpu["point_qr_info_a"] & 0xff) == ob.core.QR_VERTEX).all() and ((gpu["point_qr_info_b"] & 0xff) == ob.core.QR_VERTEX).all()
+    assert relerr(gpu["point_betas_a"], o["betas_a"]) <= RTOL, relerr(gpu["point_betas_a"], o["betas_a"])
+    assert relerr(gpu["point_betas_b"], o["betas_b"]) <= RTOL
+    nq = len(q)
+    assert relerr(gpu["point_stats"], o["point_stats"].reshape(nq, 3)) <= RTOL
+    assert np.array_equal(gpu["rep_status"], o["rep_status"]) and gpu["n_ok"] == o["n_ok"] == reps
+    assert relerr(gpu["rep_stats"], o["rep_stats"].reshape(reps, nq, 3)) <= RTOL
+    for k, ko in (("std_err", "se"), ("p_value", "p"), ("ci_lower", "ci_lo"), ("ci_upper", "ci_hi"), ("t_stat", "t")):
+        assert relerr(gpu[k], o[ko].reshape(nq, 3)) <= RTOL, k
+    # gap = characteristics + coefficients in every pass (quantile_decomposition.rs:271-275)
+    np.testing.assert_allclose(gpu["rep_stats"][..., 0], gpu["rep_stats"][..., 1] + gpu["rep_stats"][..., 2], rtol=0, atol=1e-12)
+
+
+def test_mm_golden_fixture_on_gpu():
+    """tests/golden/mm_fixture.json (HiGHS dual simplex + numpy, independent of the oracle) straight against the GPU."""
+    import oaxaca_blinder_rs_b200 as ob
+    fx = json.load(open(os.path.join(HERE, "golden", "mm_fixture.json")))
+    Xa, ya, Xb, yb = (np.array(fx[k]) for k in ("Xa", "ya", "Xb", "yb"))
+    ctx = ob.Context(0)
+    des = ob.Design.from_dense(ctx, Xa, ya, None, Xb, yb, None, n_cont=2)
+    out = ob.machado_mata(des, fx["quantiles"], simulations=fx["sims"], reps=fx["reps"], idx_a=fx["idx_a"], idx_b=fx["idx_b"],
+                          taus=fx["taus"], draw_a=fx["draw_a"], draw_b=fx["draw_b"], want_rep=True, want_betas=True)
+    des.close(); ctx.close()
+    np.testing.assert_allclose(out["point_betas_a"], fx["point_betas_a"], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(out["point_betas_b"], fx["point_betas_b"], rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(out["point_stats"], fx["point_stats"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(out["rep_stats"], fx["rep_stats"], rtol=0, atol=1e-10)
+
+
+def test_reference_known_answer_on_gpu():
+    """math/quantile_regression.rs:137-170: perfectly linear data, every regression quantile is [0, 1] (tolerance 1e-4
+    there); both groups get the same data, so every effect is 0."""
+    import oaxaca_blinder_rs_b200 as ob
+    X = np.array([[1, 1], [1, 2], [1, 3], [1, 4], [1, 5]], dtype=float)
+    y = np.array([1, 2, 3, 4, 5], dtype=float)
+    ctx = ob.Context(0)
+    des = ob.Design.from_dense(ctx, X, y, None, X, y, None, n_cont=1)
+    taus = np.array([[0.5, 0.25, 0.1, 0.9]])
+    out = ob.machado_mata(des, [0.5], simulations=4, reps=0, taus=taus, draw_a=[[0, 1, 2, 3]], draw_b=[[0, 1, 2, 3]], want_betas=True)
+    des.close(); ctx.close()
+    np.testing.assert_allclose(out["point_betas_a"], np.tile([0.0, 1.0], (4, 1)), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(out["point_stats"], 0.0, atol=1e-12)
+    assert np.isnan(out["std_err"]).all()
+
+
+def test_native_streams_are_deterministic_and_shard_invariant():
+    """Native Philox streams (resamples, random quantiles, simulated rows) are keyed by global pass ids: the same seed gives
+    the same bits, a replicate shard computes exactly its rows of the full run, another seed gives other draws; and the
+    decomposition identity holds in every pass."""
+    import oaxaca_blinder_rs_b200 as ob
+    fr = make_frame(3000, 2, seed=77)
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, fr["cont"], [fr["cat"]], [3], fr["y"], None, fr["group"])
+    kw = dict(quantiles=[0.25, 0.5, 0.75], simulations=64, reps=12, want_rep=True)
+    a = ob.machado_mata(des, seed=9, **kw)
+    b = ob.machado_mata(des, seed=9, **kw)
+    c = ob.machado_mata(des, seed=10, **kw)
+    part = ob.machado_mata(des, seed=9, rep_begin=5, rep_end=9, skip_reduce=True, **kw)
+    des.close(); ctx.close()
+    assert np.array_equal(a["rep_stats"], b["rep_stats"]) and np.array_equal(a["std_err"], b["std_err"])
+    assert not np.array_equal(a["rep_stats"], c["rep_stats"])
+    assert np.array_equal(part["rep_stats"], a["rep_stats"][5:9]) and np.array_equal(part["point_stats"], a["point_stats"])
+    assert a["n_ok"] == 12 and a["qr"]["failed"] == 0
+    np.testing.assert_allclose(a["rep_stats"][..., 0], a["rep_stats"][..., 1] + a["rep_stats"][..., 2], rtol=0, atol=1e-12)
+    assert np.isfinite(a["std_err"]).all() and (a["std_err"] > 0).all()
+    # group A's outcome is shifted up: a positive gap at every quantile, in the point pass and in every bootstrap pass
+    assert (a["point_stats"][:, 0] > 0).all() and (a["rep_stats"][..., 0] > 0).all()
+    assert (a["ci_lower"][:, 0] > 0).all() and (a["ci_lower"] <= a["ci_upper"]).all()
+
+
+def test_failed_pass_and_refusals():
+    import oaxaca_blinder_rs_b200 as ob
+    rng = np.random.default_rng(2)
+    n = 60
+    Xa = np.c_[np.ones(n), rng.normal(size=n)]
+    ya = Xa @ [1.0, 0.5] + rng.normal(size=n)
+    Xb = np.c_[np.ones(n), np.ones(n)]          # collinear: every regression of group B fails -> the point pass fails
+    ctx = ob.Context(0)
+    des = ob.Design.from_dense(ctx, Xa, ya, None, Xb, rng.normal(size=n), None, n_cont=1)
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.machado_mata(des, [0.5], simulations=8, reps=0)
+    assert e.value.kind == "NalgebraError"       # quantile_decomposition.rs:238-242
+    des.close()
+    des = ob.Design.from_dense(ctx, Xa, ya, np.ones(n), Xa, ya, np.ones(n), n_cont=1)
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.machado_mata(des, [0.5], simulations=8, reps=0)
+    assert e.value.kind == "Unsupported"
+    des.close(); ctx.close()
