@@ -229,6 +229,10 @@ int orc_qr(const double* X, const double* y, const double* c, int64_t n, int32_t
             }
             ap = fmin(0.99995 * ap, 1.0); ad = fmin(0.99995 * ad, 1.0);
         }
+        /* one step length for the primal and the dual iterate: with separate ones the iterates of the extreme quantiles
+         * (tau near 0.01 / 0.99, where all but a few percent of the dual variables end at one bound) lose centrality and
+         * the iteration count grows from ~20 to 100 and more */
+        ap = ad = fmin(ap, ad);
         gap = 0.0;
         for (int64_t i = 0; i < n; ++i) {
             if (!(u[i] > 0.0)) continue;
