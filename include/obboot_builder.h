@@ -67,6 +67,32 @@ const char* ob_results_summary(ob_results* r);       /* summary() text (display.
 const char* ob_results_markdown(ob_results* r);
 int64_t ob_results_residuals(const ob_results* r, double* out);   /* returns n_b; copies when out != NULL */
 
+/* ---- Machado-Mata: QuantileDecompositionBuilder (quantile_decomposition.rs:21-100), run() (:281-421),
+ * QuantileDecompositionResults (:425-505).  Defaults as in the reference: quantiles 0.1 0.25 0.5 0.75 0.9, 200 simulations,
+ * 20 bootstrap replications.  Results as JSON: {"results_by_quantile": {"q25": {"total_gap": {name, estimate, std_err,
+ * t_stat, p_value, ci_lower, ci_upper}, "characteristics_effect": {..}, "coefficients_effect": {..}}, ..}, "n_a", "n_b", ..}
+ * with the reference's keys "q{(tau * 100) as u32}" (:277). */
+typedef struct ob_qd_builder ob_qd_builder;
+typedef struct ob_qd_results ob_qd_results;
+ob_qd_builder* ob_qd_builder_new(const ob_frame* f, const char* outcome, const char* group, const char* reference_group);
+void ob_qd_builder_free(ob_qd_builder* b);
+ob_status ob_qd_builder_predictors(ob_qd_builder* b, const char* const* names, int32_t n);
+ob_status ob_qd_builder_categorical_predictors(ob_qd_builder* b, const char* const* names, int32_t n);
+ob_status ob_qd_builder_quantiles(ob_qd_builder* b, const double* q, int32_t n);
+ob_status ob_qd_builder_simulations(ob_qd_builder* b, int64_t reps);
+ob_status ob_qd_builder_bootstrap_reps(ob_qd_builder* b, int64_t reps);
+/* additions of the GPU path: seed of the native Philox streams, CUDA device, test-only explicit streams (ob_mm_opts) */
+ob_status ob_qd_builder_seed(ob_qd_builder* b, uint64_t seed);
+ob_status ob_qd_builder_device(ob_qd_builder* b, int32_t device);
+ob_status ob_qd_builder_streams(ob_qd_builder* b, const uint32_t* idx_a, const uint32_t* idx_b, const double* taus,
+                                const uint32_t* draw_a, const uint32_t* draw_b);
+ob_status ob_qd_builder_run(ob_qd_builder* b, ob_qd_results** out);
+const char* ob_qd_builder_last_error(const ob_qd_builder* b);
+ob_status ob_qd_builder_last_status(const ob_qd_builder* b);
+void ob_qd_results_free(ob_qd_results* r);
+const char* ob_qd_results_json(ob_qd_results* r);
+const char* ob_qd_results_summary(ob_qd_results* r);      /* summary() text (quantile_decomposition.rs:441-505) */
+
 #ifdef __cplusplus
 }
 #endif

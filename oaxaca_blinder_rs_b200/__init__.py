@@ -7,7 +7,8 @@ include/obboot.h; this package is the host-side mirror of the reference's interf
 from .core import (REF_GROUP_A, REF_GROUP_B, REF_POOLED, REF_WEIGHTED, Context, Design, NormVar,
                    OaxacaError, PinnedBuffer, bootstrap, machado_mata, num_stats, pin_in_place, reduce_stats, replicate_shard, unpin)
 
-from .builder import ComponentResult, OaxacaBlinder, OaxacaBuilder, OaxacaResults, ReferenceCoefficients, read_csv
+from .builder import (ComponentResult, OaxacaBlinder, OaxacaBuilder, OaxacaResults, QuantileDecompositionBuilder,
+                      QuantileDecompositionDetail, QuantileDecompositionResults, ReferenceCoefficients, read_csv)
 
-__all__ = ["ComponentResult", "OaxacaBlinder", "OaxacaBuilder", "OaxacaResults", "ReferenceCoefficients", "REF_GROUP_A", "REF_GROUP_B", "REF_POOLED", "REF_WEIGHTED", "Context", "Design", "NormVar",
+__all__ = ["QuantileDecompositionBuilder", "QuantileDecompositionDetail", "QuantileDecompositionResults", "ComponentResult", "OaxacaBlinder", "OaxacaBuilder", "OaxacaResults", "ReferenceCoefficients", "REF_GROUP_A", "REF_GROUP_B", "REF_POOLED", "REF_WEIGHTED", "Context", "Design", "NormVar",
            "OaxacaError", "PinnedBuffer", "pin_in_place", "unpin", "replicate_shard", "bootstrap", "machado_mata", "num_stats", "reduce_stats", "read_csv"]

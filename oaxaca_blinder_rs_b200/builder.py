@@ -5,6 +5,8 @@ include/obboot_builder.h (the builder logic itself is the C++ host layer, csrc/h
   ReferenceCoefficients decomposition.rs:5-20
   OaxacaResults / TwoFoldResults / DecompositionDetail / ComponentResult   types.rs:10-47, :162-180
   OaxacaBlinder        python.rs:193-256 (fit / fit_quantile; module currently compiled out upstream)
+  QuantileDecompositionBuilder / QuantileDecompositionResults / QuantileDecompositionDetail (Machado-Mata)
+                       quantile_decomposition.rs:21-100, :281-421, :425-522
 
 Frames are dicts of columns, pandas DataFrames or pyarrow Tables (polars is not in this image): float columns
 become f64 columns (NaN/None = null), everything else string columns (None = null).
@@ -68,6 +70,22 @@ def _blib():
         L.ob_results_summary.argtypes = [vp]; L.ob_results_summary.restype = cp
         L.ob_results_markdown.argtypes = [vp]; L.ob_results_markdown.restype = cp
         L.ob_results_residuals.argtypes = [vp, N._DP]; L.ob_results_residuals.restype = i64
+        L.ob_qd_builder_new.argtypes = [vp, cp, cp, cp]; L.ob_qd_builder_new.restype = vp
+        L.ob_qd_builder_free.argtypes = [vp]; L.ob_qd_builder_free.restype = None
+        for fn in ("predictors", "categorical_predictors"):
+            getattr(L, "ob_qd_builder_" + fn).argtypes = [vp, C.POINTER(cp), i32]
+        L.ob_qd_builder_quantiles.argtypes = [vp, N._DP, i32]
+        L.ob_qd_builder_simulations.argtypes = [vp, i64]
+        L.ob_qd_builder_bootstrap_reps.argtypes = [vp, i64]
+        L.ob_qd_builder_seed.argtypes = [vp, C.c_uint64]
+        L.ob_qd_builder_device.argtypes = [vp, i32]
+        L.ob_qd_builder_streams.argtypes = [vp, N._U32P, N._U32P, N._DP, N._U32P, N._U32P]
+        L.ob_qd_builder_run.argtypes = [vp, C.POINTER(vp)]
+        L.ob_qd_builder_last_error.argtypes = [vp]; L.ob_qd_builder_last_error.restype = cp
+        L.ob_qd_builder_last_status.argtypes = [vp]
+        L.ob_qd_results_free.argtypes = [vp]; L.ob_qd_results_free.restype = None
+        L.ob_qd_results_json.argtypes = [vp]; L.ob_qd_results_json.restype = cp
+        L.ob_qd_results_summary.argtypes = [vp]; L.ob_qd_results_summary.restype = cp
         _bl = L
     return _bl
 
@@ -79,7 +97,11 @@ BUILDER_SYMBOLS = ["ob_frame_new", "ob_frame_free", "ob_frame_add_f64", "ob_fram
                    "ob_builder_seed", "ob_builder_device", "ob_builder_index_stream", "ob_builder_run",
                    "ob_builder_decompose_quantile", "ob_builder_get_data_matrices", "ob_builder_describe", "ob_builder_last_error", "ob_builder_last_status",
                    "ob_results_free", "ob_results_json", "ob_results_summary", "ob_results_markdown",
-                   "ob_results_residuals"]
+                   "ob_results_residuals",
+                   "ob_qd_builder_new", "ob_qd_builder_free", "ob_qd_builder_predictors", "ob_qd_builder_categorical_predictors",
+                   "ob_qd_builder_quantiles", "ob_qd_builder_simulations", "ob_qd_builder_bootstrap_reps", "ob_qd_builder_seed",
+                   "ob_qd_builder_device", "ob_qd_builder_streams", "ob_qd_builder_run", "ob_qd_builder_last_error",
+                   "ob_qd_builder_last_status", "ob_qd_results_free", "ob_qd_results_json", "ob_qd_results_summary"]
 
 
 def _columns(frame) -> dict:
@@ -342,3 +364,101 @@ class OaxacaBlinder:
             return self._b.decompose_quantile(quantile)
         except OaxacaError as e:
             raise RuntimeError(str(e)) from e
+
+
+class QuantileDecompositionDetail(SimpleNamespace):
+    """quantile_decomposition.rs:512-522: total_gap, characteristics_effect, coefficients_effect (ComponentResult each)."""
+
+
+class QuantileDecompositionResults:
+    """quantile_decomposition.rs:425-437: results_by_quantile {"q25": detail, ..}, n_a, n_b (+ GPU-path bookkeeping)."""
+
+    def __init__(self, handle):
+        L = _blib()
+        self._h = handle
+        d = json.loads(L.ob_qd_results_json(handle).decode())
+        self.results_by_quantile = {
+            k: QuantileDecompositionDetail(**{name: _comps([v[name]])[0] for name in ("total_gap", "characteristics_effect", "coefficients_effect")})
+            for k, v in d["results_by_quantile"].items()}
+        self.n_a, self.n_b = d["n_a"], d["n_b"]
+        self.bootstrap_reps, self.successful_bootstraps = d["bootstrap_reps"], d["successful_bootstraps"]
+        self.qr = d["qr"]
+        self.timings_ms = dict(total=d["ms_total"])
+
+    def summary(self) -> str:
+        s = _blib().ob_qd_results_summary(self._h).decode()
+        print(s, end="")
+        return s
+
+    def to_json(self) -> str:
+        return _blib().ob_qd_results_json(self._h).decode()
+
+    def __del__(self):
+        try:
+            if self._h:
+                _blib().ob_qd_results_free(self._h)
+        except Exception:
+            pass
+
+
+class QuantileDecompositionBuilder:
+    """quantile_decomposition.rs:21-100: QuantileDecompositionBuilder::new(df, outcome, group, reference_group) and its
+    setters; defaults quantiles [0.1, 0.25, 0.5, 0.75, 0.9], 200 simulations, 20 bootstrap replications."""
+
+    def __init__(self, dataframe, outcome: str, group: str, reference_group: str):
+        L = _blib()
+        self._frame = _Frame(dataframe)
+        self._keep = []
+        self._h = C.c_void_p(L.ob_qd_builder_new(self._frame._h, outcome.encode(), group.encode(), reference_group.encode()))
+
+    def _check(self, st):
+        if st != 0:
+            raise OaxacaError(st, _blib().ob_qd_builder_last_error(self._h).decode())
+        return self
+
+    def predictors(self, predictors: Sequence[str]):
+        a, n = _names(predictors)
+        return self._check(_blib().ob_qd_builder_predictors(self._h, a, n))
+
+    def categorical_predictors(self, predictors: Sequence[str]):
+        a, n = _names(predictors)
+        return self._check(_blib().ob_qd_builder_categorical_predictors(self._h, a, n))
+
+    def quantiles(self, quantiles: Sequence[float]):
+        q = np.ascontiguousarray(quantiles, dtype=np.float64)
+        return self._check(_blib().ob_qd_builder_quantiles(self._h, q.ctypes.data_as(N._DP), len(q)))
+
+    def simulations(self, reps: int):
+        return self._check(_blib().ob_qd_builder_simulations(self._h, int(reps)))
+
+    def bootstrap_reps(self, reps: int):
+        return self._check(_blib().ob_qd_builder_bootstrap_reps(self._h, int(reps)))
+
+    def seed(self, seed: int):
+        return self._check(_blib().ob_qd_builder_seed(self._h, int(seed)))
+
+    def device(self, device: int):
+        return self._check(_blib().ob_qd_builder_device(self._h, int(device)))
+
+    def streams(self, idx_a=None, idx_b=None, taus=None, draw_a=None, draw_b=None):
+        """Test-only explicit streams (ob_mm_opts): resample indices [reps x n_g], random quantiles and simulated-row
+        positions [(reps + 1) x simulations]."""
+        u32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.uint32)
+        ia, ib, da, db = u32(idx_a), u32(idx_b), u32(draw_a), u32(draw_b)
+        t = None if taus is None else np.ascontiguousarray(taus, dtype=np.float64)
+        self._keep = [ia, ib, t, da, db]
+        p32 = lambda a: None if a is None else a.ctypes.data_as(N._U32P)
+        return self._check(_blib().ob_qd_builder_streams(self._h, p32(ia), p32(ib), None if t is None else t.ctypes.data_as(N._DP),
+                                                         p32(da), p32(db)))
+
+    def run(self) -> QuantileDecompositionResults:                   # quantile_decomposition.rs:281
+        out = C.c_void_p()
+        self._check(_blib().ob_qd_builder_run(self._h, C.byref(out)))
+        return QuantileDecompositionResults(out)
+
+    def __del__(self):
+        try:
+            if self._h:
+                _blib().ob_qd_builder_free(self._h)
+        except Exception:
+            pass

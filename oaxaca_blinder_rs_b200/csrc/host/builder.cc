@@ -682,14 +682,17 @@ static void jstr(std::ostream& os, const std::string& s) {
     for (char ch : s) { if (ch == '"' || ch == '\\') os << '\\'; os << ch; }
     os << '"';
 }
+static void jcomp(std::ostream& os, const ComponentResult& c) {
+    os << "{\"name\":"; jstr(os, c.name);
+    os << ",\"estimate\":"; jnum(os, c.estimate); os << ",\"std_err\":"; jnum(os, c.std_err);
+    os << ",\"t_stat\":"; jnum(os, c.t_stat); os << ",\"p_value\":"; jnum(os, c.p_value);
+    os << ",\"ci_lower\":"; jnum(os, c.ci_lower); os << ",\"ci_upper\":"; jnum(os, c.ci_upper); os << '}';
+}
 static void jcomps(std::ostream& os, const std::vector<ComponentResult>& v) {
     os << '[';
     for (size_t i = 0; i < v.size(); ++i) {
         if (i) os << ',';
-        os << "{\"name\":"; jstr(os, v[i].name);
-        os << ",\"estimate\":"; jnum(os, v[i].estimate); os << ",\"std_err\":"; jnum(os, v[i].std_err);
-        os << ",\"t_stat\":"; jnum(os, v[i].t_stat); os << ",\"p_value\":"; jnum(os, v[i].p_value);
-        os << ",\"ci_lower\":"; jnum(os, v[i].ci_lower); os << ",\"ci_upper\":"; jnum(os, v[i].ci_upper); os << '}';
+        jcomp(os, v[i]);
     }
     os << ']';
 }
@@ -736,6 +739,119 @@ std::string OaxacaResults::to_markdown() const {
     tab("Two-Fold Decomposition", two_fold.aggregate);
     tab("Detailed Decomposition (Explained)", two_fold.detailed_explained);
     tab("Detailed Decomposition (Unexplained)", two_fold.detailed_unexplained);
+    return os.str();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Machado-Mata quantile decomposition: QuantileDecompositionBuilder (quantile_decomposition.rs:21-522)
+QuantileDecompositionBuilder::QuantileDecompositionBuilder(DataFrame df, const std::string& outcome, const std::string& group,
+                                                           const std::string& reference_group)
+    : dataframe_(std::move(df)), outcome_(outcome), group_(group), reference_group_(reference_group) {}
+
+std::string QuantileDecompositionBuilder::quantile_key(double tau) {
+    double v = tau * 100.0;                           // `as u32` saturates: negative / NaN -> 0
+    uint32_t k = !(v > 0.0) ? 0u : (v >= 4294967295.0 ? 4294967295u : (uint32_t)v);
+    return "q" + std::to_string(k);
+}
+
+QuantileDecompositionResults QuantileDecompositionBuilder::run() const {
+    // The reference's run() does not clean the frame (quantile_decomposition.rs:286-287 only selects the columns): rows of
+    // the two groups with a null outcome are an error in prepare_data (:111-118), nulls in predictors fail the
+    // to_ndarray conversion (:141).  Rows whose group is null or a third group never reach a design (:195-206).
+    {
+        std::vector<const Column*> used;
+        const Column* gc = dataframe_.find(group_);
+        const Column* yc = dataframe_.find(outcome_);
+        if (gc && gc->is_str && yc) {
+            bool any_nulls = !yc->valid.empty();
+            for (const auto& c : predictors_) { const Column* x = dataframe_.find(c); if (x) { used.push_back(x); any_nulls |= !x->valid.empty(); } }
+            for (const auto& c : categorical_) { const Column* x = dataframe_.find(c); if (x) { used.push_back(x); any_nulls |= !x->valid.empty(); } }
+            if (any_nulls) {
+                std::set<std::string> ug;
+                for (size_t i = 0; i < dataframe_.height(); ++i) if (gc->is_valid(i)) ug.insert(gc->str[i]);
+                std::string a_name = ug.empty() ? reference_group_ : *ug.begin();
+                if (a_name == reference_group_ && ug.size() > 1) a_name = *(++ug.begin());
+                for (size_t i = 0; i < dataframe_.height(); ++i) {
+                    if (!gc->is_valid(i) || (gc->str[i] != a_name && gc->str[i] != reference_group_)) continue;
+                    if (!yc->is_valid(i))
+                        throw OaxacaError(OB_ERR_INVALID_GROUP, OaxacaError::display(OB_ERR_INVALID_GROUP, "Null outcome encountered"));
+                    for (const Column* x : used)
+                        if (!x->is_valid(i))
+                            throw OaxacaError(OB_ERR_POLARS, OaxacaError::display(OB_ERR_POLARS, "null value in predictor column '" + x->name + "'"));
+                }
+            }
+        }
+    }
+    if (quantiles_.empty()) throw OaxacaError(OB_ERR_INVALID_ARG, "no target quantiles");
+    OaxacaBuilder ingest(dataframe_, outcome_, group_, reference_group_);
+    ingest.predictors(predictors_).categorical_predictors(categorical_).device(device_);
+    OaxacaBuilder::Prepared p;
+    CtxGuard g;
+    ob_status st = ob_ctx_create(device_, &g.ctx);
+    if (st != OB_OK) throw OaxacaError(st, "no usable CUDA device (B200 / sm_100a required; there is no CPU fallback)");
+    g.des = ingest.ingest_on_device(g.ctx, p, false);
+    int64_t na = 0, nb = 0; int32_t K = 0, nc = 0;
+    ob_design_shape(g.des, &na, &nb, &K, &nc);
+
+    const int nq = (int)quantiles_.size(), S = 3 * nq;
+    ob_mm_opts o{};
+    o.simulations = (int32_t)simulations_; o.n_quantiles = nq; o.quantiles = quantiles_.data();
+    o.reps = (int64_t)bootstrap_reps_; o.seed = seed_;
+    o.idx_a = idx_a_; o.idx_b = idx_b_; o.taus = taus_; o.draw_a = draw_a_; o.draw_b = draw_b_;
+    std::vector<double> point(S), se(S), pv(S), lo(S), hi(S), t(S);
+    ob_mm_result r{};
+    r.point_stats = point.data(); r.std_err = se.data(); r.p_value = pv.data(); r.ci_lower = lo.data(); r.ci_upper = hi.data(); r.t_stat = t.data();
+    check(g.ctx, ob_mm_run(g.ctx, g.des, &o, &r));
+
+    QuantileDecompositionResults R;
+    for (int q = 0; q < nq; ++q) {                     // a later quantile with the same key replaces an earlier one (HashMap insert, :277)
+        auto comp = [&](const char* name, int j) { return ComponentResult{name, point[j], se[j], t[j], pv[j], lo[j], hi[j]}; };
+        R.results_by_quantile[quantile_key(quantiles_[q])] =
+            QuantileDecompositionDetail{comp("Total Gap", 3 * q), comp("Characteristics", 3 * q + 1), comp("Coefficients", 3 * q + 2)};   // :365-407
+    }
+    R.n_a = (size_t)na; R.n_b = (size_t)nb;
+    R.bootstrap_reps = (int64_t)bootstrap_reps_; R.successful_bootstraps = r.n_ok;
+    R.qr_total = r.qr_total; R.qr_vertex = r.qr_vertex; R.qr_approx = r.qr_approx; R.qr_failed = r.qr_failed;
+    R.ms_total = r.ms_total; R.ms_qr = r.ms_qr;
+    return R;
+}
+
+void QuantileDecompositionResults::summary(std::ostream& os) const {   // quantile_decomposition.rs:441-505
+    os << "Machado-Mata Quantile Decomposition Results\n";
+    os << "============================================\n";
+    os << "Group A (Advantaged): " << n_a << " observations\n";
+    os << "Group B (Reference):  " << n_b << " observations\n";
+    for (const auto& kv : results_by_quantile) {       // sorted keys (:449-450)
+        os << "\n--- Decomposition for Quantile: " << kv.first << " ---\n";
+        os << "| Component       | Estimate | Std. Err. | p-value | 95% CI |\n";
+        for (const ComponentResult* c : {&kv.second.total_gap, &kv.second.characteristics_effect, &kv.second.coefficients_effect}) {
+            os << "| " << c->name << std::string(c->name.size() < 15 ? 15 - c->name.size() : 0, ' ') << " | " << fmt(c->estimate, 4) << " | "
+               << fmt(c->std_err, 4) << " | " << fmt(c->p_value, 4) << " | [" << fmt(c->ci_lower, 3) << ", " << fmt(c->ci_upper, 3) << "] |\n";
+        }
+    }
+}
+
+std::string QuantileDecompositionResults::to_json() const {
+    std::ostringstream os;
+    os << "{\"results_by_quantile\":{";
+    bool first = true;
+    for (const auto& kv : results_by_quantile) {
+        if (!first) os << ",";
+        first = false;
+        jstr(os, kv.first);
+        os << ":{\"total_gap\":";
+        jcomp(os, kv.second.total_gap);
+        os << ",\"characteristics_effect\":";
+        jcomp(os, kv.second.characteristics_effect);
+        os << ",\"coefficients_effect\":";
+        jcomp(os, kv.second.coefficients_effect);
+        os << "}";
+    }
+    os << "},\"n_a\":" << n_a << ",\"n_b\":" << n_b << ",\"bootstrap_reps\":" << bootstrap_reps << ",\"successful_bootstraps\":" << successful_bootstraps
+       << ",\"qr\":{\"total\":" << qr_total << ",\"vertex\":" << qr_vertex << ",\"approx\":" << qr_approx << ",\"failed\":" << qr_failed << "}"
+       << ",\"ms_total\":";
+    jnum(os, ms_total);
+    os << "}";
     return os.str();
 }
 

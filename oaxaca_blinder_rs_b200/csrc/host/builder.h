@@ -9,6 +9,7 @@
 #pragma once
 #include <cstdint>
 #include <iosfwd>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -84,7 +85,10 @@ struct DataMatrices {      // get_data_matrices, builder.rs:252-291 (row-major)
     std::vector<std::string> predictor_names;
 };
 
+class QuantileDecompositionBuilder;
+
 class OaxacaBuilder {
+    friend class QuantileDecompositionBuilder;   // shares the device ingest (cleaning, coding, pack)
 public:
     OaxacaBuilder(DataFrame df, const std::string& outcome, const std::string& group, const std::string& reference_group);
     static OaxacaBuilder from_formula(DataFrame df, const std::string& formula, const std::string& group,
@@ -126,6 +130,53 @@ private:
     int device_ = 0;
     const uint32_t* idx_a_ = nullptr;
     const uint32_t* idx_b_ = nullptr;
+};
+
+// ---- Machado-Mata quantile decomposition (quantile_decomposition.rs:21-522) ----
+struct QuantileDecompositionDetail {      // quantile_decomposition.rs:512-522
+    ComponentResult total_gap, characteristics_effect, coefficients_effect;
+};
+
+struct QuantileDecompositionResults {     // quantile_decomposition.rs:425-437
+    std::map<std::string, QuantileDecompositionDetail> results_by_quantile;   // keys "q{(tau * 100) as u32}" (:277)
+    size_t n_a = 0, n_b = 0;
+    // bookkeeping of the GPU path (not in the reference struct)
+    int64_t bootstrap_reps = 0, successful_bootstraps = 0;
+    int64_t qr_total = 0, qr_vertex = 0, qr_approx = 0, qr_failed = 0;
+    double ms_total = 0, ms_qr = 0;
+
+    void summary(std::ostream& os) const;                     // quantile_decomposition.rs:441-505
+    std::string to_json() const;
+};
+
+class QuantileDecompositionBuilder {      // quantile_decomposition.rs:21-100
+public:
+    QuantileDecompositionBuilder(DataFrame df, const std::string& outcome, const std::string& group, const std::string& reference_group);
+    QuantileDecompositionBuilder& predictors(std::vector<std::string> p) { predictors_ = std::move(p); return *this; }
+    QuantileDecompositionBuilder& categorical_predictors(std::vector<std::string> p) { categorical_ = std::move(p); return *this; }
+    QuantileDecompositionBuilder& quantiles(std::vector<double> q) { quantiles_ = std::move(q); return *this; }
+    QuantileDecompositionBuilder& simulations(size_t reps) { simulations_ = reps; return *this; }
+    QuantileDecompositionBuilder& bootstrap_reps(size_t reps) { bootstrap_reps_ = reps; return *this; }
+    // additions of the GPU path: seed of the native streams, device, test-only explicit streams (ob_mm_opts)
+    QuantileDecompositionBuilder& seed(uint64_t s) { seed_ = s; return *this; }
+    QuantileDecompositionBuilder& device(int d) { device_ = d; return *this; }
+    QuantileDecompositionBuilder& streams(const uint32_t* idx_a, const uint32_t* idx_b, const double* taus, const uint32_t* draw_a,
+                                          const uint32_t* draw_b) {
+        idx_a_ = idx_a; idx_b_ = idx_b; taus_ = taus; draw_a_ = draw_a; draw_b_ = draw_b; return *this;
+    }
+    QuantileDecompositionResults run() const;                 // quantile_decomposition.rs:281-421
+    static std::string quantile_key(double tau);              // format!("q{}", (tau * 100.0) as u32), :277
+
+private:
+    DataFrame dataframe_;
+    std::string outcome_, group_, reference_group_;
+    std::vector<std::string> predictors_, categorical_;
+    std::vector<double> quantiles_ = {0.1, 0.25, 0.5, 0.75, 0.9};     // :57
+    size_t simulations_ = 200, bootstrap_reps_ = 20;                 // :58-59
+    uint64_t seed_ = 0x0B5EEDull;
+    int device_ = 0;
+    const uint32_t *idx_a_ = nullptr, *idx_b_ = nullptr, *draw_a_ = nullptr, *draw_b_ = nullptr;
+    const double* taus_ = nullptr;
 };
 
 }  // namespace ob

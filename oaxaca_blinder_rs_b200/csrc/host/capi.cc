@@ -10,6 +10,8 @@
 struct ob_frame { ob::DataFrame df; };
 struct ob_builder { std::unique_ptr<ob::OaxacaBuilder> b; std::string err, desc; ob_status last = OB_OK; };
 struct ob_results { ob::OaxacaResults r; std::string json, summary, markdown; };
+struct ob_qd_builder { std::unique_ptr<ob::QuantileDecompositionBuilder> b; std::string err; ob_status last = OB_OK; };
+struct ob_qd_results { ob::QuantileDecompositionResults r; std::string json, summary; };
 
 namespace {
 std::vector<std::string> strs(const char* const* names, int32_t n) {
@@ -20,8 +22,8 @@ std::vector<std::string> strs(const char* const* names, int32_t n) {
 void put_err(char* err, size_t len, const std::string& m) {
     if (err && len) { std::strncpy(err, m.c_str(), len - 1); err[len - 1] = '\0'; }
 }
-template <typename F>
-ob_status guarded(ob_builder* b, F&& f) {
+template <typename B, typename F>
+ob_status guarded(B* b, F&& f) {
     if (!b) return OB_ERR_INVALID_ARG;
     try { f(); return OB_OK; }
     catch (const ob::OaxacaError& e) { b->err = e.what(); b->last = e.kind; return e.kind; }
@@ -167,6 +169,58 @@ int64_t ob_results_residuals(const ob_results* r, double* out) {
     if (!r) return 0;
     if (out) std::memcpy(out, r->r.residuals.data(), sizeof(double) * r->r.residuals.size());
     return (int64_t)r->r.residuals.size();
+}
+
+
+/* ---- Machado-Mata: QuantileDecompositionBuilder (quantile_decomposition.rs:21-522) ---- */
+ob_qd_builder* ob_qd_builder_new(const ob_frame* f, const char* outcome, const char* group, const char* reference_group) {
+    if (!f || !outcome || !group || !reference_group) return nullptr;
+    auto b = new ob_qd_builder;
+    b->b = std::make_unique<ob::QuantileDecompositionBuilder>(f->df, outcome, group, reference_group);
+    return b;
+}
+void ob_qd_builder_free(ob_qd_builder* b) { delete b; }
+ob_status ob_qd_builder_predictors(ob_qd_builder* b, const char* const* names, int32_t n) {
+    return guarded(b, [&] { b->b->predictors(strs(names, n)); });
+}
+ob_status ob_qd_builder_categorical_predictors(ob_qd_builder* b, const char* const* names, int32_t n) {
+    return guarded(b, [&] { b->b->categorical_predictors(strs(names, n)); });
+}
+ob_status ob_qd_builder_quantiles(ob_qd_builder* b, const double* q, int32_t n) {
+    if (n < 0 || (n && !q)) return OB_ERR_INVALID_ARG;
+    return guarded(b, [&] { b->b->quantiles(std::vector<double>(q, q + n)); });
+}
+ob_status ob_qd_builder_simulations(ob_qd_builder* b, int64_t reps) {
+    if (reps < 0) return OB_ERR_INVALID_ARG;
+    return guarded(b, [&] { b->b->simulations((size_t)reps); });
+}
+ob_status ob_qd_builder_bootstrap_reps(ob_qd_builder* b, int64_t reps) {
+    if (reps < 0) return OB_ERR_INVALID_ARG;
+    return guarded(b, [&] { b->b->bootstrap_reps((size_t)reps); });
+}
+ob_status ob_qd_builder_seed(ob_qd_builder* b, uint64_t seed) { return guarded(b, [&] { b->b->seed(seed); }); }
+ob_status ob_qd_builder_device(ob_qd_builder* b, int32_t device) { return guarded(b, [&] { b->b->device(device); }); }
+ob_status ob_qd_builder_streams(ob_qd_builder* b, const uint32_t* idx_a, const uint32_t* idx_b, const double* taus,
+                                const uint32_t* draw_a, const uint32_t* draw_b) {
+    return guarded(b, [&] { b->b->streams(idx_a, idx_b, taus, draw_a, draw_b); });
+}
+ob_status ob_qd_builder_run(ob_qd_builder* b, ob_qd_results** out) {
+    if (!out) return OB_ERR_INVALID_ARG;
+    *out = nullptr;
+    return guarded(b, [&] { auto r = std::make_unique<ob_qd_results>(); r->r = b->b->run(); *out = r.release(); });
+}
+const char* ob_qd_builder_last_error(const ob_qd_builder* b) { return b ? b->err.c_str() : "null builder"; }
+ob_status ob_qd_builder_last_status(const ob_qd_builder* b) { return b ? b->last : OB_ERR_INVALID_ARG; }
+void ob_qd_results_free(ob_qd_results* r) { delete r; }
+const char* ob_qd_results_json(ob_qd_results* r) {
+    if (!r) return "";
+    r->json = r->r.to_json();
+    return r->json.c_str();
+}
+const char* ob_qd_results_summary(ob_qd_results* r) {
+    if (!r) return "";
+    std::ostringstream os; r->r.summary(os); r->summary = os.str();
+    return r->summary.c_str();
 }
 
 }  // extern "C"

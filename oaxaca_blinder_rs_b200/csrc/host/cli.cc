@@ -1,6 +1,6 @@
-// csrc/host/cli.cc -- `oaxaca-cli` front-end for the mean decomposition, same flags as the reference's clap
-// RunArgs (main.rs:44-128) and the same dispatch as run_mean_analysis (main.rs:175-232).  Analysis types other
-// than `mean` (Machado-Mata quantile, AKM, matching) are outside the B200 bootstrap path and are refused.
+// csrc/host/cli.cc -- `oaxaca-cli` front-end, same flags as the reference's clap RunArgs (main.rs:44-128) and the same
+// dispatch as run_mean_analysis (main.rs:175-232) and run_quantile_analysis (Machado-Mata, main.rs:234-258).  The other
+// analysis types (AKM, matching) are outside the B200 bootstrap path and are refused.
 #include <cerrno>
 #include <cstdio>
 #include <cstdlib>
@@ -44,7 +44,9 @@ static void usage() {
         "      --reference <REFERENCE>        Value of the group column identifying the reference group\n"
         "      --predictors <A,B,..>          Numerical predictor columns\n"
         "      --categorical <A,B,..>         Categorical predictor columns\n"
-        "      --analysis-type <TYPE>         mean (default) | quantile | akm | match  [only mean runs on the B200 path]\n"
+        "      --analysis-type <TYPE>         mean (default) | quantile (Machado-Mata) | akm | match  [mean and quantile run on the B200 path]\n"
+        "      --quantiles <A,B,..>           Quantiles to analyse (quantile analysis) [default: 0.1,0.25,0.5,0.75,0.9]\n"
+        "      --simulations <N>              Simulations of the Machado-Mata algorithm [default: 200]\n"
         "      --ref-coeffs <KIND>            group-a | group-b (default) | pooled | weighted\n"
         "      --bootstrap-reps <N>           Bootstrap replications [default: 50]\n"
         "      --formula <FORMULA>            R-style formula, e.g. \"wage ~ education + C(sector)\"\n"
@@ -69,8 +71,9 @@ int main(int argc, char** argv) {
     // typed flags, validated before any work (clap ValueEnum / typed args, main.rs:44-128): a typo must not silently
     // change which reference coefficients or how many replicates are used
     ob::ReferenceCoefficients ref_kind = ob::ReferenceCoefficients::GroupB;
-    unsigned long long reps = 0, seed = 0;
+    unsigned long long reps = 0, seed = 0, sims = 200;                                    // main.rs:86-87
     double tau = 0.0;
+    std::vector<double> quantiles = {0.1, 0.25, 0.5, 0.75, 0.9};                          // main.rs:236-239
     try {
         const std::string& rc = a["ref-coeffs"];
         if (rc == "group-a") ref_kind = ob::ReferenceCoefficients::GroupA;
@@ -80,6 +83,11 @@ int main(int argc, char** argv) {
         else throw ArgError{"invalid value '" + rc + "' for '--ref-coeffs <KIND>'\n  [possible values: group-a, group-b, pooled, weighted]"};
         reps = parse_u64("bootstrap-reps", a["bootstrap-reps"]);
         if (a.count("seed")) seed = parse_u64("seed", a["seed"]);
+        if (a.count("simulations")) sims = parse_u64("simulations", a["simulations"]);
+        if (a.count("quantiles")) {
+            quantiles.clear();
+            for (const auto& q : split_commas(a["quantiles"])) quantiles.push_back(parse_f64("quantiles", q));
+        }
         if (a.count("rif-quantile")) {
             tau = parse_f64("rif-quantile", a["rif-quantile"]);
             if (!(tau > 0.0 && tau < 1.0)) throw ArgError{"invalid value '" + a["rif-quantile"] + "' for '--rif-quantile <TAU>': must lie in (0, 1)"};
@@ -92,10 +100,20 @@ int main(int argc, char** argv) {
         for (const char* req : {"data", "outcome", "group", "reference"})
             if (!a.count(req) && !(std::string(req) == "outcome" && a.count("formula")))
                 throw ob::OaxacaError(OB_ERR_INVALID_ARG, std::string("the following required argument was not provided: --") + req);
-        if (a["analysis-type"] != "mean")
+        if (a["analysis-type"] != "mean" && a["analysis-type"] != "quantile")
             throw ob::OaxacaError(OB_ERR_UNSUPPORTED, "analysis type '" + a["analysis-type"] +
-                                  "' is outside the B200 bootstrap path (mean decomposition and RIF quantiles only)");
+                                  "' is outside the B200 bootstrap path (mean decomposition, RIF quantiles and Machado-Mata only)");
         ob::DataFrame df = ob::DataFrame::read_csv(a["data"]);
+        if (a["analysis-type"] == "quantile") {                                           // run_quantile_analysis, main.rs:234-258
+            ob::QuantileDecompositionBuilder qb(df, a["outcome"], a["group"], a["reference"]);
+            qb.predictors(split_commas(a["predictors"])).categorical_predictors(split_commas(a["categorical"]))
+              .quantiles(quantiles).bootstrap_reps((size_t)reps).simulations((size_t)sims);
+            if (a.count("seed")) qb.seed(seed);
+            const ob::QuantileDecompositionResults qr = qb.run();
+            qr.summary(std::cout);
+            if (a.count("output-json")) { std::ofstream(a["output-json"]) << qr.to_json(); }
+            return 0;
+        }
         ob::OaxacaBuilder b = a.count("formula")
             ? ob::OaxacaBuilder::from_formula(df, a["formula"], a["group"], a["reference"])
             : ob::OaxacaBuilder(df, a["outcome"], a["group"], a["reference"]);

@@ -146,3 +146,77 @@ def test_failed_pass_and_refusals():
         ob.machado_mata(des, [0.5], simulations=8, reps=0)
     assert e.value.kind == "Unsupported"
     des.close(); ctx.close()
+
+
+# ---- builder mirrors: QuantileDecompositionBuilder (quantile_decomposition.rs:21-100) ----
+def reference_frame():
+    """tests/integration_test.rs:166-172"""
+    return {"wage": [10.0, 12.0, 11.0, 13.0, 15.0, 20.0, 22.0, 21.0, 23.0, 25.0, 9.0, 18.0],
+            "education": [12.0, 16.0, 14.0, 16.0, 18.0, 12.0, 16.0, 14.0, 16.0, 18.0, 10.0, 20.0],
+            "gender": ["F", "F", "F", "F", "F", "F", "M", "M", "M", "M", "M", "M"]}
+
+
+def test_quantile_decomposition_builder_reference_test():
+    """tests/integration_test.rs:166-197, assertion for assertion."""
+    import oaxaca_blinder_rs_b200 as ob
+    b = ob.QuantileDecompositionBuilder(reference_frame(), "wage", "gender", "F")
+    results = b.predictors(["education"]).quantiles([0.25, 0.5, 0.75]).simulations(10).bootstrap_reps(2).run()
+    for key in ("q25", "q50", "q75"):
+        assert key in results.results_by_quantile
+        d = results.results_by_quantile[key]
+        assert abs(d.characteristics_effect.estimate + d.coefficients_effect.estimate - d.total_gap.estimate) < 1e-9
+        assert (d.total_gap.name, d.characteristics_effect.name, d.coefficients_effect.name) == ("Total Gap", "Characteristics", "Coefficients")
+    assert (results.n_a, results.n_b) == (6, 6)
+    s = results.summary()
+    assert "Machado-Mata Quantile Decomposition Results" in s and "--- Decomposition for Quantile: q25 ---" in s
+    assert "Group A (Advantaged): 6 observations" in s
+
+
+def test_builder_with_streams_matches_oracle(orc):
+    """The whole builder path (string group / categorical columns -> device ingest -> ob_mm_run) under explicit streams vs the
+    oracle on the matrices get_data_matrices() returns; and the reference's key format "q{(tau * 100) as u32}"
+    (quantile_decomposition.rs:277: 0.29 * 100 = 28.999999999999996 -> "q28")."""
+    import oaxaca_blinder_rs_b200 as ob
+    fr = make_frame(1200, 2, seed=31)
+    frame = {"y": fr["y"], "x0": fr["cont"][0], "x1": fr["cont"][1], "sector": np.array(["s%d" % c for c in fr["cat"]]),
+             "g": np.where(fr["group"] == 0, "A", "B")}
+    xa, ya, xb, yb = ob.OaxacaBuilder(frame, "y", "g", "B").predictors(["x0", "x1"]).categorical_predictors(["sector"]).get_data_matrices()
+    sims, reps, q = 24, 3, [0.29, 0.5, 0.9]
+    st = streams(8, reps, sims, len(ya), len(yb))
+    b = ob.QuantileDecompositionBuilder(frame, "y", "g", "B").predictors(["x0", "x1"]).categorical_predictors(["sector"])
+    res = b.quantiles(q).simulations(sims).bootstrap_reps(reps).streams(**st).run()
+    o = orc.mm_run(xa, ya, xb, yb, sims, q, reps, st["idx_a"], st["idx_b"], st["taus"], st["draw_a"], st["draw_b"], nthreads=4)
+    assert sorted(res.results_by_quantile) == ["q28", "q50", "q90"]
+    assert res.successful_bootstraps == reps and res.qr["failed"] == 0
+    for k, key in enumerate(("q28", "q50", "q90")):
+        d = res.results_by_quantile[key]
+        for j, comp in enumerate((d.total_gap, d.characteristics_effect, d.coefficients_effect)):
+            i = 3 * k + j
+            assert abs(comp.estimate - o["point_stats"][i]) <= RTOL * max(abs(o["point_stats"][i]), 1e-3)
+            assert abs(comp.std_err - o["se"][i]) <= RTOL * max(abs(o["se"][i]), 1e-3)
+            assert abs(comp.ci_lower - o["ci_lo"][i]) <= RTOL * max(abs(o["ci_lo"][i]), 1e-3)
+            assert abs(comp.t_stat - o["t"][i]) <= 1e-8 * max(abs(o["t"][i]), 1.0)
+
+
+def test_builder_null_outcome_is_an_error():
+    """prepare_data, quantile_decomposition.rs:111-118: a null outcome in one of the two groups is an error (the
+    Machado-Mata builder does not clean the frame)."""
+    import oaxaca_blinder_rs_b200 as ob
+    f = reference_frame()
+    f["wage"] = list(f["wage"]); f["wage"][3] = None
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.QuantileDecompositionBuilder(f, "wage", "gender", "F").predictors(["education"]).simulations(10).bootstrap_reps(1).run()
+    assert e.value.kind == "InvalidGroupVariable" and "Null outcome encountered" in str(e.value)
+
+
+def test_cli_quantile_decomposition(tmp_path):                     # tests/cli_test.rs:60-83
+    import subprocess
+    root = os.path.dirname(HERE)
+    cli = os.path.join(root, "oaxaca_blinder_rs_b200", "_lib", "oaxaca-cli")
+    p = subprocess.run([cli, "--data", os.path.join(HERE, "golden", "wage.csv"), "--outcome", "wage", "--group", "gender", "--reference", "F",
+                        "--predictors", "education", "--analysis-type", "quantile", "--bootstrap-reps", "2", "--simulations", "10",
+                        "--output-json", str(tmp_path / "q.json")], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    assert "Machado-Mata Quantile Decomposition Results" in p.stdout
+    d = json.load(open(tmp_path / "q.json"))
+    assert sorted(d["results_by_quantile"]) == ["q10", "q25", "q50", "q75", "q90"]       # main.rs:236-239 defaults
