@@ -26,6 +26,8 @@
 #include "common.cuh"
 #include "internal.h"
 
+#include <cstdlib>
+
 namespace ob {
 namespace {
 
@@ -47,18 +49,6 @@ struct MmShared {
     int ired[16][MM_WARPS];
     int prob, flag;
 };
-
-// raw fragment of rows i0 .. i0+3: lane (r = lane & 3, cg = lane >> 2) gets X[i0 + r][8 t + cg] for design columns and the
-// outcome column (8 t + cg <= K), zero elsewhere and on rows >= n
-template <int K8>
-__device__ __forceinline__ void load_frag(const double* __restrict__ X, int ldx, long long n, long long i0, int K, int lane,
-                                          double (&xv)[K8]) {
-    const long long row = i0 + (lane & 3);
-    const int cg = lane >> 2;
-    const double* p = X + row * ldx + cg;
-#pragma unroll
-    for (int t = 0; t < K8; ++t) xv[t] = (row < n && 8 * t + cg <= K) ? __ldg(p + 8 * t) : 0.0;
-}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -162,16 +152,32 @@ struct MmKernelArgs {
 
 constexpr int QR_VERTEX = 0, QR_APPROX = 1, QR_FAILED = 2;
 
+// The per-row iterate of a problem: six vectors in the block's slab (x, s = u - x, z, w, the affine dx, the corrected dx).
+struct St { double x, s, z, w, a, c; };
+enum : int { LX = 1, LS = 2, LZ = 4, LW = 8, LA = 16, LC = 32 };
+struct StPtr { double *x, *s, *z, *w, *a, *c; };
+template <int MASK>
+__device__ __forceinline__ void st_load(St& v, const StPtr& p, long long i, bool in) {
+    v.x = (MASK & LX) && in ? p.x[i] : 0.0;
+    v.s = (MASK & LS) && in ? p.s[i] : 0.0;
+    v.z = (MASK & LZ) && in ? p.z[i] : 0.0;
+    v.w = (MASK & LW) && in ? p.w[i] : 0.0;
+    v.a = (MASK & LA) && in ? p.a[i] : 0.0;
+    v.c = (MASK & LC) && in ? p.c[i] : 0.0;
+}
+
 // One sweep over the rows of the problem's group.  Per 32-row block (a warp owns every eighth one):
 //   DOT  : t_i = x_i'vec (vec: shared, zero beyond column K-1) and y_i, from the fragment loads
-//   rowf : lane-per-row work; returns the weight q_i and the extra column v_i of the contraction
+//   rowf : lane-per-row work on the row's iterate (the vectors named by MASK, loaded one block ahead so that their
+//          latency hides under the previous block's work); returns the weight q_i and the extra column v_i
 //   GRAM : 1 = acc += sum_i q_i [x_i | v_i][x_i | v_i]' (upper-triangle tiles), 2 = only the tiles of column K (X'Q v)
-template <int K8, bool DOT, int GRAM, typename RowF>
+template <int K8, bool DOT, int GRAM, int MASK, typename RowF>
 __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X, int ldx, long long n, int K, const double* vec,
-                                      double (&acc)[K8 * (K8 + 1) / 2][2], RowF&& rowf) {
+                                      const StPtr& sp, double (&acc)[K8 * (K8 + 1) / 2][2], RowF&& rowf) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int cg = lane >> 2, r4 = lane & 3;
     const int wb = w * 32;
+    constexpr int UNR = K8 <= 2 ? 8 : (K8 <= 4 ? 4 : 2);
     if (GRAM) {
 #pragma unroll
         for (int t = 0; t < K8 * (K8 + 1) / 2; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
@@ -182,39 +188,53 @@ __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X
         for (int t = 0; t < K8; ++t) vv[t] = vec[8 * t + cg];
     }
     const int ty = K >> 3, cy = K & 7;       // where the outcome column sits in a fragment
-    for (long long base = (long long)wb; base < n; base += MM_THREADS) {
-        if (DOT) {
-#pragma unroll 2
-            for (int ks = 0; ks < 8; ++ks) {
-                double xv[K8];
-                load_frag<K8>(X, ldx, n, base + 4 * ks, K, lane, xv);
-                double part = 0.0;
-                if (vec) {
+    bool cmask[K8];                          // which of this lane's fragment columns exist (design columns + outcome)
 #pragma unroll
-                    for (int t = 0; t < K8; ++t) part = fma(xv[t], vv[t], part);
+    for (int t = 0; t < K8; ++t) cmask[t] = 8 * t + cg <= K;
+    St nxt;
+    st_load<MASK>(nxt, sp, (long long)wb + lane, (long long)wb + lane < n);
+    for (long long base = (long long)wb; base < n; base += MM_THREADS) {
+        const St cur = nxt;
+        st_load<MASK>(nxt, sp, base + MM_THREADS + lane, base + MM_THREADS + lane < n);
+        const double* xp = X + (base + r4) * ldx + cg;
+        if (DOT) {
+#pragma unroll UNR
+            for (int ks = 0; ks < 8; ++ks) {
+                const bool rin = base + 4 * ks + r4 < n;
+                double xv[K8];
+#pragma unroll
+                for (int t = 0; t < K8; ++t) xv[t] = (rin && cmask[t]) ? __ldg(xp + (size_t)(4 * ks) * ldx + 8 * t) : 0.0;
+                double part = 0.0, yv = 0.0;
+#pragma unroll
+                for (int t = 0; t < K8; ++t) { if (vec) part = fma(xv[t], vv[t], part); if (t == ty) yv = xv[t]; }
+                if (vec) {
                     part += __shfl_xor_sync(0xffffffffu, part, 4);
                     part += __shfl_xor_sync(0xffffffffu, part, 8);
                     part += __shfl_xor_sync(0xffffffffu, part, 16);
                 }
                 if (cg == 0) sh.ts[wb + 4 * ks + r4] = part;
-                if (cg == cy) sh.ys[wb + 4 * ks + r4] = xv[ty];
+                if (cg == cy) sh.ys[wb + 4 * ks + r4] = yv;
             }
             __syncwarp();
         }
         {
             const long long i = base + lane;
             double q = 0.0, v = 0.0;
-            rowf(i, i < n, DOT ? sh.ts[wb + lane] : 0.0, DOT ? sh.ys[wb + lane] : 0.0, q, v);
+            rowf(i, i < n, DOT ? sh.ts[wb + lane] : 0.0, DOT ? sh.ys[wb + lane] : 0.0, cur, q, v);
             if (GRAM) { sh.qs[wb + lane] = q; sh.vs[wb + lane] = v; }
         }
         if (GRAM) {
             __syncwarp();
-#pragma unroll 2
+#pragma unroll UNR
             for (int ks = 0; ks < 8; ++ks) {
+                const bool rin = base + 4 * ks + r4 < n;
                 double xv[K8];
-                load_frag<K8>(X, ldx, n, base + 4 * ks, K, lane, xv);
+#pragma unroll
+                for (int t = 0; t < K8; ++t) xv[t] = (rin && cmask[t]) ? __ldg(xp + (size_t)(4 * ks) * ldx + 8 * t) : 0.0;
                 const double q = sh.qs[wb + 4 * ks + r4];
-                if (cg == cy) xv[ty] = sh.vs[wb + 4 * ks + r4];       // the extra column replaces the outcome column
+                const double ve = sh.vs[wb + 4 * ks + r4];
+#pragma unroll
+                for (int t = 0; t < K8; ++t) if (t == ty && cg == cy) xv[t] = ve;       // the extra column replaces the outcome column
                 if (GRAM == 1) {
                     int tt = 0;
 #pragma unroll
@@ -298,8 +318,8 @@ __device__ __forceinline__ double dd_residual(const double* __restrict__ xrow, d
     return hi + lo;
 }
 
-template <int K8>
-__global__ void __launch_bounds__(MM_THREADS, 2) mm_qr_kernel(const MmKernelArgs a) {
+template <int K8, int MINB>
+__global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelArgs a) {
     __shared__ MmShared sh;
     constexpr int NT = K8 * (K8 + 1) / 2;
     const int tid = threadIdx.x;
@@ -307,6 +327,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mm_qr_kernel(const MmKernelArgs
     double* const st = a.state + (size_t)blockIdx.x * 6 * a.state_stride;
     double *st_x = st, *st_s = st + a.state_stride, *st_z = st + 2 * a.state_stride, *st_w = st + 3 * a.state_stride,
            *st_dxa = st + 4 * a.state_stride, *st_dxc = st + 5 * a.state_stride;
+    const StPtr sp{st_x, st_s, st_z, st_w, st_dxa, st_dxc};
     const long long nprob = 2 * a.slots * a.sims;
     double acc[NT][2];
 
@@ -335,7 +356,7 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mm_qr_kernel(const MmKernelArgs
         double yscale, scale, usum, nact;
         {
             double r4[4] = {0.0, 0.0, 0.0, 0.0};       // max |y|, sum u |y|, sum u, active rows
-            sweep<K8, true, 1>(sh, X, ldx, n, K, nullptr, acc, [&](long long i, bool in, double, double y, double& q, double& v) {
+            sweep<K8, true, 1, 0>(sh, X, ldx, n, K, nullptr, sp, acc, [&](long long i, bool in, double, double y, const St&, double& q, double& v) {
                 double u = 0.0;
                 if (in) u = a.count_bytes == 1 ? (double)C8[(size_t)i * BM + ccol] : (double)((const unsigned short*)C8)[(size_t)i * BM + ccol];
                 if (in) st_s[i] = u;
@@ -358,9 +379,9 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mm_qr_kernel(const MmKernelArgs
             __syncthreads();
             block_chol_solve(sh, K, sh.vec[0]);
             double r1[1] = {0.0};
-            sweep<K8, true, 0>(sh, X, ldx, n, K, sh.vec[0], acc, [&](long long i, bool in, double t, double y, double&, double&) {
+            sweep<K8, true, 0, LS>(sh, X, ldx, n, K, sh.vec[0], sp, acc, [&](long long i, bool in, double t, double y, const St& c, double&, double&) {
                 if (!in) return;
-                const double u = st_s[i];
+                const double u = c.s;
                 const double r = -y - t;
                 st_z[i] = r;
                 if (u > 0.0) r1[0] += u * fabs(r);
@@ -375,32 +396,34 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mm_qr_kernel(const MmKernelArgs
             for (;;) {
                 // P1: apply the previous step (or build the starting point), new q and r, gap, Newton matrix
                 double rg[1] = {0.0};
-                sweep<K8, false, 1>(sh, X, ldx, n, K, nullptr, acc, [&](long long i, bool in, double, double, double& q, double& v) {
+                sweep<K8, false, 1, LX | LS | LZ | LW | LA | LC>(sh, X, ldx, n, K, nullptr, sp, acc,
+                                                                 [&](long long i, bool in, double, double, const St& c, double& q, double& v) {
                     if (!in) return;
                     double x, s, z, w;
                     if (first) {
-                        const double u = st_s[i];
+                        const double u = c.s;
                         if (!(u > 0.0)) { st_x[i] = 0.0; st_s[i] = 0.0; return; }
-                        const double r0 = st_z[i];
+                        const double r0 = c.z;
                         x = (1.0 - tau) * u; s = u - x;
                         z = fmax(r0, 0.0) + delta; w = fmax(-r0, 0.0) + delta;
                     } else {
-                        x = st_x[i]; s = st_s[i];
+                        x = c.x; s = c.s;
                         if (!(x + s > 0.0)) return;
-                        z = st_z[i]; w = st_w[i];
-                        const double dxa = st_dxa[i];
-                        const double dza = -z * (1.0 + dxa / x), dwa = -w * (1.0 - dxa / s);
+                        z = c.z; w = c.w;
+                        const double rx = 1.0 / x, rs = 1.0 / s;
+                        const double dxa = c.a;
+                        const double dza = -z * (1.0 + dxa * rx), dwa = -w * (1.0 - dxa * rs);
                         double dx = dxa, dz = dza, dw = dwa;
                         if (corr) {
-                            dx = st_dxc[i];
-                            dz = (mu - dxa * dza) / x - z - z / x * dx;
-                            dw = (mu + dxa * dwa) / s - w + w / s * dx;
+                            dx = c.c;
+                            dz = (mu - dxa * dza) * rx - z - z * rx * dx;
+                            dw = (mu + dxa * dwa) * rs - w + w * rs * dx;
                         }
                         x += ap * dx; s -= ap * dx; z += ad * dz; w += ad * dw;
                     }
                     st_x[i] = x; st_s[i] = s; st_z[i] = z; st_w[i] = w;
                     rg[0] += z * x + w * s;
-                    q = 1.0 / (z / x + w / s);
+                    q = (x * s) / (z * s + w * x);
                     v = z - w;
                 });
                 block_reduce<1>(sh, rg, ops1);
@@ -415,25 +438,26 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mm_qr_kernel(const MmKernelArgs
                 __syncthreads();
                 block_chol_solve(sh, K, sh.vec[1]);
                 // P2: affine step, ratio test, the sums that give the gap after the step
-                double r2[4] = {1e300, 1e300, 0.0, 0.0};
-                sweep<K8, true, 0>(sh, X, ldx, n, K, sh.vec[1], acc, [&](long long i, bool in, double t, double, double&, double&) {
+                double r2[4] = {0.0, 0.0, 0.0, 0.0};        // 1 / primal step limit, 1 / dual step limit, S1, S3
+                sweep<K8, true, 0, LX | LS | LZ | LW>(sh, X, ldx, n, K, sh.vec[1], sp, acc,
+                                                      [&](long long i, bool in, double t, double, const St& c, double&, double&) {
                     if (!in) return;
-                    const double x = st_x[i], s = st_s[i];
+                    const double x = c.x, s = c.s;
                     if (!(x + s > 0.0)) return;
-                    const double z = st_z[i], w = st_w[i];
-                    const double q = 1.0 / (z / x + w / s), r = z - w;
+                    const double z = c.z, w = c.w;
+                    const double rx = 1.0 / x, rs = 1.0 / s;
+                    const double q = 1.0 / (z * rx + w * rs), r = z - w;
                     const double dx = q * (t - r);
-                    const double dz = -z * (1.0 + dx / x), dw = -w * (1.0 - dx / s);
+                    const double dz = -z * (1.0 + dx * rx), dw = -w * (1.0 - dx * rs);
                     st_dxa[i] = dx;
-                    if (dx < 0.0) r2[0] = fmin(r2[0], -x / dx);
-                    if (dx > 0.0) r2[0] = fmin(r2[0], s / dx);
-                    if (dz < 0.0) r2[1] = fmin(r2[1], -z / dz);
-                    if (dw < 0.0) r2[1] = fmin(r2[1], -w / dw);
+                    // ratio tests: the largest step keeping x, s, z, w positive (as reciprocals: no division per row)
+                    r2[0] = fmax(r2[0], fmax(-dx * rx, dx * rs));
+                    r2[1] = fmax(r2[1], fmax(1.0 + dx * rx, 1.0 - dx * rs));
                     r2[2] += dx * r; r2[3] += dx * (dz - dw);
                 });
-                const int ops2[4] = {1, 1, 0, 0};
+                const int ops2[4] = {2, 2, 0, 0};
                 block_reduce<4>(sh, r2, ops2);
-                ap = fmin(0.99995 * r2[0], 1.0); ad = fmin(0.99995 * r2[1], 1.0);
+                ap = fmin(0.99995 / r2[0], 1.0); ad = fmin(0.99995 / r2[1], 1.0);
                 corr = fmin(ap, ad) < 1.0;
                 if (corr) {
                     const double gaff = gap + ap * r2[2] + ad * (-gap - r2[2]) + ap * ad * r2[3];
@@ -441,39 +465,41 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mm_qr_kernel(const MmKernelArgs
                     mu = gap * ratio * ratio * ratio / (2.0 * nact);
                     if (!(mu >= 0.0)) mu = 0.0;
                     // P3: right-hand side of the corrector
-                    sweep<K8, false, 2>(sh, X, ldx, n, K, nullptr, acc, [&](long long i, bool in, double, double, double& q, double& v) {
+                    sweep<K8, false, 2, LX | LS | LZ | LW | LA>(sh, X, ldx, n, K, nullptr, sp, acc,
+                                                                [&](long long, bool in, double, double, const St& c, double& q, double& v) {
                         if (!in) return;
-                        const double x = st_x[i], s = st_s[i];
+                        const double x = c.x, s = c.s;
                         if (!(x + s > 0.0)) return;
-                        const double z = st_z[i], w = st_w[i], dx = st_dxa[i];
-                        const double dz = -z * (1.0 + dx / x), dw = -w * (1.0 - dx / s);
-                        q = 1.0 / (z / x + w / s);
-                        v = (z - w) + mu * (1.0 / s - 1.0 / x) + dx * dz / x + dx * dw / s;
+                        const double z = c.z, w = c.w, dx = c.a;
+                        const double rx = 1.0 / x, rs = 1.0 / s;
+                        const double dz = -z * (1.0 + dx * rx), dw = -w * (1.0 - dx * rs);
+                        q = 1.0 / (z * rx + w * rs);
+                        v = (z - w) + mu * (rs - rx) + dx * dz * rx + dx * dw * rs;
                     });
                     rhs_to_shared<K8>(sh, acc, K, sh.vec[1]);
                     block_chol_solve(sh, K, sh.vec[1]);
                     // P4: corrected step and its ratio test
-                    double r3[2] = {1e300, 1e300};
-                    sweep<K8, true, 0>(sh, X, ldx, n, K, sh.vec[1], acc, [&](long long i, bool in, double t, double, double&, double&) {
+                    double r3[2] = {0.0, 0.0};
+                    sweep<K8, true, 0, LX | LS | LZ | LW | LA>(sh, X, ldx, n, K, sh.vec[1], sp, acc,
+                                                               [&](long long i, bool in, double t, double, const St& c, double&, double&) {
                         if (!in) return;
-                        const double x = st_x[i], s = st_s[i];
+                        const double x = c.x, s = c.s;
                         if (!(x + s > 0.0)) return;
-                        const double z = st_z[i], w = st_w[i], dxa = st_dxa[i];
-                        const double dza = -z * (1.0 + dxa / x), dwa = -w * (1.0 - dxa / s);
-                        const double q = 1.0 / (z / x + w / s);
-                        const double xi = (z - w) + mu * (1.0 / s - 1.0 / x) + dxa * dza / x + dxa * dwa / s;
+                        const double z = c.z, w = c.w, dxa = c.a;
+                        const double rx = 1.0 / x, rs = 1.0 / s;
+                        const double dza = -z * (1.0 + dxa * rx), dwa = -w * (1.0 - dxa * rs);
+                        const double q = 1.0 / (z * rx + w * rs);
+                        const double xi = (z - w) + mu * (rs - rx) + dxa * dza * rx + dxa * dwa * rs;
                         const double dx = q * (t - xi);
-                        const double dz = (mu - dxa * dza) / x - z - z / x * dx;
-                        const double dw = (mu + dxa * dwa) / s - w + w / s * dx;
+                        const double dz = (mu - dxa * dza) * rx - z - z * rx * dx;
+                        const double dw = (mu + dxa * dwa) * rs - w + w * rs * dx;
                         st_dxc[i] = dx;
-                        if (dx < 0.0) r3[0] = fmin(r3[0], -x / dx);
-                        if (dx > 0.0) r3[0] = fmin(r3[0], s / dx);
-                        if (dz < 0.0) r3[1] = fmin(r3[1], -z / dz);
-                        if (dw < 0.0) r3[1] = fmin(r3[1], -w / dw);
+                        r3[0] = fmax(r3[0], fmax(-dx * rx, dx * rs));
+                        r3[1] = fmax(r3[1], fmax(-dz / z, -dw / w));
                     });
-                    const int ops3[2] = {1, 1};
+                    const int ops3[2] = {2, 2};
                     block_reduce<2>(sh, r3, ops3);
-                    ap = fmin(0.99995 * r3[0], 1.0); ad = fmin(0.99995 * r3[1], 1.0);
+                    ap = fmin(0.99995 / r3[0], 1.0); ad = fmin(0.99995 / r3[1], 1.0);
                 }
                 // one step length for both iterates: separate ones lose centrality at the extreme quantiles (tau near 0.01 /
                 // 0.99: iteration counts of 100 and more instead of ~20)
@@ -492,10 +518,9 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mm_qr_kernel(const MmKernelArgs
             int cnt[12];
 #pragma unroll
             for (int j = 0; j < 12; ++j) cnt[j] = 0;
-            sweep<K8, true, 0>(sh, X, ldx, n, K, sh.vec[2], acc, [&](long long i, bool in, double t, double y, double&, double&) {
+            sweep<K8, true, 0, LX | LS>(sh, X, ldx, n, K, sh.vec[2], sp, acc, [&](long long i, bool in, double t, double y, const St& c, double&, double&) {
                 if (!in) return;
-                const double x = st_x[i], s = st_s[i];
-                if (!(x + s > 0.0)) return;
+                if (!(c.x + c.s > 0.0)) return;
                 const double res = y - t;
                 st_dxa[i] = res;
                 double th = yscale * 1e-3;
@@ -569,11 +594,10 @@ __global__ void __launch_bounds__(MM_THREADS, 2) mm_qr_kernel(const MmKernelArgs
                     __syncthreads();
                 }
                 double bad[1] = {0.0};
-                sweep<K8, true, 0>(sh, X, ldx, n, K, sh.vec[3], acc, [&](long long i, bool in, double t, double y, double&, double&) {
+                sweep<K8, true, 0, LX | LS | LA>(sh, X, ldx, n, K, sh.vec[3], sp, acc, [&](long long, bool in, double t, double y, const St& c, double&, double&) {
                     if (!in) return;
-                    const double x = st_x[i], s = st_s[i];
-                    if (!(x + s > 0.0)) return;
-                    const double res0 = st_dxa[i], res = y - t;
+                    if (!(c.x + c.s > 0.0)) return;
+                    const double res0 = c.a, res = y - t;
                     if (fabs(res0) < thr) { if (fabs(res) > 1e-11 * yscale) bad[0] += 1.0; }
                     else if ((res > 0.0) != (res0 > 0.0)) bad[0] += 1.0;
                 });
@@ -709,26 +733,34 @@ __global__ void __launch_bounds__(256) mm_effects_kernel(const double* Xa, const
 
 int mm_state_vectors() { return 6; }
 
-int mm_blocks_per_sm(int K) {
-    (void)K;
-    return 2;
+// resident blocks per SM the kernel is compiled for (register budget 65536 / (256 MINB))
+static int mm_minb(int K) {
+    const int K8 = (K + 1 + 7) / 8;
+    int minb = K8 <= 3 ? 3 : 2;
+    if (const char* e = getenv("OBBOOT_MM_MINB")) { const int v = atoi(e); if (v >= 2 && v <= 4 && K8 <= 3) minb = v; }
+    return minb;
 }
+int mm_blocks_per_sm(int K) { return mm_minb(K); }
 
 void mm_qr_launch(const MmArgs& m, int grid, cudaStream_t st) {
     MmKernelArgs a;
     for (int g = 0; g < 2; ++g) { a.X[g] = m.X[g]; a.C[g] = m.C[g]; a.n[g] = m.n[g]; a.n_pad[g] = m.n_pad[g]; }
     a.ldx = m.ldx; a.K = m.K; a.count_bytes = m.count_bytes; a.sims = m.sims; a.slots = m.slots; a.taus = m.taus;
     a.state = m.state; a.state_stride = m.state_stride; a.betas = m.betas; a.info = m.info; a.counter = m.counter;
-    const int K8 = (m.K + 1 + 7) / 8;
+    const int K8 = (m.K + 1 + 7) / 8, minb = mm_minb(m.K);
+#define OB_MM(K8_, MB_) mm_qr_kernel<K8_, MB_><<<grid, MM_THREADS, 0, st>>>(a)
+#define OB_MM3(K8_) do { if (minb == 4) OB_MM(K8_, 4); else if (minb == 3) OB_MM(K8_, 3); else OB_MM(K8_, 2); } while (0)
     switch (K8) {
-    case 1: mm_qr_kernel<1><<<grid, MM_THREADS, 0, st>>>(a); break;
-    case 2: mm_qr_kernel<2><<<grid, MM_THREADS, 0, st>>>(a); break;
-    case 3: mm_qr_kernel<3><<<grid, MM_THREADS, 0, st>>>(a); break;
-    case 4: mm_qr_kernel<4><<<grid, MM_THREADS, 0, st>>>(a); break;
-    case 5: mm_qr_kernel<5><<<grid, MM_THREADS, 0, st>>>(a); break;
-    case 6: mm_qr_kernel<6><<<grid, MM_THREADS, 0, st>>>(a); break;
+    case 1: OB_MM3(1); break;
+    case 2: OB_MM3(2); break;
+    case 3: OB_MM3(3); break;
+    case 4: OB_MM(4, 2); break;
+    case 5: OB_MM(5, 2); break;
+    case 6: OB_MM(6, 2); break;
     default: throw StatusError{OB_ERR_UNSUPPORTED, "Machado-Mata: more than 47 design columns"};
     }
+#undef OB_MM3
+#undef OB_MM
     OB_CUDA(cudaGetLastError());
 }
 
