@@ -353,6 +353,47 @@ def nccl_selftest(ob, obd, ctx, rank, world, dist, torch):
             "shape": "n=300k, K=10, WLS + Yun, B=200, every rank compared with its own unsharded run"}
 
 
+def measure_machado_mata(ob, ctx, threads, n=200_000, n_cont=7, sims=200, reps=20, steps=2):
+    """SURVEY 8f-3 beside the headline: the Machado-Mata decomposition (ob_mm_run; QuantileDecompositionBuilder defaults:
+    200 simulations, 20 bootstrap passes, 5 quantiles) on synthetic wage data, n = 2e5 rows, K = 1 + 7 + 2 columns:
+    (reps + 1) x sims x 2 = 8400 quantile regressions per step, each solved to the LP's vertex.  CPU: the oracle port's
+    solver on a bounded sample of the same regressions, one per host thread."""
+    import concurrent.futures as cf
+    from oaxaca_blinder_rs_b200 import synth
+    from oracle import pyoracle as orc
+    d = synth.make_wage(n, n_cont, cat_levels=(3,), weights=False, seed=7)
+    des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], None, d["group"])
+    q = [0.1, 0.25, 0.5, 0.75, 0.9]
+    ob.machado_mata(des, q, simulations=16, reps=1, seed=1)              # warm-up
+    runs = []
+    for it in range(steps):
+        t0 = time.perf_counter()
+        r = ob.machado_mata(des, q, simulations=sims, reps=reps, seed=10 + it)
+        runs.append((time.perf_counter() - t0, r))
+    dt, r = min(runs, key=lambda x: x[0])
+    K, na = des.K, des.n_a
+    nprob = r["qr"]["total"]
+    X = np.c_[np.ones(n), np.stack(d["cont"], 1), d["cat_codes"][0] == 1, d["cat_codes"][0] == 2].astype(np.float64)
+    A = d["group"] == 0
+    Xa, ya = np.ascontiguousarray(X[A]), np.ascontiguousarray(d["outcome"][A])
+    des.close()
+    taus = np.random.default_rng(0).uniform(0.01, 0.99, size=max(threads, 1))
+    orc.qr(Xa[:1000], ya[:1000], 0.5)
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(max(threads, 1)) as ex:                    # ctypes releases the GIL: one regression per host thread
+        infos = list(ex.map(lambda t: orc.qr(Xa, ya, float(t))[1], taus))
+    cdt = time.perf_counter() - t0
+    return {"what": "ob_mm_run: Machado-Mata quantile decomposition (quantile_decomposition.rs:281-421), every quantile "
+                    "regression solved on the device to the LP's vertex (interior point + polish)",
+            "workload": f"synthetic wage n={n} (n_a={na}), K={K}, simulations={sims}, bootstrap_reps={reps}, 5 target quantiles",
+            "regressions_per_step": nprob, "seconds_per_step": dt, "regressions_per_s": nprob / dt, "passes_per_s": (reps + 1) / dt,
+            "qr_kernel_ms": r["timings_ms"]["qr"], "mean_ip_iterations": r["qr"]["iterations"] / max(nprob, 1),
+            "qr_status": {k: r["qr"][k] for k in ("vertex", "approx", "failed")}, "gpu_launches": r["gpu_launches"],
+            "cpu_baseline": {"value": len(taus) / cdt, "unit": "regressions/s", "cores": int(threads), "kind": "port",
+                             "sample": f"{len(taus)} regressions of group A ({na} rows) at random quantiles, one per thread, {cdt:.1f} s; "
+                                       f"mean {np.mean([i['iters'] for i in infos]):.1f} interior-point iterations"}}
+
+
 def measure_also(name, ob, obd, ctx, torch, dist, rank, world, local, shard_rows, rif_tau, steps=2):
     """A BASELINE config other than the headline one at the same N (the row-sharded config 5, the RIF config 4), so
     that the driver's multi-GPU record holds them too: resident reps/s over `steps` steps after one warm-up, Gram
@@ -761,6 +802,11 @@ def main():
                                     "sample": f"{reps_cpu} replicates + point pass, full n, {cdt:.1f} s on {threads} of {cores} cores"}
             line["readme_shape"] = readme_calibration_cpu(min(cores, 64))
             line["readme_shape"]["gpu_seconds_e2e"] = readme_shape_gpu(ob, ctx)
+            if name.startswith("config3"):
+                try:
+                    line["machado_mata"] = measure_machado_mata(ob, ctx, threads)
+                except Exception as e:                     # never lose the headline line to the side measurement
+                    line["machado_mata"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
