@@ -40,7 +40,7 @@ constexpr int MM_MAXKP = 8 * MM_MAXK8;
 struct MmShared {
     double G[MM_MAXKP * MM_MAXKP];    // Gram of the current Newton system, then its Cholesky factor (lower triangle)
     double vec[4][MM_MAXKP];          // [0] yd (dual of the equality constraints; beta = -yd)  [1] step / rhs  [2] beta  [3] polish iterate
-    double ts[MM_THREADS], ys[MM_THREADS], qs[MM_THREADS], vs[MM_THREADS];
+    double ts[MM_THREADS], ys[MM_THREADS], qs[MM_THREADS], vs[MM_THREADS], vs2[MM_THREADS];
     double diag[MM_MAXKP], rhs[MM_MAXKP];   // diagonal of the matrix being factored (rank test), column K of the Gram
     double red[8][MM_WARPS];
     double ah[MM_MAXC];
@@ -170,7 +170,8 @@ __device__ __forceinline__ void st_load(St& v, const StPtr& p, long long i, bool
 //   DOT  : t_i = x_i'vec (vec: shared, zero beyond column K-1) and y_i, from the fragment loads
 //   rowf : lane-per-row work on the row's iterate (the vectors named by MASK, loaded one block ahead so that their
 //          latency hides under the previous block's work); returns the weight q_i and the extra column v_i
-//   GRAM : 1 = acc += sum_i q_i [x_i | v_i][x_i | v_i]' (upper-triangle tiles), 2 = only the tiles of column K (X'Q v)
+//   GRAM : 1 = acc += sum_i q_i [x_i | v_i][x_i | v_i]' (upper-triangle tiles), 2 = only the tiles of column K (X'Q v),
+//          3 = two right-hand sides at once: acc[jt] = (X'Q v, X'Q v2) for the design columns of tile jt
 template <int K8, bool DOT, int GRAM, int MASK, typename RowF>
 __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X, int ldx, long long n, int K, const double* vec,
                                       const StPtr& sp, double (&acc)[K8 * (K8 + 1) / 2][2], RowF&& rowf) {
@@ -187,10 +188,11 @@ __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X
 #pragma unroll
         for (int t = 0; t < K8; ++t) vv[t] = vec[8 * t + cg];
     }
-    const int ty = K >> 3, cy = K & 7;       // where the outcome column sits in a fragment
-    bool cmask[K8];                          // which of this lane's fragment columns exist (design columns + outcome)
-#pragma unroll
-    for (int t = 0; t < K8; ++t) cmask[t] = 8 * t + cg <= K;
+    // The outcome column K sits in the last fragment tile (K8 = K / 8 + 1), at lane group cy; the tiles before it are
+    // full, only the last one is masked (columns beyond K, possibly beyond the row).  Rows need no mask: a 32-row block
+    // that starts below n ends below n_pad (a multiple of 32), and the design's pad rows are zero.
+    const int cy = K & 7;
+    const bool clast = 8 * (K8 - 1) + cg <= K;
     St nxt;
     st_load<MASK>(nxt, sp, (long long)wb + lane, (long long)wb + lane < n);
     for (long long base = (long long)wb; base < n; base += MM_THREADS) {
@@ -200,14 +202,16 @@ __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X
         if (DOT) {
 #pragma unroll UNR
             for (int ks = 0; ks < 8; ++ks) {
-                const bool rin = base + 4 * ks + r4 < n;
                 double xv[K8];
+                const double* xr = xp + (size_t)(4 * ks) * ldx;
 #pragma unroll
-                for (int t = 0; t < K8; ++t) xv[t] = (rin && cmask[t]) ? __ldg(xp + (size_t)(4 * ks) * ldx + 8 * t) : 0.0;
-                double part = 0.0, yv = 0.0;
-#pragma unroll
-                for (int t = 0; t < K8; ++t) { if (vec) part = fma(xv[t], vv[t], part); if (t == ty) yv = xv[t]; }
+                for (int t = 0; t < K8 - 1; ++t) xv[t] = __ldg(xr + 8 * t);
+                xv[K8 - 1] = clast ? __ldg(xr + 8 * (K8 - 1)) : 0.0;
+                double part = 0.0;
+                const double yv = xv[K8 - 1];
                 if (vec) {
+#pragma unroll
+                    for (int t = 0; t < K8; ++t) part = fma(xv[t], vv[t], part);
                     part += __shfl_xor_sync(0xffffffffu, part, 4);
                     part += __shfl_xor_sync(0xffffffffu, part, 8);
                     part += __shfl_xor_sync(0xffffffffu, part, 16);
@@ -219,22 +223,23 @@ __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X
         }
         {
             const long long i = base + lane;
-            double q = 0.0, v = 0.0;
-            rowf(i, i < n, DOT ? sh.ts[wb + lane] : 0.0, DOT ? sh.ys[wb + lane] : 0.0, cur, q, v);
+            double q = 0.0, v = 0.0, v2 = 0.0;
+            rowf(i, i < n, DOT ? sh.ts[wb + lane] : 0.0, DOT ? sh.ys[wb + lane] : 0.0, cur, q, v, v2);
             if (GRAM) { sh.qs[wb + lane] = q; sh.vs[wb + lane] = v; }
+            if (GRAM == 3) sh.vs2[wb + lane] = v2;
         }
         if (GRAM) {
             __syncwarp();
 #pragma unroll UNR
             for (int ks = 0; ks < 8; ++ks) {
-                const bool rin = base + 4 * ks + r4 < n;
                 double xv[K8];
+                const double* xr = xp + (size_t)(4 * ks) * ldx;
 #pragma unroll
-                for (int t = 0; t < K8; ++t) xv[t] = (rin && cmask[t]) ? __ldg(xp + (size_t)(4 * ks) * ldx + 8 * t) : 0.0;
+                for (int t = 0; t < K8 - 1; ++t) xv[t] = __ldg(xr + 8 * t);
+                xv[K8 - 1] = clast ? __ldg(xr + 8 * (K8 - 1)) : 0.0;
                 const double q = sh.qs[wb + 4 * ks + r4];
                 const double ve = sh.vs[wb + 4 * ks + r4];
-#pragma unroll
-                for (int t = 0; t < K8; ++t) if (t == ty && cg == cy) xv[t] = ve;       // the extra column replaces the outcome column
+                if (cg == cy) xv[K8 - 1] = ve;       // the extra column replaces the outcome column
                 if (GRAM == 1) {
                     int tt = 0;
 #pragma unroll
@@ -243,9 +248,14 @@ __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X
 #pragma unroll
                         for (int lt = jt; lt < K8; ++lt, ++tt) dmma884(acc[tt][0], acc[tt][1], a, xv[lt]);
                     }
-                } else {
+                } else if (GRAM == 2) {
 #pragma unroll
                     for (int jt = 0; jt < K8; ++jt) dmma884(acc[jt][0], acc[jt][1], q * xv[jt], xv[K8 - 1]);
+                } else {
+                    // B tile: column 0 = v, column 1 = v2 of the row (lane holds B[row r4][column cg])
+                    const double b = cg == 0 ? ve : (cg == 1 ? sh.vs2[wb + 4 * ks + r4] : 0.0);
+#pragma unroll
+                    for (int jt = 0; jt < K8; ++jt) dmma884(acc[jt][0], acc[jt][1], q * xv[jt], b);
                 }
             }
         }
@@ -288,6 +298,25 @@ __device__ void rhs_to_shared(MmShared& sh, const double (&acc)[K8 * (K8 + 1) / 
                 const int row = 8 * jt + (lane >> 2);
                 if (row < K && col == K) out[row] += acc[jt][0];         // rows >= K stay zero: `out` is used as a padded vector
                 if (row < K && col + 1 == K) out[row] += acc[jt][1];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// GRAM == 3: lanes with (lane & 3) == 0 hold columns 0 and 1 of D rows 8 jt + lane / 4 -> out1, out2 [0..K)
+template <int K8>
+__device__ void rhs2_to_shared(MmShared& sh, const double (&acc)[K8 * (K8 + 1) / 2][2], int K, double* out1, double* out2) {
+    (void)sh;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x < MM_MAXKP) { out1[threadIdx.x] = 0.0; out2[threadIdx.x] = 0.0; }
+    __syncthreads();
+    for (int turn = 0; turn < MM_WARPS; ++turn) {
+        if (w == turn && (lane & 3) == 0) {
+#pragma unroll
+            for (int jt = 0; jt < K8; ++jt) {
+                const int row = 8 * jt + (lane >> 2);
+                if (row < K) { out1[row] += acc[jt][0]; out2[row] += acc[jt][1]; }
             }
         }
         __syncthreads();
@@ -356,7 +385,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
         double yscale, scale, usum, nact;
         {
             double r4[4] = {0.0, 0.0, 0.0, 0.0};       // max |y|, sum u |y|, sum u, active rows
-            sweep<K8, true, 1, 0>(sh, X, ldx, n, K, nullptr, sp, acc, [&](long long i, bool in, double, double y, const St&, double& q, double& v) {
+            sweep<K8, true, 1, 0>(sh, X, ldx, n, K, nullptr, sp, acc, [&](long long i, bool in, double, double y, const St&, double& q, double& v, double&) {
                 double u = 0.0;
                 if (in) u = a.count_bytes == 1 ? (double)C8[(size_t)i * BM + ccol] : (double)((const unsigned short*)C8)[(size_t)i * BM + ccol];
                 if (in) st_s[i] = u;
@@ -379,7 +408,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
             __syncthreads();
             block_chol_solve(sh, K, sh.vec[0]);
             double r1[1] = {0.0};
-            sweep<K8, true, 0, LS>(sh, X, ldx, n, K, sh.vec[0], sp, acc, [&](long long i, bool in, double t, double y, const St& c, double&, double&) {
+            sweep<K8, true, 0, LS>(sh, X, ldx, n, K, sh.vec[0], sp, acc, [&](long long i, bool in, double t, double y, const St& c, double&, double&, double&) {
                 if (!in) return;
                 const double u = c.s;
                 const double r = -y - t;
@@ -397,7 +426,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
                 // P1: apply the previous step (or build the starting point), new q and r, gap, Newton matrix
                 double rg[1] = {0.0};
                 sweep<K8, false, 1, LX | LS | LZ | LW | LA | LC>(sh, X, ldx, n, K, nullptr, sp, acc,
-                                                                 [&](long long i, bool in, double, double, const St& c, double& q, double& v) {
+                                                                 [&](long long i, bool in, double, double, const St& c, double& q, double& v, double&) {
                     if (!in) return;
                     double x, s, z, w;
                     if (first) {
@@ -437,19 +466,24 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
                 if (tid < MM_MAXKP) sh.vec[1][tid] = sh.rhs[tid];
                 __syncthreads();
                 block_chol_solve(sh, K, sh.vec[1]);
-                // P2: affine step, ratio test, the sums that give the gap after the step
+                // P2: affine step, ratio test, the sums that give the gap after the step -- and the two vectors the
+                // corrector's right-hand side is linear in: X'Q xi = X'Q r + mu X'Q (1/s - 1/x) + X'Q (dx dz / x + dx dw / s),
+                // so the corrector needs no sweep of its own for its right-hand side
                 double r2[4] = {0.0, 0.0, 0.0, 0.0};        // 1 / primal step limit, 1 / dual step limit, S1, S3
-                sweep<K8, true, 0, LX | LS | LZ | LW>(sh, X, ldx, n, K, sh.vec[1], sp, acc,
-                                                      [&](long long i, bool in, double t, double, const St& c, double&, double&) {
+                sweep<K8, true, 3, LX | LS | LZ | LW>(sh, X, ldx, n, K, sh.vec[1], sp, acc,
+                                                      [&](long long i, bool in, double t, double, const St& c, double& q, double& v, double& v2) {
                     if (!in) return;
                     const double x = c.x, s = c.s;
                     if (!(x + s > 0.0)) return;
                     const double z = c.z, w = c.w;
                     const double rx = 1.0 / x, rs = 1.0 / s;
-                    const double q = 1.0 / (z * rx + w * rs), r = z - w;
+                    q = 1.0 / (z * rx + w * rs);
+                    const double r = z - w;
                     const double dx = q * (t - r);
                     const double dz = -z * (1.0 + dx * rx), dw = -w * (1.0 - dx * rs);
                     st_dxa[i] = dx;
+                    v = rs - rx;
+                    v2 = dx * dz * rx + dx * dw * rs;
                     // ratio tests: the largest step keeping x, s, z, w positive (as reciprocals: no division per row)
                     r2[0] = fmax(r2[0], fmax(-dx * rx, dx * rs));
                     r2[1] = fmax(r2[1], fmax(1.0 + dx * rx, 1.0 - dx * rs));
@@ -464,24 +498,14 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
                     const double ratio = gaff / gap;
                     mu = gap * ratio * ratio * ratio / (2.0 * nact);
                     if (!(mu >= 0.0)) mu = 0.0;
-                    // P3: right-hand side of the corrector
-                    sweep<K8, false, 2, LX | LS | LZ | LW | LA>(sh, X, ldx, n, K, nullptr, sp, acc,
-                                                                [&](long long, bool in, double, double, const St& c, double& q, double& v) {
-                        if (!in) return;
-                        const double x = c.x, s = c.s;
-                        if (!(x + s > 0.0)) return;
-                        const double z = c.z, w = c.w, dx = c.a;
-                        const double rx = 1.0 / x, rs = 1.0 / s;
-                        const double dz = -z * (1.0 + dx * rx), dw = -w * (1.0 - dx * rs);
-                        q = 1.0 / (z * rx + w * rs);
-                        v = (z - w) + mu * (rs - rx) + dx * dz * rx + dx * dw * rs;
-                    });
-                    rhs_to_shared<K8>(sh, acc, K, sh.vec[1]);
+                    rhs2_to_shared<K8>(sh, acc, K, sh.vec[1], sh.ah);
+                    if (tid < K) sh.vec[1][tid] = sh.rhs[tid] + mu * sh.vec[1][tid] + sh.ah[tid];
+                    __syncthreads();
                     block_chol_solve(sh, K, sh.vec[1]);
                     // P4: corrected step and its ratio test
                     double r3[2] = {0.0, 0.0};
                     sweep<K8, true, 0, LX | LS | LZ | LW | LA>(sh, X, ldx, n, K, sh.vec[1], sp, acc,
-                                                               [&](long long i, bool in, double t, double, const St& c, double&, double&) {
+                                                               [&](long long i, bool in, double t, double, const St& c, double&, double&, double&) {
                         if (!in) return;
                         const double x = c.x, s = c.s;
                         if (!(x + s > 0.0)) return;
@@ -518,7 +542,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
             int cnt[12];
 #pragma unroll
             for (int j = 0; j < 12; ++j) cnt[j] = 0;
-            sweep<K8, true, 0, LX | LS>(sh, X, ldx, n, K, sh.vec[2], sp, acc, [&](long long i, bool in, double t, double y, const St& c, double&, double&) {
+            sweep<K8, true, 0, LX | LS>(sh, X, ldx, n, K, sh.vec[2], sp, acc, [&](long long i, bool in, double t, double y, const St& c, double&, double&, double&) {
                 if (!in) return;
                 if (!(c.x + c.s > 0.0)) return;
                 const double res = y - t;
@@ -594,7 +618,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
                     __syncthreads();
                 }
                 double bad[1] = {0.0};
-                sweep<K8, true, 0, LX | LS | LA>(sh, X, ldx, n, K, sh.vec[3], sp, acc, [&](long long, bool in, double t, double y, const St& c, double&, double&) {
+                sweep<K8, true, 0, LX | LS | LA>(sh, X, ldx, n, K, sh.vec[3], sp, acc, [&](long long, bool in, double t, double y, const St& c, double&, double&, double&) {
                     if (!in) return;
                     if (!(c.x + c.s > 0.0)) return;
                     const double res0 = c.a, res = y - t;

@@ -220,3 +220,45 @@ def test_cli_quantile_decomposition(tmp_path):                     # tests/cli_t
     assert "Machado-Mata Quantile Decomposition Results" in p.stdout
     d = json.load(open(tmp_path / "q.json"))
     assert sorted(d["results_by_quantile"]) == ["q10", "q25", "q50", "q75", "q90"]       # main.rs:236-239 defaults
+
+
+@pytest.mark.parametrize("world,reps", [(2, 9), (3, 4)])
+def test_mm_library_replicate_sharding_is_bit_identical(world, reps):
+    """Mode R for the Machado-Mata passes (ob_mm_opts.shard_replicates): every rank holds the design, takes its share of
+    the bootstrap passes, the pass rows are all-gathered over the context's communicator and reduced on every rank:
+    bit-identical to one GPU.  `world` contexts of one process joined by the in-process communicator (the transport is
+    the only difference to NCCL)."""
+    import threading
+    import oaxaca_blinder_rs_b200 as ob
+    from oaxaca_blinder_rs_b200 import core
+    fr = make_frame(2000, 2, seed=5)
+    kw = dict(quantiles=[0.1, 0.5, 0.9], simulations=32, reps=reps, seed=4, want_rep=True)
+
+    def pack(ctx):
+        return ob.Design.pack(ctx, fr["cont"], [fr["cat"]], [3], fr["y"], None, fr["group"])
+    ctx = ob.Context(0)
+    des = pack(ctx)
+    one = ob.machado_mata(des, **kw)
+    des.close(); ctx.close()
+    grp = core.LocalGroup(world)
+    outs, errs = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            c = ob.Context(0)
+            c.init_local(grp, r)
+            d = pack(c)
+            outs[r] = ob.machado_mata(d, shard_replicates=True, **kw)
+            d.close(); c.close()
+        except Exception as e:  # noqa: BLE001
+            errs[r] = e
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert all(e is None for e in errs), errs
+    for o in outs:
+        assert o["n_ok"] == one["n_ok"] == reps and o["rep_stats"].shape == one["rep_stats"].shape
+        for k in ("point_stats", "rep_stats", "rep_status", "std_err", "p_value", "ci_lower", "ci_upper", "t_stat"):
+            assert np.array_equal(np.nan_to_num(o[k], nan=-7.0), np.nan_to_num(one[k], nan=-7.0)), k
