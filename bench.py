@@ -344,13 +344,24 @@ def nccl_selftest(ob, obd, ctx, rank, world, dist, torch):
         mode_n = ob.bootstrap(shard, reps, max_workspace_bytes=200_000_000, **kw)      # several panel batches
         shard.close()
         ok_n = all(same(mode_n[k], one[k]) for k in keys)
-    flags = torch.tensor([int(ok_r), int(ok_n is not False)], device="cuda")
+    # the Machado-Mata passes under mode R (ob_mm_opts.shard_replicates): pass rows gathered over the same communicator
+    dm = synth.make_wage(20_000, 3, cat_levels=(3,), weights=False, seed=6)
+    mdes = ob.Design.pack(ctx, dm["cont"], dm["cat_codes"], dm["cat_levels"], dm["outcome"], None, dm["group"])
+    mkw = dict(quantiles=[0.1, 0.5, 0.9], simulations=32, reps=2 * world + 1, seed=3, want_rep=True)
+    m_one = ob.machado_mata(mdes, **mkw)
+    m_r = ob.machado_mata(mdes, shard_replicates=True, **mkw)
+    mdes.close()
+    ok_m = all(same(m_r[k], m_one[k]) for k in ("point_stats", "rep_stats", "std_err", "ci_lower", "ci_upper", "p_value"))
+    flags = torch.tensor([int(ok_r), int(ok_n is not False), int(ok_m)], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-    ok_r, ok_n_all = bool(flags[0].item()), bool(flags[1].item())
-    if not (ok_r and ok_n_all):
-        raise SystemExit(f"NCCL self-test failed: mode R bit-identical = {ok_r}, mode N bit-identical = {ok_n_all}")
+    ok_r, ok_n_all, ok_m = bool(flags[0].item()), bool(flags[1].item()), bool(flags[2].item())
+    if not (ok_r and ok_n_all and ok_m):
+        raise SystemExit(f"NCCL self-test failed: mode R bit-identical = {ok_r}, mode N bit-identical = {ok_n_all}, "
+                         f"Machado-Mata mode R bit-identical = {ok_m}")
     return {"mode_r_bit_identical_to_one_gpu": ok_r, "mode_n_bit_identical_to_one_gpu": None if ok_n is None else ok_n_all,
-            "shape": "n=300k, K=10, WLS + Yun, B=200, every rank compared with its own unsharded run"}
+            "machado_mata_mode_r_bit_identical_to_one_gpu": ok_m,
+            "shape": "n=300k, K=10, WLS + Yun, B=200 (Machado-Mata: n=20k, K=6, 32 simulations, 2 world + 1 passes), every rank "
+                     "compared with its own unsharded run"}
 
 
 def measure_machado_mata(ob, ctx, threads, n=200_000, n_cont=7, sims=200, reps=20, steps=2):
