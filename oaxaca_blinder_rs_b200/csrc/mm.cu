@@ -11,11 +11,13 @@
 //
 //   * Frisch-Newton primal-dual interior point (Portnoy & Koenker 1997) on the bounded dual
 //       max y'a  s.t.  X'a = (1 - tau) X'c,  0 <= a <= c,
-//     Mehrotra predictor-corrector.  Per iteration four sweeps over the group's rows; the weighted Gram X'QX and the
-//     right-hand sides are FP64 DMMA contractions (mma.sync.m8n8k4.f64) with the rows as the contraction dimension, each
-//     warp owning every eighth 32-row block; the row-wise vector algebra runs lane-per-row on the same 32 rows, fed by
-//     the same fragment loads (a 4-row x 8-column fragment is four 64-byte segments of the row-major design).
-//     Primal/dual iterates live in a per-block slab of HBM (6 doubles per row; L2-resident for small groups).
+//     Mehrotra predictor-corrector with one step length for both iterates.  Per iteration three sweeps over the group's
+//     rows (apply the step + Newton matrix; affine step + the two vectors the corrector's right-hand side is linear in;
+//     corrected step); the weighted Gram X'QX and the right-hand sides are FP64 DMMA contractions
+//     (mma.sync.m8n8k4.f64) with the rows as the contraction dimension, each warp owning every eighth 32-row block; the
+//     row-wise vector algebra runs lane-per-row on the same 32 rows, fed by the same fragment loads (a 4-row x 8-column
+//     fragment is four 64-byte segments of the row-major design).  Primal/dual iterates live in a per-block slab of HBM
+//     (6 doubles per row, loaded one block ahead of their use; L2-resident for small groups).
 //   * polish to the LP's vertex: the rows with a numerically zero residual are compacted in row order, beta is refined on
 //     them (normal equations, double-double residuals), and the result is verified (zero residuals there, unchanged
 //     residual signs elsewhere).  The answer is then independent of the interior-point path -- which is what makes a
@@ -170,7 +172,7 @@ __device__ __forceinline__ void st_load(St& v, const StPtr& p, long long i, bool
 //   DOT  : t_i = x_i'vec (vec: shared, zero beyond column K-1) and y_i, from the fragment loads
 //   rowf : lane-per-row work on the row's iterate (the vectors named by MASK, loaded one block ahead so that their
 //          latency hides under the previous block's work); returns the weight q_i and the extra column v_i
-//   GRAM : 1 = acc += sum_i q_i [x_i | v_i][x_i | v_i]' (upper-triangle tiles), 2 = only the tiles of column K (X'Q v),
+//   GRAM : 1 = acc += sum_i q_i [x_i | v_i][x_i | v_i]' (upper-triangle tiles),
 //          3 = two right-hand sides at once: acc[jt] = (X'Q v, X'Q v2) for the design columns of tile jt
 template <int K8, bool DOT, int GRAM, int MASK, typename RowF>
 __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X, int ldx, long long n, int K, const double* vec,
@@ -248,9 +250,6 @@ __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X
 #pragma unroll
                         for (int lt = jt; lt < K8; ++lt, ++tt) dmma884(acc[tt][0], acc[tt][1], a, xv[lt]);
                     }
-                } else if (GRAM == 2) {
-#pragma unroll
-                    for (int jt = 0; jt < K8; ++jt) dmma884(acc[jt][0], acc[jt][1], q * xv[jt], xv[K8 - 1]);
                 } else {
                     // B tile: column 0 = v, column 1 = v2 of the row (lane holds B[row r4][column cg])
                     const double b = cg == 0 ? ve : (cg == 1 ? sh.vs2[wb + 4 * ks + r4] : 0.0);
@@ -284,27 +283,7 @@ __device__ void gram_to_shared(MmShared& sh, const double (&acc)[K8 * (K8 + 1) /
         __syncthreads();
     }
 }
-// the same for the rhs-only sweep: column K of the tiles (jt, K8-1) -> out[0..K)
-template <int K8>
-__device__ void rhs_to_shared(MmShared& sh, const double (&acc)[K8 * (K8 + 1) / 2][2], int K, double* out) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x < MM_MAXKP) out[threadIdx.x] = 0.0;
-    __syncthreads();
-    const int col = 8 * (K8 - 1) + 2 * (lane & 3);
-    for (int turn = 0; turn < MM_WARPS; ++turn) {
-        if (w == turn) {
-#pragma unroll
-            for (int jt = 0; jt < K8; ++jt) {
-                const int row = 8 * jt + (lane >> 2);
-                if (row < K && col == K) out[row] += acc[jt][0];         // rows >= K stay zero: `out` is used as a padded vector
-                if (row < K && col + 1 == K) out[row] += acc[jt][1];
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// GRAM == 3: lanes with (lane & 3) == 0 hold columns 0 and 1 of D rows 8 jt + lane / 4 -> out1, out2 [0..K)
+// warps add their partial right-hand sides one after the other (fixed order).  GRAM == 3: lanes with (lane & 3) == 0 hold columns 0 and 1 of D rows 8 jt + lane / 4 -> out1, out2 [0..K)
 template <int K8>
 __device__ void rhs2_to_shared(MmShared& sh, const double (&acc)[K8 * (K8 + 1) / 2][2], int K, double* out1, double* out2) {
     (void)sh;

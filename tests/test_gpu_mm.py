@@ -262,3 +262,27 @@ def test_mm_library_replicate_sharding_is_bit_identical(world, reps):
         assert o["n_ok"] == one["n_ok"] == reps and o["rep_stats"].shape == one["rep_stats"].shape
         for k in ("point_stats", "rep_stats", "rep_status", "std_err", "p_value", "ci_lower", "ci_upper", "t_stat"):
             assert np.array_equal(np.nan_to_num(o[k], nan=-7.0), np.nan_to_num(one[k], nan=-7.0)), k
+
+
+def test_mm_fullsize_point_pass_matches_oracle(orc):
+    """At the size the bench line quotes (n = 2e5 rows, 1e5 per group, K = 10): every regression of the point pass and of
+    one bootstrap pass against the oracle -- long rows are where the summation order of the Gram sweeps and the
+    interior-point path differ most, and the polish has to pick K rows out of 1e5."""
+    import oaxaca_blinder_rs_b200 as ob
+    fr = make_frame(200_000, 7, seed=1)
+    (Xa, ya), (Xb, yb) = dense(fr)
+    sims, reps, q = 16, 1, [0.1, 0.5, 0.9]
+    st = streams(12, reps, sims, len(ya), len(yb))
+    st["taus"][0, :4] = [0.0102, 0.0209, 0.9791, 0.9898]          # the extreme quantiles: the hardest for the interior point
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, fr["cont"], [fr["cat"]], [3], fr["y"], None, fr["group"])
+    gpu = ob.machado_mata(des, q, simulations=sims, reps=reps, want_rep=True, want_betas=True, **st)
+    des.close(); ctx.close()
+    o = orc.mm_run(Xa, ya, Xb, yb, sims, q, reps, st["idx_a"], st["idx_b"], st["taus"], st["draw_a"], st["draw_b"], nthreads=16)
+    assert gpu["qr"] == dict(total=4 * sims, vertex=4 * sims, approx=0, failed=0, iterations=gpu["qr"]["iterations"])
+    assert relerr(gpu["point_betas_a"], o["betas_a"]) <= RTOL, relerr(gpu["point_betas_a"], o["betas_a"])
+    assert relerr(gpu["point_betas_b"], o["betas_b"]) <= RTOL, relerr(gpu["point_betas_b"], o["betas_b"])
+    assert relerr(gpu["point_stats"], o["point_stats"].reshape(3, 3)) <= RTOL
+    assert relerr(gpu["rep_stats"], o["rep_stats"].reshape(reps, 3, 3)) <= RTOL
+    iters = (gpu["point_qr_info_a"] >> 8) & 0xff
+    assert iters.max() <= 40, iters                              # incl. tau = 0.0102 and 0.9898 (one step length for both iterates)
