@@ -44,7 +44,8 @@ def streams(seed, reps, sims, na, nb):
 
 
 @pytest.mark.parametrize("n,n_x,sims,reps,round_y", [(600, 2, 40, 6, None), (4000, 3, 60, 8, None), (2500, 2, 50, 5, 2),
-                                                     (1500, 12, 30, 4, None)])
+                                                     (1500, 12, 30, 4, None), (3000, 20, 20, 2, None), (3000, 28, 16, 2, None),
+                                                     (4000, 36, 12, 1, None), (5000, 44, 12, 1, None)])
 def test_mm_matches_oracle(orc, n, n_x, sims, reps, round_y):
     import oaxaca_blinder_rs_b200 as ob
     fr = make_frame(n, n_x, seed=10 + n_x, round_y=round_y)
