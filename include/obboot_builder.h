@@ -87,6 +87,9 @@ ob_status ob_qd_builder_device(ob_qd_builder* b, int32_t device);
 ob_status ob_qd_builder_streams(ob_qd_builder* b, const uint32_t* idx_a, const uint32_t* idx_b, const double* taus,
                                 const uint32_t* draw_a, const uint32_t* draw_b);
 ob_status ob_qd_builder_run(ob_qd_builder* b, ob_qd_results** out);
+/* the key of a target quantile in results_by_quantile: format!("q{}", (tau * 100.0) as u32) (quantile_decomposition.rs:277);
+ * returns its length */
+int32_t ob_qd_quantile_key(double tau, char* out, size_t out_len);
 const char* ob_qd_builder_last_error(const ob_qd_builder* b);
 ob_status ob_qd_builder_last_status(const ob_qd_builder* b);
 void ob_qd_results_free(ob_qd_results* r);

@@ -83,6 +83,7 @@ def _blib():
         L.ob_qd_builder_run.argtypes = [vp, C.POINTER(vp)]
         L.ob_qd_builder_last_error.argtypes = [vp]; L.ob_qd_builder_last_error.restype = cp
         L.ob_qd_builder_last_status.argtypes = [vp]
+        L.ob_qd_quantile_key.argtypes = [C.c_double, C.c_char_p, C.c_size_t]; L.ob_qd_quantile_key.restype = i32
         L.ob_qd_results_free.argtypes = [vp]; L.ob_qd_results_free.restype = None
         L.ob_qd_results_json.argtypes = [vp]; L.ob_qd_results_json.restype = cp
         L.ob_qd_results_summary.argtypes = [vp]; L.ob_qd_results_summary.restype = cp
@@ -101,7 +102,7 @@ BUILDER_SYMBOLS = ["ob_frame_new", "ob_frame_free", "ob_frame_add_f64", "ob_fram
                    "ob_qd_builder_new", "ob_qd_builder_free", "ob_qd_builder_predictors", "ob_qd_builder_categorical_predictors",
                    "ob_qd_builder_quantiles", "ob_qd_builder_simulations", "ob_qd_builder_bootstrap_reps", "ob_qd_builder_seed",
                    "ob_qd_builder_device", "ob_qd_builder_streams", "ob_qd_builder_run", "ob_qd_builder_last_error",
-                   "ob_qd_builder_last_status", "ob_qd_results_free", "ob_qd_results_json", "ob_qd_results_summary"]
+                   "ob_qd_builder_last_status", "ob_qd_quantile_key", "ob_qd_results_free", "ob_qd_results_json", "ob_qd_results_summary"]
 
 
 def _columns(frame) -> dict:
@@ -450,6 +451,13 @@ class QuantileDecompositionBuilder:
         p32 = lambda a: None if a is None else a.ctypes.data_as(N._U32P)
         return self._check(_blib().ob_qd_builder_streams(self._h, p32(ia), p32(ib), None if t is None else t.ctypes.data_as(N._DP),
                                                          p32(da), p32(db)))
+
+    @staticmethod
+    def quantile_key(tau: float) -> str:
+        """format!("q{}", (tau * 100.0) as u32), quantile_decomposition.rs:277."""
+        buf = C.create_string_buffer(32)
+        _blib().ob_qd_quantile_key(float(tau), buf, 32)
+        return buf.value.decode()
 
     def run(self) -> QuantileDecompositionResults:                   # quantile_decomposition.rs:281
         out = C.c_void_p()

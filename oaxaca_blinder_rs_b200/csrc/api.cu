@@ -1633,7 +1633,7 @@ void mm_run(ob_ctx* ctx, const ob_design* d, const ob_mm_opts* o, ob_mm_result* 
         // blocks in flight: two per SM unless their iterate slabs (6 vectors of the larger group) would take more than
         // half of the budget
         const double slab = 8.0 * mm_state_vectors() * (double)stride;
-        int grid = ctx->num_sms * mm_blocks_per_sm(K);
+        int grid = ctx->num_sms * mm_blocks_per_sm(K, std::max(n_g[0], n_g[1]));
         grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, (int64_t)std::floor(0.5 * budget / slab)));
         const double per_panel = (double)(n_pad[0] + n_pad[1]) * BM * count_bytes + (index_mode ? (double)(n_g[0] + n_g[1]) * BM * 4.0 : 0.0) +
                                  (double)BM * sims * (2.0 * K * 8.0 + 2.0 * 4.0 + 8.0 + 8.0);

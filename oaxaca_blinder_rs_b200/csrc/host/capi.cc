@@ -209,6 +209,11 @@ ob_status ob_qd_builder_run(ob_qd_builder* b, ob_qd_results** out) {
     *out = nullptr;
     return guarded(b, [&] { auto r = std::make_unique<ob_qd_results>(); r->r = b->b->run(); *out = r.release(); });
 }
+int32_t ob_qd_quantile_key(double tau, char* out, size_t out_len) {
+    const std::string k = ob::QuantileDecompositionBuilder::quantile_key(tau);
+    put_err(out, out_len, k);
+    return (int32_t)k.size();
+}
 const char* ob_qd_builder_last_error(const ob_qd_builder* b) { return b ? b->err.c_str() : "null builder"; }
 ob_status ob_qd_builder_last_status(const ob_qd_builder* b) { return b ? b->last : OB_ERR_INVALID_ARG; }
 void ob_qd_results_free(ob_qd_results* r) { delete r; }

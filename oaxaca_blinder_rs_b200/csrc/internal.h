@@ -335,7 +335,7 @@ struct MmArgs {
     int* counter;                    // work queue (zeroed by the caller)
 };
 int mm_state_vectors();
-int mm_blocks_per_sm(int K);
+int mm_blocks_per_sm(int K, int64_t rows);      // rows = the larger group
 // every (group, pass, simulation) quantile regression of the batch: interior point + vertex polish, one block per problem
 void mm_qr_launch(const MmArgs& m, int grid, cudaStream_t st);
 // native streams: taus [slots][sims], simulated original rows rows_a / rows_b [slots][sims]; global pass id of slot s =

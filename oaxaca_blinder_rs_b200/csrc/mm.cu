@@ -736,21 +736,23 @@ __global__ void __launch_bounds__(256) mm_effects_kernel(const double* Xa, const
 
 int mm_state_vectors() { return 6; }
 
-// resident blocks per SM the kernel is compiled for (register budget 65536 / (256 MINB))
-static int mm_minb(int K) {
+// resident blocks per SM the kernel is compiled for (register budget 65536 / (256 MINB)).  Measured on the B200
+// (profiles/r02_mm_probe_*.json): 3 blocks beat 2 everywhere; 4 blocks (64 registers, some spills) win by 10 % while the
+// iterate slabs are short (groups of ~1e4 rows), and lose by 13 % at 1e5 rows.
+static int mm_minb(int K, int64_t rows) {
     const int K8 = (K + 1 + 7) / 8;
-    int minb = K8 <= 3 ? 3 : 2;
+    int minb = K8 <= 3 ? (rows <= 30000 ? 4 : 3) : 2;
     if (const char* e = getenv("OBBOOT_MM_MINB")) { const int v = atoi(e); if (v >= 2 && v <= 4 && K8 <= 3) minb = v; }
     return minb;
 }
-int mm_blocks_per_sm(int K) { return mm_minb(K); }
+int mm_blocks_per_sm(int K, int64_t rows) { return mm_minb(K, rows); }
 
 void mm_qr_launch(const MmArgs& m, int grid, cudaStream_t st) {
     MmKernelArgs a;
     for (int g = 0; g < 2; ++g) { a.X[g] = m.X[g]; a.C[g] = m.C[g]; a.n[g] = m.n[g]; a.n_pad[g] = m.n_pad[g]; }
     a.ldx = m.ldx; a.K = m.K; a.count_bytes = m.count_bytes; a.sims = m.sims; a.slots = m.slots; a.taus = m.taus;
     a.state = m.state; a.state_stride = m.state_stride; a.betas = m.betas; a.info = m.info; a.counter = m.counter;
-    const int K8 = (m.K + 1 + 7) / 8, minb = mm_minb(m.K);
+    const int K8 = (m.K + 1 + 7) / 8, minb = mm_minb(m.K, m.n[0] > m.n[1] ? m.n[0] : m.n[1]);
 #define OB_MM(K8_, MB_) mm_qr_kernel<K8_, MB_><<<grid, MM_THREADS, 0, st>>>(a)
 #define OB_MM3(K8_) do { if (minb == 4) OB_MM(K8_, 4); else if (minb == 3) OB_MM(K8_, 3); else OB_MM(K8_, 2); } while (0)
     switch (K8) {

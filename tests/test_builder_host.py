@@ -190,3 +190,45 @@ def test_cli_rejects_untyped_values(flag, value):
     r = subprocess.run([cli, "--data", "nope.csv", "--outcome", "y", "--group", "g", "--reference", "r", flag, value],
                        capture_output=True, text=True)
     assert r.returncode == 2 and "invalid value" in r.stderr and value in r.stderr
+
+
+# ---- Machado-Mata builder mirror: host logic that needs no device ----
+def test_quantile_decomposition_key_format():
+    """format!("q{}", (tau * 100.0) as u32), quantile_decomposition.rs:277: truncation, not rounding (0.29 * 100 =
+    28.999999999999996 -> "q28"), saturation of negative values / NaN to 0 like Rust's float -> u32 cast."""
+    import oaxaca_blinder_rs_b200 as ob
+    key = ob.QuantileDecompositionBuilder.quantile_key
+    assert [key(t) for t in (0.1, 0.25, 0.5, 0.75, 0.9)] == ["q10", "q25", "q50", "q75", "q90"]     # the defaults (:57)
+    assert key(0.29) == "q28" and key(0.57) == "q56" and key(0.58) == "q57"
+    assert key(0.999) == "q99" and key(1.0) == "q100" and key(0.0) == "q0"
+    assert key(-0.3) == "q0" and key(float("nan")) == "q0"
+    for t in (0.07, 0.14, 0.28, 0.55, 0.56):
+        assert key(t) == "q%d" % int(t * 100.0)
+
+
+def test_quantile_decomposition_null_handling():
+    """The Machado-Mata builder does not clean the frame (quantile_decomposition.rs:286-287 only selects columns): a null
+    outcome in one of the two groups is InvalidGroupVariable("Null outcome encountered") (prepare_data, :111-118), a null
+    predictor fails the ndarray conversion (:141).  Both are found before any device work."""
+    import oaxaca_blinder_rs_b200 as ob
+    base = {"wage": [10.0, 12.0, 11.0, 13.0, 20.0, 22.0, 21.0, 23.0], "education": [12.0, 16.0, 14.0, 16.0, 12.0, 16.0, 14.0, 16.0],
+            "gender": ["F", "F", "F", "F", "M", "M", "M", "M"]}
+    f = dict(base); f["wage"] = list(base["wage"]); f["wage"][2] = None
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.QuantileDecompositionBuilder(f, "wage", "gender", "F").predictors(["education"]).simulations(10).bootstrap_reps(1).run()
+    assert e.value.kind == "InvalidGroupVariable" and "Null outcome encountered" in str(e.value)
+    f = dict(base); f["education"] = list(base["education"]); f["education"][5] = None
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.QuantileDecompositionBuilder(f, "wage", "gender", "F").predictors(["education"]).simulations(10).bootstrap_reps(1).run()
+    assert e.value.kind == "PolarsError"
+    # a null in a row of a THIRD group never reaches a design (:195-206): no null error; the run then needs the device
+    f = dict(base)
+    f["gender"] = base["gender"] + ["X"]; f["wage"] = base["wage"] + [None]; f["education"] = base["education"] + [12.0]
+    import torch
+    b = ob.QuantileDecompositionBuilder(f, "wage", "gender", "F").predictors(["education"]).simulations(10).bootstrap_reps(1)
+    if torch.cuda.is_available():
+        assert (b.run().n_a, ) == (4, )
+    else:
+        with pytest.raises(ob.OaxacaError) as e:
+            b.run()
+        assert e.value.kind == "NoDevice"
