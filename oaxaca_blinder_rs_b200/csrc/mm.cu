@@ -35,6 +35,7 @@ namespace {
 
 constexpr int MM_THREADS = 256;
 constexpr int MM_WARPS = MM_THREADS / 32;
+constexpr double MM_RANK_TOL = 1e-14; // a Cholesky pivot below this fraction of its diagonal: rank-deficient up to rounding
 constexpr int MM_MAXC = 512;          // zero-residual rows the polish works on (the first ones in row order)
 constexpr int MM_MAXK8 = 6;           // design columns + 1 <= 48
 constexpr int MM_MAXKP = 8 * MM_MAXK8;
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
         if (scale == 0.0) scale = yscale;
         gram_to_shared<K8>(sh, acc);
         gram_finish(sh, K);
-        if (!dead && block_chol(sh, K, 0.0)) dead = true;
+        if (!dead && block_chol(sh, K, MM_RANK_TOL)) dead = true;
         double gap = 0.0;
         if (!dead) {
             if (tid < MM_MAXKP) sh.vec[0][tid] = sh.rhs[tid];
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
                 ++iters;
                 gram_to_shared<K8>(sh, acc);
                 gram_finish(sh, K);
-                if (block_chol(sh, K, 0.0)) break;
+                if (block_chol(sh, K, MM_RANK_TOL)) break;
                 if (tid < MM_MAXKP) sh.vec[1][tid] = sh.rhs[tid];
                 __syncthreads();
                 block_chol_solve(sh, K, sh.vec[1]);

@@ -32,9 +32,10 @@ typedef long double ld;
 /* in-place lower Cholesky of a K x K row-major matrix; 0 = ok */
 static int mm_chol(double* G, int K) {
     for (int j = 0; j < K; ++j) {
-        double d = G[j * K + j];
+        const double d0 = G[j * K + j];
+        double d = d0;
         for (int k = 0; k < j; ++k) d -= G[j * K + k] * G[j * K + k];
-        if (!(d > 0.0) || !isfinite(d)) return 1;
+        if (!(d > 1e-14 * d0) || !isfinite(d)) return 1;      /* rank-deficient up to rounding (n < K, collinear columns) */
         d = sqrt(d);
         G[j * K + j] = d;
         for (int i = j + 1; i < K; ++i) {

@@ -287,3 +287,70 @@ def test_mm_fullsize_point_pass_matches_oracle(orc):
     assert relerr(gpu["rep_stats"], o["rep_stats"].reshape(reps, 3, 3)) <= RTOL
     iters = (gpu["point_qr_info_a"] >> 8) & 0xff
     assert iters.max() <= 40, iters                              # incl. tau = 0.0102 and 0.9898 (one step length for both iterates)
+
+
+def _edge_cases():
+    rng = np.random.default_rng(0)
+    n = 200
+    X = np.c_[np.ones(n), rng.normal(size=n)]
+    y = X @ [1.0, 2.0] + rng.normal(size=n)
+    d = rng.integers(0, 3, size=n)
+    Xd = np.c_[np.ones(n), d == 1, d == 2].astype(float)
+    return {
+        "constant outcome": (X, np.full(n, 3.0)),
+        "zero outcome": (X, np.zeros(n)),
+        "two rows": (np.array([[1, 1.0], [1, 2.0]]), np.array([1.0, 3.0])),
+        "three rows": (np.array([[1, 1.0], [1, 2.0], [1, 4.0]]), np.array([1.0, 3.0, 2.0])),
+        "outcome scale 1e9": (X, 1e9 * y),
+        "outcome scale 1e-9": (X, 1e-9 * y),
+        "dummies only, integer outcome (ties)": (Xd, rng.integers(0, 5, size=n).astype(float)),
+        "intercept only": (np.ones((n, 1)), y),
+    }
+
+
+@pytest.mark.parametrize("name", list(_edge_cases()))
+def test_mm_edge_shapes_match_oracle(orc, name):
+    """Degenerate and badly scaled inputs: perfect fits (every row has a zero residual), groups of two and three rows,
+    outcomes of size 1e9 and 1e-9 (every tolerance of the solver is relative), tie-heavy data (dozens of zero-residual rows
+    per regression), an intercept-only design.  Group B is a well-behaved frame throughout."""
+    import oaxaca_blinder_rs_b200 as ob
+    Xa, ya = _edge_cases()[name]
+    rng = np.random.default_rng(1)
+    nb = 150
+    Xb = np.c_[np.ones(nb), rng.normal(size=(nb, Xa.shape[1] - 1))]
+    yb = Xb @ np.arange(1, Xa.shape[1] + 1) + rng.normal(size=nb)
+    sims, reps = 12, 0
+    st = streams(3, reps, sims, len(ya), len(yb))
+    # (not 0.05 / 0.3 / ..: with tau n an integer the tau-th quantile of an intercept-only design is a whole interval, the LP
+    # has no unique vertex, and both solvers report "interior-point solution only" -- correctly)
+    st["taus"][0, :4] = [0.0503, 0.3011, 0.8017, 0.9707]
+    q = [0.25, 0.5, 0.75]
+    ctx = ob.Context(0)
+    des = ob.Design.from_dense(ctx, Xa, ya, None, Xb, yb, None, n_cont=Xa.shape[1] - 1)
+    gpu = ob.machado_mata(des, q, simulations=sims, reps=reps, want_betas=True, taus=st["taus"], draw_a=st["draw_a"], draw_b=st["draw_b"])
+    des.close(); ctx.close()
+    o = orc.mm_pass(Xa, ya, Xb, yb, st["taus"][0], st["draw_a"][0], st["draw_b"][0], q)
+    assert o["rc"] == 0 and np.array_equal(gpu["point_qr_info_a"] & 0xff, o["status_a"]) and (o["status_a"] == orc.QR_VERTEX).all()
+    scale = np.abs(ya).max() or 1.0          # (an all-zero outcome: coefficients are 0 up to denormal noise)
+    assert np.abs(gpu["point_betas_a"] - o["betas_a"]).max() <= 1e-10 * max(scale, np.abs(o["betas_a"]).max())
+    assert relerr(gpu["point_betas_b"], o["betas_b"]) <= RTOL
+    assert np.abs(gpu["point_stats"] - o["stats"]).max() <= 1e-10 * max(np.abs(o["stats"]).max(), scale, np.abs(yb).max())
+
+
+def test_mm_rank_deficient_group_fails_like_a_dropped_fit(orc):
+    """More columns than rows in group A: every regression of A fails the rank test (status 2), on the device as in the
+    oracle, and the point pass is an error (quantile_decomposition.rs:238-242).  (clarabel would return one of the LP's
+    non-unique solutions here)"""
+    import oaxaca_blinder_rs_b200 as ob
+    Xa, ya = np.array([[1, 1.0, 2.0], [1, 2.0, 1.0]]), np.array([1.0, 3.0])
+    rng = np.random.default_rng(1)
+    Xb = np.c_[np.ones(50), rng.normal(size=(50, 2))]
+    yb = rng.normal(size=50)
+    o = orc.mm_pass(Xa, ya, Xb, yb, [0.3, 0.6], [0, 1], [0, 1], [0.5])
+    assert o["rc"] == 4 and (o["status_a"] == orc.QR_FAILED).all() and (o["status_b"] == orc.QR_VERTEX).all()
+    ctx = ob.Context(0)
+    des = ob.Design.from_dense(ctx, Xa, ya, None, Xb, yb, None, n_cont=2)
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.machado_mata(des, [0.5], simulations=2, reps=0, taus=[[0.3, 0.6]], draw_a=[[0, 1]], draw_b=[[0, 1]])
+    assert e.value.kind == "NalgebraError"
+    des.close(); ctx.close()
