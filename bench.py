@@ -364,6 +364,31 @@ def nccl_selftest(ob, obd, ctx, rank, world, dist, torch):
                      "compared with its own unsharded run"}
 
 
+def measure_machado_mata_sharded(ob, ctx, torch, dist, world, n=200_000, n_cont=7, sims=200, reps=20, steps=2):
+    """The Machado-Mata record at N > 1: the same workload as measure_machado_mata, the regressions of every pass split
+    over the ranks inside the library (ob_mm_opts.shard_replicates), coefficients all-gathered over NCCL."""
+    from oaxaca_blinder_rs_b200 import synth
+    d = synth.make_wage(n, n_cont, cat_levels=(3,), weights=False, seed=7)
+    des = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], None, d["group"])
+    q = [0.1, 0.25, 0.5, 0.75, 0.9]
+    ob.machado_mata(des, q, simulations=16, reps=1, seed=1, shard_replicates=True)
+    best, r = None, None
+    for it in range(steps):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = ob.machado_mata(des, q, simulations=sims, reps=reps, seed=10 + it, shard_replicates=True)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = t.item() if best is None else min(best, t.item())
+    des.close()
+    nprob = r["qr"]["total"]
+    return {"workload": f"synthetic wage n={n}, K={des.K}, simulations={sims}, bootstrap_reps={reps}: {nprob} regressions per step, "
+                        f"split evenly over {world} ranks inside the library",
+            "seconds_per_step": best, "value": nprob / best, "unit": "regressions/s", "passes_per_s": (reps + 1) / best,
+            "qr_status": {k: r["qr"][k] for k in ("vertex", "approx", "failed")}}
+
+
 def measure_machado_mata(ob, ctx, threads, n=200_000, n_cont=7, sims=200, reps=20, steps=2):
     """SURVEY 8f-3 beside the headline: the Machado-Mata decomposition (ob_mm_run; QuantileDecompositionBuilder defaults:
     200 simulations, 20 bootstrap passes, 5 quantiles) on synthetic wage data, n = 2e5 rows, K = 1 + 7 + 2 columns:
@@ -751,6 +776,10 @@ def main():
         also = {}
         also["config4_n5M_k30_rif_B1000"] = measure_also("config4_n5M_k30_rif_B1000", ob, obd, ctx, torch, dist, rank, world, local,
                                                           shard_rows=False, rif_tau=0.5, steps=3)
+        try:
+            also["machado_mata"] = measure_machado_mata_sharded(ob, ctx, torch, dist, world)
+        except Exception as e:                         # never lose the headline line to a side measurement
+            also["machado_mata"] = {"error": f"{type(e).__name__}: {e}"}
         if world & (world - 1) == 0:
             also["config5_n100M_k16_B10000"] = measure_also("config5_n100M_k16_B10000", ob, obd, ctx, torch, dist, rank, world, local,
                                                              shard_rows=True, rif_tau=None, steps=2)

@@ -307,7 +307,12 @@ typedef struct ob_mm_opts {
     int32_t skip_reduce;
     int32_t count_bits;              /* 0 auto, 8 or 16 */
     int64_t max_workspace_bytes;     /* 0 = default (60% of free HBM) */
-    int32_t shard_replicates;        /* mode R inside the library, as in ob_boot_opts */
+    int32_t shard_replicates;        /* mode R inside the library: every rank holds the design and makes this same call; the
+                                        library splits each batch's (pass, simulation, group) regressions evenly over the
+                                        ranks (finer than a pass-level split: 20 passes do not divide over 8 GPUs, 8400
+                                        regressions do), all-gathers the coefficients device to device over the context's
+                                        communicator and computes effects + reduction on every rank: identical results
+                                        everywhere, bit-identical to one GPU */
 } ob_mm_opts;
 
 typedef struct ob_mm_result {

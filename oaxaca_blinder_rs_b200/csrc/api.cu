@@ -1596,8 +1596,12 @@ void mm_run(ob_ctx* ctx, const ob_design* d, const ob_mm_opts* o, ob_mm_result* 
     const bool shard_reps = o->shard_replicates != 0 && ctx->comm && ctx->comm->world > 1;
     if (shard_reps && (o->rep_begin != 0 || o->rep_end != 0 || o->skip_reduce))
         fail(OB_ERR_INVALID_ARG, "shard_replicates computes the shard itself: rep_begin / rep_end / skip_reduce must be 0");
+    // Mode R inside the library shards the REGRESSIONS, not the passes: every rank builds the multiplicity columns and the
+    // streams of all passes (cheap), solves a contiguous balanced share of each batch's (pass, simulation, group) problems,
+    // the coefficients are all-gathered device to device, and effects + reduction run on every rank.  With the builder's
+    // default of 20 passes a pass-level split over 8 GPUs would leave ranks with 4 or 3 passes (the point pass included)
+    // against 2.6 on average; the problem-level split is even to one regression.
     int64_t rb = o->rep_begin, re = o->rep_end > 0 ? o->rep_end : o->reps;
-    if (shard_reps) ob_replicate_shard(o->reps, ctx->comm->world, ctx->comm->rank, &rb, &re);
     if (rb < 0 || re < rb || re > o->reps) fail(OB_ERR_INVALID_ARG, "bad replicate shard");
     const int64_t nrep = re - rb;
     const bool index_mode = o->idx_a != nullptr || o->idx_b != nullptr;
@@ -1622,7 +1626,7 @@ void mm_run(ob_ctx* ctx, const ob_design* d, const ob_mm_opts* o, ob_mm_result* 
     OB_CUDA(cudaMemcpyAsync(d_q.p, o->quantiles, sizeof(double) * (size_t)nq, cudaMemcpyHostToDevice, st));
     const int64_t stride = (std::max(n_g[0], n_g[1]) + 31) / 32 * 32;
     std::vector<int> h_info;
-    std::vector<double> h_taus;
+    std::vector<double> h_taus, h_pbetas;
     std::vector<uint32_t> h_rows[2];
 
     auto run_batches = [&] {
@@ -1643,6 +1647,7 @@ void mm_run(ob_ctx* ctx, const ob_design* d, const ob_mm_opts* o, ob_mm_result* 
         const size_t bs_max = (size_t)std::min<int64_t>(ppb * BM, slots);
         DevBuf d_state(sizeof(double) * (size_t)mm_state_vectors() * (size_t)stride * (size_t)grid);
         DevBuf d_betas(sizeof(double) * 2 * bs_max * sims * K), d_info(sizeof(int) * 2 * bs_max * sims);
+        DevBuf d_betas_all(shard_reps ? d_betas.bytes : 0), d_info_all(shard_reps ? d_info.bytes : 0);
         DevBuf d_taus(sizeof(double) * bs_max * sims), d_rows_a(sizeof(uint32_t) * bs_max * sims), d_rows_b(sizeof(uint32_t) * bs_max * sims);
         bool saturated = false;
         for (int64_t p0 = 0; p0 < panels_total && !saturated; p0 += ppb) {
@@ -1718,9 +1723,29 @@ void mm_run(ob_ctx* ctx, const ob_design* d, const ob_mm_opts* o, ob_mm_result* 
             Timer t_qr(st, &res->ms_qr);
             OB_CUDA(cudaMemsetAsync(d_counter.p, 0, sizeof(int), st));
             const int64_t nprob = 2 * bslots * sims;
-            mm_qr_launch(ma, (int)std::min<int64_t>(grid, nprob), st);
-            res->gpu_launches += 1;
+            ma.p_begin = 0; ma.p_end = nprob;
+            if (shard_reps) ob_replicate_shard(nprob, ctx->comm->world, ctx->comm->rank, &ma.p_begin, &ma.p_end);
+            if (ma.p_end > ma.p_begin) {
+                mm_qr_launch(ma, (int)std::min<int64_t>(grid, ma.p_end - ma.p_begin), st);
+                res->gpu_launches += 1;
+            }
             t_qr.stop();
+            if (shard_reps) {      // every rank's coefficients and status words, device to device, in problem order
+                Comm* cm = ctx->comm.get();
+                const int w = cm->world;
+                std::vector<size_t> off(w), sz(w);
+                auto gather = [&](const DevBuf& mine, DevBuf& all, size_t unit) {
+                    for (int r = 0; r < w; ++r) {
+                        int64_t b = 0, e = 0;
+                        ob_replicate_shard(nprob, w, r, &b, &e);
+                        off[r] = (size_t)b * unit; sz[r] = (size_t)(e - b) * unit;
+                    }
+                    cm->allgatherv(static_cast<const char*>(mine.p) + off[cm->rank], all.p, off.data(), sz.data(), st);
+                };
+                gather(d_betas, d_betas_all, sizeof(double) * (size_t)K);
+                gather(d_info, d_info_all, sizeof(int));
+                ma.betas = d_betas_all.as<double>(); ma.info = d_info_all.as<int>();
+            }
             // (4) simulation, empirical quantiles, effects
             Timer t_eff(st, &res->ms_effects);
             mm_effects_launch(ma, d_rows_a.as<uint32_t>(), d_rows_b.as<uint32_t>(), nq, d_q.as<double>(), d_stats.as<double>() + (size_t)slot_lo * S,
@@ -1730,11 +1755,10 @@ void mm_run(ob_ctx* ctx, const ob_design* d, const ob_mm_opts* o, ob_mm_result* 
             int flags[4];
             h_info.resize((size_t)2 * bslots * sims);
             OB_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, st));
-            OB_CUDA(cudaMemcpyAsync(h_info.data(), d_info.p, sizeof(int) * h_info.size(), cudaMemcpyDeviceToHost, st));
-            if (p0 == 0) {
-                const size_t nb = sizeof(double) * (size_t)sims * K;
-                if (res->point_betas_a) OB_CUDA(cudaMemcpyAsync(res->point_betas_a, d_betas.p, nb, cudaMemcpyDeviceToHost, st));
-                if (res->point_betas_b) OB_CUDA(cudaMemcpyAsync(res->point_betas_b, d_betas.as<double>() + (size_t)bslots * sims * K, nb, cudaMemcpyDeviceToHost, st));
+            OB_CUDA(cudaMemcpyAsync(h_info.data(), ma.info, sizeof(int) * h_info.size(), cudaMemcpyDeviceToHost, st));
+            if (p0 == 0 && (res->point_betas_a || res->point_betas_b)) {      // slot 0: [sims][2][K], groups interleaved
+                h_pbetas.resize((size_t)2 * sims * K);
+                OB_CUDA(cudaMemcpyAsync(h_pbetas.data(), ma.betas, sizeof(double) * h_pbetas.size(), cudaMemcpyDeviceToHost, st));
             }
             OB_CUDA(cudaStreamSynchronize(st));
             t_counts.collect(); t_qr.collect(); t_eff.collect();
@@ -1745,16 +1769,22 @@ void mm_run(ob_ctx* ctx, const ob_design* d, const ob_mm_opts* o, ob_mm_result* 
                 saturated = true;
                 break;
             }
+            if (p0 == 0 && (res->point_betas_a || res->point_betas_b))
+                for (int s_ = 0; s_ < sims; ++s_) {
+                    if (res->point_betas_a) memcpy(res->point_betas_a + (size_t)s_ * K, h_pbetas.data() + ((size_t)2 * s_ + 0) * K, sizeof(double) * (size_t)K);
+                    if (res->point_betas_b) memcpy(res->point_betas_b + (size_t)s_ * K, h_pbetas.data() + ((size_t)2 * s_ + 1) * K, sizeof(double) * (size_t)K);
+                }
             for (size_t i = 0; i < h_info.size(); ++i) {
                 const int st_ = h_info[i] & 0xff;
                 ++res->qr_total;
                 if (st_ == 0) ++res->qr_vertex; else if (st_ == 1) ++res->qr_approx; else ++res->qr_failed;
                 res->qr_iterations += (h_info[i] >> 8) & 0xff;
             }
-            if (p0 == 0) {
-                if (res->point_qr_info_a) memcpy(res->point_qr_info_a, h_info.data(), sizeof(int) * (size_t)sims);
-                if (res->point_qr_info_b) memcpy(res->point_qr_info_b, h_info.data() + (size_t)bslots * sims, sizeof(int) * (size_t)sims);
-            }
+            if (p0 == 0)
+                for (int s_ = 0; s_ < sims; ++s_) {
+                    if (res->point_qr_info_a) res->point_qr_info_a[s_] = h_info[(size_t)2 * s_];
+                    if (res->point_qr_info_b) res->point_qr_info_b[s_] = h_info[(size_t)2 * s_ + 1];
+                }
         }
         if (!saturated) break;
         count_bytes = 2;
@@ -1782,27 +1812,9 @@ void mm_run(ob_ctx* ctx, const ob_design* d, const ob_mm_opts* o, ob_mm_result* 
         run_batches();
     }
     if (res->point_stats) OB_CUDA(cudaMemcpyAsync(res->point_stats, d_stats.p, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
-    const int64_t reps_all = shard_reps ? o->reps : nrep;
-    DevBuf d_gstats, d_gstatus;
+    const int64_t reps_all = nrep;         // (mode R: every rank has computed the effects of all passes)
     const double* stats_rows = d_stats.as<double>() + S;
     const int* status_rows = d_status.as<int>() + 1;
-    if (shard_reps) {      // pass rows of all ranks, device to device, into global replicate order
-        Comm* cm = ctx->comm.get();
-        const int w = cm->world;
-        std::vector<size_t> off(w), sz(w);
-        auto gather_rows = [&](const void* mine, DevBuf& all, size_t row_bytes) {
-            all.alloc(row_bytes * (size_t)std::max<int64_t>(reps_all, 1));
-            for (int r = 0; r < w; ++r) {
-                int64_t b = 0, e = 0;
-                ob_replicate_shard(o->reps, w, r, &b, &e);
-                off[r] = (size_t)b * row_bytes; sz[r] = (size_t)(e - b) * row_bytes;
-            }
-            cm->allgatherv(mine, all.p, off.data(), sz.data(), st);
-        };
-        gather_rows(stats_rows, d_gstats, sizeof(double) * (size_t)S);
-        gather_rows(status_rows, d_gstatus, sizeof(int));
-        stats_rows = d_gstats.as<double>(); status_rows = d_gstatus.as<int>();
-    }
     if (!o->skip_reduce) {
         DevBuf d_out(sizeof(double) * 5 * (size_t)S), d_nok(sizeof(long long)), d_rs(reduce_stats_scratch_bytes(reps_all, S));
         Timer t_red(st, &res->ms_reduce);

@@ -331,8 +331,10 @@ struct MmArgs {
     int64_t slots;                   // passes (columns of the multiplicity matrix) in this batch
     const double* taus;              // [slots][sims] the random quantiles of every pass
     double* state; int64_t state_stride;     // per block mm_state_vectors() vectors of state_stride doubles
-    double* betas; int* info;        // [2][slots][sims][K], [2][slots][sims] (status | iterations << 8 | candidates << 16)
+    double* betas; int* info;        // [slots][sims][2][K], [slots][sims][2] (status | iterations << 8 | candidates << 16):
+                                     // problem-major, problem = (slot sims + sim) 2 + group
     int* counter;                    // work queue (zeroed by the caller)
+    int64_t p_begin, p_end;          // problems [p_begin, p_end) are solved by this launch (mode R: the rank's share)
 };
 int mm_state_vectors();
 int mm_blocks_per_sm(int K, int64_t rows);      // rows = the larger group

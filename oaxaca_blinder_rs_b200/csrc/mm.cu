@@ -148,9 +148,10 @@ struct MmKernelArgs {
     int sims; long long slots;                   // passes of this batch (slot = column of the multiplicity matrix)
     const double* taus;                          // [slots][sims]
     double* state; long long state_stride;       // per block: 6 vectors of state_stride doubles
-    double* betas;                               // [2][slots][sims][K]
-    int* info;                                   // [2][slots][sims]: status | iterations << 8 | min(candidates, 65535) << 16
+    double* betas;                               // [slots][sims][2][K]: problem-major (problem = (slot sims + sim) 2 + group)
+    int* info;                                   // [slots][sims][2]: status | iterations << 8 | min(candidates, 65535) << 16
     int* counter;                                // work queue
+    long long p_begin, p_end;                    // this launch solves problems [p_begin, p_end) (mode R: the rank's share)
 };
 
 constexpr int QR_VERTEX = 0, QR_APPROX = 1, QR_FAILED = 2;
@@ -337,22 +338,21 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
     double *st_x = st, *st_s = st + a.state_stride, *st_z = st + 2 * a.state_stride, *st_w = st + 3 * a.state_stride,
            *st_dxa = st + 4 * a.state_stride, *st_dxc = st + 5 * a.state_stride;
     const StPtr sp{st_x, st_s, st_z, st_w, st_dxa, st_dxc};
-    const long long nprob = 2 * a.slots * a.sims;
     double acc[NT][2];
 
     for (;;) {
         __syncthreads();
         if (tid == 0) sh.prob = atomicAdd(a.counter, 1);
         __syncthreads();
-        const long long p = sh.prob;
-        if (p >= nprob) break;
+        const long long p = a.p_begin + sh.prob;
+        if (p >= a.p_end) break;
         const int g = (int)(p & 1);
         const long long rest = p >> 1;
         const int sim = (int)(rest % a.sims);
         const long long slot = rest / a.sims;
         const long long n = a.n[g];
         const double* __restrict__ X = a.X[g];
-        const long long out_idx = ((long long)g * a.slots + slot) * a.sims + sim;
+        const long long out_idx = p;
         double tau = a.taus[slot * a.sims + sim];
         tau = fmin(fmax(tau, 1e-6), 1.0 - 1e-6);
         const unsigned char* C8 = (const unsigned char*)a.C[g] + ((size_t)(slot / BM) * a.n_pad[g]) * BM * a.count_bytes;
@@ -657,7 +657,7 @@ __global__ void mm_streams_kernel(long long slots, int sims, long long pass0, in
 }
 
 // ---- simulation and effects of a pass: quantile_decomposition.rs:244-277 ----
-// One block per pass.  betas [2][slots][sims][K], info [2][slots][sims]; rows_* [slots][sims] = the simulated ORIGINAL
+// One block per pass.  betas [slots][sims][2][K], info [slots][sims][2]; rows_* [slots][sims] = the simulated ORIGINAL
 // row of each group for the i-th pairing; stats [slots][3 nq]; status [slots].
 __global__ void __launch_bounds__(256) mm_effects_kernel(const double* Xa, const double* Xb, int ldx, int K, int sims, long long slots,
                                                          const double* betas, const int* info, const uint32_t* rows_a, const uint32_t* rows_b,
@@ -671,13 +671,12 @@ __global__ void __launch_bounds__(256) mm_effects_kernel(const double* Xa, const
     __shared__ int s_na, s_nb;
     const long long slot = blockIdx.x;
     const int tid = threadIdx.x;
-    const int* ia = info + (size_t)slot * sims;
-    const int* ib = info + ((size_t)slots + slot) * sims;
+    const int* ii = info + (size_t)slot * sims * 2;          // [sims][2]
     if (tid == 0) {          // filter_map(.ok()): order-preserving compaction (sims is a few hundred)
         int ca = 0, cb = 0;
         for (int s = 0; s < sims; ++s) {
-            if ((ia[s] & 0xff) != QR_FAILED) la[ca++] = s;
-            if ((ib[s] & 0xff) != QR_FAILED) lb[cb++] = s;
+            if ((ii[2 * s] & 0xff) != QR_FAILED) la[ca++] = s;
+            if ((ii[2 * s + 1] & 0xff) != QR_FAILED) lb[cb++] = s;
         }
         s_na = ca; s_nb = cb;
     }
@@ -696,8 +695,8 @@ __global__ void __launch_bounds__(256) mm_effects_kernel(const double* Xa, const
         if (i < ns) {
             const double* xa = Xa + (size_t)rows_a[(size_t)slot * sims + i] * ldx;
             const double* xb = Xb + (size_t)rows_b[(size_t)slot * sims + i] * ldx;
-            const double* ba = betas + ((size_t)slot * sims + la[i]) * K;
-            const double* bb = betas + (((size_t)slots + slot) * sims + lb[i]) * K;
+            const double* ba = betas + (((size_t)slot * sims + la[i]) * 2 + 0) * K;
+            const double* bb = betas + (((size_t)slot * sims + lb[i]) * 2 + 1) * K;
             yaa = ybb = yab = 0.0;
             for (int j = 0; j < K; ++j) { yaa += xa[j] * ba[j]; ybb += xb[j] * bb[j]; yab += xa[j] * bb[j]; }
         }
@@ -753,6 +752,7 @@ void mm_qr_launch(const MmArgs& m, int grid, cudaStream_t st) {
     for (int g = 0; g < 2; ++g) { a.X[g] = m.X[g]; a.C[g] = m.C[g]; a.n[g] = m.n[g]; a.n_pad[g] = m.n_pad[g]; }
     a.ldx = m.ldx; a.K = m.K; a.count_bytes = m.count_bytes; a.sims = m.sims; a.slots = m.slots; a.taus = m.taus;
     a.state = m.state; a.state_stride = m.state_stride; a.betas = m.betas; a.info = m.info; a.counter = m.counter;
+    a.p_begin = m.p_begin; a.p_end = m.p_end;
     const int K8 = (m.K + 1 + 7) / 8, minb = mm_minb(m.K, m.n[0] > m.n[1] ? m.n[0] : m.n[1]);
 #define OB_MM(K8_, MB_) mm_qr_kernel<K8_, MB_><<<grid, MM_THREADS, 0, st>>>(a)
 #define OB_MM3(K8_) do { if (minb == 4) OB_MM(K8_, 4); else if (minb == 3) OB_MM(K8_, 3); else OB_MM(K8_, 2); } while (0)
