@@ -354,3 +354,23 @@ def test_mm_rank_deficient_group_fails_like_a_dropped_fit(orc):
         ob.machado_mata(des, [0.5], simulations=2, reps=0, taus=[[0.3, 0.6]], draw_a=[[0, 1]], draw_b=[[0, 1]])
     assert e.value.kind == "NalgebraError"
     des.close(); ctx.close()
+
+
+def test_mm_batching_and_count_width_do_not_change_a_bit():
+    """More passes than one workspace batch holds (panels of 128 multiplicity columns, processed under a workspace budget)
+    and 16-bit multiplicities: the same bits as the single-batch 8-bit run, native streams (keyed by global pass ids)."""
+    import oaxaca_blinder_rs_b200 as ob
+    fr = make_frame(1500, 2, seed=3)
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, fr["cont"], [fr["cat"]], [3], fr["y"], None, fr["group"])
+    kw = dict(quantiles=[0.25, 0.5, 0.75], simulations=8, reps=300, seed=21, want_rep=True)
+    one = ob.machado_mata(des, **kw)
+    small = ob.machado_mata(des, max_workspace_bytes=1_000_000, **kw)         # one panel per batch (three batches), 13 blocks
+    wide = ob.machado_mata(des, count_bits=16, **kw)
+    des.close(); ctx.close()
+    assert one["n_ok"] == 300 and one["qr"]["total"] == 2 * 301 * 8
+    for other in (small, wide):
+        for k in ("point_stats", "rep_stats", "rep_status", "std_err", "p_value", "ci_lower", "ci_upper", "t_stat"):
+            assert np.array_equal(np.nan_to_num(other[k], nan=-7.0), np.nan_to_num(one[k], nan=-7.0)), k
+        assert other["qr"] == one["qr"]
+    assert small["gpu_launches"] > one["gpu_launches"]
