@@ -364,6 +364,20 @@ def nccl_selftest(ob, obd, ctx, rank, world, dist, torch):
                      "compared with its own unsharded run"}
 
 
+def mm_roofline(r, rows_per_group):
+    """mm_qr_kernel against the HBM roofline: algorithmic bytes = the iterate traffic of the interior-point sweeps, 21
+    doubles per row and iteration (sweep 1 reads 6 and writes 4 vectors, sweep 2 reads 4 and writes 1, sweep 3
+    reads 5 and writes 1), summed over the iterations of all regressions of the launch; the design rows come from L2."""
+    bytes_ = 168.0 * r["qr"]["iterations"] * rows_per_group
+    ms = r["timings_ms"]["qr"]
+    peak = HBM_PEAK_GBS
+    ach = bytes_ / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "mm_qr_kernel (one block per quantile regression)", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": None, "launch_ms": ms, "bytes_per_launch": bytes_,
+            "note": "latency-bound in practice (profiles/r02_mm_qr_ncu.json: long-scoreboard stalls, issue slots 44 % busy); "
+                    "ncu DRAM traffic of a smaller launch is within 15 % of this model"}
+
+
 def measure_machado_mata_sharded(ob, ctx, torch, dist, world, n=200_000, n_cont=7, sims=200, reps=20, steps=2):
     """The Machado-Mata record at N > 1: the same workload as measure_machado_mata, the regressions of every pass split
     over the ranks inside the library (ob_mm_opts.shard_replicates), coefficients all-gathered over NCCL."""
@@ -424,6 +438,7 @@ def measure_machado_mata(ob, ctx, threads, n=200_000, n_cont=7, sims=200, reps=2
             "workload": f"synthetic wage n={n} (n_a={na}), K={K}, simulations={sims}, bootstrap_reps={reps}, 5 target quantiles",
             "regressions_per_step": nprob, "seconds_per_step": dt, "regressions_per_s": nprob / dt, "passes_per_s": (reps + 1) / dt,
             "qr_kernel_ms": r["timings_ms"]["qr"], "mean_ip_iterations": r["qr"]["iterations"] / max(nprob, 1),
+            "roofline": mm_roofline(r, n / 2.0),
             "qr_status": {k: r["qr"][k] for k in ("vertex", "approx", "failed")}, "gpu_launches": r["gpu_launches"],
             "cpu_baseline": {"value": len(taus) / cdt, "unit": "regressions/s", "cores": int(threads), "kind": "port",
                              "sample": f"{len(taus)} regressions of group A ({na} rows) at random quantiles, one per thread at a time, {cdt:.1f} s; "
