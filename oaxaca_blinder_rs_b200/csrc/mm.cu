@@ -28,7 +28,17 @@
 #include "common.cuh"
 #include "internal.h"
 
+#include <cassert>
 #include <cstdlib>
+
+// compute-sanitizer is closed on this pool; `make EXTRA=-DOB_MM_BOUNDS_CHECK` compiles device-side bounds checks into every
+// global access of the Machado-Mata kernels whose index is computed (iterate slabs, design rows, multiplicity columns,
+// candidate lists, outputs); a violation traps with file:line.  tools/mm_bounds_check.sh runs the GPU tests on that build.
+#ifdef OB_MM_BOUNDS_CHECK
+#define MM_CHECK(cond) assert(cond)
+#else
+#define MM_CHECK(cond) ((void)0)
+#endif
 
 namespace ob {
 namespace {
@@ -159,9 +169,10 @@ constexpr int QR_VERTEX = 0, QR_APPROX = 1, QR_FAILED = 2;
 // The per-row iterate of a problem: six vectors in the block's slab (x, s = u - x, z, w, the affine dx, the corrected dx).
 struct St { double x, s, z, w, a, c; };
 enum : int { LX = 1, LS = 2, LZ = 4, LW = 8, LA = 16, LC = 32 };
-struct StPtr { double *x, *s, *z, *w, *a, *c; };
+struct StPtr { double *x, *s, *z, *w, *a, *c; long long len, n_pad; };      // len: doubles per vector of the slab; n_pad: rows of the design incl. zero pad rows
 template <int MASK>
 __device__ __forceinline__ void st_load(St& v, const StPtr& p, long long i, bool in) {
+    MM_CHECK(!in || (i >= 0 && i < p.len));
     v.x = (MASK & LX) && in ? p.x[i] : 0.0;
     v.s = (MASK & LS) && in ? p.s[i] : 0.0;
     v.z = (MASK & LZ) && in ? p.z[i] : 0.0;
@@ -203,6 +214,7 @@ __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X
         const St cur = nxt;
         st_load<MASK>(nxt, sp, base + MM_THREADS + lane, base + MM_THREADS + lane < n);
         const double* xp = X + (base + r4) * ldx + cg;
+        MM_CHECK(base + 31 < sp.n_pad);          // the block's 32 design rows exist (pad rows are zero)
         if (DOT) {
 #pragma unroll UNR
             for (int ks = 0; ks < 8; ++ks) {
@@ -337,7 +349,8 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
     double* const st = a.state + (size_t)blockIdx.x * 6 * a.state_stride;
     double *st_x = st, *st_s = st + a.state_stride, *st_z = st + 2 * a.state_stride, *st_w = st + 3 * a.state_stride,
            *st_dxa = st + 4 * a.state_stride, *st_dxc = st + 5 * a.state_stride;
-    const StPtr sp{st_x, st_s, st_z, st_w, st_dxa, st_dxc};
+    StPtr sp{st_x, st_s, st_z, st_w, st_dxa, st_dxc, a.state_stride, 0};
+    MM_CHECK(a.n[0] <= a.state_stride && a.n[1] <= a.state_stride && a.n[0] <= a.n_pad[0] && a.n[1] <= a.n_pad[1]);
     double acc[NT][2];
 
     for (;;) {
@@ -351,6 +364,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
         const int sim = (int)(rest % a.sims);
         const long long slot = rest / a.sims;
         const long long n = a.n[g];
+        sp.n_pad = a.n_pad[g];
         const double* __restrict__ X = a.X[g];
         const long long out_idx = p;
         double tau = a.taus[slot * a.sims + sim];
@@ -367,6 +381,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
             double r4[4] = {0.0, 0.0, 0.0, 0.0};       // max |y|, sum u |y|, sum u, active rows
             sweep<K8, true, 1, 0>(sh, X, ldx, n, K, nullptr, sp, acc, [&](long long i, bool in, double, double y, const St&, double& q, double& v, double&) {
                 double u = 0.0;
+                MM_CHECK(!in || i < a.n_pad[g]);
                 if (in) u = a.count_bytes == 1 ? (double)C8[(size_t)i * BM + ccol] : (double)((const unsigned short*)C8)[(size_t)i * BM + ccol];
                 if (in) st_s[i] = u;
                 if (u > 0.0) { r4[0] = fmax(r4[0], fabs(y)); r4[1] += u * fabs(y); r4[2] += u; r4[3] += 1.0; }
@@ -430,6 +445,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
                         }
                         x += ap * dx; s -= ap * dx; z += ad * dz; w += ad * dw;
                     }
+                    MM_CHECK(i < sp.len);
                     st_x[i] = x; st_s[i] = s; st_z[i] = z; st_w[i] = w;
                     rg[0] += z * x + w * s;
                     q = (x * s) / (z * s + w * x);
@@ -561,7 +577,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
                     long long off = m_total;
                     int tot = 0;
                     for (int w = 0; w < MM_WARPS; ++w) { const int pc = __popc(sh.wmask[w]); if (w < (tid >> 5)) off += pc; tot += pc; }
-                    if (c) { const long long pos = off + __popc(m & ((1u << (tid & 31)) - 1u)); if (pos < MM_MAXC) sh.cand[pos] = (int)i; }
+                    if (c) { const long long pos = off + __popc(m & ((1u << (tid & 31)) - 1u)); if (pos < MM_MAXC) { MM_CHECK(pos >= 0 && i < n); sh.cand[pos] = (int)i; } }
                     m_total += tot;
                     __syncthreads();
                 }
@@ -615,6 +631,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
                 }
             }
         }
+        MM_CHECK(out_idx >= 0 && out_idx < 2 * a.slots * a.sims && slot < a.slots);
         if (tid < K) a.betas[(size_t)out_idx * K + tid] = status == QR_FAILED ? __longlong_as_double(0x7ff8000000000000LL) : sh.vec[2][tid];
         if (tid == 0) a.info[out_idx] = status | (iters << 8) | (ncand << 16);
     }
@@ -693,6 +710,7 @@ __global__ void __launch_bounds__(256) mm_effects_kernel(const double* Xa, const
     for (int i = tid; i < pow2; i += blockDim.x) {
         double yaa = inf, ybb = inf, yab = inf;
         if (i < ns) {
+            MM_CHECK(la[i] < sims && lb[i] < sims);
             const double* xa = Xa + (size_t)rows_a[(size_t)slot * sims + i] * ldx;
             const double* xb = Xb + (size_t)rows_b[(size_t)slot * sims + i] * ldx;
             const double* ba = betas + (((size_t)slot * sims + la[i]) * 2 + 0) * K;
