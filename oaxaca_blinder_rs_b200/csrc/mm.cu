@@ -809,11 +809,8 @@ size_t mm_effects_smem(int sims) {
 void mm_effects_launch(const MmArgs& m, const uint32_t* rows_a, const uint32_t* rows_b, int nq, const double* d_quantiles,
                        double* stats, int* status, int* nsucc, cudaStream_t st) {
     const size_t smem = mm_effects_smem(m.sims);
-    static bool attr_set = false;
-    if (!attr_set) {
-        OB_CUDA(cudaFuncSetAttribute(mm_effects_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    // (per device, so not cached in a process-wide flag: several contexts of one process may sit on different GPUs)
+    if (smem > 48 * 1024) OB_CUDA(cudaFuncSetAttribute(mm_effects_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     mm_effects_kernel<<<(unsigned)m.slots, 256, smem, st>>>(m.X[0], m.X[1], m.ldx, m.K, m.sims, m.slots, m.betas, m.info, rows_a, rows_b, nq,
                                                            d_quantiles, stats, status, nsucc);
     OB_CUDA(cudaGetLastError());

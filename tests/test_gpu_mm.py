@@ -374,3 +374,25 @@ def test_mm_batching_and_count_width_do_not_change_a_bit():
             assert np.array_equal(np.nan_to_num(other[k], nan=-7.0), np.nan_to_num(one[k], nan=-7.0)), k
         assert other["qr"] == one["qr"]
     assert small["gpu_launches"] > one["gpu_launches"]
+
+
+def test_mm_many_simulations(orc):
+    """2000 simulations per pass: the effects kernel sorts them in more than 48 KB of (opt-in) shared memory; the sorted
+    quantiles must still equal the oracle's.  4096 is the limit of the C ABI, 4097 is refused."""
+    import oaxaca_blinder_rs_b200 as ob
+    fr = make_frame(400, 2, seed=8)
+    (Xa, ya), (Xb, yb) = dense(fr)
+    sims, q = 2000, [0.05, 0.5, 0.95]
+    st = streams(2, 0, sims, len(ya), len(yb))
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, fr["cont"], [fr["cat"]], [3], fr["y"], None, fr["group"])
+    gpu = ob.machado_mata(des, q, simulations=sims, reps=0, taus=st["taus"], draw_a=st["draw_a"], draw_b=st["draw_b"])
+    o = orc.mm_pass(Xa, ya, Xb, yb, st["taus"][0], st["draw_a"][0], st["draw_b"][0], q)
+    assert o["rc"] == 0 and gpu["qr"]["failed"] == 0 and gpu["qr"]["total"] == 2 * sims
+    assert relerr(gpu["point_stats"], o["stats"]) <= RTOL
+    big = ob.machado_mata(des, q, simulations=4096, reps=0, seed=1)
+    assert big["qr"]["total"] == 2 * 4096 and np.isfinite(big["point_stats"]).all()
+    with pytest.raises(ob.OaxacaError) as e:
+        ob.machado_mata(des, q, simulations=4097, reps=0)
+    assert e.value.kind == "InvalidArgument"
+    des.close(); ctx.close()
