@@ -423,6 +423,15 @@ def measure_machado_mata(ob, ctx, threads, n=200_000, n_cont=7, sims=200, reps=2
     dt, r = min(runs, key=lambda x: x[0])
     K, na = des.K, des.n_a
     nprob = r["qr"]["total"]
+    # end to end: host columns -> ob_design_pack (H2D + pack) -> ob_mm_run -> results on the host, per step
+    e2e = []
+    for it in range(steps):
+        t0 = time.perf_counter()
+        d2 = ob.Design.pack(ctx, d["cont"], d["cat_codes"], d["cat_levels"], d["outcome"], None, d["group"])
+        ob.machado_mata(d2, q, simulations=sims, reps=reps, seed=10 + it)
+        d2.close()
+        e2e.append(time.perf_counter() - t0)
+    h2d = 8 * n * (len(d["cont"]) + 1) + 4 * n * len(d["cat_codes"]) + n
     X = np.c_[np.ones(n), np.stack(d["cont"], 1), d["cat_codes"][0] == 1, d["cat_codes"][0] == 2].astype(np.float64)
     A = d["group"] == 0
     Xa, ya = np.ascontiguousarray(X[A]), np.ascontiguousarray(d["outcome"][A])
@@ -437,6 +446,8 @@ def measure_machado_mata(ob, ctx, threads, n=200_000, n_cont=7, sims=200, reps=2
                     "regression solved on the device to the LP's vertex (interior point + polish)",
             "workload": f"synthetic wage n={n} (n_a={na}), K={K}, simulations={sims}, bootstrap_reps={reps}, 5 target quantiles",
             "regressions_per_step": nprob, "seconds_per_step": dt, "regressions_per_s": nprob / dt, "passes_per_s": (reps + 1) / dt,
+            "e2e": {"value": nprob / min(e2e), "unit": "regressions/s", "seconds_per_step": min(e2e), "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(8 * 6 * 3 * len(q)), "path": "host columns -> ob_design_pack -> ob_mm_run -> host results"},
             "qr_kernel_ms": r["timings_ms"]["qr"], "mean_ip_iterations": r["qr"]["iterations"] / max(nprob, 1),
             "roofline": mm_roofline(r, n / 2.0),
             "qr_status": {k: r["qr"][k] for k in ("vertex", "approx", "failed")}, "gpu_launches": r["gpu_launches"],
