@@ -215,7 +215,46 @@ __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X
         st_load<MASK>(nxt, sp, base + MM_THREADS + lane, base + MM_THREADS + lane < n);
         const double* xp = X + (base + r4) * ldx + cg;
         MM_CHECK(base + 31 < sp.n_pad);          // the block's 32 design rows exist (pad rows are zero)
-        if (DOT) {
+        double t_own = 0.0;                       // x_i'vec of this lane's own row (butterfly path)
+        if (DOT && K8 <= 2) {
+            // All eight 4-row steps first (16 fragment loads in flight), then ONE butterfly over the eight lane groups that
+            // hold the pieces of a row's dot product: each exchange halves the number of sums a lane carries (4 + 2 + 1
+            // shuffles instead of 3 per step), and the step a lane ends up with is its own lane group -- lane l holds the
+            // product of row l, no trip through shared memory.
+            double part[8];
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                double xv[K8];
+                const double* xr = xp + (size_t)(4 * ks) * ldx;
+#pragma unroll
+                for (int t = 0; t < K8 - 1; ++t) xv[t] = __ldg(xr + 8 * t);
+                xv[K8 - 1] = clast ? __ldg(xr + 8 * (K8 - 1)) : 0.0;
+                double p = 0.0;
+                if (vec) {
+#pragma unroll
+                    for (int t = 0; t < K8; ++t) p = fma(xv[t], vv[t], p);
+                }
+                part[ks] = p;
+                if (cg == cy) sh.ys[wb + 4 * ks + r4] = xv[K8 - 1];
+            }
+            if (vec) {
+                const bool hi = cg & 4, mid = cg & 2, lo = cg & 1;
+                double p4[4], p2[2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double recv = __shfl_xor_sync(0xffffffffu, hi ? part[j] : part[j + 4], 16);
+                    p4[j] = (hi ? part[j + 4] : part[j]) + recv;
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const double recv = __shfl_xor_sync(0xffffffffu, mid ? p4[j] : p4[j + 2], 8);
+                    p2[j] = (mid ? p4[j + 2] : p4[j]) + recv;
+                }
+                const double recv = __shfl_xor_sync(0xffffffffu, lo ? p2[0] : p2[1], 4);
+                t_own = (lo ? p2[1] : p2[0]) + recv;
+            }
+            __syncwarp();
+        } else if (DOT) {
 #pragma unroll UNR
             for (int ks = 0; ks < 8; ++ks) {
                 double xv[K8];
@@ -236,11 +275,12 @@ __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X
                 if (cg == cy) sh.ys[wb + 4 * ks + r4] = yv;
             }
             __syncwarp();
+            t_own = sh.ts[wb + lane];
         }
         {
             const long long i = base + lane;
             double q = 0.0, v = 0.0, v2 = 0.0;
-            rowf(i, i < n, DOT ? sh.ts[wb + lane] : 0.0, DOT ? sh.ys[wb + lane] : 0.0, cur, q, v, v2);
+            rowf(i, i < n, t_own, DOT ? sh.ys[wb + lane] : 0.0, cur, q, v, v2);
             if (GRAM) { sh.qs[wb + lane] = q; sh.vs[wb + lane] = v; }
             if (GRAM == 3) sh.vs2[wb + lane] = v2;
         }
