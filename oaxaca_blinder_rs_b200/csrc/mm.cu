@@ -166,6 +166,14 @@ struct MmKernelArgs {
 
 constexpr int QR_VERTEX = 0, QR_APPROX = 1, QR_FAILED = 2;
 
+// 1/x, 1/s and the scaling q = 1 / (z/x + w/s) = x s / (z s + w x) from ONE division (an FP64 division is a dozen
+// instructions with a slow-path branch; the row algebra of a sweep used three to five of them)
+__device__ __forceinline__ void recips(double x, double s, double z, double w, double& rx, double& rs, double& q) {
+    const double xs = x * s, d = z * s + w * x;
+    const double t = 1.0 / (xs * d);
+    rx = s * d * t; rs = x * d * t; q = xs * xs * t;
+}
+
 // The per-row iterate of a problem: six vectors in the block's slab (x, s = u - x, z, w, the affine dx, the corrected dx).
 struct St { double x, s, z, w, a, c; };
 enum : int { LX = 1, LS = 2, LZ = 4, LW = 8, LA = 16, LC = 32 };
@@ -182,12 +190,12 @@ __device__ __forceinline__ void st_load(St& v, const StPtr& p, long long i, bool
 }
 
 // One sweep over the rows of the problem's group.  Per 32-row block (a warp owns every eighth one):
-//   DOT  : t_i = x_i'vec (vec: shared, zero beyond column K-1) and y_i, from the fragment loads
+//   DOT  : t_i = x_i'vec (vec: shared, zero beyond column K-1) and, with NEEDY, the outcome y_i, from the fragment loads
 //   rowf : lane-per-row work on the row's iterate (the vectors named by MASK, loaded one block ahead so that their
 //          latency hides under the previous block's work); returns the weight q_i and the extra column v_i
 //   GRAM : 1 = acc += sum_i q_i [x_i | v_i][x_i | v_i]' (upper-triangle tiles),
 //          3 = two right-hand sides at once: acc[jt] = (X'Q v, X'Q v2) for the design columns of tile jt
-template <int K8, bool DOT, int GRAM, int MASK, typename RowF>
+template <int K8, bool DOT, int GRAM, int MASK, bool NEEDY, typename RowF>
 __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X, int ldx, long long n, int K, const double* vec,
                                       const StPtr& sp, double (&acc)[K8 * (K8 + 1) / 2][2], RowF&& rowf) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -235,7 +243,7 @@ __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X
                     for (int t = 0; t < K8; ++t) p = fma(xv[t], vv[t], p);
                 }
                 part[ks] = p;
-                if (cg == cy) sh.ys[wb + 4 * ks + r4] = xv[K8 - 1];
+                if (NEEDY && cg == cy) sh.ys[wb + 4 * ks + r4] = xv[K8 - 1];
             }
             if (vec) {
                 const bool hi = cg & 4, mid = cg & 2, lo = cg & 1;
@@ -253,7 +261,7 @@ __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X
                 const double recv = __shfl_xor_sync(0xffffffffu, lo ? p2[0] : p2[1], 4);
                 t_own = (lo ? p2[1] : p2[0]) + recv;
             }
-            __syncwarp();
+            if (NEEDY) __syncwarp();
         } else if (DOT) {
 #pragma unroll UNR
             for (int ks = 0; ks < 8; ++ks) {
@@ -272,7 +280,7 @@ __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X
                     part += __shfl_xor_sync(0xffffffffu, part, 16);
                 }
                 if (cg == 0) sh.ts[wb + 4 * ks + r4] = part;
-                if (cg == cy) sh.ys[wb + 4 * ks + r4] = yv;
+                if (NEEDY && cg == cy) sh.ys[wb + 4 * ks + r4] = yv;
             }
             __syncwarp();
             t_own = sh.ts[wb + lane];
@@ -280,7 +288,7 @@ __device__ __forceinline__ void sweep(MmShared& sh, const double* __restrict__ X
         {
             const long long i = base + lane;
             double q = 0.0, v = 0.0, v2 = 0.0;
-            rowf(i, i < n, t_own, DOT ? sh.ys[wb + lane] : 0.0, cur, q, v, v2);
+            rowf(i, i < n, t_own, (DOT && NEEDY) ? sh.ys[wb + lane] : 0.0, cur, q, v, v2);
             if (GRAM) { sh.qs[wb + lane] = q; sh.vs[wb + lane] = v; }
             if (GRAM == 3) sh.vs2[wb + lane] = v2;
         }
@@ -419,7 +427,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
         double yscale, scale, usum, nact;
         {
             double r4[4] = {0.0, 0.0, 0.0, 0.0};       // max |y|, sum u |y|, sum u, active rows
-            sweep<K8, true, 1, 0>(sh, X, ldx, n, K, nullptr, sp, acc, [&](long long i, bool in, double, double y, const St&, double& q, double& v, double&) {
+            sweep<K8, true, 1, 0, true>(sh, X, ldx, n, K, nullptr, sp, acc, [&](long long i, bool in, double, double y, const St&, double& q, double& v, double&) {
                 double u = 0.0;
                 MM_CHECK(!in || i < a.n_pad[g]);
                 if (in) u = a.count_bytes == 1 ? (double)C8[(size_t)i * BM + ccol] : (double)((const unsigned short*)C8)[(size_t)i * BM + ccol];
@@ -443,7 +451,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
             __syncthreads();
             block_chol_solve(sh, K, sh.vec[0]);
             double r1[1] = {0.0};
-            sweep<K8, true, 0, LS>(sh, X, ldx, n, K, sh.vec[0], sp, acc, [&](long long i, bool in, double t, double y, const St& c, double&, double&, double&) {
+            sweep<K8, true, 0, LS, true>(sh, X, ldx, n, K, sh.vec[0], sp, acc, [&](long long i, bool in, double t, double y, const St& c, double&, double&, double&) {
                 if (!in) return;
                 const double u = c.s;
                 const double r = -y - t;
@@ -460,7 +468,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
             for (;;) {
                 // P1: apply the previous step (or build the starting point), new q and r, gap, Newton matrix
                 double rg[1] = {0.0};
-                sweep<K8, false, 1, LX | LS | LZ | LW | LA | LC>(sh, X, ldx, n, K, nullptr, sp, acc,
+                sweep<K8, false, 1, LX | LS | LZ | LW | LA | LC, false>(sh, X, ldx, n, K, nullptr, sp, acc,
                                                                  [&](long long i, bool in, double, double, const St& c, double& q, double& v, double&) {
                     if (!in) return;
                     double x, s, z, w;
@@ -474,7 +482,8 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
                         x = c.x; s = c.s;
                         if (!(x + s > 0.0)) return;
                         z = c.z; w = c.w;
-                        const double rx = 1.0 / x, rs = 1.0 / s;
+                        double rx, rs, qold;
+                        recips(x, s, z, w, rx, rs, qold);
                         const double dxa = c.a;
                         const double dza = -z * (1.0 + dxa * rx), dwa = -w * (1.0 - dxa * rs);
                         double dx = dxa, dz = dza, dw = dwa;
@@ -506,14 +515,14 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
                 // corrector's right-hand side is linear in: X'Q xi = X'Q r + mu X'Q (1/s - 1/x) + X'Q (dx dz / x + dx dw / s),
                 // so the corrector needs no sweep of its own for its right-hand side
                 double r2[4] = {0.0, 0.0, 0.0, 0.0};        // 1 / primal step limit, 1 / dual step limit, S1, S3
-                sweep<K8, true, 3, LX | LS | LZ | LW>(sh, X, ldx, n, K, sh.vec[1], sp, acc,
+                sweep<K8, true, 3, LX | LS | LZ | LW, false>(sh, X, ldx, n, K, sh.vec[1], sp, acc,
                                                       [&](long long i, bool in, double t, double, const St& c, double& q, double& v, double& v2) {
                     if (!in) return;
                     const double x = c.x, s = c.s;
                     if (!(x + s > 0.0)) return;
                     const double z = c.z, w = c.w;
-                    const double rx = 1.0 / x, rs = 1.0 / s;
-                    q = 1.0 / (z * rx + w * rs);
+                    double rx, rs;
+                    recips(x, s, z, w, rx, rs, q);
                     const double r = z - w;
                     const double dx = q * (t - r);
                     const double dz = -z * (1.0 + dx * rx), dw = -w * (1.0 - dx * rs);
@@ -540,22 +549,23 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
                     block_chol_solve(sh, K, sh.vec[1]);
                     // P4: corrected step and its ratio test
                     double r3[2] = {0.0, 0.0};
-                    sweep<K8, true, 0, LX | LS | LZ | LW | LA>(sh, X, ldx, n, K, sh.vec[1], sp, acc,
+                    sweep<K8, true, 0, LX | LS | LZ | LW | LA, false>(sh, X, ldx, n, K, sh.vec[1], sp, acc,
                                                                [&](long long i, bool in, double t, double, const St& c, double&, double&, double&) {
                         if (!in) return;
                         const double x = c.x, s = c.s;
                         if (!(x + s > 0.0)) return;
                         const double z = c.z, w = c.w, dxa = c.a;
-                        const double rx = 1.0 / x, rs = 1.0 / s;
+                        double rx, rs, q;
+                        recips(x, s, z, w, rx, rs, q);
                         const double dza = -z * (1.0 + dxa * rx), dwa = -w * (1.0 - dxa * rs);
-                        const double q = 1.0 / (z * rx + w * rs);
                         const double xi = (z - w) + mu * (rs - rx) + dxa * dza * rx + dxa * dwa * rs;
                         const double dx = q * (t - xi);
                         const double dz = (mu - dxa * dza) * rx - z - z * rx * dx;
                         const double dw = (mu + dxa * dwa) * rs - w + w * rs * dx;
                         st_dxc[i] = dx;
                         r3[0] = fmax(r3[0], fmax(-dx * rx, dx * rs));
-                        r3[1] = fmax(r3[1], fmax(-dz / z, -dw / w));
+                        const double tzw = 1.0 / (z * w);
+                        r3[1] = fmax(r3[1], fmax(-dz * w * tzw, -dw * z * tzw));
                     });
                     const int ops3[2] = {2, 2};
                     block_reduce<2>(sh, r3, ops3);
@@ -578,7 +588,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
             int cnt[12];
 #pragma unroll
             for (int j = 0; j < 12; ++j) cnt[j] = 0;
-            sweep<K8, true, 0, LX | LS>(sh, X, ldx, n, K, sh.vec[2], sp, acc, [&](long long i, bool in, double t, double y, const St& c, double&, double&, double&) {
+            sweep<K8, true, 0, LX | LS, true>(sh, X, ldx, n, K, sh.vec[2], sp, acc, [&](long long i, bool in, double t, double y, const St& c, double&, double&, double&) {
                 if (!in) return;
                 if (!(c.x + c.s > 0.0)) return;
                 const double res = y - t;
@@ -654,7 +664,7 @@ __global__ void __launch_bounds__(MM_THREADS, MINB) mm_qr_kernel(const MmKernelA
                     __syncthreads();
                 }
                 double bad[1] = {0.0};
-                sweep<K8, true, 0, LX | LS | LA>(sh, X, ldx, n, K, sh.vec[3], sp, acc, [&](long long, bool in, double t, double y, const St& c, double&, double&, double&) {
+                sweep<K8, true, 0, LX | LS | LA, true>(sh, X, ldx, n, K, sh.vec[3], sp, acc, [&](long long, bool in, double t, double y, const St& c, double&, double&, double&) {
                     if (!in) return;
                     if (!(c.x + c.s > 0.0)) return;
                     const double res0 = c.a, res = y - t;
