@@ -804,12 +804,13 @@ __global__ void __launch_bounds__(256) mm_effects_kernel(const double* Xa, const
 
 int mm_state_vectors() { return 6; }
 
-// resident blocks per SM the kernel is compiled for (register budget 65536 / (256 MINB)).  Measured on the B200
-// (profiles/r02_mm_probe_*.json): 3 blocks beat 2 everywhere; 4 blocks (64 registers, some spills) win by 10 % while the
-// iterate slabs are short (groups of ~1e4 rows), and lose by 13 % at 1e5 rows.
+// resident blocks per SM the kernel is compiled for (register budget 65536 / (256 MINB)).  Measured on the B200 with the
+// final kernel (8400 regressions, K = 10 unless noted): 1e5 rows per group 1235 / 1331 / 1364 ms at 2 / 3 / 4 blocks
+// (no spills at 128 registers; 144 and 380 bytes of spills at 80 and 64), 3e4 rows 340 / 358 / 358 ms, 1e4 rows
+// 111 / - / 111 ms, 1e4 rows with K = 6 87 / 83 / 81 ms: 2 blocks from ~1.5e4 rows on, 4 below.
 static int mm_minb(int K, int64_t rows) {
     const int K8 = (K + 1 + 7) / 8;
-    int minb = K8 <= 3 ? (rows <= 30000 ? 4 : 3) : 2;
+    int minb = K8 <= 3 ? (rows <= 15000 ? 4 : 2) : 2;
     if (const char* e = getenv("OBBOOT_MM_MINB")) { const int v = atoi(e); if (v >= 2 && v <= 4 && K8 <= 3) minb = v; }
     return minb;
 }
