@@ -6,7 +6,8 @@
  *
  * Frame: a 64-bit LCG anyone can restate (tests/test_gpu_cabi.py does, in numpy): group, two continuous predictors, one
  * categorical with 3 levels, weights, outcome.  Runs ob_design_pack_async -> ob_bootstrap_run (native stream, pooled
- * beta*, Yun on the categorical) with page-locked columns, then once more through ob_design_pack for comparison. */
+ * beta*, Yun on the categorical) with page-locked columns, then once more through ob_design_pack for comparison, then
+ * ob_mm_run (Machado-Mata, native streams) on the unweighted pack of the same frame. */
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -93,6 +94,24 @@ int main(int argc, char** argv) {
     }
     const int same = memcmp(out[0], out[1], sizeof(double) * (size_t)(6 * S + 3 * K)) == 0;   /* async pack == pack, bit for bit */
     printf("async_equals_sync %d\n", same);
+    {   /* Machado-Mata (QuantileDecompositionBuilder::run): the same frame without weights, native streams */
+        ob_frame_view fu = f;
+        fu.weights = NULL;
+        ob_design* d = NULL;
+        CHECK(ob_design_pack(ctx, &fu, &d));
+        const double quantiles[3] = {0.25, 0.5, 0.75};
+        ob_mm_opts mo;
+        memset(&mo, 0, sizeof mo);
+        mo.simulations = 24; mo.n_quantiles = 3; mo.quantiles = quantiles; mo.reps = 5; mo.seed = seed;
+        double mm[6 * 9];
+        ob_mm_result mr;
+        memset(&mr, 0, sizeof mr);
+        mr.point_stats = mm; mr.std_err = mm + 9; mr.p_value = mm + 18; mr.ci_lower = mm + 27; mr.ci_upper = mm + 36; mr.t_stat = mm + 45;
+        CHECK(ob_mm_run(ctx, d, &mo, &mr));
+        printf("mm_n_ok %lld\nmm_qr_total %lld\nmm_qr_failed %lld\n", (long long)mr.n_ok, (long long)mr.qr_total, (long long)mr.qr_failed);
+        for (int j = 0; j < 9; ++j) printf("mm_point %.17g\nmm_se %.17g\nmm_ci_lo %.17g\nmm_ci_hi %.17g\n", mm[j], mm[9 + j], mm[27 + j], mm[36 + j]);
+        ob_design_destroy(d);
+    }
     free(out[0]); free(out[1]);
     ob_host_free(x0); ob_host_free(x1); ob_host_free(y); ob_host_free(w); ob_host_free(cat); ob_host_free(grp);
     ob_ctx_destroy(ctx);

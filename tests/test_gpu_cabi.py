@@ -74,3 +74,11 @@ def test_c_program_matches_the_ctypes_binding(tmp_path):
     for v in np.abs(out["residuals_b"]).tolist():          # the C program's left-to-right sum
         rs += v
     assert vals["resid_abs_sum"][0] == rs
+    # ob_mm_run from C == the ctypes binding, bit for bit (native streams keyed by the seed)
+    ctx = ob.Context(0)
+    des = ob.Design.pack(ctx, [x0, x1], [cat], [3], y, None, grp)
+    mm = ob.machado_mata(des, [0.25, 0.5, 0.75], simulations=24, reps=5, seed=seed)
+    des.close(); ctx.close()
+    assert (vals["mm_n_ok"][0], vals["mm_qr_total"][0], vals["mm_qr_failed"][0]) == (mm["n_ok"], 2 * 6 * 24, 0)
+    assert np.array_equal(vals["mm_point"], mm["point_stats"].ravel()) and np.array_equal(vals["mm_se"], mm["std_err"].ravel())
+    assert np.array_equal(vals["mm_ci_lo"], mm["ci_lower"].ravel()) and np.array_equal(vals["mm_ci_hi"], mm["ci_upper"].ravel())
