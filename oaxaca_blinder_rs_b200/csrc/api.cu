@@ -58,6 +58,8 @@ struct ob_design {
     int K = 0, n_cont = 0, V = 0, ldx = 0;
     int T = 1;                       // outcome columns K .. K+T-1 of a design row (ob_design_apply_rif_multi: one per quantile)
     int K1 = 0;                      // selection-equation columns incl. the intercept (ob_design_attach_selection), 0 = none
+    std::vector<int> cat_levels;     // level counts of the categorical predictors (empty: unknown, ob_design_from_dense): the
+                                     // products of two dummies of one predictor are structural zeros of X'WX (gram_columns)
     bool weighted = false;
     int64_t n_frame = 0;             // rows of the frame the design was packed from (ob_design_update_outcome)
     int world = 1, rank = 0;         // row sharding (mode N): this design holds rank's rows of a world-way split
@@ -535,7 +537,7 @@ ob_status ob_design_allgather_rows(ob_ctx* ctx, const ob_design* local, ob_desig
 
         std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
         design_register(ctx, d.get()); d->stream = ctx->stream; d->device = ctx->device; d->K = local->K; d->n_cont = local->n_cont; d->V = local->V;
-        d->ldx = local->ldx; d->weighted = local->weighted;
+        d->ldx = local->ldx; d->weighted = local->weighted; d->cat_levels = local->cat_levels;
         for (int g = 0; g < 2; ++g) {
             std::vector<size_t> off_x(world), sz_x(world), off_w(world), sz_w(world);
             long long total = 0;
@@ -602,7 +604,7 @@ ob_status ob_design_redistribute_rows(ob_ctx* ctx, const ob_design* local, ob_de
 
         std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
         design_register(ctx, d.get()); d->stream = ctx->stream; d->device = ctx->device; d->K = local->K; d->n_cont = local->n_cont; d->V = local->V;
-        d->ldx = local->ldx; d->weighted = local->weighted;
+        d->ldx = local->ldx; d->weighted = local->weighted; d->cat_levels = local->cat_levels;
         d->world = world; d->rank = me;
         d->n_frame = frame_off[world];
         for (int g = 0; g < 2; ++g) {
@@ -781,6 +783,7 @@ std::unique_ptr<ob_design, void (*)(ob_design*)> pack_staged(ob_ctx* ctx, Staged
     std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
     design_register(ctx, d.get()); d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = sf.n_cont; d->V = K + 1; d->ldx = pa.ldx;
     d->weighted = sf.weighted;
+    d->cat_levels.assign(cat_levels, cat_levels + sf.n_cat);
     d->n_frame = n;
     alloc_group(ctx, d->g[0], tot[0], d->ldx, d->weighted, false);
     alloc_group(ctx, d->g[1], tot[1], d->ldx, d->weighted, false);
@@ -927,6 +930,7 @@ static ob_status pack_async_impl(ob_ctx* ctx, const ob_frame_view* f, bool shard
         std::unique_ptr<ob_design, void (*)(ob_design*)> d(new ob_design, ob_design_destroy);
         design_register(ctx, d.get()); d->stream = ctx->stream; d->device = ctx->device; d->K = K; d->n_cont = sf.n_cont; d->V = K + 1; d->ldx = pa.ldx;
         d->weighted = sf.weighted;
+        d->cat_levels.assign(f->cat_levels, f->cat_levels + sf.n_cat);
         d->n_frame = n;
         PackWindow win{};
         const PackWindow* winp = nullptr;
@@ -1378,11 +1382,13 @@ void heckman_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_resu
             d_terms[g].alloc(sizeof(double) * (size_t)nacc_t * ppb * BM); d_xterm[g].alloc(sizeof(double) * (size_t)K * ppb * BM);
         }
         DevBuf d_part(sizeof(double) * (size_t)std::max(nch[0], nch[1]) * ppb * BM * std::max(std::max(nacc_p, nacc_t), K));
-        DevBuf d_gram(sizeof(double) * 2 * (size_t)ppb * BM * Pld), d_partials, d_pairs;
+        DevBuf d_gram(sizeof(double) * 2 * (size_t)ppb * BM * Pld), d_partials, d_pairs, d_colmap;
+        const GramColumns gcols = gram_columns(K, 1, d->n_cont, d->cat_levels);
         {
-            const std::vector<uint16_t> pairs = gram_pair_table(K, 1, ntiles);
-            d_pairs.alloc(sizeof(uint16_t) * pairs.size());
-            OB_CUDA(cudaMemcpyAsync(d_pairs.p, pairs.data(), sizeof(uint16_t) * pairs.size(), cudaMemcpyHostToDevice, st));
+            d_pairs.alloc(sizeof(uint16_t) * gcols.pairs.size());
+            d_colmap.alloc(sizeof(int32_t) * gcols.colmap.size());
+            OB_CUDA(cudaMemcpyAsync(d_pairs.p, gcols.pairs.data(), sizeof(uint16_t) * gcols.pairs.size(), cudaMemcpyHostToDevice, st));
+            OB_CUDA(cudaMemcpyAsync(d_colmap.p, gcols.colmap.data(), sizeof(int32_t) * gcols.colmap.size(), cudaMemcpyHostToDevice, st));
             OB_CUDA(cudaStreamSynchronize(st));
         }
         GramPlan plan; int64_t plan_panels = -1;
@@ -1451,14 +1457,14 @@ void heckman_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* o, ob_resu
 
             // (3c) X'CX, X'Cy and column sums over the selected rows: the DMMA contraction on the masked design
             if (plan_panels != pn) {
-                plan = gram_make_plan(K, 1, d->ldx, (int)pn, d->g, count_bytes, ctx->num_sms);
+                plan = gram_make_plan(K, 1, d->ldx, (int)pn, d->g, count_bytes, ctx->num_sms, gcols);
                 plan_panels = pn;
                 d_partials.alloc(sizeof(double) * (size_t)std::max<int64_t>(plan.num_partials, 1) * BM * BN);
             }
             Timer t_gram(st, &res->ms_gram);
             GramArgs ga;
             for (int g = 0; g < 2; ++g) { ga.X[g] = d->g[g].hk_Xm; ga.C[g] = d_C[g].p; }
-            ga.count_bytes = count_bytes; ga.partials = d_partials.as<double>(); ga.d_pairs = d_pairs.as<uint16_t>(); ga.gram = d_gram.as<double>();
+            ga.count_bytes = count_bytes; ga.partials = d_partials.as<double>(); ga.d_pairs = d_pairs.as<uint16_t>(); ga.d_colmap = d_colmap.as<int32_t>(); ga.gram = d_gram.as<double>();
             { const int64_t last = bslots - (pn - 1) * BM; ga.tail_mi = (int)std::min<int64_t>(16, ((last + 7) / 8 + 3) / 4 * 4); }
             gram_launch(plan, ga, st);
             res->gpu_launches += 2;
@@ -1978,18 +1984,20 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
             const size_t gram_elems = 2 * (size_t)ppb * BM * Pld;      // [2][slots_pad][Pld]
             bool saturated = false;
             GramPlan plan; int64_t plan_panels = -1;
-            DevBuf d_partials, d_pairs;
+            DevBuf d_partials, d_pairs, d_colmap;
+            const GramColumns gcols = gram_columns(K, T, d->n_cont, d->cat_levels);
             auto allocate_workspace = [&] {
                 d_colsum.alloc(sizeof(long long) * 2 * (size_t)ppb * BM);
                 for (int g = 0; g < 2; ++g) d_C[g].alloc((size_t)ppb * n_pad[g] * BM * count_bytes);
                 d_gram.alloc(sizeof(double) * gram_elems);
                 if (comm) { d_gram_local.alloc(sizeof(double) * gram_elems); d_gathered.alloc(sizeof(double) * gram_elems * world); }
-                plan = gram_make_plan(K, T, d->ldx, (int)std::min<int64_t>(ppb, panels_total), d->g, count_bytes, ctx->num_sms);
+                plan = gram_make_plan(K, T, d->ldx, (int)std::min<int64_t>(ppb, panels_total), d->g, count_bytes, ctx->num_sms, gcols);
                 plan_panels = plan.panels;
                 d_partials.alloc(sizeof(double) * (size_t)std::max<int64_t>(plan.num_partials, 1) * BM * BN);
-                const std::vector<uint16_t> pairs = gram_pair_table(K, T, ntiles);
-                d_pairs.alloc(sizeof(uint16_t) * pairs.size());
-                OB_CUDA(cudaMemcpyAsync(d_pairs.p, pairs.data(), sizeof(uint16_t) * pairs.size(), cudaMemcpyHostToDevice, st));
+                d_pairs.alloc(sizeof(uint16_t) * gcols.pairs.size());
+                d_colmap.alloc(sizeof(int32_t) * gcols.colmap.size());
+                OB_CUDA(cudaMemcpyAsync(d_pairs.p, gcols.pairs.data(), sizeof(uint16_t) * gcols.pairs.size(), cudaMemcpyHostToDevice, st));
+                OB_CUDA(cudaMemcpyAsync(d_colmap.p, gcols.colmap.data(), sizeof(int32_t) * gcols.colmap.size(), cudaMemcpyHostToDevice, st));
                 OB_CUDA(cudaStreamSynchronize(st));
             };
             if (!comm) allocate_workspace();
@@ -2066,7 +2074,7 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
 
                 // (3) Gram / cross-product contraction
                 if (plan_panels != pn) {
-                    plan = gram_make_plan(K, T, d->ldx, (int)pn, d->g, count_bytes, ctx->num_sms);
+                    plan = gram_make_plan(K, T, d->ldx, (int)pn, d->g, count_bytes, ctx->num_sms, gcols);
                     plan_panels = pn;
                     d_partials.alloc(sizeof(double) * (size_t)std::max<int64_t>(plan.num_partials, 1) * BM * BN);
                 }
@@ -2074,7 +2082,8 @@ ob_status ob_bootstrap_run(ob_ctx* ctx, const ob_design* d, const ob_boot_opts* 
                 GramArgs ga;
                 for (int g = 0; g < 2; ++g) { ga.X[g] = d->g[g].gram_operand(); ga.C[g] = d_C[g].p; }
                 ga.count_bytes = count_bytes; ga.partials = d_partials.as<double>();
-                ga.d_pairs = d_pairs.as<uint16_t>(); ga.gram = comm ? d_gram_local.as<double>() : d_gram.as<double>();
+                ga.d_pairs = d_pairs.as<uint16_t>(); ga.d_colmap = d_colmap.as<int32_t>();
+                ga.gram = comm ? d_gram_local.as<double>() : d_gram.as<double>();
                 {   // valid slots of this batch's last panel -> 8-slot groups, rounded up to a multiple of 4
                     const int64_t last = bslots - (pn - 1) * BM;
                     ga.tail_mi = (int)std::min<int64_t>(16, ((last + 7) / 8 + 3) / 4 * 4);

@@ -12,8 +12,9 @@
 //     element, 1/64 of the DMMA work).  Column (j,l) order = row-major upper triangle of
 //     [x|y][x|y]^T, so G, X'Wy, the column sums (means) and sum(w) all come out of one pass.
 //   * CTA tile 128 slots x 128 columns, 8 warps (1 x 8), warp tile 128 x 16 = 16 x 2 DMMA sub-tiles,
-//     KT = 32 rows per stage, 3-4 stage TMA/mbarrier pipeline.  When the last column tile would be less
-//     than half full it is a half-width tile (128 x 64, warp tile 128 x 8): K = 17 costs 1.5 tiles, not 2.
+//     KT = 32 rows per stage, 3-stage TMA/mbarrier pipeline.  The last column tile is cut to one, two or three
+//     quanta of 32 columns (one 8-column DMMA sub-tile per scheduler) when that is all it needs: K = 17 costs 1.5
+//     tiles, K = 31 4.25, K = 51 with two four-level categoricals 10.75 (structural zeros are not computed).
 //   * Split-n: the rows of a group are cut into <= 256 fixed leaf segments whose size depends only on the
 //     group's GLOBAL row count.  Work unit = (group, panel, segment, column tile): accumulated from zero,
 //     flushed as one partial tile.  A persistent grid of one CTA per SM walks cost-balanced contiguous
@@ -37,7 +38,6 @@ namespace ob {
 constexpr int LGS = 18;
 constexpr int LDA2 = 148;
 constexpr int A_TILE = KT * LDA2;   // doubles per A buffer
-constexpr int BNH = BN / 2;         // width of the optional half-width tail tile
 
 struct GramKernelParams {
     const double* X[2];     // per group: (sqrt(w)-scaled) design rows [n_pad][ldx]
@@ -50,10 +50,10 @@ struct GramKernelParams {
     long long units0;       // units of group 0 = panels * ntiles * segs[0]
     long long units_total;
     int ldx, panels, ntiles;
-    int nfull, has_half;    // column tiling: nfull tiles of BN columns + (has_half ? one tile of BN/2 : none)
+    int nfull, tail_q;      // column tiling: nfull tiles of BN columns + (tail_q ? one tile of tail_q * BQ columns : none)
     int tail_mi;            // warp-specialised kernel: 8-slot groups of the LAST panel that hold valid slots, rounded up to
                             // a multiple of 4 (16 = the panel is full): its units skip the DMMAs of the empty groups
-    double* partials;       // [units_total][BM*BN], unit-major (a half tile uses the first BM*BN/2 doubles, stride BN/2)
+    double* partials;       // [units_total][BM*BN], unit-major (a tail tile uses the first BM * tail_q * BQ doubles, that row stride)
     const uint16_t* pairs;
 };
 
@@ -85,16 +85,15 @@ constexpr int WS_THREADS = GRAM_THREADS + 32 * WS_PRODUCER_WARPS;
 #define OB_WS_CONSUMER_REGS 224
 #define OB_WS_PRODUCER_REGS 56
 
-struct GramUnit { const double* Xg; const void* Cg; double* out; int nstages, nt, mi; bool half; };
+struct GramUnit { const double* Xg; const void* Cg; double* out; int nstages, nt, mi, tq; };   // tq: quanta of the tile (4 = full)
 
 // Unit sequence of the warp-specialised kernel: four cost classes, each in (group, segment, panel, tile) order --
-// wide tiles of full panels, wide tiles of the tail panel, half-width tiles of full panels, half-width tiles of the
-// tail panel.  CTA b takes positions b, b + grid, ...: equal shares of every class, lockstep through consecutive units.
+// wide tiles of full panels, wide tiles of the tail panel, tail tiles of full panels, tail tiles of the tail panel.  CTA b takes positions b, b + grid, ...: equal shares of every class, lockstep through consecutive units.
 __host__ __device__ __forceinline__ bool ws_decode(const GramKernelParams& p, long long i, int ldx, size_t count_bytes, GramUnit& u) {
     const int pt = p.tail_mi < 16 ? 1 : 0, pf = p.panels - pt;            // tail / full panels of this batch
     const long long segs01 = (long long)p.seg_n[0] + p.seg_n[1];
     const long long n0 = segs01 * pf * p.nfull, n1 = segs01 * pt * p.nfull;
-    const long long n2 = p.has_half ? segs01 * pf : 0, n3 = p.has_half ? segs01 * pt : 0;
+    const long long n2 = p.tail_q ? segs01 * pf : 0, n3 = p.tail_q ? segs01 * pt : 0;
     if (i >= n0 + n1 + n2 + n3) return false;
     int np, p0, nt_cnt, nt0;          // panels / first panel / tiles per sweep / first tile of the class
     if (i < n0) { np = pf; p0 = 0; nt_cnt = p.nfull; nt0 = 0; }
@@ -114,7 +113,7 @@ __host__ __device__ __forceinline__ bool ws_decode(const GramKernelParams& p, lo
     const long long row0 = (long long)seg * seg_rows;
     const long long row1 = row0 + seg_rows < n_pad ? row0 + seg_rows : n_pad;
     u.nstages = (int)((row1 - row0) / KT);
-    u.nt = nt; u.half = p.has_half && nt == p.nfull;
+    u.nt = nt; u.tq = (p.tail_q && nt == p.nfull) ? p.tail_q : 4;
     u.mi = panel >= pf ? p.tail_mi : 16;
     u.Xg = (g ? p.X[1] : p.X[0]) + row0 * ldx;
     u.Cg = reinterpret_cast<const unsigned char*>(g ? p.C[1] : p.C[0]) + (((long long)panel * n_pad + row0) * BM) * (long long)count_bytes;
@@ -123,18 +122,19 @@ __host__ __device__ __forceinline__ bool ws_decode(const GramKernelParams& p, lo
 }
 
 // MI = 8-slot groups of the panel this warp accumulates (16 = all 128 slots; 4 / 8 / 12 for a partly filled tail panel)
+// sub0: first of the warp's NI 8-column sub-tiles within the tile; tw: the tile's width (the partial tile's row stride)
 template <typename CountT, int LDXC, int NI, int MI, int R>
 __device__ __forceinline__ void ws_consume_unit(const GramKernelParams& p, const GramUnit& u, const double* As, const double* Xs,
-                                                uint64_t* full, uint64_t* ready, uint64_t* consumed, int ldx_rt, uint32_t& jc) {
+                                                uint64_t* full, uint64_t* ready, uint64_t* consumed, int ldx_rt, uint32_t& jc,
+                                                int sub0, int tw) {
     constexpr int KSTEPS = KT / 4;
-    constexpr int TW = 8 * NI * 8;
-    const int lane = threadIdx.x & 31, wn = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int lk = lane & 3, lg = lane >> 2;
     const int ldx = LDXC ? LDXC : ldx_rt;
     int oj[NI], ol[NI];
 #pragma unroll
     for (int s = 0; s < NI; ++s) {
-        const int col = u.nt * BN + wn * (NI * 8) + s * 8 + lg;
+        const int col = u.nt * BN + (sub0 + s) * 8 + lg;
         const uint32_t pr = *reinterpret_cast<const uint32_t*>(p.pairs + 2 * col);
         oj[s] = pr & 0xFFFFu; ol[s] = pr >> 16;
     }
@@ -176,19 +176,34 @@ __device__ __forceinline__ void ws_consume_unit(const GramKernelParams& p, const
     for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int t = 0; t < NI; ++t) {
-            const int m = i * 8 + lg, n = wn * (NI * 8) + t * 8 + 2 * lk;
-            *reinterpret_cast<double2*>(u.out + m * TW + n) = make_double2(acc[i][t][0], acc[i][t][1]);
+            const int m = i * 8 + lg, n = (sub0 + t) * 8 + 2 * lk;
+            *reinterpret_cast<double2*>(u.out + m * tw + n) = make_double2(acc[i][t][0], acc[i][t][1]);
         }
 }
 
 template <typename CountT, int LDXC, int NI, int R>
 __device__ __forceinline__ void ws_consume_dispatch(const GramKernelParams& p, const GramUnit& u, const double* As, const double* Xs,
-                                                    uint64_t* full, uint64_t* ready, uint64_t* consumed, int ldx_rt, uint32_t& jc) {
+                                                    uint64_t* full, uint64_t* ready, uint64_t* consumed, int ldx_rt, uint32_t& jc,
+                                                    int sub0, int tw) {
     switch (u.mi) {
-    case 4: ws_consume_unit<CountT, LDXC, NI, 4, R>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
-    case 8: ws_consume_unit<CountT, LDXC, NI, 8, R>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
-    case 12: ws_consume_unit<CountT, LDXC, NI, 12, R>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
-    default: ws_consume_unit<CountT, LDXC, NI, 16, R>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc); break;
+    case 4: ws_consume_unit<CountT, LDXC, NI, 4, R>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc, sub0, tw); break;
+    case 8: ws_consume_unit<CountT, LDXC, NI, 8, R>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc, sub0, tw); break;
+    case 12: ws_consume_unit<CountT, LDXC, NI, 12, R>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc, sub0, tw); break;
+    default: ws_consume_unit<CountT, LDXC, NI, 16, R>(p, u, As, Xs, full, ready, consumed, ldx_rt, jc, sub0, tw); break;
+    }
+}
+
+// A consumer warp with no columns in a one-quantum tail tile keeps step with the ring: stage j's `consumed` arrival
+// only once stage j's TMA has landed, i.e. after the slot's previous use has been released by all eight warps.
+template <int R>
+__device__ __forceinline__ void ws_idle_unit(const GramUnit& u, uint64_t* full, uint64_t* consumed, uint32_t& jc) {
+    const int lane = threadIdx.x & 31;
+    for (int s = 0; s < u.nstages; ++s) {
+        const uint32_t slot = jc % R, par = (jc / R) & 1u;
+        mbar_wait(&full[slot], par);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&consumed[slot]);
+        ++jc;
     }
 }
 
@@ -217,8 +232,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gram_ws_kernel(const GramKernel
         uint32_t jc = 0;
         GramUnit u;
         for (long long i = blockIdx.x; ws_decode(p, i, ldx, sizeof(CountT), u); i += gridDim.x) {
-            if (u.half) ws_consume_dispatch<CountT, LDXC, 1, R>(p, u, As, Xs, full, ready, consumed, ldx, jc);
-            else ws_consume_dispatch<CountT, LDXC, 2, R>(p, u, As, Xs, full, ready, consumed, ldx, jc);
+            // the tile's quanta give every scheduler (warps w and w + 4) tq sub-tiles: 2 + 2, 2 + 1, 1 + 1 or 1 + 0
+            const int tw = u.tq * BQ, hi = warp >> 2;
+            int ni, sub0;
+            if (u.tq == 4) { ni = 2; sub0 = warp * 2; }
+            else if (u.tq == 2) { ni = 1; sub0 = warp; }
+            else if (u.tq == 3) { ni = hi ? 1 : 2; sub0 = hi ? 4 + warp : warp * 2; }
+            else { ni = hi ? 0 : 1; sub0 = warp; }
+            if (ni == 2) ws_consume_dispatch<CountT, LDXC, 2, R>(p, u, As, Xs, full, ready, consumed, ldx, jc, sub0, tw);
+            else if (ni == 1) ws_consume_dispatch<CountT, LDXC, 1, R>(p, u, As, Xs, full, ready, consumed, ldx, jc, sub0, tw);
+            else ws_idle_unit<R>(u, full, consumed, jc);
         }
     } else {
         // ---------------- producers: TMA issue (warp 0 lane 0) + widening (4 warps x 8 rows) ----------------
@@ -334,10 +357,11 @@ __device__ __forceinline__ double2 tree_sum_span(const double2* __restrict__ bas
     }
 }
 
-// out[g][panel*BM + m][nt*BN + n] = tree sum over the tile's leaf partials held here (span = MAX_SEGS / world)
+// out[g][panel*BM + m][colmap[nt*BN + n]] = tree sum over the tile's leaf partials held here (span = MAX_SEGS / world);
+// the cells of the upper triangle that are not computed (structural zeros) have been zero-filled by the launcher
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ partials, int segs0, int segs1,
                                                           double* __restrict__ gram, int panels, int ntiles, int span,
-                                                          int Pld, int has_half) {
+                                                          int Pld, int tail_q, const int32_t* __restrict__ colmap) {
     const int tile_id = blockIdx.x;
     const int tiles_g = panels * ntiles;
     const int g = tile_id / tiles_g, t = tile_id - g * tiles_g;
@@ -346,13 +370,15 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restri
     // partial of (g, panel, nt, seg) sits at unit base_g + (panel * segs_g + seg) * ntiles + nt
     const size_t first = (g ? (size_t)tiles_g * segs0 : 0) + (size_t)panel * cnt * ntiles + nt;
     const size_t slots_pad = (size_t)panels * BM;
-    const int tw = (has_half && nt == ntiles - 1) ? BNH : BN;     // this tile's width
+    const int tw = (tail_q && nt == ntiles - 1) ? tail_q * BQ : BN;     // this tile's width
     for (int e = threadIdx.x + blockIdx.y * blockDim.x; e < BM * tw / 2; e += blockDim.x * gridDim.y) {
         double2 s = make_double2(0.0, 0.0);
         if (cnt > 0) s = tree_sum_span(reinterpret_cast<const double2*>(partials + first * (BM * BN)) + e, (size_t)ntiles * (BM * BN / 2), cnt, span);
         const int m = (2 * e) / tw, n = (2 * e) % tw;
-        double* dst = gram + ((size_t)g * slots_pad + (size_t)panel * BM + m) * (size_t)Pld + (size_t)nt * BN + n;
-        *reinterpret_cast<double2*>(dst) = s;
+        double* dst = gram + ((size_t)g * slots_pad + (size_t)panel * BM + m) * (size_t)Pld;
+        const int c0 = colmap[nt * BN + n], c1 = colmap[nt * BN + n + 1];
+        if (c0 >= 0) dst[c0] = s.x;
+        if (c1 >= 0) dst[c1] = s.y;
     }
 }
 
@@ -370,23 +396,46 @@ __global__ void __launch_bounds__(256) gram_combine_kernel(const double* __restr
     }
 }
 
-std::vector<uint16_t> gram_pair_table(int K, int T, int ntiles) {
-    std::vector<uint16_t> t((size_t)ntiles * BN * 2);
-    size_t c = 0;
-    for (int j = 0; j < K; ++j) {
-        for (int l = j; l < K; ++l) { t[2 * c] = (uint16_t)j; t[2 * c + 1] = (uint16_t)l; ++c; }
-        for (int o = 0; o < T; ++o) { t[2 * c] = (uint16_t)j; t[2 * c + 1] = (uint16_t)(K + o); ++c; }
+GramColumns gram_columns(int K, int T, int n_cont, const std::vector<int>& cat_levels) {
+    // dummy block of every design column (-1: intercept / continuous): two different columns of one block never are
+    // non-zero on the same row
+    std::vector<int> block((size_t)K, -1);
+    {
+        int64_t dummies = 0;
+        for (int m : cat_levels) dummies += m > 1 ? m - 1 : 0;
+        if (!cat_levels.empty() && 1 + (int64_t)n_cont + dummies == K) {
+            int c = 1 + n_cont;
+            for (size_t q = 0; q < cat_levels.size(); ++q)
+                for (int lvl = 1; lvl < cat_levels[q]; ++lvl) block[(size_t)c++] = (int)q;
+        }
     }
-    for (; c < (size_t)ntiles * BN; ++c) { t[2 * c] = (uint16_t)K; t[2 * c + 1] = (uint16_t)K; }  // (y_0,y_0) and padding: harmless duplicates
-    return t;
+    GramColumns gc;
+    std::vector<uint16_t> pj, pl; std::vector<int32_t> cm;
+    for (int j = 0; j < K; ++j) {
+        const int64_t base = pair_base(K, T, j);
+        for (int l = j; l < K; ++l) {
+            if (l > j && block[(size_t)j] >= 0 && block[(size_t)j] == block[(size_t)l]) continue;     // structural zero
+            pj.push_back((uint16_t)j); pl.push_back((uint16_t)l); cm.push_back((int32_t)(base + (l - j)));
+        }
+        for (int o = 0; o < T; ++o) { pj.push_back((uint16_t)j); pl.push_back((uint16_t)(K + o)); cm.push_back((int32_t)(base + (K - j) + o)); }
+    }
+    pj.push_back((uint16_t)K); pl.push_back((uint16_t)K); cm.push_back((int32_t)(num_pairs(K, T) - 1));    // (y_0, y_0)
+    gc.Pc = (int)cm.size();
+    gram_col_tiling(gc.Pc, gc.nfull, gc.tail_q);
+    gc.ntiles = gc.nfull + (gc.tail_q > 0);
+    const size_t cols = (size_t)gc.ntiles * BN;
+    gc.pairs.assign(cols * 2, (uint16_t)K);          // padding columns: harmless duplicates of (y_0, y_0), never stored
+    gc.colmap.assign(cols, -1);
+    for (size_t c = 0; c < cm.size(); ++c) { gc.pairs[2 * c] = pj[c]; gc.pairs[2 * c + 1] = pl[c]; gc.colmap[c] = cm[c]; }
+    return gc;
 }
 
-GramPlan gram_make_plan(int K, int T, int ldx, int panels, const GroupData gd[2], int count_bytes, int num_sms) {
+GramPlan gram_make_plan(int K, int T, int ldx, int panels, const GroupData gd[2], int count_bytes, int num_sms,
+                        const GramColumns& cols) {
     GramPlan pl;
     pl.K = K; pl.T = T; pl.ldx = ldx; pl.panels = panels;
-    gram_col_tiling(K, T, pl.nfull, pl.has_half);
-    pl.ntiles = pl.nfull + pl.has_half;
-    pl.Pld = pl.nfull * BN + pl.has_half * BNH;
+    pl.nfull = cols.nfull; pl.tail_q = cols.tail_q; pl.ntiles = cols.ntiles;
+    pl.Pld = gram_pld(K, T);
     int64_t total = 0;
     pl.leaf_span = gd[0].shard.leaf_span;
     for (int g = 0; g < 2; ++g) {
@@ -413,7 +462,7 @@ static GramKernelParams gram_params(const GramPlan& pl, const GramArgs& a, const
     p.units0 = pl.units[0];
     p.units_total = pl.units[0] + pl.units[1];
     p.ldx = pl.ldx; p.panels = pl.panels; p.ntiles = pl.ntiles;
-    p.nfull = pl.nfull; p.has_half = pl.has_half;
+    p.nfull = pl.nfull; p.tail_q = pl.tail_q;
     p.partials = a.partials; p.pairs = a.d_pairs;
     p.tail_mi = a.tail_mi >= 1 && a.tail_mi <= 16 ? a.tail_mi : 16;
     return p;
@@ -448,9 +497,11 @@ void gram_launch_leaves(const GramPlan& pl, const GramArgs& a, const int seg_lo[
 
 // fixed-tree sum of every tile's leaf partials -> gram [2][panels*BM][Pld]
 void gram_reduce_launch(const GramPlan& pl, const GramArgs& a, cudaStream_t st) {
+    // cells the contraction does not compute (structural zeros, row padding up to Pld) are 0.0
+    OB_CUDA(cudaMemsetAsync(a.gram, 0, sizeof(double) * 2 * (size_t)pl.panels * BM * (size_t)pl.Pld, st));
     dim3 rgw(2 * pl.panels * pl.ntiles, 16);
     gram_reduce_kernel<<<rgw, 256, 0, st>>>(a.partials, pl.segs[0], pl.segs[1], a.gram, pl.panels, pl.ntiles, pl.leaf_span,
-                                            pl.Pld, pl.has_half);
+                                            pl.Pld, pl.tail_q, a.d_colmap);
     OB_CUDA(cudaGetLastError());
 }
 
@@ -470,14 +521,15 @@ void gram_combine_launch(const double* gathered, int world, const int ranks_with
 }
 
 // Host-side walk of the warp-specialised kernel's unit schedule (no device needed): for every CTA the units it takes,
-// as (group, panel, tile, segment, stages, mi, half).  Lets the CPU tests check that every unit is covered exactly once
+// as (group, panel, tile, segment, stages, mi, tail quanta: 0 = a full tile).  Lets the CPU tests check that every unit is covered exactly once
 // and that CTAs get equal shares of every cost class, for any shape.
 int64_t gram_schedule_debug(int K, int panels, int64_t slots_last_panel, const GroupData gd[2], int grid, int64_t* out7, int64_t cap) {
-    GramPlan pl = gram_make_plan(K, 1, design_ldx(K + 1), panels, gd, 1, grid);
+    const GramColumns cols = gram_columns(K, 1, K - 1, std::vector<int>());
+    GramPlan pl = gram_make_plan(K, 1, design_ldx(K + 1), panels, gd, 1, grid, cols);
     GramKernelParams p{};
     for (int g = 0; g < 2; ++g) { p.n_pad[g] = pl.n_pad[g]; p.segs[g] = pl.segs[g]; p.seg_rows[g] = pl.seg_rows[g]; p.seg_lo[g] = 0; p.seg_n[g] = pl.segs[g]; }
     p.units0 = pl.units[0]; p.units_total = pl.units[0] + pl.units[1];
-    p.ldx = pl.ldx; p.panels = pl.panels; p.ntiles = pl.ntiles; p.nfull = pl.nfull; p.has_half = pl.has_half;
+    p.ldx = pl.ldx; p.panels = pl.panels; p.ntiles = pl.ntiles; p.nfull = pl.nfull; p.tail_q = pl.tail_q;
     p.tail_mi = (int)std::min<int64_t>(16, ((slots_last_panel + 7) / 8 + 3) / 4 * 4);
     p.partials = nullptr;
     int64_t count = 0;
@@ -492,7 +544,7 @@ int64_t gram_schedule_debug(int K, int panels, int64_t slots_last_panel, const G
                 const int segs = p.segs[g];
                 const long long sweep = r / p.ntiles;
                 int64_t* o = out7 + 8 * count;
-                o[0] = b; o[1] = g; o[2] = sweep / segs; o[3] = r % p.ntiles; o[4] = sweep % segs; o[5] = u.nstages; o[6] = u.mi; o[7] = u.half;
+                o[0] = b; o[1] = g; o[2] = sweep / segs; o[3] = r % p.ntiles; o[4] = sweep % segs; o[5] = u.nstages; o[6] = u.mi; o[7] = u.tq < 4 ? u.tq : 0;
             }
             ++count;
         }

@@ -122,9 +122,25 @@ void counts_philox_body_launch(const CountsArgs& a, long long* d_colsum, unsigne
 void counts_philox_fixup_launch(const CountsArgs& a, const long long* d_colsum, int* d_flags, cudaStream_t st);
 
 // ---- gram.cu ----
+constexpr int BQ = 32;            // column quantum of the Gram CTA tile: one 8-column DMMA sub-tile for each of the SM's four
+                                  // schedulers (consumer warps w and w + 4 sit on the same one)
+// The columns the contraction computes, in tile order.  P' minus the STRUCTURAL ZEROS: the product of two different
+// dummies of one categorical predictor is 0 on every row (a row has one level), so those cells of X'WX are exactly 0.0
+// whatever the multiplicities; they are not computed, the reduced Gram holds 0.0 there.  Everything downstream still
+// sees the full row-major upper triangle (pair_base): `colmap` scatters computed column c to its place.
+struct GramColumns {
+    int Pc = 0;                        // computed columns
+    int nfull = 0, tail_q = 0;         // column tiling of Pc: nfull tiles of BN columns + a tail tile of tail_q quanta (0 = none)
+    int ntiles = 0;                    // nfull + (tail_q > 0)
+    std::vector<uint16_t> pairs;       // [ntiles * BN][2] design-row offsets (j, l) of column c; padding columns: (K, K)
+    std::vector<int32_t> colmap;       // [ntiles * BN] index in the row-major upper triangle of [x|y][x|y]^T, -1 = padding
+};
+// cat_levels: level counts (incl. the base level) of the design's categorical predictors, in column order, or empty
+// when unknown (ob_design_from_dense): then nothing is dropped.
+GramColumns gram_columns(int K, int T, int n_cont, const std::vector<int>& cat_levels);
 struct GramPlan {
     int K, T, ldx, panels, ntiles;
-    int nfull, has_half, Pld;     // column tiling (gram_col_tiling) and the row stride of the reduced Gram
+    int nfull, tail_q, Pld;       // column tiling of the computed columns and the row stride of the reduced Gram (gram_pld)
     int64_t n_pad[2];             // local padded rows
     int segs[2], seg_rows[2];     // leaves held here and rows per leaf (RowShard: function of the global row count only)
     int leaf_span;                // MAX_SEGS / world: size of the aligned subtree this GPU reduces
@@ -133,23 +149,25 @@ struct GramPlan {
     int64_t num_partials;         // = units[0] + units[1]
     size_t smem_bytes; int ring;  // shared memory and pipeline depth of the Gram CTA
 };
-// Column tiling of the P' sufficient-statistic columns: nfull tiles of BN columns and, when the remainder
-// fits, one half-width tail tile (P' = 171 at K = 17 costs 1.5 tiles instead of 2).
-inline void gram_col_tiling(int K, int T, int& nfull, int& has_half) {
-    const int64_t P = num_pairs(K, T);
-    nfull = (int)(P / BN);
-    const int rem = (int)(P - (int64_t)nfull * BN);
-    has_half = 0;
-    if (rem > BN / 2) ++nfull; else if (rem > 0) has_half = 1;
+// Column tiling: tiles of BN = 128 columns (four quanta) and a tail tile of one to three quanta -- 32, 64 or 96 columns;
+// the DMMA time of a tile is proportional to its quanta.  K = 17: 171 columns = 1.5 tiles; K = 31: 528 = 4.25; K = 51
+// with two four-level categoricals: 1372 computed columns = 10.75.
+inline void gram_col_tiling(int64_t Pc, int& nfull, int& tail_q) {
+    const int64_t quanta = (Pc + BQ - 1) / BQ;
+    nfull = (int)(quanta / 4); tail_q = (int)(quanta % 4);
 }
-inline int gram_ntiles(int K, int T) { int f, h; gram_col_tiling(K, T, f, h); return f + h; }
-inline int gram_pld(int K, int T) { int f, h; gram_col_tiling(K, T, f, h); return f * BN + h * (BN / 2); }
-GramPlan gram_make_plan(int K, int T, int ldx, int panels, const GroupData g[2], int count_bytes, int num_sms);
+// upper bound on the number of column tiles (structural zeros can only lower it): workspace sizing
+inline int gram_ntiles(int K, int T) { int f, q; gram_col_tiling(num_pairs(K, T), f, q); return f + (q > 0); }
+// row stride of the reduced Gram [slot][Pld]: all P' cells of the upper triangle
+inline int gram_pld(int K, int T) { return (int)((num_pairs(K, T) + BQ - 1) / BQ * BQ); }
+GramPlan gram_make_plan(int K, int T, int ldx, int panels, const GroupData g[2], int count_bytes, int num_sms,
+                        const GramColumns& cols);
 struct GramArgs {
     const double* X[2]; const void* C[2];     // X: the (sqrt(w)-scaled when weighted) design
     int count_bytes;
     double* partials;            // [num_partials][BM*BN]
-    const uint16_t* d_pairs;     // [ntiles*BN][2] column offsets (j,l) within a design row
+    const uint16_t* d_pairs;     // [ntiles*BN][2] column offsets (j,l) within a design row (GramColumns::pairs)
+    const int32_t* d_colmap;     // [ntiles*BN] GramColumns::colmap
     double* gram;                // out: [2][panels*BM][Pld]
     int tail_mi = 16;            // 8-slot groups of the batch's last panel that hold valid slots, rounded up to a multiple
                                  // of 4 (16 = full): lets the kernel skip the DMMAs of slot groups that do not exist
@@ -164,7 +182,6 @@ void gram_reduce_launch(const GramPlan& plan, const GramArgs& args, cudaStream_t
 // = number of leading ranks that hold leaves of group g
 void gram_combine_launch(const double* gathered, int world, const int ranks_with_rows[2], int64_t per_group_elems,
                          double* gram, cudaStream_t st);
-std::vector<uint16_t> gram_pair_table(int K, int T, int ntiles);
 int64_t gram_schedule_debug(int K, int panels, int64_t slots_last_panel, const GroupData gd[2], int grid, int64_t* out8, int64_t cap);
 
 // ---- solve.cu ----

@@ -24,7 +24,7 @@ def schedule(K, na, nb, slots, world=1, rank=0, grid=148):
 SHAPES = [  # K, n_a, n_b, slots
     (51, 5_000_000, 5_000_000, 2001),      # config 3
     (21, 500_123, 499_877, 1001),          # config 2
-    (31, 2_500_000, 2_500_000, 1001),      # config 4: 4 wide tiles + a half tile
+    (31, 2_500_000, 2_500_000, 1001),      # config 4: 4 wide tiles + a one-quantum tail tile
     (17, 50_000_000, 50_000_000, 10001),   # config 5
     (6, 5000, 5000, 501), (2, 3, 4, 1), (3, 40, 33, 129), (9, 100_000, 17, 128), (90, 70_000, 70_001, 257),
 ]
@@ -35,13 +35,9 @@ def test_every_unit_once_and_balanced(K, na, nb, slots):
     u = schedule(K, na, nb, slots)
     V = K + 1
     pairs = V * (V + 1) // 2
-    nfull, rem = divmod(pairs, 128)
-    has_half = 0
-    if rem > 64:
-        nfull += 1
-    elif rem > 0:
-        has_half = 1
-    ntiles = nfull + has_half
+    quanta = -(-pairs // 32)                 # column quantum: 32 columns = one DMMA sub-tile per scheduler
+    nfull, tail_q = divmod(quanta, 4)        # tiles of 128 columns + a tail tile of one to three quanta
+    ntiles = nfull + (tail_q > 0)
     panels = -(-slots // 128)
     keys = Counter(map(tuple, u[:, 1:5]))
     assert all(c == 1 for c in keys.values())
@@ -55,12 +51,12 @@ def test_every_unit_once_and_balanced(K, na, nb, slots):
     last = slots - (panels - 1) * 128
     mi = min(16, -(-(-(-last // 8)) // 4) * 4)
     assert set(u[u[:, 2] == panels - 1][:, 6]) == {mi} and (panels == 1 or set(u[u[:, 2] < panels - 1][:, 6]) == {16})
-    assert set(u[u[:, 3] == nfull][:, 7]) <= {1} and set(u[u[:, 3] < nfull][:, 7]) <= {0}
-    # equal shares per cost class (half-width?, tail panel?) across CTAs
+    assert set(u[u[:, 3] == nfull][:, 7]) <= {tail_q} and set(u[u[:, 3] < nfull][:, 7]) <= {0}
+    # equal shares per cost class (tail tile?, tail panel?) across CTAs
     grid = min(148, len(u))
     for half in (0, 1):
         for tail in (0, 1):
-            cls = u[(u[:, 7] == half) & ((u[:, 6] < 16) == bool(tail))]
+            cls = u[((u[:, 7] > 0) == bool(half)) & ((u[:, 6] < 16) == bool(tail))]
             per = np.bincount(cls[:, 0], minlength=grid)
             assert per.max() - per.min() <= 2, (half, tail, per.max(), per.min())     # +-1, plus the class boundary
 

@@ -2,9 +2,10 @@
  * against differently built libobboot.so (LD_LIBRARY_PATH picks the variant; tools/gram_ab.sh builds and runs them).
  *
  *   gcc -O2 -I include tools/gram_ab.c -L oaxaca_blinder_rs_b200/_lib -lobboot -lm -o tools/_ab/gram_ab
- *   LD_LIBRARY_PATH=tools/_ab/<variant> tools/_ab/gram_ab <n> <p> <reps> <runs>
+ *   LD_LIBRARY_PATH=tools/_ab/<variant> tools/_ab/gram_ab <n> <p> <reps> <runs> [<ncat>]
  *
- * Frame: n rows, p continuous predictors (K = p + 1), weights, two groups, 64-bit LCG data.  Prints, per run, the
+ * Frame: n rows, p continuous predictors and ncat four-level categoricals (K = 1 + p + 3 ncat), weights, two groups,
+ * 64-bit LCG data.  Prints, per run, the
  * CUDA-event time of the contraction kernel and of the whole call, the DMMA fraction of the 37.1 TFLOP/s issue peak,
  * and a bit-level checksum of the standard errors (all variants must print the same checksum: the sums are fixed by
  * the summation tree, not by the kernel's schedule). */
@@ -32,6 +33,7 @@ int main(int argc, char** argv) {
     const int p = argc > 2 ? atoi(argv[2]) : 50;
     const int64_t reps = argc > 3 ? atoll(argv[3]) : 2000;
     const int runs = argc > 4 ? atoi(argv[4]) : 3;
+    const int ncat = argc > 5 ? atoi(argv[5]) : 0;
     ob_ctx* ctx = NULL;
     if (ob_ctx_create(0, &ctx) != OB_OK) { fprintf(stderr, "no B200 device: there is no CPU fallback\n"); return 2; }
 
@@ -40,17 +42,21 @@ int main(int argc, char** argv) {
     double* y = malloc(sizeof(double) * (size_t)n);
     double* w = malloc(sizeof(double) * (size_t)n);
     uint8_t* grp = malloc((size_t)n);
+    int32_t** cat = malloc(sizeof(int32_t*) * (size_t)(ncat > 0 ? ncat : 1));
+    int32_t* levels = malloc(sizeof(int32_t) * (size_t)(ncat > 0 ? ncat : 1));
+    for (int q = 0; q < ncat; ++q) { cat[q] = malloc(sizeof(int32_t) * (size_t)n); levels[q] = 4; }
     for (int64_t i = 0; i < n; ++i) {
         grp[i] = lcg_uniform() < 0.5 ? 0 : 1;
         double acc = grp[i] == 0 ? 2.9 : 2.7;
         for (int j = 0; j < p; ++j) { x[j][i] = lcg_uniform() * 2.0 - 1.0 + (grp[i] == 0 ? 0.2 : 0.0); acc += 0.01 * (1 + j % 5) * x[j][i]; }
+        for (int q = 0; q < ncat; ++q) { cat[q][i] = (int32_t)(lcg_uniform() * 4.0) & 3; acc += 0.05 * cat[q][i]; }
         w[i] = 0.5 + 2.5 * lcg_uniform();
         y[i] = acc + (lcg_uniform() - 0.5);
     }
-    ob_frame_view f = {n, p, (const double* const*)x, 0, NULL, NULL, y, w, grp};
+    ob_frame_view f = {n, p, (const double* const*)x, ncat, (const int32_t* const*)cat, levels, y, w, grp};
     ob_design* d = NULL;
     CHECK(ob_design_pack(ctx, &f, &d));
-    const int32_t K = p + 1;
+    const int32_t K = p + 1 + 3 * ncat;
     const int32_t S = ob_num_stats(K, 0, NULL);
     ob_boot_opts o;
     memset(&o, 0, sizeof o);
@@ -65,6 +71,8 @@ int main(int argc, char** argv) {
         CHECK(ob_bootstrap_run(ctx, d, &o, &r));
         uint64_t h = 1469598103934665603ULL;
         for (int j = 0; j < S; ++j) { uint64_t b; memcpy(&b, &r.std_err[j], 8); h = (h ^ b) * 1099511628211ULL; }
+        for (int j = 0; j < S; ++j) { uint64_t b; memcpy(&b, &r.point_stats[j], 8); h = (h ^ b) * 1099511628211ULL; }
+        for (int j = 0; j < S; ++j) { uint64_t b; memcpy(&b, &r.ci_lower[j], 8); h = (h ^ b) * 1099511628211ULL; }
         printf("run %d gram_kernel_ms %.3f total_ms %.3f frac_of_37.1TF %.4f n_ok %lld se_hash %016llx\n", it, r.ms_gram_kernel,
                r.ms_total, flop / (r.ms_gram_kernel * 1e-3) / 37.1e12, (long long)r.n_ok, (unsigned long long)h);
     }
