@@ -838,6 +838,8 @@ def main():
                      "what": "ob_design_update_outcome (new y from pinned host memory, X resident) + bootstrap per step"},
                 "gpu_launches": int(launches),
                 "device_ms_per_step": float(np.mean(total_ms)),
+                "device_step_ms": [round(float(x), 1) for x in total_ms],       # every timed step: library events, whole call
+                "gram_step_ms": [round(float(x), 1) for x in gram_ms],          # ... and its Gram launch
                 "timing": "value: host clock between barrier + cuda synchronize brackets around exactly K steps, max over ranks "
                           "(the library runs on its own stream, so torch.cuda.Event would not see it); device_ms_per_step and "
                           "stage_ms: CUDA events recorded by the library on that stream",

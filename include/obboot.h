@@ -387,11 +387,22 @@ ob_status ob_design_row_shard(const ob_design* d, int64_t* n_a_global, int64_t* 
 ob_status ob_design_redistribute_rows(ob_ctx* ctx, const ob_design* local_slice, ob_design** out);
 
 /* Host-only debugging aid (no device needed): the work-unit schedule of the Gram kernel for a problem shape -- out8
- * receives up to cap rows of (cta, group, panel, column tile, row segment, pipeline stages, 8-slot groups, half-width);
+ * receives up to cap rows of (cta, group, panel, column tile, row segment, pipeline stages, 8-slot groups, quanta of a
+ * tail tile or 0 for a full tile);
  * returns the total number of units or -1 on bad arguments.  The CPU tests use it to check that every
  * (group, panel, tile, segment) is computed exactly once and that the CTAs get equal shares. */
 int64_t ob_debug_gram_schedule(int32_t K, int64_t n_a, int64_t n_b, int64_t slots, int32_t world, int32_t rank, int32_t grid,
                                int64_t* out8, int64_t cap);
+
+/* Host-only debugging aid: the columns the Gram contraction computes for a design with n_cont continuous predictors
+ * and the categorical predictors cat_levels [n_cat] (level counts incl. the base; K must equal 1 + n_cont + sum(m - 1),
+ * else -- and for n_cat = 0 -- nothing is dropped) and T outcome columns: pairs_out [cap][2] = design-row offsets (j, l)
+ * of computed column c, colmap_out [cap] = its index in the row-major upper triangle of [x|y][x|y]^T (-1 = padding).
+ * The products of two different dummies of one categorical are structural zeros of X'WX and are not computed.
+ * tiling_out[3] (may be NULL) = {computed columns, tiles of 128 columns, quanta of 32 columns in the tail tile}.
+ * Returns the table length (tiles x 128) or -1 on bad arguments. */
+int64_t ob_debug_gram_columns(int32_t K, int32_t T, int32_t n_cont, const int32_t* cat_levels, int32_t n_cat,
+                              uint16_t* pairs_out, int32_t* colmap_out, int64_t cap, int32_t* tiling_out);
 
 /* Multiplicity counts of one replicate of the native stream (for the statistical validation
  * tests): counts_out [n] for group g (0 = A, 1 = B) of design d. */

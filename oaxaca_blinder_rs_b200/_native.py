@@ -30,7 +30,7 @@ SYMBOLS = ["ob_abi_version", "ob_device_count", "ob_ctx_create", "ob_ctx_destroy
            "ob_host_register", "ob_host_unregister", "ob_replicate_shard", "ob_design_pack_async", "ob_design_wait",
            "ob_design_redistribute_rows", "ob_design_row_shard", "ob_design_apply_rif_multi", "ob_design_num_outcomes",
            "ob_design_pack_row_shard_async", "ob_design_attach_selection", "ob_design_selection_cols", "ob_num_stats_heckman",
-           "ob_mm_run"]
+           "ob_mm_run", "ob_debug_gram_columns"]
 
 
 class FrameView(C.Structure):

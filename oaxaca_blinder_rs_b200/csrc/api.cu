@@ -2342,8 +2342,22 @@ ob_status ob_reduce_stats(ob_ctx* ctx, const double* rep_stats, const int32_t* r
     });
 }
 
+// Host-only: the columns the Gram contraction computes (gram_columns), for the CPU tests.
+int64_t ob_debug_gram_columns(int32_t K, int32_t T, int32_t n_cont, const int32_t* cat_levels, int32_t n_cat,
+                              uint16_t* pairs_out, int32_t* colmap_out, int64_t cap, int32_t* tiling_out) {
+    if (K < 1 || T < 1 || n_cont < 0 || n_cat < 0 || (n_cat > 0 && !cat_levels) || K + T > 65535) return -1;
+    const GramColumns gc = gram_columns(K, T, n_cont, std::vector<int>(cat_levels, cat_levels + n_cat));
+    const int64_t len = (int64_t)gc.colmap.size();
+    for (int64_t c = 0; c < len && c < cap; ++c) {
+        if (pairs_out) { pairs_out[2 * c] = gc.pairs[2 * (size_t)c]; pairs_out[2 * c + 1] = gc.pairs[2 * (size_t)c + 1]; }
+        if (colmap_out) colmap_out[c] = gc.colmap[(size_t)c];
+    }
+    if (tiling_out) { tiling_out[0] = gc.Pc; tiling_out[1] = gc.nfull; tiling_out[2] = gc.tail_q; }
+    return len;
+}
+
 // Host-only: the unit schedule of the Gram kernel for a problem shape (no device needed; CPU tests).  out8 receives up to
-// cap rows of (cta, group, panel, tile, segment, stages, slot groups, half-width); returns the number of units.
+// cap rows of (cta, group, panel, tile, segment, stages, slot groups, tail quanta); returns the number of units.
 int64_t ob_debug_gram_schedule(int32_t K, int64_t n_a, int64_t n_b, int64_t slots, int32_t world, int32_t rank, int32_t grid,
                                int64_t* out8, int64_t cap) {
     if (K < 1 || n_a < 0 || n_b < 0 || slots < 1 || world < 1 || (world & (world - 1)) || world > MAX_WORLD || rank < 0 ||

@@ -70,3 +70,66 @@ def test_row_shards_tile_the_group():
         for g in (0, 1):
             got = sum(p[(p[:, 1] == g) & (p[:, 2] == 0) & (p[:, 3] == 0)][:, 5].sum() for p in parts)
             assert got == tot[g], (world, g)
+
+
+def columns(K, T, n_cont, cat_levels):
+    from oaxaca_blinder_rs_b200 import _native
+    _native.build()
+    L = _native.lib()
+    lv = np.asarray(cat_levels, dtype=np.int32)
+    lvp = lv.ctypes.data_as(C.POINTER(C.c_int32)) if len(lv) else None
+    L.ob_debug_gram_columns.restype = C.c_int64
+    til = np.zeros(3, dtype=np.int32)
+    n = L.ob_debug_gram_columns(K, T, n_cont, lvp, len(lv), None, None, 0, til.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert n > 0
+    pairs = np.zeros((n, 2), dtype=np.uint16)
+    cmap = np.zeros(n, dtype=np.int32)
+    m = L.ob_debug_gram_columns(K, T, n_cont, lvp, len(lv), pairs.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                cmap.ctypes.data_as(C.POINTER(C.c_int32)), n, None)
+    assert m == n
+    return pairs, cmap, til
+
+
+def upper_triangle_index(K, T, j, l):
+    """Row-major upper triangle of [x|y][x|y]^T as the solve reads it (internal.h: pair_base)."""
+    return j * (K + T) - j * (j - 1) // 2 + (l - j)
+
+
+@pytest.mark.parametrize("K,T,n_cont,levels", [
+    (51, 1, 44, (4, 4)),          # config 3: six structural zeros -> 1372 columns = 10 tiles + 3 quanta
+    (51, 1, 50, ()),              # no categoricals: nothing dropped, 11 tiles
+    (31, 1, 30, ()),              # config 4: 4 tiles + 1 quantum
+    (31, 3, 30, ()),              # config 4, three RIF outcomes in one pass
+    (17, 1, 16, ()),              # config 5: 1 tile + 2 quanta
+    (6, 1, 2, (4,)), (12, 2, 3, (3, 2, 6)), (9, 1, 8, ()), (2, 1, 1, ()), (5, 1, 1, (4,)),
+    (8, 1, 3, (4,)),              # K does not match 1 + n_cont + dummies: the structure is ignored
+])
+def test_gram_columns_cover_the_upper_triangle(K, T, n_cont, levels):
+    pairs, cmap, til = columns(K, T, n_cont, levels)
+    known = 1 + n_cont + sum(m - 1 for m in levels) == K
+    block = {}
+    if known:
+        c = 1 + n_cont
+        for q, m in enumerate(levels):
+            for _ in range(m - 1):
+                block[c] = q
+                c += 1
+    zeros = {(j, l) for j in block for l in block if j < l and block[j] == block[l]}
+    P1 = K * (K + 1) // 2 + K * T + 1
+    expect = {}
+    for j in range(K):
+        for l in range(j, K + T):
+            if (j, l) not in zeros:
+                expect[upper_triangle_index(K, T, j, l)] = (j, l)
+    expect[P1 - 1] = (K, K)
+    real = cmap >= 0
+    assert int(real.sum()) == len(expect) == til[0] == P1 - len(zeros)
+    assert len(set(cmap[real].tolist())) == int(real.sum())                      # every cell at most once
+    for c in np.nonzero(real)[0]:
+        assert expect[int(cmap[c])] == (int(pairs[c, 0]), int(pairs[c, 1])), c     # the product feeds the right cell
+    assert real[:til[0]].all() and not real[til[0]:].any()                       # computed columns first, then padding
+    assert (pairs[~real] == K).all()                                             # padding = harmless (y_0, y_0)
+    quanta = -(-int(til[0]) // 32)
+    assert (til[1], til[2]) == divmod(quanta, 4) and len(cmap) == (til[1] + (til[2] > 0)) * 128
+    if (K, levels) == (51, (4, 4)):
+        assert tuple(til) == (1372, 10, 3)
