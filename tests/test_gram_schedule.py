@@ -79,6 +79,8 @@ def columns(K, T, n_cont, cat_levels):
     lv = np.asarray(cat_levels, dtype=np.int32)
     lvp = lv.ctypes.data_as(C.POINTER(C.c_int32)) if len(lv) else None
     L.ob_debug_gram_columns.restype = C.c_int64
+    L.ob_debug_gram_columns.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_uint16),
+                                        C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int32)]
     til = np.zeros(3, dtype=np.int32)
     n = L.ob_debug_gram_columns(K, T, n_cont, lvp, len(lv), None, None, 0, til.ctypes.data_as(C.POINTER(C.c_int32)))
     assert n > 0
